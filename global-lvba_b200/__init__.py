@@ -1,0 +1,320 @@
+"""global-lvba_b200 — host-side mirror (Python/ctypes) of the C ABI in include/lvba_b200.h.
+
+The product is `liblvba_b200.so` (CUDA, sm_100a) built from `csrc/`; this module only
+binds it.  It is what tests/ and bench.py use to drive the library exactly as a C++
+caller would (plain pointers and sizes).  There is NO CPU fallback here: if the shared
+library is missing, or no CUDA device is present, every compute call raises.
+
+The directory name contains a hyphen (it mirrors the reference repo name), so import it
+through `__graft_entry__.load_package()` / `tests/conftest.py`, which register it as the
+module `global_lvba_b200`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "liblvba_b200.so"
+_lib = None
+
+# names every build of the library must export (kept in sync with include/lvba_b200.h;
+# tests/test_abi.py cross-checks this list against the header)
+EXPORTS = [
+    "lvba_version", "lvba_device_count", "lvba_status_string", "lvba_last_error",
+    "lvba_lidar_default_opts", "lvba_visual_default_opts",
+    "lvba_lidar_lm", "lvba_lidar_create", "lvba_lidar_destroy", "lvba_lidar_set_poses",
+    "lvba_lidar_get_poses", "lvba_lidar_build", "lvba_lidar_residual", "lvba_lidar_solve",
+    "lvba_lidar_structure", "lvba_lidar_get_system", "lvba_lidar_reset_lm", "lvba_lidar_iterate",
+    "lvba_lidar_counts",
+    "lvba_visual_lm", "lvba_visual_create", "lvba_visual_destroy", "lvba_visual_set_state",
+    "lvba_visual_get_state", "lvba_visual_cost", "lvba_visual_step", "lvba_visual_structure",
+    "lvba_visual_get_system", "lvba_visual_reset_lm", "lvba_visual_iterate", "lvba_visual_counts",
+    "lvba_comm_unique_id", "lvba_comm_init", "lvba_comm_destroy", "lvba_comm_info", "lvba_shard_owner",
+]
+
+
+class LvbaError(RuntimeError):
+    def __init__(self, status, detail):
+        super().__init__(f"lvba status {status}: {detail}")
+        self.status = status
+
+
+class LidarOpts(C.Structure):
+    _fields_ = [("u0", C.c_double), ("v0", C.c_double), ("max_iter", C.c_int32), ("rel_tol", C.c_double),
+                ("device", C.c_int32), ("verbose", C.c_int32)]
+
+
+class VisualOpts(C.Structure):
+    _fields_ = [("max_iter", C.c_int32), ("initial_radius", C.c_double), ("max_radius", C.c_double),
+                ("min_radius", C.c_double), ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
+                ("min_relative_decrease", C.c_double), ("function_tolerance", C.c_double),
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+                ("jacobi_scaling", C.c_int32), ("device", C.c_int32), ("verbose", C.c_int32)]
+
+
+class Summary(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("accepted", C.c_int32), ("hessian_builds", C.c_int32),
+                ("termination", C.c_int32), ("cost_first", C.c_double), ("cost_last", C.c_double),
+                ("damping_last", C.c_double), ("ms_total", C.c_double), ("ms_setup", C.c_double),
+                ("ms_build", C.c_double), ("ms_solve", C.c_double), ("ms_residual", C.c_double),
+                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def build_library(force=False, quiet=True):
+    """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if LIB_PATH.exists() and not force:
+        src_m = max(p.stat().st_mtime for p in list((_HERE / "csrc").glob("*.cu*")) + [(_HERE.parent / "include" / "lvba_b200.h")])
+        if LIB_PATH.stat().st_mtime >= src_m:
+            return LIB_PATH
+    r = subprocess.run(["make", "-C", str(_HERE / "csrc")], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building liblvba_b200.so failed:\n" + r.stdout + r.stderr)
+    if not quiet:
+        print(r.stdout)
+    return LIB_PATH
+
+
+def load_library():
+    """dlopen liblvba_b200.so; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise LvbaError(-2, f"{LIB_PATH} not built: run __graft_entry__.build(); there is no CPU fallback")
+    lib = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+    lib.lvba_status_string.restype = C.c_char_p
+    lib.lvba_last_error.restype = C.c_char_p
+    lib.lvba_shard_owner.restype = C.c_int32
+    _lib = lib
+    return lib
+
+
+def _chk(rc):
+    if rc != 0:
+        lib = load_library()
+        raise LvbaError(rc, (lib.lvba_last_error() or b"").decode() or lib.lvba_status_string(rc).decode())
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def device_count():
+    return int(load_library().lvba_device_count())
+
+
+def shard_owner(min_pose, n_rows, n_ranks):
+    return int(load_library().lvba_shard_owner(int(min_pose), int(n_rows), int(n_ranks)))
+
+
+def lidar_default_opts():
+    o = LidarOpts()
+    load_library().lvba_lidar_default_opts(C.byref(o))
+    return o
+
+
+def visual_default_opts():
+    o = VisualOpts()
+    load_library().lvba_visual_default_opts(C.byref(o))
+    return o
+
+
+# ------------------------------------------------------------------ B1: LiDAR
+def lidar_lm(vox_ptr, pose_idx, clusters, poses, opts=None):
+    """One-shot drop-in for BALM2::damping_iter (bavoxel.hpp:662).  Returns (poses, summary dict)."""
+    lib = load_library()
+    vp = np.ascontiguousarray(vox_ptr, np.int64); pi = np.ascontiguousarray(pose_idx, np.int32)
+    cl = _f64(clusters); ps = _f64(poses).copy()
+    s = Summary()
+    _chk(lib.lvba_lidar_lm(C.c_int32(ps.shape[0]), C.c_int64(len(vp) - 1), _p(vp, C.c_int64), _p(pi, C.c_int32),
+                           _p(cl, C.c_double), _p(ps, C.c_double), C.byref(opts) if opts is not None else None,
+                           C.byref(s)))
+    return ps, s.as_dict()
+
+
+class LidarProblem:
+    """Device-resident handle (lvba_lidar_create ...)."""
+
+    def __init__(self, vox_ptr, pose_idx, clusters, poses, device=-1):
+        lib = load_library()
+        self._lib = lib
+        self.vp = np.ascontiguousarray(vox_ptr, np.int64); self.pi = np.ascontiguousarray(pose_idx, np.int32)
+        cl = _f64(clusters); ps = _f64(poses)
+        self.W = ps.shape[0]; self.V = len(self.vp) - 1
+        self._h = C.c_void_p()
+        _chk(lib.lvba_lidar_create(C.c_int32(self.W), C.c_int64(self.V), _p(self.vp, C.c_int64), _p(self.pi, C.c_int32),
+                                   _p(cl, C.c_double), _p(ps, C.c_double), C.c_int32(device), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.lvba_lidar_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_poses(self, poses):
+        ps = _f64(poses); _chk(self._lib.lvba_lidar_set_poses(self._h, _p(ps, C.c_double)))
+
+    def get_poses(self):
+        out = np.empty((self.W, 12)); _chk(self._lib.lvba_lidar_get_poses(self._h, _p(out, C.c_double))); return out
+
+    def build(self):
+        r = C.c_double(); _chk(self._lib.lvba_lidar_build(self._h, C.byref(r))); return r.value
+
+    def residual(self, poses=None):
+        r = C.c_double()
+        if poses is None:
+            _chk(self._lib.lvba_lidar_residual(self._h, None, C.byref(r)))
+        else:
+            ps = _f64(poses); _chk(self._lib.lvba_lidar_residual(self._h, _p(ps, C.c_double), C.byref(r)))
+        return r.value
+
+    def solve(self, u):
+        dx = np.empty(self.W * 6); _chk(self._lib.lvba_lidar_solve(self._h, C.c_double(u), _p(dx, C.c_double))); return dx
+
+    def structure(self):
+        nb = C.c_int64(); _chk(self._lib.lvba_lidar_structure(self._h, C.byref(nb), None, None))
+        br = np.empty(nb.value, np.int32); bc = np.empty(nb.value, np.int32)
+        _chk(self._lib.lvba_lidar_structure(self._h, C.byref(nb), _p(br, C.c_int32), _p(bc, C.c_int32)))
+        return br, bc
+
+    def get_system(self):
+        br, bc = self.structure()
+        g = np.empty((self.W, 6)); blocks = np.empty((len(br), 6, 6))
+        _chk(self._lib.lvba_lidar_get_system(self._h, _p(g, C.c_double), _p(blocks, C.c_double)))
+        return g, br, bc, blocks
+
+    def reset_lm(self, opts=None):
+        _chk(self._lib.lvba_lidar_reset_lm(self._h, C.byref(opts) if opts is not None else None))
+
+    def iterate(self, n):
+        s = Summary(); _chk(self._lib.lvba_lidar_iterate(self._h, C.c_int32(n), C.byref(s))); return s.as_dict()
+
+    def counts(self, nonzero=True):
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _chk(self._lib.lvba_lidar_counts(self._h, C.byref(a), C.byref(b), C.byref(c) if nonzero else None, C.byref(d)))
+        return dict(nnz=a.value, n_blocks_env=b.value, n_blocks_nonzero=c.value if nonzero else None, n_pairs=d.value)
+
+
+def env_blocks_to_dense(br, bc, blocks, n):
+    """Expand lower-envelope 6x6 blocks into a dense symmetric matrix (test helper)."""
+    H = np.zeros((6 * n, 6 * n))
+    for r, c, b in zip(br, bc, blocks):
+        H[6 * r:6 * r + 6, 6 * c:6 * c + 6] = b
+        if r != c:
+            H[6 * c:6 * c + 6, 6 * r:6 * r + 6] = b.T
+    return H
+
+
+# ------------------------------------------------------------------ B2: visual
+def visual_lm(q, t, X, plane_nd, obs_ptr, obs_cam, obs_uv, intr, sigma_px, sigma_plane, fixed_cam=0, opts=None):
+    """One-shot drop-in for the Ceres block of optimizeCameraPoses (lvba_system.cpp:1571-1656)."""
+    lib = load_library()
+    q = _f64(q).copy(); t = _f64(t).copy(); X = _f64(X).copy(); pl = _f64(plane_nd)
+    op = np.ascontiguousarray(obs_ptr, np.int64); oc = np.ascontiguousarray(obs_cam, np.int32)
+    uv = np.ascontiguousarray(obs_uv, np.float32); it = _f64(intr)
+    s = Summary()
+    _chk(lib.lvba_visual_lm(C.c_int32(q.shape[0]), C.c_int64(X.shape[0]), _p(q, C.c_double), _p(t, C.c_double),
+                            _p(X, C.c_double), _p(pl, C.c_double), _p(op, C.c_int64), _p(oc, C.c_int32),
+                            _p(uv, C.c_float), _p(it, C.c_double), C.c_double(sigma_px), C.c_double(sigma_plane),
+                            C.c_int32(fixed_cam), C.byref(opts) if opts is not None else None, C.byref(s)))
+    return q, t, X, s.as_dict()
+
+
+class VisualProblem:
+    def __init__(self, q, t, X, plane_nd, obs_ptr, obs_cam, obs_uv, intr, sigma_px, sigma_plane, fixed_cam=0, device=-1):
+        lib = load_library()
+        self._lib = lib
+        q = _f64(q); t = _f64(t); X = _f64(X); pl = _f64(plane_nd)
+        op = np.ascontiguousarray(obs_ptr, np.int64); oc = np.ascontiguousarray(obs_cam, np.int32)
+        uv = np.ascontiguousarray(obs_uv, np.float32); it = _f64(intr)
+        self.M, self.T = q.shape[0], X.shape[0]
+        self._h = C.c_void_p()
+        _chk(lib.lvba_visual_create(C.c_int32(self.M), C.c_int64(self.T), _p(q, C.c_double), _p(t, C.c_double),
+                                    _p(X, C.c_double), _p(pl, C.c_double), _p(op, C.c_int64), _p(oc, C.c_int32),
+                                    _p(uv, C.c_float), _p(it, C.c_double), C.c_double(sigma_px),
+                                    C.c_double(sigma_plane), C.c_int32(fixed_cam), C.c_int32(device), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.lvba_visual_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, q, t, X):
+        q = _f64(q); t = _f64(t); X = _f64(X)
+        _chk(self._lib.lvba_visual_set_state(self._h, _p(q, C.c_double), _p(t, C.c_double), _p(X, C.c_double)))
+
+    def get_state(self):
+        q = np.empty((self.M, 4)); t = np.empty((self.M, 3)); X = np.empty((self.T, 3))
+        _chk(self._lib.lvba_visual_get_state(self._h, _p(q, C.c_double), _p(t, C.c_double), _p(X, C.c_double)))
+        return q, t, X
+
+    def cost(self):
+        c = C.c_double(); _chk(self._lib.lvba_visual_cost(self._h, C.byref(c))); return c.value
+
+    def step(self, radius, jacobi_scaling=True, recompute_scale=True):
+        cs = np.empty((self.M, 6)); ps = np.empty((self.T, 3)); mc = C.c_double(); c = C.c_double()
+        _chk(self._lib.lvba_visual_step(self._h, C.c_double(radius), C.c_int32(int(jacobi_scaling)),
+                                        C.c_int32(int(recompute_scale)), _p(cs, C.c_double), _p(ps, C.c_double),
+                                        C.byref(mc), C.byref(c)))
+        return cs, ps, mc.value, c.value
+
+    def structure(self):
+        na = C.c_int32(); nb = C.c_int64()
+        _chk(self._lib.lvba_visual_structure(self._h, C.byref(na), None, C.byref(nb), None, None))
+        cam = np.empty(na.value, np.int32); br = np.empty(nb.value, np.int32); bc = np.empty(nb.value, np.int32)
+        _chk(self._lib.lvba_visual_structure(self._h, C.byref(na), _p(cam, C.c_int32), C.byref(nb), _p(br, C.c_int32), _p(bc, C.c_int32)))
+        return cam, br, bc
+
+    def get_system(self):
+        cam, br, bc = self.structure()
+        rhs = np.empty((len(cam), 6)); blocks = np.empty((len(br), 6, 6))
+        _chk(self._lib.lvba_visual_get_system(self._h, _p(rhs, C.c_double), _p(blocks, C.c_double)))
+        return cam, rhs, br, bc, blocks
+
+    def reset_lm(self, opts=None):
+        _chk(self._lib.lvba_visual_reset_lm(self._h, C.byref(opts) if opts is not None else None))
+
+    def iterate(self, n):
+        s = Summary(); _chk(self._lib.lvba_visual_iterate(self._h, C.c_int32(n), C.byref(s))); return s.as_dict()
+
+    def counts(self):
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _chk(self._lib.lvba_visual_counts(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(nnz_valid=a.value, n_valid_tracks=b.value, n_blocks_env=c.value, n_pairs=d.value)
+
+
+# ------------------------------------------------------------------ multi-GPU
+def comm_unique_id():
+    buf = (C.c_ubyte * 128)(); _chk(load_library().lvba_comm_unique_id(buf)); return bytes(buf)
+
+
+def comm_init(n_ranks, rank, uid, device):
+    buf = (C.c_ubyte * 128).from_buffer_copy(uid) if uid is not None else None
+    _chk(load_library().lvba_comm_init(C.c_int32(n_ranks), C.c_int32(rank), buf, C.c_int32(device)))
+
+
+def comm_destroy():
+    _chk(load_library().lvba_comm_destroy())

@@ -1,0 +1,167 @@
+// common.cuh — device-side small FP64 linear algebra shared by the LVBA kernels (sm_100a).
+// All 3x3 / 6x6 products are register-resident scalar FP64 (DFMA); no tensor cores (north star).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define LVBA_DEV __device__ __forceinline__
+
+namespace lvba {
+
+// ---------------------------------------------------------------- vectorised global loads
+LVBA_DEV double2 ldg2(const double2* p) { return __ldg(p); }
+
+// ---------------------------------------------------------------- 3x3 helpers (row-major double[9])
+LVBA_DEV void mat3_mul(const double* A, const double* B, double* C) {   // C = A B
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+LVBA_DEV void mat3_mul_bt(const double* A, const double* B, double* C) {  // C = A B^T
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      C[3 * i + j] = A[3 * i] * B[3 * j] + A[3 * i + 1] * B[3 * j + 1] + A[3 * i + 2] * B[3 * j + 2];
+}
+LVBA_DEV void mat3_vec(const double* A, const double* x, double* y) {    // y = A x
+#pragma unroll
+  for (int i = 0; i < 3; ++i) y[i] = A[3 * i] * x[0] + A[3 * i + 1] * x[1] + A[3 * i + 2] * x[2];
+}
+LVBA_DEV void mat3t_vec(const double* A, const double* x, double* y) {   // y = A^T x
+#pragma unroll
+  for (int i = 0; i < 3; ++i) y[i] = A[i] * x[0] + A[3 + i] * x[1] + A[6 + i] * x[2];
+}
+LVBA_DEV void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+LVBA_DEV double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+// hat(v): reference include/BALM/tools.hpp:105-112
+LVBA_DEV void hat3(const double* v, double* H) {
+  H[0] = 0.0;   H[1] = -v[2]; H[2] = v[1];
+  H[3] = v[2];  H[4] = 0.0;   H[5] = -v[0];
+  H[6] = -v[1]; H[7] = v[0];  H[8] = 0.0;
+}
+// A * hat(w) without forming hat:  (A hat(w))_{:,0} = A_{:,1} w2 - A_{:,2} w1, ...
+LVBA_DEV void mat3_mul_hat(const double* A, const double* w, double* C) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double a0 = A[3 * i], a1 = A[3 * i + 1], a2 = A[3 * i + 2];
+    C[3 * i + 0] = a1 * w[2] - a2 * w[1];
+    C[3 * i + 1] = a2 * w[0] - a0 * w[2];
+    C[3 * i + 2] = a0 * w[1] - a1 * w[0];
+  }
+}
+// hat(w) * A : row i of result = w x (columns)  ->  (hat(w) A)_{0,:} = -w2 A_{1,:} + w1 A_{2,:}
+LVBA_DEV void hat_mul_mat3(const double* w, const double* A, double* C) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double a0 = A[j], a1 = A[3 + j], a2 = A[6 + j];
+    C[j] = -w[2] * a1 + w[1] * a2;
+    C[3 + j] = w[2] * a0 - w[0] * a2;
+    C[6 + j] = -w[1] * a0 + w[0] * a1;
+  }
+}
+
+// ---------------------------------------------------------------- symmetric 3x3 eigen solver
+// Cyclic Jacobi in FP64; replaces Eigen::SelfAdjointEigenSolver<Matrix3d> (bavoxel.hpp:98,198):
+// eigenvalues ascending, eigenvectors as columns U[:,k] stored as u[k][0..2]. Eigenvector sign
+// is irrelevant for the path (every use is even in u — SURVEY.md Q6).
+template <bool kVectors>
+LVBA_DEV void eig3_sym(double a00, double a01, double a02, double a11, double a12, double a22,
+                       double lam[3], double u[3][3]) {
+  double v[3][3];
+  if (kVectors) {
+    v[0][0] = 1; v[0][1] = 0; v[0][2] = 0;
+    v[1][0] = 0; v[1][1] = 1; v[1][2] = 0;
+    v[2][0] = 0; v[2][1] = 0; v[2][2] = 1;
+  }
+#define LVBA_JROT(app, aqq, apq, apr, aqr, P, Q)                                        \
+  if (fabs(apq) > 1e-22 * (fabs(app) + fabs(aqq)) && apq != 0.0) {                      \
+    const double theta = (aqq - app) / (2.0 * apq);                                     \
+    const double tt = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0)); \
+    const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;                             \
+    app -= tt * apq; aqq += tt * apq; apq = 0.0;                                        \
+    const double t1 = c * apr - s * aqr, t2 = s * apr + c * aqr;                        \
+    apr = t1; aqr = t2;                                                                 \
+    if (kVectors) {                                                                     \
+      _Pragma("unroll") for (int k = 0; k < 3; ++k) {                                   \
+        const double vp = v[k][P], vq = v[k][Q];                                        \
+        v[k][P] = c * vp - s * vq; v[k][Q] = s * vp + c * vq;                           \
+      }                                                                                 \
+    }                                                                                   \
+    ++rot;                                                                              \
+  }
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    int rot = 0;
+    LVBA_JROT(a00, a11, a01, a02, a12, 0, 1)
+    LVBA_JROT(a00, a22, a02, a01, a12, 0, 2)
+    LVBA_JROT(a11, a22, a12, a01, a02, 1, 2)
+    if (rot == 0) break;
+  }
+#undef LVBA_JROT
+  // sort ascending (3-element network)
+  double l0 = a00, l1 = a11, l2 = a22;
+  int i0 = 0, i1 = 1, i2 = 2;
+  if (l0 > l1) { double t = l0; l0 = l1; l1 = t; int k = i0; i0 = i1; i1 = k; }
+  if (l1 > l2) { double t = l1; l1 = l2; l2 = t; int k = i1; i1 = i2; i2 = k; }
+  if (l0 > l1) { double t = l0; l0 = l1; l1 = t; int k = i0; i0 = i1; i1 = k; }
+  lam[0] = l0; lam[1] = l1; lam[2] = l2;
+  if (kVectors) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      // dynamic column select without local-memory indexing
+      u[0][k] = (i0 == 0) ? v[k][0] : (i0 == 1) ? v[k][1] : v[k][2];
+      u[1][k] = (i1 == 0) ? v[k][0] : (i1 == 1) ? v[k][1] : v[k][2];
+      u[2][k] = (i2 == 0) ? v[k][0] : (i2 == 1) ? v[k][1] : v[k][2];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- Rodrigues, reference tools.hpp:62-77
+LVBA_DEV void so3_exp(const double* w, double* R) {
+  const double th = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  if (th >= 1e-11) {
+    const double a[3] = {w[0] / th, w[1] / th, w[2] / th};
+    double s, c;
+    sincos(th, &s, &c);
+    double K[9], KK[9];
+    hat3(a, K);
+    mat3_mul(K, K, KK);
+    const double oc = 1.0 - c;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = s * K[i] + oc * KK[i];
+    R[0] += 1.0; R[4] += 1.0; R[8] += 1.0;
+  } else {
+    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+  }
+}
+
+// ---------------------------------------------------------------- block reductions
+LVBA_DEV double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// deterministic block sum; `red` is >= 32 doubles of shared memory; result valid in thread 0
+template <int kThreads>
+LVBA_DEV double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = (lane < kThreads / 32) ? red[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+}  // namespace lvba

@@ -1,0 +1,208 @@
+// envelope.cuh — block-envelope (skyline) storage of the symmetric 6x6-block pose system and its
+// LDL^T solve on the device.
+//
+// Replaces, for hot path A, the dense->triplet->Eigen::SimplicialLDLT sequence of
+// BALM2::damping_iter (reference include/BALM/bavoxel.hpp:692-710; SimplicialLDLT reads the lower
+// triangle only — SURVEY.md Q4 — and performs LDL^T without pivoting, which is required because the
+// BALM2 Newton Hessian is indefinite — Q5), and for hot path B the DENSE_SCHUR Cholesky of the reduced
+// camera system inside ceres::Solve (src/lvba_system.cpp:1574,1643).
+//
+// Storage: lower block triangle by rows.  Row r keeps the 6x6 blocks of columns first[r]..r
+// contiguously: block (r,c) lives at (row_start[r] + c - first[r]) * 36, row-major, element [a][b] =
+// M[6r+a, 6c+b].  first[] is made monotone non-decreasing on the host so that the row set below a
+// pivot column k is the contiguous range k+1..last[k]; all LDL^T fill stays inside the envelope.
+#pragma once
+#include "common.cuh"
+
+namespace lvba {
+
+struct EnvView {
+  int n;                       // block rows
+  const int* first;            // [n]
+  const long long* row_start;  // [n+1] in blocks
+  const int* last;             // [n]   last[k] = max row i with first[i] <= k
+  long long nblocks;
+};
+
+LVBA_DEV long long env_block(const EnvView& e, int r, int c) { return e.row_start[r] + (c - e.first[r]); }
+
+constexpr int kEnvMaxCol = 320;     // max rows below one pivot column handled by the factor kernel
+constexpr int kFactorThreads = 1024;
+
+// L <- H + diag(dadd)   (dadd: [6n] added on the scalar diagonal).  Grid-stride over doubles.
+__global__ void env_copy_damped_kernel(EnvView e, const double* __restrict__ H, const double* __restrict__ dadd,
+                                       double* __restrict__ L) {
+  const long long total = e.nblocks * 36;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    L[i] = H[i];
+}
+__global__ void env_add_diag_kernel(EnvView e, const double* __restrict__ dadd, double* __restrict__ L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 6 * e.n) {
+    const int r = i / 6, a = i % 6;
+    L[env_block(e, r, r) * 36 + a * 7] += dadd[i];
+  }
+}
+// diag[6r+a] = H[(r,r)][a][a]
+__global__ void env_get_diag_kernel(EnvView e, const double* __restrict__ H, double* __restrict__ diag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 6 * e.n) {
+    const int r = i / 6, a = i % 6;
+    diag[i] = H[env_block(e, r, r) * 36 + a * 7];
+  }
+}
+
+// decode lower-triangular linear index t -> (i, j), j <= i
+LVBA_DEV void tri_decode(int t, int& i, int& j) {
+  int ii = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((ii + 1) * (ii + 2) / 2 <= t) ++ii;
+  while (ii * (ii + 1) / 2 > t) --ii;
+  i = ii;
+  j = t - ii * (ii + 1) / 2;
+}
+
+// Right-looking block LDL^T, in place on L (which enters holding H + damping), with the forward
+// substitution of the right-hand side fused in.  One CTA walks the pivot columns in order; the
+// parallelism is inside one column step (<= n(n+1)/2 trailing 6x6 blocks, n = last[k]-k).
+//   after return:  block (i,k), i>k  holds  L_ik = A_ik D_k^-1
+//                  dinv[k] (36)      holds  D_k^-1   (D_k = Schur-updated diagonal block)
+//                  z[6k..]           holds  (L^-1 b)_k
+// status[0] = 1 if a non-finite pivot inverse appeared.
+__global__ void __launch_bounds__(kFactorThreads, 1)
+env_factor_kernel(EnvView e, double* __restrict__ L, double* __restrict__ dinv, double* __restrict__ z,
+                  int* __restrict__ status) {
+  extern __shared__ double smem[];
+  double* sT = smem;                       // [kEnvMaxCol][36]  A_ik before scaling
+  double* sL = sT + kEnvMaxCol * 36;       // [kEnvMaxCol][36]  L_ik = A_ik D^-1
+  double* sK = sL + kEnvMaxCol * 36;       // [36] D_k^-1
+  double* sZ = sK + 36;                    // [6]  z_k
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int bad = 0;
+
+  for (int k = 0; k < e.n; ++k) {
+    const int n = e.last[k] - k;           // rows k+1 .. k+n below the pivot
+    // ---- phase 1: stage the pivot block (lower triangle mirrored, as SimplicialLDLT reads it) and
+    //      column k into shared memory
+    if (tid < 36) {
+      const long long bk = env_block(e, k, k) * 36;
+      const int r = tid / 6, c = tid % 6;
+      sK[tid] = (r >= c) ? L[bk + r * 6 + c] : L[bk + c * 6 + r];
+    }
+    for (int idx = tid; idx < n * 36; idx += kFactorThreads) {
+      const int i = idx / 36, el = idx % 36;
+      sT[idx] = L[env_block(e, k + 1 + i, k) * 36 + el];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // D_k^-1 by in-place Gauss-Jordan WITHOUT pivoting (same pivots d_p as the scalar LDL^T the
+      // reference runs): one warp, 36 elements over 32 lanes with a second slot on lanes 0..3.
+      const int e0 = lane, e1 = 32 + lane;           // e1 valid for lane < 4
+      const int r0 = e0 / 6, c0 = e0 % 6, r1 = (e1 < 36) ? e1 / 6 : 0, c1 = (e1 < 36) ? e1 % 6 : 0;
+#pragma unroll
+      for (int p = 0; p < 6; ++p) {
+        const double piv = sK[p * 7];
+        const double ip = 1.0 / piv;
+        const double x0 = sK[e0], xr0 = sK[r0 * 6 + p], xc0 = sK[p * 6 + c0];
+        const double x1 = (e1 < 36) ? sK[e1] : 0.0, xr1 = sK[r1 * 6 + p], xc1 = sK[p * 6 + c1];
+        __syncwarp();
+        double n0, n1;
+        if (r0 == p && c0 == p) n0 = ip; else if (r0 == p) n0 = xc0 * ip; else if (c0 == p) n0 = -xr0 * ip; else n0 = x0 - xr0 * xc0 * ip;
+        if (r1 == p && c1 == p) n1 = ip; else if (r1 == p) n1 = xc1 * ip; else if (c1 == p) n1 = -xr1 * ip; else n1 = x1 - xr1 * xc1 * ip;
+        sK[e0] = n0;
+        if (e1 < 36) sK[e1] = n1;
+        __syncwarp();
+      }
+      double chk = sK[lane] + ((lane < 4) ? sK[32 + lane] : 0.0);
+      if (!isfinite(chk)) bad = 1;
+      dinv[(long long)k * 36 + lane] = sK[lane];
+      if (lane < 4) dinv[(long long)k * 36 + 32 + lane] = sK[32 + lane];
+    }
+    if (tid >= 32 && tid < 38) sZ[tid - 32] = z[6 * k + (tid - 32)];
+    __syncthreads();
+    // ---- phase 2: L_ik = A_ik D^-1, written to smem and back to global
+    for (int idx = tid; idx < n * 36; idx += kFactorThreads) {
+      const int i = idx / 36, el = idx % 36, a = el / 6, b = el % 6;
+      const double* t = sT + i * 36 + a * 6;
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s += t[c] * sK[c * 6 + b];
+      sL[idx] = s;
+      L[env_block(e, k + 1 + i, k) * 36 + el] = s;
+    }
+    __syncthreads();
+    // ---- phase 3: trailing update A_ij -= L_ik A_jk^T for k < j <= i <= k+n; half a block (3 rows)
+    //      per thread.  Fused forward substitution: z_i -= L_ik z_k.
+    const int nhalf = n * (n + 1);            // (n(n+1)/2 blocks) * 2 halves
+    for (int h = tid; h < nhalf; h += kFactorThreads) {
+      int i, j;
+      tri_decode(h >> 1, i, j);
+      const int a0 = (h & 1) * 3;
+      const double* li = sL + i * 36 + a0 * 6;
+      const double* tj = sT + j * 36;
+      double* dst = L + env_block(e, k + 1 + i, k + 1 + j) * 36 + a0 * 6;
+      double acc[18];
+#pragma unroll
+      for (int q = 0; q < 18; ++q) acc[q] = dst[q];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+          double s = 0.0;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) s += li[a * 6 + c] * tj[b * 6 + c];
+          acc[a * 6 + b] -= s;
+        }
+#pragma unroll
+      for (int q = 0; q < 18; ++q) dst[q] = acc[q];
+    }
+    for (int idx = tid; idx < n * 6; idx += kFactorThreads) {
+      const int i = idx / 6, a = idx % 6;
+      const double* li = sL + i * 36 + a * 6;
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s += li[c] * sZ[c];
+      z[6 * (k + 1 + i) + a] -= s;
+    }
+    __syncthreads();
+  }
+  if (bad) status[0] = 1;
+}
+
+// x = L^-T D^-1 z  (z from env_factor_kernel).  One warp walks the columns backwards; lanes split
+// the rows below the pivot, partial 6-vectors are shuffle-reduced.
+__global__ void __launch_bounds__(32, 1)
+env_backsolve_kernel(EnvView e, const double* __restrict__ L, const double* __restrict__ dinv,
+                     const double* __restrict__ z, double* __restrict__ x) {
+  const int lane = threadIdx.x;
+  for (int k = e.n - 1; k >= 0; --k) {
+    const int n = e.last[k] - k;
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = lane; i < n; i += 32) {
+      const double* b = L + env_block(e, k + 1 + i, k) * 36;
+      const double* xi = x + 6 * (k + 1 + i);
+      double xv[6];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) xv[a] = xi[a];
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s[c] += b[a * 6 + c] * xv[a];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s[c] = warp_sum(s[c]);
+    if (lane < 6) {
+      const double* K = dinv + (long long)k * 36 + lane * 6;
+      double w = 0.0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) w += K[c] * z[6 * k + c];
+      // select s[lane] without dynamic register indexing
+      double sl = (lane == 0) ? s[0] : (lane == 1) ? s[1] : (lane == 2) ? s[2] : (lane == 3) ? s[3] : (lane == 4) ? s[4] : s[5];
+      x[6 * k + lane] = w - sl;
+    }
+    __syncwarp();
+    __threadfence_block();
+  }
+}
+
+}  // namespace lvba

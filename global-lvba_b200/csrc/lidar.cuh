@@ -1,0 +1,390 @@
+// lidar.cuh — hot path A kernels: BALM2 voxel plane-factor gradient / Hessian accumulation and the
+// residual-only pass.  Restates (in a different, batch-flattened schedule) the arithmetic of
+//   VOX_HESS::acc_evaluate2            reference include/BALM/bavoxel.hpp:68-174
+//   VOX_HESS::evaluate_only_residual   reference include/BALM/bavoxel.hpp:176-203
+//   PointCluster::transform            reference include/BALM/tools.hpp:450-456
+//
+// Work decomposition (B200-first, not the reference's 16 std::threads over dense W-slot vectors):
+//   * the non-empty (voxel, pose) slots are stored CSR and cut on the host into *batches* of
+//     consecutive voxels holding <= kSlots slots; one CTA of kSlots threads owns one batch;
+//   * phase 1: one thread per slot — coalesced double2 loads of the SoA cluster record, gathered pose,
+//              rigid transform of the cluster, staged in shared memory;
+//   * phase 2: one thread per voxel — merge the staged clusters, 3x3 Jacobi eigen-solve;
+//   * phase 3: one thread per slot — A_i (3x6), g_i, H_ii and the three 6-vectors
+//              f1 = A_i^T u1, f2 = A_i^T u2, b = [v_i x R_i^T u0 ; n_i u0]; the off-diagonal block of any
+//              pose pair is the rank-3 product  c1 f1_i f1_j^T + c2 f2_i f2_j^T - 2/N^2 b_i b_j^T
+//              (algebraically identical to bavoxel.hpp:159-163, re-associated);
+//   * phase 4: every warp takes 8 pose pairs at a time: 8*36 = 288 block elements = 9 per lane, each a
+//              3-FMA product of shared-memory factors followed by one RED.ADD.F64 into the block-envelope
+//              Hessian.  A warp's 32 REDs of one instruction hit 32 consecutive doubles (coalesced
+//              sectors).  Diagonal blocks and g_i are staged in shared memory and flushed the same way.
+// FP64 throughout: lambda0 ~ 1e-4 m^2 is a difference of O(1e4) m^2 terms (P/N - vbar vbar^T).
+#pragma once
+#include "common.cuh"
+#include "envelope.cuh"
+
+namespace lvba {
+
+constexpr int kSlots = 128;            // slots (threads) per batch CTA
+constexpr int kMaxVoxPerBatch = 64;    // K >= 2 per voxel  =>  <= kSlots/2 voxels per batch
+constexpr int kStageStride = 37;       // doubles per slot in the staging buffer (36 + 1 pad: odd => no LDS.64 bank conflicts)
+constexpr int kFStride = 19;           // 18 factor doubles + 1 pad
+constexpr int kVoxParams = 16;
+
+struct LidarView {
+  int W;
+  int n_batches;
+  const double2* cl;        // [5][nnz_pad] SoA pairs: (Pxx,Pxy) (Pxz,Pyy) (Pyz,Pzz) (vx,vy) (vz,N)
+  long long nnz_pad;
+  const int* pidx;          // [nnz] pose index per slot
+  const int* vox_ptr;       // [V_local+1] slot offsets
+  const int* batch_vox;     // [n_batches+1] voxel range per batch
+  const long long* batch_pair;  // [n_batches+1] pair range per batch
+  const unsigned* pairs;    // packed (li | lj<<8 | lv<<16), li<lj local slot ids, lv local voxel id
+};
+
+struct SlotData {
+  double R[9], t[3], P[6], v[3], n;
+};
+
+LVBA_DEV void load_slot(const LidarView& lv, const double* __restrict__ poses, long long slot, int pose, SlotData& s) {
+  const double2 c0 = ldg2(lv.cl + 0 * lv.nnz_pad + slot);
+  const double2 c1 = ldg2(lv.cl + 1 * lv.nnz_pad + slot);
+  const double2 c2 = ldg2(lv.cl + 2 * lv.nnz_pad + slot);
+  const double2 c3 = ldg2(lv.cl + 3 * lv.nnz_pad + slot);
+  const double2 c4 = ldg2(lv.cl + 4 * lv.nnz_pad + slot);
+  const double2* pp = reinterpret_cast<const double2*>(poses + 12 * (long long)pose);
+  const double2 p0 = pp[0], p1 = pp[1], p2 = pp[2], p3 = pp[3], p4 = pp[4], p5 = pp[5];
+  s.P[0] = c0.x; s.P[1] = c0.y; s.P[2] = c1.x; s.P[3] = c1.y; s.P[4] = c2.x; s.P[5] = c2.y;
+  s.v[0] = c3.x; s.v[1] = c3.y; s.v[2] = c4.x; s.n = c4.y;
+  s.R[0] = p0.x; s.R[1] = p0.y; s.R[2] = p1.x; s.R[3] = p1.y; s.R[4] = p2.x; s.R[5] = p2.y;
+  s.R[6] = p3.x; s.R[7] = p3.y; s.R[8] = p4.x; s.t[0] = p4.y; s.t[1] = p5.x; s.t[2] = p5.y;
+}
+
+// PointCluster::transform (tools.hpp:450-456): out[0..5] = P' (xx xy xz yy yz zz), out[6..8] = v', out[9] = N
+LVBA_DEV void transform_cluster(const SlotData& s, double* out) {
+  const double Pf[9] = {s.P[0], s.P[1], s.P[2], s.P[1], s.P[3], s.P[4], s.P[2], s.P[4], s.P[5]};
+  double RP[9], RPRt[9], Rv[3];
+  mat3_mul(s.R, Pf, RP);
+  mat3_mul_bt(RP, s.R, RPRt);
+  mat3_vec(s.R, s.v, Rv);
+  const double* t = s.t;
+  out[0] = RPRt[0] + 2.0 * Rv[0] * t[0] + s.n * t[0] * t[0];
+  out[1] = RPRt[1] + Rv[0] * t[1] + Rv[1] * t[0] + s.n * t[0] * t[1];
+  out[2] = RPRt[2] + Rv[0] * t[2] + Rv[2] * t[0] + s.n * t[0] * t[2];
+  out[3] = RPRt[4] + 2.0 * Rv[1] * t[1] + s.n * t[1] * t[1];
+  out[4] = RPRt[5] + Rv[1] * t[2] + Rv[2] * t[1] + s.n * t[1] * t[2];
+  out[5] = RPRt[8] + 2.0 * Rv[2] * t[2] + s.n * t[2] * t[2];
+  out[6] = Rv[0] + s.n * t[0];
+  out[7] = Rv[1] + s.n * t[1];
+  out[8] = Rv[2] + s.n * t[2];
+  out[9] = s.n;
+}
+
+// merged covariance of one voxel from the staged clusters (bavoxel.hpp:87-98)
+LVBA_DEV void voxel_cov(const double* stage, int s_lo, int s_hi, double cov[6], double vbar[3], double& Nsum) {
+  double acc[10];
+#pragma unroll
+  for (int q = 0; q < 10; ++q) acc[q] = 0.0;
+  for (int s = s_lo; s < s_hi; ++s) {
+    const double* p = stage + s * kStageStride;
+#pragma unroll
+    for (int q = 0; q < 10; ++q) acc[q] += p[q];
+  }
+  Nsum = acc[9];
+  const double inv = 1.0 / Nsum;
+  vbar[0] = acc[6] * inv; vbar[1] = acc[7] * inv; vbar[2] = acc[8] * inv;
+  cov[0] = acc[0] * inv - vbar[0] * vbar[0];
+  cov[1] = acc[1] * inv - vbar[0] * vbar[1];
+  cov[2] = acc[2] * inv - vbar[0] * vbar[2];
+  cov[3] = acc[3] * inv - vbar[1] * vbar[1];
+  cov[4] = acc[4] * inv - vbar[1] * vbar[2];
+  cov[5] = acc[5] * inv - vbar[2] * vbar[2];
+}
+
+// ------------------------------------------------------------------------------------------------
+// residual-only pass: sum_v lambda0 (per-batch partial written to batch_res[blockIdx.x])
+__global__ void __launch_bounds__(kSlots)
+lidar_residual_kernel(LidarView lv, const double* __restrict__ poses, double* __restrict__ batch_res) {
+  constexpr int kS = 11;                      // 10 doubles per slot + 1 pad (odd stride)
+  __shared__ double stage[kSlots * kS];
+  __shared__ double red[32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int v0 = lv.batch_vox[b], v1 = lv.batch_vox[b + 1];
+  const int s0 = lv.vox_ptr[v0], ns = lv.vox_ptr[v1] - s0;
+  if (tid < ns) {
+    SlotData s;
+    load_slot(lv, poses, s0 + tid, lv.pidx[s0 + tid], s);
+    double out[10];
+    transform_cluster(s, out);
+#pragma unroll
+    for (int q = 0; q < 10; ++q) stage[tid * kS + q] = out[q];
+  }
+  __syncthreads();
+  double lam0 = 0.0;
+  if (tid < v1 - v0) {
+    const int lo = lv.vox_ptr[v0 + tid] - s0, hi = lv.vox_ptr[v0 + tid + 1] - s0;
+    double acc[10];
+#pragma unroll
+    for (int q = 0; q < 10; ++q) acc[q] = 0.0;
+    for (int s = lo; s < hi; ++s)
+#pragma unroll
+      for (int q = 0; q < 10; ++q) acc[q] += stage[s * kS + q];
+    const double inv = 1.0 / acc[9];
+    const double m0 = acc[6] * inv, m1 = acc[7] * inv, m2 = acc[8] * inv;
+    double lam[3], u[3][3];
+    eig3_sym<false>(acc[0] * inv - m0 * m0, acc[1] * inv - m0 * m1, acc[2] * inv - m0 * m2,
+                    acc[3] * inv - m1 * m1, acc[4] * inv - m1 * m2, acc[5] * inv - m2 * m2, lam, u);
+    lam0 = lam[0];
+  }
+  const double tot = block_sum<kSlots>(lam0, red);
+  if (tid == 0) batch_res[b] = tot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hessian + gradient + residual build
+__global__ void __launch_bounds__(kSlots)
+lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, double* __restrict__ H,
+                   double* __restrict__ g, double* __restrict__ batch_res) {
+  extern __shared__ double sm[];
+  double* stage = sm;                                   // [kSlots][kStageStride]
+  double* sF = stage + kSlots * kStageStride;           // [kSlots][kFStride]
+  double* sG = sF + kSlots * kFStride;                  // [kSlots][6]
+  double* sV = sG + kSlots * 6;                         // [kMaxVoxPerBatch][kVoxParams]
+  double* red = sV + kMaxVoxPerBatch * kVoxParams;      // [32]
+  long long* sDiag = reinterpret_cast<long long*>(red + 32);   // [kSlots] element offset of the slot's diagonal block
+  int* sPose = reinterpret_cast<int*>(sDiag + kSlots);  // [kSlots]
+  unsigned char* sVoxOf = reinterpret_cast<unsigned char*>(sPose + kSlots);   // [kSlots]
+  // per-warp pair scratch
+  long long* sPairBase = reinterpret_cast<long long*>(sVoxOf + kSlots);       // [4 warps][8]
+  unsigned* sPairCode = reinterpret_cast<unsigned*>(sPairBase + (kSlots / 32) * 8);   // [4 warps][8]
+
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int v0 = lv.batch_vox[b], v1 = lv.batch_vox[b + 1], nv = v1 - v0;
+  const int s0 = lv.vox_ptr[v0], ns = lv.vox_ptr[v1] - s0;
+
+  // ---- phase 1: load + transform
+  SlotData s;
+  int pose = 0;
+  if (tid < ns) {
+    pose = lv.pidx[s0 + tid];
+    load_slot(lv, poses, s0 + tid, pose, s);
+    double out[10];
+    transform_cluster(s, out);
+#pragma unroll
+    for (int q = 0; q < 10; ++q) stage[tid * kStageStride + q] = out[q];
+    sPose[tid] = pose;
+    sDiag[tid] = env_block(env, pose, pose) * 36;
+  }
+  __syncthreads();
+
+  // ---- phase 2: per voxel merge + eigen solve (bavoxel.hpp:97-110)
+  double lam0 = 0.0;
+  if (tid < nv) {
+    const int lo = lv.vox_ptr[v0 + tid] - s0, hi = lv.vox_ptr[v0 + tid + 1] - s0;
+    double cov[6], vbar[3], Nsum;
+    voxel_cov(stage, lo, hi, cov, vbar, Nsum);
+    double lam[3], u[3][3];
+    eig3_sym<true>(cov[0], cov[1], cov[2], cov[3], cov[4], cov[5], lam, u);
+    lam0 = lam[0];
+    double* p = sV + tid * kVoxParams;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { p[k] = u[0][k]; p[3 + k] = u[1][k]; p[6 + k] = u[2][k]; p[12 + k] = vbar[k]; }
+    p[9] = 2.0 / (lam[0] - lam[1]);       // umumT weights, bavoxel.hpp:110
+    p[10] = 2.0 / (lam[0] - lam[2]);
+    p[11] = (double)(int)Nsum;            // int NN = sig.N, bavoxel.hpp:101
+    for (int q = lo; q < hi; ++q) sVoxOf[q] = (unsigned char)tid;
+  }
+  const double tot = block_sum<kSlots>(lam0, red);   // contains __syncthreads
+  if (tid == 0) batch_res[b] = tot;
+  __syncthreads();
+
+  // ---- phase 3: per slot A_i, g_i, H_ii, factors (bavoxel.hpp:112-149)
+  if (tid < ns) {
+    const double* vp = sV + sVoxOf[tid] * kVoxParams;
+    const double uk[3] = {vp[0], vp[1], vp[2]}, u1[3] = {vp[3], vp[4], vp[5]}, u2[3] = {vp[6], vp[7], vp[8]};
+    const double c1 = vp[9], c2 = vp[10], NN = vp[11];
+    const double iN = 1.0 / NN;
+    const double Pf[9] = {s.P[0], s.P[1], s.P[2], s.P[1], s.P[3], s.P[4], s.P[2], s.P[4], s.P[5]};
+    double a[3], Pa[3], w[3], tiv[3], Rv[3];
+    mat3t_vec(s.R, uk, a);                 // RiTuk
+    mat3_vec(Pf, a, Pa);                   // PiRiTuk
+    cross3(s.v, a, w);                     // viRiTuk = hat(vi) RiTuk
+    tiv[0] = s.t[0] - vp[12]; tiv[1] = s.t[1] - vp[13]; tiv[2] = s.t[2] - vp[14];
+    const double sc = dot3(uk, tiv);       // ukTti_v
+    const double x[3] = {Pa[0] + sc * s.v[0], Pa[1] + sc * s.v[1], Pa[2] + sc * s.v[2]};   // combo1 = hat(x)
+    mat3_vec(s.R, s.v, Rv);
+    const double c2v[3] = {Rv[0] + s.n * tiv[0], Rv[1] + s.n * tiv[1], Rv[2] + s.n * tiv[2]};   // combo2
+    // Auk (3x6), rows r, cols 0..5
+    double M1[9], A0[9], Rc1[9];
+    mat3_mul(s.R, Pf, M1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) M1[3 * i + j] += tiv[i] * s.v[j];
+    mat3_mul_hat(M1, a, A0);               // (Ri Pi + ti_v vi^T) hat(RiTuk)
+    mat3_mul_hat(s.R, x, Rc1);             // Ri * combo1
+    double Auk[18];
+    const double c2u = dot3(c2v, uk);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        Auk[6 * i + j] = (A0[3 * i + j] - Rc1[3 * i + j]) * iN;
+        Auk[6 * i + 3 + j] = (c2v[i] * uk[j] + ((i == j) ? c2u : 0.0)) * iN;
+      }
+    }
+    double jjt[6], f1[6], f2[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      jjt[j] = Auk[j] * uk[0] + Auk[6 + j] * uk[1] + Auk[12 + j] * uk[2];
+      f1[j] = Auk[j] * u1[0] + Auk[6 + j] * u1[1] + Auk[12 + j] * u1[2];
+      f2[j] = Auk[j] * u2[0] + Auk[6 + j] * u2[1] + Auk[12 + j] * u2[2];
+    }
+    // diagonal block
+    double Hb[36];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) Hb[6 * i + j] = c1 * f1[i] * f1[j] + c2 * f2[i] * f2[j];
+    {
+      // (0,0) += 2/NN (combo1 - hat(a) Pi) hat(a) - 2/NN^2 w w^T - 0.5 hat(jjt[0:3])
+      double haP[9], D0[9], hx[9], E[9];
+      hat_mul_mat3(a, Pf, haP);
+      hat3(x, hx);
+#pragma unroll
+      for (int q = 0; q < 9; ++q) D0[q] = hx[q] - haP[q];
+      mat3_mul_hat(D0, a, E);
+      double hj[9];
+      hat3(jjt, hj);
+      const double k2 = 2.0 * iN, k22 = 2.0 * iN * iN;
+      const double hrt = 2.0 * iN * (1.0 - s.n * iN);
+      const double k33 = 2.0 * iN * (s.n - s.n * s.n * iN);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          Hb[6 * i + j] += k2 * E[3 * i + j] - k22 * w[i] * w[j] - 0.5 * hj[3 * i + j];
+          const double h = hrt * w[i] * uk[j];
+          Hb[6 * i + 3 + j] += h;
+          Hb[6 * (3 + j) + i] += h;
+          Hb[6 * (3 + i) + 3 + j] += k33 * uk[i] * uk[j];
+        }
+    }
+    // stage: diagonal block, gradient, factors
+    double* st = stage + tid * kStageStride;
+#pragma unroll
+    for (int q = 0; q < 36; ++q) st[q] = Hb[q];
+    double* sg = sG + tid * 6;
+    double* sf = sF + tid * kFStride;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { sg[j] = jjt[j]; sf[j] = f1[j]; sf[6 + j] = f2[j]; }
+    sf[12] = w[0]; sf[13] = w[1]; sf[14] = w[2];
+    sf[15] = s.n * uk[0]; sf[16] = s.n * uk[1]; sf[17] = s.n * uk[2];
+  }
+  __syncthreads();
+
+  // ---- phase 4a: flush diagonal blocks and gradients (coalesced REDs)
+  for (int e = tid; e < ns * 36; e += kSlots) {
+    const int sl = e / 36, el = e - sl * 36;
+    atomicAdd(H + sDiag[sl] + el, stage[sl * kStageStride + el]);
+  }
+  for (int e = tid; e < ns * 6; e += kSlots) {
+    const int sl = e / 6, el = e - sl * 6;
+    atomicAdd(g + 6 * (long long)sPose[sl] + el, sG[e]);
+  }
+
+  // ---- phase 4b: off-diagonal blocks, 8 pairs (288 elements) per warp iteration
+  const long long p0 = lv.batch_pair[b], np = lv.batch_pair[b + 1] - p0;
+  long long* myBase = sPairBase + warp * 8;
+  unsigned* myCode = sPairCode + warp * 8;
+  for (long long c = (long long)warp * 8; c < np; c += (kSlots / 32) * 8) {
+    const int cnt = (int)((np - c < 8) ? (np - c) : 8);
+    __syncwarp();
+    if (lane < cnt) {
+      const unsigned code = lv.pairs[p0 + c + lane];
+      const int li = code & 0xff, lj = (code >> 8) & 0xff;
+      myCode[lane] = code;
+      // lower-triangle block: row = larger pose (slot lj, ascending order inside a voxel), col = slot li
+      myBase[lane] = env_block(env, sPose[lj], sPose[li]) * 36;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 9; ++m) {
+      const int e = lane + 32 * m;
+      const int pr = e / 36, el = e - pr * 36;
+      if (pr < cnt) {
+        const unsigned code = myCode[pr];
+        const int li = code & 0xff, lj = (code >> 8) & 0xff, vx = (code >> 16) & 0xff;
+        const int a = el / 6, bq = el - a * 6;          // block(row j, col i)[a][bq] = Hb_ij[bq][a]
+        const double* fi = sF + li * kFStride;
+        const double* fj = sF + lj * kFStride;
+        const double* vp = sV + vx * kVoxParams;
+        const double iN = 1.0 / vp[11];
+        double val = vp[9] * fi[bq] * fj[a];
+        val += vp[10] * fi[6 + bq] * fj[6 + a];
+        val -= 2.0 * iN * iN * fi[12 + bq] * fj[12 + a];
+        atomicAdd(H + myBase[pr] + el, val);
+      }
+    }
+  }
+}
+
+constexpr size_t lidar_build_smem_bytes() {
+  return sizeof(double) * (kSlots * kStageStride + kSlots * kFStride + kSlots * 6 + kMaxVoxPerBatch * kVoxParams + 32)
+       + sizeof(long long) * kSlots + sizeof(int) * kSlots + kSlots /*u8*/
+       + sizeof(long long) * (kSlots / 32) * 8 + sizeof(unsigned) * (kSlots / 32) * 8 + 64;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small LM helpers
+// deterministic sum of n partials by one block
+__global__ void reduce_partials_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += part[i];
+  const double tot = block_sum<256>(s, red);
+  if (threadIdx.x == 0) out[0] = tot;
+}
+
+// trial = poses (+) dx : R <- R Exp(dphi), p <- p + dp   (bavoxel.hpp:722-727)
+__global__ void lidar_retract_kernel(int W, const double* __restrict__ poses, const double* __restrict__ dx,
+                                     double* __restrict__ trial) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= W) return;
+  const double* p = poses + 12 * j;
+  const double* d = dx + 6 * j;
+  double E[9], R[9], Rn[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) R[q] = p[q];
+  so3_exp(d, E);
+  mat3_mul(R, E, Rn);
+  double* o = trial + 12 * j;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) o[q] = Rn[q];
+  o[9] = p[9] + d[3]; o[10] = p[10] + d[4]; o[11] = p[11] + d[5];
+}
+
+// q1 = 0.5 * dx . (u * D * dx - g), D = diag(H)   (bavoxel.hpp:729); also flags non-finite dx
+__global__ void lidar_q1_kernel(int n6, const double* __restrict__ dx, const double* __restrict__ diag,
+                                const double* __restrict__ g, double u, double* __restrict__ out /* [2]: q1, nonfinite */) {
+  __shared__ double red[32];
+  double s = 0.0, bad = 0.0;
+  for (int i = threadIdx.x; i < n6; i += 256) {
+    const double d = dx[i];
+    s += d * (u * diag[i] * d - g[i]);
+    if (!isfinite(d)) bad = 1.0;
+  }
+  const double tot = block_sum<256>(s, red);
+  const double tb = block_sum<256>(bad, red);
+  if (threadIdx.x == 0) { out[0] = 0.5 * tot; out[1] = tb; }
+}
+
+// z = -g ; dadd = u * diag
+__global__ void lidar_rhs_kernel(int n6, const double* __restrict__ g, const double* __restrict__ diag, double u,
+                                 double* __restrict__ z, double* __restrict__ dadd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n6) { z[i] = -g[i]; dadd[i] = u * diag[i]; }
+}
+
+}  // namespace lvba

@@ -1,0 +1,493 @@
+// lidar_api.cuh — host side of boundary B1 (include/lvba_b200.h): symbolic set-up, device-resident
+// problem handle and the damping_iter LM loop of reference include/BALM/bavoxel.hpp:662-767.
+#pragma once
+#include <cmath>
+#include <unordered_set>
+
+#include "comm.cuh"
+#include "lidar.cuh"
+#include "runtime.cuh"
+
+namespace lvba {
+
+__global__ void lidar_aos_to_soa_kernel(long long nnz, long long nnz_pad, const double* __restrict__ aos,
+                                        double2* __restrict__ soa) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  const double2* r = reinterpret_cast<const double2*>(aos + 10 * i);   // 80-byte records: 16-byte aligned
+#pragma unroll
+  for (int q = 0; q < 5; ++q) soa[q * nnz_pad + i] = r[q];
+}
+
+}  // namespace lvba
+
+struct lvba_lidar_problem {
+  int W = 0;
+  long long V_total = 0;          // voxels of the whole problem (the AVG_THR divisor, bavoxel.hpp:635)
+  long long V_local = 0, nnz_local = 0, n_pairs = 0;
+  int n_batches = 0;
+  int device = 0;
+  // host copies kept for counters / structure queries
+  std::vector<long long> h_vox_ptr_all;
+  std::vector<int> h_pose_idx_all;
+  cudaStream_t stream = nullptr;
+  lvba::DevBuf<double2> cl;
+  lvba::DevBuf<int> pidx, vox_ptr, batch_vox;
+  lvba::DevBuf<long long> batch_pair;
+  lvba::DevBuf<unsigned> pairs;
+  lvba::DevBuf<double> poses, trial, H, g, diag, dadd, dx, batch_res, scal;
+  lvba::Envelope env;
+  lvba::EnvSolver solver;
+  lvba::PhaseTimers timers;
+  double* h_scal = nullptr;       // pinned: [0] r1 sum, [1] q1, [2] dx non-finite flag, [3] r2 sum, [4] factor status
+  int64_t launches = 0, h2d = 0, d2h = 0;
+  double ms_setup = 0.0;
+  // LM state (bavoxel.hpp:664-671)
+  lvba_lidar_opts opts;
+  double u = 0.01, v = 2.0, residual1 = 0.0;
+  bool is_calc_hess = true, have_first = false, converged = false;
+  double cost_first = 0.0, cost_last = 0.0;
+  int iters = 0, accepted = 0, builds = 0, termination = LVBA_TERM_MAX_ITER;
+
+  lvba::LidarView view() const {
+    lvba::LidarView v_;
+    v_.W = W; v_.n_batches = n_batches; v_.cl = cl.p; v_.nnz_pad = (long long)(cl.n / 5);
+    v_.pidx = pidx.p; v_.vox_ptr = vox_ptr.p; v_.batch_vox = batch_vox.p; v_.batch_pair = batch_pair.p;
+    v_.pairs = pairs.p;
+    return v_;
+  }
+  ~lvba_lidar_problem() {
+    if (h_scal) cudaFreeHost(h_scal);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace lvba {
+
+inline int lidar_validate(int32_t W, int64_t V, const int64_t* vox_ptr, const int32_t* pose_idx,
+                          const double* clusters, const double* poses) {
+  if (W <= 0 || V < 0) return fail(LVBA_ERR_INVALID_ARG, "W=%d V=%lld must be positive", W, (long long)V);
+  if (!vox_ptr || !poses || (V > 0 && (!pose_idx || !clusters))) return fail(LVBA_ERR_INVALID_ARG, "null input pointer");
+  if (vox_ptr[0] != 0) return fail(LVBA_ERR_INVALID_ARG, "vox_ptr[0] must be 0");
+  for (int64_t a = 0; a < V; ++a) {
+    const int64_t lo = vox_ptr[a], hi = vox_ptr[a + 1];
+    if (hi <= lo) return fail(LVBA_ERR_INVALID_ARG, "voxel %lld has no slots (vox_ptr not increasing)", (long long)a);
+    if (hi - lo > kSlots)
+      return fail(LVBA_ERR_UNSUPPORTED, "voxel %lld is observed from %lld poses; this build handles <= %d per voxel",
+                  (long long)a, (long long)(hi - lo), kSlots);
+    for (int64_t s = lo; s < hi; ++s) {
+      const int p = pose_idx[s];
+      if (p < 0 || p >= W) return fail(LVBA_ERR_INVALID_ARG, "pose_idx[%lld]=%d out of [0,%d)", (long long)s, p, W);
+      if (s > lo && pose_idx[s - 1] >= p) return fail(LVBA_ERR_INVALID_ARG, "pose_idx must be strictly ascending inside voxel %lld", (long long)a);
+    }
+  }
+  if (vox_ptr[V] >= (1LL << 31)) return fail(LVBA_ERR_UNSUPPORTED, "more than 2^31 slots");
+  return LVBA_OK;
+}
+
+inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const int32_t* pose_idx,
+                             const double* clusters, const double* poses, int32_t device,
+                             lvba_lidar_problem** out) {
+  if (!out) return fail(LVBA_ERR_INVALID_ARG, "out is null");
+  *out = nullptr;
+  LVBA_TRY(lidar_validate(W, V, vox_ptr, pose_idx, clusters, poses));
+  LVBA_TRY(select_device(device));
+  const double t0 = wall_ms();
+  std::unique_ptr<lvba_lidar_problem> P(new lvba_lidar_problem());
+  P->W = W; P->V_total = V;
+  LVBA_CUDA(cudaGetDevice(&P->device));
+  LVBA_CUDA(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
+  P->timers.stream = P->stream;
+  LVBA_CUDA(cudaMallocHost((void**)&P->h_scal, 8 * sizeof(double)));
+  cudaStream_t s = P->stream;
+
+  P->h_vox_ptr_all.assign(vox_ptr, vox_ptr + V + 1);
+  P->h_pose_idx_all.assign(pose_idx, pose_idx + vox_ptr[V]);
+
+  // ---- envelope structure over ALL voxels (identical on every rank)
+  std::vector<int> first_raw(W);
+  for (int r = 0; r < W; ++r) first_raw[r] = r;
+  for (int64_t a = 0; a < V; ++a) {
+    const int m = pose_idx[vox_ptr[a]];
+    for (int64_t q = vox_ptr[a]; q < vox_ptr[a + 1]; ++q) first_raw[pose_idx[q]] = std::min(first_raw[pose_idx[q]], m);
+  }
+  LVBA_TRY(P->env.build(first_raw, s, &P->h2d));
+  LVBA_TRY(P->solver.prepare(P->env));
+
+  // ---- shard: voxel -> owner of its lowest pose index
+  Comm& cm = comm();
+  std::vector<int64_t> mine;
+  mine.reserve((size_t)V);
+  for (int64_t a = 0; a < V; ++a)
+    if (!cm.active() || shard_owner(pose_idx[vox_ptr[a]], W, cm.n_ranks) == cm.rank) mine.push_back(a);
+  const int64_t Vl = (int64_t)mine.size();
+  std::vector<int> l_vox_ptr(Vl + 1, 0);
+  for (int64_t i = 0; i < Vl; ++i) l_vox_ptr[i + 1] = l_vox_ptr[i] + (int)(vox_ptr[mine[i] + 1] - vox_ptr[mine[i]]);
+  const long long nnz = l_vox_ptr[Vl];
+  P->V_local = Vl; P->nnz_local = nnz;
+
+  // ---- batches of consecutive voxels, <= kSlots slots and <= kMaxVoxPerBatch voxels each
+  std::vector<int> batch_vox{0};
+  {
+    int ns = 0, nv = 0;
+    for (int64_t i = 0; i < Vl; ++i) {
+      const int K = l_vox_ptr[i + 1] - l_vox_ptr[i];
+      if (nv > 0 && (ns + K > kSlots || nv + 1 > kMaxVoxPerBatch)) { batch_vox.push_back((int)i); ns = 0; nv = 0; }
+      ns += K; ++nv;
+    }
+    if (Vl > 0) batch_vox.push_back((int)Vl);
+  }
+  P->n_batches = (int)batch_vox.size() - 1;
+  // ---- pair table
+  std::vector<long long> batch_pair(P->n_batches + 1, 0);
+  long long np = 0;
+  for (int b = 0; b < P->n_batches; ++b) {
+    for (int i = batch_vox[b]; i < batch_vox[b + 1]; ++i) {
+      const long long K = l_vox_ptr[i + 1] - l_vox_ptr[i];
+      np += K * (K - 1) / 2;
+    }
+    batch_pair[b + 1] = np;
+  }
+  P->n_pairs = np;
+  std::vector<unsigned> pairs((size_t)np);
+  {
+    size_t w = 0;
+    for (int b = 0; b < P->n_batches; ++b) {
+      const int sbase = l_vox_ptr[batch_vox[b]];
+      for (int i = batch_vox[b]; i < batch_vox[b + 1]; ++i) {
+        const unsigned lv = (unsigned)(i - batch_vox[b]);
+        const int lo = l_vox_ptr[i] - sbase, hi = l_vox_ptr[i + 1] - sbase;
+        for (int x = lo; x < hi; ++x)
+          for (int y = x + 1; y < hi; ++y) pairs[w++] = (unsigned)x | ((unsigned)y << 8) | (lv << 16);
+      }
+    }
+  }
+
+  // ---- upload.  Clusters: the caller's AoS records go up as they are (per contiguous run of owned
+  //      voxels) and are transposed to the SoA double2 layout by a kernel.
+  const long long nnz_pad = ((nnz + 31) / 32) * 32 + 32;
+  LVBA_TRY(P->cl.alloc((size_t)5 * nnz_pad));
+  LVBA_TRY(P->cl.zero(s));
+  std::vector<int> l_pidx((size_t)nnz);
+  {
+    DevBuf<double> aos;
+    LVBA_TRY(aos.alloc((size_t)std::max<long long>(nnz, 1) * 10));
+    long long w = 0;
+    int64_t i = 0;
+    while (i < Vl) {   // coalesce runs of consecutive global voxels into one memcpy
+      int64_t j = i;
+      while (j + 1 < Vl && mine[j + 1] == mine[j] + 1) ++j;
+      const int64_t g0 = vox_ptr[mine[i]], g1 = vox_ptr[mine[j] + 1];
+      LVBA_CUDA(cudaMemcpyAsync(aos.p + 10 * w, clusters + 10 * g0, (size_t)(g1 - g0) * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
+      std::copy(pose_idx + g0, pose_idx + g1, l_pidx.begin() + w);
+      P->h2d += (g1 - g0) * 80;
+      w += g1 - g0;
+      i = j + 1;
+    }
+    if (nnz > 0) {
+      lidar_aos_to_soa_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(nnz, nnz_pad, aos.p, P->cl.p);
+      ++P->launches;
+    }
+    LVBA_CUDA(cudaStreamSynchronize(s));   // aos is freed on scope exit
+  }
+  LVBA_TRY(P->pidx.upload(l_pidx, s, &P->h2d));
+  LVBA_TRY(P->vox_ptr.upload(l_vox_ptr, s, &P->h2d));
+  LVBA_TRY(P->batch_vox.upload(batch_vox, s, &P->h2d));
+  LVBA_TRY(P->batch_pair.upload(batch_pair, s, &P->h2d));
+  if (np > 0) LVBA_TRY(P->pairs.upload(pairs, s, &P->h2d));
+  LVBA_TRY(P->poses.upload(poses, (size_t)W * 12, s, &P->h2d));
+  LVBA_TRY(P->trial.alloc((size_t)W * 12));
+  LVBA_TRY(P->H.alloc((size_t)P->env.nblocks * 36));
+  LVBA_TRY(P->g.alloc((size_t)W * 6));
+  LVBA_TRY(P->diag.alloc((size_t)W * 6));
+  LVBA_TRY(P->dadd.alloc((size_t)W * 6));
+  LVBA_TRY(P->dx.alloc((size_t)W * 6));
+  LVBA_TRY(P->batch_res.alloc((size_t)std::max(P->n_batches, 1)));
+  LVBA_TRY(P->scal.alloc(8));
+  LVBA_TRY(P->scal.zero(s));
+  LVBA_CUDA(cudaFuncSetAttribute(lidar_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lidar_build_smem_bytes()));
+  LVBA_CUDA(cudaStreamSynchronize(s));
+  lvba_lidar_default_opts(&P->opts);
+  P->ms_setup = wall_ms() - t0;
+  *out = P.release();
+  return LVBA_OK;
+}
+
+// H, g, sum(lambda0) at the poses in `d_poses`; result scalar lands in scal[slot]
+inline int lidar_build_dev(lvba_lidar_problem* P, const double* d_poses, int slot) {
+  cudaStream_t s = P->stream;
+  LVBA_TRY(P->H.zero(s));
+  LVBA_TRY(P->g.zero(s));
+  if (P->n_batches > 0) {
+    lidar_build_kernel<<<P->n_batches, kSlots, lidar_build_smem_bytes(), s>>>(P->view(), P->env.view(), d_poses, P->H.p, P->g.p, P->batch_res.p);
+    ++P->launches;
+  }
+  reduce_partials_kernel<<<1, 256, 0, s>>>(P->batch_res.p, P->n_batches, P->scal.p + slot);
+  ++P->launches;
+  LVBA_CUDA(cudaGetLastError());
+  Comm& cm = comm();
+  if (cm.active()) {
+    LVBA_TRY(cm.allreduce_sum(P->H.p, (size_t)P->env.nblocks * 36, s));
+    LVBA_TRY(cm.allreduce_sum(P->g.p, (size_t)P->W * 6, s));
+    LVBA_TRY(cm.allreduce_sum(P->scal.p + slot, 1, s));
+  }
+  return LVBA_OK;
+}
+
+inline int lidar_residual_dev(lvba_lidar_problem* P, const double* d_poses, int slot) {
+  cudaStream_t s = P->stream;
+  if (P->n_batches > 0) {
+    lidar_residual_kernel<<<P->n_batches, kSlots, 0, s>>>(P->view(), d_poses, P->batch_res.p);
+    ++P->launches;
+  }
+  reduce_partials_kernel<<<1, 256, 0, s>>>(P->batch_res.p, P->n_batches, P->scal.p + slot);
+  ++P->launches;
+  LVBA_CUDA(cudaGetLastError());
+  Comm& cm = comm();
+  if (cm.active()) LVBA_TRY(cm.allreduce_sum(P->scal.p + slot, 1, s));
+  return LVBA_OK;
+}
+
+// (H + u diag(H)) dx = -g ; q1 ; leaves dx on the device.  scal[1] = q1, scal[2] = non-finite flag
+inline int lidar_solve_dev(lvba_lidar_problem* P, double u) {
+  cudaStream_t s = P->stream;
+  const int n6 = 6 * P->W;
+  const EnvView ev = P->env.view();
+  env_get_diag_kernel<<<(n6 + 255) / 256, 256, 0, s>>>(ev, P->H.p, P->diag.p);
+  lidar_rhs_kernel<<<(n6 + 255) / 256, 256, 0, s>>>(n6, P->g.p, P->diag.p, u, P->solver.z.p, P->dadd.p);
+  P->launches += 2;
+  LVBA_TRY(P->solver.solve(P->env, P->H.p, P->dadd.p, P->dx.p, s, &P->launches));
+  lidar_q1_kernel<<<1, 256, 0, s>>>(n6, P->dx.p, P->diag.p, P->g.p, u, P->scal.p + 1);
+  ++P->launches;
+  LVBA_CUDA(cudaGetLastError());
+  return LVBA_OK;
+}
+
+inline int lidar_fetch_scal(lvba_lidar_problem* P) {
+  LVBA_CUDA(cudaMemcpyAsync(P->h_scal, P->scal.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+  LVBA_CUDA(cudaMemcpyAsync(P->h_scal + 7, P->solver.status.p, sizeof(int), cudaMemcpyDeviceToHost, P->stream));
+  LVBA_CUDA(cudaStreamSynchronize(P->stream));
+  P->d2h += 8 * sizeof(double) + sizeof(int);
+  return LVBA_OK;
+}
+
+// n passes of the damping_iter loop body (bavoxel.hpp:686-766)
+inline int lidar_iterate_impl(lvba_lidar_problem* P, int n_iter, lvba_summary* sum) {
+  const double t0 = wall_ms();
+  const int64_t l0 = P->launches, h0 = P->h2d, d0 = P->d2h;
+  const double V = (double)P->V_total;
+  const int iters0 = P->iters, acc0 = P->accepted, builds0 = P->builds;
+  for (int it = 0; it < n_iter && !P->converged; ++it) {
+    if (P->is_calc_hess) {                                   // divide_thread, :688-689
+      P->timers.begin(PH_BUILD);
+      LVBA_TRY(lidar_build_dev(P, P->poses.p, 0));
+      P->timers.end();
+      ++P->builds;
+    }
+    P->timers.begin(PH_SOLVE);
+    LVBA_TRY(lidar_solve_dev(P, P->u));                      // :692-710, :729
+    P->timers.end();
+    P->timers.begin(PH_RESID);
+    lidar_retract_kernel<<<(P->W + 127) / 128, 128, 0, P->stream>>>(P->W, P->poses.p, P->dx.p, P->trial.p);   // :722-727
+    ++P->launches;
+    LVBA_TRY(lidar_residual_dev(P, P->trial.p, 3));          // only_residual, :731
+    P->timers.end();
+    LVBA_TRY(lidar_fetch_scal(P));
+    if (P->is_calc_hess) P->residual1 = P->h_scal[0] / V;    // AVG_THR, :635
+    if (!P->have_first) { P->cost_first = P->residual1; P->cost_last = P->residual1; P->have_first = true; }
+    const double q1 = P->h_scal[1] / V;                      // :732
+    double residual2 = P->h_scal[3] / V;
+    const bool bad = P->h_scal[2] != 0.0 || !std::isfinite(residual2) || !std::isfinite(q1);
+    if (bad) residual2 = NAN;
+    double q = P->residual1 - residual2;
+    ++P->iters;
+    if (P->opts.verbose)
+      fprintf(stderr, "[lvba lidar] iter %d: (%.9g %.9g) u: %g v: %g q: %g q1: %g\n", P->iters - 1, P->residual1, residual2, P->u, P->v, q, q1);
+    if (q > 0) {                                             // :744-752
+      std::swap(P->poses.p, P->trial.p);
+      q = q / q1;
+      P->v = 2;
+      q = 1 - std::pow(2 * q - 1, 3);
+      P->u *= (q < (1.0 / 3.0) ? (1.0 / 3.0) : q);
+      P->is_calc_hess = true;
+      ++P->accepted;
+      P->cost_last = residual2;
+    } else {                                                 // :753-758
+      P->u = P->u * P->v;
+      P->v = 2 * P->v;
+      P->is_calc_hess = false;
+    }
+    if (P->opts.rel_tol >= 0 && std::fabs(P->residual1 - residual2) / P->residual1 < P->opts.rel_tol) {   // :760
+      P->converged = true;
+      P->termination = LVBA_TERM_FUNCTION_TOL;
+    }
+  }
+  if (sum) {
+    memset(sum, 0, sizeof *sum);
+    LVBA_CUDA(cudaStreamSynchronize(P->stream));
+    double ms[PH_COUNT] = {0, 0, 0};
+    P->timers.collect(ms);
+    sum->iterations = P->iters - iters0; sum->accepted = P->accepted - acc0; sum->hessian_builds = P->builds - builds0;
+    sum->termination = P->termination;
+    sum->cost_first = P->cost_first; sum->cost_last = P->cost_last; sum->damping_last = P->u;
+    sum->ms_total = wall_ms() - t0; sum->ms_setup = 0.0;
+    sum->ms_build = ms[PH_BUILD]; sum->ms_solve = ms[PH_SOLVE]; sum->ms_residual = ms[PH_RESID];
+    sum->kernel_launches = P->launches - l0; sum->h2d_bytes = P->h2d - h0; sum->d2h_bytes = P->d2h - d0;
+  }
+  return LVBA_OK;
+}
+
+}  // namespace lvba
+
+// ================================================================ C ABI
+extern "C" {
+
+void lvba_lidar_default_opts(lvba_lidar_opts* o) {
+  if (!o) return;
+  o->u0 = 0.01; o->v0 = 2.0; o->max_iter = 10; o->rel_tol = 1e-6; o->device = -1; o->verbose = 0;
+}
+
+int lvba_lidar_create(int32_t W, int64_t V, const int64_t* vox_ptr, const int32_t* pose_idx,
+                      const double* clusters, const double* poses, int32_t device, lvba_lidar_problem** out) {
+  try { return lvba::lidar_create_impl(W, V, vox_ptr, pose_idx, clusters, poses, device, out); }
+  catch (const std::bad_alloc&) { return lvba::fail(LVBA_ERR_NOMEM, "host allocation failed"); }
+  catch (...) { return lvba::fail(LVBA_ERR_INVALID_ARG, "unexpected exception in lvba_lidar_create"); }
+}
+
+int lvba_lidar_destroy(lvba_lidar_problem* p) {
+  if (!p) return LVBA_OK;
+  cudaSetDevice(p->device);
+  delete p;
+  return LVBA_OK;
+}
+
+int lvba_lidar_set_poses(lvba_lidar_problem* p, const double* poses) {
+  if (!p || !poses) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  LVBA_CUDA(cudaSetDevice(p->device));
+  LVBA_TRY(p->poses.upload(poses, (size_t)p->W * 12, p->stream, &p->h2d));
+  LVBA_CUDA(cudaStreamSynchronize(p->stream));
+  return LVBA_OK;
+}
+
+int lvba_lidar_get_poses(lvba_lidar_problem* p, double* poses) {
+  if (!p || !poses) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  LVBA_CUDA(cudaSetDevice(p->device));
+  LVBA_CUDA(cudaMemcpyAsync(poses, p->poses.p, (size_t)p->W * 12 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  LVBA_CUDA(cudaStreamSynchronize(p->stream));
+  p->d2h += (int64_t)p->W * 96;
+  return LVBA_OK;
+}
+
+int lvba_lidar_build(lvba_lidar_problem* p, double* residual_sum) {
+  if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  LVBA_CUDA(cudaSetDevice(p->device));
+  LVBA_TRY(lvba::lidar_build_dev(p, p->poses.p, 0));
+  LVBA_TRY(lvba::lidar_fetch_scal(p));
+  if (residual_sum) *residual_sum = p->h_scal[0];
+  return LVBA_OK;
+}
+
+int lvba_lidar_residual(lvba_lidar_problem* p, const double* poses, double* residual_sum) {
+  if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  LVBA_CUDA(cudaSetDevice(p->device));
+  const double* dp = p->poses.p;
+  if (poses) {
+    LVBA_TRY(p->trial.upload(poses, (size_t)p->W * 12, p->stream, &p->h2d));
+    dp = p->trial.p;
+  }
+  LVBA_TRY(lvba::lidar_residual_dev(p, dp, 3));
+  LVBA_TRY(lvba::lidar_fetch_scal(p));
+  if (residual_sum) *residual_sum = p->h_scal[3];
+  return LVBA_OK;
+}
+
+int lvba_lidar_solve(lvba_lidar_problem* p, double u, double* dx) {
+  if (!p || !dx) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  LVBA_CUDA(cudaSetDevice(p->device));
+  LVBA_TRY(lvba::lidar_solve_dev(p, u));
+  LVBA_CUDA(cudaMemcpyAsync(dx, p->dx.p, (size_t)p->W * 6 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  LVBA_TRY(lvba::lidar_fetch_scal(p));
+  p->d2h += (int64_t)p->W * 48;
+  return LVBA_OK;
+}
+
+int lvba_lidar_structure(lvba_lidar_problem* p, int64_t* nblocks, int32_t* brow, int32_t* bcol) {
+  if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  if (nblocks) *nblocks = p->env.nblocks;
+  if (brow && bcol) {
+    for (int r = 0; r < p->env.n; ++r)
+      for (int c = p->env.first[r]; c <= r; ++c) {
+        const long long b = p->env.row_start[r] + (c - p->env.first[r]);
+        brow[b] = r; bcol[b] = c;
+      }
+  }
+  return LVBA_OK;
+}
+
+int lvba_lidar_get_system(lvba_lidar_problem* p, double* g, double* blocks) {
+  if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  LVBA_CUDA(cudaSetDevice(p->device));
+  if (g) LVBA_CUDA(cudaMemcpyAsync(g, p->g.p, (size_t)p->W * 6 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  if (blocks) LVBA_CUDA(cudaMemcpyAsync(blocks, p->H.p, (size_t)p->env.nblocks * 36 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  LVBA_CUDA(cudaStreamSynchronize(p->stream));
+  return LVBA_OK;
+}
+
+int lvba_lidar_reset_lm(lvba_lidar_problem* p, const lvba_lidar_opts* opts) {
+  if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  if (opts) p->opts = *opts; else lvba_lidar_default_opts(&p->opts);
+  p->u = p->opts.u0; p->v = p->opts.v0; p->is_calc_hess = true; p->have_first = false; p->converged = false;
+  p->iters = p->accepted = p->builds = 0; p->termination = LVBA_TERM_MAX_ITER; p->residual1 = 0.0;
+  return LVBA_OK;
+}
+
+int lvba_lidar_iterate(lvba_lidar_problem* p, int32_t n_iter, lvba_summary* summary) {
+  if (!p || n_iter < 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "bad argument");
+  LVBA_CUDA(cudaSetDevice(p->device));
+  return lvba::lidar_iterate_impl(p, n_iter, summary);
+}
+
+int lvba_lidar_counts(lvba_lidar_problem* p, int64_t* nnz, int64_t* n_blocks_env, int64_t* n_blocks_nonzero, int64_t* n_pairs) {
+  if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  if (nnz) *nnz = (int64_t)p->h_pose_idx_all.size();
+  if (n_blocks_env) *n_blocks_env = p->env.nblocks;
+  int64_t np = 0;
+  std::unordered_set<uint64_t> seen;
+  const bool want_nz = n_blocks_nonzero != nullptr;
+  for (int64_t a = 0; a < p->V_total; ++a) {
+    const int64_t lo = p->h_vox_ptr_all[a], hi = p->h_vox_ptr_all[a + 1];
+    np += (hi - lo) * (hi - lo - 1) / 2;
+    if (want_nz)
+      for (int64_t x = lo; x < hi; ++x)
+        for (int64_t y = x; y < hi; ++y)
+          seen.insert(((uint64_t)p->h_pose_idx_all[x] << 32) | (uint32_t)p->h_pose_idx_all[y]);
+  }
+  if (n_pairs) *n_pairs = np;
+  if (want_nz) *n_blocks_nonzero = (int64_t)seen.size();
+  return LVBA_OK;
+}
+
+int lvba_lidar_lm(int32_t W, int64_t V, const int64_t* vox_ptr, const int32_t* pose_idx, const double* clusters,
+                  double* poses, const lvba_lidar_opts* opts, lvba_summary* summary) {
+  const double t0 = lvba::wall_ms();
+  lvba_lidar_opts o;
+  if (opts) o = *opts; else lvba_lidar_default_opts(&o);
+  lvba_lidar_problem* p = nullptr;
+  int rc = lvba_lidar_create(W, V, vox_ptr, pose_idx, clusters, poses, o.device, &p);
+  if (rc != LVBA_OK) return rc;
+  lvba_summary s;
+  memset(&s, 0, sizeof s);
+  rc = lvba_lidar_reset_lm(p, &o);
+  if (rc == LVBA_OK && V > 0) rc = lvba_lidar_iterate(p, o.max_iter, &s);
+  if (rc == LVBA_OK) rc = lvba_lidar_get_poses(p, poses);     // x_stats written back only on success
+  if (rc == LVBA_OK && summary) {
+    *summary = s;
+    summary->ms_setup = p->ms_setup;
+    summary->kernel_launches = p->launches; summary->h2d_bytes = p->h2d; summary->d2h_bytes = p->d2h;
+    summary->ms_total = lvba::wall_ms() - t0;
+  }
+  lvba_lidar_destroy(p);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+// runtime.cuh — host-side plumbing shared by both paths: error reporting, device buffers,
+// CUDA-event phase timers, the block-envelope structure builder and the LDL^T solve driver.
+#pragma once
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lvba_b200.h"
+#include "envelope.cuh"
+
+namespace lvba {
+
+// ---------------------------------------------------------------- errors
+inline std::string& last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+inline int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+#define LVBA_CUDA(call)                                                                        \
+  do {                                                                                         \
+    cudaError_t err__ = (call);                                                                \
+    if (err__ != cudaSuccess)                                                                  \
+      return ::lvba::fail(LVBA_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,  \
+                          cudaGetErrorString(err__));                                          \
+  } while (0)
+#define LVBA_TRY(call)             \
+  do {                             \
+    int rc__ = (call);             \
+    if (rc__ != LVBA_OK) return rc__; \
+  } while (0)
+
+inline int device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+inline int select_device(int device) {
+  const int n = device_count();
+  if (n <= 0) return fail(LVBA_ERR_NO_DEVICE, "no CUDA device available: the LVBA hot path has no CPU fallback");
+  if (device >= n) return fail(LVBA_ERR_INVALID_ARG, "device %d out of range (have %d)", device, n);
+  if (device >= 0) LVBA_CUDA(cudaSetDevice(device));
+  return LVBA_OK;
+}
+
+// ---------------------------------------------------------------- device buffer
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  int alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return LVBA_OK;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e != cudaSuccess) { p = nullptr; n = 0; return fail(LVBA_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); }
+    return LVBA_OK;
+  }
+  int upload(const T* h, size_t count, cudaStream_t s, int64_t* bytes = nullptr) {
+    if (count > n) LVBA_TRY(alloc(count));
+    if (count) LVBA_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    if (bytes) *bytes += (int64_t)(count * sizeof(T));
+    return LVBA_OK;
+  }
+  int upload(const std::vector<T>& h, cudaStream_t s, int64_t* bytes = nullptr) { return upload(h.data(), h.size(), s, bytes); }
+  int zero(cudaStream_t s) {
+    if (n) LVBA_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    return LVBA_OK;
+  }
+};
+
+// ---------------------------------------------------------------- phase timers (CUDA events on the launch stream)
+enum Phase { PH_BUILD = 0, PH_SOLVE = 1, PH_RESID = 2, PH_COUNT = 3 };
+struct PhaseTimers {
+  struct Span { cudaEvent_t a, b; int ph; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> pool;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void begin(int ph) { Span s{get(), get(), ph}; cudaEventRecord(s.a, stream); spans.push_back(s); }
+  void end() { cudaEventRecord(spans.back().b, stream); }
+  // must be called after a stream synchronize
+  void collect(double ms[PH_COUNT]) {
+    for (auto& s : spans) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) ms[s.ph] += t;
+      pool.push_back(s.a); pool.push_back(s.b);
+    }
+    spans.clear();
+  }
+  ~PhaseTimers() {
+    for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto e : pool) cudaEventDestroy(e);
+  }
+};
+inline double wall_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------- block envelope (host build + device copy)
+struct Envelope {
+  int n = 0;
+  std::vector<int> first, last;
+  std::vector<long long> row_start;
+  long long nblocks = 0;
+  int max_col = 0;
+  DevBuf<int> d_first, d_last;
+  DevBuf<long long> d_row_start;
+
+  // first_raw[r] = smallest column coupled to row r (<= r).  Made monotone so that the rows below a
+  // pivot column form a contiguous range (see envelope.cuh header).
+  int build(const std::vector<int>& first_raw, cudaStream_t s, int64_t* bytes) {
+    n = (int)first_raw.size();
+    first = first_raw;
+    for (int r = 0; r < n; ++r) first[r] = std::min(first[r], r);
+    for (int r = n - 2; r >= 0; --r) first[r] = std::min(first[r], first[r + 1]);
+    row_start.assign(n + 1, 0);
+    for (int r = 0; r < n; ++r) row_start[r + 1] = row_start[r] + (r - first[r] + 1);
+    nblocks = row_start[n];
+    last.assign(n, 0);
+    // last[k] = max i with first[i] <= k ; first monotone => two-pointer sweep
+    int i = 0;
+    max_col = 0;
+    for (int k = 0; k < n; ++k) {
+      if (i < k) i = k;
+      while (i + 1 < n && first[i + 1] <= k) ++i;
+      last[k] = i;
+      max_col = std::max(max_col, i - k);
+    }
+    LVBA_TRY(d_first.upload(first, s, bytes));
+    LVBA_TRY(d_last.upload(last, s, bytes));
+    LVBA_TRY(d_row_start.upload(row_start, s, bytes));
+    return LVBA_OK;
+  }
+  EnvView view() const { return EnvView{n, d_first.p, d_row_start.p, d_last.p, nblocks}; }
+};
+
+// ---------------------------------------------------------------- LDL^T solve driver
+struct EnvSolver {
+  DevBuf<double> L, dinv, z;
+  DevBuf<int> status;
+  bool configured = false;
+  int prepare(const Envelope& env) {
+    if (env.max_col > kEnvMaxCol)
+      return fail(LVBA_ERR_UNSUPPORTED, "envelope column height %d exceeds the factor kernel limit %d", env.max_col, kEnvMaxCol);
+    LVBA_TRY(L.alloc((size_t)env.nblocks * 36));
+    LVBA_TRY(dinv.alloc((size_t)env.n * 36));
+    LVBA_TRY(z.alloc((size_t)env.n * 6));
+    LVBA_TRY(status.alloc(1));
+    if (!configured) {
+      LVBA_CUDA(cudaFuncSetAttribute(env_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)factor_smem()));
+      configured = true;
+    }
+    return LVBA_OK;
+  }
+  static size_t factor_smem() { return sizeof(double) * (2 * kEnvMaxCol * 36 + 36 + 8); }
+  // Solves (H + diag(dadd)) x = z_in where z already holds the right-hand side.  x may alias nothing.
+  int solve(const Envelope& env, const double* H, const double* dadd, double* x, cudaStream_t s, int64_t* launches) {
+    const EnvView v = env.view();
+    LVBA_CUDA(cudaMemcpyAsync(L.p, H, (size_t)env.nblocks * 36 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    LVBA_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), s));
+    const int n6 = 6 * env.n;
+    env_add_diag_kernel<<<(n6 + 255) / 256, 256, 0, s>>>(v, dadd, L.p);
+    env_factor_kernel<<<1, kFactorThreads, factor_smem(), s>>>(v, L.p, dinv.p, z.p, status.p);
+    env_backsolve_kernel<<<1, 32, 0, s>>>(v, L.p, dinv.p, z.p, x);
+    *launches += 3;
+    LVBA_CUDA(cudaGetLastError());
+    return LVBA_OK;
+  }
+};
+
+}  // namespace lvba

@@ -1,0 +1,213 @@
+/*
+ * lvba_b200.h — C ABI of the B200-native LiDAR-visual bundle-adjustment hot path.
+ *
+ * This is the drop-in boundary for the two solver call sites of xuankuzcr/Global-LVBA
+ * (SURVEY.md §8b).  The reference has no FFI of its own: both call sites are plain C++
+ * inside one translation unit, so every entry point below cites the reference code it
+ * replaces.  All buffers are HOST pointers owned by the caller; the library copies in
+ * at call time, keeps its own device memory, writes results back before returning and
+ * retains no caller pointer.  Nothing throws across this boundary: every function
+ * returns LVBA_OK (0) or a negative lvba_status, and on error in/out buffers are left
+ * untouched.  There is no CPU fallback: without a CUDA device every compute entry
+ * point returns LVBA_ERR_NO_DEVICE.
+ *
+ * Conventions shared with the reference:
+ *   pose           12 doubles: R (3x3 row-major, body->world) then p      IMUST.R/.p   include/BALM/tools.hpp:147-153
+ *   cluster        10 doubles: Pxx Pxy Pxz Pyy Pyz Pzz vx vy vz N          PointCluster include/BALM/tools.hpp:407-424
+ *   tangent order  (dphi, dp) per pose, R <- R*Exp(dphi), p <- p + dp      include/BALM/bavoxel.hpp:722-727
+ *   quaternion     {w,x,y,z} (memory order of qs[k])                      src/lvba_system.cpp:1513-1516
+ *   intr[8]        fx fy cx cy k1 k2 p1 p2 (Brown-Conrady)                 include/utils.hpp:53-58
+ */
+#ifndef LVBA_B200_H
+#define LVBA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LVBA_B200_VERSION 100   /* 0.1.0 */
+
+typedef enum lvba_status {
+  LVBA_OK = 0,
+  LVBA_ERR_INVALID_ARG = -1,   /* null pointer, negative size, index out of range, non-monotone CSR */
+  LVBA_ERR_NO_DEVICE = -2,     /* no CUDA device / driver: the product path has no CPU fallback */
+  LVBA_ERR_CUDA = -3,          /* a CUDA runtime call failed; see lvba_last_error() */
+  LVBA_ERR_UNSUPPORTED = -4,   /* problem shape outside what this build handles */
+  LVBA_ERR_NUMERIC = -5,       /* non-finite step / zero pivot and no recovery possible */
+  LVBA_ERR_COMM = -6,          /* NCCL not loadable or a collective failed */
+  LVBA_ERR_NOMEM = -7
+} lvba_status;
+
+/* ---- path A options: BALM2::damping_iter constants, include/BALM/bavoxel.hpp:664,686,760 */
+typedef struct lvba_lidar_opts {
+  double u0;           /* 0.01  initial damping            (bavoxel.hpp:664) */
+  double v0;           /* 2.0   initial damping growth     (bavoxel.hpp:664) */
+  int32_t max_iter;    /* 10                               (bavoxel.hpp:686) */
+  double rel_tol;      /* 1e-6  |r1-r2|/r1 stop            (bavoxel.hpp:760); <0 disables the test */
+  int32_t device;      /* CUDA device ordinal; -1 = current */
+  int32_t verbose;     /* 1: print one line per LM iteration to stderr */
+} lvba_lidar_opts;
+
+/* ---- path B options: the ceres::Solver::Options in force at src/lvba_system.cpp:1572-1576
+ *      (ceres-solver 2.1.0 defaults everywhere else) */
+typedef struct lvba_visual_opts {
+  int32_t max_iter;              /* 50      options.max_num_iterations (:1573) */
+  double initial_radius;         /* 1e4  */
+  double max_radius;             /* 1e16 */
+  double min_radius;             /* 1e-32 */
+  double min_lm_diagonal;        /* 1e-6 */
+  double max_lm_diagonal;        /* 1e32 */
+  double min_relative_decrease;  /* 1e-3 */
+  double function_tolerance;     /* 1e-6;  <0 disables */
+  double gradient_tolerance;     /* 1e-10; <0 disables */
+  double parameter_tolerance;    /* 1e-8;  <0 disables */
+  int32_t jacobi_scaling;        /* 1 */
+  int32_t device;
+  int32_t verbose;
+} lvba_visual_opts;
+
+typedef enum lvba_termination {
+  LVBA_TERM_MAX_ITER = 0,
+  LVBA_TERM_FUNCTION_TOL = 1,   /* A: bavoxel.hpp:760 ; B: Ceres function tolerance */
+  LVBA_TERM_PARAMETER_TOL = 2,
+  LVBA_TERM_GRADIENT_TOL = 3,
+  LVBA_TERM_RADIUS = 4,
+  LVBA_TERM_INVALID_STEPS = 5
+} lvba_termination;
+
+typedef struct lvba_summary {
+  int32_t iterations;        /* LM loop passes executed (accepted + rejected) */
+  int32_t accepted;          /* accepted steps */
+  int32_t hessian_builds;    /* passes that rebuilt H/g (A) or J/S (B) */
+  int32_t termination;       /* lvba_termination */
+  double cost_first;         /* A: sum(lambda0)/V at entry ; B: 1/2 sum r^2 at entry */
+  double cost_last;          /* same quantity at the returned state */
+  double damping_last;       /* A: u ; B: trust-region radius */
+  double ms_total;           /* wall time inside the call (host clock) */
+  double ms_setup;           /* host symbolic analysis + H2D upload */
+  double ms_build;           /* CUDA-event time in Hessian / Jacobian+Schur build kernels */
+  double ms_solve;           /* CUDA-event time in factorisation + substitution */
+  double ms_residual;        /* CUDA-event time in residual-only passes + retraction */
+  int64_t kernel_launches;   /* launches of this library's own kernels during the call */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+} lvba_summary;
+
+/* ---- misc ------------------------------------------------------------------------------ */
+int         lvba_version(void);
+int         lvba_device_count(void);          /* 0 when no usable GPU; never fails */
+const char* lvba_status_string(int status);
+const char* lvba_last_error(void);            /* thread-local detail of the last failure */
+void        lvba_lidar_default_opts(lvba_lidar_opts* o);
+void        lvba_visual_default_opts(lvba_visual_opts* o);
+
+/* ======================================================================================
+ * B1  LiDAR LM — replaces  void BALM2::damping_iter(vector<IMUST>& x_stats, VOX_HESS& voxhess)
+ *     include/BALM/bavoxel.hpp:662-767, called at src/lvba_system.cpp:264 and :386.
+ *
+ *   W          number of poses (BALM2::win_size)
+ *   V          number of plane voxels (VOX_HESS::plvec_voxels.size())
+ *   vox_ptr    [V+1] CSR offsets; voxel a owns slots vox_ptr[a]..vox_ptr[a+1]
+ *   pose_idx   [nnz] pose index i of every slot with (*plvec_voxels[a])[i].N != 0, ascending inside a voxel
+ *   clusters   [nnz*10] body-frame PointCluster of that slot
+ *   poses      [W*12] in/out
+ * ====================================================================================== */
+int lvba_lidar_lm(int32_t W, int64_t V, const int64_t* vox_ptr, const int32_t* pose_idx,
+                  const double* clusters, double* poses, const lvba_lidar_opts* opts,
+                  lvba_summary* summary);
+
+/* Device-resident handle for the same problem: lets a caller (bench, parity tests, a ROS
+ * node that re-solves after outlier removal) run single phases with inputs already in HBM. */
+typedef struct lvba_lidar_problem lvba_lidar_problem;
+
+int lvba_lidar_create(int32_t W, int64_t V, const int64_t* vox_ptr, const int32_t* pose_idx,
+                      const double* clusters, const double* poses, int32_t device,
+                      lvba_lidar_problem** out);
+int lvba_lidar_destroy(lvba_lidar_problem* p);
+int lvba_lidar_set_poses(lvba_lidar_problem* p, const double* poses);     /* H2D, W*12 */
+int lvba_lidar_get_poses(lvba_lidar_problem* p, double* poses);           /* D2H, W*12 */
+/* VOX_HESS::acc_evaluate2 + divide_thread (bavoxel.hpp:68-174, 597-639) at the current poses:
+ * builds H and g on the device, returns sum_v lambda0 (NOT divided by V). */
+int lvba_lidar_build(lvba_lidar_problem* p, double* residual_sum);
+/* VOX_HESS::evaluate_only_residual (bavoxel.hpp:176-203) at `poses` (host, W*12) or at the
+ * current device poses when poses == NULL. */
+int lvba_lidar_residual(lvba_lidar_problem* p, const double* poses, double* residual_sum);
+/* (H + u*diag(H)) dx = -g  (bavoxel.hpp:692-710); dx [W*6] to host. */
+int lvba_lidar_solve(lvba_lidar_problem* p, double u, double* dx);
+/* Block structure of the lower-triangular envelope that stores H: nblocks and per block (row, col). */
+int lvba_lidar_structure(lvba_lidar_problem* p, int64_t* nblocks, int32_t* brow, int32_t* bcol);
+/* Copy out g [W*6] and the envelope blocks [nblocks*36, row-major 6x6, block (r,c) = H[6r.., 6c..]]. */
+int lvba_lidar_get_system(lvba_lidar_problem* p, double* g, double* blocks);
+/* n LM passes of damping_iter starting from the handle's state (u, v, poses carried in the
+ * handle; call lvba_lidar_reset_lm to restart).  Device-resident: no problem data crosses PCIe. */
+int lvba_lidar_reset_lm(lvba_lidar_problem* p, const lvba_lidar_opts* opts);
+int lvba_lidar_iterate(lvba_lidar_problem* p, int32_t n_iter, lvba_summary* summary);
+/* exact algorithmic byte / flop counters of SURVEY.md §8(d) for this problem instance */
+int lvba_lidar_counts(lvba_lidar_problem* p, int64_t* nnz, int64_t* n_blocks_env,
+                      int64_t* n_blocks_nonzero, int64_t* n_pairs);
+
+/* ======================================================================================
+ * B2  visual LM — replaces the Ceres block of LvbaSystem::optimizeCameraPoses(),
+ *     src/lvba_system.cpp:1571-1656 (problem build :1578-1640, ceres::Solve :1643,
+ *     write-back :1651-1665).  Residual functors: include/utils.hpp:51-147.
+ *
+ *   M, T        cameras, landmarks
+ *   q_wxyz      [M*4] in/out   qs[k]   (:1513-1516)
+ *   t           [M*3] in/out   ts[k]
+ *   X           [T*3] in/out   Xs[pi]  (:1521-1525); landmarks without a valid plane are left untouched
+ *   plane_nd    [T*4] (n, d); n == 0 marks "no valid plane" => landmark and its observations are skipped (:1598-1603)
+ *   obs_ptr     [T+1] CSR; obs_cam [nnz] camera of each inlier observation; obs_uv [nnz*2] float pixel (:1624-1625)
+ *   fixed_cam   camera held constant (0 in the reference, :1582-1583); -1 = none
+ * ====================================================================================== */
+int lvba_visual_lm(int32_t M, int64_t T, double* q_wxyz, double* t, double* X,
+                   const double* plane_nd, const int64_t* obs_ptr, const int32_t* obs_cam,
+                   const float* obs_uv, const double intr[8], double sigma_px, double sigma_plane,
+                   int32_t fixed_cam, const lvba_visual_opts* opts, lvba_summary* summary);
+
+typedef struct lvba_visual_problem lvba_visual_problem;
+
+int lvba_visual_create(int32_t M, int64_t T, const double* q_wxyz, const double* t, const double* X,
+                       const double* plane_nd, const int64_t* obs_ptr, const int32_t* obs_cam,
+                       const float* obs_uv, const double intr[8], double sigma_px, double sigma_plane,
+                       int32_t fixed_cam, int32_t device, lvba_visual_problem** out);
+int lvba_visual_destroy(lvba_visual_problem* p);
+int lvba_visual_set_state(lvba_visual_problem* p, const double* q_wxyz, const double* t, const double* X);
+int lvba_visual_get_state(lvba_visual_problem* p, double* q_wxyz, double* t, double* X);
+/* 1/2 sum r^2 over all residual blocks at the current device state */
+int lvba_visual_cost(lvba_visual_problem* p, double* cost);
+/* One linearisation + Schur elimination + reduced solve + back-substitution at the current state
+ * with the given trust-region radius; writes the (unscaled) tangent step: cam_step [M*6] (zeros for
+ * inactive cameras), pt_step [T*3] (zeros for skipped landmarks), and the model cost change. */
+int lvba_visual_step(lvba_visual_problem* p, double radius, int32_t jacobi_scaling, int32_t recompute_scale,
+                     double* cam_step, double* pt_step, double* model_cost_change, double* cost);
+/* Reduced camera system of the last lvba_visual_step: block structure + values + rhs (for parity tests). */
+int lvba_visual_structure(lvba_visual_problem* p, int32_t* n_active, int32_t* cam_of_row /* [n_active] */,
+                          int64_t* nblocks, int32_t* brow, int32_t* bcol);
+int lvba_visual_get_system(lvba_visual_problem* p, double* rhs /* [n_active*6] */, double* blocks /* [nblocks*36] */);
+int lvba_visual_reset_lm(lvba_visual_problem* p, const lvba_visual_opts* opts);
+int lvba_visual_iterate(lvba_visual_problem* p, int32_t n_iter, lvba_summary* summary);
+int lvba_visual_counts(lvba_visual_problem* p, int64_t* nnz_valid, int64_t* n_valid_tracks,
+                       int64_t* n_blocks_env, int64_t* n_pairs);
+
+/* ======================================================================================
+ * Multi-GPU (one process per GPU).  The path shards by contiguous pose-block rows
+ * (SURVEY.md §8e): voxel / track -> owner of its lowest pose / camera index.  Every rank
+ * passes the FULL problem to *_create; after lvba_comm_init each rank keeps only its shard
+ * of voxels / tracks on its GPU and H, g, S, rhs and the scalar costs are summed with
+ * ncclAllReduce over NVLink.  NCCL is dlopen()ed (libnccl.so.2) on first use.
+ * ====================================================================================== */
+#define LVBA_NCCL_ID_BYTES 128
+int lvba_comm_unique_id(void* id_out /* LVBA_NCCL_ID_BYTES */);
+int lvba_comm_init(int32_t n_ranks, int32_t rank, const void* id /* LVBA_NCCL_ID_BYTES */, int32_t device);
+int lvba_comm_destroy(void);
+int lvba_comm_info(int32_t* n_ranks, int32_t* rank);
+/* Host-only shard rule (no GPU needed; used by the gloo CPU tests): owner rank of a unit whose
+ * lowest pose index is `min_pose` when `n_rows` pose-block rows are split over `n_ranks`. */
+int32_t lvba_shard_owner(int32_t min_pose, int32_t n_rows, int32_t n_ranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVBA_B200_H */
