@@ -310,3 +310,27 @@ def ceres_lm(prob: VisualProblem, max_iter=50, radius0=1e4, log=None, scaling=Tr
     info["cost"] = cost
     info["radius"] = radius
     return prob, info
+
+
+def single_step(prob: VisualProblem, radius=1e4, scaling=True, min_diag=1e-6, max_diag=1e32):
+    """One linearisation + LM solve at the current state (what lvba_visual_step computes).
+    Returns dict(cost, model, cam_step[M,6], pt_step[T,3], scale, S, rhs) — S/rhs only for small problems."""
+    res, J = prob.residuals(jac=True)
+    cost = 0.5 * float(res @ res)
+    scale = 1.0 / (1.0 + np.sqrt(np.asarray(J.multiply(J).sum(0)).ravel())) if scaling else np.ones(prob.ncols)
+    Js = (J @ sp.diags(scale)).tocsr()
+    diag = np.clip(np.asarray(Js.multiply(Js).sum(0)).ravel(), min_diag, max_diag)
+    lm = np.sqrt(diag / radius)
+    A = (Js.T @ Js + sp.diags(lm * lm)).tocsc()
+    y = spla.spsolve(A, -(Js.T @ res))
+    Jy = Js @ y
+    model = -float(Jy @ (res + 0.5 * Jy))
+    delta = y * scale
+    cam_step = np.zeros((prob.M, 6)); pt_step = np.zeros((prob.T, 3))
+    cam_step[prob.cam_active] = delta[:6 * prob.nc].reshape(prob.nc, 6)
+    pt_step[prob.tv] = delta[6 * prob.nc:].reshape(prob.npt, 3)
+    out = dict(cost=cost, model=model, cam_step=cam_step, pt_step=pt_step, scale=scale, y=y)
+    if prob.ncols <= 6000:
+        out["S"], out["rhs"] = schur_system(Js, res, lm, prob.nc)
+        out["S_nodamp"] = out["S"] - np.diag((lm * lm)[:6 * prob.nc])
+    return out
