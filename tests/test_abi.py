@@ -1,0 +1,74 @@
+"""No-GPU checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, exports every
+symbol include/lvba_b200.h declares, and refuses to compute without a CUDA device (no CPU fallback)."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _declared():
+    txt = (ROOT / "include" / "lvba_b200.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(lvba_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_header_symbols_are_exported(pkg):
+    lib = pkg.load_library()
+    names = _declared()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(pkg.EXPORTS) == names
+
+
+def test_library_is_sm100a_only(pkg):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", str(pkg.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert not re.search(r"sm_(?!100a)\d+", out)
+
+
+def test_version_and_strings(pkg):
+    lib = pkg.load_library()
+    assert lib.lvba_version() == 100
+    assert lib.lvba_status_string(-2).decode().startswith("no CUDA device")
+    o = pkg.lidar_default_opts()
+    assert (o.u0, o.v0, o.max_iter, o.rel_tol) == (0.01, 2.0, 10, 1e-6)       # bavoxel.hpp:664,686,760
+    v = pkg.visual_default_opts()
+    assert (v.max_iter, v.initial_radius, v.min_relative_decrease) == (50, 1e4, 1e-3)
+
+
+def test_no_cpu_fallback(pkg, problem_small):
+    """On a box without a GPU every compute entry point must fail loudly, never compute on the CPU."""
+    if pkg.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    p = problem_small
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.lidar_lm(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"])
+    assert e.value.status == -2
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.visual_lm(p["q"], p["t"], p["X"], p["plane_nd"], p["obs_ptr"], p["obs_cam"], p["obs_uv"], p["intr"], 0.5, 0.01)
+    assert e.value.status == -2
+
+
+def test_argument_validation_happens_before_device_use(pkg, problem_small):
+    p = problem_small
+    bad = p["pose_idx"].copy(); bad[0] = -1
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.lidar_lm(p["vox_ptr"], bad, p["clusters"], p["poses"])
+    assert e.value.status == -1
+    poses_before = p["poses"].copy()
+    assert np.array_equal(p["poses"], poses_before)          # in/out buffer untouched on error
+
+
+def test_shard_owner_rule(pkg):
+    """Contiguous pose-block rows: rows [p*n/P, (p+1)*n/P) -> rank p."""
+    for n, P in ((10, 3), (5000, 8), (7, 7), (3, 8)):
+        owners = [pkg.shard_owner(i, n, P) for i in range(n)]
+        assert owners == sorted(owners) and (n < P or owners[0] == 0) and max(owners) <= P - 1
+        for r in range(P):
+            rows = [i for i in range(n) if owners[i] == r]
+            assert rows == list(range(r * n // P, (r + 1) * n // P))
