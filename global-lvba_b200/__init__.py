@@ -29,11 +29,11 @@ EXPORTS = [
     "lvba_lidar_default_opts", "lvba_visual_default_opts",
     "lvba_lidar_lm", "lvba_lidar_create", "lvba_lidar_destroy", "lvba_lidar_set_poses",
     "lvba_lidar_get_poses", "lvba_lidar_build", "lvba_lidar_residual", "lvba_lidar_solve",
-    "lvba_lidar_structure", "lvba_lidar_get_system", "lvba_lidar_reset_lm", "lvba_lidar_iterate",
+    "lvba_lidar_structure", "lvba_lidar_get_system", "lvba_lidar_reset_lm", "lvba_lidar_reset_state", "lvba_lidar_iterate",
     "lvba_lidar_counts",
     "lvba_visual_lm", "lvba_visual_create", "lvba_visual_destroy", "lvba_visual_set_state",
     "lvba_visual_get_state", "lvba_visual_cost", "lvba_visual_step", "lvba_visual_structure",
-    "lvba_visual_get_system", "lvba_visual_reset_lm", "lvba_visual_iterate", "lvba_visual_counts",
+    "lvba_visual_get_system", "lvba_visual_reset_lm", "lvba_visual_reset_state", "lvba_visual_iterate", "lvba_visual_counts",
     "lvba_comm_unique_id", "lvba_comm_init", "lvba_comm_destroy", "lvba_comm_info", "lvba_shard_owner",
 ]
 
@@ -203,6 +203,9 @@ class LidarProblem:
     def reset_lm(self, opts=None):
         _chk(self._lib.lvba_lidar_reset_lm(self._h, C.byref(opts) if opts is not None else None))
 
+    def reset_state(self):
+        _chk(self._lib.lvba_lidar_reset_state(self._h))
+
     def iterate(self, n):
         s = Summary(); _chk(self._lib.lvba_lidar_iterate(self._h, C.c_int32(n), C.byref(s))); return s.as_dict()
 
@@ -296,6 +299,9 @@ class VisualProblem:
 
     def reset_lm(self, opts=None):
         _chk(self._lib.lvba_visual_reset_lm(self._h, C.byref(opts) if opts is not None else None))
+
+    def reset_state(self):
+        _chk(self._lib.lvba_visual_reset_state(self._h))
 
     def iterate(self, n):
         s = Summary(); _chk(self._lib.lvba_visual_iterate(self._h, C.c_int32(n), C.byref(s))); return s.as_dict()

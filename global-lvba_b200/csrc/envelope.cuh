@@ -205,4 +205,300 @@ env_backsolve_kernel(EnvView e, const double* __restrict__ L, const double* __re
   }
 }
 
+
+// =====================================================================================================
+// v2: register-resident sliding-window factorisation for envelopes whose column height is < P (P <= 32).
+//
+// The trailing window of a banded LDL^T holds P(P+1)/2 live 6x6 blocks (rows/cols k..k+P-1).  A 6x6x6
+// block update costs 216 DFMA but would move 144 doubles if the target lived in shared memory or L2, so
+// one SM's shared-memory (128 B/clk) and L2 bandwidth cap the step at ~2x the FP64 time.  Here every
+// live block lives in the REGISTERS of one thread for its whole life:
+//   * thread t <-> unordered slot pair {a,b}, a >= b, a,b in [0,P): at step k it owns block (i,j) with
+//     {i mod P, j mod P} = {a,b} and k <= j <= i < k+P.  Exactly one of (a,b)/(b,a) is live at a time, and
+//     when column k retires, block (i,k)'s registers are re-used for the entering block (k+P, i);
+//   * per step:  P1a column threads publish A_ik (transposed) to shared memory and load their entering
+//                block from global (its latency hides under P3);
+//                P1b four warps form L_ik = A_ik D_k^-1, store it to global + shared;
+//                P3  every trailing thread does C -= L_i T_j^T from shared-memory operands (LDS.128,
+//                one operand broadcast per warp), while a dedicated pivot warp looks ahead: it finishes
+//                block (k+1,k+1), inverts it (Gauss-Jordan, no pivoting), applies the fused forward
+//                substitution z_i -= L_ik z_k and fetches the row metadata of the next entering row.
+//   Three block barriers per pivot column; no global-memory round trip on the critical path.
+template <int P>
+struct RegCfg {
+  static constexpr int kPairs = P * (P + 1) / 2;
+  static constexpr int kPairWarps = (kPairs + 31) / 32;
+  static constexpr int kThreads = kPairWarps * 32 + 32;          // + the pivot warp
+  static constexpr int kScaleThreads = (kPairWarps < 4 ? kPairWarps : 4) * 32;
+  static constexpr int kStride = 38;                             // doubles per transposed block in smem (16B aligned, conflict-free)
+};
+
+LVBA_DEV void warp_gj_inverse36(double* K, int lane, int& bad) {
+  // in-place Gauss-Jordan without pivoting on K (36 doubles in shared memory), one warp
+  const int e0 = lane, e1 = 32 + lane;
+  const int r0 = e0 / 6, c0 = e0 % 6, r1 = (e1 < 36) ? e1 / 6 : 0, c1 = (e1 < 36) ? e1 % 6 : 0;
+  // mirror the lower triangle (the reference's SimplicialLDLT reads only the lower triangle)
+  const double m0 = (r0 >= c0) ? K[e0] : K[c0 * 6 + r0];
+  const double m1 = (e1 < 36) ? ((r1 >= c1) ? K[e1] : K[c1 * 6 + r1]) : 0.0;
+  __syncwarp();
+  K[e0] = m0;
+  if (e1 < 36) K[e1] = m1;
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    const double ip = 1.0 / K[p * 7];
+    const double x0 = K[e0], xr0 = K[r0 * 6 + p], xc0 = K[p * 6 + c0];
+    const double x1 = (e1 < 36) ? K[e1] : 0.0, xr1 = K[r1 * 6 + p], xc1 = K[p * 6 + c1];
+    __syncwarp();
+    double n0, n1;
+    if (r0 == p && c0 == p) n0 = ip; else if (r0 == p) n0 = xc0 * ip; else if (c0 == p) n0 = -xr0 * ip; else n0 = x0 - xr0 * xc0 * ip;
+    if (r1 == p && c1 == p) n1 = ip; else if (r1 == p) n1 = xc1 * ip; else if (c1 == p) n1 = -xr1 * ip; else n1 = x1 - xr1 * xc1 * ip;
+    K[e0] = n0;
+    if (e1 < 36) K[e1] = n1;
+    __syncwarp();
+  }
+  const double chk = K[lane] + ((lane < 4) ? K[32 + lane] : 0.0);
+  if (!isfinite(chk)) bad = 1;
+}
+
+template <int P>
+__global__ void __launch_bounds__(RegCfg<P>::kThreads, 1) __maxnreg__(P == 32 ? 112 : 160)
+env_factor_reg_kernel(EnvView e, double* __restrict__ L, double* __restrict__ dinv, double* __restrict__ z,
+                      int* __restrict__ status) {
+  using Cfg = RegCfg<P>;
+  constexpr int S = Cfg::kStride;
+  __shared__ __align__(16) double sTt[P * S];   // A_ik transposed: [slot][q*6 + a] = A[a][q]
+  __shared__ __align__(16) double sLt[P * S];   // L_ik transposed
+  __shared__ double sK[2][36];                  // D_k^-1 (parity k&1)
+  __shared__ double sDg[2][36];                 // diagonal block handed to the look-ahead (parity of its row)
+  __shared__ double sZ[P * 6];                  // forward-substitution window of z, by row slot
+  __shared__ long long sRS[P];                  // row_start of the row living in each slot
+  __shared__ int sFirst[P];                     // first    "
+  __shared__ int sNk[2];                        // last[k]-k (parity k&1)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_pair = tid < Cfg::kPairs;
+  const bool is_pivot_warp = warp == Cfg::kPairWarps;
+  const int n = e.n;
+  int a = 0, b = 0;
+  if (is_pair) tri_decode(tid, a, b);           // a >= b
+  double C[36];
+  int bad = 0;
+
+  auto load_block = [&](int r, int col, int slot) {
+    if (r < n && col >= sFirst[slot]) {
+      const double2* src = reinterpret_cast<const double2*>(L + (sRS[slot] + (col - sFirst[slot])) * 36);
+#pragma unroll
+      for (int q = 0; q < 18; ++q) { const double2 v = src[q]; C[2 * q] = v.x; C[2 * q + 1] = v.y; }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 36; ++q) C[q] = 0.0;
+    }
+  };
+
+  // ---------------- prologue: rows 0..P-1
+  for (int r = tid; r < P; r += Cfg::kThreads) {
+    if (r < n) { sFirst[r] = e.first[r]; sRS[r] = e.row_start[r]; }
+    else { sFirst[r] = 0x7fffffff; sRS[r] = 0; }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) sZ[r * 6 + q] = (r < n) ? z[6 * r + q] : 0.0;
+  }
+  __syncthreads();
+  if (is_pair) load_block(a, b, a);
+  __syncthreads();
+  if (is_pivot_warp) {
+    // D_0^-1 ; A_11 for the first look-ahead ; n_0 ; slot 0 <- row P
+    const long long b0 = sRS[0] * 36;             // block (0,0) is the first block of row 0
+    sK[0][lane] = L[b0 + lane];
+    if (lane < 4) sK[0][32 + lane] = L[b0 + 32 + lane];
+    if (n > 1) {
+      const long long b1 = (sRS[1] + (1 - sFirst[1])) * 36;
+      sDg[1][lane] = L[b1 + lane];
+      if (lane < 4) sDg[1][32 + lane] = L[b1 + 32 + lane];
+    }
+    __syncwarp();
+    warp_gj_inverse36(sK[0], lane, bad);
+    dinv[lane] = sK[0][lane];
+    if (lane < 4) dinv[32 + lane] = sK[0][32 + lane];
+    if (lane == 0) {
+      sNk[0] = e.last[0];
+      if (P < n) { sFirst[0] = e.first[P]; sRS[0] = e.row_start[P]; } else { sFirst[0] = 0x7fffffff; sRS[0] = 0; }
+    }
+  }
+  __syncthreads();
+
+  int c = 0;                                     // k mod P
+  for (int k = 0; k < n; ++k) {
+    const int nk = sNk[k & 1];
+    int da = a - c; if (da < 0) da += P;
+    int db = b - c; if (db < 0) db += P;
+    const int hi = da > db ? da : db, lo = da > db ? db : da;
+    const int islot = da >= db ? a : b, jslot = da >= db ? b : a;     // slots of the block's row / column
+    // ---- P1a: publish the pivot column, fetch entering blocks
+    if (is_pair && lo == 0) {
+      if (hi >= 1 && hi <= nk) {
+        double* dst = sTt + islot * S;
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+#pragma unroll
+          for (int x = 0; x < 6; ++x) dst[q * 6 + x] = C[x * 6 + q];
+      }
+      load_block(k + P, (hi == 0) ? k + P : k + hi, c);
+    }
+    __syncthreads();
+    // ---- P1b: L_ik = A_ik D_k^-1
+    if (tid < Cfg::kScaleThreads) {
+      const double* K = sK[k & 1];
+      for (int o = tid; o < nk * 36; o += Cfg::kScaleThreads) {
+        const int h = 1 + o / 36, el = o - (h - 1) * 36, x = el / 6, cc = el - x * 6;
+        int slot = c + h; if (slot >= P) slot -= P;
+        const double* t = sTt + slot * S;
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) v += t[q * 6 + x] * K[q * 6 + cc];
+        sLt[slot * S + cc * 6 + x] = v;
+        L[(sRS[slot] + (k - sFirst[slot])) * 36 + el] = v;
+      }
+    }
+    __syncthreads();
+    // ---- P3: trailing update (pair threads) | look-ahead (pivot warp)
+    if (is_pair) {
+      if (lo >= 1 && hi <= nk) {
+        const double2* lp = reinterpret_cast<const double2*>(sLt + islot * S);
+        const double2* tp = reinterpret_cast<const double2*>(sTt + jslot * S);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const double2 l0 = lp[3 * q], l1 = lp[3 * q + 1], l2 = lp[3 * q + 2];
+          const double2 t0 = tp[3 * q], t1 = tp[3 * q + 1], t2 = tp[3 * q + 2];
+          const double lv[6] = {l0.x, l0.y, l1.x, l1.y, l2.x, l2.y};
+          const double tv[6] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y};
+#pragma unroll
+          for (int x = 0; x < 6; ++x)
+#pragma unroll
+            for (int y = 0; y < 6; ++y) C[x * 6 + y] -= lv[x] * tv[y];
+        }
+      }
+      if (da == 2 % P && db == 2 % P) {            // block (k+2,k+2): hand it to the look-ahead of step k+1
+        double* dst = sDg[(k + 2) & 1];
+#pragma unroll
+        for (int q = 0; q < 36; ++q) dst[q] = C[q];
+      }
+    } else if (is_pivot_warp) {
+      // forward substitution with the final z_k
+      double zk[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) zk[q] = sZ[c * 6 + q];
+      if (lane < 6) z[6 * (long long)k + lane] = sZ[c * 6 + lane];
+      for (int o = lane; o < nk * 6; o += 32) {
+        const int h = 1 + o / 6, x = o - (h - 1) * 6;
+        int slot = c + h; if (slot >= P) slot -= P;
+        const double* lt = sLt + slot * S;
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) v += lt[q * 6 + x] * zk[q];
+        sZ[slot * 6 + x] -= v;
+      }
+      __syncwarp();
+      if (lane < 6) sZ[c * 6 + lane] = (k + P < n) ? z[6 * (long long)(k + P) + lane] : 0.0;
+      // look-ahead: D_{k+1} = A_{k+1,k+1} - L_{k+1,k} T_{k+1,k}^T, then invert
+      if (k + 1 < n) {
+        double* Kn = sK[(k + 1) & 1];
+        const double* dg = sDg[(k + 1) & 1];
+        int s1 = c + 1; if (s1 >= P) s1 -= P;
+        const double* lt = sLt + s1 * S;
+        const double* tt = sTt + s1 * S;
+        const int e0 = lane, e1 = 32 + lane;
+        double v0 = dg[e0], v1 = (e1 < 36) ? dg[e1] : 0.0;
+        if (nk >= 1) {
+          const int x0 = e0 / 6, y0 = e0 % 6, x1 = (e1 < 36) ? e1 / 6 : 0, y1 = (e1 < 36) ? e1 % 6 : 0;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) { v0 -= lt[q * 6 + x0] * tt[q * 6 + y0]; v1 -= lt[q * 6 + x1] * tt[q * 6 + y1]; }
+        }
+        Kn[e0] = v0;
+        if (e1 < 36) Kn[e1] = v1;
+        __syncwarp();
+        warp_gj_inverse36(Kn, lane, bad);
+        dinv[(long long)(k + 1) * 36 + lane] = Kn[lane];
+        if (lane < 4) dinv[(long long)(k + 1) * 36 + 32 + lane] = Kn[32 + lane];
+        if (lane == 0) {
+          sNk[(k + 1) & 1] = e.last[k + 1] - (k + 1);
+          const int r = k + 1 + P;
+          if (r < n) { sFirst[s1] = e.first[r]; sRS[s1] = e.row_start[r]; } else { sFirst[s1] = 0x7fffffff; sRS[s1] = 0; }
+        }
+      }
+    }
+    __syncthreads();
+    if (++c == P) c = 0;
+  }
+  if (bad) status[0] = 1;
+}
+
+// x = D^-1 z  (block diagonal solve, fully parallel)
+__global__ void env_dinv_apply_kernel(int n, const double* __restrict__ dinv, const double* __restrict__ z, double* __restrict__ x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 6 * n) return;
+  const int k = i / 6, r = i - 6 * k;
+  const double* K = dinv + (long long)k * 36 + r * 6;
+  const double* zz = z + 6 * (long long)k;
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) s += K[q] * zz[q];
+  x[i] = s;
+}
+
+// Backward substitution x <- L^-T x, row oriented: once x_i is final, row i of L (contiguous in the
+// envelope) updates every pending x_j, j in [first[i], i).  One warp; the next row's blocks are
+// prefetched into registers while the current row is applied.  Requires row length < 32 blocks.
+__global__ void __launch_bounds__(32, 1)
+env_backsolve_row_kernel(EnvView e, const double* __restrict__ L, double* __restrict__ x) {
+  constexpr int W = 32;
+  __shared__ double sX[W * 6];
+  const int lane = threadIdx.x, n = e.n;
+  // window rows (i-W, i]; slot = row % W
+  for (int r = n - 1 - lane; r >= 0 && r > n - 1 - W; r -= 32)
+#pragma unroll
+    for (int q = 0; q < 6; ++q) sX[(r % W) * 6 + q] = x[6 * (long long)r + q];
+  __syncwarp();
+  double cur[36], nxt[36];
+  auto fetch = [&](int i, double* buf) {
+    if (i < 0) return;
+    const int f = e.first[i], cnt = i - f;
+    const double* row = L + e.row_start[i] * 36;
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+      const int o = lane + 32 * m;
+      if (o < cnt * 6) {
+        const int jr = o / 6, cc = o - jr * 6;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) buf[m * 6 + q] = row[jr * 36 + q * 6 + cc];
+      }
+    }
+  };
+  fetch(n - 1, cur);
+  for (int i = n - 1; i >= 0; --i) {
+    fetch(i - 1, nxt);
+    const int f = e.first[i], cnt = i - f;
+    double xi[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) xi[q] = sX[(i % W) * 6 + q];
+    if (lane < 6) x[6 * (long long)i + lane] = sX[(i % W) * 6 + lane];
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+      const int o = lane + 32 * m;
+      if (o < cnt * 6) {
+        const int jr = o / 6, cc = o - jr * 6;
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) v += cur[m * 6 + q] * xi[q];
+        sX[((f + jr) % W) * 6 + cc] -= v;
+      }
+    }
+    // entering row i-W takes the slot row i just left
+    if (lane < 6 && i - W >= 0) sX[(i % W) * 6 + lane] = x[6 * (long long)(i - W) + lane];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 36; ++q) cur[q] = nxt[q];
+  }
+}
+
 }  // namespace lvba

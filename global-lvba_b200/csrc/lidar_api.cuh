@@ -35,7 +35,7 @@ struct lvba_lidar_problem {
   lvba::DevBuf<int> pidx, vox_ptr, batch_vox;
   lvba::DevBuf<long long> batch_pair;
   lvba::DevBuf<unsigned> pairs;
-  lvba::DevBuf<double> poses, trial, H, g, diag, dadd, dx, batch_res, scal;
+  lvba::DevBuf<double> poses, poses0, trial, H, g, diag, dadd, dx, batch_res, scal;
   lvba::Envelope env;
   lvba::EnvSolver solver;
   lvba::PhaseTimers timers;
@@ -196,6 +196,7 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   LVBA_TRY(P->batch_pair.upload(batch_pair, s, &P->h2d));
   if (np > 0) LVBA_TRY(P->pairs.upload(pairs, s, &P->h2d));
   LVBA_TRY(P->poses.upload(poses, (size_t)W * 12, s, &P->h2d));
+  LVBA_TRY(P->poses0.upload(poses, (size_t)W * 12, s));
   LVBA_TRY(P->trial.alloc((size_t)W * 12));
   LVBA_TRY(P->H.alloc((size_t)P->env.nblocks * 36));
   LVBA_TRY(P->g.alloc((size_t)W * 6));
@@ -438,6 +439,13 @@ int lvba_lidar_reset_lm(lvba_lidar_problem* p, const lvba_lidar_opts* opts) {
   if (opts) p->opts = *opts; else lvba_lidar_default_opts(&p->opts);
   p->u = p->opts.u0; p->v = p->opts.v0; p->is_calc_hess = true; p->have_first = false; p->converged = false;
   p->iters = p->accepted = p->builds = 0; p->termination = LVBA_TERM_MAX_ITER; p->residual1 = 0.0;
+  return LVBA_OK;
+}
+
+int lvba_lidar_reset_state(lvba_lidar_problem* p) {
+  if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  LVBA_CUDA(cudaSetDevice(p->device));
+  LVBA_CUDA(cudaMemcpyAsync(p->poses.p, p->poses0.p, (size_t)p->W * 12 * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
   return LVBA_OK;
 }
 

@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -164,9 +165,14 @@ struct EnvSolver {
   DevBuf<double> L, dinv, z;
   DevBuf<int> status;
   bool configured = false;
+  bool force_generic = false;   // tests: exercise the wide-envelope kernel on narrow problems
   int prepare(const Envelope& env) {
     if (env.max_col > kEnvMaxCol)
       return fail(LVBA_ERR_UNSUPPORTED, "envelope column height %d exceeds the factor kernel limit %d", env.max_col, kEnvMaxCol);
+    {
+      const char* fg = getenv("LVBA_FORCE_GENERIC_SOLVER");      // tests: run the wide-envelope kernel on narrow problems
+      force_generic = fg && fg[0] == '1';
+    }
     LVBA_TRY(L.alloc((size_t)env.nblocks * 36));
     LVBA_TRY(dinv.alloc((size_t)env.n * 36));
     LVBA_TRY(z.alloc((size_t)env.n * 6));
@@ -185,9 +191,23 @@ struct EnvSolver {
     LVBA_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), s));
     const int n6 = 6 * env.n;
     env_add_diag_kernel<<<(n6 + 255) / 256, 256, 0, s>>>(v, dadd, L.p);
-    env_factor_kernel<<<1, kFactorThreads, factor_smem(), s>>>(v, L.p, dinv.p, z.p, status.p);
-    env_backsolve_kernel<<<1, 32, 0, s>>>(v, L.p, dinv.p, z.p, x);
-    *launches += 3;
+    ++*launches;
+    // column height < P: register-resident sliding-window kernel (envelope.cuh v2); wider: global-memory kernel
+    const int mc = env.max_col;
+    const bool reg_path = mc < 32 && env.n >= 3 && !force_generic;
+    if (reg_path) {
+      if (mc < 8) env_factor_reg_kernel<8><<<1, RegCfg<8>::kThreads, 0, s>>>(v, L.p, dinv.p, z.p, status.p);
+      else if (mc < 16) env_factor_reg_kernel<16><<<1, RegCfg<16>::kThreads, 0, s>>>(v, L.p, dinv.p, z.p, status.p);
+      else if (mc < 24) env_factor_reg_kernel<24><<<1, RegCfg<24>::kThreads, 0, s>>>(v, L.p, dinv.p, z.p, status.p);
+      else env_factor_reg_kernel<32><<<1, RegCfg<32>::kThreads, 0, s>>>(v, L.p, dinv.p, z.p, status.p);
+      env_dinv_apply_kernel<<<(n6 + 127) / 128, 128, 0, s>>>(env.n, dinv.p, z.p, x);
+      env_backsolve_row_kernel<<<1, 32, 0, s>>>(v, L.p, x);
+      *launches += 3;
+    } else {
+      env_factor_kernel<<<1, kFactorThreads, factor_smem(), s>>>(v, L.p, dinv.p, z.p, status.p);
+      env_backsolve_kernel<<<1, 32, 0, s>>>(v, L.p, dinv.p, z.p, x);
+      *launches += 2;
+    }
     LVBA_CUDA(cudaGetLastError());
     return LVBA_OK;
   }

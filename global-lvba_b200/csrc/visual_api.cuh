@@ -23,6 +23,7 @@ struct lvba_visual_problem {
   lvba::DevBuf<float2> obs_uv;
   lvba::DevBuf<double> plane;
   lvba::DevBuf<double> q, t, X, qc, tc, Xc;         // state and candidate
+  lvba::DevBuf<double> q0, t0, X0;                  // state given at create (lvba_visual_reset_state)
   lvba::DevBuf<double> S, rhs, y, dadd, cam_colsq, cam_grad, s_cam, s_pt, pt_colsq;
   lvba::DevBuf<double> batch_cost, batch_gmax, batch_out, cam_out, scal, cam_step, pt_step;
   lvba::Envelope env;
@@ -210,6 +211,7 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   LVBA_TRY(P->q.upload(q, (size_t)M * 4, s, &P->h2d));
   LVBA_TRY(P->t.upload(t, (size_t)M * 3, s, &P->h2d));
   LVBA_TRY(P->X.upload(X, (size_t)T * 3, s, &P->h2d));
+  LVBA_TRY(P->q0.upload(q, (size_t)M * 4, s)); LVBA_TRY(P->t0.upload(t, (size_t)M * 3, s)); LVBA_TRY(P->X0.upload(X, (size_t)T * 3, s));
   LVBA_TRY(P->qc.upload(q, (size_t)M * 4, s));
   LVBA_TRY(P->tc.upload(t, (size_t)M * 3, s));
   LVBA_TRY(P->Xc.upload(X, (size_t)T * 3, s));
@@ -493,6 +495,17 @@ int lvba_visual_reset_lm(lvba_visual_problem* p, const lvba_visual_opts* opts) {
   if (opts) p->opts = *opts; else lvba_visual_default_opts(&p->opts);
   p->radius = p->opts.initial_radius; p->nu = 2.0; p->have_scale = false; p->have_first = false; p->converged = false;
   p->iters = p->accepted = p->builds = p->invalid = 0; p->termination = LVBA_TERM_MAX_ITER;
+  return LVBA_OK;
+}
+
+int lvba_visual_reset_state(lvba_visual_problem* p) {
+  if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  LVBA_CUDA(cudaSetDevice(p->device));
+  cudaStream_t s = p->stream;
+  const size_t nq = (size_t)p->M * 4 * sizeof(double), nt = (size_t)p->M * 3 * sizeof(double), nx = (size_t)p->T * 3 * sizeof(double);
+  LVBA_CUDA(cudaMemcpyAsync(p->q.p, p->q0.p, nq, cudaMemcpyDeviceToDevice, s)); LVBA_CUDA(cudaMemcpyAsync(p->qc.p, p->q0.p, nq, cudaMemcpyDeviceToDevice, s));
+  LVBA_CUDA(cudaMemcpyAsync(p->t.p, p->t0.p, nt, cudaMemcpyDeviceToDevice, s)); LVBA_CUDA(cudaMemcpyAsync(p->tc.p, p->t0.p, nt, cudaMemcpyDeviceToDevice, s));
+  if (nx) { LVBA_CUDA(cudaMemcpyAsync(p->X.p, p->X0.p, nx, cudaMemcpyDeviceToDevice, s)); LVBA_CUDA(cudaMemcpyAsync(p->Xc.p, p->X0.p, nx, cudaMemcpyDeviceToDevice, s)); }
   return LVBA_OK;
 }
 

@@ -143,6 +143,8 @@ int lvba_lidar_get_system(lvba_lidar_problem* p, double* g, double* blocks);
 /* n LM passes of damping_iter starting from the handle's state (u, v, poses carried in the
  * handle; call lvba_lidar_reset_lm to restart).  Device-resident: no problem data crosses PCIe. */
 int lvba_lidar_reset_lm(lvba_lidar_problem* p, const lvba_lidar_opts* opts);
+/* restore the poses passed to lvba_lidar_create (device-to-device; nothing crosses PCIe) */
+int lvba_lidar_reset_state(lvba_lidar_problem* p);
 int lvba_lidar_iterate(lvba_lidar_problem* p, int32_t n_iter, lvba_summary* summary);
 /* exact algorithmic byte / flop counters of SURVEY.md §8(d) for this problem instance */
 int lvba_lidar_counts(lvba_lidar_problem* p, int64_t* nnz, int64_t* n_blocks_env,
@@ -187,6 +189,8 @@ int lvba_visual_structure(lvba_visual_problem* p, int32_t* n_active, int32_t* ca
                           int64_t* nblocks, int32_t* brow, int32_t* bcol);
 int lvba_visual_get_system(lvba_visual_problem* p, double* rhs /* [n_active*6] */, double* blocks /* [nblocks*36] */);
 int lvba_visual_reset_lm(lvba_visual_problem* p, const lvba_visual_opts* opts);
+/* restore q, t, X passed to lvba_visual_create (device-to-device) */
+int lvba_visual_reset_state(lvba_visual_problem* p);
 int lvba_visual_iterate(lvba_visual_problem* p, int32_t n_iter, lvba_summary* summary);
 int lvba_visual_counts(lvba_visual_problem* p, int64_t* nnz_valid, int64_t* n_valid_tracks,
                        int64_t* n_blocks_env, int64_t* n_pairs);
