@@ -227,11 +227,19 @@ env_backsolve_kernel(EnvView e, const double* __restrict__ L, const double* __re
 template <int P>
 struct RegCfg {
   static constexpr int kPairs = P * (P + 1) / 2;
-  static constexpr int kPairWarps = (kPairs + 31) / 32;
-  static constexpr int kThreads = kPairWarps * 32 + 32;          // + the pivot warp
-  static constexpr int kScaleThreads = (kPairWarps < 4 ? kPairWarps : 4) * 32;
+  static constexpr int kPairGroups = (kPairs + 127) / 128;       // warpgroups (4 warps) of pair threads
+  static constexpr int kPairThreads = kPairGroups * 128;
+  static constexpr int kThreads = kPairThreads + 128;            // + one look-ahead warpgroup
   static constexpr int kStride = 38;                             // doubles per transposed block in smem (16B aligned, conflict-free)
+  // register re-allocation (setmaxnreg): only needed when 5 warps share an SMSP (P = 31)
+  static constexpr bool kRealloc = kThreads > 512;
+  static constexpr int kPairRegs = 104, kAheadRegs = 56;   // 512*104 + 128*56 <= 640*96 (the CTA pool only holds what the CTA owns)
+  static constexpr size_t kSmem = sizeof(double) * (size_t)(2 * P * kStride + P * kStride + 2 * P * 36 + 2 * 36 + 2 * 36 + P * 6) +
+                                  sizeof(long long) * P + sizeof(int) * (P + 4) + 32;
 };
+
+template <int N> LVBA_DEV void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(N)); }
+template <int N> LVBA_DEV void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N)); }
 
 LVBA_DEV void warp_gj_inverse36(double* K, int lane, int& bad) {
   // in-place Gauss-Jordan without pivoting on K (36 doubles in shared memory), one warp
@@ -261,175 +269,299 @@ LVBA_DEV void warp_gj_inverse36(double* K, int lane, int& bad) {
   if (!isfinite(chk)) bad = 1;
 }
 
-template <int P>
-__global__ void __launch_bounds__(RegCfg<P>::kThreads, 1) __maxnreg__(P == 32 ? 112 : 160)
-env_factor_reg_kernel(EnvView e, double* __restrict__ L, double* __restrict__ dinv, double* __restrict__ z,
-                      int* __restrict__ status) {
-  using Cfg = RegCfg<P>;
-  constexpr int S = Cfg::kStride;
-  __shared__ __align__(16) double sTt[P * S];   // A_ik transposed: [slot][q*6 + a] = A[a][q]
-  __shared__ __align__(16) double sLt[P * S];   // L_ik transposed
-  __shared__ double sK[2][36];                  // D_k^-1 (parity k&1)
-  __shared__ double sDg[2][36];                 // diagonal block handed to the look-ahead (parity of its row)
-  __shared__ double sZ[P * 6];                  // forward-substitution window of z, by row slot
-  __shared__ long long sRS[P];                  // row_start of the row living in each slot
-  __shared__ int sFirst[P];                     // first    "
-  __shared__ int sNk[2];                        // last[k]-k (parity k&1)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool is_pair = tid < Cfg::kPairs;
-  const bool is_pivot_warp = warp == Cfg::kPairWarps;
-  const int n = e.n;
-  int a = 0, b = 0;
-  if (is_pair) tri_decode(tid, a, b);           // a >= b
-  double C[36];
-  int bad = 0;
+// 6x6 symmetric inverse by the symmetric sweep operator (Goodnight 1979), no pivoting, entirely in
+// registers + warp shuffles: lane l < 21 owns the lower-triangle element (r,c), l = r(r+1)/2 + c.
+// Sweeping pivot p:  x_pp <- -1/x_pp ; x_ip <- x_ip / x_pp ; x_ij <- x_ij - x_ip x_jp / x_pp.
+// After the six sweeps the matrix holds -A^-1.  The pivots are the d_p of the unpivoted LDL^T that the
+// reference's SimplicialLDLT computes on the same (lower-triangle) data.  Writes K (36, row-major).
+LVBA_DEV void warp_sym_inverse6(const double* Ain /*36, lower triangle read*/, double* K, int lane, int& bad) {
+  const int l = lane < 21 ? lane : 0;
+  const int r = (l >= 15) ? 5 : (l >= 10) ? 4 : (l >= 6) ? 3 : (l >= 3) ? 2 : (l >= 1) ? 1 : 0;
+  const int c = l - r * (r + 1) / 2;
+  double x = Ain[r * 6 + c];
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    const int lpp = p * (p + 1) / 2 + p;
+    const int lrp = (r >= p) ? r * (r + 1) / 2 + p : p * (p + 1) / 2 + r;
+    const int lcp = (c >= p) ? c * (c + 1) / 2 + p : p * (p + 1) / 2 + c;
+    const double d = __shfl_sync(0xffffffffu, x, lpp);
+    const double xrp = __shfl_sync(0xffffffffu, x, lrp);
+    const double xcp = __shfl_sync(0xffffffffu, x, lcp);
+    const double ip = __drcp_rn(d);
+    if (r == p && c == p) x = -ip;
+    else if (c == p) x = xrp * ip;        // (r,p), r > p
+    else if (r == p) x = xcp * ip;        // (p,c), c < p
+    else x = x - xrp * xcp * ip;
+  }
+  if (lane < 21) {
+    const double v = -x;
+    if (!isfinite(v)) bad = 1;
+    K[r * 6 + c] = v;
+    K[c * 6 + r] = v;
+  }
+  __syncwarp();
+}
 
-  auto load_block = [&](int r, int col, int slot) {
-    if (r < n && col >= sFirst[slot]) {
-      const double2* src = reinterpret_cast<const double2*>(L + (sRS[slot] + (col - sFirst[slot])) * 36);
+template <int P>
+__global__ void __launch_bounds__(RegCfg<P>::kThreads, 1)
+env_factor_reg_kernel(EnvView e, double* __restrict__ L, double* __restrict__ dinv, double* __restrict__ z,
+                      int* __restrict__ status, long long* __restrict__ dbg) {
+  using Cfg = RegCfg<P>;
+  // optional phase timing (LVBA_FACTOR_TIMING=1): dbg[(k*8 + role)*4 + stamp], role 0..3 = pair warps 0..3, 4..7 = look-ahead warps
+#define LVBA_STAMP(role, stamp) do { if (dbg && lane == 0) dbg[((long long)k * 8 + (role)) * 4 + (stamp)] = clock64(); } while (0)
+  constexpr int S = Cfg::kStride;
+  extern __shared__ __align__(16) double smem_reg[];
+  double* sTt0 = smem_reg;                       // [2][P][S] A_ik transposed ([q*6+a] = A[a][q]); parity = pivot column & 1
+  double* sLt = sTt0 + 2 * P * S;                // [P][S]    L_ik transposed (current pivot column)
+  double* sEnter0 = sLt + P * S;                 // [2][P][36] entering row, by column slot; parity = retiring column & 1
+  double* sK0 = sEnter0 + 2 * P * 36;            // [2][36]   D_k^-1
+  double* sDg0 = sK0 + 72;                       // [2][36]   diagonal block handed to the look-ahead
+  double* sZ = sDg0 + 72;                        // [P][6]
+  long long* sRS = reinterpret_cast<long long*>(sZ + P * 6);   // [P]
+  int* sFirst = reinterpret_cast<int*>(sRS + P);               // [P]
+  int* sNk = sFirst + P;                                       // [4] ring: sNk[k & 3] = last[k] - k
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n = e.n;
+  const bool is_ahead = tid >= Cfg::kPairThreads;               // look-ahead warpgroup (warp-uniform)
+
+  // shared by both roles: L_ik = A_ik D_k^-1 for rows k+1..k+nk, all threads of the CTA
+  auto scale_column = [&](int k, int c, int nk) {
+    const double* K = sK0 + (k & 1) * 36;
+    const double* tb = sTt0 + (k & 1) * P * S;
+    for (int o = tid; o < nk * 36; o += Cfg::kThreads) {
+      const int h = 1 + o / 36, el = o - (h - 1) * 36, x = el / 6, cc = el - x * 6;
+      int slot = c + h; if (slot >= P) slot -= P;
+      const double* t = tb + slot * S;
+      double v = 0.0;
 #pragma unroll
-      for (int q = 0; q < 18; ++q) { const double2 v = src[q]; C[2 * q] = v.x; C[2 * q + 1] = v.y; }
-    } else {
-#pragma unroll
-      for (int q = 0; q < 36; ++q) C[q] = 0.0;
+      for (int q = 0; q < 6; ++q) v += t[q * 6 + x] * K[q * 6 + cc];
+      sLt[slot * S + cc * 6 + x] = v;
+      L[(sRS[slot] + (k - sFirst[slot])) * 36 + el] = v;
     }
   };
 
-  // ---------------- prologue: rows 0..P-1
+  // ---------------- prologue (all threads, launch register budget)
   for (int r = tid; r < P; r += Cfg::kThreads) {
-    if (r < n) { sFirst[r] = e.first[r]; sRS[r] = e.row_start[r]; }
-    else { sFirst[r] = 0x7fffffff; sRS[r] = 0; }
+    if (r < n) { sFirst[r] = e.first[r]; sRS[r] = e.row_start[r]; } else { sFirst[r] = 0x7fffffff; sRS[r] = 0; }
 #pragma unroll
     for (int q = 0; q < 6; ++q) sZ[r * 6 + q] = (r < n) ? z[6 * r + q] : 0.0;
   }
-  __syncthreads();
-  if (is_pair) load_block(a, b, a);
-  __syncthreads();
-  if (is_pivot_warp) {
-    // D_0^-1 ; A_11 for the first look-ahead ; n_0 ; slot 0 <- row P
-    const long long b0 = sRS[0] * 36;             // block (0,0) is the first block of row 0
-    sK[0][lane] = L[b0 + lane];
-    if (lane < 4) sK[0][32 + lane] = L[b0 + 32 + lane];
-    if (n > 1) {
-      const long long b1 = (sRS[1] + (1 - sFirst[1])) * 36;
-      sDg[1][lane] = L[b1 + lane];
-      if (lane < 4) sDg[1][32 + lane] = L[b1 + 32 + lane];
-    }
-    __syncwarp();
-    warp_gj_inverse36(sK[0], lane, bad);
-    dinv[lane] = sK[0][lane];
-    if (lane < 4) dinv[32 + lane] = sK[0][32 + lane];
-    if (lane == 0) {
-      sNk[0] = e.last[0];
-      if (P < n) { sFirst[0] = e.first[P]; sRS[0] = e.row_start[P]; } else { sFirst[0] = 0x7fffffff; sRS[0] = 0; }
-    }
-  }
+  if (tid == 0) { sNk[0] = e.last[0]; sNk[1] = (n > 1) ? e.last[1] - 1 : 0; sNk[2] = (n > 2) ? e.last[2] - 2 : 0; sNk[3] = 0; }
   __syncthreads();
 
-  int c = 0;                                     // k mod P
-  for (int k = 0; k < n; ++k) {
-    const int nk = sNk[k & 1];
-    int da = a - c; if (da < 0) da += P;
-    int db = b - c; if (db < 0) db += P;
-    const int hi = da > db ? da : db, lo = da > db ? db : da;
-    const int islot = da >= db ? a : b, jslot = da >= db ? b : a;     // slots of the block's row / column
-    // ---- P1a: publish the pivot column, fetch entering blocks
-    if (is_pair && lo == 0) {
-      if (hi >= 1 && hi <= nk) {
-        double* dst = sTt + islot * S;
+  if (!is_ahead) {
+    // =================================================== pair threads: one live 6x6 block in registers
+    if (Cfg::kRealloc) reg_alloc<Cfg::kPairRegs>();
+    const bool is_pair = tid < Cfg::kPairs;
+    int a = 0, b = 0;
+    if (is_pair) tri_decode(tid, a, b);            // a >= b
+    double C[36];
+    auto publish_T = [&](double* dst) {            // dst[q*6+x] = C[x][q]
 #pragma unroll
-        for (int q = 0; q < 6; ++q)
-#pragma unroll
-          for (int x = 0; x < 6; ++x) dst[q * 6 + x] = C[x * 6 + q];
+      for (int q = 0; q < 6; ++q) {
+        double2* d2 = reinterpret_cast<double2*>(dst + q * 6);
+        d2[0] = make_double2(C[q], C[6 + q]);
+        d2[1] = make_double2(C[12 + q], C[18 + q]);
+        d2[2] = make_double2(C[24 + q], C[30 + q]);
       }
-      load_block(k + P, (hi == 0) ? k + P : k + hi, c);
-    }
-    __syncthreads();
-    // ---- P1b: L_ik = A_ik D_k^-1
-    if (tid < Cfg::kScaleThreads) {
-      const double* K = sK[k & 1];
-      for (int o = tid; o < nk * 36; o += Cfg::kScaleThreads) {
-        const int h = 1 + o / 36, el = o - (h - 1) * 36, x = el / 6, cc = el - x * 6;
-        int slot = c + h; if (slot >= P) slot -= P;
-        const double* t = sTt + slot * S;
-        double v = 0.0;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) v += t[q * 6 + x] * K[q * 6 + cc];
-        sLt[slot * S + cc * 6 + x] = v;
-        L[(sRS[slot] + (k - sFirst[slot])) * 36 + el] = v;
-      }
-    }
-    __syncthreads();
-    // ---- P3: trailing update (pair threads) | look-ahead (pivot warp)
+    };
     if (is_pair) {
-      if (lo >= 1 && hi <= nk) {
-        const double2* lp = reinterpret_cast<const double2*>(sLt + islot * S);
-        const double2* tp = reinterpret_cast<const double2*>(sTt + jslot * S);
+      if (a < n && b >= sFirst[a]) {
+        const double2* src = reinterpret_cast<const double2*>(L + (sRS[a] + (b - sFirst[a])) * 36);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          const double2 l0 = lp[3 * q], l1 = lp[3 * q + 1], l2 = lp[3 * q + 2];
-          const double2 t0 = tp[3 * q], t1 = tp[3 * q + 1], t2 = tp[3 * q + 2];
-          const double lv[6] = {l0.x, l0.y, l1.x, l1.y, l2.x, l2.y};
-          const double tv[6] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y};
+        for (int q = 0; q < 18; ++q) { const double2 v = src[q]; C[2 * q] = v.x; C[2 * q + 1] = v.y; }
+      } else {
 #pragma unroll
-          for (int x = 0; x < 6; ++x)
-#pragma unroll
-            for (int y = 0; y < 6; ++y) C[x * 6 + y] -= lv[x] * tv[y];
-        }
+        for (int q = 0; q < 36; ++q) C[q] = 0.0;
       }
-      if (da == 2 % P && db == 2 % P) {            // block (k+2,k+2): hand it to the look-ahead of step k+1
-        double* dst = sDg[(k + 2) & 1];
+      if (b == 0 && a >= 1) publish_T(sTt0 + a * S);            // column 0
+      if (a == 1 && b == 1) {
 #pragma unroll
-        for (int q = 0; q < 36; ++q) dst[q] = C[q];
+        for (int q = 0; q < 36; ++q) sDg0[36 + q] = C[q];
       }
-    } else if (is_pivot_warp) {
-      // forward substitution with the final z_k
-      double zk[6];
+      if (a == 0 && b == 0) {
 #pragma unroll
-      for (int q = 0; q < 6; ++q) zk[q] = sZ[c * 6 + q];
-      if (lane < 6) z[6 * (long long)k + lane] = sZ[c * 6 + lane];
-      for (int o = lane; o < nk * 6; o += 32) {
-        const int h = 1 + o / 6, x = o - (h - 1) * 6;
-        int slot = c + h; if (slot >= P) slot -= P;
-        const double* lt = sLt + slot * S;
-        double v = 0.0;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) v += lt[q * 6 + x] * zk[q];
-        sZ[slot * 6 + x] -= v;
-      }
-      __syncwarp();
-      if (lane < 6) sZ[c * 6 + lane] = (k + P < n) ? z[6 * (long long)(k + P) + lane] : 0.0;
-      // look-ahead: D_{k+1} = A_{k+1,k+1} - L_{k+1,k} T_{k+1,k}^T, then invert
-      if (k + 1 < n) {
-        double* Kn = sK[(k + 1) & 1];
-        const double* dg = sDg[(k + 1) & 1];
-        int s1 = c + 1; if (s1 >= P) s1 -= P;
-        const double* lt = sLt + s1 * S;
-        const double* tt = sTt + s1 * S;
-        const int e0 = lane, e1 = 32 + lane;
-        double v0 = dg[e0], v1 = (e1 < 36) ? dg[e1] : 0.0;
-        if (nk >= 1) {
-          const int x0 = e0 / 6, y0 = e0 % 6, x1 = (e1 < 36) ? e1 / 6 : 0, y1 = (e1 < 36) ? e1 % 6 : 0;
-#pragma unroll
-          for (int q = 0; q < 6; ++q) { v0 -= lt[q * 6 + x0] * tt[q * 6 + y0]; v1 -= lt[q * 6 + x1] * tt[q * 6 + y1]; }
-        }
-        Kn[e0] = v0;
-        if (e1 < 36) Kn[e1] = v1;
-        __syncwarp();
-        warp_gj_inverse36(Kn, lane, bad);
-        dinv[(long long)(k + 1) * 36 + lane] = Kn[lane];
-        if (lane < 4) dinv[(long long)(k + 1) * 36 + 32 + lane] = Kn[32 + lane];
-        if (lane == 0) {
-          sNk[(k + 1) & 1] = e.last[k + 1] - (k + 1);
-          const int r = k + 1 + P;
-          if (r < n) { sFirst[s1] = e.first[r]; sRS[s1] = e.row_start[r]; } else { sFirst[s1] = 0x7fffffff; sRS[s1] = 0; }
-        }
+        for (int q = 0; q < 36; ++q) sK0[q] = C[q];
       }
     }
-    __syncthreads();
-    if (++c == P) c = 0;
+    __syncthreads();     // (A) column 0 published
+    __syncthreads();     // (B) look-ahead group finished D_0^-1 and the first entering row
+    int c = 0;
+    for (int k = 0; k < n; ++k) {
+      const int cur = k & 1;
+      const int nk = sNk[k & 3];
+      if (tid < 128) LVBA_STAMP(tid >> 5, 0);
+      scale_column(k, c, nk);
+      if (tid < 128) LVBA_STAMP(tid >> 5, 1);
+      __syncthreads();
+      if (tid < 128) LVBA_STAMP(tid >> 5, 2);
+      if (is_pair) {
+        int da = a - c; if (da < 0) da += P;
+        int db = b - c; if (db < 0) db += P;
+        const int hi = da > db ? da : db, lo = da > db ? db : da;
+        const int islot = da >= db ? a : b, jslot = da >= db ? b : a;
+        double* sTn = sTt0 + (cur ^ 1) * P * S;
+        if (lo == 0) {                             // column-k block is dead: take the entering block (k+P, .)
+          const double2* src = reinterpret_cast<const double2*>(sEnter0 + (cur * P + islot) * 36);
+#pragma unroll
+          for (int q = 0; q < 18; ++q) { const double2 v = src[q]; C[2 * q] = v.x; C[2 * q + 1] = v.y; }
+          if (hi == 1) publish_T(sTn + c * S);     // block (k+P, k+1): last row of column k+1
+        } else {
+          if (hi <= nk) {
+            const double2* lp = reinterpret_cast<const double2*>(sLt + islot * S);
+            const double2* tp = reinterpret_cast<const double2*>(sTt0 + (cur * P + jslot) * S);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+              const double2 t0 = tp[3 * q], t1 = tp[3 * q + 1], t2 = tp[3 * q + 2];
+#pragma unroll
+              for (int xx = 0; xx < 3; ++xx) {
+                const double2 l = lp[3 * q + xx];
+                double* c0 = C + (2 * xx) * 6;
+                double* c1 = C + (2 * xx + 1) * 6;
+                c0[0] -= l.x * t0.x; c0[1] -= l.x * t0.y; c0[2] -= l.x * t1.x; c0[3] -= l.x * t1.y; c0[4] -= l.x * t2.x; c0[5] -= l.x * t2.y;
+                c1[0] -= l.y * t0.x; c1[1] -= l.y * t0.y; c1[2] -= l.y * t1.x; c1[3] -= l.y * t1.y; c1[4] -= l.y * t2.x; c1[5] -= l.y * t2.y;
+              }
+            }
+          }
+          if (lo == 1 && hi >= 2) publish_T(sTn + islot * S);    // column k+1, rows k+2..k+P-1
+          if (da == 2 % P && db == 2 % P) {          // block (k+2,k+2) for the look-ahead of step k+1
+#pragma unroll
+            for (int q = 0; q < 36; ++q) sDg0[cur * 36 + q] = C[q];   // (k+2)&1 == k&1
+          }
+        }
+      }
+      if (tid < 128) LVBA_STAMP(tid >> 5, 3);
+      __syncthreads();
+      if (++c == P) c = 0;
+    }
+  } else {
+    // =================================================== look-ahead warpgroup (4 warps, one per SMSP)
+    if (Cfg::kRealloc) reg_dealloc<Cfg::kAheadRegs>();
+    const int aw = (tid - Cfg::kPairThreads) >> 5;              // 0: pivot inverse + metadata, 1: forward substitution, 2,3 (+1): row prefetch
+    const int pl = tid - Cfg::kPairThreads - 32;                // prefetch lane id over warps 1..3 (0..95), negative for warp 0
+    int bad = 0;
+    // entering row kc+P -> registers (issue early) -> sEnter[kc&1] (retire late); 96 lanes, <= 6 double2 each
+    constexpr int kPf = (P * 18 + 95) / 96;
+    __syncthreads();     // (A)
+    // D_0^-1 (warp 0) ; first entering row P (warps 1..3)
+    if (aw == 0) {
+      warp_sym_inverse6(sK0, sK0, lane, bad);
+      dinv[lane] = sK0[lane];
+      if (lane < 4) dinv[32 + lane] = sK0[32 + lane];
+    }
+    {
+      const int rf = (P < n) ? e.first[P] : 0x7fffffff;
+      const long long rrs = (P < n) ? e.row_start[P] : 0;
+      if (pl >= 0)
+        for (int o = pl; o < P * 18; o += 96) {
+          const int cs = o / 18, w = o - cs * 18;
+          int dcol = cs; if (dcol <= 0) dcol += P;                // kc = 0: col = dcol ; cs == 0 <=> col == P
+          double2 v = make_double2(0.0, 0.0);
+          if (P < n && dcol >= rf) v = reinterpret_cast<const double2*>(L + (rrs + (dcol - rf)) * 36)[w];
+          reinterpret_cast<double2*>(sEnter0)[o] = v;
+        }
+      if (aw == 0 && lane == 0) { sFirst[0] = rf; sRS[0] = rrs; }   // slot 0 now describes row P (nobody reads row 0's label any more)
+    }
+    __syncthreads();     // (B)
+    int c = 0;
+    for (int k = 0; k < n; ++k) {
+      const int cur = k & 1;
+      const int nk = sNk[k & 3];
+      LVBA_STAMP(4 + aw, 0);
+      scale_column(k, c, nk);
+      LVBA_STAMP(4 + aw, 1);
+      __syncthreads();
+      LVBA_STAMP(4 + aw, 2);
+      int s1 = c + 1; if (s1 >= P) s1 -= P;
+      if (aw == 0) {
+        // metadata of the entering row k+1+P and n_{k+3}: loads issued first, consumed after the inverse
+        int m_first = 0x7fffffff, m_last = 0; long long m_rs = 0;
+        if (lane == 0) {
+          const int r1 = k + 1 + P;
+          m_first = (r1 < n) ? e.first[r1] : 0x7fffffff;
+          m_rs = (r1 < n) ? e.row_start[r1] : 0;
+          m_last = (k + 3 < n) ? e.last[k + 3] - (k + 3) : 0;
+        }
+        // look-ahead: D_{k+1} = A_{k+1,k+1} - L_{k+1,k} T_{k+1,k}^T, then invert (Gauss-Jordan, no pivoting)
+        if (k + 1 < n) {
+          double* Kn = sK0 + (cur ^ 1) * 36;
+          const double* dg = sDg0 + (cur ^ 1) * 36;
+          const double* lt = sLt + s1 * S;
+          const double* tt = sTt0 + (cur * P + s1) * S;
+          const int e0 = lane, e1 = 32 + lane;
+          double v0 = dg[e0], v1 = (e1 < 36) ? dg[e1] : 0.0;
+          if (nk >= 1) {
+            const int x0 = e0 / 6, y0 = e0 % 6, x1 = (e1 < 36) ? e1 / 6 : 0, y1 = (e1 < 36) ? e1 % 6 : 0;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { v0 -= lt[q * 6 + x0] * tt[q * 6 + y0]; v1 -= lt[q * 6 + x1] * tt[q * 6 + y1]; }
+          }
+          Kn[e0] = v0;
+          if (e1 < 36) Kn[e1] = v1;
+          __syncwarp();
+          warp_sym_inverse6(Kn, Kn, lane, bad);
+          dinv[(long long)(k + 1) * 36 + lane] = Kn[lane];
+          if (lane < 4) dinv[(long long)(k + 1) * 36 + 32 + lane] = Kn[32 + lane];
+        }
+        if (lane == 0) {
+          sFirst[s1] = m_first; sRS[s1] = m_rs;                   // slot of row k+1 now describes row k+1+P
+          sNk[(k + 3) & 3] = m_last;                              // n_{k+3} (slot last used by n_{k-1})
+        }
+      } else {
+        // ---- warps 1..3: stream the row that enters when column k+1 retires (row k+1+P) into sEnter[(k+1)&1]
+        const int kc = k + 1, r = kc + P;
+        // first/row_start are tiny L2-resident arrays: read the entering row's label straight from global
+        const int rf = (r < n) ? e.first[r] : 0x7fffffff;
+        const long long rrs = (r < n) ? e.row_start[r] : 0;
+        double2 buf[kPf];
+#pragma unroll
+        for (int m = 0; m < kPf; ++m) {
+          const int o = pl + 96 * m;
+          double2 v = make_double2(0.0, 0.0);
+          if (o < P * 18) {
+            const int cs = o / 18, w = o - cs * 18;
+            int dcol = cs - s1; if (dcol <= 0) dcol += P;          // col = kc + dcol ; dcol == P <=> col == r
+            const int col = kc + dcol;
+            if (r < n && col >= rf) v = reinterpret_cast<const double2*>(L + (rrs + (col - rf)) * 36)[w];
+          }
+          buf[m] = v;
+        }
+        double zin = 0.0;
+        if (aw == 1 && lane < 6 && k + P < n) zin = z[6 * (long long)(k + P) + lane];
+        if (aw == 1) {
+          // forward substitution with the final z_k : lane <-> row k+1+lane
+          double zk[6];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) zk[q] = sZ[c * 6 + q];
+          if (lane < 6) z[6 * (long long)k + lane] = sZ[c * 6 + lane];
+          for (int h = 1 + lane; h <= nk; h += 32) {
+            int slot = c + h; if (slot >= P) slot -= P;
+            const double* lt = sLt + slot * S;
+            double acc[6];
+#pragma unroll
+            for (int x = 0; x < 6; ++x) acc[x] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+#pragma unroll
+              for (int x = 0; x < 6; ++x) acc[x] += lt[q * 6 + x] * zk[q];
+#pragma unroll
+            for (int x = 0; x < 6; ++x) sZ[slot * 6 + x] -= acc[x];
+          }
+          __syncwarp();
+          if (lane < 6) sZ[c * 6 + lane] = zin;                   // row k+P takes slot c
+        }
+#pragma unroll
+        for (int m = 0; m < kPf; ++m) {
+          const int o = pl + 96 * m;
+          if (o < P * 18) reinterpret_cast<double2*>(sEnter0 + ((kc & 1) * P) * 36)[o] = buf[m];
+        }
+      }
+      LVBA_STAMP(4 + aw, 3);
+      __syncthreads();
+      if (++c == P) c = 0;
+    }
+    if (bad) status[0] = 1;
   }
-  if (bad) status[0] = 1;
 }
 
 // x = D^-1 z  (block diagonal solve, fully parallel)
@@ -445,59 +577,55 @@ __global__ void env_dinv_apply_kernel(int n, const double* __restrict__ dinv, co
   x[i] = s;
 }
 
-// Backward substitution x <- L^-T x, row oriented: once x_i is final, row i of L (contiguous in the
-// envelope) updates every pending x_j, j in [first[i], i).  One warp; the next row's blocks are
-// prefetched into registers while the current row is applied.  Requires row length < 32 blocks.
+// Backward substitution, row oriented, with the rows of L streamed through a 4-deep cp.async ring in
+// shared memory (one warp).  Requires row length (blocks left of the diagonal) <= 31.
+LVBA_DEV void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+LVBA_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> LVBA_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(32, 1)
-env_backsolve_row_kernel(EnvView e, const double* __restrict__ L, double* __restrict__ x) {
-  constexpr int W = 32;
+env_backsolve_ring_kernel(EnvView e, const double* __restrict__ L, double* __restrict__ x) {
+  constexpr int W = 32, D = 4, ROWMAX = 31 * 36;
+  __shared__ __align__(16) double ring[D][ROWMAX];
   __shared__ double sX[W * 6];
+  __shared__ int sF[D];
   const int lane = threadIdx.x, n = e.n;
-  // window rows (i-W, i]; slot = row % W
   for (int r = n - 1 - lane; r >= 0 && r > n - 1 - W; r -= 32)
 #pragma unroll
     for (int q = 0; q < 6; ++q) sX[(r % W) * 6 + q] = x[6 * (long long)r + q];
-  __syncwarp();
-  double cur[36], nxt[36];
-  auto fetch = [&](int i, double* buf) {
-    if (i < 0) return;
-    const int f = e.first[i], cnt = i - f;
-    const double* row = L + e.row_start[i] * 36;
-#pragma unroll
-    for (int m = 0; m < 6; ++m) {
-      const int o = lane + 32 * m;
-      if (o < cnt * 6) {
-        const int jr = o / 6, cc = o - jr * 6;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) buf[m * 6 + q] = row[jr * 36 + q * 6 + cc];
-      }
+  auto issue = [&](int i) {                             // stream row i into ring[i % D]
+    if (i >= 0) {
+      const int f = e.first[i], cnt = i - f;
+      if (lane == 0) sF[i % D] = f;
+      const double* row = L + e.row_start[i] * 36;
+      for (int o = lane; o < cnt * 18; o += 32) cp_async16(&ring[i % D][2 * o], row + 2 * o);
     }
+    cp_async_commit();
   };
-  fetch(n - 1, cur);
+  for (int d = 0; d < D - 1; ++d) issue(n - 1 - d);
   for (int i = n - 1; i >= 0; --i) {
-    fetch(i - 1, nxt);
-    const int f = e.first[i], cnt = i - f;
+    issue(i - (D - 1));
+    cp_async_wait<D - 1>();
+    __syncwarp();
+    const int f = sF[i % D], cnt = i - f;
+    const double* cur = ring[i % D];
     double xi[6];
 #pragma unroll
     for (int q = 0; q < 6; ++q) xi[q] = sX[(i % W) * 6 + q];
     if (lane < 6) x[6 * (long long)i + lane] = sX[(i % W) * 6 + lane];
     __syncwarp();
+    for (int o = lane; o < cnt * 6; o += 32) {
+      const int jr = o / 6, cc = o - jr * 6;
+      double v = 0.0;
 #pragma unroll
-    for (int m = 0; m < 6; ++m) {
-      const int o = lane + 32 * m;
-      if (o < cnt * 6) {
-        const int jr = o / 6, cc = o - jr * 6;
-        double v = 0.0;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) v += cur[m * 6 + q] * xi[q];
-        sX[((f + jr) % W) * 6 + cc] -= v;
-      }
+      for (int q = 0; q < 6; ++q) v += cur[jr * 36 + q * 6 + cc] * xi[q];
+      sX[((f + jr) % W) * 6 + cc] -= v;
     }
-    // entering row i-W takes the slot row i just left
     if (lane < 6 && i - W >= 0) sX[(i % W) * 6 + lane] = x[6 * (long long)(i - W) + lane];
     __syncwarp();
-#pragma unroll
-    for (int q = 0; q < 36; ++q) cur[q] = nxt[q];
   }
 }
 

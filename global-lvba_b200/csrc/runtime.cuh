@@ -164,6 +164,8 @@ struct Envelope {
 struct EnvSolver {
   DevBuf<double> L, dinv, z;
   DevBuf<int> status;
+  DevBuf<long long> dbg;        // LVBA_FACTOR_TIMING=1: per-step phase clocks of the register-window kernel
+  int dbg_dumped = 0;
   bool configured = false;
   bool force_generic = false;   // tests: exercise the wide-envelope kernel on narrow problems
   int prepare(const Envelope& env) {
@@ -177,8 +179,16 @@ struct EnvSolver {
     LVBA_TRY(dinv.alloc((size_t)env.n * 36));
     LVBA_TRY(z.alloc((size_t)env.n * 6));
     LVBA_TRY(status.alloc(1));
+    {
+      const char* ft = getenv("LVBA_FACTOR_TIMING");
+      if (ft && ft[0] == '1') { LVBA_TRY(dbg.alloc((size_t)env.n * 32)); }
+    }
     if (!configured) {
       LVBA_CUDA(cudaFuncSetAttribute(env_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)factor_smem()));
+      LVBA_CUDA(cudaFuncSetAttribute(env_factor_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RegCfg<8>::kSmem));
+      LVBA_CUDA(cudaFuncSetAttribute(env_factor_reg_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RegCfg<16>::kSmem));
+      LVBA_CUDA(cudaFuncSetAttribute(env_factor_reg_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RegCfg<24>::kSmem));
+      LVBA_CUDA(cudaFuncSetAttribute(env_factor_reg_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RegCfg<31>::kSmem));
       configured = true;
     }
     return LVBA_OK;
@@ -194,14 +204,33 @@ struct EnvSolver {
     ++*launches;
     // column height < P: register-resident sliding-window kernel (envelope.cuh v2); wider: global-memory kernel
     const int mc = env.max_col;
-    const bool reg_path = mc < 32 && env.n >= 3 && !force_generic;
+    const bool reg_path = mc <= 30 && env.n >= 3 && !force_generic;
     if (reg_path) {
-      if (mc < 8) env_factor_reg_kernel<8><<<1, RegCfg<8>::kThreads, 0, s>>>(v, L.p, dinv.p, z.p, status.p);
-      else if (mc < 16) env_factor_reg_kernel<16><<<1, RegCfg<16>::kThreads, 0, s>>>(v, L.p, dinv.p, z.p, status.p);
-      else if (mc < 24) env_factor_reg_kernel<24><<<1, RegCfg<24>::kThreads, 0, s>>>(v, L.p, dinv.p, z.p, status.p);
-      else env_factor_reg_kernel<32><<<1, RegCfg<32>::kThreads, 0, s>>>(v, L.p, dinv.p, z.p, status.p);
+      if (mc <= 7) env_factor_reg_kernel<8><<<1, RegCfg<8>::kThreads, RegCfg<8>::kSmem, s>>>(v, L.p, dinv.p, z.p, status.p, dbg.p);
+      else if (mc <= 15) env_factor_reg_kernel<16><<<1, RegCfg<16>::kThreads, RegCfg<16>::kSmem, s>>>(v, L.p, dinv.p, z.p, status.p, dbg.p);
+      else if (mc <= 23) env_factor_reg_kernel<24><<<1, RegCfg<24>::kThreads, RegCfg<24>::kSmem, s>>>(v, L.p, dinv.p, z.p, status.p, dbg.p);
+      else env_factor_reg_kernel<31><<<1, RegCfg<31>::kThreads, RegCfg<31>::kSmem, s>>>(v, L.p, dinv.p, z.p, status.p, dbg.p);
+      if (dbg.p && dbg_dumped < 2) {
+        cudaStreamSynchronize(s);
+        std::vector<long long> h((size_t)env.n * 32);
+        cudaMemcpy(h.data(), dbg.p, h.size() * 8, cudaMemcpyDeviceToHost);
+        // average per role: scale (1-0), barrier-1 wait (2-1), main phase (3-2), barrier-2 wait (next 0 - 3), step (next 0 - 0)
+        const int k0 = 64, k1 = env.n - 64;
+        fprintf(stderr, "[factor timing] n=%d max_col=%d   role: scale | bar1 wait | main | bar2 wait | step   (cycles, avg over k=%d..%d)\n", env.n, mc, k0, k1);
+        for (int role = 0; role < 8; ++role) {
+          double acc[5] = {0, 0, 0, 0, 0};
+          for (int k = k0; k < k1; ++k) {
+            const long long* a = &h[((size_t)k * 8 + role) * 4];
+            const long long* b = &h[((size_t)(k + 1) * 8 + role) * 4];
+            acc[0] += a[1] - a[0]; acc[1] += a[2] - a[1]; acc[2] += a[3] - a[2]; acc[3] += b[0] - a[3]; acc[4] += b[0] - a[0];
+          }
+          fprintf(stderr, "  role %d (%s): %8.0f %8.0f %8.0f %8.0f %8.0f\n", role, role < 4 ? "pair warp" : (role == 4 ? "inverse  " : role == 5 ? "fwd subst" : "prefetch "),
+                  acc[0] / (k1 - k0), acc[1] / (k1 - k0), acc[2] / (k1 - k0), acc[3] / (k1 - k0), acc[4] / (k1 - k0));
+        }
+        ++dbg_dumped;
+      }
       env_dinv_apply_kernel<<<(n6 + 127) / 128, 128, 0, s>>>(env.n, dinv.p, z.p, x);
-      env_backsolve_row_kernel<<<1, 32, 0, s>>>(v, L.p, x);
+      env_backsolve_ring_kernel<<<1, 32, 0, s>>>(v, L.p, x);
       *launches += 3;
     } else {
       env_factor_kernel<<<1, kFactorThreads, factor_smem(), s>>>(v, L.p, dinv.p, z.p, status.p);
