@@ -616,4 +616,18 @@ __global__ void reduce_max_kernel(const double* __restrict__ part, int n, double
   }
 }
 
+// multi-GPU gather of the landmark updates: every rank owns a disjoint set of landmarks
+__global__ void visual_delta_kernel(long long Tv, const int* __restrict__ trk_id, const double* __restrict__ X,
+                                    const double* __restrict__ X0, double* __restrict__ delta) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= Tv * 3) return;
+  const long long k = i / 3, q = i - 3 * k;
+  const long long tr = trk_id[k];
+  delta[3 * tr + q] = X[3 * tr + q] - X0[3 * tr + q];
+}
+__global__ void visual_add_kernel(long long n, const double* __restrict__ X0, const double* __restrict__ delta, double* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = X0[i] + delta[i];
+}
+
 }  // namespace lvba

@@ -431,7 +431,22 @@ int lvba_visual_get_state(lvba_visual_problem* p, double* q, double* t, double* 
   LVBA_CUDA(cudaSetDevice(p->device));
   if (q) LVBA_CUDA(cudaMemcpyAsync(q, p->q.p, (size_t)p->M * 4 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
   if (t) LVBA_CUDA(cudaMemcpyAsync(t, p->t.p, (size_t)p->M * 3 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-  if (X && p->T > 0) LVBA_CUDA(cudaMemcpyAsync(X, p->X.p, (size_t)p->T * 3 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  if (X && p->T > 0) {
+    if (lvba::comm().active()) {
+      // landmarks are sharded: gather every rank's updates (disjoint) with one all-reduce of the deltas
+      lvba::DevBuf<double> delta, merged;
+      const long long n3 = (long long)p->T * 3;
+      LVBA_TRY(delta.alloc((size_t)n3)); LVBA_TRY(merged.alloc((size_t)n3));
+      LVBA_TRY(delta.zero(p->stream));
+      if (p->Tv > 0) { lvba::visual_delta_kernel<<<(unsigned)((p->Tv * 3 + 255) / 256), 256, 0, p->stream>>>(p->Tv, p->trk_id.p, p->X.p, p->X0.p, delta.p); ++p->launches; }
+      LVBA_TRY(lvba::comm().allreduce_sum(delta.p, (size_t)n3, p->stream));
+      lvba::visual_add_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, p->stream>>>(n3, p->X0.p, delta.p, merged.p); ++p->launches;
+      LVBA_CUDA(cudaMemcpyAsync(X, merged.p, (size_t)n3 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+      LVBA_CUDA(cudaStreamSynchronize(p->stream));
+    } else {
+      LVBA_CUDA(cudaMemcpyAsync(X, p->X.p, (size_t)p->T * 3 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    }
+  }
   LVBA_CUDA(cudaStreamSynchronize(p->stream));
   p->d2h += (int64_t)p->M * 56 + p->T * 24;
   return LVBA_OK;

@@ -1,0 +1,38 @@
+// Compiles global-lvba_b200/host/lvba_shim.hpp against mock types shaped like the reference's
+// IMUST / PointCluster / VOX_HESS (tools.hpp:147-207, 407-466, bavoxel.hpp:32-54) and calls through the C ABI.
+// Exit codes: 0 = solved on a GPU, 2 = library refused for lack of a CUDA device (expected on CPU boxes).
+#include <cmath>
+#include <cstdio>
+#include "../../global-lvba_b200/host/lvba_shim.hpp"
+
+struct M3 { double m[9]; double& operator()(int r, int c) { return m[3 * r + c]; } double operator()(int r, int c) const { return m[3 * r + c]; } };
+struct V3 { double v[3]; double& operator()(int r) { return v[r]; } double operator()(int r) const { return v[r]; } };
+struct IMUST { M3 R; V3 p; };
+struct PointCluster { M3 P{}; V3 v{}; int N = 0; void push(const double* x) { ++N; for (int i = 0; i < 3; ++i) { v.v[i] += x[i]; for (int j = 0; j < 3; ++j) P.m[3 * i + j] += x[i] * x[j]; } } };
+struct VOX_HESS { std::vector<const std::vector<PointCluster>*> plvec_voxels; int win_size; };
+
+int main() {
+  const int W = 4;
+  std::vector<IMUST> xs(W);
+  for (int i = 0; i < W; ++i) { xs[i].R = M3{{1, 0, 0, 0, 1, 0, 0, 0, 1}}; xs[i].p = V3{{0.5 * i, 0.01 * i, 0}}; }
+  std::vector<std::vector<PointCluster>> store(6, std::vector<PointCluster>(W));
+  VOX_HESS vh; vh.win_size = W;
+  unsigned s = 12345;
+  auto rnd = [&] { s = s * 1664525u + 1013904223u; return (double)(s >> 8) / (1u << 24) - 0.5; };
+  for (int a = 0; a < 6; ++a) {
+    const double n[3] = {a % 3 == 0 ? 1.0 : 0.0, a % 3 == 1 ? 1.0 : 0.0, a % 3 == 2 ? 1.0 : 0.0};
+    for (int i = 0; i < W; ++i) for (int k = 0; k < 20; ++k) {
+      double w[3] = {3 + rnd(), 2 + rnd(), 1 + rnd()};
+      for (int d = 0; d < 3; ++d) if (n[d] == 1.0) w[d] = 2.0 + 0.01 * rnd();
+      const double b[3] = {w[0] - 0.5 * i, w[1], w[2]};          // ground-truth body frame (true p = (0.5 i, 0, 0))
+      store[a][i].push(b);
+    }
+    vh.plvec_voxels.push_back(&store[a]);
+  }
+  lvba_summary sum{};
+  const int rc = lvba_b200::damping_iter(xs, vh, nullptr, &sum);
+  if (rc == LVBA_ERR_NO_DEVICE) { std::printf("no device: %s\n", lvba_last_error()); return 2; }
+  if (rc != LVBA_OK) { std::printf("error %d: %s\n", rc, lvba_last_error()); return 1; }
+  std::printf("ok: %d iterations, cost %.3e -> %.3e\n", sum.iterations, sum.cost_first, sum.cost_last);
+  return (sum.cost_last <= sum.cost_first) ? 0 : 1;
+}

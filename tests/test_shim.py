@@ -1,0 +1,34 @@
+"""The C++ host shim (global-lvba_b200/host/lvba_shim.hpp) compiles with plain g++ against mock reference
+types, links the C-ABI library, and — on a box without a GPU — gets LVBA_ERR_NO_DEVICE (exit code 2)."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _build(pkg, tmp_path):
+    exe = tmp_path / "test_shim"
+    cmd = ["g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), str(ROOT / "tests" / "shim" / "test_shim.cpp"),
+           "-o", str(exe), str(pkg.LIB_PATH), f"-Wl,-rpath,{pkg.LIB_PATH.parent}", "-L/usr/local/cuda/lib64", "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_shim_compiles_and_refuses_without_gpu(pkg, tmp_path):
+    exe = _build(pkg, tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if pkg.device_count() == 0:
+        assert r.returncode == 2, r.stdout + r.stderr
+    else:
+        assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_shim_solves_on_gpu(gpu_pkg, tmp_path):
+    exe = _build(gpu_pkg, tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok:" in r.stdout

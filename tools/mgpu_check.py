@@ -1,0 +1,41 @@
+"""Multi-GPU parity check (run under torchrun): the N-rank sharded solve must reproduce the oracle.
+    python -m torch.distributed.run --nproc-per-node N tools/mgpu_check.py [config]"""
+import os, sys
+sys.path.insert(0, '.')
+import numpy as np
+import torch, torch.distributed as dist
+import __graft_entry__ as g
+from oracle import synth, lidar_oracle as lo, visual_oracle as vo
+rank = int(os.environ.get("RANK", 0)); lrank = int(os.environ.get("LOCAL_RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+torch.cuda.set_device(lrank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
+pkg = g.load_package(); pkg.load_library()
+uid = [pkg.comm_unique_id() if rank == 0 else None]; dist.broadcast_object_list(uid, src=0)
+pkg.comm_init(world, rank, uid[0], lrank)
+name = sys.argv[1] if len(sys.argv) > 1 else "A"
+p = synth.make_config(name)
+W = p["n_poses"]
+P = pkg.LidarProblem(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"], device=lrank)
+r = P.build(); g_, br, bc, bl = P.get_system()
+ok = True
+if rank == 0 and W <= 500:
+    r0, g0, blocks = lo.acc_evaluate2(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"], W)
+    H = pkg.env_blocks_to_dense(br, bc, bl, W); H0 = lo.assemble_dense(blocks, W)
+    e = (abs(r - r0) / r0, np.abs(g_ - g0).max() / np.abs(g0).max(), np.abs(H - H0).max() / np.abs(H0).max())
+    print("lidar build vs oracle (res, g, H):", e); ok &= max(e) < 1e-7
+P.close()
+poses, s = pkg.lidar_lm(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"])
+K = ("q", "t", "X", "plane_nd", "obs_ptr", "obs_cam", "obs_uv", "intr", "sigma_px", "sigma_plane")
+q, t, X, sv = pkg.visual_lm(*[p[k] for k in K])
+if rank == 0:
+    print("lidar lm:", {k: s[k] for k in ("iterations", "accepted", "cost_first", "cost_last", "ms_total")})
+    print("visual lm:", {k: sv[k] for k in ("iterations", "accepted", "cost_first", "cost_last", "ms_total")})
+    if W <= 500:
+        ps0, info = lo.damping_iter(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"])
+        pr, inf = vo.ceres_lm(vo.VisualProblem(*[p[k] for k in K]))
+        e = (abs(s["cost_last"] - info["r_last"]) / info["r_last"], np.abs(poses - ps0).max(), abs(sv["cost_last"] - inf["cost"]) / inf["cost"],
+             np.abs(q - pr.q).max(), np.abs(X - pr.X).max())
+        print("lm vs oracle (costA, poses, costB, q, X):", e); ok &= max(e) < 1e-6
+        ok &= s["iterations"] == info["iters"] and sv["iterations"] == inf["iters"]
+    print("MGPU_CHECK", "PASS" if ok else "FAIL", "world", world)
+pkg.comm_destroy(); dist.destroy_process_group()
