@@ -25,7 +25,7 @@ _lib = None
 # names every build of the library must export (kept in sync with include/lvba_b200.h;
 # tests/test_abi.py cross-checks this list against the header)
 EXPORTS = [
-    "lvba_version", "lvba_device_count", "lvba_status_string", "lvba_last_error",
+    "lvba_version", "lvba_device_count", "lvba_status_string", "lvba_last_error", "lvba_release_cached_memory",
     "lvba_lidar_default_opts", "lvba_visual_default_opts",
     "lvba_lidar_lm", "lvba_lidar_create", "lvba_lidar_destroy", "lvba_lidar_set_poses",
     "lvba_lidar_get_poses", "lvba_lidar_build", "lvba_lidar_residual", "lvba_lidar_solve",

@@ -233,6 +233,7 @@ struct RegCfg {
   static constexpr int kStride = 38;                             // doubles per transposed block in smem (16B aligned, conflict-free)
   // register re-allocation (setmaxnreg): only needed when 5 warps share an SMSP (P = 31)
   static constexpr bool kRealloc = kThreads > 512;
+  static constexpr int kStaggerCycles = (kPairThreads >= 256) ? 300 : 0;
   static constexpr int kPairRegs = 104, kAheadRegs = 56;   // 512*104 + 128*56 <= 640*96 (the CTA pool only holds what the CTA owns)
   static constexpr size_t kSmem = sizeof(double) * (size_t)(2 * P * kStride + P * kStride + 2 * P * 36 + 2 * 36 + 2 * 36 + P * 6) +
                                   sizeof(long long) * P + sizeof(int) * (P + 4) + 32;
@@ -303,10 +304,46 @@ LVBA_DEV void warp_sym_inverse6(const double* Ain /*36, lower triangle read*/, d
   __syncwarp();
 }
 
+// 6x6 LDL^T without pivoting, in registers (every lane of the look-ahead warp holds the whole lower
+// triangle, 21 doubles: no shuffles / shared memory on the dependent chain).  x[i(i+1)/2 + j], i >= j.
+// On return x holds the unit-lower factor below the diagonal and 1/d_p on the diagonal — the scalar LDL^T
+// the reference's SimplicialLDLT computes on these six rows.
+#define LVBA_T(i, j) ((i) * ((i) + 1) / 2 + (j))
+LVBA_DEV void sym6_ldlt(double (&x)[21]) {
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    const double ip = __drcp_rn(x[LVBA_T(p, p)]);
+    double li[6];
+#pragma unroll
+    for (int i = p + 1; i < 6; ++i) li[i] = x[LVBA_T(i, p)] * ip;
+#pragma unroll
+    for (int i = p + 1; i < 6; ++i)
+#pragma unroll
+      for (int j = p + 1; j <= i; ++j) x[LVBA_T(i, j)] -= li[i] * x[LVBA_T(j, p)];
+#pragma unroll
+    for (int i = p + 1; i < 6; ++i) x[LVBA_T(i, p)] = li[i];
+    x[LVBA_T(p, p)] = ip;
+  }
+}
+// r = t D^-1 with D = L diag(1/f_pp) L^T given the 21 packed factors f (shared or global memory, broadcast reads)
+LVBA_DEV void ldlt_solve6(const double* __restrict__ f, double (&t)[6]) {
+#pragma unroll
+  for (int i = 1; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) t[i] -= f[LVBA_T(i, j)] * t[j];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) t[i] *= f[LVBA_T(i, i)];
+#pragma unroll
+  for (int i = 4; i >= 0; --i)
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) t[i] -= f[LVBA_T(j, i)] * t[j];
+}
+
 template <int P>
 __global__ void __launch_bounds__(RegCfg<P>::kThreads, 1)
-env_factor_reg_kernel(EnvView e, double* __restrict__ L, double* __restrict__ dinv, double* __restrict__ z,
-                      int* __restrict__ status, long long* __restrict__ dbg) {
+env_factor_reg_kernel(EnvView e, const unsigned short* __restrict__ pair_map, double* __restrict__ L,
+                      double* __restrict__ dinv, double* __restrict__ z, int* __restrict__ status,
+                      long long* __restrict__ dbg) {
   using Cfg = RegCfg<P>;
   // optional phase timing (LVBA_FACTOR_TIMING=1): dbg[(k*8 + role)*4 + stamp], role 0..3 = pair warps 0..3, 4..7 = look-ahead warps
 #define LVBA_STAMP(role, stamp) do { if (dbg && lane == 0) dbg[((long long)k * 8 + (role)) * 4 + (stamp)] = clock64(); } while (0)
@@ -325,19 +362,25 @@ env_factor_reg_kernel(EnvView e, double* __restrict__ L, double* __restrict__ di
   const int n = e.n;
   const bool is_ahead = tid >= Cfg::kPairThreads;               // look-ahead warpgroup (warp-uniform)
 
-  // shared by both roles: L_ik = A_ik D_k^-1 for rows k+1..k+nk, all threads of the CTA
+  // L_ik = A_ik D_k^-1 for rows k+1..k+nk: one (row, x) item per thread = row x of L_ik, obtained by the two
+  // triangular solves with the LDL^T factors of D_k (sK0: 21 doubles, broadcast reads)
   auto scale_column = [&](int k, int c, int nk) {
-    const double* K = sK0 + (k & 1) * 36;
+    const double* F = sK0 + (k & 1) * 36;
     const double* tb = sTt0 + (k & 1) * P * S;
-    for (int o = tid; o < nk * 36; o += Cfg::kThreads) {
-      const int h = 1 + o / 36, el = o - (h - 1) * 36, x = el / 6, cc = el - x * 6;
+    // executed by the look-ahead warpgroup only: the pair threads keep all their registers for the live block
+    for (int o = tid - Cfg::kPairThreads; o < nk * 6; o += 128) {
+      const int h = 1 + o / 6, x = o - (h - 1) * 6;
       int slot = c + h; if (slot >= P) slot -= P;
       const double* t = tb + slot * S;
-      double v = 0.0;
+      double v[6];
 #pragma unroll
-      for (int q = 0; q < 6; ++q) v += t[q * 6 + x] * K[q * 6 + cc];
-      sLt[slot * S + cc * 6 + x] = v;
-      L[(sRS[slot] + (k - sFirst[slot])) * 36 + el] = v;
+      for (int q = 0; q < 6; ++q) v[q] = t[q * 6 + x];
+      ldlt_solve6(F, v);
+      double* lt = sLt + slot * S;
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) lt[cc * 6 + x] = v[cc];
+      double2* g = reinterpret_cast<double2*>(L + (sRS[slot] + (k - sFirst[slot])) * 36 + x * 6);
+      g[0] = make_double2(v[0], v[1]); g[1] = make_double2(v[2], v[3]); g[2] = make_double2(v[4], v[5]);
     }
   };
 
@@ -353,9 +396,9 @@ env_factor_reg_kernel(EnvView e, double* __restrict__ L, double* __restrict__ di
   if (!is_ahead) {
     // =================================================== pair threads: one live 6x6 block in registers
     if (Cfg::kRealloc) reg_alloc<Cfg::kPairRegs>();
-    const bool is_pair = tid < Cfg::kPairs;
-    int a = 0, b = 0;
-    if (is_pair) tri_decode(tid, a, b);            // a >= b
+    const unsigned short pm = pair_map[tid];       // host-built map: lanes of a warp share few distinct slots
+    const bool is_pair = pm != 0xffff;
+    const int a = pm & 0xff, b = (pm >> 8) & 0xff; // a >= b
     double C[36];
     auto publish_T = [&](double* dst) {            // dst[q*6+x] = C[x][q]
 #pragma unroll
@@ -386,16 +429,22 @@ env_factor_reg_kernel(EnvView e, double* __restrict__ L, double* __restrict__ di
       }
     }
     __syncthreads();     // (A) column 0 published
-    __syncthreads();     // (B) look-ahead group finished D_0^-1 and the first entering row
+    __syncthreads();     // (B) look-ahead group finished D_0^-1 and the first entering rows
     int c = 0;
     for (int k = 0; k < n; ++k) {
       const int cur = k & 1;
       const int nk = sNk[k & 3];
       if (tid < 128) LVBA_STAMP(tid >> 5, 0);
-      scale_column(k, c, nk);
       if (tid < 128) LVBA_STAMP(tid >> 5, 1);
-      __syncthreads();
+      __syncthreads();                             // L_ik of this pivot column is ready (look-ahead group)
       if (tid < 128) LVBA_STAMP(tid >> 5, 2);
+      // Two of the four pair warps on every SMSP start half an operand-period late: the shared-memory pipe
+      // (the binding resource: 576 B of operands per thread and step) then serves one half while the other
+      // half runs its DFMAs, instead of all 16 warps alternating between the two in lockstep.
+      if (Cfg::kStaggerCycles > 0 && (tid & 128)) {
+        const unsigned t_0 = (unsigned)clock();
+        while ((unsigned)clock() - t_0 < (unsigned)Cfg::kStaggerCycles) { }
+      }
       if (is_pair) {
         int da = a - c; if (da < 0) da += P;
         int db = b - c; if (db < 0) db += P;
@@ -438,30 +487,67 @@ env_factor_reg_kernel(EnvView e, double* __restrict__ L, double* __restrict__ di
   } else {
     // =================================================== look-ahead warpgroup (4 warps, one per SMSP)
     if (Cfg::kRealloc) reg_dealloc<Cfg::kAheadRegs>();
-    const int aw = (tid - Cfg::kPairThreads) >> 5;              // 0: pivot inverse + metadata, 1: forward substitution, 2,3 (+1): row prefetch
-    const int pl = tid - Cfg::kPairThreads - 32;                // prefetch lane id over warps 1..3 (0..95), negative for warp 0
+    const int aw = (tid - Cfg::kPairThreads) >> 5;              // 0: pivot LDL^T + labels, 1: forward substitution, 2,3: row prefetch
+    const int pl = tid - Cfg::kPairThreads - 64;                // prefetch lane id over warps 2..3 (0..63), negative otherwise
     int bad = 0;
-    // entering row kc+P -> registers (issue early) -> sEnter[kc&1] (retire late); 96 lanes, <= 6 double2 each
-    constexpr int kPf = (P * 18 + 95) / 96;
-    __syncthreads();     // (A)
-    // D_0^-1 (warp 0) ; first entering row P (warps 1..3)
-    if (aw == 0) {
-      warp_sym_inverse6(sK0, sK0, lane, bad);
-      dinv[lane] = sK0[lane];
-      if (lane < 4) dinv[32 + lane] = sK0[32 + lane];
-    }
-    {
-      const int rf = (P < n) ? e.first[P] : 0x7fffffff;
-      const long long rrs = (P < n) ? e.row_start[P] : 0;
-      if (pl >= 0)
-        for (int o = pl; o < P * 18; o += 96) {
+    constexpr int kPf = (P * 18 + 63) / 64;                     // double2 per prefetch lane per row
+    double2 buf[kPf];                                           // row loaded during the previous step
+    double zin = 0.0;
+    int pf_first = 0x7fffffff; long long pf_rs = 0;             // label of the row to be loaded THIS step (fetched a step earlier)
+    auto issue_row = [&](int kc, int rf, long long rrs) {       // row kc+P -> buf (registers; latency hides under the step)
+      const int r = kc + P, ck = kc % P;
+#pragma unroll
+      for (int m = 0; m < kPf; ++m) {
+        const int o = pl + 64 * m;
+        double2 v = make_double2(0.0, 0.0);
+        if (o < P * 18) {
           const int cs = o / 18, w = o - cs * 18;
-          int dcol = cs; if (dcol <= 0) dcol += P;                // kc = 0: col = dcol ; cs == 0 <=> col == P
-          double2 v = make_double2(0.0, 0.0);
-          if (P < n && dcol >= rf) v = reinterpret_cast<const double2*>(L + (rrs + (dcol - rf)) * 36)[w];
-          reinterpret_cast<double2*>(sEnter0)[o] = v;
+          int dcol = cs - ck; if (dcol <= 0) dcol += P;          // col = kc + dcol ; dcol == P <=> col == r
+          const int col = kc + dcol;
+          if (r < n && col >= rf) v = reinterpret_cast<const double2*>(L + (rrs + (col - rf)) * 36)[w];
         }
-      if (aw == 0 && lane == 0) { sFirst[0] = rf; sRS[0] = rrs; }   // slot 0 now describes row P (nobody reads row 0's label any more)
+        buf[m] = v;
+      }
+    };
+    auto retire_row = [&](int kc) {                             // buf -> sEnter[kc & 1]
+#pragma unroll
+      for (int m = 0; m < kPf; ++m) {
+        const int o = pl + 64 * m;
+        if (o < P * 18) reinterpret_cast<double2*>(sEnter0 + ((kc & 1) * P) * 36)[o] = buf[m];
+      }
+    };
+    // warp 0: D (36 row-major in `src`, lower triangle read) -> LDL^T factors (21) in `dst` (shared) and in dinv[kc]
+    auto factor_pivot = [&](const double* src, double* dst, int kc) {
+      double x[21];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) x[LVBA_T(i, j)] = src[i * 6 + j];
+      __syncwarp();
+      sym6_ldlt(x);
+      double chk = 0.0;
+#pragma unroll
+      for (int q = 0; q < 21; ++q) { dst[q] = x[q]; chk += x[q]; }
+      if (!isfinite(chk)) bad = 1;
+      __syncwarp();
+      if (lane < 21) dinv[(long long)kc * 36 + lane] = dst[lane];
+    };
+    __syncthreads();     // (A)
+    if (aw == 0) {
+      factor_pivot(sK0, sK0, 0);
+      if (lane == 0) {                                          // slot 0 now describes row P (row 0's label is dead)
+        sFirst[0] = (P < n) ? e.first[P] : 0x7fffffff;
+        sRS[0] = (P < n) ? e.row_start[P] : 0;
+      }
+    } else if (aw == 1) {
+      if (lane < 6) zin = (P < n) ? z[6 * (long long)P + lane] : 0.0;      // z of row P, stored at step 0
+    } else {
+      // rows P (needed at step 0) and P+1 (stored at step 0); label of row P+2
+      issue_row(0, (P < n) ? e.first[P] : 0x7fffffff, (P < n) ? e.row_start[P] : 0);
+      retire_row(0);
+      issue_row(1, (P + 1 < n) ? e.first[P + 1] : 0x7fffffff, (P + 1 < n) ? e.row_start[P + 1] : 0);
+      pf_first = (P + 2 < n) ? e.first[P + 2] : 0x7fffffff;
+      pf_rs = (P + 2 < n) ? e.row_start[P + 2] : 0;
     }
     __syncthreads();     // (B)
     int c = 0;
@@ -475,7 +561,7 @@ env_factor_reg_kernel(EnvView e, double* __restrict__ L, double* __restrict__ di
       LVBA_STAMP(4 + aw, 2);
       int s1 = c + 1; if (s1 >= P) s1 -= P;
       if (aw == 0) {
-        // metadata of the entering row k+1+P and n_{k+3}: loads issued first, consumed after the inverse
+        // label of the entering row k+1+P and n_{k+3}: loads issued first, consumed after the factorisation
         int m_first = 0x7fffffff, m_last = 0; long long m_rs = 0;
         if (lane == 0) {
           const int r1 = k + 1 + P;
@@ -483,78 +569,61 @@ env_factor_reg_kernel(EnvView e, double* __restrict__ L, double* __restrict__ di
           m_rs = (r1 < n) ? e.row_start[r1] : 0;
           m_last = (k + 3 < n) ? e.last[k + 3] - (k + 3) : 0;
         }
-        // look-ahead: D_{k+1} = A_{k+1,k+1} - L_{k+1,k} T_{k+1,k}^T, then invert (Gauss-Jordan, no pivoting)
+        // look-ahead: D_{k+1} = A_{k+1,k+1} - L_{k+1,k} T_{k+1,k}^T (lane <-> lower-triangle element), then LDL^T
         if (k + 1 < n) {
           double* Kn = sK0 + (cur ^ 1) * 36;
           const double* dg = sDg0 + (cur ^ 1) * 36;
           const double* lt = sLt + s1 * S;
           const double* tt = sTt0 + (cur * P + s1) * S;
-          const int e0 = lane, e1 = 32 + lane;
-          double v0 = dg[e0], v1 = (e1 < 36) ? dg[e1] : 0.0;
+          const int l21 = lane < 21 ? lane : 0;
+          const int i = (l21 >= 15) ? 5 : (l21 >= 10) ? 4 : (l21 >= 6) ? 3 : (l21 >= 3) ? 2 : (l21 >= 1) ? 1 : 0;
+          const int j = l21 - i * (i + 1) / 2;
+          double v = dg[i * 6 + j];
           if (nk >= 1) {
-            const int x0 = e0 / 6, y0 = e0 % 6, x1 = (e1 < 36) ? e1 / 6 : 0, y1 = (e1 < 36) ? e1 % 6 : 0;
 #pragma unroll
-            for (int q = 0; q < 6; ++q) { v0 -= lt[q * 6 + x0] * tt[q * 6 + y0]; v1 -= lt[q * 6 + x1] * tt[q * 6 + y1]; }
+            for (int q = 0; q < 6; ++q) v -= lt[q * 6 + i] * tt[q * 6 + j];
           }
-          Kn[e0] = v0;
-          if (e1 < 36) Kn[e1] = v1;
           __syncwarp();
-          warp_sym_inverse6(Kn, Kn, lane, bad);
-          dinv[(long long)(k + 1) * 36 + lane] = Kn[lane];
-          if (lane < 4) dinv[(long long)(k + 1) * 36 + 32 + lane] = Kn[32 + lane];
+          if (lane < 21) Kn[i * 6 + j] = v;                       // lower triangle, row-major 6x6 scratch
+          __syncwarp();
+          factor_pivot(Kn, Kn, k + 1);
         }
         if (lane == 0) {
           sFirst[s1] = m_first; sRS[s1] = m_rs;                   // slot of row k+1 now describes row k+1+P
           sNk[(k + 3) & 3] = m_last;                              // n_{k+3} (slot last used by n_{k-1})
         }
+      } else if (aw == 1) {
+        // forward substitution with the final z_k : lane <-> row k+1+lane
+        double zk[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) zk[q] = sZ[c * 6 + q];
+        if (lane < 6) z[6 * (long long)k + lane] = sZ[c * 6 + lane];
+        for (int h = 1 + lane; h <= nk; h += 32) {
+          int slot = c + h; if (slot >= P) slot -= P;
+          const double2* lt2 = reinterpret_cast<const double2*>(sLt + slot * S);
+          double acc[6];
+#pragma unroll
+          for (int x = 0; x < 6; ++x) acc[x] = 0.0;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const double2 l0 = lt2[3 * q], l1 = lt2[3 * q + 1], l2 = lt2[3 * q + 2];
+            acc[0] += l0.x * zk[q]; acc[1] += l0.y * zk[q]; acc[2] += l1.x * zk[q]; acc[3] += l1.y * zk[q]; acc[4] += l2.x * zk[q]; acc[5] += l2.y * zk[q];
+          }
+#pragma unroll
+          for (int x = 0; x < 6; ++x) sZ[slot * 6 + x] -= acc[x];
+        }
+        __syncwarp();
+        if (lane < 6) {
+          sZ[c * 6 + lane] = zin;                               // row k+P takes slot c (loaded one step earlier)
+          zin = (k + 1 + P < n) ? z[6 * (long long)(k + 1 + P) + lane] : 0.0;
+        }
       } else {
-        // ---- warps 1..3: stream the row that enters when column k+1 retires (row k+1+P) into sEnter[(k+1)&1]
-        const int kc = k + 1, r = kc + P;
-        // first/row_start are tiny L2-resident arrays: read the entering row's label straight from global
-        const int rf = (r < n) ? e.first[r] : 0x7fffffff;
-        const long long rrs = (r < n) ? e.row_start[r] : 0;
-        double2 buf[kPf];
-#pragma unroll
-        for (int m = 0; m < kPf; ++m) {
-          const int o = pl + 96 * m;
-          double2 v = make_double2(0.0, 0.0);
-          if (o < P * 18) {
-            const int cs = o / 18, w = o - cs * 18;
-            int dcol = cs - s1; if (dcol <= 0) dcol += P;          // col = kc + dcol ; dcol == P <=> col == r
-            const int col = kc + dcol;
-            if (r < n && col >= rf) v = reinterpret_cast<const double2*>(L + (rrs + (col - rf)) * 36)[w];
-          }
-          buf[m] = v;
-        }
-        double zin = 0.0;
-        if (aw == 1 && lane < 6 && k + P < n) zin = z[6 * (long long)(k + P) + lane];
-        if (aw == 1) {
-          // forward substitution with the final z_k : lane <-> row k+1+lane
-          double zk[6];
-#pragma unroll
-          for (int q = 0; q < 6; ++q) zk[q] = sZ[c * 6 + q];
-          if (lane < 6) z[6 * (long long)k + lane] = sZ[c * 6 + lane];
-          for (int h = 1 + lane; h <= nk; h += 32) {
-            int slot = c + h; if (slot >= P) slot -= P;
-            const double* lt = sLt + slot * S;
-            double acc[6];
-#pragma unroll
-            for (int x = 0; x < 6; ++x) acc[x] = 0.0;
-#pragma unroll
-            for (int q = 0; q < 6; ++q)
-#pragma unroll
-              for (int x = 0; x < 6; ++x) acc[x] += lt[q * 6 + x] * zk[q];
-#pragma unroll
-            for (int x = 0; x < 6; ++x) sZ[slot * 6 + x] -= acc[x];
-          }
-          __syncwarp();
-          if (lane < 6) sZ[c * 6 + lane] = zin;                   // row k+P takes slot c
-        }
-#pragma unroll
-        for (int m = 0; m < kPf; ++m) {
-          const int o = pl + 96 * m;
-          if (o < P * 18) reinterpret_cast<double2*>(sEnter0 + ((kc & 1) * P) * 36)[o] = buf[m];
-        }
+        // ---- warps 2,3: retire the row loaded last step (row k+1+P -> sEnter[(k+1)&1]), issue row k+2+P
+        retire_row(k + 1);
+        issue_row(k + 2, pf_first, pf_rs);
+        const int r3 = k + 3 + P;
+        pf_first = (r3 < n) ? e.first[r3] : 0x7fffffff;
+        pf_rs = (r3 < n) ? e.row_start[r3] : 0;
       }
       LVBA_STAMP(4 + aw, 3);
       __syncthreads();
@@ -562,6 +631,20 @@ env_factor_reg_kernel(EnvView e, double* __restrict__ L, double* __restrict__ di
     }
     if (bad) status[0] = 1;
   }
+#undef LVBA_STAMP
+}
+
+
+// x = D^-1 z with the packed LDL^T factors of every pivot block (register-window path)
+__global__ void env_ldl_apply_kernel(int n, const double* __restrict__ dinv, const double* __restrict__ z, double* __restrict__ x) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double t[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) t[q] = z[6 * (long long)k + q];
+  ldlt_solve6(dinv + (long long)k * 36, t);
+#pragma unroll
+  for (int q = 0; q < 6; ++q) x[6 * (long long)k + q] = t[q];
 }
 
 // x = D^-1 z  (block diagonal solve, fully parallel)

@@ -90,9 +90,14 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
                              lvba_lidar_problem** out) {
   if (!out) return fail(LVBA_ERR_INVALID_ARG, "out is null");
   *out = nullptr;
+  const double t_val0 = wall_ms();
   LVBA_TRY(lidar_validate(W, V, vox_ptr, pose_idx, clusters, poses));
   LVBA_TRY(select_device(device));
   const double t0 = wall_ms();
+  const bool tlog = getenv("LVBA_SETUP_TIMING") != nullptr;
+  double tprev = t0;
+  auto lap = [&](const char* what) { if (tlog) { cudaStreamSynchronize(nullptr); const double t = wall_ms(); fprintf(stderr, "[lidar setup] %-22s %8.2f ms\n", what, t - tprev); tprev = t; } };
+  if (tlog) fprintf(stderr, "[lidar setup] %-22s %8.2f ms\n", "validate", t0 - t_val0);
   std::unique_ptr<lvba_lidar_problem> P(new lvba_lidar_problem());
   P->W = W; P->V_total = V;
   LVBA_CUDA(cudaGetDevice(&P->device));
@@ -101,8 +106,10 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   LVBA_CUDA(cudaMallocHost((void**)&P->h_scal, 8 * sizeof(double)));
   cudaStream_t s = P->stream;
 
+  lap("ctx/stream/pinned");
   P->h_vox_ptr_all.assign(vox_ptr, vox_ptr + V + 1);
   P->h_pose_idx_all.assign(pose_idx, pose_idx + vox_ptr[V]);
+  lap("host copies");
 
   // ---- envelope structure over ALL voxels (identical on every rank)
   std::vector<int> first_raw(W);
@@ -113,6 +120,7 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   }
   LVBA_TRY(P->env.build(first_raw, s, &P->h2d));
   LVBA_TRY(P->solver.prepare(P->env));
+  lap("envelope+solver alloc");
 
   // ---- shard: voxel -> owner of its lowest pose index
   Comm& cm = comm();
@@ -163,6 +171,7 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
     }
   }
 
+  lap("batches+pair table");
   // ---- upload.  Clusters: the caller's AoS records go up as they are (per contiguous run of owned
   //      voxels) and are transposed to the SoA double2 layout by a kernel.
   const long long nnz_pad = ((nnz + 31) / 32) * 32 + 32;
@@ -190,6 +199,7 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
     }
     LVBA_CUDA(cudaStreamSynchronize(s));   // aos is freed on scope exit
   }
+  if (tlog) { cudaStreamSynchronize(s); } lap("cluster upload+SoA");
   LVBA_TRY(P->pidx.upload(l_pidx, s, &P->h2d));
   LVBA_TRY(P->vox_ptr.upload(l_vox_ptr, s, &P->h2d));
   LVBA_TRY(P->batch_vox.upload(batch_vox, s, &P->h2d));
@@ -208,6 +218,7 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   LVBA_TRY(P->scal.zero(s));
   LVBA_CUDA(cudaFuncSetAttribute(lidar_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lidar_build_smem_bytes()));
   LVBA_CUDA(cudaStreamSynchronize(s));
+  lap("index upload+allocs");
   lvba_lidar_default_opts(&P->opts);
   P->ms_setup = wall_ms() - t0;
   *out = P.release();

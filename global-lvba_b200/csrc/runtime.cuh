@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -56,25 +58,74 @@ inline int select_device(int device) {
   return LVBA_OK;
 }
 
+// ---------------------------------------------------------------- device memory pool
+// cudaMalloc / cudaFree cost milliseconds each (cudaFree also synchronises the device); the one-shot ABI calls
+// create and destroy ~40 buffers per call.  Freed buffers are therefore parked in a per-device, size-bucketed
+// pool and reused by later calls of the same process (identical problem sizes hit exactly).  The pool is
+// capped; lvba_release_cached_memory() (include/lvba_b200.h) empties it.
+struct DevicePool {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void*> free_list;     // (device, bytes) -> pointer
+  size_t cached_bytes = 0;
+  static constexpr size_t kMaxCached = 16ull << 30;
+  static size_t bucket(size_t bytes) { return (bytes + 511) & ~size_t(511); }
+  void* take(int dev, size_t bytes) {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = free_list.find({dev, bytes});
+    if (it == free_list.end()) return nullptr;
+    void* p = it->second;
+    free_list.erase(it);
+    cached_bytes -= bytes;
+    return p;
+  }
+  void give(int dev, size_t bytes, void* p) {
+    std::lock_guard<std::mutex> g(mu);
+    if (cached_bytes + bytes > kMaxCached) { cudaFree(p); return; }
+    free_list.insert({{dev, bytes}, p});
+    cached_bytes += bytes;
+  }
+  void clear() {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& kv : free_list) cudaFree(kv.second);
+    free_list.clear();
+    cached_bytes = 0;
+  }
+};
+inline DevicePool& device_pool() {
+  static DevicePool* p = new DevicePool();     // intentionally leaked: no CUDA calls in static destructors
+  return *p;
+}
+
 // ---------------------------------------------------------------- device buffer
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  size_t bytes_ = 0;
+  int dev_ = 0;
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
-    p = nullptr; n = 0;
+    if (p) device_pool().give(dev_, bytes_, p);
+    p = nullptr; n = 0; bytes_ = 0;
   }
   int alloc(size_t count) {
     release();
     n = count;
     if (count == 0) return LVBA_OK;
-    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-    if (e != cudaSuccess) { p = nullptr; n = 0; return fail(LVBA_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); }
+    bytes_ = DevicePool::bucket(count * sizeof(T));
+    cudaGetDevice(&dev_);
+    p = (T*)device_pool().take(dev_, bytes_);
+    if (p) return LVBA_OK;
+    cudaError_t e = cudaMalloc((void**)&p, bytes_);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      device_pool().clear();                                   // give cached memory back and retry once
+      e = cudaMalloc((void**)&p, bytes_);
+    }
+    if (e != cudaSuccess) { p = nullptr; n = 0; bytes_ = 0; return fail(LVBA_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); }
     return LVBA_OK;
   }
   int upload(const T* h, size_t count, cudaStream_t s, int64_t* bytes = nullptr) {
@@ -160,10 +211,48 @@ struct Envelope {
   EnvView view() const { return EnvView{n, d_first.p, d_row_start.p, d_last.p, nblocks}; }
 };
 
+// Thread -> slot-pair map of the register-window kernel.  Pairs {a,b}, a >= b, are grouped by 8x8 super
+// blocks of the slot triangle so that the 32 lanes of a warp touch <= 8 distinct slots per operand: the
+// shared-memory operand loads of a warp then need 1-2 wavefronts instead of 4-5.
+inline std::vector<unsigned short> build_pair_map(int P, int n_threads) {
+  std::vector<std::vector<unsigned short>> chunks;          // full 32-lane chunks first, leftovers after
+  std::vector<std::vector<unsigned short>> left;
+  const int nb = (P + 7) / 8;
+  for (int A = 0; A < nb; ++A)
+    for (int B = 0; B <= A; ++B) {
+      std::vector<unsigned short> cur;
+      for (int a = 8 * A; a < std::min(P, 8 * A + 8); ++a)
+        for (int b = 8 * B; b < std::min(P, 8 * B + 8) && b <= a; ++b) {
+          cur.push_back((unsigned short)(a | (b << 8)));
+          if ((int)cur.size() == 32) { chunks.push_back(cur); cur.clear(); }
+        }
+      if (!cur.empty()) left.push_back(cur);
+    }
+  std::sort(left.begin(), left.end(), [](const auto& x, const auto& y) { return x.size() > y.size(); });
+  const int n_warps = n_threads / 32;
+  std::vector<std::vector<unsigned short>> warps = chunks;
+  for (auto& l : left) {                                     // first-fit into a warp with room, else a new warp, else split
+    bool placed = false;
+    for (size_t w = chunks.size(); w < warps.size() && !placed; ++w)
+      if (warps[w].size() + l.size() <= 32) { warps[w].insert(warps[w].end(), l.begin(), l.end()); placed = true; }
+    if (!placed && (int)warps.size() < n_warps) { warps.push_back(l); placed = true; }
+    if (!placed) {
+      for (auto& w : warps)
+        while (w.size() < 32 && !l.empty()) { w.push_back(l.back()); l.pop_back(); }
+    }
+  }
+  std::vector<unsigned short> map((size_t)n_threads, (unsigned short)0xffff);
+  for (size_t w = 0; w < warps.size() && (int)w < n_warps; ++w)
+    for (size_t i = 0; i < warps[w].size(); ++i) map[w * 32 + i] = warps[w][i];
+  return map;
+}
+
 // ---------------------------------------------------------------- LDL^T solve driver
 struct EnvSolver {
   DevBuf<double> L, dinv, z;
   DevBuf<int> status;
+  DevBuf<unsigned short> pair_map;   // thread -> slot pair of the register-window kernel (depends on P only)
+  int map_P = 0;
   DevBuf<long long> dbg;        // LVBA_FACTOR_TIMING=1: per-step phase clocks of the register-window kernel
   int dbg_dumped = 0;
   bool configured = false;
@@ -206,10 +295,19 @@ struct EnvSolver {
     const int mc = env.max_col;
     const bool reg_path = mc <= 30 && env.n >= 3 && !force_generic;
     if (reg_path) {
-      if (mc <= 7) env_factor_reg_kernel<8><<<1, RegCfg<8>::kThreads, RegCfg<8>::kSmem, s>>>(v, L.p, dinv.p, z.p, status.p, dbg.p);
-      else if (mc <= 15) env_factor_reg_kernel<16><<<1, RegCfg<16>::kThreads, RegCfg<16>::kSmem, s>>>(v, L.p, dinv.p, z.p, status.p, dbg.p);
-      else if (mc <= 23) env_factor_reg_kernel<24><<<1, RegCfg<24>::kThreads, RegCfg<24>::kSmem, s>>>(v, L.p, dinv.p, z.p, status.p, dbg.p);
-      else env_factor_reg_kernel<31><<<1, RegCfg<31>::kThreads, RegCfg<31>::kSmem, s>>>(v, L.p, dinv.p, z.p, status.p, dbg.p);
+      const int P = mc <= 7 ? 8 : mc <= 15 ? 16 : mc <= 23 ? 24 : 31;
+      if (map_P != P) {
+        const int nthr = P == 8 ? RegCfg<8>::kPairThreads : P == 16 ? RegCfg<16>::kPairThreads : P == 24 ? RegCfg<24>::kPairThreads : RegCfg<31>::kPairThreads;
+        std::vector<unsigned short> m = build_pair_map(P, nthr);
+        size_t cnt = 0; for (auto v2 : m) cnt += v2 != 0xffff;
+        if ((int)cnt != P * (P + 1) / 2) return fail(LVBA_ERR_UNSUPPORTED, "pair map for P=%d covers %zu of %d pairs", P, cnt, P * (P + 1) / 2);
+        LVBA_TRY(pair_map.upload(m, s));
+        map_P = P;
+      }
+      if (mc <= 7) env_factor_reg_kernel<8><<<1, RegCfg<8>::kThreads, RegCfg<8>::kSmem, s>>>(v, pair_map.p, L.p, dinv.p, z.p, status.p, dbg.p);
+      else if (mc <= 15) env_factor_reg_kernel<16><<<1, RegCfg<16>::kThreads, RegCfg<16>::kSmem, s>>>(v, pair_map.p, L.p, dinv.p, z.p, status.p, dbg.p);
+      else if (mc <= 23) env_factor_reg_kernel<24><<<1, RegCfg<24>::kThreads, RegCfg<24>::kSmem, s>>>(v, pair_map.p, L.p, dinv.p, z.p, status.p, dbg.p);
+      else env_factor_reg_kernel<31><<<1, RegCfg<31>::kThreads, RegCfg<31>::kSmem, s>>>(v, pair_map.p, L.p, dinv.p, z.p, status.p, dbg.p);
       if (dbg.p && dbg_dumped < 2) {
         cudaStreamSynchronize(s);
         std::vector<long long> h((size_t)env.n * 32);
@@ -229,7 +327,7 @@ struct EnvSolver {
         }
         ++dbg_dumped;
       }
-      env_dinv_apply_kernel<<<(n6 + 127) / 128, 128, 0, s>>>(env.n, dinv.p, z.p, x);
+      env_ldl_apply_kernel<<<(env.n + 127) / 128, 128, 0, s>>>(env.n, dinv.p, z.p, x);
       env_backsolve_ring_kernel<<<1, 32, 0, s>>>(v, L.p, x);
       *launches += 3;
     } else {

@@ -100,6 +100,9 @@ int         lvba_version(void);
 int         lvba_device_count(void);          /* 0 when no usable GPU; never fails */
 const char* lvba_status_string(int status);
 const char* lvba_last_error(void);            /* thread-local detail of the last failure */
+/* Device buffers of destroyed problems are cached for reuse by later calls (cudaMalloc/cudaFree cost
+ * milliseconds each); this returns the cached memory to the driver. */
+int         lvba_release_cached_memory(void);
 void        lvba_lidar_default_opts(lvba_lidar_opts* o);
 void        lvba_visual_default_opts(lvba_visual_opts* o);
 
