@@ -136,7 +136,7 @@ def run_reference(args, p, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C", choices=["A", "B", "C", "E"])
@@ -257,10 +257,17 @@ def main():
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()); peak = float(peaks["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
         except Exception:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        traffic = None
+        try:     # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (same config)
+            prof = json.loads((ROOT / "profiles" / "r01_ncu_full_summary.json").read_text())["lidar_build_kernel"]
+            if args.config == "C" and world == 1:
+                traffic = (float(prof["dram__bytes_read.sum"]) + float(prof["dram__bytes_write.sum"])) * 1e6
+        except Exception:
+            pass
         build_ms = dev_ms["build_A"] / args.steps
         achieved = ab["lidar_build"] / (build_ms * 1e-3) / 1e9
         roofline = {"kernel": "lidar_build_kernel (+ memset of H, + partial-sum reduce)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": ab["lidar_build"], "avg_launch_ms": build_ms,
                     "note": "timed with CUDA events on the library's launch stream; the kernel is atomic/FP64 bound, not HBM bound (DESIGN.md)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -270,6 +277,9 @@ def main():
                            "l2": "256 MiB buffer written between timed steps (L2 flush)",
                            "step": "1 LM pass of path A + 1 of path B from the initial state, inputs resident in HBM"},
                 "device_ms_per_step": {k: v / args.steps for k, v in dev_ms.items()},
+                "dominant_kernel_by_time": {"kernel": "env_factor_reg_kernel<P> (block LDL^T of the pose system, one CTA)",
+                                            "share_of_step": (dev_ms["solve_A"] + dev_ms["solve_B"]) / max(dev_total_ms, 1e-9),
+                                            "bound": "FP64 pipe + shared-memory bandwidth of ONE SM, sequential over pivot columns (DESIGN.md section 4); not an HBM-bound kernel"},
                 "device_ms_per_step_total_max_over_ranks": dev_ms_max / args.steps,
                 "timed_region_wall_s": wall,
                 "roofline": roofline, "algorithmic_bytes": ab,

@@ -233,7 +233,7 @@ struct RegCfg {
   static constexpr int kStride = 38;                             // doubles per transposed block in smem (16B aligned, conflict-free)
   // register re-allocation (setmaxnreg): only needed when 5 warps share an SMSP (P = 31)
   static constexpr bool kRealloc = kThreads > 512;
-  static constexpr int kStaggerCycles = (kPairThreads >= 256) ? 300 : 0;
+  static constexpr int kStaggerCycles = 0;   // tools/ubench/p3_pipe.cu: staggering the pair warps does not help (LDS and DFMA already overlap)
   static constexpr int kPairRegs = 104, kAheadRegs = 56;   // 512*104 + 128*56 <= 640*96 (the CTA pool only holds what the CTA owns)
   static constexpr size_t kSmem = sizeof(double) * (size_t)(2 * P * kStride + P * kStride + 2 * P * 36 + 2 * 36 + 2 * 36 + P * 6) +
                                   sizeof(long long) * P + sizeof(int) * (P + 4) + 32;
@@ -669,46 +669,71 @@ LVBA_DEV void cp_async16(void* smem, const void* gmem) {
 LVBA_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> LVBA_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(32, 1)
+// Block of 7 warps: warps 0..5 own one output (row jr, component cc) of the row being applied, warp 6 is the
+// producer that streams future rows of L through a cp.async ring and prefetches their labels and the x entries
+// that enter the 32-row window.  Two block barriers per row; no global-memory latency on the dependent chain.
+constexpr int kBsThreads = 224, kBsDepth = 5;
+__global__ void __launch_bounds__(kBsThreads, 1)
 env_backsolve_ring_kernel(EnvView e, const double* __restrict__ L, double* __restrict__ x) {
-  constexpr int W = 32, D = 4, ROWMAX = 31 * 36;
+  constexpr int W = 32, D = kBsDepth, ROWMAX = 31 * 36;
   __shared__ __align__(16) double ring[D][ROWMAX];
   __shared__ double sX[W * 6];
   __shared__ int sF[D];
-  const int lane = threadIdx.x, n = e.n;
-  for (int r = n - 1 - lane; r >= 0 && r > n - 1 - W; r -= 32)
-#pragma unroll
-    for (int q = 0; q < 6; ++q) sX[(r % W) * 6 + q] = x[6 * (long long)r + q];
-  auto issue = [&](int i) {                             // stream row i into ring[i % D]
+  const int tid = threadIdx.x, lane = tid & 31, n = e.n;
+  const bool producer = tid >= 192;
+  for (int idx = tid; idx < W * 6; idx += kBsThreads) {
+    const int r = n - 1 - idx / 6;                       // rows n-1 .. n-32
+    if (r >= 0) sX[(r % W) * 6 + idx % 6] = x[6 * (long long)r + idx % 6];
+  }
+  // producer state: label of the next row to issue (prefetched one step earlier), entering x value
+  int nf = 0; long long nrs = 0; double xin = 0.0;
+  auto issue = [&](int i) {                               // stream row i (label in nf/nrs) into ring[i % D]
     if (i >= 0) {
-      const int f = e.first[i], cnt = i - f;
-      if (lane == 0) sF[i % D] = f;
-      const double* row = L + e.row_start[i] * 36;
+      const int cnt = i - nf;
+      if (lane == 0) sF[i % D] = nf;
+      const double* row = L + nrs * 36;
       for (int o = lane; o < cnt * 18; o += 32) cp_async16(&ring[i % D][2 * o], row + 2 * o);
     }
     cp_async_commit();
   };
-  for (int d = 0; d < D - 1; ++d) issue(n - 1 - d);
-  for (int i = n - 1; i >= 0; --i) {
-    issue(i - (D - 1));
-    cp_async_wait<D - 1>();
-    __syncwarp();
-    const int f = sF[i % D], cnt = i - f;
-    const double* cur = ring[i % D];
-    double xi[6];
-#pragma unroll
-    for (int q = 0; q < 6; ++q) xi[q] = sX[(i % W) * 6 + q];
-    if (lane < 6) x[6 * (long long)i + lane] = sX[(i % W) * 6 + lane];
-    __syncwarp();
-    for (int o = lane; o < cnt * 6; o += 32) {
-      const int jr = o / 6, cc = o - jr * 6;
-      double v = 0.0;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) v += cur[jr * 36 + q * 6 + cc] * xi[q];
-      sX[((f + jr) % W) * 6 + cc] -= v;
+  if (producer) {
+    for (int d = 0; d < D - 1; ++d) {
+      const int i = n - 1 - d;
+      if (i >= 0) { nf = e.first[i]; nrs = e.row_start[i]; }
+      issue(i);
     }
-    if (lane < 6 && i - W >= 0) sX[(i % W) * 6 + lane] = x[6 * (long long)(i - W) + lane];
-    __syncwarp();
+    const int inext = n - 1 - (D - 1);
+    if (inext >= 0) { nf = e.first[inext]; nrs = e.row_start[inext]; }
+    if (lane < 6 && n - 1 - W >= 0) xin = x[6 * (long long)(n - 1 - W) + lane];
+  }
+  __syncthreads();
+  const int jr = tid / 6, cc = tid - jr * 6;              // consumer output (tid < 192 -> jr < 32)
+  for (int i = n - 1; i >= 0; --i) {
+    if (producer) {
+      issue(i - (D - 1));                                 // label was fetched during the previous step
+      const int i2 = i - D;                               // label for the next issue
+      if (i2 >= 0) { nf = e.first[i2]; nrs = e.row_start[i2]; }
+      cp_async_wait<D - 1>();                             // row i has landed
+    }
+    __syncthreads();                                      // (A) row i visible; x_i final
+    if (!producer) {
+      const int f = sF[i % D], cnt = i - f;
+      const double* cur = ring[i % D];
+      if (tid < 6) x[6 * (long long)i + tid] = sX[(i % W) * 6 + tid];
+      if (jr < cnt) {
+        const double* xi = sX + (i % W) * 6;
+        const double* lb = cur + jr * 36 + cc;
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) v += lb[q * 6] * xi[q];
+        sX[((f + jr) % W) * 6 + cc] -= v;
+      }
+    }
+    __syncthreads();                                      // (B) updates applied; slot of row i is free
+    if (producer && lane < 6) {
+      if (i - W >= 0) sX[(i % W) * 6 + lane] = xin;       // row i-W enters the window
+      if (i - 1 - W >= 0) xin = x[6 * (long long)(i - 1 - W) + lane];
+    }
   }
 }
 

@@ -328,7 +328,7 @@ struct EnvSolver {
         ++dbg_dumped;
       }
       env_ldl_apply_kernel<<<(env.n + 127) / 128, 128, 0, s>>>(env.n, dinv.p, z.p, x);
-      env_backsolve_ring_kernel<<<1, 32, 0, s>>>(v, L.p, x);
+      env_backsolve_ring_kernel<<<1, kBsThreads, 0, s>>>(v, L.p, x);
       *launches += 3;
     } else {
       env_factor_kernel<<<1, kFactorThreads, factor_smem(), s>>>(v, L.p, dinv.p, z.p, status.p);
