@@ -153,8 +153,10 @@ lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, 
   double* sV = sG + kSlots * 6;                         // [kMaxVoxPerBatch][kVoxParams]
   double* red = sV + kMaxVoxPerBatch * kVoxParams;      // [32]
   long long* sDiag = reinterpret_cast<long long*>(red + 32);   // [kSlots] element offset of the slot's diagonal block
-  int* sPose = reinterpret_cast<int*>(sDiag + kSlots);  // [kSlots]
-  unsigned char* sVoxOf = reinterpret_cast<unsigned char*>(sPose + kSlots);   // [kSlots]
+  long long* sRowRS = sDiag + kSlots;                   // [kSlots] envelope row_start of the slot's pose row
+  int* sPose = reinterpret_cast<int*>(sRowRS + kSlots); // [kSlots]
+  int* sRowFirst = sPose + kSlots;                      // [kSlots] envelope first[] of the slot's pose row
+  unsigned char* sVoxOf = reinterpret_cast<unsigned char*>(sRowFirst + kSlots);   // [kSlots]
   // per-warp pair scratch
   long long* sPairBase = reinterpret_cast<long long*>(sVoxOf + kSlots);       // [4 warps][8]
   unsigned* sPairCode = reinterpret_cast<unsigned*>(sPairBase + (kSlots / 32) * 8);   // [4 warps][8]
@@ -174,7 +176,10 @@ lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, 
 #pragma unroll
     for (int q = 0; q < 10; ++q) stage[tid * kStageStride + q] = out[q];
     sPose[tid] = pose;
-    sDiag[tid] = env_block(env, pose, pose) * 36;
+    const long long rs = env.row_start[pose];
+    const int fr = env.first[pose];
+    sRowRS[tid] = rs; sRowFirst[tid] = fr;
+    sDiag[tid] = (rs + (pose - fr)) * 36;
   }
   __syncthreads();
 
@@ -277,10 +282,14 @@ lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, 
     for (int q = 0; q < 36; ++q) st[q] = Hb[q];
     double* sg = sG + tid * 6;
     double* sf = sF + tid * kFStride;
+    // off-diagonal blocks are  c1 f1 f1^T + c2 f2 f2^T - 2/N^2 b b^T  with c1, c2 < 0 (lambda0 is the smallest
+    // eigenvalue): store the factors pre-scaled by sqrt(|c|) so that phase 4 is a plain 3-term dot product
+    const double s1 = sqrt(-c1), s2 = sqrt(-c2), s3 = 1.4142135623730951 * iN;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) { sg[j] = jjt[j]; sf[j] = f1[j]; sf[6 + j] = f2[j]; }
-    sf[12] = w[0]; sf[13] = w[1]; sf[14] = w[2];
-    sf[15] = s.n * uk[0]; sf[16] = s.n * uk[1]; sf[17] = s.n * uk[2];
+    for (int j = 0; j < 6; ++j) { sg[j] = jjt[j]; sf[j] = s1 * f1[j]; sf[6 + j] = s2 * f2[j]; }
+    sf[12] = s3 * w[0]; sf[13] = s3 * w[1]; sf[14] = s3 * w[2];
+    const double s3n = s3 * s.n;
+    sf[15] = s3n * uk[0]; sf[16] = s3n * uk[1]; sf[17] = s3n * uk[2];
   }
   __syncthreads();
 
@@ -298,33 +307,44 @@ lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, 
   const long long p0 = lv.batch_pair[b], np = lv.batch_pair[b + 1] - p0;
   long long* myBase = sPairBase + warp * 8;
   unsigned* myCode = sPairCode + warp * 8;
+  // lane-constant decode of element e = lane + 32 m -> (pair slot pr, row a, col bq, el): pr | a<<4 | bq<<8 | el<<12
+  unsigned dec[9];
+#pragma unroll
+  for (int m = 0; m < 9; ++m) {
+    const int e = lane + 32 * m;
+    const int pr = e / 36, el = e - pr * 36, aa = el / 6, bq = el - aa * 6;
+    dec[m] = (unsigned)pr | ((unsigned)aa << 4) | ((unsigned)bq << 8) | ((unsigned)el << 12);
+  }
+  unsigned code_next = 0;
+  {
+    const long long c0 = (long long)warp * 8;
+    if (c0 + lane < np && lane < 8) code_next = lv.pairs[p0 + c0 + lane];
+  }
   for (long long c = (long long)warp * 8; c < np; c += (kSlots / 32) * 8) {
     const int cnt = (int)((np - c < 8) ? (np - c) : 8);
+    const unsigned code = code_next;
+    {                                                     // prefetch the next chunk's pair codes
+      const long long cn = c + (kSlots / 32) * 8;
+      code_next = (lane < 8 && cn + lane < np) ? lv.pairs[p0 + cn + lane] : 0u;
+    }
     __syncwarp();
     if (lane < cnt) {
-      const unsigned code = lv.pairs[p0 + c + lane];
       const int li = code & 0xff, lj = (code >> 8) & 0xff;
-      myCode[lane] = code;
       // lower-triangle block: row = larger pose (slot lj, ascending order inside a voxel), col = slot li
-      myBase[lane] = env_block(env, sPose[lj], sPose[li]) * 36;
+      myBase[lane] = (sRowRS[lj] + (sPose[li] - sRowFirst[lj])) * 36;
+      myCode[lane] = (unsigned)(li * kFStride) | ((unsigned)(lj * kFStride) << 16);
     }
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < 9; ++m) {
-      const int e = lane + 32 * m;
-      const int pr = e / 36, el = e - pr * 36;
+      const unsigned d = dec[m];
+      const int pr = d & 15;
       if (pr < cnt) {
-        const unsigned code = myCode[pr];
-        const int li = code & 0xff, lj = (code >> 8) & 0xff, vx = (code >> 16) & 0xff;
-        const int a = el / 6, bq = el - a * 6;          // block(row j, col i)[a][bq] = Hb_ij[bq][a]
-        const double* fi = sF + li * kFStride;
-        const double* fj = sF + lj * kFStride;
-        const double* vp = sV + vx * kVoxParams;
-        const double iN = 1.0 / vp[11];
-        double val = vp[9] * fi[bq] * fj[a];
-        val += vp[10] * fi[6 + bq] * fj[6 + a];
-        val -= 2.0 * iN * iN * fi[12 + bq] * fj[12 + a];
-        atomicAdd(H + myBase[pr] + el, val);
+        const unsigned off = myCode[pr];
+        const double* fi = sF + (off & 0xffff) + ((d >> 8) & 15);      // column index bq of the (j,i) block
+        const double* fj = sF + (off >> 16) + ((d >> 4) & 15);         // row index a
+        const double val = -(fi[0] * fj[0] + fi[6] * fj[6] + fi[12] * fj[12]);
+        atomicAdd(H + myBase[pr] + (d >> 12), val);
       }
     }
   }
@@ -332,7 +352,7 @@ lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, 
 
 constexpr size_t lidar_build_smem_bytes() {
   return sizeof(double) * (kSlots * kStageStride + kSlots * kFStride + kSlots * 6 + kMaxVoxPerBatch * kVoxParams + 32)
-       + sizeof(long long) * kSlots + sizeof(int) * kSlots + kSlots /*u8*/
+       + sizeof(long long) * 2 * kSlots + sizeof(int) * 2 * kSlots + kSlots /*u8*/
        + sizeof(long long) * (kSlots / 32) * 8 + sizeof(unsigned) * (kSlots / 32) * 8 + 64;
 }
 

@@ -330,8 +330,10 @@ visual_build_kernel(VisualView vv, EnvView env, VisualState st, VisualLM lm, dou
   double* sT = sG + kSlots * 18;                         // [kMaxTrkPerBatch][kTrkParams]
   double* red = sT + kMaxTrkPerBatch * kTrkParams;       // [32]
   long long* sDiag = reinterpret_cast<long long*>(red + 32);     // [kSlots]
-  int* sRow = reinterpret_cast<int*>(sDiag + kSlots);            // [kSlots]
-  long long* sPairBase = reinterpret_cast<long long*>(sRow + kSlots);          // [warps][8]
+  long long* sRowRS = sDiag + kSlots;                            // [kSlots] envelope row_start of the camera row
+  int* sRow = reinterpret_cast<int*>(sRowRS + kSlots);           // [kSlots]
+  int* sRowFirst = sRow + kSlots;                                // [kSlots]
+  long long* sPairBase = reinterpret_cast<long long*>(sRowFirst + kSlots);     // [warps][8]
   unsigned* sPairCode = reinterpret_cast<unsigned*>(sPairBase + (kSlots / 32) * 8);
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -395,7 +397,10 @@ visual_build_kernel(VisualView vv, EnvView env, VisualState st, VisualLM lm, dou
       }
 #pragma unroll
       for (int q = 0; q < 18; ++q) { sf[q] = Y[q]; sf[18 + q] = E[q]; }
-      sDiag[tid] = env_block(env, row, row) * 36;
+      const long long rs = env.row_start[row];
+      const int fr = env.first[row];
+      sRowRS[tid] = rs; sRowFirst[tid] = fr;
+      sDiag[tid] = (rs + (row - fr)) * 36;
     } else {
       sDiag[tid] = -1;
     }
@@ -419,28 +424,42 @@ visual_build_kernel(VisualView vv, EnvView env, VisualState st, VisualLM lm, dou
   const long long p0 = vv.batch_pair[b], np = vv.batch_pair[b + 1] - p0;
   long long* myBase = sPairBase + warp * 8;
   unsigned* myCode = sPairCode + warp * 8;
+  unsigned dec[9];
+#pragma unroll
+  for (int m = 0; m < 9; ++m) {
+    const int e = lane + 32 * m;
+    const int pr = e / 36, el = e - pr * 36, aa = el / 6, bq = el - aa * 6;
+    dec[m] = (unsigned)pr | ((unsigned)aa << 4) | ((unsigned)bq << 8) | ((unsigned)el << 12);
+  }
+  unsigned code_next = 0;
+  {
+    const long long c0 = (long long)warp * 8;
+    if (c0 + lane < np && lane < 8) code_next = vv.pairs[p0 + c0 + lane];
+  }
   for (long long c = (long long)warp * 8; c < np; c += (kSlots / 32) * 8) {
     const int cnt = (int)((np - c < 8) ? (np - c) : 8);
+    const unsigned code = code_next;
+    {
+      const long long cn = c + (kSlots / 32) * 8;
+      code_next = (lane < 8 && cn + lane < np) ? vv.pairs[p0 + cn + lane] : 0u;
+    }
     __syncwarp();
     if (lane < cnt) {
-      const unsigned code = vv.pairs[p0 + c + lane];
       const int hi = code & 0xff, lo = (code >> 8) & 0xff;
-      myCode[lane] = code;
-      myBase[lane] = env_block(env, sRow[hi], sRow[lo]) * 36;
+      myBase[lane] = (sRowRS[hi] + (sRow[lo] - sRowFirst[hi])) * 36;
+      myCode[lane] = (unsigned)(hi * kVFStride) | ((unsigned)(lo * kVFStride + 18) << 16);
     }
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < 9; ++m) {
-      const int e = lane + 32 * m;
-      const int pr = e / 36, el = e - pr * 36;
+      const unsigned d = dec[m];
+      const int pr = d & 15;
       if (pr < cnt) {
-        const unsigned code = myCode[pr];
-        const int hi = code & 0xff, lo = (code >> 8) & 0xff;
-        const int a = el / 6, bq = el - a * 6;
-        const double* y = sF + hi * kVFStride + 3 * a;
-        const double* ee = sF + lo * kVFStride + 18 + 3 * bq;
+        const unsigned off = myCode[pr];
+        const double* y = sF + (off & 0xffff) + 3 * ((d >> 4) & 15);      // Y_hi row a
+        const double* ee = sF + (off >> 16) + 3 * ((d >> 8) & 15);        // E_lo row bq
         const double val = -(y[0] * ee[0] + y[1] * ee[1] + y[2] * ee[2]);
-        atomicAdd(S + myBase[pr] + el, val);
+        atomicAdd(S + myBase[pr] + (d >> 12), val);
       }
     }
   }
@@ -448,7 +467,7 @@ visual_build_kernel(VisualView vv, EnvView env, VisualState st, VisualLM lm, dou
 
 constexpr size_t visual_build_smem_bytes() {
   return sizeof(double) * (kSlots * kStageStride + kSlots * kVFStride + kSlots * 18 + kMaxTrkPerBatch * kTrkParams + 32)
-       + sizeof(long long) * kSlots + sizeof(int) * kSlots
+       + sizeof(long long) * 2 * kSlots + sizeof(int) * 2 * kSlots
        + sizeof(long long) * (kSlots / 32) * 8 + sizeof(unsigned) * (kSlots / 32) * 8 + 64;
 }
 
