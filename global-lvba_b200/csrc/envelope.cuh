@@ -339,12 +339,32 @@ LVBA_DEV void ldlt_solve6(const double* __restrict__ f, double (&t)[6]) {
     for (int j = i + 1; j < 6; ++j) t[i] -= f[LVBA_T(j, i)] * t[j];
 }
 
+// One factorisation instance.  The twisted solve (runtime.cuh) runs two at once (gridDim.x = 2): the top half of
+// the pose system in natural order and the bottom half in REVERSED order, each on its own SM; both stop at the
+// separator (n_stop < n) and dump their Schur-updated trailing window + forward-substituted rhs.
+struct FactorJob {
+  EnvView e;
+  double* L;       // in: matrix (H + damping) in envelope layout; out: L_ik below the pivots
+  double* dinv;    // out: packed LDL^T factors of every pivot block (21 of 36 doubles used)
+  double* z;       // in: rhs ; out: forward-substituted rhs of the pivots
+  int n_stop;      // number of pivots to eliminate (== e.n for a complete factorisation)
+  double* wdump;   // [bs*bs*36] trailing window at n_stop, block (i,j) at ((i-n_stop)*bs + (j-n_stop))*36, bs = e.n - n_stop
+  double* zdump;   // [bs*6]
+};
+struct FactorJobs { FactorJob j[2]; };
+
 template <int P>
 __global__ void __launch_bounds__(RegCfg<P>::kThreads, 1)
-env_factor_reg_kernel(EnvView e, const unsigned short* __restrict__ pair_map, double* __restrict__ L,
-                      double* __restrict__ dinv, double* __restrict__ z, int* __restrict__ status,
-                      long long* __restrict__ dbg) {
+env_factor_reg_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_map, int* __restrict__ status,
+                      long long* __restrict__ dbg_all) {
   using Cfg = RegCfg<P>;
+  const FactorJob& J = jobs.j[blockIdx.x];
+  const EnvView e = J.e;
+  double* __restrict__ L = J.L;
+  double* __restrict__ dinv = J.dinv;
+  double* __restrict__ z = J.z;
+  const int n_stop = J.n_stop;
+  long long* dbg = (blockIdx.x == 0) ? dbg_all : nullptr;
   // optional phase timing (LVBA_FACTOR_TIMING=1): dbg[(k*8 + role)*4 + stamp], role 0..3 = pair warps 0..3, 4..7 = look-ahead warps
 #define LVBA_STAMP(role, stamp) do { if (dbg && lane == 0) dbg[((long long)k * 8 + (role)) * 4 + (stamp)] = clock64(); } while (0)
   constexpr int S = Cfg::kStride;
@@ -431,7 +451,7 @@ env_factor_reg_kernel(EnvView e, const unsigned short* __restrict__ pair_map, do
     __syncthreads();     // (A) column 0 published
     __syncthreads();     // (B) look-ahead group finished D_0^-1 and the first entering rows
     int c = 0;
-    for (int k = 0; k < n; ++k) {
+    for (int k = 0; k < n_stop; ++k) {
       const int cur = k & 1;
       const int nk = sNk[k & 3];
       if (tid < 128) LVBA_STAMP(tid >> 5, 0);
@@ -483,6 +503,18 @@ env_factor_reg_kernel(EnvView e, const unsigned short* __restrict__ pair_map, do
       if (tid < 128) LVBA_STAMP(tid >> 5, 3);
       __syncthreads();
       if (++c == P) c = 0;
+    }
+    // partial factorisation: hand the Schur-updated trailing window (rows/cols n_stop..n-1) to the separator solve
+    if (n_stop < n && J.wdump && is_pair) {
+      int da = a - c; if (da < 0) da += P;
+      int db = b - c; if (db < 0) db += P;
+      const int hi = da > db ? da : db, lo = da > db ? db : da;
+      const int bs = n - n_stop;
+      if (hi < bs) {
+        double2* dst = reinterpret_cast<double2*>(J.wdump + ((long long)hi * bs + lo) * 36);
+#pragma unroll
+        for (int q = 0; q < 18; ++q) dst[q] = make_double2(C[2 * q], C[2 * q + 1]);
+      }
     }
   } else {
     // =================================================== look-ahead warpgroup (4 warps, one per SMSP)
@@ -551,7 +583,7 @@ env_factor_reg_kernel(EnvView e, const unsigned short* __restrict__ pair_map, do
     }
     __syncthreads();     // (B)
     int c = 0;
-    for (int k = 0; k < n; ++k) {
+    for (int k = 0; k < n_stop; ++k) {
       const int cur = k & 1;
       const int nk = sNk[k & 3];
       LVBA_STAMP(4 + aw, 0);
@@ -629,6 +661,12 @@ env_factor_reg_kernel(EnvView e, const unsigned short* __restrict__ pair_map, do
       __syncthreads();
       if (++c == P) c = 0;
     }
+    if (n_stop < n && J.zdump && aw == 1) {                     // forward-substituted rhs of the separator rows
+      for (int o = lane; o < (n - n_stop) * 6; o += 32) {
+        const int i = n_stop + o / 6;
+        J.zdump[o] = sZ[(i % P) * 6 + o % 6];
+      }
+    }
     if (bad) status[0] = 1;
   }
 #undef LVBA_STAMP
@@ -673,24 +711,37 @@ template <int N> LVBA_DEV void cp_async_wait() { asm volatile("cp.async.wait_gro
 // producer that streams future rows of L through a cp.async ring and prefetches their labels and the x entries
 // that enter the 32-row window.  Two block barriers per row; no global-memory latency on the dependent chain.
 constexpr int kBsThreads = 224, kBsDepth = 5;
+struct BacksolveJob {
+  EnvView e;
+  const double* L;
+  double* x;        // in: D^-1 z for the pivots (rows < n_given) and the FINAL solution for rows >= n_given ; out: solution
+  int n_given;      // rows >= n_given are given (separator of the twisted solve); == e.n for a plain solve
+};
+struct BacksolveJobs { BacksolveJob j[2]; };
+
 __global__ void __launch_bounds__(kBsThreads, 1)
-env_backsolve_ring_kernel(EnvView e, const double* __restrict__ L, double* __restrict__ x) {
+env_backsolve_ring_kernel(BacksolveJobs jobs) {
   constexpr int W = 32, D = kBsDepth, ROWMAX = 31 * 36;
   __shared__ __align__(16) double ring[D][ROWMAX];
   __shared__ double sX[W * 6];
-  __shared__ int sF[D];
+  __shared__ int sF[D], sCnt[D];
+  const BacksolveJob& J = jobs.j[blockIdx.x];
+  const EnvView e = J.e;
+  const double* __restrict__ L = J.L;
+  double* __restrict__ x = J.x;
+  const int n_given = J.n_given;
   const int tid = threadIdx.x, lane = tid & 31, n = e.n;
   const bool producer = tid >= 192;
   for (int idx = tid; idx < W * 6; idx += kBsThreads) {
     const int r = n - 1 - idx / 6;                       // rows n-1 .. n-32
     if (r >= 0) sX[(r % W) * 6 + idx % 6] = x[6 * (long long)r + idx % 6];
   }
-  // producer state: label of the next row to issue (prefetched one step earlier), entering x value
   int nf = 0; long long nrs = 0; double xin = 0.0;
   auto issue = [&](int i) {                               // stream row i (label in nf/nrs) into ring[i % D]
     if (i >= 0) {
-      const int cnt = i - nf;
-      if (lane == 0) sF[i % D] = nf;
+      const int upto = i < n_given ? i : n_given;         // given rows only act on the pivots' columns
+      const int cnt = upto > nf ? upto - nf : 0;
+      if (lane == 0) { sF[i % D] = nf; sCnt[i % D] = cnt; }
       const double* row = L + nrs * 36;
       for (int o = lane; o < cnt * 18; o += 32) cp_async16(&ring[i % D][2 * o], row + 2 * o);
     }
@@ -710,14 +761,14 @@ env_backsolve_ring_kernel(EnvView e, const double* __restrict__ L, double* __res
   const int jr = tid / 6, cc = tid - jr * 6;              // consumer output (tid < 192 -> jr < 32)
   for (int i = n - 1; i >= 0; --i) {
     if (producer) {
-      issue(i - (D - 1));                                 // label was fetched during the previous step
-      const int i2 = i - D;                               // label for the next issue
+      issue(i - (D - 1));
+      const int i2 = i - D;
       if (i2 >= 0) { nf = e.first[i2]; nrs = e.row_start[i2]; }
-      cp_async_wait<D - 1>();                             // row i has landed
+      cp_async_wait<D - 1>();
     }
     __syncthreads();                                      // (A) row i visible; x_i final
     if (!producer) {
-      const int f = sF[i % D], cnt = i - f;
+      const int f = sF[i % D], cnt = sCnt[i % D];
       const double* cur = ring[i % D];
       if (tid < 6) x[6 * (long long)i + tid] = sX[(i % W) * 6 + tid];
       if (jr < cnt) {
@@ -731,10 +782,70 @@ env_backsolve_ring_kernel(EnvView e, const double* __restrict__ L, double* __res
     }
     __syncthreads();                                      // (B) updates applied; slot of row i is free
     if (producer && lane < 6) {
-      if (i - W >= 0) sX[(i % W) * 6 + lane] = xin;       // row i-W enters the window
+      if (i - W >= 0) sX[(i % W) * 6 + lane] = xin;
       if (i - 1 - W >= 0) xin = x[6 * (long long)(i - 1 - W) + lane];
     }
   }
+}
+
+// ---- twisted solve helpers -------------------------------------------------------------------------------
+// Reversed copy of the bottom part: row r' of the reversed matrix = original row n-1-r'; its lower blocks are the
+// transposes of the original column's blocks.  One CTA per reversed row.
+__global__ void env_reverse_gather_kernel(EnvView eo, EnvView eb, const double* __restrict__ Lo, double* __restrict__ Lb,
+                                          const double* __restrict__ zo, double* __restrict__ zb) {
+  const int n = eo.n;
+  for (int rp = blockIdx.x; rp < eb.n; rp += gridDim.x) {
+    const int ir = n - 1 - rp;                            // original index of this reversed row
+    const int f = eb.first[rp];
+    const long long base = eb.row_start[rp] * 36;
+    const int nblk = rp - f + 1;
+    for (int o = threadIdx.x; o < nblk * 36; o += blockDim.x) {
+      const int cb = o / 36, el = o - cb * 36, a = el / 6, b2 = el - a * 6;
+      const int ic = n - 1 - (f + cb);                    // original row of the coupled pose (ic >= ir)
+      // reversed block (rp, f+cb)[a][b2] = original block (ic, ir)[b2][a]
+      Lb[base + o] = Lo[(eo.row_start[ic] + (ir - eo.first[ic])) * 36 + b2 * 6 + a];
+    }
+    if (threadIdx.x < 6) zb[6 * (long long)rp + threadIdx.x] = zo[6 * (long long)ir + threadIdx.x];
+  }
+}
+
+// Separator system: S = W_top + W_bot^T(reversed) - A_sep ; z_sep = z_top + z_bot(reversed) - z_orig
+__global__ void env_twist_combine_kernel(EnvView eo, int m, int bs, const double* __restrict__ Lo, const double* __restrict__ zo,
+                                         const double* __restrict__ wtop, const double* __restrict__ wbot,
+                                         const double* __restrict__ ztop, const double* __restrict__ zbot,
+                                         double* __restrict__ Lsep, double* __restrict__ zsep) {
+  const int nblk = bs * (bs + 1) / 2;
+  for (int o = threadIdx.x; o < nblk * 36; o += blockDim.x) {
+    const int blk = o / 36, el = o - blk * 36, a = el / 6, b2 = el - a * 6;
+    int si, sj;
+    tri_decode(blk, si, sj);                              // si >= sj, dense lower envelope: block index si(si+1)/2 + sj
+    const int i = m + si, j = m + sj;
+    const double orig = (j >= eo.first[i]) ? Lo[(eo.row_start[i] + (j - eo.first[i])) * 36 + el] : 0.0;
+    const int ur = bs - 1 - sj, uc = bs - 1 - si;         // reversed-local indices: (ur >= uc)
+    const double top = wtop[((long long)si * bs + sj) * 36 + el];
+    const double bot = wbot[((long long)ur * bs + uc) * 36 + b2 * 6 + a];
+    Lsep[o] = top + bot - orig;
+  }
+  for (int o = threadIdx.x; o < bs * 6; o += blockDim.x) {
+    const int si = o / 6, q = o - si * 6;
+    zsep[o] = ztop[o] + zbot[(bs - 1 - si) * 6 + q] - zo[6 * (long long)(m + si) + q];
+  }
+}
+
+// x_top[m..m+bs) = x_sep ; x_bot tail (reversed) = x_sep
+__global__ void env_twist_place_sep_kernel(int m, int bs, int nb_stop, const double* __restrict__ xsep, double* __restrict__ xtop, double* __restrict__ xbot) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= bs * 6) return;
+  const int si = o / 6, q = o - si * 6;
+  xtop[6 * (long long)(m + si) + q] = xsep[o];
+  xbot[6 * (long long)(nb_stop + (bs - 1 - si)) + q] = xsep[o];
+}
+// x[orig i] = x_bot[n-1-i] for the bottom pivots
+__global__ void env_twist_scatter_kernel(int n, int nb_stop, const double* __restrict__ xbot, double* __restrict__ x) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= nb_stop * 6) return;
+  const int rp = o / 6, q = o - rp * 6;
+  x[6 * (long long)(n - 1 - rp) + q] = xbot[o];
 }
 
 }  // namespace lvba

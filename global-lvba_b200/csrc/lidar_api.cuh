@@ -119,7 +119,7 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
     for (int64_t q = vox_ptr[a]; q < vox_ptr[a + 1]; ++q) first_raw[pose_idx[q]] = std::min(first_raw[pose_idx[q]], m);
   }
   LVBA_TRY(P->env.build(first_raw, s, &P->h2d));
-  LVBA_TRY(P->solver.prepare(P->env));
+  LVBA_TRY(P->solver.prepare(P->env, s));
   lap("envelope+solver alloc");
 
   // ---- shard: voxel -> owner of its lowest pose index

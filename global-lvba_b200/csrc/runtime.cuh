@@ -251,13 +251,23 @@ inline std::vector<unsigned short> build_pair_map(int P, int n_threads) {
 struct EnvSolver {
   DevBuf<double> L, dinv, z;
   DevBuf<int> status;
-  DevBuf<unsigned short> pair_map;   // thread -> slot pair of the register-window kernel (depends on P only)
-  int map_P = 0;
+  DevBuf<unsigned short> pair_map[4];   // thread -> slot pair of the register-window kernel, per P in {8,16,24,31}
+  bool have_map[4] = {false, false, false, false};
   DevBuf<long long> dbg;        // LVBA_FACTOR_TIMING=1: per-step phase clocks of the register-window kernel
   int dbg_dumped = 0;
   bool configured = false;
   bool force_generic = false;   // tests: exercise the wide-envelope kernel on narrow problems
-  int prepare(const Envelope& env) {
+  // ---- twisted (two-ended) factorisation: top half in natural order on one SM, bottom half reversed on another,
+  //      joined at a separator of `tw_bs` rows (see envelope.cuh, FactorJob)
+  bool tw = false;
+  int tw_m = 0, tw_send = 0, tw_bs = 0, tw_nb = 0, tw_nbstop = 0;
+  Envelope env_bot, env_sep;
+  DevBuf<double> Lbot, dinv_bot, zbot, xbot, wtop, wbot, ztopd, zbotd, Lsep, dinv_sep, zsep, xsep;
+
+  static int pid(int mc) { return mc <= 7 ? 0 : mc <= 15 ? 1 : mc <= 23 ? 2 : 3; }
+  static int pval(int id) { return id == 0 ? 8 : id == 1 ? 16 : id == 2 ? 24 : 31; }
+
+  int prepare(const Envelope& env, cudaStream_t s) {
     if (env.max_col > kEnvMaxCol)
       return fail(LVBA_ERR_UNSUPPORTED, "envelope column height %d exceeds the factor kernel limit %d", env.max_col, kEnvMaxCol);
     {
@@ -280,10 +290,84 @@ struct EnvSolver {
       LVBA_CUDA(cudaFuncSetAttribute(env_factor_reg_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RegCfg<31>::kSmem));
       configured = true;
     }
+    // ---- twisted split: worthwhile when each half is many pivots long
+    tw = false;
+    const char* nt = getenv("LVBA_NO_TWIST");
+    const bool reg_ok = env.max_col <= 30 && env.n >= 3 && !force_generic;
+    if (reg_ok && env.n >= 256 && !(nt && nt[0] == '1')) {
+      const int n = env.n;
+      const int m = n / 2;
+      const int send = env.last[m - 1] + 1;            // rows >= send do not couple to rows < m
+      const int bs = send - m;
+      if (bs >= 3 && bs <= 30 && send < n - 32) {
+        tw_m = m; tw_send = send; tw_bs = bs; tw_nb = n - m; tw_nbstop = n - send;
+        std::vector<int> fb((size_t)tw_nb);
+        for (int rp = 0; rp < tw_nb; ++rp) fb[rp] = n - 1 - env.last[n - 1 - rp];     // reversed row couples up to the original column's last row
+        int64_t dummy = 0;
+        LVBA_TRY(env_bot.build(fb, s, &dummy));
+        std::vector<int> fs((size_t)bs, 0);
+        LVBA_TRY(env_sep.build(fs, s, &dummy));
+        if (env_bot.max_col <= 30) {
+          LVBA_TRY(Lbot.alloc((size_t)env_bot.nblocks * 36)); LVBA_TRY(dinv_bot.alloc((size_t)tw_nb * 36));
+          LVBA_TRY(zbot.alloc((size_t)tw_nb * 6)); LVBA_TRY(xbot.alloc((size_t)tw_nb * 6));
+          LVBA_TRY(wtop.alloc((size_t)bs * bs * 36)); LVBA_TRY(wbot.alloc((size_t)bs * bs * 36));
+          LVBA_TRY(ztopd.alloc((size_t)bs * 6)); LVBA_TRY(zbotd.alloc((size_t)bs * 6));
+          LVBA_TRY(Lsep.alloc((size_t)env_sep.nblocks * 36)); LVBA_TRY(dinv_sep.alloc((size_t)bs * 36));
+          LVBA_TRY(zsep.alloc((size_t)bs * 6)); LVBA_TRY(xsep.alloc((size_t)bs * 6));
+          LVBA_TRY(wtop.zero(s)); LVBA_TRY(wbot.zero(s));
+          tw = true;
+        }
+      }
+    }
     return LVBA_OK;
   }
   static size_t factor_smem() { return sizeof(double) * (2 * kEnvMaxCol * 36 + 36 + 8); }
-  // Solves (H + diag(dadd)) x = z_in where z already holds the right-hand side.  x may alias nothing.
+
+  int ensure_map(int id, cudaStream_t s) {
+    if (have_map[id]) return LVBA_OK;
+    const int P = pval(id);
+    const int nthr = id == 0 ? RegCfg<8>::kPairThreads : id == 1 ? RegCfg<16>::kPairThreads : id == 2 ? RegCfg<24>::kPairThreads : RegCfg<31>::kPairThreads;
+    std::vector<unsigned short> m = build_pair_map(P, nthr);
+    size_t cnt = 0; for (auto v2 : m) cnt += v2 != 0xffff;
+    if ((int)cnt != P * (P + 1) / 2) return fail(LVBA_ERR_UNSUPPORTED, "pair map for P=%d covers %zu of %d pairs", P, cnt, P * (P + 1) / 2);
+    LVBA_TRY(pair_map[id].upload(m, s));
+    LVBA_CUDA(cudaStreamSynchronize(s));               // `m` is a local vector
+    have_map[id] = true;
+    return LVBA_OK;
+  }
+  int launch_factor(int id, int grid, const FactorJobs& jobs, cudaStream_t s, int64_t* launches) {
+    LVBA_TRY(ensure_map(id, s));
+    const unsigned short* pm = pair_map[id].p;
+    if (id == 0) env_factor_reg_kernel<8><<<grid, RegCfg<8>::kThreads, RegCfg<8>::kSmem, s>>>(jobs, pm, status.p, dbg.p);
+    else if (id == 1) env_factor_reg_kernel<16><<<grid, RegCfg<16>::kThreads, RegCfg<16>::kSmem, s>>>(jobs, pm, status.p, dbg.p);
+    else if (id == 2) env_factor_reg_kernel<24><<<grid, RegCfg<24>::kThreads, RegCfg<24>::kSmem, s>>>(jobs, pm, status.p, dbg.p);
+    else env_factor_reg_kernel<31><<<grid, RegCfg<31>::kThreads, RegCfg<31>::kSmem, s>>>(jobs, pm, status.p, dbg.p);
+    ++*launches;
+    return LVBA_OK;
+  }
+  void dump_timing(const Envelope& env, cudaStream_t s) {
+    if (!(dbg.p && dbg_dumped < 2)) return;
+    cudaStreamSynchronize(s);
+    const int nsteps = tw ? tw_m : env.n;
+    std::vector<long long> h((size_t)env.n * 32);
+    cudaMemcpy(h.data(), dbg.p, h.size() * 8, cudaMemcpyDeviceToHost);
+    const int k0 = 64, k1 = nsteps - 64;
+    if (k1 <= k0) return;
+    fprintf(stderr, "[factor timing] n=%d max_col=%d twisted=%d  role: scale | bar1 wait | main | bar2 wait | step   (cycles, avg over k=%d..%d)\n", env.n, env.max_col, (int)tw, k0, k1);
+    for (int role = 0; role < 8; ++role) {
+      double acc[5] = {0, 0, 0, 0, 0};
+      for (int k = k0; k < k1; ++k) {
+        const long long* a = &h[((size_t)k * 8 + role) * 4];
+        const long long* b = &h[((size_t)(k + 1) * 8 + role) * 4];
+        acc[0] += a[1] - a[0]; acc[1] += a[2] - a[1]; acc[2] += a[3] - a[2]; acc[3] += b[0] - a[3]; acc[4] += b[0] - a[0];
+      }
+      fprintf(stderr, "  role %d (%s): %8.0f %8.0f %8.0f %8.0f %8.0f\n", role, role < 4 ? "pair warp" : (role == 4 ? "pivot LDLT" : role == 5 ? "fwd subst" : "prefetch "),
+              acc[0] / (k1 - k0), acc[1] / (k1 - k0), acc[2] / (k1 - k0), acc[3] / (k1 - k0), acc[4] / (k1 - k0));
+    }
+    ++dbg_dumped;
+  }
+
+  // Solves (H + diag(dadd)) x = z_in where z already holds the right-hand side.
   int solve(const Envelope& env, const double* H, const double* dadd, double* x, cudaStream_t s, int64_t* launches) {
     const EnvView v = env.view();
     LVBA_CUDA(cudaMemcpyAsync(L.p, H, (size_t)env.nblocks * 36 * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -291,45 +375,51 @@ struct EnvSolver {
     const int n6 = 6 * env.n;
     env_add_diag_kernel<<<(n6 + 255) / 256, 256, 0, s>>>(v, dadd, L.p);
     ++*launches;
-    // column height < P: register-resident sliding-window kernel (envelope.cuh v2); wider: global-memory kernel
     const int mc = env.max_col;
     const bool reg_path = mc <= 30 && env.n >= 3 && !force_generic;
-    if (reg_path) {
-      const int P = mc <= 7 ? 8 : mc <= 15 ? 16 : mc <= 23 ? 24 : 31;
-      if (map_P != P) {
-        const int nthr = P == 8 ? RegCfg<8>::kPairThreads : P == 16 ? RegCfg<16>::kPairThreads : P == 24 ? RegCfg<24>::kPairThreads : RegCfg<31>::kPairThreads;
-        std::vector<unsigned short> m = build_pair_map(P, nthr);
-        size_t cnt = 0; for (auto v2 : m) cnt += v2 != 0xffff;
-        if ((int)cnt != P * (P + 1) / 2) return fail(LVBA_ERR_UNSUPPORTED, "pair map for P=%d covers %zu of %d pairs", P, cnt, P * (P + 1) / 2);
-        LVBA_TRY(pair_map.upload(m, s));
-        map_P = P;
-      }
-      if (mc <= 7) env_factor_reg_kernel<8><<<1, RegCfg<8>::kThreads, RegCfg<8>::kSmem, s>>>(v, pair_map.p, L.p, dinv.p, z.p, status.p, dbg.p);
-      else if (mc <= 15) env_factor_reg_kernel<16><<<1, RegCfg<16>::kThreads, RegCfg<16>::kSmem, s>>>(v, pair_map.p, L.p, dinv.p, z.p, status.p, dbg.p);
-      else if (mc <= 23) env_factor_reg_kernel<24><<<1, RegCfg<24>::kThreads, RegCfg<24>::kSmem, s>>>(v, pair_map.p, L.p, dinv.p, z.p, status.p, dbg.p);
-      else env_factor_reg_kernel<31><<<1, RegCfg<31>::kThreads, RegCfg<31>::kSmem, s>>>(v, pair_map.p, L.p, dinv.p, z.p, status.p, dbg.p);
-      if (dbg.p && dbg_dumped < 2) {
-        cudaStreamSynchronize(s);
-        std::vector<long long> h((size_t)env.n * 32);
-        cudaMemcpy(h.data(), dbg.p, h.size() * 8, cudaMemcpyDeviceToHost);
-        // average per role: scale (1-0), barrier-1 wait (2-1), main phase (3-2), barrier-2 wait (next 0 - 3), step (next 0 - 0)
-        const int k0 = 64, k1 = env.n - 64;
-        fprintf(stderr, "[factor timing] n=%d max_col=%d   role: scale | bar1 wait | main | bar2 wait | step   (cycles, avg over k=%d..%d)\n", env.n, mc, k0, k1);
-        for (int role = 0; role < 8; ++role) {
-          double acc[5] = {0, 0, 0, 0, 0};
-          for (int k = k0; k < k1; ++k) {
-            const long long* a = &h[((size_t)k * 8 + role) * 4];
-            const long long* b = &h[((size_t)(k + 1) * 8 + role) * 4];
-            acc[0] += a[1] - a[0]; acc[1] += a[2] - a[1]; acc[2] += a[3] - a[2]; acc[3] += b[0] - a[3]; acc[4] += b[0] - a[0];
-          }
-          fprintf(stderr, "  role %d (%s): %8.0f %8.0f %8.0f %8.0f %8.0f\n", role, role < 4 ? "pair warp" : (role == 4 ? "inverse  " : role == 5 ? "fwd subst" : "prefetch "),
-                  acc[0] / (k1 - k0), acc[1] / (k1 - k0), acc[2] / (k1 - k0), acc[3] / (k1 - k0), acc[4] / (k1 - k0));
-        }
-        ++dbg_dumped;
-      }
+    if (reg_path && tw) {
+      // ---------------- twisted: two half factorisations on two SMs, joined at the separator
+      const int n = env.n, m = tw_m, bs = tw_bs;
+      EnvView vt = v; vt.n = tw_send;                               // the top instance is a prefix of the matrix
+      const EnvView vb = env_bot.view(), vs = env_sep.view();
+      env_reverse_gather_kernel<<<std::min(tw_nb, 2048), 128, 0, s>>>(v, vb, L.p, Lbot.p, z.p, zbot.p);
+      FactorJobs jobs;
+      jobs.j[0] = FactorJob{vt, L.p, dinv.p, z.p, m, wtop.p, ztopd.p};
+      jobs.j[1] = FactorJob{vb, Lbot.p, dinv_bot.p, zbot.p, tw_nbstop, wbot.p, zbotd.p};
+      ++*launches;
+      LVBA_TRY(launch_factor(pid(std::max(mc, env_bot.max_col)), 2, jobs, s, launches));
+      dump_timing(env, s);
+      env_twist_combine_kernel<<<1, 1024, 0, s>>>(v, m, bs, L.p, z.p, wtop.p, wbot.p, ztopd.p, zbotd.p, Lsep.p, zsep.p);
+      FactorJobs js;
+      js.j[0] = FactorJob{vs, Lsep.p, dinv_sep.p, zsep.p, bs, nullptr, nullptr};
+      js.j[1] = js.j[0];
+      ++*launches;
+      LVBA_TRY(launch_factor(pid(env_sep.max_col), 1, js, s, launches));
+      env_ldl_apply_kernel<<<(bs + 127) / 128, 128, 0, s>>>(bs, dinv_sep.p, zsep.p, xsep.p);
+      BacksolveJobs bj;
+      bj.j[0] = BacksolveJob{vs, Lsep.p, xsep.p, bs};
+      bj.j[1] = bj.j[0];
+      env_backsolve_ring_kernel<<<1, kBsThreads, 0, s>>>(bj);
+      env_ldl_apply_kernel<<<(m + 127) / 128, 128, 0, s>>>(m, dinv.p, z.p, x);
+      env_ldl_apply_kernel<<<(tw_nbstop + 127) / 128, 128, 0, s>>>(tw_nbstop, dinv_bot.p, zbot.p, xbot.p);
+      env_twist_place_sep_kernel<<<(bs * 6 + 127) / 128, 128, 0, s>>>(m, bs, tw_nbstop, xsep.p, x, xbot.p);
+      bj.j[0] = BacksolveJob{vt, L.p, x, m};
+      bj.j[1] = BacksolveJob{vb, Lbot.p, xbot.p, tw_nbstop};
+      env_backsolve_ring_kernel<<<2, kBsThreads, 0, s>>>(bj);
+      env_twist_scatter_kernel<<<(tw_nbstop * 6 + 255) / 256, 256, 0, s>>>(n, tw_nbstop, xbot.p, x);
+      *launches += 7;
+    } else if (reg_path) {
+      FactorJobs jobs;
+      jobs.j[0] = FactorJob{v, L.p, dinv.p, z.p, env.n, nullptr, nullptr};
+      jobs.j[1] = jobs.j[0];
+      LVBA_TRY(launch_factor(pid(mc), 1, jobs, s, launches));
+      dump_timing(env, s);
       env_ldl_apply_kernel<<<(env.n + 127) / 128, 128, 0, s>>>(env.n, dinv.p, z.p, x);
-      env_backsolve_ring_kernel<<<1, kBsThreads, 0, s>>>(v, L.p, x);
-      *launches += 3;
+      BacksolveJobs bj;
+      bj.j[0] = BacksolveJob{v, L.p, x, env.n};
+      bj.j[1] = bj.j[0];
+      env_backsolve_ring_kernel<<<1, kBsThreads, 0, s>>>(bj);
+      *launches += 2;
     } else {
       env_factor_kernel<<<1, kFactorThreads, factor_smem(), s>>>(v, L.p, dinv.p, z.p, status.p);
       env_backsolve_kernel<<<1, 32, 0, s>>>(v, L.p, dinv.p, z.p, x);

@@ -128,7 +128,7 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   if (P->n_rows > 0) {
     first_raw.resize(P->n_rows);
     LVBA_TRY(P->env.build(first_raw, s, &P->h2d));
-    LVBA_TRY(P->solver.prepare(P->env));
+    LVBA_TRY(P->solver.prepare(P->env, s));
   }
 
   // ---- shard: landmark -> owner of its lowest camera index

@@ -146,3 +146,22 @@ def test_config_B_single_iteration_cost_match(gpu_pkg):
     r2_ref = lo.only_residual(p["vox_ptr"], p["pose_idx"], p["clusters"], trial)
     assert abs(r2 - r2_ref) <= 1e-8 * abs(r2_ref)
     P.close()
+
+
+def test_twisted_and_single_ended_factorisation_agree(gpu_pkg, monkeypatch):
+    """n >= 256 pose systems are factorised from both ends on two SMs (top half natural order, bottom half
+    reversed, joined at a separator).  Same solution as the single-ended and the generic kernels."""
+    p = synth.make_config("B", visual=False)
+    dx = {}
+    for mode, env in (("twisted", {}), ("single", {"LVBA_NO_TWIST": "1"}), ("generic", {"LVBA_FORCE_GENERIC_SOLVER": "1"})):
+        for k in ("LVBA_NO_TWIST", "LVBA_FORCE_GENERIC_SOLVER"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        P = gpu_pkg.LidarProblem(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"])
+        P.build()
+        dx[mode] = P.solve(0.05)
+        P.close()
+    ref = np.abs(dx["generic"]).max()
+    assert np.abs(dx["twisted"] - dx["generic"]).max() <= 1e-8 * ref
+    assert np.abs(dx["single"] - dx["generic"]).max() <= 1e-8 * ref
