@@ -15,6 +15,7 @@
 
 #include "../../include/lvba_b200.h"
 #include "envelope.cuh"
+#include "factor_la.cuh"
 
 namespace lvba {
 
@@ -254,9 +255,10 @@ struct EnvSolver {
   DevBuf<unsigned short> pair_map[4];   // thread -> slot pair of the register-window kernel, per P in {8,16,24,31}
   bool have_map[4] = {false, false, false, false};
   DevBuf<long long> dbg;        // LVBA_FACTOR_TIMING=1: per-step phase clocks of the register-window kernel
-  int dbg_dumped = 0;
+  int dbg_dumped = 0, dbg_max_dumps = 2;
   bool configured = false;
   bool force_generic = false;   // tests: exercise the wide-envelope kernel on narrow problems
+  bool use_la = true, use_warp_bs = true, la_first = true;
   // ---- twisted (two-ended) factorisation: top half in natural order on one SM, bottom half reversed on another,
   //      joined at a separator of `tw_bs` rows (see envelope.cuh, FactorJob)
   bool tw = false;
@@ -270,6 +272,13 @@ struct EnvSolver {
   int prepare(const Envelope& env, cudaStream_t s) {
     if (env.max_col > kEnvMaxCol)
       return fail(LVBA_ERR_UNSUPPORTED, "envelope column height %d exceeds the factor kernel limit %d", env.max_col, kEnvMaxCol);
+    {
+      const char* sv = getenv("LVBA_SOLVER");                     // development switch: v6 = first register-window kernel
+      use_la = !(sv && sv[0] == 'v' && sv[1] == '6');
+      la_first = !(sv && sv[0] == 'v' && sv[1] == '7' && sv[2] == 'l');   // v7l: look-ahead warpgroup on the last warp ids
+      const char* bv = getenv("LVBA_BACKSOLVE");                  // development switch: ring = block-barrier ring kernel
+      use_warp_bs = !(bv && bv[0] == 'r');
+    }
     {
       const char* fg = getenv("LVBA_FORCE_GENERIC_SOLVER");      // tests: run the wide-envelope kernel on narrow problems
       force_generic = fg && fg[0] == '1';
@@ -288,6 +297,15 @@ struct EnvSolver {
       LVBA_CUDA(cudaFuncSetAttribute(env_factor_reg_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RegCfg<16>::kSmem));
       LVBA_CUDA(cudaFuncSetAttribute(env_factor_reg_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RegCfg<24>::kSmem));
       LVBA_CUDA(cudaFuncSetAttribute(env_factor_reg_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RegCfg<31>::kSmem));
+      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<8>::kSmem));
+      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<8>::kSmem));
+      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<16>::kSmem));
+      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<16>::kSmem));
+      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<24>::kSmem));
+      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<24, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<24>::kSmem));
+      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<31>::kSmem));
+      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<31, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<31>::kSmem));
+      LVBA_CUDA(cudaFuncSetAttribute(env_backsolve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBsSmem));
       configured = true;
     }
     // ---- twisted split: worthwhile when each half is many pivots long
@@ -338,6 +356,17 @@ struct EnvSolver {
   int launch_factor(int id, int grid, const FactorJobs& jobs, cudaStream_t s, int64_t* launches) {
     LVBA_TRY(ensure_map(id, s));
     const unsigned short* pm = pair_map[id].p;
+    if (use_la) {
+#define LVBA_LAUNCH_LA(PP, FIRST) env_factor_la_kernel<PP, FIRST><<<grid, LaCfg<PP>::kThreads, LaCfg<PP>::kSmem, s>>>(jobs, pm, status.p, dbg.p)
+      if (la_first) {
+        if (id == 0) LVBA_LAUNCH_LA(8, true); else if (id == 1) LVBA_LAUNCH_LA(16, true); else if (id == 2) LVBA_LAUNCH_LA(24, true); else LVBA_LAUNCH_LA(31, true);
+      } else {
+        if (id == 0) LVBA_LAUNCH_LA(8, false); else if (id == 1) LVBA_LAUNCH_LA(16, false); else if (id == 2) LVBA_LAUNCH_LA(24, false); else LVBA_LAUNCH_LA(31, false);
+      }
+#undef LVBA_LAUNCH_LA
+      ++*launches;
+      return LVBA_OK;
+    }
     if (id == 0) env_factor_reg_kernel<8><<<grid, RegCfg<8>::kThreads, RegCfg<8>::kSmem, s>>>(jobs, pm, status.p, dbg.p);
     else if (id == 1) env_factor_reg_kernel<16><<<grid, RegCfg<16>::kThreads, RegCfg<16>::kSmem, s>>>(jobs, pm, status.p, dbg.p);
     else if (id == 2) env_factor_reg_kernel<24><<<grid, RegCfg<24>::kThreads, RegCfg<24>::kSmem, s>>>(jobs, pm, status.p, dbg.p);
@@ -345,15 +374,19 @@ struct EnvSolver {
     ++*launches;
     return LVBA_OK;
   }
+  void launch_backsolve(int grid, const BacksolveJobs& bj, cudaStream_t s) {
+    if (use_warp_bs) env_backsolve_warp_kernel<<<grid, 64, kBsSmem, s>>>(bj);
+    else env_backsolve_ring_kernel<<<grid, kBsThreads, 0, s>>>(bj);
+  }
   void dump_timing(const Envelope& env, cudaStream_t s) {
-    if (!(dbg.p && dbg_dumped < 2)) return;
+    if (!(dbg.p && dbg_dumped < dbg_max_dumps)) return;
     cudaStreamSynchronize(s);
     const int nsteps = tw ? tw_m : env.n;
     std::vector<long long> h((size_t)env.n * 32);
     cudaMemcpy(h.data(), dbg.p, h.size() * 8, cudaMemcpyDeviceToHost);
     const int k0 = 64, k1 = nsteps - 64;
     if (k1 <= k0) return;
-    fprintf(stderr, "[factor timing] n=%d max_col=%d twisted=%d  role: scale | bar1 wait | main | bar2 wait | step   (cycles, avg over k=%d..%d)\n", env.n, env.max_col, (int)tw, k0, k1);
+    fprintf(stderr, "[factor timing] n=%d max_col=%d twisted=%d la=%d la_first=%d : per role  s1-s0 | s2-s1 | s3-s2 | next s0-s3 | step   (cycles, avg over k=%d..%d)\n", env.n, env.max_col, (int)tw, (int)use_la, (int)la_first, k0, k1);
     for (int role = 0; role < 8; ++role) {
       double acc[5] = {0, 0, 0, 0, 0};
       for (int k = k0; k < k1; ++k) {
@@ -361,8 +394,7 @@ struct EnvSolver {
         const long long* b = &h[((size_t)(k + 1) * 8 + role) * 4];
         acc[0] += a[1] - a[0]; acc[1] += a[2] - a[1]; acc[2] += a[3] - a[2]; acc[3] += b[0] - a[3]; acc[4] += b[0] - a[0];
       }
-      fprintf(stderr, "  role %d (%s): %8.0f %8.0f %8.0f %8.0f %8.0f\n", role, role < 4 ? "pair warp" : (role == 4 ? "pivot LDLT" : role == 5 ? "fwd subst" : "prefetch "),
-              acc[0] / (k1 - k0), acc[1] / (k1 - k0), acc[2] / (k1 - k0), acc[3] / (k1 - k0), acc[4] / (k1 - k0));
+      fprintf(stderr, "  role %d: %8.0f %8.0f %8.0f %8.0f %8.0f\n", role, acc[0] / (k1 - k0), acc[1] / (k1 - k0), acc[2] / (k1 - k0), acc[3] / (k1 - k0), acc[4] / (k1 - k0));
     }
     ++dbg_dumped;
   }
@@ -399,13 +431,13 @@ struct EnvSolver {
       BacksolveJobs bj;
       bj.j[0] = BacksolveJob{vs, Lsep.p, xsep.p, bs};
       bj.j[1] = bj.j[0];
-      env_backsolve_ring_kernel<<<1, kBsThreads, 0, s>>>(bj);
+      launch_backsolve(1, bj, s);
       env_ldl_apply_kernel<<<(m + 127) / 128, 128, 0, s>>>(m, dinv.p, z.p, x);
       env_ldl_apply_kernel<<<(tw_nbstop + 127) / 128, 128, 0, s>>>(tw_nbstop, dinv_bot.p, zbot.p, xbot.p);
       env_twist_place_sep_kernel<<<(bs * 6 + 127) / 128, 128, 0, s>>>(m, bs, tw_nbstop, xsep.p, x, xbot.p);
       bj.j[0] = BacksolveJob{vt, L.p, x, m};
       bj.j[1] = BacksolveJob{vb, Lbot.p, xbot.p, tw_nbstop};
-      env_backsolve_ring_kernel<<<2, kBsThreads, 0, s>>>(bj);
+      launch_backsolve(2, bj, s);
       env_twist_scatter_kernel<<<(tw_nbstop * 6 + 255) / 256, 256, 0, s>>>(n, tw_nbstop, xbot.p, x);
       *launches += 7;
     } else if (reg_path) {
@@ -418,7 +450,7 @@ struct EnvSolver {
       BacksolveJobs bj;
       bj.j[0] = BacksolveJob{v, L.p, x, env.n};
       bj.j[1] = bj.j[0];
-      env_backsolve_ring_kernel<<<1, kBsThreads, 0, s>>>(bj);
+      launch_backsolve(1, bj, s);
       *launches += 2;
     } else {
       env_factor_kernel<<<1, kFactorThreads, factor_smem(), s>>>(v, L.p, dinv.p, z.p, status.p);
