@@ -1,4 +1,5 @@
-// factor_la.cuh — register-window block LDL^T with a panel look-ahead group ("v7").
+// factor_la.cuh — register-window block LDL^T with a panel look-ahead group, and the single-warp backward
+// substitution that follows it.
 //
 // Same job as SimplicialLDLT in BALM2::damping_iter (reference include/BALM/bavoxel.hpp:695-710, lower
 // triangle, no pivoting — SURVEY.md Q4/Q5) and as the DENSE_SCHUR Cholesky of the reduced camera system
@@ -6,17 +7,16 @@
 //
 // One CTA walks the pivot columns.  Every live 6x6 block of the trailing window (rows/cols k..k+P-1) lives in
 // the registers of one PAIR thread for its whole life (thread <-> unordered slot pair {a,b}, slot = row mod P).
-// What is new against the first register-window kernel:
 //   * symmetric update form.  The stored block G always has its rows on slot a and its columns on slot b,
 //     whichever of the two is the lower row: A_ab -= L_a D L_b^T = L_a T_b^T holds for both orientations, so a
-//     thread reads the SAME two shared-memory operands (L of slot a, T of slot b) at every step and the 32 lanes
-//     of a warp (an 8x4 tile of the slot triangle) touch 8 + 4 distinct operands: one wavefront per LDS.128;
+//     thread reads the SAME two shared-memory operands (L of slot a, T of slot b) at every step;
 //   * the look-ahead group owns the NEXT pivot column.  During step k it applies column k to column k+1 itself
-//     (30 block updates), factorises D_{k+1} (6x6 LDL^T in registers), scales the column and publishes
-//     L_{.,k+1} / T_{.,k+1} for step k+1, all overlapped with the pair threads' trailing update of step k.  The
-//     pair threads therefore never wait for a scale phase: ONE block barrier per pivot column (was two, with the
-//     scale serialised between them);
-//   * the entering row is streamed global -> shared with cp.async (no staging registers).
+//     (30 block updates), inverts D_{k+1} (two 3x3 adjugates + Schur complement: two reciprocals on the dependent
+//     chain instead of the six of a scalar LDL^T), scales the column and publishes L_{.,k+1} / T_{.,k+1} for step
+//     k+1, all overlapped with the pair threads' trailing update of step k: ONE block barrier per pivot column;
+//   * the entering row is streamed global -> shared with cp.async in its natural (contiguous) order.
+// Measured limits on one B200 SM (profiles/): the step is bound by shared-memory wavefronts (operand fetch of the
+// pair threads, ~3 wavefronts per LDS.128) and by the latency of the look-ahead chain, not by HBM.
 #pragma once
 #include "envelope.cuh"
 
@@ -35,8 +35,8 @@ struct LaCfg {
   static constexpr int S = 38;                                   // doubles per transposed block (16 B aligned, conflict-free over 8 slots)
   static constexpr bool kRealloc = kThreads > 512;               // P = 31: 640 threads launch at 96 registers
   static constexpr int kPairRegs = 104, kLaRegs = 64;            // 512*104 + 128*64 == 640*96
-  static constexpr int kDoubles = 6 * P * S + 2 * P * 36 + 2 * 36 + 36 + 2 * 24 + P * 6;
-  static constexpr size_t kSmem = sizeof(double) * (size_t)kDoubles + sizeof(long long) * P + sizeof(int) * (P + 4) + 32;
+  static constexpr int kDoubles = 6 * P * S + 2 * P * 36 + 2 * 36 + 36 + 2 * 36 + P * 6 + 48;
+  static constexpr size_t kSmem = sizeof(double) * (size_t)kDoubles + sizeof(long long) * 64 + sizeof(int) * 64 + 32;
 };
 
 LVBA_DEV void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
@@ -47,16 +47,71 @@ LVBA_DEV void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
 LVBA_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 LVBA_DEV void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+// Inverse of a symmetric 6x6 block from its lower triangle x[i(i+1)/2 + j] (i >= j), no pivoting:
+// D = [A B^T; B C] (3x3 blocks): A^-1 by the adjugate, W = B A^-1, S = C - W B^T, S^-1 by the adjugate,
+// K22 = S^-1, K21 = -S^-1 W, K11 = A^-1 - W^T K21.  Two reciprocals on the dependent chain.
+// K is returned as the packed lower triangle.  Needs det(A) != 0 and det(S) != 0 (a scalar LDL^T needs all six
+// leading minors non-zero).
+LVBA_DEV void sym3_adj_inverse(double a00, double a10, double a11, double a20, double a21, double a22, double (&o)[6]) {
+  const double c00 = a11 * a22 - a21 * a21;
+  const double c10 = a20 * a21 - a10 * a22;
+  const double c20 = a10 * a21 - a20 * a11;
+  const double c11 = a00 * a22 - a20 * a20;
+  const double c21 = a10 * a20 - a00 * a21;
+  const double c22 = a00 * a11 - a10 * a10;
+  const double det = a00 * c00 + a10 * c10 + a20 * c20;
+  const double r = __drcp_rn(det);
+  o[0] = c00 * r; o[1] = c10 * r; o[2] = c11 * r; o[3] = c20 * r; o[4] = c21 * r; o[5] = c22 * r;   // (0,0) (1,0) (1,1) (2,0) (2,1) (2,2)
+}
+LVBA_DEV void sym6_block_inverse(const double (&x)[21], double (&K)[21]) {
+  double Ai[6];
+  sym3_adj_inverse(x[LVBA_T(0, 0)], x[LVBA_T(1, 0)], x[LVBA_T(1, 1)], x[LVBA_T(2, 0)], x[LVBA_T(2, 1)], x[LVBA_T(2, 2)], Ai);
+  auto ai = [&](int i, int j) -> double { return i >= j ? Ai[i * (i + 1) / 2 + j] : Ai[j * (j + 1) / 2 + i]; };
+  double W[3][3];                                   // W = B A^-1, B[i][m] = x(3+i, m)
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      W[i][j] = x[LVBA_T(3 + i, 0)] * ai(0, j) + x[LVBA_T(3 + i, 1)] * ai(1, j) + x[LVBA_T(3 + i, 2)] * ai(2, j);
+  double Sm[6];                                     // S = C - W B^T (lower triangle)
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j)
+      Sm[i * (i + 1) / 2 + j] = x[LVBA_T(3 + i, 3 + j)] - (W[i][0] * x[LVBA_T(3 + j, 0)] + W[i][1] * x[LVBA_T(3 + j, 1)] + W[i][2] * x[LVBA_T(3 + j, 2)]);
+  double Si[6];
+  sym3_adj_inverse(Sm[0], Sm[1], Sm[2], Sm[3], Sm[4], Sm[5], Si);
+  auto si = [&](int i, int j) -> double { return i >= j ? Si[i * (i + 1) / 2 + j] : Si[j * (j + 1) / 2 + i]; };
+  double K21[3][3];                                 // K21 = -S^-1 W
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      K21[i][j] = -(si(i, 0) * W[0][j] + si(i, 1) * W[1][j] + si(i, 2) * W[2][j]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      K[LVBA_T(i, j)] = ai(i, j) - (W[0][i] * K21[0][j] + W[1][i] * K21[1][j] + W[2][i] * K21[2][j]);
+      K[LVBA_T(3 + i, 3 + j)] = si(i, j);
+    }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) K[LVBA_T(3 + i, j)] = K21[i][j];
+}
+
 #ifdef LVBA_LAB
 __device__ int g_la_mode = 0;      // solver_lab only: 1 = pair threads skip their update, 2 = look-ahead group skips its math
 #endif
 
-template <int P, bool kLaFirst>
+template <int P, bool kTiming>
 __global__ void __launch_bounds__(LaCfg<P>::kThreads, 1)
 env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_map, int* __restrict__ status,
                      long long* __restrict__ dbg_all) {
   using Cfg = LaCfg<P>;
   constexpr int S = Cfg::S;
+  constexpr int PS = P * S;                       // one parity of sL / sT / sA
   const FactorJob& J = jobs.j[blockIdx.x];
   const EnvView e = J.e;
   double* __restrict__ L = J.L;
@@ -65,42 +120,43 @@ env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_ma
   const int n_stop = J.n_stop;
   long long* dbg = (blockIdx.x == 0) ? dbg_all : nullptr;
   // optional phase clocks (LVBA_FACTOR_TIMING=1): dbg[(k*8 + role)*4 + stamp]
-#define LVBA_STAMP(role, stamp) do { if (dbg && lane == 0) dbg[((long long)k * 8 + (role)) * 4 + (stamp)] = clock64(); } while (0)
+#define LVBA_STAMP(role, stamp) do { if (kTiming && dbg && lane == 0) dbg[((long long)k * 8 + (role)) * 4 + (stamp)] = clock64(); } while (0)
 
   extern __shared__ __align__(16) double smem_la[];
   double* sL = smem_la;                          // [2][P][S] L_ik transposed ([q*6+x] = L[x][q]); parity = pivot column & 1
-  double* sT = sL + 2 * P * S;                   // [2][P][S] T_ik = A_ik (updated, unscaled), same layout
-  double* sA = sT + 2 * P * S;                   // [2][P][S] next-next column handed to the look-ahead group, same layout
-  double* sEnter = sA + 2 * P * S;               // [2][P][36] entering row by column slot, row-major blocks
+  double* sT = sL + 2 * PS;                      // [2][P][S] T_ik = A_ik (updated, unscaled), same layout
+  double* sA = sT + 2 * PS;                      // [2][P][S] next-next column handed to the look-ahead group, same layout
+  double* sEnter = sA + 2 * PS;                  // [2][P][36] entering row r: block (r, r-P+1+d) at index d (d = P-1: diagonal), row-major
   double* sDg = sEnter + 2 * P * 36;             // [2][36]   diagonal block of the next pivot (before column k's update)
   double* sDu = sDg + 72;                        // [36]      updated diagonal block of the next pivot (kept for the window dump)
-  double* sF = sDu + 36;                         // [2][24]   packed LDL^T factors of the pivot block
-  double* sZ = sF + 48;                          // [P][6]
-  long long* sRS = reinterpret_cast<long long*>(sZ + P * 6);   // [P]
-  int* sFirst = reinterpret_cast<int*>(sRS + P);               // [P]
+  double* sK = sDu + 36;                         // [2][36]   D^-1 of the pivot block (full symmetric, row-major)
+  double* sZ = sK + 72;                          // [P][6]
+  double* sZin = sZ + P * 6;                     // [8][6]   rhs entries of the rows about to enter (ring by row & 7)
+  long long* sLabRS = reinterpret_cast<long long*>(sZin + 48);   // [64] row_start of row r at r & 63 (ring, filled by cp.async)
+  int* sLabF = reinterpret_cast<int*>(sLabRS + 64);              // [64] first column of row r at r & 63
   const int tid = threadIdx.x, lane = tid & 31;
   const int n = e.n;
-  // warp-uniform roles.  kLaFirst puts the look-ahead warpgroup on the LOWEST warp ids (the warp scheduler's
-  // oldest-first tie break then favours its dependent chain over the pair warps' long independent DFMA runs)
-  const bool is_la = kLaFirst ? tid < Cfg::kLaThreads : tid >= Cfg::kPairThreads;
-  const int pt = kLaFirst ? tid - Cfg::kLaThreads : tid;       // pair thread index
+  const bool is_la = tid >= Cfg::kPairThreads;                 // warp-uniform
 #ifdef LVBA_LAB
   const int lab_mode = g_la_mode;
 #endif
 
   // ---------------- prologue: labels and rhs of the first P rows
-  for (int r = tid; r < P; r += Cfg::kThreads) {
-    if (r < n) { sFirst[r] = e.first[r]; sRS[r] = e.row_start[r]; } else { sFirst[r] = 0x7fffffff; sRS[r] = 0; }
-#pragma unroll
-    for (int q = 0; q < 6; ++q) sZ[r * 6 + q] = (r < n) ? z[6 * r + q] : 0.0;
+  for (int r = tid; r < 64; r += Cfg::kThreads) {
+    sLabF[r] = (r < n) ? e.first[r] : 0; sLabRS[r] = (r < n) ? e.row_start[r] : 0;
   }
-  for (int o = tid; o < 6 * P * S; o += Cfg::kThreads) sL[o] = 0.0;      // sL, sT, sA (padding included)
+  for (int o = tid; o < (P + 4) * 6; o += Cfg::kThreads) {             // rhs of rows 0..P-1 (window) and P..P+3 (entering ring)
+    const int r = o / 6, q = o - r * 6;
+    const double v = (r < n) ? z[6 * (long long)r + q] : 0.0;
+    if (r < P) sZ[o] = v; else sZin[(r & 7) * 6 + q] = v;
+  }
+  for (int o = tid; o < 6 * PS; o += Cfg::kThreads) sL[o] = 0.0;         // sL, sT, sA (padding included)
   __syncthreads();
 
   if (!is_la) {
     // =================================================== pair threads: one live 6x6 block in registers
     if (Cfg::kRealloc) reg_alloc<Cfg::kPairRegs>();
-    const unsigned short pm = pair_map[pt];
+    const unsigned short pm = pair_map[tid];
     const bool is_pair = pm != 0xffff;
     const int a = pm & 0xff, b = (pm >> 8) & 0xff;             // a >= b
     double G[36];                                              // rows <-> slot a, columns <-> slot b
@@ -119,8 +175,8 @@ env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_ma
       for (int q = 0; q < 18; ++q) d2[q] = make_double2(G[2 * q], G[2 * q + 1]);
     };
     if (is_pair) {
-      if (a < n && b >= sFirst[a]) {
-        const double2* src = reinterpret_cast<const double2*>(L + (sRS[a] + (b - sFirst[a])) * 36);
+      if (a < n && b >= sLabF[a]) {
+        const double2* src = reinterpret_cast<const double2*>(L + (sLabRS[a] + (b - sLabF[a])) * 36);
 #pragma unroll
         for (int q = 0; q < 18; ++q) { const double2 v = src[q]; G[2 * q] = v.x; G[2 * q + 1] = v.y; }
       } else {
@@ -133,20 +189,21 @@ env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_ma
       if (a == 1 % P && b == 1 % P) publish_N(sDg);                      // block (1,1) -> sDg[0]
     }
     __syncthreads();     // (A) columns 0, 1 published
-    __syncthreads();     // (B) look-ahead group: F_0, L_{.,0}, entering row P
-    int c = 0;
+    __syncthreads();     // (B) look-ahead group: K_0, L_{.,0}, entering row P
+    // per-thread constants of the loop: operand addresses (parity 0) and the distances of the two slots from the pivot
+    const double2* lp0 = reinterpret_cast<const double2*>(sL + a * S);
+    const double2* tp0 = reinterpret_cast<const double2*>(sT + b * S);
+    int da = a, db = b;                                        // (slot - c) mod P ; c = k mod P
+    const int prole = (tid < 32) ? 0 : (tid >= Cfg::kPairThreads - 32) ? 1 : -1;
     for (int k = 0; k < n_stop; ++k) {
       const int cur = k & 1;
-      const int prole = (pt < 32) ? 0 : (pt >= Cfg::kPairThreads - 32) ? 1 : -1;
-      if (prole >= 0) LVBA_STAMP(prole, 0);
+      if (kTiming && prole >= 0) LVBA_STAMP(prole, 0);
       if (is_pair) {
-        int da = a - c; if (da < 0) da += P;
-        int db = b - c; if (db < 0) db += P;
         const int lo = da < db ? da : db, hi = da < db ? db : da;
         if (lo == 0) {
           // the column-k block is dead: take the entering block (k+P, k+hi) (hi == 0: the diagonal (k+P,k+P))
-          const int col_slot = (da == 0) ? b : a;
-          const double2* src = reinterpret_cast<const double2*>(sEnter + (cur * P + col_slot) * 36);
+          const int eidx = (hi == 0) ? P - 1 : hi - 1;
+          const double2* src = reinterpret_cast<const double2*>(sEnter + (cur * P + eidx) * 36);
           if (da == 0) {                          // slot a is the entering row: G = E
 #pragma unroll
             for (int q = 0; q < 18; ++q) { const double2 v = src[q]; G[2 * q] = v.x; G[2 * q + 1] = v.y; }
@@ -161,8 +218,8 @@ env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_ma
                    && lab_mode != 1
 #endif
         ) {
-          const double2* lp = reinterpret_cast<const double2*>(sL + (cur * P + a) * S);
-          const double2* tp = reinterpret_cast<const double2*>(sT + (cur * P + b) * S);
+          const double2* lp = lp0 + cur * (PS / 2);
+          const double2* tp = tp0 + cur * (PS / 2);
 #pragma unroll
           for (int q = 0; q < 6; ++q) {
             const double2 t0 = tp[3 * q], t1 = tp[3 * q + 1], t2 = tp[3 * q + 2];
@@ -176,24 +233,23 @@ env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_ma
             }
           }
         }
-        if (prole >= 0) LVBA_STAMP(prole, 1);
+        if (kTiming && prole >= 0) LVBA_STAMP(prole, 1);
         // hand column k+2 (the look-ahead group's column of the NEXT step) over: blocks (k+hi, k+2)
-        if (lo != 1 && P > 2) {
-          double* nA = sA + ((cur ^ 1) * P) * S;
+        if (lo != 1 && P > 2 && (da == 2 || db == 2)) {
+          double* nA = sA + (cur ^ 1) * PS;
           if (da == 2 && db == 2) publish_N(sDg + (cur ^ 1) * 36);
           else if (db == 2) publish_T(nA + a * S);           // slot a is the row
-          else if (da == 2) publish_N(nA + b * S);           // slot b is the row: G = A^T
+          else publish_N(nA + b * S);                        // slot b is the row: G = A^T
         }
       }
-      if (prole >= 0) LVBA_STAMP(prole, 2);
+      if (kTiming && prole >= 0) LVBA_STAMP(prole, 2);
       __syncthreads();
-      if (prole >= 0) LVBA_STAMP(prole, 3);
-      if (++c == P) c = 0;
+      if (kTiming && prole >= 0) LVBA_STAMP(prole, 3);
+      da = (da == 0) ? P - 1 : da - 1;
+      db = (db == 0) ? P - 1 : db - 1;
     }
     // partial factorisation: hand the Schur-updated trailing window (rows/cols n_stop..n-1) to the separator solve
     if (n_stop < n && J.wdump && is_pair) {
-      int da = a - c; if (da < 0) da += P;
-      int db = b - c; if (db < 0) db += P;
       const int lo = da < db ? da : db, hi = da < db ? db : da;
       const int bs = n - n_stop;
       if (hi < bs) {
@@ -204,7 +260,7 @@ env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_ma
         } else if (lo == 0) {
           // column n_stop was the look-ahead group's: T_{i,n_stop} sits in sT[fin][slot of the hi row], [q*6+x] = T[x][q]
           const int row_slot = (da == 0) ? b : a;
-          const double* t = sT + (fin * P + row_slot) * S;
+          const double* t = sT + fin * PS + row_slot * S;
           for (int q = 0; q < 36; ++q) { const int x = q / 6, y = q % 6; dst[q] = t[y * 6 + x]; }
         } else if (da >= db) {
 #pragma unroll
@@ -220,69 +276,75 @@ env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_ma
   } else {
     // =================================================== look-ahead warpgroup (4 warps, one per SMSP)
     if (Cfg::kRealloc) reg_dealloc<Cfg::kLaRegs>();
-    const int lt = kLaFirst ? tid : tid - Cfg::kPairThreads;    // 0..127
-    const int aw = lt >> 5;                                     // 0: pivot chain + forward substitution + labels; 1..3: column items + row prefetch
+    const int lt = tid - Cfg::kPairThreads;                     // 0..127
+    const int aw = lt >> 5;                                     // 0: pivot chain + forward substitution + labels; 1..3: column items + row stream
     const int it = lt - 32;                                     // item thread id (0..95), negative on warp 0
     int bad = 0;
-    double zin = 0.0;
-    int pf_first = 0x7fffffff; long long pf_rs = 0;             // label of the row this thread streams THIS step (fetched a step earlier)
+    // row labels and entering rhs entries reach shared memory by cp.async (rings above): no global-load result is
+    // ever held in a look-ahead register (a spilled in-flight load would stall the chain for a full memory latency)
+    auto lab_first = [&](int r) -> int { return r < n ? sLabF[r & 63] : 0x7fffffff; };
+    auto lab_rs = [&](int r) -> long long { return sLabRS[r & 63]; };
 
-    // row kc+P -> sEnter[kc & 1], by column slot (cp.async, zero-filled outside the envelope / past the last row)
-    auto stream_row = [&](int kc, int rf, long long rrs) {
-      const int r = kc + P, ck = kc % P;
+    // row kc+P -> sEnter[kc & 1] in natural order: 16-byte chunk o of the row's envelope part lands at chunk
+    // o_lo + o, o_lo = 18 (first - kc - 1); everything else is zero-filled (cp.async src-size 0)
+    auto stream_row = [&](int kc) {
       double* dstb = sEnter + ((kc & 1) * P) * 36;
+      const int o_lo = (kc + P < n) ? (lab_first(kc + P) - kc - 1) * 18 : 0x40000000;
+      const double* rowp = L + lab_rs(kc + P) * 36;
+#pragma unroll 2
       for (int o = it; o < P * 18; o += Cfg::kItemThreads) {
-        const int cs = o / 18, w = o - cs * 18;
-        int dcol = cs - ck; if (dcol <= 0) dcol += P;            // col = kc + dcol ; dcol == P <=> col == r
-        const int col = kc + dcol;
-        const bool valid = r < n && col >= rf;
-        const double* src = valid ? L + (rrs + (col - rf)) * 36 + 2 * w : L;
-        cp_async16_zfill(dstb + 2 * o, src, valid);
+        const bool valid = o >= o_lo;
+        cp_async16_zfill(dstb + 2 * o, valid ? rowp + 2 * (o - o_lo) : L, valid);
       }
     };
-    // warp 0: packed factors of the pivot block.  src: 36 row-major, lower triangle read.
-    auto factor_pivot = [&](const double* src, double* dst, int kc) {
-      double x[21];
+    // warp 0: K = D^-1.  src: 36 row-major, lower triangle read.  dst: 36 row-major, full symmetric.
+    auto invert_pivot = [&](const double* src, double* dst, int kc) {
+      double x[21], K[21];
 #pragma unroll
       for (int i = 0; i < 6; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j) x[LVBA_T(i, j)] = src[i * 6 + j];
-      __syncwarp();
-      sym6_ldlt(x);
-      double chk = 0.0;
-#pragma unroll
-      for (int q = 0; q < 21; ++q) chk += x[q];
-      if (!isfinite(chk)) bad = 1;
+      sym6_block_inverse(x, K);
+      // every entry of K carries one of the two reciprocals: four entries are enough to catch a singular pivot
+      if (!isfinite((K[LVBA_T(0, 0)] + K[LVBA_T(5, 5)]) + (K[LVBA_T(3, 0)] + K[LVBA_T(2, 1)]))) bad = 1;
       if (lane == 0) {
 #pragma unroll
-        for (int q = 0; q < 21; ++q) dst[q] = x[q];
+        for (int i = 0; i < 6; ++i) {
+          double2* d2 = reinterpret_cast<double2*>(dst + i * 6);
+          auto kk = [&](int r, int c) -> double { return r >= c ? K[LVBA_T(r, c)] : K[LVBA_T(c, r)]; };
+          d2[0] = make_double2(kk(i, 0), kk(i, 1)); d2[1] = make_double2(kk(i, 2), kk(i, 3)); d2[2] = make_double2(kk(i, 4), kk(i, 5));
+        }
       }
       __syncwarp();
-      if (lane < 21 && kc < n_stop) dinv[(long long)kc * 36 + lane] = dst[lane];
+      if (lane < 18 && kc < n_stop) reinterpret_cast<double2*>(dinv + (long long)kc * 36)[lane] = reinterpret_cast<const double2*>(dst)[lane];
     };
-    // column item: row slot `slot`, block row x.  t = T_{i,col}[x][.] (already updated); writes L_{i,col}[x][.] = t D^-1
-    auto scale_item = [&](const double* F, double (&t)[6], int slot, int x, int col, int par) {
-      ldlt_solve6(F, t);
-      double* lt_ = sL + (par * P + slot) * S;
+    // column item: row slot `slot`, block row x.  t = T_{i,col}[x][.] (already updated); writes L_{i,col}[x][.] = t K
+    auto scale_item = [&](const double* Kp, const double (&t)[6], int slot, int x, int row, int col, int par) {
+      const double2* k2 = reinterpret_cast<const double2*>(Kp);
+      double v0[6], v1[6];
 #pragma unroll
-      for (int q = 0; q < 6; ++q) lt_[q * 6 + x] = t[q];
-      const int rf = sFirst[slot];
+      for (int c = 0; c < 6; ++c) { v0[c] = 0.0; v1[c] = 0.0; }
+#pragma unroll
+      for (int q = 0; q < 6; q += 2) {
+        const double2 a0 = k2[3 * q], a1 = k2[3 * q + 1], a2 = k2[3 * q + 2];
+        const double2 b0 = k2[3 * q + 3], b1 = k2[3 * q + 4], b2 = k2[3 * q + 5];
+        v0[0] += t[q] * a0.x; v0[1] += t[q] * a0.y; v0[2] += t[q] * a1.x; v0[3] += t[q] * a1.y; v0[4] += t[q] * a2.x; v0[5] += t[q] * a2.y;
+        v1[0] += t[q + 1] * b0.x; v1[1] += t[q + 1] * b0.y; v1[2] += t[q + 1] * b1.x; v1[3] += t[q + 1] * b1.y; v1[4] += t[q + 1] * b2.x; v1[5] += t[q + 1] * b2.y;
+      }
+      double* lt_ = sL + par * PS + slot * S;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { v0[c] += v1[c]; lt_[c * 6 + x] = v0[c]; }
+      const int rf = lab_first(row);
       if (col >= rf && col < n_stop) {      // a partial factorisation leaves column n_stop (the separator's first) untouched in memory
-        double2* g = reinterpret_cast<double2*>(L + (sRS[slot] + (col - rf)) * 36 + x * 6);
-        g[0] = make_double2(t[0], t[1]); g[1] = make_double2(t[2], t[3]); g[2] = make_double2(t[4], t[5]);
+        double2* g = reinterpret_cast<double2*>(L + (lab_rs(row) + (col - rf)) * 36 + x * 6);
+        g[0] = make_double2(v0[0], v0[1]); g[1] = make_double2(v0[2], v0[3]); g[2] = make_double2(v0[4], v0[5]);
       }
     };
 
     __syncthreads();     // (A)
-    // ---- column 0: F_0, L_{.,0}; entering row P; labels
-    if (aw == 0) {
-      factor_pivot(sDg + 36, sF, 0);
-      if (lane < 6) zin = (P < n) ? z[6 * (long long)P + lane] : 0.0;
-    } else {
-      stream_row(0, (P < n) ? e.first[P] : 0x7fffffff, (P < n) ? e.row_start[P] : 0);
-      pf_first = (P + 1 < n) ? e.first[P + 1] : 0x7fffffff;
-      pf_rs = (P + 1 < n) ? e.row_start[P + 1] : 0;
-    }
+    // ---- column 0: K_0, L_{.,0}; entering row P; labels
+    if (aw == 0) invert_pivot(sDg + 36, sK, 0);
+    else stream_row(0);
     named_bar_sync(1, Cfg::kLaThreads);
     if (aw != 0) {
       for (int o = it; o < Cfg::kItems; o += Cfg::kItemThreads) {
@@ -290,33 +352,35 @@ env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_ma
         double t[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) t[q] = sT[h * S + q * 6 + x];
-        scale_item(sF, t, h, x, 0, 0);
+        scale_item(sK, t, h, x, h, 0, 0);
       }
       cp_async_wait_all();
     }
-    named_bar_sync(1, Cfg::kLaThreads);
-    if (aw == 0 && lane == 0) {                                    // slot 0 now describes row P
-      sFirst[0] = (P < n) ? e.first[P] : 0x7fffffff;
-      sRS[0] = (P < n) ? e.row_start[P] : 0;
-    }
     __syncthreads();     // (B)
 
+    // per-thread item constants: item o -> row k+h (h = 2..P), block row x ; slot = (c + h) mod P advances with c
+    int slot_[Cfg::kRounds], x_[Cfg::kRounds], h_[Cfg::kRounds];
+    bool act_[Cfg::kRounds], ent_[Cfg::kRounds];
+#pragma unroll
+    for (int rd = 0; rd < Cfg::kRounds; ++rd) {
+      const int o = it + rd * Cfg::kItemThreads;
+      const int oo = (o >= 0 && o < Cfg::kItems) ? o : 0;
+      const int h = 2 + oo / 6;
+      x_[rd] = oo - (h - 2) * 6;
+      h_[rd] = h;
+      slot_[rd] = h % P;                                            // c = 0
+      act_[rd] = o >= 0 && o < Cfg::kItems;
+      ent_[rd] = h == P;                                            // the entering row k+P
+    }
     int c = 0;
     for (int k = 0; k < n_stop; ++k) {
       const int cur = k & 1, nxt = cur ^ 1;
       int s1 = c + 1; if (s1 >= P) s1 -= P;
-      const double* Lc = sL + cur * P * S;
-      const double* Tc = sT + cur * P * S;
-      const double* T1 = Tc + s1 * S;                               // T_{k+1,k}: [r*6+q] = T[q][r]
+      const double* Lc = sL + cur * PS;
+      const double* T1 = sT + cur * PS + s1 * S;                    // T_{k+1,k}: [r*6+q] = T[q][r]
       LVBA_STAMP(4 + aw, 0);
       if (aw == 0) {
-        // ---- pivot chain: D_{k+1} = A_{k+1,k+1} - L_{k+1,k} T_{k+1,k}^T (lane <-> lower-triangle element), LDL^T
-        int m_first = 0x7fffffff; long long m_rs = 0;
-        if (lane == 0) {                                            // label of row k+1+P (consumed at the end of the step)
-          const int r1 = k + 1 + P;
-          m_first = (r1 < n) ? e.first[r1] : 0x7fffffff;
-          m_rs = (r1 < n) ? e.row_start[r1] : 0;
-        }
+        // ---- pivot chain: D_{k+1} = A_{k+1,k+1} - L_{k+1,k} T_{k+1,k}^T (lane <-> lower-triangle element), inverse
         if (k + 1 < n
 #ifdef LVBA_LAB
             && lab_mode != 2
@@ -328,15 +392,16 @@ env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_ma
           const int i = (l21 >= 15) ? 5 : (l21 >= 10) ? 4 : (l21 >= 6) ? 3 : (l21 >= 3) ? 2 : (l21 >= 1) ? 1 : 0;
           const int j = l21 - i * (i + 1) / 2;
           double v = dg[i * 6 + j];
+          double w = 0.0;
 #pragma unroll
-          for (int q = 0; q < 6; ++q) v -= l1[q * 6 + i] * T1[q * 6 + j];
-          __syncwarp();
+          for (int q = 0; q < 6; q += 2) { v -= l1[q * 6 + i] * T1[q * 6 + j]; w += l1[(q + 1) * 6 + i] * T1[(q + 1) * 6 + j]; }
+          v -= w;
           if (lane < 21) sDu[i * 6 + j] = v;
           __syncwarp();
-          factor_pivot(sDu, sF + nxt * 24, k + 1);
+          invert_pivot(sDu, sK + nxt * 36, k + 1);
         }
         LVBA_STAMP(4, 1);
-        named_bar_sync(1, Cfg::kLaThreads);                         // F_{k+1} visible to the item warps
+        named_bar_sync(1, Cfg::kLaThreads);                         // K_{k+1} visible to the item warps
         LVBA_STAMP(4, 2);
         // ---- forward substitution with the final z_k : lane <-> row k+1+lane
         double zk[6];
@@ -344,59 +409,53 @@ env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_ma
         for (int q = 0; q < 6; ++q) zk[q] = sZ[c * 6 + q];
         if (lane < 6) z[6 * (long long)k + lane] = sZ[c * 6 + lane];
         __syncwarp();
-        for (int h = 1 + lane; h < P; h += 32) {
-          int slot = c + h; if (slot >= P) slot -= P;
+        if (lane + 1 < P) {
+          int slot = c + 1 + lane; if (slot >= P) slot -= P;
           const double2* lt2 = reinterpret_cast<const double2*>(Lc + slot * S);
           double acc[6];
 #pragma unroll
-          for (int x = 0; x < 6; ++x) acc[x] = 0.0;
+          for (int x = 0; x < 6; ++x) acc[x] = sZ[slot * 6 + x];
 #pragma unroll
           for (int q = 0; q < 6; ++q) {
             const double2 l0 = lt2[3 * q], l1 = lt2[3 * q + 1], l2 = lt2[3 * q + 2];
-            acc[0] += l0.x * zk[q]; acc[1] += l0.y * zk[q]; acc[2] += l1.x * zk[q]; acc[3] += l1.y * zk[q]; acc[4] += l2.x * zk[q]; acc[5] += l2.y * zk[q];
+            acc[0] -= l0.x * zk[q]; acc[1] -= l0.y * zk[q]; acc[2] -= l1.x * zk[q]; acc[3] -= l1.y * zk[q]; acc[4] -= l2.x * zk[q]; acc[5] -= l2.y * zk[q];
           }
 #pragma unroll
-          for (int x = 0; x < 6; ++x) sZ[slot * 6 + x] -= acc[x];
+          for (int x = 0; x < 6; ++x) sZ[slot * 6 + x] = acc[x];
         }
         __syncwarp();
-        if (lane < 6) {
-          sZ[c * 6 + lane] = zin;                                   // row k+P takes slot c
-          zin = (k + 1 + P < n) ? z[6 * (long long)(k + 1 + P) + lane] : 0.0;
-        }
-        if (lane == 0) { sFirst[s1] = m_first; sRS[s1] = m_rs; }   // slot of row k+1 now describes row k+1+P
+        if (lane < 6) sZ[c * 6 + lane] = (k + P < n) ? sZin[((k + P) & 7) * 6 + lane] : 0.0;   // row k+P takes slot c
         LVBA_STAMP(4, 3);
       } else {
         // ---- column items: T_{i,k+1} = A_{i,k+1} - L_{i,k} T_{k+1,k}^T for rows i = k+2 .. k+P, then L = T D_{k+1}^-1
-        stream_row(k + 1, pf_first, pf_rs);                         // row k+1+P -> sEnter[nxt]
-        {
-          const int r2 = k + 2 + P;
-          pf_first = (r2 < n) ? e.first[r2] : 0x7fffffff;
-          pf_rs = (r2 < n) ? e.row_start[r2] : 0;
+        stream_row(k + 1);                                          // row k+1+P -> sEnter[nxt]
+        if (it < 5) {                                               // ring refills: labels of row k+40, rhs of row k+P+4
+          const int rl = k + 40, rz = k + P + 4;
+          if (it == 0 && rl < n) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(sLabF + (rl & 63))), "l"(e.first + rl));
+          } else if (it == 1 && rl < n) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sLabRS + (rl & 63))), "l"(e.row_start + rl));
+          } else if (it >= 2 && rz < n) {
+            cp_async16_zfill(sZin + (rz & 7) * 6 + 2 * (it - 2), z + 6 * (long long)rz + 2 * (it - 2), true);
+          }
         }
         double t[Cfg::kRounds][6];
-        int slot_[Cfg::kRounds], x_[Cfg::kRounds];
-#ifdef LVBA_LAB
-        if (lab_mode == 2) {
-#pragma unroll
-          for (int rd = 0; rd < Cfg::kRounds; ++rd) { slot_[rd] = 0; x_[rd] = 0;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) t[rd][q] = 0.0; }
-        } else
-#endif
 #pragma unroll
         for (int rd = 0; rd < Cfg::kRounds; ++rd) {
-          const int o = it + rd * Cfg::kItemThreads;
-          const int oo = o < Cfg::kItems ? o : 0;
-          const int h = 2 + oo / 6;                                 // row k+h, h = 2..P
-          const int x = oo - (h - 2) * 6;
-          int slot = c + h; if (slot >= P) slot -= P;               // h == P -> slot c (the entering row k+P)
-          slot_[rd] = slot; x_[rd] = x;
-          if (h == P) {
-            const double* en = sEnter + (cur * P + s1) * 36 + x * 6;   // block (k+P, k+1), row-major
+          const int slot = slot_[rd], x = x_[rd];
+#ifdef LVBA_LAB
+          if (lab_mode == 2) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) t[rd][q] = 0.0;
+            continue;
+          }
+#endif
+          if (ent_[rd]) {
+            const double* en = sEnter + (cur * P) * 36 + x * 6;     // block (k+P, k+1): index 0, row-major
 #pragma unroll
             for (int q = 0; q < 6; ++q) t[rd][q] = en[q];
           } else {
-            const double* as = sA + (cur * P + slot) * S;
+            const double* as = sA + cur * PS + slot * S;
 #pragma unroll
             for (int q = 0; q < 6; ++q) t[rd][q] = as[q * 6 + x];
             const double* lr = Lc + slot * S;
@@ -409,24 +468,24 @@ env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_ma
               t[rd][0] -= lv * u0.x; t[rd][1] -= lv * u0.y; t[rd][2] -= lv * u1.x; t[rd][3] -= lv * u1.y; t[rd][4] -= lv * u2.x; t[rd][5] -= lv * u2.y;
             }
           }
-          if (o < Cfg::kItems) {
-            double* tn = sT + (nxt * P + slot) * S;
+          if (act_[rd]) {
+            double* tn = sT + nxt * PS + slot * S;
 #pragma unroll
             for (int q = 0; q < 6; ++q) tn[q * 6 + x] = t[rd][q];
           }
         }
         LVBA_STAMP(4 + aw, 1);
-        named_bar_sync(1, Cfg::kLaThreads);                         // F_{k+1} ready
+        named_bar_sync(1, Cfg::kLaThreads);                         // K_{k+1} ready
         LVBA_STAMP(4 + aw, 2);
-        const double* F = sF + nxt * 24;
+        const double* Kp = sK + nxt * 36;
 #pragma unroll
         for (int rd = 0; rd < Cfg::kRounds; ++rd) {
-          const int o = it + rd * Cfg::kItemThreads;
-          if (o < Cfg::kItems
+          if (act_[rd]
 #ifdef LVBA_LAB
               && lab_mode != 2
 #endif
-          ) scale_item(F, t[rd], slot_[rd], x_[rd], k + 1, nxt);
+          ) scale_item(Kp, t[rd], slot_[rd], x_[rd], k + h_[rd], k + 1, nxt);
+          if (++slot_[rd] == P) slot_[rd] = 0;
         }
         cp_async_wait_all();
         LVBA_STAMP(4 + aw, 3);
@@ -451,18 +510,17 @@ env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_ma
 // Row-oriented: when x_i is final, every block L_ij of row i (columns first[i]..i-1, contiguous in memory) sends
 // x_j -= L_ij^T x_i.  Lane s of the consumer warp OWNS x_j for the row j == s (mod 32) of the live 32-row window and
 // keeps it in registers; x_i reaches the other lanes by shuffles, so the dependent chain per row is one shuffle +
-// a short FMA tree (~100 cycles) instead of two block barriers.  A producer warp streams L through a ring of
-// shared-memory stages guarded by full/empty mbarriers: rows are contiguous in memory, so ONE cp.async.bulk brings a
-// group of kBsGroup consecutive rows.  Row labels travel in registers (32 rows per coalesced load, one chunk ahead),
-// the x entries that enter the window are fetched kBsXDist rows ahead, the next row's block is loaded from shared
-// memory while the current row is applied (software pipeline), and the two quarter-warp halves read their blocks in
-// an XOR-swizzled 16-byte order so that the 288-byte block stride does not collide on the banks.
+// a short FMA tree instead of two block barriers.  A producer warp streams L through a ring of shared-memory stages
+// guarded by full/empty mbarriers: rows are contiguous in memory, so ONE cp.async.bulk brings a group of kBsGroup
+// consecutive rows; it also leaves each row's first column and offset in the stage header.  The x entries that
+// enter the window are fetched kBsXDist rows ahead, and the next row's block is loaded from shared memory while the
+// current row is applied (software pipeline).
 constexpr int kBsStages = 4;
 constexpr int kBsGroup = 4;                                  // rows per stage (divides 32)
-constexpr int kBsStageDoubles = kBsGroup * 31 * 36;
-constexpr int kBsXDist = 8;                                  // prefetch distance (rows) of the entering x entries
+constexpr int kBsRowsDoubles = kBsGroup * 31 * 36;           // L blocks of the staged rows
+constexpr int kBsStageDoubles = kBsRowsDoubles + kBsGroup * 6;   // + the x entries that enter the window with these rows
 constexpr size_t kBsSmem = sizeof(double) * (size_t)kBsStages * kBsStageDoubles + 2 * kBsStages * sizeof(unsigned long long) +
-                           kBsStages * sizeof(long long) + 64;
+                           kBsStages * kBsGroup * 3 * sizeof(int) + 64;
 
 LVBA_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 LVBA_DEV void mbar_init(unsigned long long* bar, int count) {
@@ -493,7 +551,9 @@ env_backsolve_warp_kernel(BacksolveJobs jobs) {
   double* ring = smem_bs;                                                       // [NS][kBsStageDoubles]
   unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + NS * kBsStageDoubles);   // [NS]
   unsigned long long* empty = full + NS;                                        // [NS]
-  long long* sBase = reinterpret_cast<long long*>(empty + NS);                  // [NS] row_start of the lowest staged row
+  int* sRowF = reinterpret_cast<int*>(empty + NS);                              // [NS][R] first column of each staged row
+  int* sRowOff = sRowF + NS * R;                                                // [NS][R] offset (doubles) of each staged row inside the stage
+  int* sRowX = sRowOff + NS * R;                                                // [NS][R] offset (doubles) of the x entry that replaces the row, or -1
   const BacksolveJob& J = jobs.j[blockIdx.x];
   const EnvView e = J.e;
   const double* __restrict__ L = J.L;
@@ -505,9 +565,10 @@ env_backsolve_warp_kernel(BacksolveJobs jobs) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (n <= 0) return;
   const int n_groups = (n + R - 1) / R;
   if (tid >= 32) {
-    // ------------------------------------------------ producer warp: one bulk copy per group of R rows
+    // ------------------------------------------------ producer warp: two bulk copies per group of R rows (L rows, x entries)
     int lab_f = 0; long long lab_rs = 0;
     for (int g = 0; g < n_groups; ++g) {
       const int itn = g * R;                         // rows i_hi = n-1-itn down to i_lo
@@ -518,112 +579,106 @@ env_backsolve_warp_kernel(BacksolveJobs jobs) {
         lab_f = (r >= 0) ? e.first[r] : 0;
         lab_rs = (r >= 0) ? e.row_start[r] : 0;
       }
-      const int f_hi = __shfl_sync(0xffffffffu, lab_f, itn & 31);
-      const long long rs_hi = __shfl_sync(0xffffffffu, lab_rs, itn & 31);
-      const long long rs_lo = __shfl_sync(0xffffffffu, lab_rs, (itn & 31) + (i_hi - i_lo));
+      const int base_l = itn & 31;
+      const int f_hi = __shfl_sync(0xffffffffu, lab_f, base_l);
+      const long long rs_hi = __shfl_sync(0xffffffffu, lab_rs, base_l);
+      const long long rs_lo = __shfl_sync(0xffffffffu, lab_rs, base_l + (i_hi - i_lo));
+      // this lane's row of the group (lanes 0..R-1): first column and offset from the group's base
+      const int my_f = __shfl_sync(0xffffffffu, lab_f, base_l + (lane < R ? lane : 0));
+      const long long my_rs = __shfl_sync(0xffffffffu, lab_rs, base_l + (lane < R ? lane : 0));
+      const int st = g % NS;
+      const unsigned ph = (unsigned)((g / NS) & 1);
+      if (lane == 0) mbar_wait(empty + st, ph ^ 1u);
+      __syncwarp();
+      const int xr_hi = i_hi - 32;                   // x entries of rows i_lo-32 .. i_hi-32 (those >= 0), ascending in memory
+      const int xr_lo = (i_lo - 32 > 0) ? i_lo - 32 : 0;
+      if (lane < R && i_hi - lane >= 0) {
+        const int i = i_hi - lane;
+        sRowF[st * R + lane] = my_f;
+        sRowOff[st * R + lane] = (int)((my_rs - rs_lo) * 36);
+        sRowX[st * R + lane] = (i - 32 >= 0) ? kBsRowsDoubles + (i - 32 - xr_lo) * 6 : -1;
+      }
+      __syncwarp();
       if (lane == 0) {
-        const int st = g % NS;
-        const unsigned ph = (unsigned)((g / NS) & 1);
-        mbar_wait(empty + st, ph ^ 1u);
         const long long nblk = rs_hi + (i_hi - f_hi + 1) - rs_lo;      // blocks of rows i_lo..i_hi, diagonal blocks included
-        sBase[st] = rs_lo;
-        mbar_arrive_expect_tx(full + st, (unsigned)(nblk * 288));
-        bulk_g2s(ring + st * kBsStageDoubles, L + rs_lo * 36, (unsigned)(nblk * 288), full + st);
+        const unsigned xbytes = (xr_hi >= xr_lo) ? (unsigned)((xr_hi - xr_lo + 1) * 48) : 0u;
+        double* dst = ring + st * kBsStageDoubles;
+        mbar_arrive_expect_tx(full + st, (unsigned)(nblk * 288) + xbytes);
+        bulk_g2s(dst, L + rs_lo * 36, (unsigned)(nblk * 288), full + st);
+        if (xbytes) bulk_g2s(dst + kBsRowsDoubles, x + 6 * (long long)xr_lo, xbytes, full + st);
       }
     }
   } else {
-    // ------------------------------------------------ consumer warp
-    double xs[6], xn[6];
+    // ------------------------------------------------ consumer warp: three-stage software pipeline over the rows
+    //   M: row metadata (first column, offsets) two rows ahead ; B: block + x entry one row ahead ; C: apply
+    double xs[6];
     {
       const int r = (n - 1) - (((n - 1) - lane) % 32 + 32) % 32;   // the row == lane (mod 32) inside [n-32, n-1]
 #pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        xs[q] = (r >= 0) ? x[6 * (long long)r + q] : 0.0;
-        xn[q] = (r - 32 >= 0) ? x[6 * (long long)(r - 32) + q] : 0.0;
-      }
+      for (int q = 0; q < 6; ++q) xs[q] = (r >= 0) ? x[6 * (long long)r + q] : 0.0;
     }
-    // row labels: lane l holds row (chunk top - l); the next chunk is fetched one chunk ahead
-    int lab_f, lab_f2 = 0; long long lab_rs, lab_rs2 = 0;
-    {
-      const int r = n - 1 - lane;
-      lab_f = (r >= 0) ? e.first[r] : 0;
-      lab_rs = (r >= 0) ? e.row_start[r] : 0;
-    }
-    double2 blk[18];                                   // block of the row being applied (this lane's column)
-    bool blk_on = false;
-    auto load_block = [&](int i, int itn) {            // stage the block of row i for this lane into blk
-      const int f = __shfl_sync(0xffffffffu, lab_f, itn & 31);
-      const long long rs = __shfl_sync(0xffffffffu, lab_rs, itn & 31);
-      const int g = itn / R, st = g % NS;
-      if (itn % R == 0) mbar_wait(full + st, (unsigned)((g / NS) & 1));
-      const int upto = i < n_given ? i : n_given;      // given rows only act on the pivots' columns
-      const int cnt = upto > f ? upto - f : 0;
-      const int jo = (lane - f) & 31;                  // column f + jo is the one congruent to this lane
-      blk_on = jo < cnt;
-      if (blk_on) {
-        const double2* b2 = reinterpret_cast<const double2*>(ring + st * kBsStageDoubles + (rs - sBase[st]) * 36 + jo * 36);
-        const int sw = (jo >> 2) & 1;
-#pragma unroll
-        for (int t = 0; t < 18; ++t) blk[t] = b2[t ^ sw];
-        if (sw) {
-#pragma unroll
-          for (int t = 0; t < 18; t += 2) { const double2 tmp = blk[t]; blk[t] = blk[t + 1]; blk[t + 1] = tmp; }
-        }
-      }
+    double2 blk0[18], blk1[18];
+    double xe0[6], xe1[6];
+    int mF = 0, mOff = 0, mX = -1;                     // metadata of the row whose block is loaded next
+    auto meta = [&](int itn) {                         // stage M for the row of iteration itn
+      const int g = itn / R, st = g % NS, rr = itn % R;
+      if (rr == 0) { mbar_wait(full + st, (unsigned)((g / NS) & 1)); __syncwarp(); }
+      mF = sRowF[st * R + rr]; mOff = sRowOff[st * R + rr]; mX = sRowX[st * R + rr];
     };
-    if (n > 0) load_block(n - 1, 0);
-    for (int i = n - 1; i >= 0; --i) {
-      const int itn = n - 1 - i;
+    auto fetch = [&](int i, int itn, double2 (&blk)[18], double (&xe)[6]) {   // stage B for row i, using the metadata in mF/mOff/mX
+      const double* stg = ring + ((itn / R) % NS) * kBsStageDoubles;
+      const int upto = i < n_given ? i : n_given;      // given rows only act on the pivots' columns
+      const int cnt = upto > mF ? upto - mF : 0;
+      const int jo = (lane - mF) & 31;                 // column mF + jo is the one congruent to this lane
+      const bool on = jo < cnt;
+      const double2* b2 = reinterpret_cast<const double2*>(stg + mOff + (on ? jo : 0) * 36);
+#pragma unroll
+      for (int t = 0; t < 18; ++t) { const double2 v = b2[t]; blk[t] = on ? v : make_double2(0.0, 0.0); }
+      const double2* x2 = reinterpret_cast<const double2*>(stg + (mX >= 0 ? mX : 0));
+      const bool xon = mX >= 0;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) { const double2 v = x2[t]; xe[2 * t] = xon ? v.x : 0.0; xe[2 * t + 1] = xon ? v.y : 0.0; }
+    };
+    auto apply = [&](int i, int itn, const double2 (&blk)[18], const double (&xe)[6]) {   // stage C for row i
       const int owner = i & 31;
+      const bool mine = lane == owner;
       double xi[6];
 #pragma unroll
       for (int q = 0; q < 6; ++q) xi[q] = __shfl_sync(0xffffffffu, xs[q], owner);
-      if (lane == owner) {
+      if (mine) {
         double2* xo = reinterpret_cast<double2*>(x + 6 * (long long)i);
         xo[0] = make_double2(xs[0], xs[1]); xo[1] = make_double2(xs[2], xs[3]); xo[2] = make_double2(xs[4], xs[5]);
       }
-      // apply row i with the block loaded one iteration earlier
       double v0[6], v1[6];
-      const bool on = blk_on;
 #pragma unroll
       for (int cc = 0; cc < 6; ++cc) { v0[cc] = 0.0; v1[cc] = 0.0; }
-      if (on) {
 #pragma unroll
-        for (int q = 0; q < 6; q += 2) {
-          const double2 a0 = blk[3 * q], a1 = blk[3 * q + 1], a2 = blk[3 * q + 2];
-          const double2 c0 = blk[3 * q + 3], c1 = blk[3 * q + 4], c2 = blk[3 * q + 5];
-          v0[0] += a0.x * xi[q]; v0[1] += a0.y * xi[q]; v0[2] += a1.x * xi[q]; v0[3] += a1.y * xi[q]; v0[4] += a2.x * xi[q]; v0[5] += a2.y * xi[q];
-          v1[0] += c0.x * xi[q + 1]; v1[1] += c0.y * xi[q + 1]; v1[2] += c1.x * xi[q + 1]; v1[3] += c1.y * xi[q + 1]; v1[4] += c2.x * xi[q + 1]; v1[5] += c2.y * xi[q + 1];
-        }
-#pragma unroll
-        for (int cc = 0; cc < 6; ++cc) xs[cc] -= (v0[cc] + v1[cc]);
+      for (int q = 0; q < 6; q += 2) {
+        const double2 a0 = blk[3 * q], a1 = blk[3 * q + 1], a2 = blk[3 * q + 2];
+        const double2 c0 = blk[3 * q + 3], c1 = blk[3 * q + 4], c2 = blk[3 * q + 5];
+        v0[0] += a0.x * xi[q]; v0[1] += a0.y * xi[q]; v0[2] += a1.x * xi[q]; v0[3] += a1.y * xi[q]; v0[4] += a2.x * xi[q]; v0[5] += a2.y * xi[q];
+        v1[0] += c0.x * xi[q + 1]; v1[1] += c0.y * xi[q + 1]; v1[2] += c1.x * xi[q + 1]; v1[3] += c1.y * xi[q + 1]; v1[4] += c2.x * xi[q + 1]; v1[5] += c2.y * xi[q + 1];
       }
-      if (lane == owner) {                             // row i leaves the window, row i-32 takes its lane
 #pragma unroll
-        for (int q = 0; q < 6; ++q) xs[q] = xn[q];
-      }
-      // x entry of the lane that becomes owner kBsXDist rows from now
-      {
-        const int it = i - kBsXDist;                   // its turn
-        if (it >= 0 && lane == (it & 31)) {
-          const int r = it - 32;
-#pragma unroll
-          for (int q = 0; q < 6; ++q) xn[q] = (r >= 0) ? x[6 * (long long)r + q] : 0.0;
-        }
-      }
-      // the group of row i is consumed once its last row's block is in registers
-      if ((itn % R) == R - 1 || i == 0) {
+      for (int cc = 0; cc < 6; ++cc) xs[cc] = mine ? xe[cc] : xs[cc] - (v0[cc] + v1[cc]);   // row i leaves, row i-32 takes its lane
+      if ((itn % R) == R - 1 || i == 0) {              // every row of this group has been applied: the stage is free
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + ((itn / R) % NS));
       }
-      // labels: swap in the next chunk, fetch the one after
-      if ((itn & 31) == 31) { lab_f = lab_f2; lab_rs = lab_rs2; }
-      if ((itn & 31) == 0) {
-        const int r = i - 32 - lane;
-        lab_f2 = (r >= 0) ? e.first[r] : 0;
-        lab_rs2 = (r >= 0) ? e.row_start[r] : 0;
+    };
+    meta(0);
+    fetch(n - 1, 0, blk0, xe0);
+    if (n > 1) meta(1);
+    for (int i = n - 1; i >= 0; i -= 2) {
+      const int itn = n - 1 - i;
+      if (i >= 1) fetch(i - 1, itn + 1, blk1, xe1);
+      if (i >= 2) meta(itn + 2);
+      apply(i, itn, blk0, xe0);
+      if (i >= 1) {
+        if (i >= 2) fetch(i - 2, itn + 2, blk0, xe0);
+        if (i >= 3) meta(itn + 3);
+        apply(i - 1, itn + 1, blk1, xe1);
       }
-      if (i > 0) load_block(i - 1, itn + 1);
     }
   }
 }

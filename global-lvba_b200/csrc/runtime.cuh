@@ -258,7 +258,6 @@ struct EnvSolver {
   int dbg_dumped = 0, dbg_max_dumps = 2;
   bool configured = false;
   bool force_generic = false;   // tests: exercise the wide-envelope kernel on narrow problems
-  bool use_la = true, use_warp_bs = true, la_first = true;
   // ---- twisted (two-ended) factorisation: top half in natural order on one SM, bottom half reversed on another,
   //      joined at a separator of `tw_bs` rows (see envelope.cuh, FactorJob)
   bool tw = false;
@@ -273,13 +272,6 @@ struct EnvSolver {
     if (env.max_col > kEnvMaxCol)
       return fail(LVBA_ERR_UNSUPPORTED, "envelope column height %d exceeds the factor kernel limit %d", env.max_col, kEnvMaxCol);
     {
-      const char* sv = getenv("LVBA_SOLVER");                     // development switch: v6 = first register-window kernel
-      use_la = !(sv && sv[0] == 'v' && sv[1] == '6');
-      la_first = !(sv && sv[0] == 'v' && sv[1] == '7' && sv[2] == 'l');   // v7l: look-ahead warpgroup on the last warp ids
-      const char* bv = getenv("LVBA_BACKSOLVE");                  // development switch: ring = block-barrier ring kernel
-      use_warp_bs = !(bv && bv[0] == 'r');
-    }
-    {
       const char* fg = getenv("LVBA_FORCE_GENERIC_SOLVER");      // tests: run the wide-envelope kernel on narrow problems
       force_generic = fg && fg[0] == '1';
     }
@@ -293,10 +285,6 @@ struct EnvSolver {
     }
     if (!configured) {
       LVBA_CUDA(cudaFuncSetAttribute(env_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)factor_smem()));
-      LVBA_CUDA(cudaFuncSetAttribute(env_factor_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RegCfg<8>::kSmem));
-      LVBA_CUDA(cudaFuncSetAttribute(env_factor_reg_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RegCfg<16>::kSmem));
-      LVBA_CUDA(cudaFuncSetAttribute(env_factor_reg_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RegCfg<24>::kSmem));
-      LVBA_CUDA(cudaFuncSetAttribute(env_factor_reg_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RegCfg<31>::kSmem));
       LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<8>::kSmem));
       LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<8>::kSmem));
       LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<16>::kSmem));
@@ -344,7 +332,7 @@ struct EnvSolver {
   int ensure_map(int id, cudaStream_t s) {
     if (have_map[id]) return LVBA_OK;
     const int P = pval(id);
-    const int nthr = id == 0 ? RegCfg<8>::kPairThreads : id == 1 ? RegCfg<16>::kPairThreads : id == 2 ? RegCfg<24>::kPairThreads : RegCfg<31>::kPairThreads;
+    const int nthr = id == 0 ? LaCfg<8>::kPairThreads : id == 1 ? LaCfg<16>::kPairThreads : id == 2 ? LaCfg<24>::kPairThreads : LaCfg<31>::kPairThreads;
     std::vector<unsigned short> m = build_pair_map(P, nthr);
     size_t cnt = 0; for (auto v2 : m) cnt += v2 != 0xffff;
     if ((int)cnt != P * (P + 1) / 2) return fail(LVBA_ERR_UNSUPPORTED, "pair map for P=%d covers %zu of %d pairs", P, cnt, P * (P + 1) / 2);
@@ -356,28 +344,21 @@ struct EnvSolver {
   int launch_factor(int id, int grid, const FactorJobs& jobs, cudaStream_t s, int64_t* launches) {
     LVBA_TRY(ensure_map(id, s));
     const unsigned short* pm = pair_map[id].p;
-    if (use_la) {
-#define LVBA_LAUNCH_LA(PP, FIRST) env_factor_la_kernel<PP, FIRST><<<grid, LaCfg<PP>::kThreads, LaCfg<PP>::kSmem, s>>>(jobs, pm, status.p, dbg.p)
-      if (la_first) {
-        if (id == 0) LVBA_LAUNCH_LA(8, true); else if (id == 1) LVBA_LAUNCH_LA(16, true); else if (id == 2) LVBA_LAUNCH_LA(24, true); else LVBA_LAUNCH_LA(31, true);
-      } else {
-        if (id == 0) LVBA_LAUNCH_LA(8, false); else if (id == 1) LVBA_LAUNCH_LA(16, false); else if (id == 2) LVBA_LAUNCH_LA(24, false); else LVBA_LAUNCH_LA(31, false);
-      }
-#undef LVBA_LAUNCH_LA
-      ++*launches;
-      return LVBA_OK;
+#define LVBA_LAUNCH_LA(PP, TT) env_factor_la_kernel<PP, TT><<<grid, LaCfg<PP>::kThreads, LaCfg<PP>::kSmem, s>>>(jobs, pm, status.p, dbg.p)
+    if (dbg.p) {
+      if (id == 0) LVBA_LAUNCH_LA(8, true); else if (id == 1) LVBA_LAUNCH_LA(16, true); else if (id == 2) LVBA_LAUNCH_LA(24, true); else LVBA_LAUNCH_LA(31, true);
+    } else {
+      if (id == 0) LVBA_LAUNCH_LA(8, false); else if (id == 1) LVBA_LAUNCH_LA(16, false); else if (id == 2) LVBA_LAUNCH_LA(24, false); else LVBA_LAUNCH_LA(31, false);
     }
-    if (id == 0) env_factor_reg_kernel<8><<<grid, RegCfg<8>::kThreads, RegCfg<8>::kSmem, s>>>(jobs, pm, status.p, dbg.p);
-    else if (id == 1) env_factor_reg_kernel<16><<<grid, RegCfg<16>::kThreads, RegCfg<16>::kSmem, s>>>(jobs, pm, status.p, dbg.p);
-    else if (id == 2) env_factor_reg_kernel<24><<<grid, RegCfg<24>::kThreads, RegCfg<24>::kSmem, s>>>(jobs, pm, status.p, dbg.p);
-    else env_factor_reg_kernel<31><<<grid, RegCfg<31>::kThreads, RegCfg<31>::kSmem, s>>>(jobs, pm, status.p, dbg.p);
+#undef LVBA_LAUNCH_LA
     ++*launches;
     return LVBA_OK;
   }
-  void launch_backsolve(int grid, const BacksolveJobs& bj, cudaStream_t s) {
-    if (use_warp_bs) env_backsolve_warp_kernel<<<grid, 64, kBsSmem, s>>>(bj);
-    else env_backsolve_ring_kernel<<<grid, kBsThreads, 0, s>>>(bj);
+  // x = D^-1 z for the pivots
+  void launch_apply(int nrows, const double* dinv_p, const double* z_p, double* x_p, cudaStream_t s) {
+    if (nrows > 0) env_dinv_apply_kernel<<<(6 * nrows + 127) / 128, 128, 0, s>>>(nrows, dinv_p, z_p, x_p);
   }
+  void launch_backsolve(int grid, const BacksolveJobs& bj, cudaStream_t s) { env_backsolve_warp_kernel<<<grid, 64, kBsSmem, s>>>(bj); }
   void dump_timing(const Envelope& env, cudaStream_t s) {
     if (!(dbg.p && dbg_dumped < dbg_max_dumps)) return;
     cudaStreamSynchronize(s);
@@ -386,7 +367,7 @@ struct EnvSolver {
     cudaMemcpy(h.data(), dbg.p, h.size() * 8, cudaMemcpyDeviceToHost);
     const int k0 = 64, k1 = nsteps - 64;
     if (k1 <= k0) return;
-    fprintf(stderr, "[factor timing] n=%d max_col=%d twisted=%d la=%d la_first=%d : per role  s1-s0 | s2-s1 | s3-s2 | next s0-s3 | step   (cycles, avg over k=%d..%d)\n", env.n, env.max_col, (int)tw, (int)use_la, (int)la_first, k0, k1);
+    fprintf(stderr, "[factor timing] n=%d max_col=%d twisted=%d : per role  s1-s0 | s2-s1 | s3-s2 | next s0-s3 | step   (cycles, avg over k=%d..%d)\n", env.n, env.max_col, (int)tw, k0, k1);
     for (int role = 0; role < 8; ++role) {
       double acc[5] = {0, 0, 0, 0, 0};
       for (int k = k0; k < k1; ++k) {
@@ -427,13 +408,13 @@ struct EnvSolver {
       js.j[1] = js.j[0];
       ++*launches;
       LVBA_TRY(launch_factor(pid(env_sep.max_col), 1, js, s, launches));
-      env_ldl_apply_kernel<<<(bs + 127) / 128, 128, 0, s>>>(bs, dinv_sep.p, zsep.p, xsep.p);
+      launch_apply(bs, dinv_sep.p, zsep.p, xsep.p, s);
       BacksolveJobs bj;
       bj.j[0] = BacksolveJob{vs, Lsep.p, xsep.p, bs};
       bj.j[1] = bj.j[0];
       launch_backsolve(1, bj, s);
-      env_ldl_apply_kernel<<<(m + 127) / 128, 128, 0, s>>>(m, dinv.p, z.p, x);
-      env_ldl_apply_kernel<<<(tw_nbstop + 127) / 128, 128, 0, s>>>(tw_nbstop, dinv_bot.p, zbot.p, xbot.p);
+      launch_apply(m, dinv.p, z.p, x, s);
+      launch_apply(tw_nbstop, dinv_bot.p, zbot.p, xbot.p, s);
       env_twist_place_sep_kernel<<<(bs * 6 + 127) / 128, 128, 0, s>>>(m, bs, tw_nbstop, xsep.p, x, xbot.p);
       bj.j[0] = BacksolveJob{vt, L.p, x, m};
       bj.j[1] = BacksolveJob{vb, Lbot.p, xbot.p, tw_nbstop};
@@ -446,7 +427,7 @@ struct EnvSolver {
       jobs.j[1] = jobs.j[0];
       LVBA_TRY(launch_factor(pid(mc), 1, jobs, s, launches));
       dump_timing(env, s);
-      env_ldl_apply_kernel<<<(env.n + 127) / 128, 128, 0, s>>>(env.n, dinv.p, z.p, x);
+      launch_apply(env.n, dinv.p, z.p, x, s);
       BacksolveJobs bj;
       bj.j[0] = BacksolveJob{v, L.p, x, env.n};
       bj.j[1] = bj.j[0];

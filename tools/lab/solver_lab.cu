@@ -18,6 +18,7 @@ static double maxdiff(const std::vector<double>& a, const std::vector<double>& b
   return d;
 }
 
+static bool g_prof = false;
 static int run_case(int n, int b, int ragged, unsigned seed, bool timing = false) {
   cudaStream_t s;
   cudaStreamCreate(&s);
@@ -48,16 +49,13 @@ static int run_case(int n, int b, int ragged, unsigned seed, bool timing = false
   for (int tw = 1; tw >= 0; --tw) {
     setenv("LVBA_NO_TWIST", tw ? "0" : "1", 1);
     // cfg: factor kernel x backsolve kernel (+ lab modes that disable one side of the factor kernel: timing only)
-    struct Cfg { const char* solver; const char* bs; int mode; };
-    const Cfg cfgs[] = {{"v6", "ring", 0}, {"v7", "ring", 0}, {"v7l", "ring", 0}, {"v6", "warp", 0}, {"v7", "warp", 0},
-                        {"v7", "warp", 1}, {"v7", "warp", 2}, {"v7l", "warp", 1}, {"v7l", "warp", 2}};
+    struct Cfg { int mode; };
+    const Cfg cfgs[] = {{0}, {1}, {2}};
     for (int cfg = 0; cfg < (int)(sizeof cfgs / sizeof cfgs[0]); ++cfg) {
       if (cfgs[cfg].mode != 0 && !(timing && tw == 1)) continue;
-      const bool la = cfgs[cfg].solver[1] == '7', wbs = cfgs[cfg].bs[0] == 'w';
+      if (g_prof && !(cfg == 0 && tw == 1)) continue;     // profiling run: twisted, once
       EnvSolver sol;
-      setenv("LVBA_SOLVER", cfgs[cfg].solver, 1);
-      setenv("LVBA_BACKSOLVE", cfgs[cfg].bs, 1);
-      setenv("LVBA_FACTOR_TIMING", (timing && tw == 1) ? "1" : "0", 1);
+      setenv("LVBA_FACTOR_TIMING", (timing && tw == 1 && !g_prof) ? "1" : "0", 1);
       sol.dbg_max_dumps = 1;
       cudaMemcpyToSymbol(g_la_mode, &cfgs[cfg].mode, sizeof(int));
       if (sol.prepare(env, s) != LVBA_OK) { printf("prepare failed: %s\n", last_error_ref().c_str()); return 1; }
@@ -65,14 +63,14 @@ static int run_case(int n, int b, int ragged, unsigned seed, bool timing = false
       float best = 1e30f;
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0); cudaEventCreate(&e1);
-      for (int rep = 0; rep < 4; ++rep) {
+      for (int rep = 0; rep < (g_prof ? 1 : 4); ++rep) {
         cudaMemcpyAsync(sol.z.p, rhs.data(), rhs.size() * 8, cudaMemcpyHostToDevice, s);
         cudaMemsetAsync(dX.p, 0, (size_t)n * 48, s);
         cudaEventRecord(e0, s);
         if (sol.solve(env, dH.p, dD.p, dX.p, s, &launches) != LVBA_OK) { printf("solve failed: %s\n", last_error_ref().c_str()); return 1; }
         cudaEventRecord(e1, s);
         cudaError_t err = cudaStreamSynchronize(s);
-        if (err != cudaSuccess) { printf("  tw=%d la=%d wbs=%d CUDA ERROR %s\n", tw, la, wbs, cudaGetErrorString(err)); return 2; }
+        if (err != cudaSuccess) { printf("  tw=%d CUDA ERROR %s\n", tw, cudaGetErrorString(err)); return 2; }
         float ms; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms);
       }
       std::vector<double> x((size_t)n * 6), Lh((size_t)env.nblocks * 36), zh((size_t)n * 6);
@@ -98,9 +96,8 @@ static int run_case(int n, int b, int ragged, unsigned seed, bool timing = false
       double sx = 0, dx = 0, sl = 0, dl = 0, sz = 0, dz = 0;
       if (x0.empty() || cfg == 0) { if (tw == 1 && cfg == 0) { x0 = x; } L0 = Lh; z0 = zh; }
       dx = maxdiff(x0, x, &sx); dl = maxdiff(L0, Lh, &sl); dz = maxdiff(z0, zh, &sz);
-      (void)la; (void)wbs;
-      printf("  twisted=%d factor=%-3s backsolve=%s mode=%d : %.3f ms  status=%d  |resid|=%.2e  dx=%.2e (of %.1e)  dL=%.2e (of %.1e)  dz=%.2e\n",
-             tw, cfgs[cfg].solver, cfgs[cfg].bs, cfgs[cfg].mode, best, st, rn, dx, sx, dl, sl, dz);
+      printf("  twisted=%d mode=%d : %.3f ms  status=%d  |resid|=%.2e  dx=%.2e (of %.1e)  dL=%.2e (of %.1e)  dz=%.2e\n",
+             tw, cfgs[cfg].mode, best, st, rn, dx, sx, dl, sl, dz);
       fflush(stdout);
       if (cfgs[cfg].mode == 0 && (!(rn < 1e-9) || st != 0)) rc_all = 3;
       cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -112,6 +109,7 @@ static int run_case(int n, int b, int ragged, unsigned seed, bool timing = false
 
 int main(int argc, char** argv) {
   int rc = 0;
+  if (argc > 1 && std::string(argv[1]) == "prof") { g_prof = true; return run_case(2000, 30, 0, 1, true); }
   rc |= run_case(2000, 30, 0, 1, true);
   rc |= run_case(1999, 20, 0, 2, true);
   rc |= run_case(700, 30, 3, 3);
