@@ -27,7 +27,7 @@ _lib = None
 EXPORTS = [
     "lvba_version", "lvba_device_count", "lvba_status_string", "lvba_last_error", "lvba_release_cached_memory",
     "lvba_lidar_default_opts", "lvba_visual_default_opts",
-    "lvba_lidar_lm", "lvba_lidar_create", "lvba_lidar_destroy", "lvba_lidar_set_poses",
+    "lvba_lidar_lm", "lvba_lidar_lm_batch", "lvba_lidar_create", "lvba_lidar_destroy", "lvba_lidar_set_poses",
     "lvba_lidar_get_poses", "lvba_lidar_build", "lvba_lidar_residual", "lvba_lidar_solve",
     "lvba_lidar_structure", "lvba_lidar_get_system", "lvba_lidar_reset_lm", "lvba_lidar_reset_state", "lvba_lidar_iterate",
     "lvba_lidar_counts",
@@ -142,6 +142,23 @@ def lidar_lm(vox_ptr, pose_idx, clusters, poses, opts=None):
                            _p(cl, C.c_double), _p(ps, C.c_double), C.byref(opts) if opts is not None else None,
                            C.byref(s)))
     return ps, s.as_dict()
+
+
+def lidar_lm_batch(win_ptr, vox_ptr, pose_idx, clusters, poses, min_voxels_per_pose=3, opts=None):
+    """Every window of LvbaSystem::runWindowBA (src/lvba_system.cpp:232-302) in one call.
+    Returns (poses, [per-window summary dict], total summary dict)."""
+    lib = load_library()
+    wp = np.ascontiguousarray(win_ptr, np.int32)
+    vp = np.ascontiguousarray(vox_ptr, np.int64); pi = np.ascontiguousarray(pose_idx, np.int32)
+    cl = _f64(clusters); ps = _f64(poses).copy()
+    nw = len(wp) - 1
+    sums = (Summary * max(nw, 1))()
+    tot = Summary()
+    _chk(lib.lvba_lidar_lm_batch(C.c_int32(nw), _p(wp, C.c_int32), C.c_int64(len(vp) - 1), _p(vp, C.c_int64),
+                                 _p(pi, C.c_int32), _p(cl, C.c_double), _p(ps, C.c_double),
+                                 C.c_int32(min_voxels_per_pose), C.byref(opts) if opts is not None else None,
+                                 sums, C.byref(tot)))
+    return ps, [sums[i].as_dict() for i in range(nw)], tot.as_dict()
 
 
 class LidarProblem:

@@ -222,8 +222,9 @@ struct FactorJob {
   int n_stop;      // number of pivots to eliminate (== e.n for a complete factorisation)
   double* wdump;   // [bs*bs*36] trailing window at n_stop, block (i,j) at ((i-n_stop)*bs + (j-n_stop))*36, bs = e.n - n_stop
   double* zdump;   // [bs*6]
+  int* status;     // set to 1 when a pivot block is singular / non-finite
 };
-struct FactorJobs { FactorJob j[2]; };
+// Jobs live in device memory (one per CTA): two for the twisted solve, one per window for the batched window BA.
 
 // x = D^-1 z  (block diagonal solve, fully parallel)
 __global__ void env_dinv_apply_kernel(int n, const double* __restrict__ dinv, const double* __restrict__ z, double* __restrict__ x) {
@@ -244,7 +245,11 @@ struct BacksolveJob {
   double* x;        // in: D^-1 z for the pivots (rows < n_given) and the FINAL solution for rows >= n_given ; out: solution
   int n_given;      // rows >= n_given are given (separator of the twisted solve); == e.n for a plain solve
 };
-struct BacksolveJobs { BacksolveJob j[2]; };
+
+// status[0] |= status[1..n-1]  (the twisted solve has one flag per factorisation instance)
+__global__ void env_status_or_kernel(int* __restrict__ status, int n) {
+  if (threadIdx.x == 0) { int v = 0; for (int i = 0; i < n; ++i) v |= status[i]; status[0] = v; }
+}
 
 // ---- twisted solve helpers -------------------------------------------------------------------------------
 // Reversed copy of the bottom part: row r' of the reversed matrix = original row n-1-r'; its lower blocks are the

@@ -107,12 +107,12 @@ __device__ int g_la_mode = 0;      // solver_lab only: 1 = pair threads skip the
 
 template <int P, bool kTiming>
 __global__ void __launch_bounds__(LaCfg<P>::kThreads, 1)
-env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_map, int* __restrict__ status,
+env_factor_la_kernel(const FactorJob* __restrict__ jobs, const unsigned short* __restrict__ pair_map,
                      long long* __restrict__ dbg_all) {
   using Cfg = LaCfg<P>;
   constexpr int S = Cfg::S;
   constexpr int PS = P * S;                       // one parity of sL / sT / sA
-  const FactorJob& J = jobs.j[blockIdx.x];
+  const FactorJob J = jobs[blockIdx.x];
   const EnvView e = J.e;
   double* __restrict__ L = J.L;
   double* __restrict__ dinv = J.dinv;
@@ -499,7 +499,7 @@ env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_ma
         J.zdump[o] = sZ[(i % P) * 6 + o % 6];
       }
     }
-    if (bad) status[0] = 1;
+    if (bad) J.status[0] = 1;
   }
 #undef LVBA_STAMP
 }
@@ -515,7 +515,7 @@ env_factor_la_kernel(FactorJobs jobs, const unsigned short* __restrict__ pair_ma
 // consecutive rows; it also leaves each row's first column and offset in the stage header.  The x entries that
 // enter the window are fetched kBsXDist rows ahead, and the next row's block is loaded from shared memory while the
 // current row is applied (software pipeline).
-constexpr int kBsStages = 4;
+constexpr int kBsStages = 6;
 constexpr int kBsGroup = 4;                                  // rows per stage (divides 32)
 constexpr int kBsRowsDoubles = kBsGroup * 31 * 36;           // L blocks of the staged rows
 constexpr int kBsStageDoubles = kBsRowsDoubles + kBsGroup * 6;   // + the x entries that enter the window with these rows
@@ -545,7 +545,7 @@ LVBA_DEV void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long
 }
 
 __global__ void __launch_bounds__(64, 1)
-env_backsolve_warp_kernel(BacksolveJobs jobs) {
+env_backsolve_warp_kernel(const BacksolveJob* __restrict__ jobs) {
   constexpr int NS = kBsStages, R = kBsGroup;
   extern __shared__ __align__(128) double smem_bs[];
   double* ring = smem_bs;                                                       // [NS][kBsStageDoubles]
@@ -554,7 +554,7 @@ env_backsolve_warp_kernel(BacksolveJobs jobs) {
   int* sRowF = reinterpret_cast<int*>(empty + NS);                              // [NS][R] first column of each staged row
   int* sRowOff = sRowF + NS * R;                                                // [NS][R] offset (doubles) of each staged row inside the stage
   int* sRowX = sRowOff + NS * R;                                                // [NS][R] offset (doubles) of the x entry that replaces the row, or -1
-  const BacksolveJob& J = jobs.j[blockIdx.x];
+  const BacksolveJob J = jobs[blockIdx.x];
   const EnvView e = J.e;
   const double* __restrict__ L = J.L;
   double* __restrict__ x = J.x;
@@ -618,28 +618,31 @@ env_backsolve_warp_kernel(BacksolveJobs jobs) {
       for (int q = 0; q < 6; ++q) xs[q] = (r >= 0) ? x[6 * (long long)r + q] : 0.0;
     }
     double2 blk0[18], blk1[18];
-    double xe0[6], xe1[6];
+    double2 xe0[3], xe1[3];
+    bool on0 = false, on1 = false, xon0 = false, xon1 = false;
     int mF = 0, mOff = 0, mX = -1;                     // metadata of the row whose block is loaded next
     auto meta = [&](int itn) {                         // stage M for the row of iteration itn
       const int g = itn / R, st = g % NS, rr = itn % R;
       if (rr == 0) { mbar_wait(full + st, (unsigned)((g / NS) & 1)); __syncwarp(); }
       mF = sRowF[st * R + rr]; mOff = sRowOff[st * R + rr]; mX = sRowX[st * R + rr];
     };
-    auto fetch = [&](int i, int itn, double2 (&blk)[18], double (&xe)[6]) {   // stage B for row i, using the metadata in mF/mOff/mX
+    // stage B for row i, using the metadata in mF/mOff/mX.  The loaded values are used unconditionally; the flags
+    // decide at the END of the apply stage whether they count (no select sits between the loads and their use)
+    auto fetch = [&](int i, int itn, double2 (&blk)[18], double2 (&xe)[3], bool& on, bool& xon) {
       const double* stg = ring + ((itn / R) % NS) * kBsStageDoubles;
       const int upto = i < n_given ? i : n_given;      // given rows only act on the pivots' columns
       const int cnt = upto > mF ? upto - mF : 0;
       const int jo = (lane - mF) & 31;                 // column mF + jo is the one congruent to this lane
-      const bool on = jo < cnt;
+      on = jo < cnt;
+      xon = mX >= 0;
       const double2* b2 = reinterpret_cast<const double2*>(stg + mOff + (on ? jo : 0) * 36);
 #pragma unroll
-      for (int t = 0; t < 18; ++t) { const double2 v = b2[t]; blk[t] = on ? v : make_double2(0.0, 0.0); }
-      const double2* x2 = reinterpret_cast<const double2*>(stg + (mX >= 0 ? mX : 0));
-      const bool xon = mX >= 0;
+      for (int t = 0; t < 18; ++t) blk[t] = b2[t];
+      const double2* x2 = reinterpret_cast<const double2*>(stg + (xon ? mX : 0));
 #pragma unroll
-      for (int t = 0; t < 3; ++t) { const double2 v = x2[t]; xe[2 * t] = xon ? v.x : 0.0; xe[2 * t + 1] = xon ? v.y : 0.0; }
+      for (int t = 0; t < 3; ++t) xe[t] = x2[t];
     };
-    auto apply = [&](int i, int itn, const double2 (&blk)[18], const double (&xe)[6]) {   // stage C for row i
+    auto apply = [&](int i, int itn, const double2 (&blk)[18], const double2 (&xe)[3], bool on, bool xon) {   // stage C for row i
       const int owner = i & 31;
       const bool mine = lane == owner;
       double xi[6];
@@ -659,25 +662,30 @@ env_backsolve_warp_kernel(BacksolveJobs jobs) {
         v0[0] += a0.x * xi[q]; v0[1] += a0.y * xi[q]; v0[2] += a1.x * xi[q]; v0[3] += a1.y * xi[q]; v0[4] += a2.x * xi[q]; v0[5] += a2.y * xi[q];
         v1[0] += c0.x * xi[q + 1]; v1[1] += c0.y * xi[q + 1]; v1[2] += c1.x * xi[q + 1]; v1[3] += c1.y * xi[q + 1]; v1[4] += c2.x * xi[q + 1]; v1[5] += c2.y * xi[q + 1];
       }
+      const double xen[6] = {xe[0].x, xe[0].y, xe[1].x, xe[1].y, xe[2].x, xe[2].y};
 #pragma unroll
-      for (int cc = 0; cc < 6; ++cc) xs[cc] = mine ? xe[cc] : xs[cc] - (v0[cc] + v1[cc]);   // row i leaves, row i-32 takes its lane
+      for (int cc = 0; cc < 6; ++cc) {
+        const double upd = xs[cc] - (v0[cc] + v1[cc]);
+        // row i leaves the window and row i-32 takes its lane; lanes without a block in row i keep their value
+        xs[cc] = mine ? (xon ? xen[cc] : 0.0) : (on ? upd : xs[cc]);
+      }
       if ((itn % R) == R - 1 || i == 0) {              // every row of this group has been applied: the stage is free
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + ((itn / R) % NS));
       }
     };
     meta(0);
-    fetch(n - 1, 0, blk0, xe0);
+    fetch(n - 1, 0, blk0, xe0, on0, xon0);
     if (n > 1) meta(1);
     for (int i = n - 1; i >= 0; i -= 2) {
       const int itn = n - 1 - i;
-      if (i >= 1) fetch(i - 1, itn + 1, blk1, xe1);
+      if (i >= 1) fetch(i - 1, itn + 1, blk1, xe1, on1, xon1);
       if (i >= 2) meta(itn + 2);
-      apply(i, itn, blk0, xe0);
+      apply(i, itn, blk0, xe0, on0, xon0);
       if (i >= 1) {
-        if (i >= 2) fetch(i - 2, itn + 2, blk0, xe0);
+        if (i >= 2) fetch(i - 2, itn + 2, blk0, xe0, on0, xon0);
         if (i >= 3) meta(itn + 3);
-        apply(i - 1, itn + 1, blk1, xe1);
+        apply(i - 1, itn + 1, blk1, xe1, on1, xon1);
       }
     }
   }

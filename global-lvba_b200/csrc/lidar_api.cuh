@@ -19,6 +19,46 @@ __global__ void lidar_aos_to_soa_kernel(long long nnz, long long nnz_pad, const 
   for (int q = 0; q < 5; ++q) soa[q * nnz_pad + i] = r[q];
 }
 
+// ---- batched window BA (LvbaSystem::runWindowBA, reference src/lvba_system.cpp:232-302): per-window reductions.
+// One CTA per window; ranges are contiguous because batches and poses are ordered by window.
+__global__ void lidar_group_sum_kernel(const double* __restrict__ part, const int* __restrict__ rng /*[G+1]*/, double* __restrict__ out, int slot) {
+  __shared__ double red[32];
+  const int g = blockIdx.x;
+  double s = 0.0;
+  for (int i = rng[g] + threadIdx.x; i < rng[g + 1]; i += 128) s += part[i];
+  const double tot = block_sum<128>(s, red);
+  if (threadIdx.x == 0) out[4 * g + slot] = tot;
+}
+// z = -g ; dadd = u_w * diag with the window's own damping (bavoxel.hpp:692-693 per window)
+__global__ void lidar_rhs_grouped_kernel(int n6, const double* __restrict__ g, const double* __restrict__ diag, const double* __restrict__ u_grp,
+                                         const int* __restrict__ pose_grp, double* __restrict__ z, double* __restrict__ dadd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n6) { z[i] = -g[i]; dadd[i] = u_grp[pose_grp[i / 6]] * diag[i]; }
+}
+// q1_w = 0.5 dx_w . (u_w D dx_w - g_w) (bavoxel.hpp:729) -> out[4w+1]; non-finite dx or singular pivot -> out[4w+2]
+__global__ void lidar_q1_grouped_kernel(const int* __restrict__ grp_ptr, const double* __restrict__ dx, const double* __restrict__ diag,
+                                        const double* __restrict__ g, const double* __restrict__ u_grp, const int* __restrict__ status,
+                                        double* __restrict__ out) {
+  __shared__ double red[32];
+  const int w = blockIdx.x;
+  const double u = u_grp[w];
+  double s = 0.0, bad = 0.0;
+  for (int i = 6 * grp_ptr[w] + threadIdx.x; i < 6 * grp_ptr[w + 1]; i += 128) {
+    const double d = dx[i];
+    s += d * (u * diag[i] * d - g[i]);
+    if (!isfinite(d)) bad = 1.0;
+  }
+  const double tot = block_sum<128>(s, red);
+  const double tb = block_sum<128>(bad, red);
+  if (threadIdx.x == 0) { out[4 * w + 1] = 0.5 * tot; out[4 * w + 2] = tb + (status[w] ? 1.0 : 0.0); }
+}
+// poses <- trial for the windows whose step was accepted (bavoxel.hpp:744-746 per window)
+__global__ void lidar_select_poses_kernel(int W, const int* __restrict__ pose_grp, const int* __restrict__ accept,
+                                          const double* __restrict__ trial, double* __restrict__ poses) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 12 * W && accept[pose_grp[i / 12]]) poses[i] = trial[i];
+}
+
 }  // namespace lvba
 
 struct lvba_lidar_problem {
@@ -48,6 +88,13 @@ struct lvba_lidar_problem {
   bool is_calc_hess = true, have_first = false, converged = false;
   double cost_first = 0.0, cost_last = 0.0;
   int iters = 0, accepted = 0, builds = 0, termination = LVBA_TERM_MAX_ITER;
+  // ---- batched window BA: n_groups independent windows in one block-diagonal system
+  int n_groups = 0;
+  std::vector<int> grp_ptr;            // [G+1] pose offsets
+  std::vector<long long> grp_V;        // voxels per window (AVG_THR divisor of each window)
+  lvba::DevBuf<int> d_grp_ptr, d_pose_grp, d_grp_batch, d_accept;
+  lvba::DevBuf<double> d_u_grp, d_grp_scal;
+  double* h_grp_scal = nullptr;        // pinned [4G]: r1 sum, q1, bad flag, r2 sum per window
 
   lvba::LidarView view() const {
     lvba::LidarView v_;
@@ -58,6 +105,7 @@ struct lvba_lidar_problem {
   }
   ~lvba_lidar_problem() {
     if (h_scal) cudaFreeHost(h_scal);
+    if (h_grp_scal) cudaFreeHost(h_grp_scal);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -87,7 +135,7 @@ inline int lidar_validate(int32_t W, int64_t V, const int64_t* vox_ptr, const in
 
 inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const int32_t* pose_idx,
                              const double* clusters, const double* poses, int32_t device,
-                             lvba_lidar_problem** out) {
+                             lvba_lidar_problem** out, int32_t n_groups = 0, const int32_t* grp_ptr = nullptr) {
   if (!out) return fail(LVBA_ERR_INVALID_ARG, "out is null");
   *out = nullptr;
   const double t_val0 = wall_ms();
@@ -120,6 +168,24 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   }
   LVBA_TRY(P->env.build(first_raw, s, &P->h2d));
   LVBA_TRY(P->solver.prepare(P->env, s));
+  // ---- batched window BA: window of every pose, every voxel inside one window
+  std::vector<int> pose_grp;
+  if (n_groups > 0) {
+    if (comm().active()) return fail(LVBA_ERR_UNSUPPORTED, "the batched window BA runs on one GPU per call (windows are independent: shard them across ranks)");
+    P->n_groups = n_groups;
+    P->grp_ptr.assign(grp_ptr, grp_ptr + n_groups + 1);
+    pose_grp.resize((size_t)W);
+    for (int g = 0; g < n_groups; ++g)
+      for (int r = grp_ptr[g]; r < grp_ptr[g + 1]; ++r) pose_grp[r] = g;
+    P->grp_V.assign((size_t)n_groups, 0);
+    for (int64_t a = 0; a < V; ++a) {
+      const int g = pose_grp[pose_idx[vox_ptr[a]]];
+      if (pose_grp[pose_idx[vox_ptr[a + 1] - 1]] != g)
+        return fail(LVBA_ERR_INVALID_ARG, "voxel %lld spans two windows", (long long)a);
+      ++P->grp_V[g];
+    }
+    LVBA_TRY(P->solver.prepare_batch(P->env, P->grp_ptr, s));
+  }
   lap("envelope+solver alloc");
 
   // ---- shard: voxel -> owner of its lowest pose index
@@ -128,6 +194,8 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   mine.reserve((size_t)V);
   for (int64_t a = 0; a < V; ++a)
     if (!cm.active() || shard_owner(pose_idx[vox_ptr[a]], W, cm.n_ranks) == cm.rank) mine.push_back(a);
+  if (n_groups > 0)      // windows in order: batches and their partial sums become contiguous per window
+    std::stable_sort(mine.begin(), mine.end(), [&](int64_t x, int64_t y) { return pose_grp[pose_idx[vox_ptr[x]]] < pose_grp[pose_idx[vox_ptr[y]]]; });
   const int64_t Vl = (int64_t)mine.size();
   std::vector<int> l_vox_ptr(Vl + 1, 0);
   for (int64_t i = 0; i < Vl; ++i) l_vox_ptr[i + 1] = l_vox_ptr[i] + (int)(vox_ptr[mine[i] + 1] - vox_ptr[mine[i]]);
@@ -140,12 +208,27 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
     int ns = 0, nv = 0;
     for (int64_t i = 0; i < Vl; ++i) {
       const int K = l_vox_ptr[i + 1] - l_vox_ptr[i];
-      if (nv > 0 && (ns + K > kSlots || nv + 1 > kMaxVoxPerBatch)) { batch_vox.push_back((int)i); ns = 0; nv = 0; }
+      const bool new_grp = n_groups > 0 && i > 0 && pose_grp[pose_idx[vox_ptr[mine[i]]]] != pose_grp[pose_idx[vox_ptr[mine[i - 1]]]];
+      if (nv > 0 && (ns + K > kSlots || nv + 1 > kMaxVoxPerBatch || new_grp)) { batch_vox.push_back((int)i); ns = 0; nv = 0; }
       ns += K; ++nv;
     }
     if (Vl > 0) batch_vox.push_back((int)Vl);
   }
   P->n_batches = (int)batch_vox.size() - 1;
+  if (n_groups > 0) {
+    std::vector<int> grp_batch((size_t)n_groups + 1, 0);       // batch range of every window
+    for (int b = 0; b < P->n_batches; ++b) ++grp_batch[pose_grp[pose_idx[vox_ptr[mine[batch_vox[b]]]]] + 1];
+    for (int g = 0; g < n_groups; ++g) grp_batch[g + 1] += grp_batch[g];
+    LVBA_TRY(P->d_grp_batch.upload(grp_batch, s, &P->h2d));
+    LVBA_TRY(P->d_grp_ptr.upload(P->grp_ptr, s, &P->h2d));
+    LVBA_TRY(P->d_pose_grp.upload(pose_grp, s, &P->h2d));
+    LVBA_TRY(P->d_accept.alloc((size_t)n_groups));
+    LVBA_TRY(P->d_u_grp.alloc((size_t)n_groups));
+    LVBA_TRY(P->d_grp_scal.alloc((size_t)4 * n_groups));
+    LVBA_TRY(P->d_grp_scal.zero(s));
+    LVBA_CUDA(cudaMallocHost((void**)&P->h_grp_scal, (size_t)4 * n_groups * sizeof(double)));
+    LVBA_CUDA(cudaStreamSynchronize(s));                       // local vectors
+  }
   // ---- pair table
   std::vector<long long> batch_pair(P->n_batches + 1, 0);
   long long np = 0;
@@ -349,6 +432,130 @@ inline int lidar_iterate_impl(lvba_lidar_problem* P, int n_iter, lvba_summary* s
   return LVBA_OK;
 }
 
+// ---------------------------------------------------------------- batched window BA
+// damping_iter (bavoxel.hpp:662-767) for every window at once: the windows share the kernels (one block-diagonal
+// system, one CTA per window in the factorisation) but keep their own u, v, accept/reject decision and stop test,
+// exactly as n_windows separate calls would.  A rejected window keeps its poses, so rebuilding H for everybody
+// reproduces its previous H (":753-758 H not rebuilt" costs nothing in parity).
+inline int lidar_batch_lm_impl(lvba_lidar_problem* P, int min_voxels_per_pose, lvba_summary* sums, lvba_summary* total) {
+  const double t0 = wall_ms();
+  const int G = P->n_groups;
+  cudaStream_t s = P->stream;
+  struct WinState { double u, v, residual1, cost_first, cost_last; bool active, converged, have_first, skipped; int iters, accepted, term; };
+  std::vector<WinState> ws((size_t)G);
+  std::vector<double> u_host((size_t)G);
+  std::vector<int> acc_host((size_t)G);
+  int n_active = 0;
+  for (int g = 0; g < G; ++g) {
+    const int Wg = P->grp_ptr[g + 1] - P->grp_ptr[g];
+    WinState& w = ws[g];
+    w.u = P->opts.u0; w.v = P->opts.v0; w.residual1 = 0; w.cost_first = w.cost_last = 0;
+    w.converged = false; w.have_first = false; w.iters = w.accepted = 0; w.term = LVBA_TERM_MAX_ITER;
+    w.skipped = Wg <= 0 || P->grp_V[g] == 0 || P->grp_V[g] < (long long)min_voxels_per_pose * Wg;   // src/lvba_system.cpp:262-266
+    w.active = !w.skipped;
+    if (w.skipped) w.term = LVBA_TERM_SKIPPED;
+    n_active += w.active;
+  }
+  const int n6 = 6 * P->W;
+  const EnvView ev = P->env.view();
+  int passes = 0;
+  for (int it = 0; it < P->opts.max_iter && n_active > 0; ++it, ++passes) {
+    for (int g = 0; g < G; ++g) u_host[g] = ws[g].u;
+    LVBA_CUDA(cudaMemcpyAsync(P->d_u_grp.p, u_host.data(), (size_t)G * sizeof(double), cudaMemcpyHostToDevice, s));
+    P->h2d += (int64_t)G * 8;
+    // ---- H, g, sum(lambda0) per window
+    P->timers.begin(PH_BUILD);
+    LVBA_TRY(P->H.zero(s));
+    LVBA_TRY(P->g.zero(s));
+    if (P->n_batches > 0) {
+      lidar_build_kernel<<<P->n_batches, kSlots, lidar_build_smem_bytes(), s>>>(P->view(), ev, P->poses.p, P->H.p, P->g.p, P->batch_res.p);
+      ++P->launches;
+    }
+    lidar_group_sum_kernel<<<G, 128, 0, s>>>(P->batch_res.p, P->d_grp_batch.p, P->d_grp_scal.p, 0);
+    ++P->launches;
+    P->timers.end();
+    ++P->builds;
+    // ---- (H + u_w diag(H)) dx = -g, q1 per window
+    P->timers.begin(PH_SOLVE);
+    env_get_diag_kernel<<<(n6 + 255) / 256, 256, 0, s>>>(ev, P->H.p, P->diag.p);
+    lidar_rhs_grouped_kernel<<<(n6 + 255) / 256, 256, 0, s>>>(n6, P->g.p, P->diag.p, P->d_u_grp.p, P->d_pose_grp.p, P->solver.z.p, P->dadd.p);
+    P->launches += 2;
+    LVBA_TRY(P->solver.solve(P->env, P->H.p, P->dadd.p, P->dx.p, s, &P->launches));
+    lidar_q1_grouped_kernel<<<G, 128, 0, s>>>(P->d_grp_ptr.p, P->dx.p, P->diag.p, P->g.p, P->d_u_grp.p, P->solver.status.p, P->d_grp_scal.p);
+    ++P->launches;
+    P->timers.end();
+    // ---- trial state and its residual per window
+    P->timers.begin(PH_RESID);
+    lidar_retract_kernel<<<(P->W + 127) / 128, 128, 0, s>>>(P->W, P->poses.p, P->dx.p, P->trial.p);
+    ++P->launches;
+    if (P->n_batches > 0) {
+      lidar_residual_kernel<<<P->n_batches, kSlots, 0, s>>>(P->view(), P->trial.p, P->batch_res.p);
+      ++P->launches;
+    }
+    lidar_group_sum_kernel<<<G, 128, 0, s>>>(P->batch_res.p, P->d_grp_batch.p, P->d_grp_scal.p, 3);
+    ++P->launches;
+    P->timers.end();
+    LVBA_CUDA(cudaMemcpyAsync(P->h_grp_scal, P->d_grp_scal.p, (size_t)4 * G * sizeof(double), cudaMemcpyDeviceToHost, s));
+    LVBA_CUDA(cudaStreamSynchronize(s));
+    P->d2h += (int64_t)G * 32;
+    LVBA_CUDA(cudaGetLastError());
+    // ---- per-window decision (bavoxel.hpp:733-762)
+    for (int g = 0; g < G; ++g) {
+      WinState& w = ws[g];
+      acc_host[g] = 0;
+      if (!w.active) continue;
+      const double Vg = (double)P->grp_V[g];
+      const double* sc = P->h_grp_scal + 4 * g;
+      w.residual1 = sc[0] / Vg;                                // AVG_THR, :635
+      if (!w.have_first) { w.cost_first = w.cost_last = w.residual1; w.have_first = true; }
+      const double q1 = sc[1] / Vg;                            // :732
+      double residual2 = sc[3] / Vg;
+      const bool bad = sc[2] != 0.0 || !std::isfinite(residual2) || !std::isfinite(q1);
+      if (bad) residual2 = NAN;
+      double q = w.residual1 - residual2;
+      ++w.iters;
+      if (P->opts.verbose)
+        fprintf(stderr, "[lvba window %d] iter %d: (%.9g %.9g) u: %g v: %g q: %g q1: %g\n", g, w.iters - 1, w.residual1, residual2, w.u, w.v, q, q1);
+      if (q > 0) {                                             // :744-752
+        acc_host[g] = 1;
+        q = q / q1;
+        w.v = 2;
+        q = 1 - std::pow(2 * q - 1, 3);
+        w.u *= (q < (1.0 / 3.0) ? (1.0 / 3.0) : q);
+        ++w.accepted;
+        w.cost_last = residual2;
+      } else {                                                 // :753-758
+        w.u = w.u * w.v;
+        w.v = 2 * w.v;
+      }
+      if (P->opts.rel_tol >= 0 && std::fabs(w.residual1 - residual2) / w.residual1 < P->opts.rel_tol) {   // :760
+        w.converged = true; w.active = false; w.term = LVBA_TERM_FUNCTION_TOL; --n_active;
+      }
+    }
+    LVBA_CUDA(cudaMemcpyAsync(P->d_accept.p, acc_host.data(), (size_t)G * sizeof(int), cudaMemcpyHostToDevice, s));
+    P->h2d += (int64_t)G * 4;
+    lidar_select_poses_kernel<<<(12 * P->W + 255) / 256, 256, 0, s>>>(P->W, P->d_pose_grp.p, P->d_accept.p, P->trial.p, P->poses.p);
+    ++P->launches;
+    LVBA_CUDA(cudaStreamSynchronize(s));                       // acc_host is reused next pass
+  }
+  double ms[PH_COUNT] = {0, 0, 0};
+  P->timers.collect(ms);
+  if (sums)
+    for (int g = 0; g < G; ++g) {
+      lvba_summary& o = sums[g];
+      memset(&o, 0, sizeof o);
+      o.iterations = ws[g].iters; o.accepted = ws[g].accepted; o.hessian_builds = ws[g].iters; o.termination = ws[g].term;
+      o.cost_first = ws[g].cost_first; o.cost_last = ws[g].cost_last; o.damping_last = ws[g].u;
+    }
+  if (total) {
+    memset(total, 0, sizeof *total);
+    total->iterations = passes; total->hessian_builds = passes;
+    for (int g = 0; g < G; ++g) total->accepted += ws[g].accepted;
+    total->ms_total = wall_ms() - t0; total->ms_build = ms[PH_BUILD]; total->ms_solve = ms[PH_SOLVE]; total->ms_residual = ms[PH_RESID];
+  }
+  return LVBA_OK;
+}
+
 }  // namespace lvba
 
 // ================================================================ C ABI
@@ -504,6 +711,39 @@ int lvba_lidar_lm(int32_t W, int64_t V, const int64_t* vox_ptr, const int32_t* p
     summary->ms_setup = p->ms_setup;
     summary->kernel_launches = p->launches; summary->h2d_bytes = p->h2d; summary->d2h_bytes = p->d2h;
     summary->ms_total = lvba::wall_ms() - t0;
+  }
+  lvba_lidar_destroy(p);
+  return rc;
+}
+
+int lvba_lidar_lm_batch(int32_t n_windows, const int32_t* win_ptr, int64_t V, const int64_t* vox_ptr, const int32_t* pose_idx,
+                        const double* clusters, double* poses, int32_t min_voxels_per_pose, const lvba_lidar_opts* opts,
+                        lvba_summary* summaries, lvba_summary* total) {
+  const double t0 = lvba::wall_ms();
+  if (n_windows <= 0 || !win_ptr) return lvba::fail(LVBA_ERR_INVALID_ARG, "n_windows=%d must be positive and win_ptr non-null", n_windows);
+  if (win_ptr[0] != 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "win_ptr[0] must be 0");
+  for (int w = 0; w < n_windows; ++w)
+    if (win_ptr[w + 1] < win_ptr[w]) return lvba::fail(LVBA_ERR_INVALID_ARG, "win_ptr must be non-decreasing");
+  if (min_voxels_per_pose < 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "min_voxels_per_pose must be >= 0");
+  lvba_lidar_opts o;
+  if (opts) o = *opts; else lvba_lidar_default_opts(&o);
+  lvba_lidar_problem* p = nullptr;
+  int rc;
+  try { rc = lvba::lidar_create_impl(win_ptr[n_windows], V, vox_ptr, pose_idx, clusters, poses, o.device, &p, n_windows, win_ptr); }
+  catch (const std::bad_alloc&) { return lvba::fail(LVBA_ERR_NOMEM, "host allocation failed"); }
+  catch (...) { return lvba::fail(LVBA_ERR_INVALID_ARG, "unexpected exception in lvba_lidar_lm_batch"); }
+  if (rc != LVBA_OK) return rc;
+  p->opts = o;
+  lvba_summary tot;
+  memset(&tot, 0, sizeof tot);
+  try { rc = lvba::lidar_batch_lm_impl(p, min_voxels_per_pose, summaries, &tot); }
+  catch (...) { rc = lvba::fail(LVBA_ERR_NOMEM, "host allocation failed in lvba_lidar_lm_batch"); }
+  if (rc == LVBA_OK) rc = lvba_lidar_get_poses(p, poses);     // written back only on success; skipped windows are unchanged on the device
+  if (rc == LVBA_OK && total) {
+    *total = tot;
+    total->ms_setup = p->ms_setup;
+    total->kernel_launches = p->launches; total->h2d_bytes = p->h2d; total->d2h_bytes = p->d2h;
+    total->ms_total = lvba::wall_ms() - t0;
   }
   lvba_lidar_destroy(p);
   return rc;

@@ -252,6 +252,15 @@ inline std::vector<unsigned short> build_pair_map(int P, int n_threads) {
 struct EnvSolver {
   DevBuf<double> L, dinv, z;
   DevBuf<int> status;
+  // device job tables of the register-window path (built at the first solve, when the solution buffer is known)
+  DevBuf<FactorJob> d_fjobs;
+  DevBuf<BacksolveJob> d_bjobs;
+  const double* jobs_x = nullptr;
+  // ---- batched mode (window BA): the system is block diagonal; every group is factorised by its own CTA
+  bool batch = false;
+  int n_groups = 0;
+  std::vector<int> grp_ptr;     // [n_groups+1] row offsets
+  DevBuf<int> first_rel;        // first[r] relative to the first row of r's group
   DevBuf<unsigned short> pair_map[4];   // thread -> slot pair of the register-window kernel, per P in {8,16,24,31}
   bool have_map[4] = {false, false, false, false};
   DevBuf<long long> dbg;        // LVBA_FACTOR_TIMING=1: per-step phase clocks of the register-window kernel
@@ -278,7 +287,8 @@ struct EnvSolver {
     LVBA_TRY(L.alloc((size_t)env.nblocks * 36));
     LVBA_TRY(dinv.alloc((size_t)env.n * 36));
     LVBA_TRY(z.alloc((size_t)env.n * 6));
-    LVBA_TRY(status.alloc(1));
+    LVBA_TRY(status.alloc(4));
+    jobs_x = nullptr;
     {
       const char* ft = getenv("LVBA_FACTOR_TIMING");
       if (ft && ft[0] == '1') { LVBA_TRY(dbg.alloc((size_t)env.n * 32)); }
@@ -341,10 +351,10 @@ struct EnvSolver {
     have_map[id] = true;
     return LVBA_OK;
   }
-  int launch_factor(int id, int grid, const FactorJobs& jobs, cudaStream_t s, int64_t* launches) {
+  int launch_factor(int id, int grid, const FactorJob* jobs, cudaStream_t s, int64_t* launches) {
     LVBA_TRY(ensure_map(id, s));
     const unsigned short* pm = pair_map[id].p;
-#define LVBA_LAUNCH_LA(PP, TT) env_factor_la_kernel<PP, TT><<<grid, LaCfg<PP>::kThreads, LaCfg<PP>::kSmem, s>>>(jobs, pm, status.p, dbg.p)
+#define LVBA_LAUNCH_LA(PP, TT) env_factor_la_kernel<PP, TT><<<grid, LaCfg<PP>::kThreads, LaCfg<PP>::kSmem, s>>>(jobs, pm, dbg.p)
     if (dbg.p) {
       if (id == 0) LVBA_LAUNCH_LA(8, true); else if (id == 1) LVBA_LAUNCH_LA(16, true); else if (id == 2) LVBA_LAUNCH_LA(24, true); else LVBA_LAUNCH_LA(31, true);
     } else {
@@ -358,7 +368,7 @@ struct EnvSolver {
   void launch_apply(int nrows, const double* dinv_p, const double* z_p, double* x_p, cudaStream_t s) {
     if (nrows > 0) env_dinv_apply_kernel<<<(6 * nrows + 127) / 128, 128, 0, s>>>(nrows, dinv_p, z_p, x_p);
   }
-  void launch_backsolve(int grid, const BacksolveJobs& bj, cudaStream_t s) { env_backsolve_warp_kernel<<<grid, 64, kBsSmem, s>>>(bj); }
+  void launch_backsolve(int grid, const BacksolveJob* bj, cudaStream_t s) { env_backsolve_warp_kernel<<<grid, 64, kBsSmem, s>>>(bj); }
   void dump_timing(const Envelope& env, cudaStream_t s) {
     if (!(dbg.p && dbg_dumped < dbg_max_dumps)) return;
     cudaStreamSynchronize(s);
@@ -380,58 +390,101 @@ struct EnvSolver {
     ++dbg_dumped;
   }
 
-  // Solves (H + diag(dadd)) x = z_in where z already holds the right-hand side.
+  // Block-diagonal system of independent groups (window BA): group g owns rows grp[g]..grp[g+1]-1; every group
+  // must fit the register window (<= 31 rows).  Call after prepare().
+  int prepare_batch(const Envelope& env, const std::vector<int>& grp, cudaStream_t s) {
+    n_groups = (int)grp.size() - 1;
+    grp_ptr = grp;
+    std::vector<int> fr((size_t)env.n);
+    for (int g = 0; g < n_groups; ++g) {
+      if (grp[g + 1] - grp[g] > 31)
+        return fail(LVBA_ERR_UNSUPPORTED, "window %d has %d poses; the batched solve handles <= 31 per window", g, grp[g + 1] - grp[g]);
+      for (int r = grp[g]; r < grp[g + 1]; ++r) {
+        if (env.first[r] < grp[g]) return fail(LVBA_ERR_INVALID_ARG, "row %d couples to a pose outside its window", r);
+        fr[r] = env.first[r] - grp[g];
+      }
+    }
+    LVBA_TRY(first_rel.upload(fr, s));
+    LVBA_TRY(status.alloc((size_t)std::max(n_groups, 4)));
+    LVBA_CUDA(cudaStreamSynchronize(s));
+    batch = true; tw = false; jobs_x = nullptr;
+    return LVBA_OK;
+  }
+
+  int build_jobs(const Envelope& env, double* x, cudaStream_t s) {
+    if (jobs_x == x && d_fjobs.p) return LVBA_OK;
+    const EnvView v = env.view();
+    std::vector<FactorJob> fj;
+    std::vector<BacksolveJob> bj;
+    if (batch) {
+      for (int g = 0; g < n_groups; ++g) {
+        const int r0 = grp_ptr[g], ng = grp_ptr[g + 1] - r0;
+        EnvView vg{ng, first_rel.p + r0, env.d_row_start.p + r0, env.d_last.p + r0, env.nblocks};
+        fj.push_back(FactorJob{vg, L.p, dinv.p + 36 * (size_t)r0, z.p + 6 * (size_t)r0, ng, nullptr, nullptr, status.p + g});
+        bj.push_back(BacksolveJob{vg, L.p, x + 6 * (size_t)r0, ng});
+      }
+    } else if (tw) {
+      EnvView vt = v; vt.n = tw_send;                               // the top instance is a prefix of the matrix
+      const EnvView vb = env_bot.view(), vs = env_sep.view();
+      fj.push_back(FactorJob{vt, L.p, dinv.p, z.p, tw_m, wtop.p, ztopd.p, status.p});
+      fj.push_back(FactorJob{vb, Lbot.p, dinv_bot.p, zbot.p, tw_nbstop, wbot.p, zbotd.p, status.p + 1});
+      fj.push_back(FactorJob{vs, Lsep.p, dinv_sep.p, zsep.p, tw_bs, nullptr, nullptr, status.p + 2});
+      bj.push_back(BacksolveJob{vs, Lsep.p, xsep.p, tw_bs});
+      bj.push_back(BacksolveJob{vt, L.p, x, tw_m});
+      bj.push_back(BacksolveJob{vb, Lbot.p, xbot.p, tw_nbstop});
+    } else {
+      fj.push_back(FactorJob{v, L.p, dinv.p, z.p, env.n, nullptr, nullptr, status.p});
+      bj.push_back(BacksolveJob{v, L.p, x, env.n});
+    }
+    LVBA_TRY(d_fjobs.upload(fj, s));
+    LVBA_TRY(d_bjobs.upload(bj, s));
+    LVBA_CUDA(cudaStreamSynchronize(s));               // local vectors
+    jobs_x = x;
+    return LVBA_OK;
+  }
+
+  // Solves (H + diag(dadd)) x = z_in where z already holds the right-hand side.  status[0] != 0 afterwards flags a
+  // singular pivot (batched mode: status[g] per group).
   int solve(const Envelope& env, const double* H, const double* dadd, double* x, cudaStream_t s, int64_t* launches) {
     const EnvView v = env.view();
     LVBA_CUDA(cudaMemcpyAsync(L.p, H, (size_t)env.nblocks * 36 * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    LVBA_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), s));
+    LVBA_CUDA(cudaMemsetAsync(status.p, 0, status.n * sizeof(int), s));
     const int n6 = 6 * env.n;
     env_add_diag_kernel<<<(n6 + 255) / 256, 256, 0, s>>>(v, dadd, L.p);
     ++*launches;
     const int mc = env.max_col;
-    const bool reg_path = mc <= 30 && env.n >= 3 && !force_generic;
-    if (reg_path && tw) {
+    const bool reg_path = batch || (mc <= 30 && env.n >= 3 && !force_generic);
+    if (reg_path) LVBA_TRY(build_jobs(env, x, s));
+    if (batch) {
+      LVBA_TRY(launch_factor(pid(mc), n_groups, d_fjobs.p, s, launches));
+      launch_apply(env.n, dinv.p, z.p, x, s);
+      launch_backsolve(n_groups, d_bjobs.p, s);
+      *launches += 2;
+    } else if (reg_path && tw) {
       // ---------------- twisted: two half factorisations on two SMs, joined at the separator
       const int n = env.n, m = tw_m, bs = tw_bs;
-      EnvView vt = v; vt.n = tw_send;                               // the top instance is a prefix of the matrix
-      const EnvView vb = env_bot.view(), vs = env_sep.view();
+      const EnvView vb = env_bot.view();
       env_reverse_gather_kernel<<<std::min(tw_nb, 2048), 128, 0, s>>>(v, vb, L.p, Lbot.p, z.p, zbot.p);
-      FactorJobs jobs;
-      jobs.j[0] = FactorJob{vt, L.p, dinv.p, z.p, m, wtop.p, ztopd.p};
-      jobs.j[1] = FactorJob{vb, Lbot.p, dinv_bot.p, zbot.p, tw_nbstop, wbot.p, zbotd.p};
       ++*launches;
-      LVBA_TRY(launch_factor(pid(std::max(mc, env_bot.max_col)), 2, jobs, s, launches));
+      LVBA_TRY(launch_factor(pid(std::max(mc, env_bot.max_col)), 2, d_fjobs.p, s, launches));
       dump_timing(env, s);
       env_twist_combine_kernel<<<1, 1024, 0, s>>>(v, m, bs, L.p, z.p, wtop.p, wbot.p, ztopd.p, zbotd.p, Lsep.p, zsep.p);
-      FactorJobs js;
-      js.j[0] = FactorJob{vs, Lsep.p, dinv_sep.p, zsep.p, bs, nullptr, nullptr};
-      js.j[1] = js.j[0];
       ++*launches;
-      LVBA_TRY(launch_factor(pid(env_sep.max_col), 1, js, s, launches));
+      LVBA_TRY(launch_factor(pid(env_sep.max_col), 1, d_fjobs.p + 2, s, launches));
       launch_apply(bs, dinv_sep.p, zsep.p, xsep.p, s);
-      BacksolveJobs bj;
-      bj.j[0] = BacksolveJob{vs, Lsep.p, xsep.p, bs};
-      bj.j[1] = bj.j[0];
-      launch_backsolve(1, bj, s);
+      launch_backsolve(1, d_bjobs.p, s);
       launch_apply(m, dinv.p, z.p, x, s);
       launch_apply(tw_nbstop, dinv_bot.p, zbot.p, xbot.p, s);
       env_twist_place_sep_kernel<<<(bs * 6 + 127) / 128, 128, 0, s>>>(m, bs, tw_nbstop, xsep.p, x, xbot.p);
-      bj.j[0] = BacksolveJob{vt, L.p, x, m};
-      bj.j[1] = BacksolveJob{vb, Lbot.p, xbot.p, tw_nbstop};
-      launch_backsolve(2, bj, s);
+      launch_backsolve(2, d_bjobs.p + 1, s);
       env_twist_scatter_kernel<<<(tw_nbstop * 6 + 255) / 256, 256, 0, s>>>(n, tw_nbstop, xbot.p, x);
-      *launches += 7;
+      env_status_or_kernel<<<1, 32, 0, s>>>(status.p, 3);
+      *launches += 8;
     } else if (reg_path) {
-      FactorJobs jobs;
-      jobs.j[0] = FactorJob{v, L.p, dinv.p, z.p, env.n, nullptr, nullptr};
-      jobs.j[1] = jobs.j[0];
-      LVBA_TRY(launch_factor(pid(mc), 1, jobs, s, launches));
+      LVBA_TRY(launch_factor(pid(mc), 1, d_fjobs.p, s, launches));
       dump_timing(env, s);
       launch_apply(env.n, dinv.p, z.p, x, s);
-      BacksolveJobs bj;
-      bj.j[0] = BacksolveJob{v, L.p, x, env.n};
-      bj.j[1] = bj.j[0];
-      launch_backsolve(1, bj, s);
+      launch_backsolve(1, d_bjobs.p, s);
       *launches += 2;
     } else {
       env_factor_kernel<<<1, kFactorThreads, factor_smem(), s>>>(v, L.p, dinv.p, z.p, status.p);

@@ -74,7 +74,8 @@ typedef enum lvba_termination {
   LVBA_TERM_PARAMETER_TOL = 2,
   LVBA_TERM_GRADIENT_TOL = 3,
   LVBA_TERM_RADIUS = 4,
-  LVBA_TERM_INVALID_STEPS = 5
+  LVBA_TERM_INVALID_STEPS = 5,
+  LVBA_TERM_SKIPPED = 6         /* window BA: fewer than min_voxels_per_pose * W voxels, poses untouched */
 } lvba_termination;
 
 typedef struct lvba_summary {
@@ -121,6 +122,21 @@ int lvba_lidar_lm(int32_t W, int64_t V, const int64_t* vox_ptr, const int32_t* p
                   const double* clusters, double* poses, const lvba_lidar_opts* opts,
                   lvba_summary* summary);
 
+/* B1 batched — every window of LvbaSystem::runWindowBA (src/lvba_system.cpp:232-302: consecutive windows of
+ * `window_size` poses, one BALM2::damping_iter each, :264) in ONE call: one block-diagonal system, one CTA per
+ * window in the factorisation, per-window u / v / accept-reject / stop test.  Results equal n_windows separate
+ * lvba_lidar_lm calls.
+ *   win_ptr    [n_windows+1] window w owns poses win_ptr[w] .. win_ptr[w+1]-1 of the concatenated `poses`
+ *   pose_idx   indices into the concatenated pose array; every voxel lies inside ONE window
+ *   min_voxels_per_pose   windows with fewer than this many voxels per pose are skipped and their poses left
+ *              untouched (3 in the reference, :262-266); their summary carries LVBA_TERM_SKIPPED
+ *   summaries  [n_windows] per-window LM summary (iterations, accepted, costs, damping, termination); may be NULL
+ *   total      timing / traffic of the whole call; may be NULL
+ * Windows of more than 31 poses return LVBA_ERR_UNSUPPORTED (solve those with lvba_lidar_lm). */
+int lvba_lidar_lm_batch(int32_t n_windows, const int32_t* win_ptr, int64_t V, const int64_t* vox_ptr,
+                        const int32_t* pose_idx, const double* clusters, double* poses,
+                        int32_t min_voxels_per_pose, const lvba_lidar_opts* opts,
+                        lvba_summary* summaries, lvba_summary* total);
 /* Device-resident handle for the same problem: lets a caller (bench, parity tests, a ROS
  * node that re-solves after outlier removal) run single phases with inputs already in HBM. */
 typedef struct lvba_lidar_problem lvba_lidar_problem;

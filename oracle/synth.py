@@ -282,3 +282,36 @@ def make_problem(n_poses, n_vox, n_tracks, seed, lidar=True, visual=True):
 def make_config(name, **kw):
     idx, n, v, t = CONFIGS[name]
     return make_problem(n, v, t, BASE_SEED + idx, **kw)
+
+
+def make_window_problem(window_sizes, vox_per_window, seed, k_hi=8):
+    """Consecutive independent window-BA problems (LvbaSystem::runWindowBA, src/lvba_system.cpp:232-302) laid out
+    the way lvba_lidar_lm_batch takes them: concatenated poses, pose indices into the concatenation, every voxel
+    inside one window.  `vox_per_window` may be an int or a per-window list (0 voxels = a window that gets skipped).
+    Returns dict(win_ptr, vox_ptr, pose_idx, clusters, poses, windows=[per-window single problems])."""
+    sizes = list(window_sizes)
+    if np.isscalar(vox_per_window):
+        vox_per_window = [int(vox_per_window)] * len(sizes)
+    win_ptr = np.zeros(len(sizes) + 1, np.int32)
+    win_ptr[1:] = np.cumsum(sizes)
+    vp_all, pi_all, cl_all, ps_all, windows = [np.zeros(1, np.int64)], [], [], [], []
+    nnz = 0
+    for w, (nw, nv) in enumerate(zip(sizes, vox_per_window)):
+        p = make_problem(max(nw, 2), max(nv, 1), 0, seed=seed + 17 * w, visual=False)
+        poses = p["poses"][:nw]
+        if nv > 0 and nw >= 2:
+            keep = [a for a in range(len(p["vox_ptr"]) - 1) if p["pose_idx"][p["vox_ptr"][a + 1] - 1] < nw][:nv]
+        else:
+            keep = []
+        vp = [0]; pi = []; cl = []
+        for a in keep:
+            lo, hi = p["vox_ptr"][a], p["vox_ptr"][a + 1]
+            pi.append(p["pose_idx"][lo:hi]); cl.append(p["clusters"][lo:hi]); vp.append(vp[-1] + hi - lo)
+        pi = np.concatenate(pi).astype(np.int32) if pi else np.zeros(0, np.int32)
+        cl = np.concatenate(cl) if cl else np.zeros((0, 10))
+        vp = np.asarray(vp, np.int64)
+        windows.append(dict(vox_ptr=vp, pose_idx=pi, clusters=cl, poses=poses.copy()))
+        vp_all.append(vp[1:] + nnz); pi_all.append(pi + win_ptr[w]); cl_all.append(cl); ps_all.append(poses)
+        nnz += int(vp[-1])
+    return dict(win_ptr=win_ptr, vox_ptr=np.concatenate(vp_all), pose_idx=np.concatenate(pi_all).astype(np.int32),
+                clusters=np.concatenate(cl_all), poses=np.concatenate(ps_all), windows=windows)

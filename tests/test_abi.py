@@ -72,3 +72,18 @@ def test_shard_owner_rule(pkg):
         for r in range(P):
             rows = [i for i in range(n) if owners[i] == r]
             assert rows == list(range(r * n // P, (r + 1) * n // P))
+
+
+def test_window_batch_argument_checks_need_no_gpu(pkg):
+    """lvba_lidar_lm_batch validates its window table on the host before touching a device."""
+    p_ = np.zeros((4, 12)); wp = np.array([0, 4], np.int32)
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.lidar_lm_batch(np.array([1, 4], np.int32), np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros((0, 10)), p_)
+    assert e.value.status == -1                                              # win_ptr[0] != 0
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.lidar_lm_batch(np.array([0, 4, 2], np.int32), np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros((0, 10)), p_)
+    assert e.value.status == -1                                              # decreasing
+    if pkg.device_count() == 0:
+        with pytest.raises(pkg.LvbaError) as e:
+            pkg.lidar_lm_batch(wp, np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros((0, 10)), p_)
+        assert e.value.status == -2                                          # no CPU fallback

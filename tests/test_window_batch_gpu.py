@@ -1,0 +1,75 @@
+"""GPU parity tests for the batched window BA (lvba_lidar_lm_batch) — every window of
+LvbaSystem::runWindowBA (reference src/lvba_system.cpp:232-302) in one call.
+
+Bar: each window behaves exactly as its own BALM2::damping_iter (bavoxel.hpp:662-767): same accept/reject
+sequence and iteration count as the numpy oracle run on that window alone, final cost within rel 1e-6,
+poses within 1e-6; windows below the reference's 3-voxels-per-pose rule (:262-266) are left untouched."""
+import numpy as np
+import pytest
+
+from oracle import lidar_oracle as lo
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def windows():
+    # 20-pose windows as in the reference config, a short tail window, one window below the 3*W rule, one empty
+    return synth.make_window_problem([20, 20, 14, 6, 10, 12, 2], [260, 300, 170, 90, 12, 0, 40], seed=23)
+
+
+def test_batch_matches_per_window_oracle(gpu_pkg, windows):
+    p = windows
+    poses, sums, tot = gpu_pkg.lidar_lm_batch(p["win_ptr"], p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"])
+    assert tot["kernel_launches"] > 0
+    for w, win in enumerate(p["windows"]):
+        lo_, hi_ = p["win_ptr"][w], p["win_ptr"][w + 1]
+        W, V = hi_ - lo_, len(win["vox_ptr"]) - 1
+        if V < 3 * W:
+            assert sums[w]["termination"] == 6                                  # LVBA_TERM_SKIPPED
+            assert np.array_equal(poses[lo_:hi_], p["poses"][lo_:hi_])          # untouched
+            continue
+        ref, info = lo.damping_iter(win["vox_ptr"], win["pose_idx"], win["clusters"], win["poses"])
+        assert sums[w]["iterations"] == info["iters"], w
+        assert sums[w]["accepted"] == info["accepted"], w
+        assert abs(sums[w]["cost_first"] - info["r_first"]) <= 1e-8 * info["r_first"]
+        assert abs(sums[w]["cost_last"] - info["r_last"]) <= 1e-6 * info["r_last"]
+        assert np.abs(poses[lo_:hi_] - ref).max() <= 1e-6
+        assert abs(sums[w]["damping_last"] - info["u_last"]) <= 1e-6 * info["u_last"]
+
+
+def test_batch_equals_separate_calls(gpu_pkg, windows):
+    p = windows
+    poses, sums, _ = gpu_pkg.lidar_lm_batch(p["win_ptr"], p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"])
+    for w, win in enumerate(p["windows"]):
+        lo_, hi_ = p["win_ptr"][w], p["win_ptr"][w + 1]
+        if len(win["vox_ptr"]) - 1 < 3 * (hi_ - lo_):
+            continue
+        single, s = gpu_pkg.lidar_lm(win["vox_ptr"], win["pose_idx"], win["clusters"], win["poses"])
+        assert s["iterations"] == sums[w]["iterations"] and s["accepted"] == sums[w]["accepted"]
+        assert np.abs(single - poses[lo_:hi_]).max() <= 1e-9
+
+
+def test_batch_many_windows_and_threshold(gpu_pkg):
+    p = synth.make_window_problem([16] * 40, 120, seed=5)
+    poses, sums, tot = gpu_pkg.lidar_lm_batch(p["win_ptr"], p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"])
+    assert all(s["termination"] != 6 and s["iterations"] >= 1 for s in sums)
+    assert all(s["cost_last"] <= s["cost_first"] for s in sums)
+    # with an impossible threshold every window is skipped and nothing changes
+    poses2, sums2, _ = gpu_pkg.lidar_lm_batch(p["win_ptr"], p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"],
+                                              min_voxels_per_pose=1000)
+    assert all(s["termination"] == 6 for s in sums2)
+    assert np.array_equal(poses2, p["poses"])
+
+
+def test_batch_invalid_arguments(gpu_pkg, windows):
+    p = windows
+    with pytest.raises(gpu_pkg.LvbaError) as e:          # a voxel that spans two windows
+        bad = p["win_ptr"].copy(); bad[1] = 15
+        gpu_pkg.lidar_lm_batch(bad, p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"])
+    assert e.value.status == -1
+    with pytest.raises(gpu_pkg.LvbaError) as e:          # a window wider than the register window
+        q = synth.make_window_problem([40], 300, seed=1)
+        gpu_pkg.lidar_lm_batch(q["win_ptr"], q["vox_ptr"], q["pose_idx"], q["clusters"], q["poses"])
+    assert e.value.status == -4
