@@ -6,6 +6,8 @@
 //
 //   lvba_b200::damping_iter(x_stats, voxhess)        replaces BALM2::damping_iter   include/BALM/bavoxel.hpp:662-767
 //   lvba_b200::solve_visual(...)                     replaces the Ceres block       src/lvba_system.cpp:1571-1656
+//   lvba_b200::WindowBatch                           collects the windows of runWindowBA (src/lvba_system.cpp:232-302) and
+//                                                    solves them in one lvba_lidar_lm_batch call
 //
 // Same names, argument meaning and error behaviour as the reference: void-like use (the reference ignores
 // solver failure), state written back only on success, size mismatches throw std::runtime_error like
@@ -56,6 +58,68 @@ inline int damping_iter(PoseVec& x_stats, VoxHess& voxhess, const lvba_lidar_opt
   }
   return LVBA_OK;
 }
+
+// ---- B1 batched: runWindowBA builds one (x_win, voxhess) pair per window and calls damping_iter on each
+//      (src/lvba_system.cpp:239-264).  WindowBatch::add() packs a window instead of solving it; solve() runs every
+//      packed window in one call and writes the poses back into the x_win vectors it was given (which must outlive
+//      solve()).  Windows below the reference's `plvec_voxels.size() < 3 * x_win.size()` rule (:262-266) are packed too
+//      and come back untouched with LVBA_TERM_SKIPPED, so the caller's bookkeeping (win_skipped) can read the summary.
+template <class PoseVec>
+class WindowBatch {
+ public:
+  template <class VoxHess>
+  void add(PoseVec& x_win, const VoxHess& voxhess) {
+    const int W = voxhess.win_size;
+    if ((int)x_win.size() < W) throw std::runtime_error("lvba_b200::WindowBatch::add: x_win smaller than win_size");
+    const int32_t base = win_ptr_.back();
+    for (const auto* sigp : voxhess.plvec_voxels) {
+      const auto& sig = *sigp;
+      for (int i = 0; i < W; ++i) {
+        if (sig[i].N == 0) continue;
+        pose_idx_.push_back(base + i);
+        const auto& P = sig[i].P; const auto& v = sig[i].v;
+        const double rec[10] = {P(0, 0), P(0, 1), P(0, 2), P(1, 1), P(1, 2), P(2, 2), v(0), v(1), v(2), (double)sig[i].N};
+        clusters_.insert(clusters_.end(), rec, rec + 10);
+      }
+      vox_ptr_.push_back((int64_t)pose_idx_.size());
+    }
+    for (int i = 0; i < W; ++i) {
+      double rec[12];
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) rec[3 * r + c] = x_win[i].R(r, c);
+      for (int r = 0; r < 3; ++r) rec[9 + r] = x_win[i].p(r);
+      poses_.insert(poses_.end(), rec, rec + 12);
+    }
+    win_ptr_.push_back(base + W);
+    targets_.push_back(&x_win);
+  }
+  int size() const { return (int)targets_.size(); }
+  // returns LVBA_OK or a negative lvba_status; on failure no window is modified (reference: silent, state untouched)
+  int solve(int min_voxels_per_pose = 3, const lvba_lidar_opts* opts = nullptr, std::vector<lvba_summary>* summaries = nullptr,
+            lvba_summary* total = nullptr) {
+    if (targets_.empty()) return LVBA_OK;
+    std::vector<lvba_summary> local((size_t)size());
+    const int rc = lvba_lidar_lm_batch(size(), win_ptr_.data(), (int64_t)vox_ptr_.size() - 1, vox_ptr_.data(), pose_idx_.data(),
+                                       clusters_.data(), poses_.data(), min_voxels_per_pose, opts, local.data(), total);
+    if (rc != LVBA_OK) return rc;
+    for (int w = 0; w < size(); ++w) {
+      PoseVec& x = *targets_[w];
+      for (int i = 0; i < win_ptr_[w + 1] - win_ptr_[w]; ++i) {
+        const double* rec = poses_.data() + 12 * (size_t)(win_ptr_[w] + i);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) x[i].R(r, c) = rec[3 * r + c];
+        for (int r = 0; r < 3; ++r) x[i].p(r) = rec[9 + r];
+      }
+    }
+    if (summaries) *summaries = local;
+    return LVBA_OK;
+  }
+
+ private:
+  std::vector<int32_t> win_ptr_{0};
+  std::vector<int64_t> vox_ptr_{0};
+  std::vector<int32_t> pose_idx_;
+  std::vector<double> clusters_, poses_;
+  std::vector<PoseVec*> targets_;
+};
 
 // ---- B2: the flat arrays optimizeCameraPoses already builds (qs, ts, Xs, plane_n, plane_d) plus the
 //      observation list it walks at :1614-1631.  obs_of_point[pi] = list of (cam_id, u, v).

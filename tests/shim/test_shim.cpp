@@ -34,5 +34,21 @@ int main() {
   if (rc == LVBA_ERR_NO_DEVICE) { std::printf("no device: %s\n", lvba_last_error()); return 2; }
   if (rc != LVBA_OK) { std::printf("error %d: %s\n", rc, lvba_last_error()); return 1; }
   std::printf("ok: %d iterations, cost %.3e -> %.3e\n", sum.iterations, sum.cost_first, sum.cost_last);
-  return (sum.cost_last <= sum.cost_first) ? 0 : 1;
+  if (!(sum.cost_last <= sum.cost_first)) return 1;
+  // the same window twice through the batched entry point (runWindowBA): both copies must land on the single-call result
+  std::vector<IMUST> xa(W), xb(W);
+  for (int i = 0; i < W; ++i) { xa[i].R = M3{{1, 0, 0, 0, 1, 0, 0, 0, 1}}; xa[i].p = V3{{0.5 * i, 0.01 * i, 0}}; xb[i] = xa[i]; }
+  lvba_b200::WindowBatch<std::vector<IMUST>> batch;
+  batch.add(xa, vh);
+  batch.add(xb, vh);
+  std::vector<lvba_summary> sums;
+  const int rb = batch.solve(/*min_voxels_per_pose=*/1, nullptr, &sums);
+  if (rb != LVBA_OK) { std::printf("batch error %d: %s\n", rb, lvba_last_error()); return 1; }
+  double worst = 0;
+  for (int i = 0; i < W; ++i) for (int d = 0; d < 3; ++d) {
+    worst = std::fmax(worst, std::fabs(xa[i].p(d) - xs[i].p(d)));
+    worst = std::fmax(worst, std::fabs(xb[i].p(d) - xs[i].p(d)));
+  }
+  std::printf("batch ok: %d windows, %d / %d iterations, max |p - single| = %.2e\n", batch.size(), sums[0].iterations, sums[1].iterations, worst);
+  return (worst < 1e-9 && sums[0].iterations == sum.iterations) ? 0 : 1;
 }
