@@ -22,20 +22,31 @@
 
 namespace lvba {
 
-template <int P>
+// kTile2: a pair thread owns TWO blocks that share their row slot ({a,b1} and {a,b2}): the L operand of slot a is
+// fetched once for both updates (three operand blocks per two updates instead of four), and half as many pair
+// warps contend with the look-ahead warps for the issue slots and the shared-memory pipe.
+// Measured on B200 (tools/lab): two blocks per thread win for the widest window (P = 31: step 5436 -> 4911 cycles,
+// the look-ahead chain gains most: half as many pair warps compete with it and it keeps 96 registers); for P <= 24
+// the 144 accumulator registers cost more than the saved operand fetches.
+constexpr bool la_tile2(int P) { return P > 24; }
+constexpr int la_tile2_threads(int P) { int s = 0; for (int m = 1; m <= P; ++m) s += (m + 1) / 2; return s; }
+template <int P, bool kTile2>
 struct LaCfg {
   static constexpr int kPairs = P * (P + 1) / 2;
-  static constexpr int kPairGroups = (kPairs + 127) / 128;       // warpgroups (4 warps) of pair threads
-  static constexpr int kPairThreads = kPairGroups * 128;
+  static constexpr int kOwners = kTile2 ? la_tile2_threads(P) : kPairs;          // threads that own blocks
+  // the register re-allocation (setmaxnreg) works on warpgroups of 4 warps: P = 31 keeps whole warpgroups
+  static constexpr bool kRealloc = P > 24;
+  static constexpr int kPairThreads = kRealloc ? ((kOwners + 127) / 128) * 128 : ((kOwners + 31) / 32) * 32;
   static constexpr int kLaThreads = 128;                         // one look-ahead warpgroup
   static constexpr int kThreads = kPairThreads + kLaThreads;
   static constexpr int kItemThreads = 96;                        // look-ahead warps 1..3
   static constexpr int kItems = (P - 1) * 6;                     // (row of the next column, block row x)
   static constexpr int kRounds = (kItems + kItemThreads - 1) / kItemThreads;
   static constexpr int S = 38;                                   // doubles per transposed block (16 B aligned, conflict-free over 8 slots)
-  static constexpr bool kRealloc = kThreads > 512;               // P = 31: 640 threads launch at 96 registers
-  static constexpr int kPairRegs = 104, kLaRegs = 64;            // 512*104 + 128*64 == 640*96
-  static constexpr int kDoubles = 6 * P * S + 2 * P * 36 + 2 * 36 + 36 + 2 * 36 + P * 6 + 48;
+  // P = 31: one block per thread: 640 threads launch at 96 registers, 512*104 + 128*64 == 640*96
+  //         two blocks per thread: 384 threads launch at 168, 256*200 + 128*96 <= 384*168
+  static constexpr int kPairRegs = kTile2 ? 200 : 104, kLaRegs = kTile2 ? 96 : 64;
+  static constexpr int kDoubles = 6 * P * S + 2 * P * 36 + 2 * 36 + 36 + 2 * 36 + P * 6 + 48 + 40;
   static constexpr size_t kSmem = sizeof(double) * (size_t)kDoubles + sizeof(long long) * 64 + sizeof(int) * 64 + 32;
 };
 
@@ -105,11 +116,11 @@ LVBA_DEV void sym6_block_inverse(const double (&x)[21], double (&K)[21]) {
 __device__ int g_la_mode = 0;      // solver_lab only: 1 = pair threads skip their update, 2 = look-ahead group skips its math
 #endif
 
-template <int P, bool kTiming>
-__global__ void __launch_bounds__(LaCfg<P>::kThreads, 1)
-env_factor_la_kernel(const FactorJob* __restrict__ jobs, const unsigned short* __restrict__ pair_map,
+template <int P, bool kTiming, bool kTile2>
+__global__ void __launch_bounds__(LaCfg<P, kTile2>::kThreads, 1)
+env_factor_la_kernel(const FactorJob* __restrict__ jobs, const unsigned* __restrict__ pair_map,
                      long long* __restrict__ dbg_all) {
-  using Cfg = LaCfg<P>;
+  using Cfg = LaCfg<P, kTile2>;
   constexpr int S = Cfg::S;
   constexpr int PS = P * S;                       // one parity of sL / sT / sA
   const FactorJob J = jobs[blockIdx.x];
@@ -132,7 +143,8 @@ env_factor_la_kernel(const FactorJob* __restrict__ jobs, const unsigned short* _
   double* sK = sDu + 36;                         // [2][36]   D^-1 of the pivot block (full symmetric, row-major)
   double* sZ = sK + 72;                          // [P][6]
   double* sZin = sZ + P * 6;                     // [8][6]   rhs entries of the rows about to enter (ring by row & 7)
-  long long* sLabRS = reinterpret_cast<long long*>(sZin + 48);   // [64] row_start of row r at r & 63 (ring, filled by cp.async)
+  double* sZero = sZin + 48;                     // [S]      zero operand (a block that must not change this step)
+  long long* sLabRS = reinterpret_cast<long long*>(sZero + 40);   // [64] row_start of row r at r & 63 (ring, filled by cp.async)
   int* sLabF = reinterpret_cast<int*>(sLabRS + 64);              // [64] first column of row r at r & 63
   const int tid = threadIdx.x, lane = tid & 31;
   const int n = e.n;
@@ -151,13 +163,152 @@ env_factor_la_kernel(const FactorJob* __restrict__ jobs, const unsigned short* _
     if (r < P) sZ[o] = v; else sZin[(r & 7) * 6 + q] = v;
   }
   for (int o = tid; o < 6 * PS; o += Cfg::kThreads) sL[o] = 0.0;         // sL, sT, sA (padding included)
+  if (tid < 40) sZero[tid] = 0.0;
   __syncthreads();
 
-  if (!is_la) {
+  if (!is_la && kTile2) {
+    // =================================================== pair threads, two live 6x6 blocks each: {a,b0} and {a,b1}
+    if (Cfg::kRealloc) reg_alloc<Cfg::kPairRegs>();
+    const unsigned pm = pair_map[tid];
+    const bool is_pair = pm != 0xffffffffu;
+    const int a = pm & 0xff, b0 = (pm >> 8) & 0xff, b1r = (pm >> 16) & 0xff;     // a >= b0, b1 ; b1r == 0xff: no second block
+    const bool has1 = b1r != 0xff;
+    const int b1 = has1 ? b1r : b0;
+    double G0[36], G1[36];                                     // rows <-> slot a, columns <-> slot b0 / b1
+    auto publish_T = [&](const double (&G)[36], double* dst) {  // dst[q*6+x] = G[x][q]
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        double2* d2 = reinterpret_cast<double2*>(dst + q * 6);
+        d2[0] = make_double2(G[q], G[6 + q]);
+        d2[1] = make_double2(G[12 + q], G[18 + q]);
+        d2[2] = make_double2(G[24 + q], G[30 + q]);
+      }
+    };
+    auto publish_N = [&](const double (&G)[36], double* dst) {  // dst[q*6+x] = G[q][x]
+      double2* d2 = reinterpret_cast<double2*>(dst);
+#pragma unroll
+      for (int q = 0; q < 18; ++q) d2[q] = make_double2(G[2 * q], G[2 * q + 1]);
+    };
+    auto load_N = [&](double (&G)[36], const double2* src) {    // G = E
+#pragma unroll
+      for (int q = 0; q < 18; ++q) { const double2 v = src[q]; G[2 * q] = v.x; G[2 * q + 1] = v.y; }
+    };
+    auto load_T = [&](double (&G)[36], const double2* src) {    // G = E^T
+#pragma unroll
+      for (int x = 0; x < 6; ++x)
+#pragma unroll
+        for (int y2 = 0; y2 < 3; ++y2) { const double2 v = src[x * 3 + y2]; G[(2 * y2) * 6 + x] = v.x; G[(2 * y2 + 1) * 6 + x] = v.y; }
+    };
+    auto init_block = [&](double (&G)[36], int b, bool on) {
+      if (on && a < n && b >= sLabF[a]) load_N(G, reinterpret_cast<const double2*>(L + (sLabRS[a] + (b - sLabF[a])) * 36));
+      else {
+#pragma unroll
+        for (int q = 0; q < 36; ++q) G[q] = 0.0;
+      }
+      if (!on) return;
+      if (b == 0 && a >= 1) publish_T(G, sT + a * S);                    // column 0 -> sT[0]
+      if (a == 0 && b == 0) publish_N(G, sDg + 36);                      // pivot 0 (scratch: sDg[1])
+      if (P > 1 && b == 1 % P && a >= 2) publish_T(G, sA + a * S);       // column 1 -> sA[0]
+      if (a == 1 % P && b == 1 % P) publish_N(G, sDg);                   // block (1,1) -> sDg[0]
+    };
+    init_block(G0, b0, is_pair);
+    init_block(G1, b1, is_pair && has1);
+    __syncthreads();     // (A) columns 0, 1 published
+    __syncthreads();     // (B) look-ahead group: K_0, L_{.,0}, entering row P
+    const double2* lp0 = reinterpret_cast<const double2*>(sL + a * S);
+    const double2* tq0 = reinterpret_cast<const double2*>(sT + b0 * S);
+    const double2* tq1 = reinterpret_cast<const double2*>(sT + b1 * S);
+    const double2* zero2 = reinterpret_cast<const double2*>(sZero);
+    int da = a, db0 = b0, db1 = b1;                            // (slot - c) mod P ; c = k mod P
+    const int prole = (tid < 32) ? 0 : (tid >= Cfg::kPairThreads - 32) ? 1 : -1;
+    // after its update (if any) a block either takes the entering block, or hands column k+2 over, or rests
+    auto settle = [&](double (&G)[36], int b, int db, int cur) {
+      const int lo = da < db ? da : db, hi = da < db ? db : da;
+      if (lo == 0) {
+        const int eidx = (hi == 0) ? P - 1 : hi - 1;           // block (k+P, k+hi) ; hi == 0: the diagonal (k+P,k+P)
+        const double2* src = reinterpret_cast<const double2*>(sEnter + (cur * P + eidx) * 36);
+        if (da == 0) load_N(G, src); else load_T(G, src);      // slot a / slot b is the entering row
+      }
+      if (lo != 1 && P > 2 && (da == 2 || db == 2)) {          // column k+2 goes to the look-ahead group of the next step
+        double* nA = sA + (cur ^ 1) * PS;
+        if (da == 2 && db == 2) publish_N(G, sDg + (cur ^ 1) * 36);
+        else if (db == 2) publish_T(G, nA + a * S);            // slot a is the row
+        else publish_N(G, nA + b * S);                         // slot b is the row: G = A^T
+      }
+    };
+    for (int k = 0; k < n_stop; ++k) {
+      const int cur = k & 1;
+      if (kTiming && prole >= 0) LVBA_STAMP(prole, 0);
+      if (is_pair) {
+        if (da >= 2
+#ifdef LVBA_LAB
+            && lab_mode != 1
+#endif
+        ) {
+          // both blocks in one sweep over L_a; a block that must not change (dead, resting or absent) multiplies by zero
+          const double2* lp = lp0 + cur * (PS / 2);
+          const double2* t0p = (db0 >= 2) ? tq0 + cur * (PS / 2) : zero2;
+          const double2* t1p = (has1 && db1 >= 2) ? tq1 + cur * (PS / 2) : zero2;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const double2 u0 = t0p[3 * q], u1 = t0p[3 * q + 1], u2 = t0p[3 * q + 2];
+            const double2 w0 = t1p[3 * q], w1 = t1p[3 * q + 1], w2 = t1p[3 * q + 2];
+#pragma unroll
+            for (int xx = 0; xx < 3; ++xx) {
+              const double2 l = lp[3 * q + xx];
+              double* c0 = G0 + (2 * xx) * 6;
+              double* c1 = G0 + (2 * xx + 1) * 6;
+              c0[0] -= l.x * u0.x; c0[1] -= l.x * u0.y; c0[2] -= l.x * u1.x; c0[3] -= l.x * u1.y; c0[4] -= l.x * u2.x; c0[5] -= l.x * u2.y;
+              c1[0] -= l.y * u0.x; c1[1] -= l.y * u0.y; c1[2] -= l.y * u1.x; c1[3] -= l.y * u1.y; c1[4] -= l.y * u2.x; c1[5] -= l.y * u2.y;
+              double* e0 = G1 + (2 * xx) * 6;
+              double* e1 = G1 + (2 * xx + 1) * 6;
+              e0[0] -= l.x * w0.x; e0[1] -= l.x * w0.y; e0[2] -= l.x * w1.x; e0[3] -= l.x * w1.y; e0[4] -= l.x * w2.x; e0[5] -= l.x * w2.y;
+              e1[0] -= l.y * w0.x; e1[1] -= l.y * w0.y; e1[2] -= l.y * w1.x; e1[3] -= l.y * w1.y; e1[4] -= l.y * w2.x; e1[5] -= l.y * w2.y;
+            }
+          }
+        }
+        if (kTiming && prole >= 0) LVBA_STAMP(prole, 1);
+        settle(G0, b0, db0, cur);
+        if (has1) settle(G1, b1, db1, cur);
+      }
+      if (kTiming && prole >= 0) LVBA_STAMP(prole, 2);
+      __syncthreads();
+      if (kTiming && prole >= 0) LVBA_STAMP(prole, 3);
+      da = (da == 0) ? P - 1 : da - 1;
+      db0 = (db0 == 0) ? P - 1 : db0 - 1;
+      db1 = (db1 == 0) ? P - 1 : db1 - 1;
+    }
+    // partial factorisation: hand the Schur-updated trailing window (rows/cols n_stop..n-1) to the separator solve
+    if (n_stop < n && J.wdump && is_pair) {
+      const int bs = n - n_stop, fin = n_stop & 1;
+      auto dump = [&](const double (&G)[36], int b, int db) {
+        const int lo = da < db ? da : db, hi = da < db ? db : da;
+        if (hi >= bs) return;
+        double* dst = J.wdump + ((long long)hi * bs + lo) * 36;      // block (n_stop+hi, n_stop+lo), rows on the hi row
+        if (lo == 0 && hi == 0) {
+          for (int q = 0; q < 36; ++q) { const int i = q / 6, j = q % 6; dst[q] = (i >= j) ? sDu[i * 6 + j] : sDu[j * 6 + i]; }
+        } else if (lo == 0) {
+          const int row_slot = (da == 0) ? b : a;                    // column n_stop was the look-ahead group's
+          const double* t = sT + fin * PS + row_slot * S;
+          for (int q = 0; q < 36; ++q) { const int x = q / 6, y = q % 6; dst[q] = t[y * 6 + x]; }
+        } else if (da >= db) {
+#pragma unroll
+          for (int q = 0; q < 36; ++q) dst[q] = G[q];
+        } else {
+#pragma unroll
+          for (int x = 0; x < 6; ++x)
+#pragma unroll
+            for (int y = 0; y < 6; ++y) dst[x * 6 + y] = G[y * 6 + x];
+        }
+      };
+      dump(G0, b0, db0);
+      if (has1) dump(G1, b1, db1);
+    }
+  } else if (!is_la) {
     // =================================================== pair threads: one live 6x6 block in registers
     if (Cfg::kRealloc) reg_alloc<Cfg::kPairRegs>();
-    const unsigned short pm = pair_map[tid];
-    const bool is_pair = pm != 0xffff;
+    const unsigned pm = pair_map[tid];
+    const bool is_pair = pm != 0xffffffffu;
     const int a = pm & 0xff, b = (pm >> 8) & 0xff;             // a >= b
     double G[36];                                              // rows <-> slot a, columns <-> slot b
     auto publish_T = [&](double* dst) {                        // dst[q*6+x] = G[x][q]

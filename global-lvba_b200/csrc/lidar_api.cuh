@@ -59,6 +59,46 @@ __global__ void lidar_select_poses_kernel(int W, const int* __restrict__ pose_gr
   if (i < 12 * W && accept[pose_grp[i / 12]]) poses[i] = trial[i];
 }
 
+// sharded problems: the rank's slots are scattered through the caller's array; the whole array goes up in ONE copy
+// and the kernel picks the owned slots (src[i] = global slot of local slot i)
+__global__ void lidar_aos_to_soa_gather_kernel(long long nnz, long long nnz_pad, const double* __restrict__ aos,
+                                               const int* __restrict__ src, double2* __restrict__ soa) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  const double2* r = reinterpret_cast<const double2*>(aos + 10 * (long long)src[i]);
+#pragma unroll
+  for (int q = 0; q < 5; ++q) soa[q * nnz_pad + i] = r[q];
+}
+
+// Pair table of the Hessian build (one word per pose pair of every voxel: li | lj << 8 | lv << 16), generated on the
+// device from the voxel CSR: thread = local slot x of the batch, it writes the pairs (x, y), y > x, of its voxel in the
+// order the build kernel walks them.  (5.2 M words for config C: 6 ms of host loops + a 21 MB upload otherwise.)
+__global__ void __launch_bounds__(kSlots)
+lidar_pairs_kernel(int n_batches, const int* __restrict__ vox_ptr, const int* __restrict__ batch_vox,
+                   const long long* __restrict__ batch_pair, unsigned* __restrict__ pairs) {
+  __shared__ long long off[kMaxVoxPerBatch + 1];
+  __shared__ int vlo[kMaxVoxPerBatch + 1];
+  const int b = blockIdx.x;
+  const int v0 = batch_vox[b], v1 = batch_vox[b + 1], sbase = vox_ptr[v0];
+  if (threadIdx.x == 0) {
+    long long o = batch_pair[b];
+    for (int i = 0; i < v1 - v0; ++i) {
+      const int lo = vox_ptr[v0 + i] - sbase, K = vox_ptr[v0 + i + 1] - vox_ptr[v0 + i];
+      off[i] = o; vlo[i] = lo;
+      o += (long long)K * (K - 1) / 2;
+    }
+    vlo[v1 - v0] = vox_ptr[v1] - sbase;
+  }
+  __syncthreads();
+  const int x = threadIdx.x;
+  if (x >= vlo[v1 - v0]) return;
+  int lv = 0;
+  while (vlo[lv + 1] <= x) ++lv;
+  const int lo = vlo[lv], hi = vlo[lv + 1], K = hi - lo, j = x - lo;
+  unsigned* dst = pairs + off[lv] + (long long)j * (K - 1) - (long long)j * (j - 1) / 2;
+  for (int y = x + 1; y < hi; ++y) *dst++ = (unsigned)x | ((unsigned)y << 8) | ((unsigned)lv << 16);
+}
+
 }  // namespace lvba
 
 struct lvba_lidar_problem {
@@ -240,19 +280,6 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
     batch_pair[b + 1] = np;
   }
   P->n_pairs = np;
-  std::vector<unsigned> pairs((size_t)np);
-  {
-    size_t w = 0;
-    for (int b = 0; b < P->n_batches; ++b) {
-      const int sbase = l_vox_ptr[batch_vox[b]];
-      for (int i = batch_vox[b]; i < batch_vox[b + 1]; ++i) {
-        const unsigned lv = (unsigned)(i - batch_vox[b]);
-        const int lo = l_vox_ptr[i] - sbase, hi = l_vox_ptr[i + 1] - sbase;
-        for (int x = lo; x < hi; ++x)
-          for (int y = x + 1; y < hi; ++y) pairs[w++] = (unsigned)x | ((unsigned)y << 8) | (lv << 16);
-      }
-    }
-  }
 
   lap("batches+pair table");
   // ---- upload.  Clusters: the caller's AoS records go up as they are (per contiguous run of owned
@@ -263,31 +290,47 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   std::vector<int> l_pidx((size_t)nnz);
   {
     DevBuf<double> aos;
-    LVBA_TRY(aos.alloc((size_t)std::max<long long>(nnz, 1) * 10));
-    long long w = 0;
-    int64_t i = 0;
-    while (i < Vl) {   // coalesce runs of consecutive global voxels into one memcpy
-      int64_t j = i;
-      while (j + 1 < Vl && mine[j + 1] == mine[j] + 1) ++j;
-      const int64_t g0 = vox_ptr[mine[i]], g1 = vox_ptr[mine[j] + 1];
-      LVBA_CUDA(cudaMemcpyAsync(aos.p + 10 * w, clusters + 10 * g0, (size_t)(g1 - g0) * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
-      std::copy(pose_idx + g0, pose_idx + g1, l_pidx.begin() + w);
-      P->h2d += (g1 - g0) * 80;
-      w += g1 - g0;
-      i = j + 1;
+    const bool contiguous = Vl == V && n_groups == 0;            // single rank, caller's order: the records go up as they are
+    if (contiguous) {
+      LVBA_TRY(aos.alloc((size_t)std::max<long long>(nnz, 1) * 10));
+      if (nnz > 0) {
+        LVBA_CUDA(cudaMemcpyAsync(aos.p, clusters, (size_t)nnz * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
+        std::copy(pose_idx, pose_idx + nnz, l_pidx.begin());
+        P->h2d += nnz * 80;
+        lidar_aos_to_soa_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(nnz, nnz_pad, aos.p, P->cl.p);
+        ++P->launches;
+      }
+      LVBA_CUDA(cudaStreamSynchronize(s));   // aos is freed on scope exit
+    } else {
+      // a shard (or a window-sorted batch) owns scattered voxels: ONE copy of the caller's array + a device-side gather
+      // (per-run copies cost ~2.5 us each: 100k runs = 250 ms on a 2-rank split of config C)
+      const long long nnz_all = vox_ptr[V];
+      LVBA_TRY(aos.alloc((size_t)std::max<long long>(nnz_all, 1) * 10));
+      std::vector<int> src((size_t)nnz);
+      long long w = 0;
+      for (int64_t i = 0; i < Vl; ++i)
+        for (int64_t q = vox_ptr[mine[i]]; q < vox_ptr[mine[i] + 1]; ++q, ++w) { src[w] = (int)q; l_pidx[w] = pose_idx[q]; }
+      DevBuf<int> d_src;
+      if (nnz > 0) {
+        LVBA_CUDA(cudaMemcpyAsync(aos.p, clusters, (size_t)nnz_all * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
+        LVBA_TRY(d_src.upload(src, s, &P->h2d));
+        P->h2d += nnz_all * 80;
+        lidar_aos_to_soa_gather_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(nnz, nnz_pad, aos.p, d_src.p, P->cl.p);
+        ++P->launches;
+      }
+      LVBA_CUDA(cudaStreamSynchronize(s));   // aos, src, d_src are freed on scope exit
     }
-    if (nnz > 0) {
-      lidar_aos_to_soa_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(nnz, nnz_pad, aos.p, P->cl.p);
-      ++P->launches;
-    }
-    LVBA_CUDA(cudaStreamSynchronize(s));   // aos is freed on scope exit
   }
   if (tlog) { cudaStreamSynchronize(s); } lap("cluster upload+SoA");
   LVBA_TRY(P->pidx.upload(l_pidx, s, &P->h2d));
   LVBA_TRY(P->vox_ptr.upload(l_vox_ptr, s, &P->h2d));
   LVBA_TRY(P->batch_vox.upload(batch_vox, s, &P->h2d));
   LVBA_TRY(P->batch_pair.upload(batch_pair, s, &P->h2d));
-  if (np > 0) LVBA_TRY(P->pairs.upload(pairs, s, &P->h2d));
+  if (np > 0) {                                                // pair table: generated on the device from the CSR just uploaded
+    LVBA_TRY(P->pairs.alloc((size_t)np));
+    lidar_pairs_kernel<<<P->n_batches, kSlots, 0, s>>>(P->n_batches, P->vox_ptr.p, P->batch_vox.p, P->batch_pair.p, P->pairs.p);
+    ++P->launches;
+  }
   LVBA_TRY(P->poses.upload(poses, (size_t)W * 12, s, &P->h2d));
   LVBA_TRY(P->poses0.upload(poses, (size_t)W * 12, s));
   LVBA_TRY(P->trial.alloc((size_t)W * 12));

@@ -248,6 +248,32 @@ inline std::vector<unsigned short> build_pair_map(int P, int n_threads) {
   return map;
 }
 
+// Thread -> blocks map of the register-window kernel, one 32-bit word per pair thread: a | b0 << 8 | b1 << 16
+// (b1 = 0xff: no second block; 0xffffffff: idle thread).  kTile2 = false: one block {a,b0} per thread, grouped as
+// build_pair_map does.  kTile2 = true: the blocks {a,b}, b <= a, of one row slot are paired (b = 2m, 2m+1) and the
+// threads are ordered by 8x8 super block so that the lanes of a warp share few distinct operand slots.
+inline std::vector<unsigned> build_pair_map32(int P, bool tile2, int n_threads) {
+  std::vector<unsigned> map((size_t)n_threads, 0xffffffffu);
+  if (!tile2) {
+    const std::vector<unsigned short> m16 = build_pair_map(P, n_threads);
+    for (int t = 0; t < n_threads; ++t)
+      if (m16[t] != 0xffff) map[t] = (unsigned)(m16[t] & 0xff) | ((unsigned)(m16[t] >> 8) << 8) | (0xffu << 16);
+    return map;
+  }
+  struct Tri { int a, b0, b1; };
+  std::vector<Tri> tris;
+  for (int a = 0; a < P; ++a)
+    for (int b = 0; b <= a; b += 2) tris.push_back(Tri{a, b, (b + 1 <= a) ? b + 1 : 0xff});
+  std::stable_sort(tris.begin(), tris.end(), [](const Tri& x, const Tri& y) {
+    const int kx[4] = {x.a / 8, x.b0 / 8, x.a, x.b0}, ky[4] = {y.a / 8, y.b0 / 8, y.a, y.b0};
+    for (int i = 0; i < 4; ++i) if (kx[i] != ky[i]) return kx[i] < ky[i];
+    return false;
+  });
+  for (size_t t = 0; t < tris.size() && (int)t < n_threads; ++t)
+    map[t] = (unsigned)tris[t].a | ((unsigned)tris[t].b0 << 8) | ((unsigned)tris[t].b1 << 16);
+  return map;
+}
+
 // ---------------------------------------------------------------- LDL^T solve driver
 struct EnvSolver {
   DevBuf<double> L, dinv, z;
@@ -261,7 +287,7 @@ struct EnvSolver {
   int n_groups = 0;
   std::vector<int> grp_ptr;     // [n_groups+1] row offsets
   DevBuf<int> first_rel;        // first[r] relative to the first row of r's group
-  DevBuf<unsigned short> pair_map[4];   // thread -> slot pair of the register-window kernel, per P in {8,16,24,31}
+  DevBuf<unsigned> pair_map[4];         // thread -> blocks of the register-window kernel, per P in {8,16,24,31}
   bool have_map[4] = {false, false, false, false};
   DevBuf<long long> dbg;        // LVBA_FACTOR_TIMING=1: per-step phase clocks of the register-window kernel
   int dbg_dumped = 0, dbg_max_dumps = 2;
@@ -295,14 +321,10 @@ struct EnvSolver {
     }
     if (!configured) {
       LVBA_CUDA(cudaFuncSetAttribute(env_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)factor_smem()));
-      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<8>::kSmem));
-      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<8>::kSmem));
-      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<16>::kSmem));
-      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<16>::kSmem));
-      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<24>::kSmem));
-      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<24, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<24>::kSmem));
-      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<31>::kSmem));
-      LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<31, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<31>::kSmem));
+#define LVBA_SET_SMEM(PP, TT) LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<PP, TT, la_tile2(PP)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<PP, la_tile2(PP)>::kSmem))
+      LVBA_SET_SMEM(8, false); LVBA_SET_SMEM(8, true); LVBA_SET_SMEM(16, false); LVBA_SET_SMEM(16, true);
+      LVBA_SET_SMEM(24, false); LVBA_SET_SMEM(24, true); LVBA_SET_SMEM(31, false); LVBA_SET_SMEM(31, true);
+#undef LVBA_SET_SMEM
       LVBA_CUDA(cudaFuncSetAttribute(env_backsolve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBsSmem));
       configured = true;
     }
@@ -342,9 +364,12 @@ struct EnvSolver {
   int ensure_map(int id, cudaStream_t s) {
     if (have_map[id]) return LVBA_OK;
     const int P = pval(id);
-    const int nthr = id == 0 ? LaCfg<8>::kPairThreads : id == 1 ? LaCfg<16>::kPairThreads : id == 2 ? LaCfg<24>::kPairThreads : LaCfg<31>::kPairThreads;
-    std::vector<unsigned short> m = build_pair_map(P, nthr);
-    size_t cnt = 0; for (auto v2 : m) cnt += v2 != 0xffff;
+    const int nthr = id == 0 ? LaCfg<8, la_tile2(8)>::kPairThreads : id == 1 ? LaCfg<16, la_tile2(16)>::kPairThreads
+                   : id == 2 ? LaCfg<24, la_tile2(24)>::kPairThreads : LaCfg<31, la_tile2(31)>::kPairThreads;
+    const bool tile2 = la_tile2(P);
+    std::vector<unsigned> m = build_pair_map32(P, tile2, nthr);
+    size_t cnt = 0;
+    for (auto v2 : m) if (v2 != 0xffffffffu) cnt += ((v2 >> 16) & 0xff) != 0xff ? 2 : 1;
     if ((int)cnt != P * (P + 1) / 2) return fail(LVBA_ERR_UNSUPPORTED, "pair map for P=%d covers %zu of %d pairs", P, cnt, P * (P + 1) / 2);
     LVBA_TRY(pair_map[id].upload(m, s));
     LVBA_CUDA(cudaStreamSynchronize(s));               // `m` is a local vector
@@ -353,13 +378,10 @@ struct EnvSolver {
   }
   int launch_factor(int id, int grid, const FactorJob* jobs, cudaStream_t s, int64_t* launches) {
     LVBA_TRY(ensure_map(id, s));
-    const unsigned short* pm = pair_map[id].p;
-#define LVBA_LAUNCH_LA(PP, TT) env_factor_la_kernel<PP, TT><<<grid, LaCfg<PP>::kThreads, LaCfg<PP>::kSmem, s>>>(jobs, pm, dbg.p)
-    if (dbg.p) {
-      if (id == 0) LVBA_LAUNCH_LA(8, true); else if (id == 1) LVBA_LAUNCH_LA(16, true); else if (id == 2) LVBA_LAUNCH_LA(24, true); else LVBA_LAUNCH_LA(31, true);
-    } else {
-      if (id == 0) LVBA_LAUNCH_LA(8, false); else if (id == 1) LVBA_LAUNCH_LA(16, false); else if (id == 2) LVBA_LAUNCH_LA(24, false); else LVBA_LAUNCH_LA(31, false);
-    }
+    const unsigned* pm = pair_map[id].p;
+#define LVBA_LAUNCH_LA(PP, TT) env_factor_la_kernel<PP, TT, la_tile2(PP)><<<grid, LaCfg<PP, la_tile2(PP)>::kThreads, LaCfg<PP, la_tile2(PP)>::kSmem, s>>>(jobs, pm, dbg.p)
+    if (dbg.p) { if (id == 0) LVBA_LAUNCH_LA(8, true); else if (id == 1) LVBA_LAUNCH_LA(16, true); else if (id == 2) LVBA_LAUNCH_LA(24, true); else LVBA_LAUNCH_LA(31, true); }
+    else { if (id == 0) LVBA_LAUNCH_LA(8, false); else if (id == 1) LVBA_LAUNCH_LA(16, false); else if (id == 2) LVBA_LAUNCH_LA(24, false); else LVBA_LAUNCH_LA(31, false); }
 #undef LVBA_LAUNCH_LA
     ++*launches;
     return LVBA_OK;

@@ -49,8 +49,8 @@ static int run_case(int n, int b, int ragged, unsigned seed, bool timing = false
   for (int tw = 1; tw >= 0; --tw) {
     setenv("LVBA_NO_TWIST", tw ? "0" : "1", 1);
     // cfg: factor kernel x backsolve kernel (+ lab modes that disable one side of the factor kernel: timing only)
-    struct Cfg { int mode; };
-    const Cfg cfgs[] = {{0}, {1}, {2}};
+    struct Cfg { int mode; int tile2; };
+    const Cfg cfgs[] = {{0, 1}, {1, 1}, {2, 1}};
     for (int cfg = 0; cfg < (int)(sizeof cfgs / sizeof cfgs[0]); ++cfg) {
       if (cfgs[cfg].mode != 0 && !(timing && tw == 1)) continue;
       if (g_prof && !(cfg == 0 && tw == 1)) continue;     // profiling run: twisted, once
@@ -96,8 +96,8 @@ static int run_case(int n, int b, int ragged, unsigned seed, bool timing = false
       double sx = 0, dx = 0, sl = 0, dl = 0, sz = 0, dz = 0;
       if (x0.empty() || cfg == 0) { if (tw == 1 && cfg == 0) { x0 = x; } L0 = Lh; z0 = zh; }
       dx = maxdiff(x0, x, &sx); dl = maxdiff(L0, Lh, &sl); dz = maxdiff(z0, zh, &sz);
-      printf("  twisted=%d mode=%d : %.3f ms  status=%d  |resid|=%.2e  dx=%.2e (of %.1e)  dL=%.2e (of %.1e)  dz=%.2e\n",
-             tw, cfgs[cfg].mode, best, st, rn, dx, sx, dl, sl, dz);
+      printf("  twisted=%d tile2=%d mode=%d : %.3f ms  status=%d  |resid|=%.2e  dx=%.2e (of %.1e)  dL=%.2e (of %.1e)  dz=%.2e\n",
+             tw, cfgs[cfg].tile2, cfgs[cfg].mode, best, st, rn, dx, sx, dl, sl, dz);
       fflush(stdout);
       if (cfgs[cfg].mode == 0 && (!(rn < 1e-9) || st != 0)) rc_all = 3;
       cudaEventDestroy(e0); cudaEventDestroy(e1);
