@@ -157,16 +157,32 @@ inline int lidar_validate(int32_t W, int64_t V, const int64_t* vox_ptr, const in
   if (W <= 0 || V < 0) return fail(LVBA_ERR_INVALID_ARG, "W=%d V=%lld must be positive", W, (long long)V);
   if (!vox_ptr || !poses || (V > 0 && (!pose_idx || !clusters))) return fail(LVBA_ERR_INVALID_ARG, "null input pointer");
   if (vox_ptr[0] != 0) return fail(LVBA_ERR_INVALID_ARG, "vox_ptr[0] must be 0");
-  for (int64_t a = 0; a < V; ++a) {
-    const int64_t lo = vox_ptr[a], hi = vox_ptr[a + 1];
-    if (hi <= lo) return fail(LVBA_ERR_INVALID_ARG, "voxel %lld has no slots (vox_ptr not increasing)", (long long)a);
-    if (hi - lo > kSlots)
-      return fail(LVBA_ERR_UNSUPPORTED, "voxel %lld is observed from %lld poses; this build handles <= %d per voxel",
-                  (long long)a, (long long)(hi - lo), kSlots);
-    for (int64_t s = lo; s < hi; ++s) {
-      const int p = pose_idx[s];
-      if (p < 0 || p >= W) return fail(LVBA_ERR_INVALID_ARG, "pose_idx[%lld]=%d out of [0,%d)", (long long)s, p, W);
-      if (s > lo && pose_idx[s - 1] >= p) return fail(LVBA_ERR_INVALID_ARG, "pose_idx must be strictly ascending inside voxel %lld", (long long)a);
+  // the CSR is checked in parallel chunks; the first offending voxel (lowest index) is reported
+  int64_t bad_at[kMaxSetupThreads]; int bad_kind[kMaxSetupThreads]; int64_t bad_aux[kMaxSetupThreads];
+  for (int w = 0; w < kMaxSetupThreads; ++w) { bad_at[w] = -1; bad_kind[w] = 0; bad_aux[w] = 0; }
+  parallel_chunks(V, 1 << 14, [&](int64_t a0, int64_t a1, int w) {
+    for (int64_t a = a0; a < a1; ++a) {
+      const int64_t lo = vox_ptr[a], hi = vox_ptr[a + 1];
+      int kind = 0; int64_t aux = 0;
+      if (hi <= lo) kind = 1;
+      else if (hi - lo > kSlots) { kind = 2; aux = hi - lo; }
+      else
+        for (int64_t s = lo; s < hi; ++s) {
+          const int p = pose_idx[s];
+          if (p < 0 || p >= W) { kind = 3; aux = s; break; }
+          if (s > lo && pose_idx[s - 1] >= p) { kind = 4; break; }
+        }
+      if (kind) { bad_at[w] = a; bad_kind[w] = kind; bad_aux[w] = aux; return; }
+    }
+  });
+  for (int w = 0; w < kMaxSetupThreads; ++w) {
+    if (bad_at[w] < 0) continue;
+    const long long a = (long long)bad_at[w];
+    switch (bad_kind[w]) {
+      case 1: return fail(LVBA_ERR_INVALID_ARG, "voxel %lld has no slots (vox_ptr not increasing)", a);
+      case 2: return fail(LVBA_ERR_UNSUPPORTED, "voxel %lld is observed from %lld poses; this build handles <= %d per voxel", a, (long long)bad_aux[w], kSlots);
+      case 3: return fail(LVBA_ERR_INVALID_ARG, "pose_idx[%lld]=%d out of [0,%d)", (long long)bad_aux[w], pose_idx[bad_aux[w]], W);
+      default: return fail(LVBA_ERR_INVALID_ARG, "pose_idx must be strictly ascending inside voxel %lld", a);
     }
   }
   if (vox_ptr[V] >= (1LL << 31)) return fail(LVBA_ERR_UNSUPPORTED, "more than 2^31 slots");

@@ -73,10 +73,21 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   if (!q || !t || !intr || !obs_ptr || (T > 0 && (!X || !plane_nd || !obs_cam || !obs_uv))) return fail(LVBA_ERR_INVALID_ARG, "null input pointer");
   if (!(sigma_px > 0)) return fail(LVBA_ERR_INVALID_ARG, "sigma_px must be positive");
   if (obs_ptr[0] != 0) return fail(LVBA_ERR_INVALID_ARG, "obs_ptr[0] must be 0");
-  for (int64_t i = 0; i < T; ++i) {
-    if (obs_ptr[i + 1] < obs_ptr[i]) return fail(LVBA_ERR_INVALID_ARG, "obs_ptr not monotone at %lld", (long long)i);
-    for (int64_t s = obs_ptr[i]; s < obs_ptr[i + 1]; ++s)
-      if (obs_cam[s] < 0 || obs_cam[s] >= M) return fail(LVBA_ERR_INVALID_ARG, "obs_cam[%lld]=%d out of [0,%d)", (long long)s, obs_cam[s], M);
+  {
+    int64_t bad_i[kMaxSetupThreads], bad_s[kMaxSetupThreads];
+    for (int w = 0; w < kMaxSetupThreads; ++w) { bad_i[w] = -1; bad_s[w] = -1; }
+    parallel_chunks(T, 1 << 14, [&](int64_t i0, int64_t i1, int w) {
+      for (int64_t i = i0; i < i1; ++i) {
+        if (obs_ptr[i + 1] < obs_ptr[i]) { bad_i[w] = i; return; }
+        for (int64_t s = obs_ptr[i]; s < obs_ptr[i + 1]; ++s)
+          if (obs_cam[s] < 0 || obs_cam[s] >= M) { bad_i[w] = i; bad_s[w] = s; return; }
+      }
+    });
+    for (int w = 0; w < kMaxSetupThreads; ++w) {
+      if (bad_i[w] < 0) continue;
+      if (bad_s[w] < 0) return fail(LVBA_ERR_INVALID_ARG, "obs_ptr not monotone at %lld", (long long)bad_i[w]);
+      return fail(LVBA_ERR_INVALID_ARG, "obs_cam[%lld]=%d out of [0,%d)", (long long)bad_s[w], obs_cam[bad_s[w]], M);
+    }
   }
   LVBA_TRY(select_device(device));
   const double t_begin = wall_ms();
@@ -148,15 +159,17 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   std::vector<int> l_cam((size_t)nnz), l_row((size_t)nnz);
   std::vector<float2> l_uv((size_t)nnz);
   std::vector<double> l_plane((size_t)Tv * 4);
-  for (int64_t k = 0; k < Tv; ++k) {
-    const int64_t i = mine[k];
-    for (int j = 0; j < 4; ++j) l_plane[4 * k + j] = plane_nd[4 * i + j];
-    long long w = trk_ptr[k];
-    for (int64_t q_ = obs_ptr[i]; q_ < obs_ptr[i + 1]; ++q_, ++w) {
-      l_cam[w] = obs_cam[q_]; l_row[w] = row_of_cam[obs_cam[q_]];
-      l_uv[w] = make_float2(obs_uv[2 * q_], obs_uv[2 * q_ + 1]);
+  parallel_chunks(Tv, 1 << 13, [&](int64_t k0, int64_t k1, int) {
+    for (int64_t k = k0; k < k1; ++k) {
+      const int64_t i = mine[k];
+      for (int j = 0; j < 4; ++j) l_plane[4 * k + j] = plane_nd[4 * i + j];
+      long long w = trk_ptr[k];
+      for (int64_t q_ = obs_ptr[i]; q_ < obs_ptr[i + 1]; ++q_, ++w) {
+        l_cam[w] = obs_cam[q_]; l_row[w] = row_of_cam[obs_cam[q_]];
+        l_uv[w] = make_float2(obs_uv[2 * q_], obs_uv[2 * q_ + 1]);
+      }
     }
-  }
+  });
   // ---- batches
   std::vector<int> batch_trk{0};
   {
@@ -172,26 +185,36 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   // ---- camera pair table (both cameras active; hi = larger reduced row)
   std::vector<long long> batch_pair(P->n_batches + 1, 0);
   std::vector<unsigned> pairs;
-  for (int b = 0; b < P->n_batches; ++b) {
-    const int sbase = trk_ptr[batch_trk[b]];
-    for (int k = batch_trk[b]; k < batch_trk[b + 1]; ++k) {
-      const unsigned lt = (unsigned)(k - batch_trk[b]);
-      const int lo = trk_ptr[k] - sbase, hi = trk_ptr[k + 1] - sbase;
-      for (int x = lo; x < hi; ++x) {
-        if (l_row[sbase + x] < 0) continue;
-        for (int y2 = x + 1; y2 < hi; ++y2) {
-          if (l_row[sbase + y2] < 0) continue;
-          const int rx = l_row[sbase + x], ry = l_row[sbase + y2];
-          if (rx > ry) pairs.push_back((unsigned)x | ((unsigned)y2 << 8) | (lt << 16));
-          else if (ry > rx) pairs.push_back((unsigned)y2 | ((unsigned)x << 8) | (lt << 16));
-          else {   // same camera observed twice: both orderings land in the diagonal block
-            pairs.push_back((unsigned)x | ((unsigned)y2 << 8) | (lt << 16));
-            pairs.push_back((unsigned)y2 | ((unsigned)x << 8) | (lt << 16));
+  {
+    // visit the pairs of batch b in the order the build kernel walks them; emit(code) is called once per table entry
+    auto walk = [&](int b, auto&& emit) {
+      const int sbase = trk_ptr[batch_trk[b]];
+      for (int k = batch_trk[b]; k < batch_trk[b + 1]; ++k) {
+        const unsigned lt = (unsigned)(k - batch_trk[b]);
+        const int lo = trk_ptr[k] - sbase, hi = trk_ptr[k + 1] - sbase;
+        for (int x = lo; x < hi; ++x) {
+          if (l_row[sbase + x] < 0) continue;
+          for (int y2 = x + 1; y2 < hi; ++y2) {
+            if (l_row[sbase + y2] < 0) continue;
+            const int rx = l_row[sbase + x], ry = l_row[sbase + y2];
+            if (rx > ry) emit((unsigned)x | ((unsigned)y2 << 8) | (lt << 16));
+            else if (ry > rx) emit((unsigned)y2 | ((unsigned)x << 8) | (lt << 16));
+            else {   // same camera observed twice: both orderings land in the diagonal block
+              emit((unsigned)x | ((unsigned)y2 << 8) | (lt << 16));
+              emit((unsigned)y2 | ((unsigned)x << 8) | (lt << 16));
+            }
           }
         }
       }
-    }
-    batch_pair[b + 1] = (long long)pairs.size();
+    };
+    parallel_chunks(P->n_batches, 256, [&](int64_t b0, int64_t b1, int) {        // pass 1: entries per batch
+      for (int64_t b = b0; b < b1; ++b) { long long c = 0; walk((int)b, [&](unsigned) { ++c; }); batch_pair[b + 1] = c; }
+    });
+    for (int b = 0; b < P->n_batches; ++b) batch_pair[b + 1] += batch_pair[b];
+    pairs.resize((size_t)batch_pair[P->n_batches]);
+    parallel_chunks(P->n_batches, 256, [&](int64_t b0, int64_t b1, int) {        // pass 2: fill
+      for (int64_t b = b0; b < b1; ++b) { unsigned* dst = pairs.data() + batch_pair[b]; walk((int)b, [&](unsigned code) { *dst++ = code; }); }
+    });
   }
   P->n_pairs = (long long)pairs.size();
 
