@@ -29,14 +29,7 @@ LVBA_DEV long long env_block(const EnvView& e, int r, int c) { return e.row_star
 constexpr int kEnvMaxCol = 320;     // max rows below one pivot column handled by the factor kernel
 constexpr int kFactorThreads = 1024;
 
-// L <- H + diag(dadd)   (dadd: [6n] added on the scalar diagonal).  Grid-stride over doubles.
-__global__ void env_copy_damped_kernel(EnvView e, const double* __restrict__ H, const double* __restrict__ dadd,
-                                       double* __restrict__ L) {
-  const long long total = e.nblocks * 36;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x)
-    L[i] = H[i];
-}
+// L += diag(dadd)   (dadd: [6n] added on the scalar diagonal of the copy of H that the factorisation overwrites)
 __global__ void env_add_diag_kernel(EnvView e, const double* __restrict__ dadd, double* __restrict__ L) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 6 * e.n) {

@@ -1,0 +1,65 @@
+"""Host-side argument validation of the one-shot entry points runs BEFORE any device work (and on several
+threads for large inputs): a malformed CSR must come back as LVBA_ERR_INVALID_ARG / LVBA_ERR_UNSUPPORTED with the
+first offending item named, on a box without a GPU as well."""
+import numpy as np
+import pytest
+
+
+def _lidar_inputs(V=40_000, K=3, W=64, seed=0):
+    rng = np.random.default_rng(seed)
+    vox_ptr = np.arange(V + 1, dtype=np.int64) * K
+    base = rng.integers(0, W - K, V)
+    pose_idx = (base[:, None] + np.arange(K)[None, :]).astype(np.int32).ravel()
+    clusters = np.ones((V * K, 10))
+    poses = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float64), (W, 1))
+    return vox_ptr, pose_idx, clusters, poses
+
+
+@pytest.mark.parametrize("where", [5, 20_001, 39_999])          # first, middle and last validation chunk
+def test_lidar_pose_index_out_of_range_is_reported(pkg, where):
+    vp, pi, cl, ps = _lidar_inputs()
+    pi = pi.copy(); pi[3 * where + 1] = 64                       # == W: out of range
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.lidar_lm(vp, pi, cl, ps)
+    assert e.value.status == -1 and f"pose_idx[{3 * where + 1}]=64" in str(e.value)
+
+
+def test_lidar_first_offender_wins(pkg):
+    vp, pi, cl, ps = _lidar_inputs()
+    pi = pi.copy()
+    pi[3 * 30_000 + 1] = pi[3 * 30_000]                          # not strictly ascending (later chunk)
+    pi[3 * 100 + 2] = -1                                         # out of range (first chunk)
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.lidar_lm(vp, pi, cl, ps)
+    assert e.value.status == -1 and "pose_idx[302]=-1" in str(e.value)
+
+
+def test_lidar_unsupported_and_empty_voxels(pkg):
+    vp, pi, cl, ps = _lidar_inputs(V=30_000)
+    bad = vp.copy(); bad[20_000] = bad[19_999]                   # voxel 19999 has no slots
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.lidar_lm(bad, pi, cl, ps)
+    assert e.value.status == -1 and "voxel 19999 has no slots" in str(e.value)
+    W = 200
+    vp2 = np.array([0, 129], np.int64); pi2 = np.arange(129, dtype=np.int32)
+    with pytest.raises(pkg.LvbaError) as e:                      # more poses per voxel than a batch CTA holds
+        pkg.lidar_lm(vp2, pi2, np.ones((129, 10)), np.tile(ps[:1], (W, 1)))
+    assert e.value.status == -4
+
+
+def test_visual_observation_checks(pkg):
+    M, T, L = 50, 60_000, 3
+    rng = np.random.default_rng(1)
+    obs_ptr = np.arange(T + 1, dtype=np.int64) * L
+    obs_cam = rng.integers(0, M, T * L).astype(np.int32)
+    q = np.tile(np.array([1.0, 0, 0, 0]), (M, 1)); t = np.zeros((M, 3)); X = np.ones((T, 3))
+    plane = np.tile(np.array([0, 0, 1.0, -1.0]), (T, 1)); uv = np.zeros((T * L, 2), np.float32)
+    intr = np.array([600.0, 600, 320, 256, 0, 0, 0, 0])
+    bad = obs_cam.copy(); bad[3 * 45_000 + 2] = M
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.visual_lm(q, t, X, plane, obs_ptr, bad, uv, intr, 0.5, 0.01)
+    assert e.value.status == -1 and f"obs_cam[{3 * 45_000 + 2}]={M}" in str(e.value)
+    badp = obs_ptr.copy(); badp[30_000] = badp[29_999] - 1
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.visual_lm(q, t, X, plane, badp, obs_cam, uv, intr, 0.5, 0.01)
+    assert e.value.status == -1 and "obs_ptr not monotone" in str(e.value)
