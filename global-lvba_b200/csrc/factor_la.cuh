@@ -27,7 +27,8 @@ namespace lvba {
 // warps contend with the look-ahead warps for the issue slots and the shared-memory pipe.
 // Measured on B200 (tools/lab): two blocks per thread win for the widest window (P = 31: step 5436 -> 4911 cycles,
 // the look-ahead chain gains most: half as many pair warps compete with it and it keeps 96 registers); for P <= 24
-// the 144 accumulator registers cost more than the saved operand fetches.
+// the five pair warps that remain do not spread evenly over the four SMSPs (P = 24: 2.51 -> 2.89 ms even with the
+// register re-allocation) and the 144 accumulator registers cost more than the saved operand fetches.
 constexpr bool la_tile2(int P) { return P > 24; }
 constexpr int la_tile2_threads(int P) { int s = 0; for (int m = 1; m <= P; ++m) s += (m + 1) / 2; return s; }
 template <int P, bool kTile2>
