@@ -304,8 +304,11 @@ struct EnvSolver {
   int n_groups = 0;
   std::vector<int> grp_ptr;     // [n_groups+1] row offsets
   DevBuf<int> first_rel;        // first[r] relative to the first row of r's group
-  DevBuf<unsigned> pair_map[4];         // thread -> blocks of the register-window kernel, per P in {8,16,24,31}
-  bool have_map[4] = {false, false, false, false};
+  // window sizes P the register-window kernel is built for (P - 1 = widest column it holds): the work per pivot column
+  // grows with P^2, so a system is factorised with the smallest P that fits its envelope
+  static constexpr int kNumP = 6;
+  DevBuf<unsigned> pair_map[kNumP];     // thread -> blocks of the register-window kernel, per P
+  bool have_map[kNumP] = {false, false, false, false, false, false};
   DevBuf<long long> dbg;        // LVBA_FACTOR_TIMING=1: per-step phase clocks of the register-window kernel
   int dbg_dumped = 0, dbg_max_dumps = 2;
   bool configured = false;
@@ -317,8 +320,8 @@ struct EnvSolver {
   Envelope env_bot, env_sep;
   DevBuf<double> Lbot, dinv_bot, zbot, xbot, wtop, wbot, ztopd, zbotd, Lsep, dinv_sep, zsep, xsep;
 
-  static int pid(int mc) { return mc <= 7 ? 0 : mc <= 15 ? 1 : mc <= 23 ? 2 : 3; }
-  static int pval(int id) { return id == 0 ? 8 : id == 1 ? 16 : id == 2 ? 24 : 31; }
+  static int pid(int mc) { return mc <= 7 ? 0 : mc <= 11 ? 1 : mc <= 15 ? 2 : mc <= 20 ? 3 : mc <= 23 ? 4 : 5; }
+  static int pval(int id) { return id == 0 ? 8 : id == 1 ? 12 : id == 2 ? 16 : id == 3 ? 21 : id == 4 ? 24 : 31; }
 
   int prepare(const Envelope& env, cudaStream_t s) {
     if (env.max_col > kEnvMaxCol)
@@ -339,7 +342,8 @@ struct EnvSolver {
     if (!configured) {
       LVBA_CUDA(cudaFuncSetAttribute(env_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)factor_smem()));
 #define LVBA_SET_SMEM(PP, TT) LVBA_CUDA(cudaFuncSetAttribute(env_factor_la_kernel<PP, TT, la_tile2(PP)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LaCfg<PP, la_tile2(PP)>::kSmem))
-      LVBA_SET_SMEM(8, false); LVBA_SET_SMEM(8, true); LVBA_SET_SMEM(16, false); LVBA_SET_SMEM(16, true);
+      LVBA_SET_SMEM(8, false); LVBA_SET_SMEM(8, true); LVBA_SET_SMEM(12, false); LVBA_SET_SMEM(12, true);
+      LVBA_SET_SMEM(16, false); LVBA_SET_SMEM(16, true); LVBA_SET_SMEM(21, false); LVBA_SET_SMEM(21, true);
       LVBA_SET_SMEM(24, false); LVBA_SET_SMEM(24, true); LVBA_SET_SMEM(31, false); LVBA_SET_SMEM(31, true);
 #undef LVBA_SET_SMEM
       LVBA_CUDA(cudaFuncSetAttribute(env_backsolve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBsSmem));
@@ -381,8 +385,9 @@ struct EnvSolver {
   int ensure_map(int id, cudaStream_t s) {
     if (have_map[id]) return LVBA_OK;
     const int P = pval(id);
-    const int nthr = id == 0 ? LaCfg<8, la_tile2(8)>::kPairThreads : id == 1 ? LaCfg<16, la_tile2(16)>::kPairThreads
-                   : id == 2 ? LaCfg<24, la_tile2(24)>::kPairThreads : LaCfg<31, la_tile2(31)>::kPairThreads;
+    const int nthr = id == 0 ? LaCfg<8, la_tile2(8)>::kPairThreads : id == 1 ? LaCfg<12, la_tile2(12)>::kPairThreads
+                   : id == 2 ? LaCfg<16, la_tile2(16)>::kPairThreads : id == 3 ? LaCfg<21, la_tile2(21)>::kPairThreads
+                   : id == 4 ? LaCfg<24, la_tile2(24)>::kPairThreads : LaCfg<31, la_tile2(31)>::kPairThreads;
     const bool tile2 = la_tile2(P);
     std::vector<unsigned> m = build_pair_map32(P, tile2, nthr);
     size_t cnt = 0;
@@ -397,8 +402,10 @@ struct EnvSolver {
     LVBA_TRY(ensure_map(id, s));
     const unsigned* pm = pair_map[id].p;
 #define LVBA_LAUNCH_LA(PP, TT) env_factor_la_kernel<PP, TT, la_tile2(PP)><<<grid, LaCfg<PP, la_tile2(PP)>::kThreads, LaCfg<PP, la_tile2(PP)>::kSmem, s>>>(jobs, pm, dbg.p)
-    if (dbg.p) { if (id == 0) LVBA_LAUNCH_LA(8, true); else if (id == 1) LVBA_LAUNCH_LA(16, true); else if (id == 2) LVBA_LAUNCH_LA(24, true); else LVBA_LAUNCH_LA(31, true); }
-    else { if (id == 0) LVBA_LAUNCH_LA(8, false); else if (id == 1) LVBA_LAUNCH_LA(16, false); else if (id == 2) LVBA_LAUNCH_LA(24, false); else LVBA_LAUNCH_LA(31, false); }
+#define LVBA_LAUNCH_ID(TT) do { switch (id) { case 0: LVBA_LAUNCH_LA(8, TT); break; case 1: LVBA_LAUNCH_LA(12, TT); break; case 2: LVBA_LAUNCH_LA(16, TT); break; \
+                                   case 3: LVBA_LAUNCH_LA(21, TT); break; case 4: LVBA_LAUNCH_LA(24, TT); break; default: LVBA_LAUNCH_LA(31, TT); } } while (0)
+    if (dbg.p) LVBA_LAUNCH_ID(true); else LVBA_LAUNCH_ID(false);
+#undef LVBA_LAUNCH_ID
 #undef LVBA_LAUNCH_LA
     ++*launches;
     return LVBA_OK;
