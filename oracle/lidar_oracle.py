@@ -260,3 +260,30 @@ def damping_iter(vox_ptr, pose_idx, clusters, poses, u0=0.01, v0=2.0, max_iter=1
             break
     info["u_last"], info["v_last"] = u, v
     return poses, info
+
+
+def window_ba(win_ptr, vox_ptr, pose_idx, clusters, poses, min_voxels_per_pose=3, **lm_kw):
+    """The window loop of LvbaSystem::runWindowBA (reference src/lvba_system.cpp:232-302) restated on the flat
+    layout of lvba_lidar_lm_batch: window w owns poses win_ptr[w]..win_ptr[w+1]-1; every voxel lies in one window;
+    pose_idx indexes the concatenated pose array.  Each window with at least `min_voxels_per_pose` voxels per pose
+    (`plvec_voxels.size() < 3 * x_win.size()` -> continue, :262-266) runs its own damping_iter (:264); the others keep
+    their poses.  Returns (poses, [info or None per window])."""
+    win_ptr = np.asarray(win_ptr)
+    poses = np.array(poses, dtype=np.float64, copy=True)
+    first_pose = pose_idx[np.asarray(vox_ptr[:-1])] if len(vox_ptr) > 1 else np.zeros(0, np.int64)
+    win_of_vox = np.searchsorted(win_ptr, first_pose, side="right") - 1
+    infos = []
+    for w in range(len(win_ptr) - 1):
+        lo_, hi_ = int(win_ptr[w]), int(win_ptr[w + 1])
+        vs = np.nonzero(win_of_vox == w)[0]
+        if hi_ - lo_ <= 0 or len(vs) == 0 or len(vs) < min_voxels_per_pose * (hi_ - lo_):
+            infos.append(None)
+            continue
+        vp = np.zeros(len(vs) + 1, np.int64)
+        sl = [np.arange(vox_ptr[a], vox_ptr[a + 1]) for a in vs]
+        vp[1:] = np.cumsum([len(x) for x in sl])
+        idx = np.concatenate(sl)
+        new, info = damping_iter(vp, (pose_idx[idx] - lo_).astype(np.int32), clusters[idx], poses[lo_:hi_], **lm_kw)
+        poses[lo_:hi_] = new
+        infos.append(info)
+    return poses, infos

@@ -31,4 +31,17 @@ pr, info = vo.ceres_lm(pr)
 out["B_lm_q"] = pr.q; out["B_lm_t"] = pr.t; out["B_lm_X"] = pr.X; out["B_lm_cost"] = np.float64(info["cost"])
 out["B_lm_iters"] = np.int64(info["iters"]); out["B_lm_accepted"] = np.int64(info["accepted"])
 np.savez_compressed(Path(__file__).with_name("small_problem.npz"), **out)
+
+# ---- window BA (lvba_lidar_lm_batch): five small windows, one below the 3-voxels-per-pose rule, one empty
+wp = synth.make_window_problem([8, 6, 5, 7, 4], [60, 40, 9, 0, 30], seed=99)
+wposes, winfos = lo.window_ba(wp["win_ptr"], wp["vox_ptr"], wp["pose_idx"], wp["clusters"], wp["poses"])
+wout = {k: wp[k] for k in ("win_ptr", "vox_ptr", "pose_idx", "clusters", "poses")}
+wout["W_poses"] = wposes
+wout["W_skipped"] = np.array([i is None for i in winfos])
+wout["W_iters"] = np.array([0 if i is None else i["iters"] for i in winfos], np.int64)
+wout["W_accepted"] = np.array([0 if i is None else i["accepted"] for i in winfos], np.int64)
+wout["W_cost_first"] = np.array([0.0 if i is None else i["r_first"] for i in winfos])
+wout["W_cost_last"] = np.array([0.0 if i is None else i["r_last"] for i in winfos])
+np.savez_compressed(Path(__file__).with_name("window_problem.npz"), **wout)
+print("wrote window_problem.npz", wout["W_iters"], wout["W_accepted"], wout["W_skipped"])
 print("wrote", Path(__file__).with_name("small_problem.npz"), {k: (v.shape if hasattr(v, 'shape') else v) for k, v in out.items() if k.startswith(('A_', 'B_'))})

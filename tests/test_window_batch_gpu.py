@@ -4,11 +4,15 @@ LvbaSystem::runWindowBA (reference src/lvba_system.cpp:232-302) in one call.
 Bar: each window behaves exactly as its own BALM2::damping_iter (bavoxel.hpp:662-767): same accept/reject
 sequence and iteration count as the numpy oracle run on that window alone, final cost within rel 1e-6,
 poses within 1e-6; windows below the reference's 3-voxels-per-pose rule (:262-266) are left untouched."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
 from oracle import lidar_oracle as lo
 from oracle import synth
+
+GOLD = np.load(Path(__file__).parent / "golden" / "window_problem.npz")
 
 pytestmark = pytest.mark.gpu
 
@@ -39,6 +43,26 @@ def test_batch_matches_per_window_oracle(gpu_pkg, windows):
         # the damping itself is not compared: the last update uses rho = (r1 - r2) / q1 with r1 - r2 at the 1e-6
         # stop threshold or below, where the ~1e-9 summation-order noise of the residuals dominates
         # rho (the reference's own u depends on its thread split there); decisions and state are compared instead
+
+
+def test_batch_matches_golden_fixture(gpu_pkg):
+    """Committed known-answer vectors (tests/golden/make_golden.py): no input is regenerated on the GPU box."""
+    poses, sums, _ = gpu_pkg.lidar_lm_batch(GOLD["win_ptr"], GOLD["vox_ptr"], GOLD["pose_idx"], GOLD["clusters"], GOLD["poses"])
+    for w in range(len(GOLD["win_ptr"]) - 1):
+        if GOLD["W_skipped"][w]:
+            assert sums[w]["termination"] == 6
+            continue
+        assert sums[w]["iterations"] == GOLD["W_iters"][w] and sums[w]["accepted"] == GOLD["W_accepted"][w]
+        assert abs(sums[w]["cost_last"] - GOLD["W_cost_last"][w]) <= 1e-6 * GOLD["W_cost_last"][w]
+    assert np.abs(poses - GOLD["W_poses"]).max() <= 1e-6
+
+
+def test_batch_matches_window_oracle_as_a_whole(gpu_pkg, windows):
+    p = windows
+    ref, infos = lo.window_ba(p["win_ptr"], p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"])
+    poses, sums, _ = gpu_pkg.lidar_lm_batch(p["win_ptr"], p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"])
+    assert [s["termination"] == 6 for s in sums] == [i is None for i in infos]
+    assert np.abs(poses - ref).max() <= 1e-6
 
 
 def test_batch_equals_separate_calls(gpu_pkg, windows):
