@@ -19,8 +19,11 @@
 
 namespace lvba {
 
-constexpr int kSpikeCols = 30;           // right-hand sides per spike CTA
-constexpr int kSpikeThreads = 192;       // 6 x 30 outputs per row (+ 12 idle)
+// First measurement (profiles/r01_four_chunk_lab.txt) ran with 30 right-hand sides per CTA (6 CTAs per job): every output
+// issues 12 LDS per 6 FMA, ~2 000 warp-LDS per row and CTA, i.e. the spike alone took ~0.6 ms.  Ten right-hand sides per CTA
+// (18 CTAs per job, 36 SMs for the two spikes) cut the per-CTA shared-memory work by three; UNMEASURED so far.
+constexpr int kSpikeCols = 10;           // right-hand sides per spike CTA
+constexpr int kSpikeThreads = 64;        // 6 x 10 outputs per row (+ 4 idle)
 constexpr size_t kSpikeSmem = sizeof(double) * (2 * 31 * 36 + 32 * 6 * kSpikeCols);
 
 // Forward substitution of KS right-hand sides through the unit-lower block factor of one factorisation instance.
