@@ -298,8 +298,8 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   P->n_pairs = np;
 
   lap("batches+pair table");
-  // ---- upload.  Clusters: the caller's AoS records go up as they are (per contiguous run of owned
-  //      voxels) and are transposed to the SoA double2 layout by a kernel.
+  // ---- upload.  Clusters: the caller's AoS records go up in ONE copy and are transposed to the SoA double2 layout
+  //      by a kernel (which also picks the owned slots when the problem is sharded or window-sorted).
   const long long nnz_pad = ((nnz + 31) / 32) * 32 + 32;
   LVBA_TRY(P->cl.alloc((size_t)5 * nnz_pad));
   LVBA_TRY(P->cl.zero(s));
