@@ -34,6 +34,8 @@ EXPORTS = [
     "lvba_visual_lm", "lvba_visual_create", "lvba_visual_destroy", "lvba_visual_set_state",
     "lvba_visual_get_state", "lvba_visual_cost", "lvba_visual_step", "lvba_visual_structure",
     "lvba_visual_get_system", "lvba_visual_reset_lm", "lvba_visual_reset_state", "lvba_visual_iterate", "lvba_visual_counts",
+    "lvba_voxel_default_opts", "lvba_voxel_map_create", "lvba_voxel_map_summary", "lvba_voxel_map_export",
+    "lvba_voxel_map_lookup", "lvba_voxel_map_destroy",
     "lvba_comm_unique_id", "lvba_comm_init", "lvba_comm_destroy", "lvba_comm_info", "lvba_shard_owner",
 ]
 
@@ -68,10 +70,26 @@ class Summary(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class VoxelOpts(C.Structure):
+    _fields_ = [("voxel_size", C.c_double), ("eigen_ratio", C.c_float * 4), ("layer_limit", C.c_int32),
+                ("min_points", C.c_int32), ("device", C.c_int32)]
+
+
+class VoxelSummary(C.Structure):
+    _fields_ = [("n_points", C.c_int64), ("n_voxels", C.c_int64), ("nnz", C.c_int64), ("n_nodes", C.c_int64 * 3),
+                ("ms_total", C.c_double), ("ms_upload", C.c_double), ("ms_device", C.c_double),
+                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["n_nodes"] = list(self.n_nodes)
+        return d
+
+
 def build_library(force=False, quiet=True):
     """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU)."""
     if LIB_PATH.exists() and not force:
-        src_m = max(p.stat().st_mtime for p in list((_HERE / "csrc").glob("*.cu*")) + [(_HERE.parent / "include" / "lvba_b200.h")])
+        src_m = max(p.stat().st_mtime for p in list((_HERE / "csrc").glob("*.cu*")) + list((_HERE / "csrc").glob("*.h")) + [(_HERE.parent / "include" / "lvba_b200.h")])
         if LIB_PATH.stat().st_mtime >= src_m:
             return LIB_PATH
     r = subprocess.run(["make", "-C", str(_HERE / "csrc")], capture_output=True, text=True)
@@ -327,6 +345,74 @@ class VisualProblem:
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         _chk(self._lib.lvba_visual_counts(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return dict(nnz_valid=a.value, n_valid_tracks=b.value, n_blocks_env=c.value, n_pairs=d.value)
+
+
+# ------------------------------------------------------------------ B3: adaptive voxel map
+def voxel_default_opts():
+    o = VoxelOpts()
+    load_library().lvba_voxel_default_opts(C.byref(o))
+    return o
+
+
+class VoxelMap:
+    """Device-resident adaptive voxel map (cut_voxel + recut + tras_opt, bavoxel.hpp:799-836, 420-474).
+    scans: list of (n_i, 3) float32 body-frame clouds (or one (N, stride) float32 array with scan_ptr); poses (W, 12)."""
+
+    def __init__(self, scans, poses, voxel_size=1.0, eigen_ratio=None, layer_limit=2, min_points=15, device=-1,
+                 scan_ptr=None):
+        lib = load_library()
+        self._lib = lib
+        ps = _f64(poses)
+        if scan_ptr is None:
+            W = len(scans)
+            sp = np.zeros(W + 1, np.int64)
+            sp[1:] = np.cumsum([len(s) for s in scans])
+            xyz = (np.concatenate([np.asarray(s, np.float32).reshape(-1, 3) for s in scans]) if W else np.zeros((0, 3), np.float32))
+        else:
+            sp = np.ascontiguousarray(scan_ptr, np.int64); W = len(sp) - 1
+            xyz = np.asarray(scans, np.float32)
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        stride = xyz.shape[1] if xyz.ndim == 2 else 3
+        o = voxel_default_opts()
+        o.voxel_size = float(voxel_size); o.layer_limit = int(layer_limit); o.min_points = int(min_points); o.device = int(device)
+        if eigen_ratio is not None:
+            for k in range(4):
+                o.eigen_ratio[k] = float(eigen_ratio[k])
+        self._h = C.c_void_p()
+        s = VoxelSummary()
+        _chk(lib.lvba_voxel_map_create(C.c_int32(W), _p(sp, C.c_int64), _p(xyz, C.c_float), C.c_int32(stride),
+                                       _p(ps, C.c_double), C.byref(o), C.byref(self._h), C.byref(s)))
+        self.summary = s.as_dict()
+
+    def close(self):
+        if self._h:
+            self._lib.lvba_voxel_map_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def export(self):
+        """dict: vox_ptr, pose_idx, clusters (arguments of lidar_lm) + key, path, centre, normal, eigenvalues per voxel."""
+        V, nnz = self.summary["n_voxels"], self.summary["nnz"]
+        o = dict(vox_ptr=np.zeros(V + 1, np.int64), pose_idx=np.zeros(nnz, np.int32), clusters=np.zeros((nnz, 10)),
+                 key=np.zeros((V, 3), np.int64), path=np.zeros((V, 3), np.int8), centre=np.zeros((V, 3)),
+                 normal=np.zeros((V, 3)), eigenvalues=np.zeros((V, 3)))
+        _chk(self._lib.lvba_voxel_map_export(self._h, _p(o["vox_ptr"], C.c_int64), _p(o["pose_idx"], C.c_int32),
+                                             _p(o["clusters"], C.c_double), _p(o["key"], C.c_int64), _p(o["path"], C.c_int8),
+                                             _p(o["centre"], C.c_double), _p(o["normal"], C.c_double),
+                                             _p(o["eigenvalues"], C.c_double)))
+        return o
+
+    def lookup(self, X):
+        """recompute_local_planes (lvba_system.cpp:1529-1566): (n, 4) plane (n, d) per world point, zeros when none."""
+        X = _f64(X).reshape(-1, 3)
+        out = np.zeros((len(X), 4))
+        _chk(self._lib.lvba_voxel_map_lookup(self._h, C.c_int64(len(X)), _p(X, C.c_double), _p(out, C.c_double)))
+        return out
 
 
 # ------------------------------------------------------------------ multi-GPU

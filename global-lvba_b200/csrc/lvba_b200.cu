@@ -4,6 +4,7 @@
 
 #include "lidar_api.cuh"
 #include "visual_api.cuh"
+#include "voxel_api.cuh"
 
 extern "C" {
 

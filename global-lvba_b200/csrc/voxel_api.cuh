@@ -1,0 +1,255 @@
+// voxel_api.cuh — boundary B3: the adaptive voxel map on the device.
+// The passes themselves are in voxel_pipeline.h; this file supplies the CUDA execution policy (one grid-stride kernel
+// per pass, cub for the stable radix sorts / scans / min-max) and the C entry points of include/lvba_b200.h.
+// There is no host path: without a CUDA device every entry point returns LVBA_ERR_NO_DEVICE.
+#pragma once
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "runtime.cuh"
+#include "voxel_pipeline.h"
+
+namespace lvba {
+
+// Each pass is a functor over an index range.  Grid: enough 256-thread CTAs to cover n, capped at 16 per SM on the
+// 148 SMs of a B200 (grid-stride beyond that); the point passes are HBM streams, the segment / node passes are
+// latency-bound gathers that want many warps in flight.
+template <class F>
+__global__ void __launch_bounds__(256) vox_for_each_kernel(int64_t n, F f) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
+}
+
+struct CudaExec {
+  template <class T>
+  using Buf = DevBuf<T>;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;            // launches of this library's own kernels (cub's are library calls, not counted)
+  DevBuf<uint8_t> temp;
+  DevBuf<int32_t> red;
+
+  template <class F>
+  int for_each(int64_t n, const F& f) {
+    if (n <= 0) return LVBA_OK;
+    const int64_t want = (n + 255) / 256;
+    const int grid = (int)std::min<int64_t>(want, 148 * 16);
+    vox_for_each_kernel<F><<<grid, 256, 0, stream>>>(n, f);
+    LVBA_CUDA(cudaGetLastError());
+    ++launches;
+    return LVBA_OK;
+  }
+  template <class T>
+  int fill_zero(T* p, size_t n) {
+    if (n) LVBA_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), stream));
+    return LVBA_OK;
+  }
+  template <class T>
+  int fetch(T* host, const T* dev, size_t n) {
+    if (n) LVBA_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, stream));
+    LVBA_CUDA(cudaStreamSynchronize(stream));
+    return LVBA_OK;
+  }
+  int reserve_temp(size_t bytes) {
+    if (bytes == 0) bytes = 1;                       // cub reads a null temp pointer as a size query
+    if (bytes > temp.n) LVBA_TRY(temp.alloc(bytes));
+    return LVBA_OK;
+  }
+  int min_max(const int32_t* p, int64_t n, int32_t* mn, int32_t* mx) {
+    if (red.n < 2) LVBA_TRY(red.alloc(2));
+    size_t b0 = 0, b1 = 0;
+    LVBA_CUDA(cub::DeviceReduce::Min(nullptr, b0, p, red.p, n, stream));
+    LVBA_CUDA(cub::DeviceReduce::Max(nullptr, b1, p, red.p + 1, n, stream));
+    LVBA_TRY(reserve_temp(std::max(b0, b1)));
+    size_t tb = temp.n;
+    LVBA_CUDA(cub::DeviceReduce::Min(temp.p, tb, p, red.p, n, stream));
+    tb = temp.n;
+    LVBA_CUDA(cub::DeviceReduce::Max(temp.p, tb, p, red.p + 1, n, stream));
+    int32_t h[2];
+    LVBA_TRY(fetch(h, red.p, 2));
+    *mn = h[0]; *mx = h[1];
+    return LVBA_OK;
+  }
+  // stable LSD radix sort on key bits [0, end_bit)
+  int sort_pairs(const uint64_t* kin, uint64_t* kout, const uint32_t* vin, uint32_t* vout, int64_t n, int end_bit) {
+    if (n <= 0) return LVBA_OK;
+    size_t bytes = 0;
+    LVBA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, n, 0, end_bit, stream));
+    LVBA_TRY(reserve_temp(bytes));
+    bytes = temp.n;
+    LVBA_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, bytes, kin, kout, vin, vout, n, 0, end_bit, stream));
+    return LVBA_OK;
+  }
+  template <class T>
+  int exclusive_scan(const T* in, T* out, int64_t n) {
+    if (n <= 0) return LVBA_OK;
+    size_t bytes = 0;
+    LVBA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, stream));
+    LVBA_TRY(reserve_temp(bytes));
+    bytes = temp.n;
+    LVBA_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, bytes, in, out, n, stream));
+    return LVBA_OK;
+  }
+  int sync() {
+    LVBA_CUDA(cudaStreamSynchronize(stream));
+    return LVBA_OK;
+  }
+};
+
+}  // namespace lvba
+
+struct lvba_voxel_map {
+  lvba::vox::VoxelMap<lvba::CudaExec> map;
+  int device = 0;
+  lvba_voxel_summary sum{};
+};
+
+namespace lvba {
+
+inline int voxel_check_opts(const lvba_voxel_opts* o) {
+  if (!(o->voxel_size > 0.0) || !std::isfinite(o->voxel_size)) return fail(LVBA_ERR_INVALID_ARG, "voxel_size must be positive and finite");
+  if (o->layer_limit < 0 || o->layer_limit > 2) return fail(LVBA_ERR_UNSUPPORTED, "layer_limit %d outside 0..2", o->layer_limit);
+  if (o->min_points < 0) return fail(LVBA_ERR_INVALID_ARG, "min_points < 0");
+  for (int k = 0; k < 4; ++k)
+    if (!(o->eigen_ratio[k] >= 0.0f)) return fail(LVBA_ERR_INVALID_ARG, "eigen_ratio[%d] is negative or NaN", k);
+  return LVBA_OK;
+}
+
+inline int voxel_map_create_impl(int32_t W, const int64_t* scan_ptr, const float* xyz, int32_t stride, const double* poses,
+                                 const lvba_voxel_opts* opts_in, lvba_voxel_map** out, lvba_voxel_summary* summary) {
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  if (!out) return fail(LVBA_ERR_INVALID_ARG, "null output handle");
+  *out = nullptr;
+  if (W < 0 || !scan_ptr || (W > 0 && !poses)) return fail(LVBA_ERR_INVALID_ARG, "null argument or negative scan count");
+  if (stride < 3) return fail(LVBA_ERR_INVALID_ARG, "xyz_stride %d < 3 floats", stride);
+  lvba_voxel_opts o;
+  if (opts_in) o = *opts_in; else lvba_voxel_default_opts(&o);
+  LVBA_TRY(voxel_check_opts(&o));
+  if (scan_ptr[0] != 0) return fail(LVBA_ERR_INVALID_ARG, "scan_ptr[0] != 0");
+  for (int32_t j = 0; j < W; ++j)
+    if (scan_ptr[j + 1] < scan_ptr[j]) return fail(LVBA_ERR_INVALID_ARG, "scan_ptr not monotone at scan %d", j);
+  const int64_t N = scan_ptr[W];
+  if (N >= (int64_t)0xfffffff0ll) return fail(LVBA_ERR_UNSUPPORTED, "%lld points: more than 2^32 per map", (long long)N);
+  if (N > 0 && !xyz) return fail(LVBA_ERR_INVALID_ARG, "null xyz");
+  for (int64_t k = 0; k < (int64_t)W * 12; ++k)
+    if (!std::isfinite(poses[k])) return fail(LVBA_ERR_INVALID_ARG, "non-finite pose entry %lld", (long long)k);
+  LVBA_TRY(select_device(o.device));
+
+  std::unique_ptr<lvba_voxel_map> h(new lvba_voxel_map());
+  cudaGetDevice(&h->device);
+  CudaExec& ex = h->map.ex;
+  // ---- upload: points packed to 12 B each (a PCL PointXYZINormal array has stride 12 floats; only x, y, z are used)
+  DevBuf<float> d_xyz;
+  DevBuf<int64_t> d_scan;
+  DevBuf<double> d_poses;
+  int64_t h2d = 0;
+  std::vector<float> packed;
+  const float* src = xyz;
+  if (stride != 3 && N > 0) {
+    packed.resize((size_t)N * 3);
+    float* dst = packed.data();
+    parallel_chunks(N, 1 << 16, [=](int64_t a, int64_t b, int) {
+      for (int64_t i = a; i < b; ++i) { dst[3 * i] = xyz[i * stride]; dst[3 * i + 1] = xyz[i * stride + 1]; dst[3 * i + 2] = xyz[i * stride + 2]; }
+    });
+    src = packed.data();
+  }
+  LVBA_TRY(d_xyz.upload(src, (size_t)N * 3, ex.stream, &h2d));
+  LVBA_TRY(d_scan.upload(scan_ptr, (size_t)W + 1, ex.stream, &h2d));
+  LVBA_TRY(d_poses.upload(poses, (size_t)W * 12, ex.stream, &h2d));
+  cudaEvent_t e0, e1;
+  LVBA_CUDA(cudaEventCreate(&e0));
+  LVBA_CUDA(cudaEventCreate(&e1));
+  LVBA_CUDA(cudaEventRecord(e0, ex.stream));
+  const auto t1 = clk::now();
+  vox::VoxParams prm{o.voxel_size, {o.eigen_ratio[0], o.eigen_ratio[1], o.eigen_ratio[2], o.eigen_ratio[3]}, o.layer_limit, o.min_points};
+  const int rc = h->map.build(d_xyz.p, d_scan.p, d_poses.p, W, N, prm);
+  if (rc != LVBA_OK) {
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (h->map.error[0]) return fail(rc, "%s", h->map.error);
+    return rc;
+  }
+  LVBA_CUDA(cudaEventRecord(e1, ex.stream));
+  LVBA_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  LVBA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  ex.temp.release();
+  lvba_voxel_summary& s = h->sum;
+  s.n_points = N; s.n_voxels = h->map.V; s.nnz = h->map.nnz;
+  for (int L = 0; L < 3; ++L) s.n_nodes[L] = L < h->map.n_layers ? h->map.layer[L].n_nodes : 0;
+  s.ms_device = ms;
+  s.ms_upload = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  s.ms_total = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  s.kernel_launches = ex.launches;
+  s.h2d_bytes = h2d;
+  if (summary) *summary = s;
+  *out = h.release();
+  return LVBA_OK;
+}
+
+}  // namespace lvba
+
+extern "C" {
+
+void lvba_voxel_default_opts(lvba_voxel_opts* o) {
+  if (!o) return;
+  o->voxel_size = 1.0;
+  o->eigen_ratio[0] = 0.3f; o->eigen_ratio[1] = 0.1f; o->eigen_ratio[2] = 0.06f; o->eigen_ratio[3] = 0.03f;   // bavoxel.hpp:17
+  o->layer_limit = 2;                                                                                           // bavoxel.hpp:13
+  o->min_points = 15;                                                                                           // bavoxel.hpp:24
+  o->device = -1;
+}
+
+int lvba_voxel_map_create(int32_t W, const int64_t* scan_ptr, const float* xyz, int32_t xyz_stride_floats, const double* poses,
+                          const lvba_voxel_opts* opts, lvba_voxel_map** out, lvba_voxel_summary* summary) {
+  return lvba::voxel_map_create_impl(W, scan_ptr, xyz, xyz_stride_floats, poses, opts, out, summary);
+}
+
+int lvba_voxel_map_summary(const lvba_voxel_map* m, lvba_voxel_summary* summary) {
+  if (!m || !summary) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  *summary = m->sum;
+  return LVBA_OK;
+}
+
+int lvba_voxel_map_export(lvba_voxel_map* m, int64_t* vox_ptr, int32_t* pose_idx, double* clusters, int64_t* root_key,
+                          int8_t* path, double* centre, double* normal, double* eigenvalues) {
+  if (!m) return lvba::fail(LVBA_ERR_INVALID_ARG, "null map");
+  LVBA_CUDA(cudaSetDevice(m->device));
+  auto& v = m->map;
+  cudaStream_t s = v.ex.stream;
+  const size_t V = (size_t)v.V, nnz = (size_t)v.nnz;
+  if (vox_ptr) LVBA_CUDA(cudaMemcpyAsync(vox_ptr, v.vox_ptr.p, (V + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  if (pose_idx && nnz) LVBA_CUDA(cudaMemcpyAsync(pose_idx, v.vox_pose.p, nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (clusters && nnz) LVBA_CUDA(cudaMemcpyAsync(clusters, v.vox_cluster.p, nnz * 10 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (root_key && V) LVBA_CUDA(cudaMemcpyAsync(root_key, v.vox_root.p, V * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  if (path && V) LVBA_CUDA(cudaMemcpyAsync(path, v.vox_path.p, V * 3, cudaMemcpyDeviceToHost, s));
+  if (centre && V) LVBA_CUDA(cudaMemcpyAsync(centre, v.vox_centre.p, V * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (normal && V) LVBA_CUDA(cudaMemcpyAsync(normal, v.vox_direct.p, V * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (eigenvalues && V) LVBA_CUDA(cudaMemcpyAsync(eigenvalues, v.vox_eig.p, V * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  LVBA_CUDA(cudaStreamSynchronize(s));
+  return LVBA_OK;
+}
+
+int lvba_voxel_map_lookup(lvba_voxel_map* m, int64_t n, const double* X, double* plane_nd) {
+  if (!m || n < 0 || (n > 0 && (!X || !plane_nd))) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument or negative count");
+  if (n == 0) return LVBA_OK;
+  LVBA_CUDA(cudaSetDevice(m->device));
+  auto& v = m->map;
+  lvba::DevBuf<double> dX, dout;
+  LVBA_TRY(dX.upload(X, (size_t)n * 3, v.ex.stream));
+  LVBA_TRY(dout.alloc((size_t)n * 4));
+  LVBA_TRY(v.lookup(n, dX.p, dout.p));
+  LVBA_CUDA(cudaMemcpyAsync(plane_nd, dout.p, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, v.ex.stream));
+  LVBA_CUDA(cudaStreamSynchronize(v.ex.stream));
+  m->sum.kernel_launches = v.ex.launches;
+  return LVBA_OK;
+}
+
+int lvba_voxel_map_destroy(lvba_voxel_map* m) {
+  if (!m) return LVBA_OK;
+  cudaSetDevice(m->device);
+  delete m;
+  return LVBA_OK;
+}
+
+}  // extern "C"

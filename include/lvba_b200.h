@@ -215,6 +215,63 @@ int lvba_visual_counts(lvba_visual_problem* p, int64_t* nnz_valid, int64_t* n_va
                        int64_t* n_blocks_env, int64_t* n_pairs);
 
 /* ======================================================================================
+ * B3  adaptive voxel map (set-up stage) — replaces the cut_voxel / recut / tras_opt sequence in front of every
+ *     LiDAR solve and the plane lookup in front of the visual solve:
+ *       cut_voxel per scan       include/BALM/bavoxel.hpp:799-836   src/lvba_system.cpp:248-251, 366-369, 1499-1502
+ *       recut + tras_opt         include/BALM/bavoxel.hpp:420-474   src/lvba_system.cpp:255-258, 374-377, 1504-1506
+ *       recompute_local_planes   src/lvba_system.cpp:1529-1566 with findCorrespondPoint, bavoxel.hpp:320-333
+ *     The map is built on the device from the raw scans (sort-based, no hash table, no per-point allocation) and
+ *     stays there; the plane voxels come back in exactly the layout lvba_lidar_lm takes.
+ *
+ *   W                  number of scans = poses of the window (win_size)
+ *   scan_ptr           [W+1] CSR offsets into the point array; scan j owns points scan_ptr[j] .. scan_ptr[j+1]-1
+ *   xyz                body-frame points, x y z as float at the start of every record
+ *   xyz_stride_floats  record size in floats: 3 for packed xyz, 12 for an array of pcl::PointXYZINormal (48 B)
+ *   poses              [W*12] pose of every scan (x_buf / anchor_poses)
+ *   Voxel order: ascending (root key x, y, z), then octant path — the reference's unordered_map order is unspecified.
+ *   A non-finite point, or one more than 2^30 root voxels from the origin, is LVBA_ERR_INVALID_ARG (the reference's
+ *   float -> int64 cast is undefined there).
+ * ====================================================================================== */
+typedef struct lvba_voxel_opts {
+  double voxel_size;       /* root voxel edge: stage1_root_voxel_size_ / stage2_root_voxel_size_ (lvba_system.cpp:344-345) */
+  float eigen_ratio[4];    /* eigen_ratio_array per layer, bavoxel.hpp:17-22 (set_eigen_ratio_array, lvba_system.cpp:360) */
+  int32_t layer_limit;     /* 2   bavoxel.hpp:13; 0..2 supported */
+  int32_t min_points;      /* 15  min_ps, bavoxel.hpp:24 */
+  int32_t device;          /* CUDA device ordinal; -1 = current */
+} lvba_voxel_opts;
+
+typedef struct lvba_voxel_summary {
+  int64_t n_points;
+  int64_t n_voxels;        /* plane voxels seen from >= 2 poses (VOX_HESS::plvec_voxels.size()) */
+  int64_t nnz;             /* (voxel, pose) clusters */
+  int64_t n_nodes[3];      /* octree nodes per layer that hold points (layers never reached are 0) */
+  double ms_total;         /* wall time inside lvba_voxel_map_create (host clock) */
+  double ms_upload;        /* validation + packing + H2D enqueue */
+  double ms_device;        /* CUDA-event time of the build passes */
+  int64_t kernel_launches; /* launches of this library's own kernels (the cub sorts / scans are not counted) */
+  int64_t h2d_bytes;
+} lvba_voxel_summary;
+
+typedef struct lvba_voxel_map lvba_voxel_map;
+
+void lvba_voxel_default_opts(lvba_voxel_opts* o);
+int lvba_voxel_map_create(int32_t W, const int64_t* scan_ptr, const float* xyz, int32_t xyz_stride_floats,
+                          const double* poses, const lvba_voxel_opts* opts, lvba_voxel_map** out,
+                          lvba_voxel_summary* summary /* may be NULL */);
+int lvba_voxel_map_summary(const lvba_voxel_map* m, lvba_voxel_summary* summary);
+/* Copy out the plane voxels (sizes from the summary).  Any pointer may be NULL.
+ *   vox_ptr [V+1], pose_idx [nnz], clusters [nnz*10]   the arguments of lvba_lidar_lm / lvba_lidar_create
+ *   root_key [V*3] int64 voxel key; path [V*3] int8 (layer, octant1 or -1, octant2 or -1)
+ *   centre, normal, eigenvalues [V*3]   judge_eigen's center / direct / value_vector (bavoxel.hpp:346-349); the sign
+ *   of `normal` is not defined (nor is it by Eigen's solver) */
+int lvba_voxel_map_export(lvba_voxel_map* m, int64_t* vox_ptr, int32_t* pose_idx, double* clusters, int64_t* root_key,
+                          int8_t* path, double* centre, double* normal, double* eigenvalues);
+/* recompute_local_planes: for n world points X [n*3] the plane (n, d) [n*4] of the PLANE node each one falls in,
+ * zeros when there is none — the plane_nd argument of lvba_visual_lm. */
+int lvba_voxel_map_lookup(lvba_voxel_map* m, int64_t n, const double* X, double* plane_nd);
+int lvba_voxel_map_destroy(lvba_voxel_map* m);
+
+/* ======================================================================================
  * Multi-GPU (one process per GPU).  The path shards by contiguous pose-block rows
  * (SURVEY.md §8e): voxel / track -> owner of its lowest pose / camera index.  Every rank
  * passes the FULL problem to *_create; after lvba_comm_init each rank keeps only its shard

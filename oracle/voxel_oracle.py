@@ -8,6 +8,7 @@ Follows, line by line:
   judge_eigen          include/BALM/bavoxel.hpp:335-352   merged world-frame covariance, lambda0/lambda2 <= eigen_ratio_array[layer]
   cut_func             include/BALM/bavoxel.hpp:391-418   octant by strict '>' against the float centre
   tras_opt/push_voxel  include/BALM/bavoxel.hpp:466-474, 45-54   PLANE nodes seen from >= 2 poses become BA voxels
+  findCorrespondPoint  include/BALM/bavoxel.hpp:320-333 and recompute_local_planes, src/lvba_system.cpp:1529-1566
   PointCluster         include/BALM/tools.hpp:407-456
 
 Two independent implementations that the tests compare:
@@ -172,10 +173,13 @@ class _Node:
         self.pts = [[] for _ in range(W)]
         self.centre = centre; self.quater = quater; self.layer = layer
         self.leaves = {}
+        self.state = "UNKNOWN"; self.plane = None
 
 
-def voxelize_literal(scans, poses, voxel_size=1.0, eigen_ratio=EIGEN_RATIO_DEFAULT, layer_limit=LAYER_LIMIT, min_ps=MIN_PS):
-    """The reference's tree, literally: per-node point lists, recursive recut (small inputs only)."""
+def build_tree_literal(scans, poses, voxel_size=1.0, eigen_ratio=EIGEN_RATIO_DEFAULT, layer_limit=LAYER_LIMIT, min_ps=MIN_PS):
+    """The reference's surf_map after cut_voxel + recut, literally: {root key: _Node} with per-node point lists, states
+    UNKNOWN (split; children in .leaves) / MID_NODE / PLANE and, for every node that reached judge_eigen, .plane =
+    (is_plane, center, direct, eigenvalues).  Small inputs only."""
     W = len(scans)
     roots = {}
     for i, s in enumerate(scans):                                          # cut_voxel, one call per scan (:254-257 of lvba_system.cpp)
@@ -186,27 +190,20 @@ def voxelize_literal(scans, poses, voxel_size=1.0, eigen_ratio=EIGEN_RATIO_DEFAU
                 c, q = _root_centre(np.array(key), voxel_size)
                 roots[key] = _Node(W, c, q, 0)
             roots[key].pts[i].append(p)
-    out = []
 
-    def clusters(node):
-        cl = {}
-        for i in range(W):
-            if node.pts[i]:
-                a = np.asarray(node.pts[i], np.float64)
-                cl[i] = (a.T @ a, a.sum(0), len(a))
-        return cl
-
-    def recut(node, key, path):
-        cl = clusters(node)
-        if sum(c[2] for c in cl.values()) < min_ps:
+    def recut(node):
+        node.clusters = _clusters_of(node, W)
+        if sum(c[2] for c in node.clusters.values()) < min_ps:             # :427-433
+            node.state = "MID_NODE"
             return
-        plane = _plane_test(cl, poses, node.layer, eigen_ratio)
-        if plane[0]:
-            _emit(out, key, path, node.layer, cl, plane)
+        node.plane = _plane_test(node.clusters, poses, node.layer, eigen_ratio)
+        if node.plane[0]:                                                  # :435-443
+            node.state = "PLANE"
             return
-        if node.layer == layer_limit:
+        if node.layer == layer_limit:                                      # :446-452
+            node.state = "MID_NODE"
             return
-        for i in range(W):                                                 # cut_func per pose
+        for i in range(W):                                                 # cut_func per pose (:391-418)
             for p in node.pts[i]:
                 pw = _world(np.asarray(p)[None, :], poses[i])[0]
                 leaf, bits = _octant(pw, node.centre)
@@ -216,8 +213,64 @@ def voxelize_literal(scans, poses, voxel_size=1.0, eigen_ratio=EIGEN_RATIO_DEFAU
                     node.leaves[leaf] = _Node(W, c, q, node.layer + 1)
                 node.leaves[leaf].pts[i].append(p)
         for leaf in sorted(node.leaves):
-            recut(node.leaves[leaf], key, path + (leaf,))
+            recut(node.leaves[leaf])
 
     for key in sorted(roots):
-        recut(roots[key], key, ())
+        recut(roots[key])
+    return roots
+
+
+def _clusters_of(node, W):
+    cl = {}
+    for i in range(W):
+        if node.pts[i]:
+            a = np.asarray(node.pts[i], np.float64)
+            cl[i] = (a.T @ a, a.sum(0), len(a))
+    return cl
+
+
+def voxelize_literal(scans, poses, voxel_size=1.0, eigen_ratio=EIGEN_RATIO_DEFAULT, layer_limit=LAYER_LIMIT, min_ps=MIN_PS):
+    """tras_opt over the literal tree (:466-474): PLANE nodes, pushed when seen from >= 2 poses."""
+    roots = build_tree_literal(scans, poses, voxel_size, eigen_ratio, layer_limit, min_ps)
+    out = []
+
+    def tras_opt(node, key, path):
+        if node.state == "PLANE":
+            _emit(out, key, path, node.layer, node.clusters, node.plane)
+        else:
+            for leaf in sorted(node.leaves):
+                tras_opt(node.leaves[leaf], key, path + (leaf,))
+
+    for key in sorted(roots):
+        tras_opt(roots[key], key, ())
     return _pack(out)
+
+
+def plane_lookup_literal(roots, X, voxel_size=1.0, layer_limit=LAYER_LIMIT):
+    """recompute_local_planes, src/lvba_system.cpp:1529-1566, with OCTO_TREE_NODE::findCorrespondPoint (bavoxel.hpp:320-333):
+    (n, d) of the PLANE node a world point falls in, zeros when there is none.  X: (n, 3).  Returns (n, 4)."""
+    X = np.asarray(X, np.float64).reshape(-1, 3)
+    out = np.zeros((len(X), 4))
+    for pi, x in enumerate(X):
+        if not np.all(np.isfinite(x)):                                     # :1532-1534
+            continue
+        loc = (x / voxel_size).astype(np.float32)                          # :1537-1541 (float; `-= 1.0f`)
+        loc = np.where(loc < 0, loc - np.float32(1.0), loc).astype(np.float32)
+        key = tuple(int(k) for k in np.trunc(loc).astype(np.int64))
+        node = roots.get(key)
+        if node is None:                                                   # :1546-1549
+            continue
+        while not (node.state == "PLANE" or node.layer >= layer_limit):    # findCorrespondPoint
+            leaf, _ = _octant(x, node.centre)
+            nxt = node.leaves.get(int(leaf))
+            if nxt is None:
+                break
+            node = nxt
+        if node.state != "PLANE":                                          # :1552-1554
+            continue
+        direct, centre = node.plane[2], node.plane[1]
+        if not np.all(np.isfinite(direct)) or np.linalg.norm(direct) < 1e-6 or not np.all(np.isfinite(centre)):
+            continue
+        n = direct / np.linalg.norm(direct)                                # :1560-1563
+        out[pi, :3] = n; out[pi, 3] = -n @ centre
+    return out

@@ -1,0 +1,86 @@
+// voxel_emu.cpp — TEST INFRASTRUCTURE: runs the voxel-map pipeline of global-lvba_b200/csrc/voxel_pipeline.h with a
+// sequential host execution policy, so that the logic every CUDA pass executes (keys, stable sort order, segment sums,
+// node states, emission order, plane lookup) is checked against oracle/voxel_oracle.py on a machine without a GPU.
+// Built by tests/test_voxel_emu.py with g++ -ffp-contract=off; never part of liblvba_b200.so — the product
+// instantiates the pipeline with the CUDA policy only (voxel_api.cuh) and has no host path.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../global-lvba_b200/csrc/voxel_pipeline.h"
+
+namespace {
+
+struct HostExec {
+  template <class T>
+  struct Buf {
+    T* p = nullptr;
+    size_t n = 0;
+    std::vector<T> v;
+    int alloc(size_t count) { v.assign(count, T()); p = v.data(); n = count; return 0; }
+  };
+  template <class F>
+  int for_each(int64_t n, const F& f) { for (int64_t i = 0; i < n; ++i) f(i); return 0; }
+  template <class T>
+  int fill_zero(T* p, size_t n) { std::memset(p, 0, n * sizeof(T)); return 0; }
+  template <class T>
+  int fetch(T* host, const T* dev, size_t n) { std::memcpy(host, dev, n * sizeof(T)); return 0; }
+  int min_max(const int32_t* p, int64_t n, int32_t* mn, int32_t* mx) {
+    *mn = *std::min_element(p, p + n); *mx = *std::max_element(p, p + n); return 0;
+  }
+  int sort_pairs(const uint64_t* kin, uint64_t* kout, const uint32_t* vin, uint32_t* vout, int64_t n, int end_bit) {
+    const uint64_t mask = end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1);
+    std::vector<int64_t> perm((size_t)n);
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](int64_t a, int64_t b) { return (kin[a] & mask) < (kin[b] & mask); });
+    for (int64_t i = 0; i < n; ++i) { kout[i] = kin[perm[i]]; vout[i] = vin[perm[i]]; }
+    return 0;
+  }
+  template <class T>
+  int exclusive_scan(const T* in, T* out, int64_t n) { T acc = 0; for (int64_t i = 0; i < n; ++i) { const T v = in[i]; out[i] = acc; acc += v; } return 0; }
+  int sync() { return 0; }
+};
+
+using Map = lvba::vox::VoxelMap<HostExec>;
+
+}  // namespace
+
+extern "C" {
+
+int emu_voxel_map_create(int32_t W, const int64_t* scan_ptr, const float* xyz, const double* poses, double voxel_size,
+                         const float* eigen_ratio, int32_t layer_limit, int32_t min_points, void** out) {
+  Map* m = new Map();
+  lvba::vox::VoxParams prm{voxel_size, {eigen_ratio[0], eigen_ratio[1], eigen_ratio[2], eigen_ratio[3]}, layer_limit, min_points};
+  const int rc = m->build(xyz, scan_ptr, poses, W, scan_ptr[W], prm);
+  if (rc != 0) { delete m; return rc; }
+  *out = m;
+  return 0;
+}
+
+int emu_voxel_map_sizes(void* h, int64_t* n_voxels, int64_t* nnz, int64_t* n_nodes) {
+  Map* m = (Map*)h;
+  *n_voxels = m->V; *nnz = m->nnz;
+  for (int L = 0; L < 3; ++L) n_nodes[L] = L < m->n_layers ? m->layer[L].n_nodes : 0;
+  return 0;
+}
+
+int emu_voxel_map_export(void* h, int64_t* vox_ptr, int32_t* pose_idx, double* clusters, int64_t* root_key, int8_t* path,
+                         double* centre, double* normal, double* eigenvalues) {
+  Map* m = (Map*)h;
+  std::memcpy(vox_ptr, m->vox_ptr.p, (size_t)(m->V + 1) * sizeof(int64_t));
+  std::memcpy(pose_idx, m->vox_pose.p, (size_t)m->nnz * sizeof(int32_t));
+  std::memcpy(clusters, m->vox_cluster.p, (size_t)m->nnz * 10 * sizeof(double));
+  std::memcpy(root_key, m->vox_root.p, (size_t)m->V * 3 * sizeof(int64_t));
+  std::memcpy(path, m->vox_path.p, (size_t)m->V * 3);
+  std::memcpy(centre, m->vox_centre.p, (size_t)m->V * 3 * sizeof(double));
+  std::memcpy(normal, m->vox_direct.p, (size_t)m->V * 3 * sizeof(double));
+  std::memcpy(eigenvalues, m->vox_eig.p, (size_t)m->V * 3 * sizeof(double));
+  return 0;
+}
+
+int emu_voxel_map_lookup(void* h, int64_t n, const double* X, double* plane_nd) { return ((Map*)h)->lookup(n, X, plane_nd); }
+
+int emu_voxel_map_destroy(void* h) { delete (Map*)h; return 0; }
+
+}  // extern "C"

@@ -87,3 +87,30 @@ def test_window_batch_argument_checks_need_no_gpu(pkg):
         with pytest.raises(pkg.LvbaError) as e:
             pkg.lidar_lm_batch(wp, np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros((0, 10)), p_)
         assert e.value.status == -2                                          # no CPU fallback
+
+
+def test_voxel_map_argument_checks_need_no_gpu(pkg):
+    """lvba_voxel_map_create validates scans / options on the host; without a device it then refuses (no CPU path)."""
+    o = pkg.voxel_default_opts()
+    assert (o.voxel_size, o.layer_limit, o.min_points) == (1.0, 2, 15)                    # bavoxel.hpp:13,24
+    assert [round(float(x), 6) for x in o.eigen_ratio] == [0.3, 0.1, 0.06, 0.03]          # bavoxel.hpp:17
+    scans = [np.zeros((4, 3), np.float32), np.ones((5, 3), np.float32)]
+    poses = np.tile(np.concatenate([np.eye(3).ravel(), np.zeros(3)]), (2, 1))
+    for kw in (dict(voxel_size=0.0), dict(voxel_size=float("nan")), dict(min_points=-1), dict(eigen_ratio=(0.3, -1, 0.06, 0.03))):
+        with pytest.raises(pkg.LvbaError) as e:
+            pkg.VoxelMap(scans, poses, **kw)
+        assert e.value.status == -1
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.VoxelMap(scans, poses, layer_limit=3)
+    assert e.value.status == -4
+    with pytest.raises(pkg.LvbaError) as e:                                               # non-monotone scan table
+        pkg.VoxelMap(np.zeros((9, 3), np.float32), poses, scan_ptr=[0, 6, 4])
+    assert e.value.status == -1
+    bad = poses.copy(); bad[1, 4] = np.inf
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.VoxelMap(scans, bad)
+    assert e.value.status == -1
+    if pkg.device_count() == 0:
+        with pytest.raises(pkg.LvbaError) as e:
+            pkg.VoxelMap(scans, poses)
+        assert e.value.status == -2

@@ -9,24 +9,7 @@ from oracle import synth
 from oracle import voxel_oracle as vox
 
 
-def _scene(seed, W=5, n_per_scan=2500):
-    """A corner of a room (floor + two walls, 1 cm noise) and some clutter, seen from W nearby poses; float32 body frame."""
-    rng = np.random.default_rng(seed)
-    poses = np.zeros((W, 12))
-    scans = []
-    for i in range(W):
-        R = synth.so3_exp(rng.normal(0, 0.05, (1, 3)))[0]
-        p = np.array([0.4 * i - 1.0, 0.3 * np.sin(i), 0.1 * i]) + rng.normal(0, 0.02, 3)
-        poses[i, :9] = R.ravel(); poses[i, 9:] = p
-        k = n_per_scan
-        u = rng.uniform(-3, 3, (k, 2)); kind = rng.integers(0, 4, k)
-        w = np.zeros((k, 3))
-        w[kind == 0] = np.column_stack([u[kind == 0], -1.2 + rng.normal(0, 0.01, (kind == 0).sum())])               # floor z = -1.2
-        w[kind == 1] = np.column_stack([np.full((kind == 1).sum(), 2.6) + rng.normal(0, 0.01, (kind == 1).sum()), u[kind == 1]])   # wall x = 2.6
-        w[kind == 2] = np.column_stack([u[kind == 2][:, 0], np.full((kind == 2).sum(), -2.4) + rng.normal(0, 0.01, (kind == 2).sum()), u[kind == 2][:, 1]])
-        w[kind == 3] = rng.uniform(-3, 3, ((kind == 3).sum(), 3))                                                  # clutter
-        scans.append(((w - p) @ R).astype(np.float32))                                                            # R^T (w - p)
-    return scans, poses
+_scene = synth.make_scan_scene
 
 
 @pytest.mark.parametrize("seed,voxel_size", [(1, 1.0), (2, 0.5), (3, 2.0)])
