@@ -8,6 +8,9 @@
 //   lvba_b200::solve_visual(...)                     replaces the Ceres block       src/lvba_system.cpp:1571-1656
 //   lvba_b200::WindowBatch                           collects the windows of runWindowBA (src/lvba_system.cpp:232-302) and
 //                                                    solves them in one lvba_lidar_lm_batch call
+//   lvba_b200::SurfMap                               replaces the surf_map built by cut_voxel + recut (+ tras_opt) in front of
+//                                                    every solve (src/lvba_system.cpp:247-258, 361-378, 1498-1506) and the
+//                                                    plane lookup of recompute_local_planes (:1529-1566)
 //
 // Same names, argument meaning and error behaviour as the reference: void-like use (the reference ignores
 // solver failure), state written back only on success, size mismatches throw std::runtime_error like
@@ -119,6 +122,101 @@ class WindowBatch {
   std::vector<int32_t> pose_idx_;
   std::vector<double> clusters_, poses_;
   std::vector<PoseVec*> targets_;
+};
+
+// ---- B3: the adaptive voxel map.  The reference fills an unordered_map<VOXEL_LOC, OCTO_TREE_ROOT*> with one
+//      cut_voxel call per scan, then recut()s every root and walks it with tras_opt (BA voxels) or
+//      findCorrespondPoint (plane of a landmark).  SurfMap takes the same inputs — the scans as
+//      pcl::PointCloud<PointType>::Ptr-like handles (anything with ->points[k].x/.y/.z and ->points.size()), the poses,
+//      the root voxel size and the eigen-ratio array — builds the map on the device and keeps it there.
+template <class PoseVec>
+class SurfMap {
+ public:
+  SurfMap() = default;
+  SurfMap(const SurfMap&) = delete;
+  SurfMap& operator=(const SurfMap&) = delete;
+  ~SurfMap() { clear(); }
+  void clear() { if (map_) lvba_voxel_map_destroy(map_); map_ = nullptr; }
+
+  // cut_voxel(surf_map, *clouds[j], x_buf[j], j, win_size, voxel_size, eigen_ratio) for every j, then recut(x_buf).
+  // eigen_ratio_array: the four per-layer thresholds in force (set_eigen_ratio_array, src/lvba_system.cpp:360).
+  template <class CloudPtrVec>
+  int build(const CloudPtrVec& clouds, const PoseVec& x_buf, double voxel_size, const float eigen_ratio_array[4],
+            lvba_voxel_summary* summary = nullptr) {
+    clear();
+    const int W = (int)clouds.size();
+    if ((int)x_buf.size() < W) throw std::runtime_error("lvba_b200::SurfMap::build: fewer poses than scans");
+    std::vector<int64_t> scan_ptr((size_t)W + 1, 0);
+    for (int j = 0; j < W; ++j) scan_ptr[j + 1] = scan_ptr[j] + (int64_t)clouds[j]->points.size();
+    std::vector<float> xyz((size_t)scan_ptr[W] * 3);
+    for (int j = 0; j < W; ++j) {
+      float* dst = xyz.data() + 3 * (size_t)scan_ptr[j];
+      for (const auto& pt : clouds[j]->points) { *dst++ = pt.x; *dst++ = pt.y; *dst++ = pt.z; }
+    }
+    std::vector<double> poses((size_t)W * 12);
+    for (int i = 0; i < W; ++i) {
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) poses[12 * i + 3 * r + c] = x_buf[i].R(r, c);
+      for (int r = 0; r < 3; ++r) poses[12 * i + 9 + r] = x_buf[i].p(r);
+    }
+    lvba_voxel_opts o;
+    lvba_voxel_default_opts(&o);
+    o.voxel_size = voxel_size;
+    for (int k = 0; k < 4; ++k) o.eigen_ratio[k] = eigen_ratio_array[k];
+    win_size_ = W;
+    return lvba_voxel_map_create(W, scan_ptr.data(), xyz.data(), 3, poses.data(), &o, &map_, summary);
+  }
+
+  // tras_opt(voxhess) + BALM2::damping_iter(x_stats, voxhess) on the map's plane voxels.  min_voxels_per_pose mirrors the
+  // caller's `plvec_voxels.size() < 3 * x_win.size()` skip (src/lvba_system.cpp:262-266): returns LVBA_OK with
+  // summary->termination = LVBA_TERM_SKIPPED and x_stats untouched when there are too few voxels.
+  int damping_iter(PoseVec& x_stats, int min_voxels_per_pose = 0, const lvba_lidar_opts* opts = nullptr, lvba_summary* summary = nullptr) {
+    if (!map_) throw std::runtime_error("lvba_b200::SurfMap::damping_iter: map not built");
+    if ((int)x_stats.size() < win_size_) throw std::runtime_error("lvba_b200::SurfMap::damping_iter: x_stats smaller than win_size");
+    lvba_voxel_summary vs;
+    int rc = lvba_voxel_map_summary(map_, &vs);
+    if (rc != LVBA_OK) return rc;
+    if (vs.n_voxels < (int64_t)min_voxels_per_pose * win_size_) {
+      if (summary) { *summary = lvba_summary{}; summary->termination = LVBA_TERM_SKIPPED; }
+      return LVBA_OK;
+    }
+    std::vector<int64_t> vox_ptr((size_t)vs.n_voxels + 1);
+    std::vector<int32_t> pose_idx((size_t)vs.nnz);
+    std::vector<double> clusters((size_t)vs.nnz * 10), poses((size_t)win_size_ * 12);
+    rc = lvba_voxel_map_export(map_, vox_ptr.data(), pose_idx.data(), clusters.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc != LVBA_OK) return rc;
+    for (int i = 0; i < win_size_; ++i) {
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) poses[12 * i + 3 * r + c] = x_stats[i].R(r, c);
+      for (int r = 0; r < 3; ++r) poses[12 * i + 9 + r] = x_stats[i].p(r);
+    }
+    rc = lvba_lidar_lm(win_size_, vs.n_voxels, vox_ptr.data(), pose_idx.data(), clusters.data(), poses.data(), opts, summary);
+    if (rc != LVBA_OK) return rc;
+    for (int i = 0; i < win_size_; ++i) {
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) x_stats[i].R(r, c) = poses[12 * i + 3 * r + c];
+      for (int r = 0; r < 3; ++r) x_stats[i].p(r) = poses[12 * i + 9 + r];
+    }
+    return LVBA_OK;
+  }
+
+  // recompute_local_planes (src/lvba_system.cpp:1529-1566): plane_n[pi], plane_d[pi] of the PLANE node Xs[pi] falls in,
+  // zeros when there is none.
+  int recompute_local_planes(const std::vector<std::array<double, 3>>& Xs, std::vector<std::array<double, 3>>& plane_n,
+                             std::vector<double>& plane_d) {
+    if (!map_) throw std::runtime_error("lvba_b200::SurfMap::recompute_local_planes: map not built");
+    const int64_t n = (int64_t)Xs.size();
+    std::vector<double> nd((size_t)n * 4);
+    const int rc = lvba_voxel_map_lookup(map_, n, n ? Xs[0].data() : nullptr, nd.data());
+    if (rc != LVBA_OK) return rc;
+    plane_n.resize((size_t)n); plane_d.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) { plane_n[i] = {nd[4 * i], nd[4 * i + 1], nd[4 * i + 2]}; plane_d[i] = nd[4 * i + 3]; }
+    return LVBA_OK;
+  }
+
+  int64_t voxels() const { lvba_voxel_summary vs{}; return map_ && lvba_voxel_map_summary(map_, &vs) == LVBA_OK ? vs.n_voxels : 0; }
+  lvba_voxel_map* handle() const { return map_; }
+
+ private:
+  lvba_voxel_map* map_ = nullptr;
+  int win_size_ = 0;
 };
 
 // ---- B2: the flat arrays optimizeCameraPoses already builds (qs, ts, Xs, plane_n, plane_d) plus the

@@ -10,8 +10,53 @@ struct V3 { double v[3]; double& operator()(int r) { return v[r]; } double opera
 struct IMUST { M3 R; V3 p; };
 struct PointCluster { M3 P{}; V3 v{}; int N = 0; void push(const double* x) { ++N; for (int i = 0; i < 3; ++i) { v.v[i] += x[i]; for (int j = 0; j < 3; ++j) P.m[3 * i + j] += x[i] * x[j]; } } };
 struct VOX_HESS { std::vector<const std::vector<PointCluster>*> plvec_voxels; int win_size; };
+struct PointXYZINormal { float x, y, z, pad0, nx, ny, nz, pad1, intensity, curvature, pad2, pad3; };   // 48 B, like PCL's
+struct Cloud { std::vector<PointXYZINormal> points; };
 
-int main() {
+// B3: raw scans of two perpendicular walls and a floor -> SurfMap -> damping_iter / plane lookup
+static int surf_map_case() {
+  const int W = 3;
+  std::vector<IMUST> xs(W);
+  std::vector<Cloud> store(W);
+  std::vector<Cloud*> clouds;
+  unsigned s = 777;
+  auto rnd = [&] { s = s * 1664525u + 1013904223u; return (double)(s >> 8) / (1u << 24) - 0.5; };
+  for (int i = 0; i < W; ++i) {
+    xs[i].R = M3{{1, 0, 0, 0, 1, 0, 0, 0, 1}}; xs[i].p = V3{{0.3 * i, 0.0, 0.0}};
+    for (int k = 0; k < 6000; ++k) {
+      double w[3] = {4.0 * rnd(), 4.0 * rnd(), 4.0 * rnd()};
+      w[k % 3] = (k % 3 == 0 ? 1.9 : k % 3 == 1 ? -1.7 : -1.2) + 0.01 * rnd();
+      PointXYZINormal p{};
+      p.x = (float)(w[0] - 0.3 * i); p.y = (float)w[1]; p.z = (float)w[2];
+      store[i].points.push_back(p);
+    }
+    clouds.push_back(&store[i]);
+  }
+  const float ratios[4] = {0.3f, 0.1f, 0.06f, 0.03f};
+  lvba_b200::SurfMap<std::vector<IMUST>> map;
+  lvba_voxel_summary vs{};
+  int rc = map.build(clouds, xs, 1.0, ratios, &vs);
+  if (rc == LVBA_ERR_NO_DEVICE) return 2;
+  if (rc != LVBA_OK) { std::printf("surf map error %d: %s\n", rc, lvba_last_error()); return 1; }
+  if (vs.n_points != 3 * 6000 || vs.n_voxels < 10) { std::printf("surf map: %lld voxels\n", (long long)vs.n_voxels); return 1; }
+  for (int i = 1; i < W; ++i) xs[i].p(1) += 0.02;                            // perturb, then let the LM pull it back
+  lvba_summary sum{};
+  rc = map.damping_iter(xs, 3, nullptr, &sum);
+  if (rc != LVBA_OK || !(sum.cost_last < sum.cost_first)) { std::printf("surf map LM error %d\n", rc); return 1; }
+  std::vector<std::array<double, 3>> Xs = {{0.5, 0.5, -1.2}, {1.9, 0.3, 0.4}, {50.0, 50.0, 50.0}}, pn;
+  std::vector<double> pd;
+  rc = map.recompute_local_planes(Xs, pn, pd);
+  if (rc != LVBA_OK) return 1;
+  const bool floor_ok = std::fabs(std::fabs(pn[0][2]) - 1.0) < 1e-2 && std::fabs(std::fabs(pd[0]) - 1.2) < 5e-2;
+  const bool wall_ok = std::fabs(std::fabs(pn[1][0]) - 1.0) < 1e-2 && std::fabs(std::fabs(pd[1]) - 1.9) < 5e-2;
+  const bool none_ok = pn[2][0] == 0 && pn[2][1] == 0 && pn[2][2] == 0 && pd[2] == 0;
+  std::printf("surf map ok: %lld voxels from %lld points, LM %.3e -> %.3e, planes %d%d%d\n", (long long)vs.n_voxels,
+              (long long)vs.n_points, sum.cost_first, sum.cost_last, (int)floor_ok, (int)wall_ok, (int)none_ok);
+  return (floor_ok && wall_ok && none_ok) ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && std::string(argv[1]) == "surfmap") return surf_map_case();     // B3, run by tests/test_zz_voxel_gpu.py
   const int W = 4;
   std::vector<IMUST> xs(W);
   for (int i = 0; i < W; ++i) { xs[i].R = M3{{1, 0, 0, 0, 1, 0, 0, 0, 1}}; xs[i].p = V3{{0.5 * i, 0.01 * i, 0}}; }

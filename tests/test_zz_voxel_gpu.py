@@ -164,3 +164,18 @@ def test_large_map_invariants():
     assert np.count_nonzero(np.any(nd != 0, axis=1)) >= 0.9 * V
     m.close()
     """, timeout=600)
+
+
+@pytest.mark.gpu
+def test_shim_surf_map(tmp_path):
+    """The C++ mirror of the reference call sites (lvba_b200::SurfMap, host/lvba_shim.hpp): scans -> map -> LM -> planes."""
+    sys.path.insert(0, str(ROOT))
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    exe = tmp_path / "test_shim"
+    cmd = ["g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), str(ROOT / "tests" / "shim" / "test_shim.cpp"),
+           "-o", str(exe), str(pkg.LIB_PATH), f"-Wl,-rpath,{pkg.LIB_PATH.parent}", "-L/usr/local/cuda/lib64", "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), "surfmap"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "surf map ok" in r.stdout, r.stdout + r.stderr
