@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--config", default="C", choices=["A", "B", "C", "E"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-voxel-map", action="store_true", help="skip the boundary-B3 (voxel map) side measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -312,6 +313,16 @@ def main():
             line["cpu_baseline"] = {"value": 1e3 / (tA + tB), "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "2 LM passes of path A + 2 of path B on the full problem (oracle/cpu_ref.cpp), per-pass time with Hessian build",
                                     "ms_A": tA, "ms_B": tB}
+        if world == 1 and not args.no_voxel_map:
+            # Boundary B3 (set-up stage) measured OUTSIDE the timed region, in a child process so that
+            # nothing it does can disturb the numbers above; reported next to them, not part of `value` / `e2e`.
+            import subprocess
+            try:
+                r = subprocess.run([sys.executable, str(ROOT / "tools" / "bench_voxel_map.py")], capture_output=True, text=True, timeout=300)
+                last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                line["voxel_map"] = json.loads(last[-1]) if last else {"error": (r.stderr or r.stdout)[-400:], "rc": r.returncode}
+            except Exception as e:          # noqa: BLE001 - a side measurement must never take the bench line down
+                line["voxel_map"] = {"error": repr(e)[:400]}
         print(json.dumps(line), flush=True)
     L.close(); Vz.close()
     if world > 1:

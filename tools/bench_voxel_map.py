@@ -1,0 +1,108 @@
+"""Boundary B3 measured on one GPU: raw scans -> device voxel map (lvba_voxel_map_create) -> plane voxels, and the
+plane lookup.  Prints ONE JSON line.  bench.py runs this as a child process after its own timed region (rank 0, N = 1)
+and attaches the line as `voxel_map`; it can also be run directly:
+
+    python tools/bench_voxel_map.py [--scans 400] [--points 50000] [--voxel-size 1.0] [--repeats 3]
+
+Workload (synthetic, seeded): a vehicle driving 0.5 m per scan along a street — ground plane, two facades 8 m to
+either side, 10 % clutter — every scan sees the surfaces within 30 m.  20 M points by default (config C of the LM
+bench corresponds to ~34 M).  Times: `ms_device` = CUDA events around the build passes inside the library,
+`ms_call` = the whole ABI call from host memory (validation, H2D, build), best of `repeats` after one warm-up.
+The CPU figure next to it is oracle/voxel_oracle.py (numpy group-by restatement, one thread) on a bounded sample."""
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+
+def street_scans(n_scans, n_points, seed=0):
+    rng = np.random.default_rng(seed)
+    poses = np.zeros((n_scans, 12))
+    scan_ptr = np.arange(n_scans + 1, dtype=np.int64) * n_points
+    xyz = np.empty((n_scans * n_points, 3), np.float32)
+    for i in range(n_scans):
+        yaw = 0.02 * np.sin(0.05 * i)
+        c, s = np.cos(yaw), np.sin(yaw)
+        R = np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+        p = np.array([0.5 * i, 0.3 * np.sin(0.02 * i), 0.0])
+        poses[i, :9] = R.ravel(); poses[i, 9:] = p
+        kind = rng.integers(0, 10, n_points)
+        w = np.empty((n_points, 3))
+        r = 30.0 * np.sqrt(rng.uniform(0, 1, n_points)); a = rng.uniform(0, 2 * np.pi, n_points)
+        w[:, 0] = p[0] + r * np.cos(a); w[:, 1] = p[1] + r * np.sin(a); w[:, 2] = -1.37 + rng.normal(0, 0.01, n_points)      # ground
+        wall = (kind >= 5) & (kind < 9)
+        nw = int(wall.sum())
+        w[wall, 0] = p[0] + rng.uniform(-30, 30, nw)
+        w[wall, 1] = np.where(rng.integers(0, 2, nw) == 0, -7.73, 7.73) + rng.normal(0, 0.01, nw)
+        w[wall, 2] = rng.uniform(-1.37, 4.0, nw)
+        cl = kind == 9
+        w[cl] = p + rng.uniform(-20, 20, (int(cl.sum()), 3))
+        xyz[i * n_points:(i + 1) * n_points] = ((w - p) @ R).astype(np.float32)
+    return xyz, scan_ptr, poses
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scans", type=int, default=400)
+    ap.add_argument("--points", type=int, default=50000)
+    ap.add_argument("--voxel-size", type=float, default=1.0)
+    ap.add_argument("--repeats", type=int, default=3)
+    ap.add_argument("--queries", type=int, default=200000)
+    ap.add_argument("--cpu-sample-scans", type=int, default=8)
+    args = ap.parse_args()
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    pkg.load_library()
+    if pkg.device_count() < 1:
+        print(json.dumps({"error": "no CUDA device (no CPU fallback)"})); return 1
+    xyz, scan_ptr, poses = street_scans(args.scans, args.points)
+    N = len(xyz)
+    best_call, best_dev, summ, g = 1e30, 1e30, None, None
+    for rep in range(args.repeats + 1):
+        t0 = time.perf_counter()
+        m = pkg.VoxelMap(xyz, poses, args.voxel_size, scan_ptr=scan_ptr)
+        dt = (time.perf_counter() - t0) * 1e3
+        if rep > 0:
+            best_call = min(best_call, dt); best_dev = min(best_dev, m.summary["ms_device"])
+        summ = m.summary
+        if rep < args.repeats:
+            m.close()
+    g = m.export()
+    vp, pi, cl = g["vox_ptr"], g["pose_idx"], g["clusters"]
+    V = len(vp) - 1
+    checks = {"every voxel seen from >= 2 poses": bool(np.all(np.diff(vp) >= 2)),
+              "min_ps points per voxel": bool(np.all(np.add.reduceat(cl[:, 9], vp[:-1]) >= 15)) if V else True,
+              "keys ascending": bool(np.all(np.diff(g["key"][:, 0]) >= 0)),
+              "points conserved (<= input)": bool(cl[:, 9].sum() <= N)}
+    rng = np.random.default_rng(1)
+    X = np.column_stack([rng.uniform(0, 0.5 * args.scans, args.queries), rng.uniform(-9, 9, args.queries), rng.uniform(-2, 4, args.queries)])
+    m.lookup(X[:1000])
+    t0 = time.perf_counter(); nd = m.lookup(X); t_lookup = (time.perf_counter() - t0) * 1e3
+    m.close()
+    # CPU restatement on a bounded sample (first scans only)
+    cpu = None
+    if args.cpu_sample_scans > 0:
+        from oracle import voxel_oracle as vox
+        k = min(args.cpu_sample_scans, args.scans)
+        scans = [xyz[scan_ptr[j]:scan_ptr[j + 1]] for j in range(k)]
+        t0 = time.perf_counter(); vox.voxelize(scans, poses[:k], args.voxel_size); tc = time.perf_counter() - t0
+        cpu = {"points_per_s": k * args.points / tc, "kind": "port (numpy, 1 thread)", "sample": f"{k} scans x {args.points} points"}
+    out = {"workload": f"{args.scans} scans x {args.points} points (street scene), root voxel {args.voxel_size} m, layer_limit 2",
+           "n_points": int(N), "n_voxels": int(summ["n_voxels"]), "nnz": int(summ["nnz"]), "n_nodes": summ["n_nodes"],
+           "ms_device": best_dev, "ms_call": best_call, "points_per_s_device": N / (best_dev * 1e-3), "points_per_s_call": N / (best_call * 1e-3),
+           "algorithmic_GBps_device": (12.0 * N + 80.0 * summ["nnz"]) / (best_dev * 1e-3) / 1e9,
+           "h2d_bytes": int(summ["h2d_bytes"]), "kernel_launches": int(summ["kernel_launches"]),
+           "lookup": {"queries": int(args.queries), "ms_call": t_lookup, "hit_fraction": float(np.mean(np.any(nd != 0, axis=1)))},
+           "checks": checks, "cpu": cpu}
+    print(json.dumps(out), flush=True)
+    return 0 if all(checks.values()) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
