@@ -62,3 +62,21 @@ def test_threshold_and_layer_limit():
     coarse = vox.voxelize(scans, poses, 1.0, layer_limit=0)
     full = vox.voxelize(scans, poses, 1.0, layer_limit=2)
     assert np.all(coarse[3]["layer"] == 0) and len(full[0]) >= len(coarse[0])
+
+
+def test_golden_fixture_is_reproduced():
+    """tests/golden/voxel_scene.npz (literal restatement, committed) against the vectorised restatement run now."""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "voxel_scene.npz")
+    sp = g["scan_ptr"]
+    scans = [g["xyz"][sp[j]:sp[j + 1]] for j in range(len(sp) - 1)]
+    layers = set()
+    for tag, vs in zip("ab", g["voxel_sizes"]):
+        vp, pi, cl, meta = vox.voxelize(scans, g["poses"], float(vs))
+        assert np.array_equal(vp, g[f"vox_ptr_{tag}"]) and np.array_equal(pi, g[f"pose_idx_{tag}"])
+        assert np.array_equal(meta["key"], g[f"key_{tag}"]) and np.array_equal(meta["layer"], g[f"path_{tag}"][:, 0])
+        assert np.abs(cl - g[f"clusters_{tag}"]).max() <= 1e-9 * np.abs(cl).max()
+        roots = vox.build_tree_literal(scans, g["poses"], float(vs))
+        assert np.array_equal(vox.plane_lookup_literal(roots, g["X"], float(vs)), g[f"plane_nd_{tag}"])
+        layers |= set(meta["layer"].tolist())
+    assert layers == {0, 1, 2}

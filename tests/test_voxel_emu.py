@@ -183,3 +183,23 @@ def test_negative_coordinates_and_key_order(emu):
     k = got["key"]
     assert np.any(k[:, 0] < 0) and np.all(np.diff(k[:, 0]) >= 0)
     m.close()
+
+
+def golden_case(tag):
+    g = np.load(ROOT / "tests" / "golden" / "voxel_scene.npz")
+    sp = g["scan_ptr"]
+    scans = [g["xyz"][sp[j]:sp[j + 1]] for j in range(len(sp) - 1)]
+    path = g[f"path_{tag}"]
+    meta = dict(key=g[f"key_{tag}"], layer=path[:, 0].astype(np.int32), path=[tuple(int(x) for x in r[1:1 + r[0]]) for r in path],
+                centre=g[f"centre_{tag}"], direct=g[f"direct_{tag}"], eigenvalues=g[f"eigenvalues_{tag}"])
+    ref = (g[f"vox_ptr_{tag}"], g[f"pose_idx_{tag}"], g[f"clusters_{tag}"], meta)
+    return scans, g["poses"], float(g["voxel_sizes"]["ab".index(tag)]), ref, g["X"], g[f"plane_nd_{tag}"]
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_pipeline_equals_golden_fixture(emu, tag):
+    scans, poses, voxel_size, ref, X, plane_nd = golden_case(tag)
+    m = EmuMap(emu, scans, poses, voxel_size)
+    compare_with_oracle(m.export(), ref)
+    compare_lookup(m.lookup(X), plane_nd)
+    m.close()

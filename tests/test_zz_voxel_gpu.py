@@ -68,6 +68,23 @@ def test_voxel_map_equals_oracle():
 
 
 @pytest.mark.gpu
+def test_voxel_map_equals_golden_fixture():
+    """Committed known-answer vectors (tests/golden/voxel_scene.npz): planes at every octree layer + plane lookups."""
+    _run("""
+    g = np.load("tests/golden/voxel_scene.npz")
+    sp = g["scan_ptr"]
+    for tag, vs in zip("ab", g["voxel_sizes"]):
+        path = g[f"path_{tag}"]
+        meta = dict(key=g[f"key_{tag}"], layer=path[:, 0].astype(np.int32), path=[tuple(int(x) for x in r[1:1 + r[0]]) for r in path],
+                    centre=g[f"centre_{tag}"], direct=g[f"direct_{tag}"], eigenvalues=g[f"eigenvalues_{tag}"])
+        m = pkg.VoxelMap(g["xyz"], g["poses"], float(vs), scan_ptr=sp)
+        compare_with_oracle(m.export(), (g[f"vox_ptr_{tag}"], g[f"pose_idx_{tag}"], g[f"clusters_{tag}"], meta))
+        compare_lookup(m.lookup(g["X"]), g[f"plane_nd_{tag}"])
+        m.close()
+    """)
+
+
+@pytest.mark.gpu
 def test_voxel_map_edge_cases():
     _run("""
     scans, poses = synth.make_scan_scene(9, W=5, n_per_scan=1500)
