@@ -35,7 +35,7 @@ EXPORTS = [
     "lvba_visual_get_state", "lvba_visual_cost", "lvba_visual_step", "lvba_visual_structure",
     "lvba_visual_get_system", "lvba_visual_reset_lm", "lvba_visual_reset_state", "lvba_visual_iterate", "lvba_visual_counts",
     "lvba_voxel_default_opts", "lvba_voxel_map_create", "lvba_voxel_map_summary", "lvba_voxel_map_export",
-    "lvba_voxel_map_lookup", "lvba_voxel_map_destroy",
+    "lvba_voxel_map_lookup", "lvba_voxel_map_lidar_create", "lvba_voxel_map_lidar_lm", "lvba_voxel_map_destroy",
     "lvba_comm_unique_id", "lvba_comm_init", "lvba_comm_destroy", "lvba_comm_info", "lvba_shard_owner",
 ]
 
@@ -191,6 +191,12 @@ class LidarProblem:
         self._h = C.c_void_p()
         _chk(lib.lvba_lidar_create(C.c_int32(self.W), C.c_int64(self.V), _p(self.vp, C.c_int64), _p(self.pi, C.c_int32),
                                    _p(cl, C.c_double), _p(ps, C.c_double), C.c_int32(device), C.byref(self._h)))
+
+    @classmethod
+    def _from_handle(cls, h, W, V):
+        self = cls.__new__(cls)
+        self._lib = load_library(); self._h = h; self.W = W; self.V = V; self.vp = None; self.pi = None
+        return self
 
     def close(self):
         if self._h:
@@ -406,6 +412,22 @@ class VoxelMap:
                                              _p(o["centre"], C.c_double), _p(o["normal"], C.c_double),
                                              _p(o["eigenvalues"], C.c_double)))
         return o
+
+    def lidar_lm(self, poses, min_voxels_per_pose=0, opts=None):
+        """tras_opt + BALM2::damping_iter on the map's voxels without the clusters leaving the device.
+        Returns (poses, summary dict)."""
+        ps = _f64(poses).copy()
+        s = Summary()
+        _chk(self._lib.lvba_voxel_map_lidar_lm(self._h, _p(ps, C.c_double), C.c_int32(min_voxels_per_pose),
+                                               C.byref(opts) if opts is not None else None, C.byref(s)))
+        return ps, s.as_dict()
+
+    def lidar_problem(self, poses):
+        """Device-resident LidarProblem of the map's voxels (lvba_voxel_map_lidar_create)."""
+        ps = _f64(poses)
+        h = C.c_void_p()
+        _chk(self._lib.lvba_voxel_map_lidar_create(self._h, _p(ps, C.c_double), C.byref(h)))
+        return LidarProblem._from_handle(h, ps.shape[0], self.summary["n_voxels"])
 
     def lookup(self, X):
         """recompute_local_planes (lvba_system.cpp:1529-1566): (n, 4) plane (n, d) per world point, zeros when none."""

@@ -191,11 +191,14 @@ inline int lidar_validate(int32_t W, int64_t V, const int64_t* vox_ptr, const in
 
 inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const int32_t* pose_idx,
                              const double* clusters, const double* poses, int32_t device,
-                             lvba_lidar_problem** out, int32_t n_groups = 0, const int32_t* grp_ptr = nullptr) {
+                             lvba_lidar_problem** out, int32_t n_groups = 0, const int32_t* grp_ptr = nullptr,
+                             const double* d_clusters = nullptr) {
+  // d_clusters: the same AoS records already resident on the selected device (a voxel map's export buffer); when set,
+  // `clusters` may be null and no cluster bytes cross PCIe.
   if (!out) return fail(LVBA_ERR_INVALID_ARG, "out is null");
   *out = nullptr;
   const double t_val0 = wall_ms();
-  LVBA_TRY(lidar_validate(W, V, vox_ptr, pose_idx, clusters, poses));
+  LVBA_TRY(lidar_validate(W, V, vox_ptr, pose_idx, d_clusters ? d_clusters : clusters, poses));
   LVBA_TRY(select_device(device));
   const double t0 = wall_ms();
   const bool tlog = getenv("LVBA_SETUP_TIMING") != nullptr;
@@ -308,12 +311,16 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
     DevBuf<double> aos;
     const bool contiguous = Vl == V && n_groups == 0;            // single rank, caller's order: the records go up as they are
     if (contiguous) {
-      LVBA_TRY(aos.alloc((size_t)std::max<long long>(nnz, 1) * 10));
+      const double* aos_src = d_clusters;
+      if (!aos_src) LVBA_TRY(aos.alloc((size_t)std::max<long long>(nnz, 1) * 10));
       if (nnz > 0) {
-        LVBA_CUDA(cudaMemcpyAsync(aos.p, clusters, (size_t)nnz * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (!aos_src) {
+          LVBA_CUDA(cudaMemcpyAsync(aos.p, clusters, (size_t)nnz * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
+          P->h2d += nnz * 80;
+          aos_src = aos.p;
+        }
         std::copy(pose_idx, pose_idx + nnz, l_pidx.begin());
-        P->h2d += nnz * 80;
-        lidar_aos_to_soa_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(nnz, nnz_pad, aos.p, P->cl.p);
+        lidar_aos_to_soa_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(nnz, nnz_pad, aos_src, P->cl.p);
         ++P->launches;
       }
       LVBA_CUDA(cudaStreamSynchronize(s));   // aos is freed on scope exit
@@ -321,17 +328,21 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
       // a shard (or a window-sorted batch) owns scattered voxels: ONE copy of the caller's array + a device-side gather
       // (per-run copies cost ~2.5 us each: 100k runs = 250 ms on a 2-rank split of config C)
       const long long nnz_all = vox_ptr[V];
-      LVBA_TRY(aos.alloc((size_t)std::max<long long>(nnz_all, 1) * 10));
+      const double* aos_src = d_clusters;
+      if (!aos_src) LVBA_TRY(aos.alloc((size_t)std::max<long long>(nnz_all, 1) * 10));
       std::vector<int> src((size_t)nnz);
       long long w = 0;
       for (int64_t i = 0; i < Vl; ++i)
         for (int64_t q = vox_ptr[mine[i]]; q < vox_ptr[mine[i] + 1]; ++q, ++w) { src[w] = (int)q; l_pidx[w] = pose_idx[q]; }
       DevBuf<int> d_src;
       if (nnz > 0) {
-        LVBA_CUDA(cudaMemcpyAsync(aos.p, clusters, (size_t)nnz_all * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (!aos_src) {
+          LVBA_CUDA(cudaMemcpyAsync(aos.p, clusters, (size_t)nnz_all * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
+          P->h2d += nnz_all * 80;
+          aos_src = aos.p;
+        }
         LVBA_TRY(d_src.upload(src, s, &P->h2d));
-        P->h2d += nnz_all * 80;
-        lidar_aos_to_soa_gather_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(nnz, nnz_pad, aos.p, d_src.p, P->cl.p);
+        lidar_aos_to_soa_gather_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(nnz, nnz_pad, aos_src, d_src.p, P->cl.p);
         ++P->launches;
       }
       LVBA_CUDA(cudaStreamSynchronize(s));   // aos, src, d_src are freed on scope exit

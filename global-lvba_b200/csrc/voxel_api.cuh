@@ -7,6 +7,7 @@
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include "lidar_api.cuh"
 #include "runtime.cuh"
 #include "voxel_pipeline.h"
 
@@ -243,6 +244,57 @@ int lvba_voxel_map_lookup(lvba_voxel_map* m, int64_t n, const double* X, double*
   LVBA_CUDA(cudaStreamSynchronize(v.ex.stream));
   m->sum.kernel_launches = v.ex.launches;
   return LVBA_OK;
+}
+
+// tras_opt straight into path A: the map's plane voxels become a device-resident LiDAR problem.  Only the CSR index
+// arrays (12 B per cluster) visit the host, for the symbolic analysis; the 80-byte cluster records stay in HBM.
+int lvba_voxel_map_lidar_create(lvba_voxel_map* m, const double* poses, lvba_lidar_problem** out) {
+  if (!m || !poses || !out) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  LVBA_CUDA(cudaSetDevice(m->device));
+  auto& v = m->map;
+  if (v.W <= 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "the map has no scans");
+  std::vector<int64_t> vox_ptr((size_t)v.V + 1);
+  std::vector<int32_t> pose_idx((size_t)v.nnz);
+  LVBA_CUDA(cudaMemcpyAsync(vox_ptr.data(), v.vox_ptr.p, vox_ptr.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, v.ex.stream));
+  if (v.nnz) LVBA_CUDA(cudaMemcpyAsync(pose_idx.data(), v.vox_pose.p, pose_idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, v.ex.stream));
+  LVBA_CUDA(cudaStreamSynchronize(v.ex.stream));
+  try {
+    return lvba::lidar_create_impl(v.W, v.V, vox_ptr.data(), pose_idx.data(), nullptr, poses, m->device, out, 0, nullptr,
+                                   v.vox_cluster.p);
+  } catch (const std::bad_alloc&) { return lvba::fail(LVBA_ERR_NOMEM, "host allocation failed"); }
+}
+
+// cut_voxel + recut (the map) -> tras_opt + BALM2::damping_iter (this call).  min_voxels_per_pose: the caller-side skip of
+// src/lvba_system.cpp:262-266 (`plvec_voxels.size() < 3 * x_win.size()`): LVBA_OK, LVBA_TERM_SKIPPED, poses untouched.
+int lvba_voxel_map_lidar_lm(lvba_voxel_map* m, double* poses, int32_t min_voxels_per_pose, const lvba_lidar_opts* opts,
+                            lvba_summary* summary) {
+  if (!m || !poses) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  if (min_voxels_per_pose < 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "min_voxels_per_pose must be >= 0");
+  const double t0 = lvba::wall_ms();
+  lvba_lidar_opts o;
+  if (opts) o = *opts; else lvba_lidar_default_opts(&o);
+  lvba_summary s;
+  memset(&s, 0, sizeof s);
+  if (m->map.V < (int64_t)min_voxels_per_pose * m->map.W || m->map.V == 0) {
+    s.termination = LVBA_TERM_SKIPPED;
+    if (summary) *summary = s;
+    return LVBA_OK;
+  }
+  lvba_lidar_problem* p = nullptr;
+  int rc = lvba_voxel_map_lidar_create(m, poses, &p);
+  if (rc != LVBA_OK) return rc;
+  rc = lvba_lidar_reset_lm(p, &o);
+  if (rc == LVBA_OK) rc = lvba_lidar_iterate(p, o.max_iter, &s);
+  if (rc == LVBA_OK) rc = lvba_lidar_get_poses(p, poses);
+  if (rc == LVBA_OK && summary) {
+    *summary = s;
+    summary->ms_setup = p->ms_setup;
+    summary->kernel_launches = p->launches; summary->h2d_bytes = p->h2d; summary->d2h_bytes = p->d2h;
+    summary->ms_total = lvba::wall_ms() - t0;
+  }
+  lvba_lidar_destroy(p);
+  return rc;
 }
 
 int lvba_voxel_map_destroy(lvba_voxel_map* m) {

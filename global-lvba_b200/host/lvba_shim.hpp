@@ -172,24 +172,16 @@ class SurfMap {
   int damping_iter(PoseVec& x_stats, int min_voxels_per_pose = 0, const lvba_lidar_opts* opts = nullptr, lvba_summary* summary = nullptr) {
     if (!map_) throw std::runtime_error("lvba_b200::SurfMap::damping_iter: map not built");
     if ((int)x_stats.size() < win_size_) throw std::runtime_error("lvba_b200::SurfMap::damping_iter: x_stats smaller than win_size");
-    lvba_voxel_summary vs;
-    int rc = lvba_voxel_map_summary(map_, &vs);
-    if (rc != LVBA_OK) return rc;
-    if (vs.n_voxels < (int64_t)min_voxels_per_pose * win_size_) {
-      if (summary) { *summary = lvba_summary{}; summary->termination = LVBA_TERM_SKIPPED; }
-      return LVBA_OK;
-    }
-    std::vector<int64_t> vox_ptr((size_t)vs.n_voxels + 1);
-    std::vector<int32_t> pose_idx((size_t)vs.nnz);
-    std::vector<double> clusters((size_t)vs.nnz * 10), poses((size_t)win_size_ * 12);
-    rc = lvba_voxel_map_export(map_, vox_ptr.data(), pose_idx.data(), clusters.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
-    if (rc != LVBA_OK) return rc;
+    std::vector<double> poses((size_t)win_size_ * 12);
     for (int i = 0; i < win_size_; ++i) {
       for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) poses[12 * i + 3 * r + c] = x_stats[i].R(r, c);
       for (int r = 0; r < 3; ++r) poses[12 * i + 9 + r] = x_stats[i].p(r);
     }
-    rc = lvba_lidar_lm(win_size_, vs.n_voxels, vox_ptr.data(), pose_idx.data(), clusters.data(), poses.data(), opts, summary);
+    lvba_summary local{};
+    const int rc = lvba_voxel_map_lidar_lm(map_, poses.data(), min_voxels_per_pose, opts, &local);   // clusters stay on the device
     if (rc != LVBA_OK) return rc;
+    if (summary) *summary = local;
+    if (local.termination == LVBA_TERM_SKIPPED) return LVBA_OK;
     for (int i = 0; i < win_size_; ++i) {
       for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) x_stats[i].R(r, c) = poses[12 * i + 3 * r + c];
       for (int r = 0; r < 3; ++r) x_stats[i].p(r) = poses[12 * i + 9 + r];

@@ -269,6 +269,15 @@ int lvba_voxel_map_export(lvba_voxel_map* m, int64_t* vox_ptr, int32_t* pose_idx
 /* recompute_local_planes: for n world points X [n*3] the plane (n, d) [n*4] of the PLANE node each one falls in,
  * zeros when there is none — the plane_nd argument of lvba_visual_lm. */
 int lvba_voxel_map_lookup(lvba_voxel_map* m, int64_t n, const double* X, double* plane_nd);
+/* tras_opt straight into B1: the map's plane voxels as a device-resident LiDAR problem (handle API above).  The cluster
+ * records never leave HBM; only the CSR index arrays (12 B per cluster) visit the host for the symbolic analysis.
+ * poses [W*12]: the linearisation point (normally the poses the map was built with). */
+int lvba_voxel_map_lidar_create(lvba_voxel_map* m, const double* poses, lvba_lidar_problem** out);
+/* ... and solved: cut_voxel + recut (the map) -> tras_opt + BALM2::damping_iter (this call), poses [W*12] in/out.
+ * Fewer than min_voxels_per_pose * W voxels (the caller-side rule of src/lvba_system.cpp:262-266; pass 0 for
+ * runLidarBA, which has none) or an empty map: LVBA_OK, LVBA_TERM_SKIPPED, poses untouched. */
+int lvba_voxel_map_lidar_lm(lvba_voxel_map* m, double* poses, int32_t min_voxels_per_pose, const lvba_lidar_opts* opts,
+                            lvba_summary* summary);
 int lvba_voxel_map_destroy(lvba_voxel_map* m);
 
 /* ======================================================================================

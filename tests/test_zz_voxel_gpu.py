@@ -149,6 +149,17 @@ def test_scans_to_lm_chain():
     assert s["cost_last"] < s["cost_first"]
     assert abs(s["cost_last"] - info["r_last"]) <= 1e-6 * info["r_last"]
     assert np.abs(out_gpu - out_ref).max() <= 1e-6
+    # the same solve with the clusters never leaving the device (lvba_voxel_map_lidar_lm): identical input, identical result
+    m = pkg.VoxelMap(scans, noisy)
+    out_dev, s2 = m.lidar_lm(noisy)
+    assert np.abs(out_dev - out_gpu).max() <= 1e-9 and s2["iterations"] == s["iterations"]   # (atomic sums: not bitwise)
+    assert s2["h2d_bytes"] < s["h2d_bytes"] - 70 * len(g["pose_idx"])          # the 80 B records were not uploaded
+    P = m.lidar_problem(noisy)
+    assert abs(P.build() - s["cost_first"] * (len(vp) - 1)) <= 1e-9 * abs(P.build())
+    P.close()
+    out_skip, s3 = m.lidar_lm(noisy, min_voxels_per_pose=10 ** 6)
+    assert s3["termination"] == 6 and np.array_equal(out_skip, noisy)          # LVBA_TERM_SKIPPED
+    m.close()
     """)
 
 
