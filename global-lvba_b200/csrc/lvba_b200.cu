@@ -5,6 +5,7 @@
 #include "lidar_api.cuh"
 #include "visual_api.cuh"
 #include "voxel_api.cuh"
+#include "depth_api.cuh"
 
 extern "C" {
 

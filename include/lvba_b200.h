@@ -281,6 +281,42 @@ int lvba_voxel_map_lidar_lm(lvba_voxel_map* m, double* poses, int32_t min_voxels
 int lvba_voxel_map_destroy(lvba_voxel_map* m);
 
 /* ======================================================================================
+ * B4  depth rendering — replaces the world point grid and the per-image z-buffer in front of the track fusion:
+ *       buildGridMapFromOptimized   src/lvba_system.cpp:1266-1338   (0.5 m voxels of ALL world points, per-frame voxel sets,
+ *                                                                    per image the voxels of the frames within +-0.5 s)
+ *       generateDepthWithVoxel      src/lvba_system.cpp:835-919     (project every point of those voxels, (int) pixel,
+ *                                                                    `if (d == 0 || Z < d) d = (float)Z`)
+ *     The z-buffer is float(min Z) whatever the visiting order, so the images are reproducible bit for bit.
+ *
+ *   n_frames, scan_ptr, xyz, xyz_stride_floats, poses   as for B3: pl_fulls_ / x_buf_ (dataset_io_)
+ *   frame_ts     [n_frames] LiDAR frame timestamps x_buf_[i].t, ascending (the reference binary-searches them, :1318-1319)
+ *   voxel_size   0.5 in the reference (:1277)
+ *   cams         [n_images*12] Rcw (row-major) then tcw per image: Rcw_all_optimized_ / tcw_all_optimized_ (:861-864)
+ *   image_ts     [n_images] image timestamps; NaN = an image name that does not parse (:1309-1314) -> empty image
+ *   half_window  0.5 s in the reference (:1299)
+ *   intr         fx fy cx cy k1 k2 p1 p2
+ *   depth        [n_images * height * width] float, row-major per image (cv::Mat CV_32FC1), 0 = no point
+ * ====================================================================================== */
+typedef struct lvba_depth_summary {
+  int64_t n_points, n_voxels;
+  int64_t n_pairs;          /* distinct (frame, voxel) pairs = sum of the per_frame_voxels set sizes */
+  double ms_total, ms_upload, ms_device;
+  int64_t kernel_launches, h2d_bytes, d2h_bytes;
+  int64_t work_pairs;       /* render: (image, frame-in-window, voxel) triples examined */
+  int64_t work_chunks;      /* render: 64-point chunks projected (every voxel of a window once) */
+} lvba_depth_summary;
+
+typedef struct lvba_depth_grid lvba_depth_grid;
+
+int lvba_depth_grid_create(int32_t n_frames, const int64_t* scan_ptr, const float* xyz, int32_t xyz_stride_floats,
+                           const double* poses, const double* frame_ts, double voxel_size, int32_t device,
+                           lvba_depth_grid** out, lvba_depth_summary* summary /* may be NULL */);
+int lvba_depth_render(lvba_depth_grid* g, int32_t n_images, const double* cams, const double* image_ts, double half_window,
+                      const double intr[8], int32_t width, int32_t height, float* depth,
+                      lvba_depth_summary* summary /* may be NULL */);
+int lvba_depth_grid_destroy(lvba_depth_grid* g);
+
+/* ======================================================================================
  * Multi-GPU (one process per GPU).  The path shards by contiguous pose-block rows
  * (SURVEY.md §8e): voxel / track -> owner of its lowest pose / camera index.  Every rank
  * passes the FULL problem to *_create; after lvba_comm_init each rank keeps only its shard

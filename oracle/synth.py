@@ -335,3 +335,23 @@ def make_scan_scene(seed, W=5, n_per_scan=2500):
         w[kind == 3] = rng.uniform(-3, 3, ((kind == 3).sum(), 3))                                                  # clutter
         scans.append(((w - p) @ R).astype(np.float32))                                                            # R^T (w - p)
     return scans, poses
+
+
+def make_depth_scene(seed, F=6, n_per_scan=1500, M=4, width=160, height=120):
+    """Scans of make_scan_scene with frame timestamps 0.25 s apart, and M pinhole cameras (mild Brown-Conrady distortion)
+    riding on interpolated frame poses, looking at the x = 2.6 wall / the floor.  Returns a dict for oracle.depth_oracle."""
+    scans, poses = make_scan_scene(seed, W=F, n_per_scan=n_per_scan)
+    rng = np.random.default_rng(seed + 1000)
+    frame_ts = 100.0 + 0.25 * np.arange(F)
+    image_ts = np.sort(rng.uniform(frame_ts[0] - 0.2, frame_ts[-1] + 0.2, M))
+    cams = np.zeros((M, 12))
+    for k in range(M):
+        f = int(np.clip(np.searchsorted(frame_ts, image_ts[k]), 0, F - 1))
+        Rwi = poses[f, :9].reshape(3, 3); pwi = poses[f, 9:]
+        # camera axes in the body frame: z_c forward = body +x (towards the wall), x_c = body -y, y_c = body -z, plus a small tilt
+        Rci = np.array([[0.0, -1.0, 0.0], [0.0, 0.0, -1.0], [1.0, 0.0, 0.0]]) @ so3_exp(rng.normal(0, 0.15, (1, 3)))[0]
+        tci = rng.normal(0, 0.05, 3)
+        Rcw = Rci @ Rwi.T
+        cams[k, :9] = Rcw.ravel(); cams[k, 9:] = -Rcw @ pwi + tci                       # lvba_system.cpp:861-862
+    intr = np.array([0.6 * width, 0.6 * width, 0.5 * width - 0.3, 0.5 * height + 0.2, -0.08, 0.01, 5e-4, -3e-4])
+    return dict(scans=scans, poses=poses, frame_ts=frame_ts, cams=cams, image_ts=image_ts, intr=intr, width=width, height=height)

@@ -3,44 +3,12 @@
 // node states, emission order, plane lookup) is checked against oracle/voxel_oracle.py on a machine without a GPU.
 // Built by tests/test_voxel_emu.py with g++ -ffp-contract=off; never part of liblvba_b200.so — the product
 // instantiates the pipeline with the CUDA policy only (voxel_api.cuh) and has no host path.
-#include <algorithm>
 #include <cstring>
-#include <numeric>
-#include <vector>
 
 #include "../../global-lvba_b200/csrc/voxel_pipeline.h"
+#include "host_exec.h"
 
 namespace {
-
-struct HostExec {
-  template <class T>
-  struct Buf {
-    T* p = nullptr;
-    size_t n = 0;
-    std::vector<T> v;
-    int alloc(size_t count) { v.assign(count, T()); p = v.data(); n = count; return 0; }
-  };
-  template <class F>
-  int for_each(int64_t n, const F& f) { for (int64_t i = 0; i < n; ++i) f(i); return 0; }
-  template <class T>
-  int fill_zero(T* p, size_t n) { std::memset(p, 0, n * sizeof(T)); return 0; }
-  template <class T>
-  int fetch(T* host, const T* dev, size_t n) { std::memcpy(host, dev, n * sizeof(T)); return 0; }
-  int min_max(const int32_t* p, int64_t n, int32_t* mn, int32_t* mx) {
-    *mn = *std::min_element(p, p + n); *mx = *std::max_element(p, p + n); return 0;
-  }
-  int sort_pairs(const uint64_t* kin, uint64_t* kout, const uint32_t* vin, uint32_t* vout, int64_t n, int end_bit) {
-    const uint64_t mask = end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1);
-    std::vector<int64_t> perm((size_t)n);
-    std::iota(perm.begin(), perm.end(), 0);
-    std::stable_sort(perm.begin(), perm.end(), [&](int64_t a, int64_t b) { return (kin[a] & mask) < (kin[b] & mask); });
-    for (int64_t i = 0; i < n; ++i) { kout[i] = kin[perm[i]]; vout[i] = vin[perm[i]]; }
-    return 0;
-  }
-  template <class T>
-  int exclusive_scan(const T* in, T* out, int64_t n) { T acc = 0; for (int64_t i = 0; i < n; ++i) { const T v = in[i]; out[i] = acc; acc += v; } return 0; }
-  int sync() { return 0; }
-};
 
 using Map = lvba::vox::VoxelMap<HostExec>;
 

@@ -114,3 +114,20 @@ def test_voxel_map_argument_checks_need_no_gpu(pkg):
         with pytest.raises(pkg.LvbaError) as e:
             pkg.VoxelMap(scans, poses)
         assert e.value.status == -2
+
+
+def test_depth_grid_argument_checks_need_no_gpu(pkg):
+    """lvba_depth_grid_create validates on the host; without a device it then refuses (no CPU path)."""
+    scans = [np.zeros((4, 3), np.float32), np.ones((5, 3), np.float32)]
+    poses = np.tile(np.concatenate([np.eye(3).ravel(), np.zeros(3)]), (2, 1))
+    for kw, ts in ((dict(voxel_size=0.0), [0.0, 0.1]), (dict(), [0.2, 0.1]), (dict(), [0.0, float("nan")])):
+        with pytest.raises(pkg.LvbaError) as e:
+            pkg.DepthGrid(scans, poses, ts, **kw)
+        assert e.value.status == -1
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.DepthGrid(np.zeros((9, 3), np.float32), poses, [0.0, 0.1], scan_ptr=[0, 6, 4])
+    assert e.value.status == -1
+    if pkg.device_count() == 0:
+        with pytest.raises(pkg.LvbaError) as e:
+            pkg.DepthGrid(scans, poses, [0.0, 0.1])
+        assert e.value.status == -2

@@ -1,0 +1,93 @@
+"""Boundary B4 on a B200: depth images rendered on the device (lvba_depth_grid_create / lvba_depth_render,
+global-lvba_b200/csrc/depth_api.cuh) against oracle/depth_oracle.py through the C ABI — EXACT image equality, the
+comparisons of tests/test_depth_emu.py.  Each case runs in a child process under a timeout (first hardware run of this
+path; the file sorts last so that nothing here can disturb the CUDA context of the other GPU tests)."""
+import subprocess
+import sys
+import textwrap
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+PRELUDE = """
+import sys
+import numpy as np
+sys.path.insert(0, %r)
+import __graft_entry__ as graft
+from oracle import synth, depth_oracle as dep
+pkg = graft.load_package(); pkg.load_library()
+assert pkg.device_count() >= 1
+
+def gpu_render(s, voxel_size=0.5, half_window=0.5):
+    g = pkg.DepthGrid(s["scans"], s["poses"], s["frame_ts"], voxel_size)
+    img, info = g.render(s["cams"], s["image_ts"], s["intr"], s["width"], s["height"], half_window)
+    info.update(n_voxels=g.summary["n_voxels"], n_pairs=g.summary["n_pairs"]); g.close()
+    return img, info
+
+def oracle_render(s, **kw):
+    return dep.render(s["scans"], s["poses"], s["frame_ts"], s["cams"], s["image_ts"], s["intr"], s["width"], s["height"], **kw)
+""" % str(ROOT)
+
+
+def _run(body, timeout=300):
+    code = PRELUDE + textwrap.dedent(body) + "\nprint('CHILD-OK')\n"
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=timeout, cwd=str(ROOT))
+    assert r.returncode == 0 and "CHILD-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+    return r.stdout
+
+
+@pytest.mark.gpu
+def test_images_equal_oracle_exactly():
+    _run("""
+    for seed, vs, hw in [(1, 0.5, 0.5), (2, 0.5, 0.3), (3, 1.0, 0.5), (4, 0.25, 0.12)]:
+        s = synth.make_depth_scene(seed, F=7, n_per_scan=2500, M=5)
+        got, info = gpu_render(s, vs, hw)
+        assert np.array_equal(got, oracle_render(s, voxel_size=vs, half_window=hw))
+        assert np.count_nonzero(got) > 500 and info["kernel_launches"] > 0 and info["work_chunks"] > 0
+    """)
+
+
+@pytest.mark.gpu
+def test_edge_cases():
+    _run("""
+    s = synth.make_depth_scene(6, F=5, n_per_scan=800, M=4)
+    s2 = dict(s); s2["image_ts"] = s["image_ts"].copy(); s2["image_ts"][2] = np.nan
+    got, _ = gpu_render(s2); assert not got[2].any() and np.array_equal(got, oracle_render(s2))
+    far = dict(s); far["image_ts"] = s["image_ts"] + 1e4
+    assert not gpu_render(far)[0].any()
+    ragged = dict(s); ragged["scans"] = [s["scans"][0], np.zeros((0, 3), np.float32), s["scans"][2], s["scans"][3][:1], np.zeros((0, 3), np.float32)]
+    assert np.array_equal(gpu_render(ragged)[0], oracle_render(ragged))
+    empty = dict(s); empty["scans"] = [np.zeros((0, 3), np.float32)] * 5
+    assert not gpu_render(empty)[0].any()
+    behind = dict(s); behind["cams"] = s["cams"].copy(); behind["cams"][:, 6:9] *= -1; behind["cams"][:, 11] *= -1
+    assert np.array_equal(gpu_render(behind)[0], oracle_render(behind))
+    bad = dict(s); bad["scans"] = [x.copy() for x in s["scans"]]; bad["scans"][1][3, 0] = np.inf
+    try:
+        gpu_render(bad); raise SystemExit("Inf point accepted")
+    except pkg.LvbaError as e:
+        assert e.status == -1
+    """)
+
+
+@pytest.mark.gpu
+def test_large_render_properties():
+    """Beyond what the oracle follows in seconds: size-independent properties (idempotence, monotonicity in the window,
+    splitting the image list, every depth in front of the camera)."""
+    _run("""
+    s = synth.make_depth_scene(11, F=40, n_per_scan=40000, M=12, width=640, height=480)
+    g = pkg.DepthGrid(s["scans"], s["poses"], s["frame_ts"])
+    a, ia = g.render(s["cams"], s["image_ts"], s["intr"], 640, 480)
+    b, _ = g.render(s["cams"], s["image_ts"], s["intr"], 640, 480)
+    assert np.array_equal(a, b) and np.count_nonzero(a) > 10000
+    assert a[a > 0].min() >= 1e-3
+    halves = np.concatenate([g.render(s["cams"][:5], s["image_ts"][:5], s["intr"], 640, 480)[0],
+                             g.render(s["cams"][5:], s["image_ts"][5:], s["intr"], 640, 480)[0]])
+    assert np.array_equal(a, halves)
+    n, _ = g.render(s["cams"], s["image_ts"], s["intr"], 640, 480, half_window=0.1)
+    both = (n > 0) & (a > 0)
+    assert np.count_nonzero(n) <= np.count_nonzero(a) and np.all(a[both] <= n[both])
+    assert ia["work_chunks"] * 64 >= np.count_nonzero(a)
+    g.close()
+    """, timeout=600)
