@@ -11,11 +11,14 @@
 //   lvba_b200::SurfMap                               replaces the surf_map built by cut_voxel + recut (+ tras_opt) in front of
 //                                                    every solve (src/lvba_system.cpp:247-258, 361-378, 1498-1506) and the
 //                                                    plane lookup of recompute_local_planes (:1529-1566)
+//   lvba_b200::DepthRenderer                         replaces buildGridMapFromOptimized + generateDepthWithVoxel
+//                                                    (src/lvba_system.cpp:1266-1338, 835-919)
 //
 // Same names, argument meaning and error behaviour as the reference: void-like use (the reference ignores
 // solver failure), state written back only on success, size mismatches throw std::runtime_error like
 // src/lvba_system.cpp:1427-1432.  See INTEGRATION.md for the three-line patches.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <stdexcept>
@@ -209,6 +212,64 @@ class SurfMap {
  private:
   lvba_voxel_map* map_ = nullptr;
   int win_size_ = 0;
+};
+
+// ---- B4: depth rendering.  buildGridMapFromOptimized() buckets the world points of every LiDAR frame
+//      (dataset_io_->pl_fulls_, x_buf_ with .R .p and the timestamp .t) into 0.5 m voxels and lists, per image, the voxels
+//      of the frames within +-0.5 s; generateDepthWithVoxel() z-buffers them into one CV_32FC1 image per camera pose.
+//      DepthRenderer does both on the device.  Depth images come back in one contiguous float array, image k at
+//      depth.data() + k * width * height (wrap as cv::Mat(height, width, CV_32FC1, ptr) — see INTEGRATION.md).
+class DepthRenderer {
+ public:
+  DepthRenderer() = default;
+  DepthRenderer(const DepthRenderer&) = delete;
+  DepthRenderer& operator=(const DepthRenderer&) = delete;
+  ~DepthRenderer() { clear(); }
+  void clear() { if (grid_) lvba_depth_grid_destroy(grid_); grid_ = nullptr; }
+
+  // buildGridMapFromOptimized: clouds[i]->points[k].x/.y/.z, x_buf[i].R / .p / .t (ascending), vox = 0.5
+  template <class CloudPtrVec, class PoseVec>
+  int buildGridMapFromOptimized(const CloudPtrVec& pl_fulls, const PoseVec& x_buf, double vox = 0.5, lvba_depth_summary* summary = nullptr) {
+    clear();
+    const int F = (int)std::min(pl_fulls.size(), x_buf.size());                       // :1271
+    std::vector<int64_t> scan_ptr((size_t)F + 1, 0);
+    for (int j = 0; j < F; ++j) scan_ptr[j + 1] = scan_ptr[j] + (int64_t)pl_fulls[j]->points.size();
+    std::vector<float> xyz((size_t)scan_ptr[F] * 3);
+    for (int j = 0; j < F; ++j) {
+      float* dst = xyz.data() + 3 * (size_t)scan_ptr[j];
+      for (const auto& pt : pl_fulls[j]->points) { *dst++ = pt.x; *dst++ = pt.y; *dst++ = pt.z; }
+    }
+    std::vector<double> poses((size_t)F * 12), ts((size_t)F);
+    for (int i = 0; i < F; ++i) {
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) poses[12 * i + 3 * r + c] = x_buf[i].R(r, c);
+      for (int r = 0; r < 3; ++r) poses[12 * i + 9 + r] = x_buf[i].p(r);
+      ts[i] = x_buf[i].t;
+    }
+    return lvba_depth_grid_create(F, scan_ptr.data(), xyz.data(), 3, poses.data(), ts.data(), vox, -1, &grid_, summary);
+  }
+
+  // generateDepthWithVoxel: Rcw_all[k](r,c), tcw_all[k](r) as computed at :861-864; image_ts[k] = the parsed image id
+  // (NaN when parseTimestampFromName fails, :1309-1314).  depth: n_images * height * width floats, 0 = no point.
+  template <class Mat3Vec, class Vec3Vec>
+  int generateDepthWithVoxel(const Mat3Vec& Rcw_all, const Vec3Vec& tcw_all, const std::vector<double>& image_ts,
+                             double fx, double fy, double cx, double cy, double k1, double k2, double p1, double p2,
+                             int image_width, int image_height, std::vector<float>& depth, double half_w = 0.5,
+                             lvba_depth_summary* summary = nullptr) {
+    if (!grid_) throw std::runtime_error("lvba_b200::DepthRenderer: grid not built");
+    const int M = (int)image_ts.size();
+    if ((int)Rcw_all.size() != M || (int)tcw_all.size() != M) throw std::runtime_error("lvba_b200::DepthRenderer: pose / image count mismatch");   // cf. :839-846
+    std::vector<double> cams((size_t)M * 12);
+    for (int k = 0; k < M; ++k) {
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) cams[12 * k + 3 * r + c] = Rcw_all[k](r, c);
+      for (int r = 0; r < 3; ++r) cams[12 * k + 9 + r] = tcw_all[k](r);
+    }
+    const double intr[8] = {fx, fy, cx, cy, k1, k2, p1, p2};
+    depth.assign((size_t)M * image_width * image_height, 0.0f);
+    return lvba_depth_render(grid_, M, cams.data(), image_ts.data(), half_w, intr, image_width, image_height, depth.data(), summary);
+  }
+
+ private:
+  lvba_depth_grid* grid_ = nullptr;
 };
 
 // ---- B2: the flat arrays optimizeCameraPoses already builds (qs, ts, Xs, plane_n, plane_d) plus the

@@ -55,7 +55,38 @@ static int surf_map_case() {
   return (floor_ok && wall_ok && none_ok) ? 0 : 1;
 }
 
+// B4: three frames of a wall 4 m in front of a forward-looking camera -> every covered pixel reads ~4 m
+struct IMUST_T { M3 R; V3 p; double t; };
+static int depth_case() {
+  const int F = 3;
+  std::vector<IMUST_T> xs(F);
+  std::vector<Cloud> store(F);
+  std::vector<Cloud*> clouds;
+  unsigned s = 4242;
+  auto rnd = [&] { s = s * 1664525u + 1013904223u; return (double)(s >> 8) / (1u << 24) - 0.5; };
+  for (int i = 0; i < F; ++i) {
+    xs[i].R = M3{{1, 0, 0, 0, 1, 0, 0, 0, 1}}; xs[i].p = V3{{0.0, 0.1 * i, 0.0}}; xs[i].t = 10.0 + 0.1 * i;
+    for (int k = 0; k < 20000; ++k) { PointXYZINormal p{}; p.x = (float)(6.0 * rnd()); p.y = (float)(6.0 * rnd() - 0.1 * i); p.z = 4.0f; store[i].points.push_back(p); }
+    clouds.push_back(&store[i]);
+  }
+  lvba_b200::DepthRenderer dr;
+  int rc = dr.buildGridMapFromOptimized(clouds, xs);
+  if (rc == LVBA_ERR_NO_DEVICE) return 2;
+  if (rc != LVBA_OK) { std::printf("depth grid error %d: %s\n", rc, lvba_last_error()); return 1; }
+  std::vector<M3> Rcw = {M3{{1, 0, 0, 0, 1, 0, 0, 0, 1}}, M3{{1, 0, 0, 0, 1, 0, 0, 0, 1}}};
+  std::vector<V3> tcw = {V3{{0, 0, 0}}, V3{{0, 0, 1.0}}};
+  std::vector<double> ts = {10.1, 99.0};                                       // the second image has no frame in its window
+  std::vector<float> depth;
+  rc = dr.generateDepthWithVoxel(Rcw, tcw, ts, 100, 100, 80, 60, 0, 0, 0, 0, 160, 120, depth);
+  if (rc != LVBA_OK) { std::printf("depth render error %d: %s\n", rc, lvba_last_error()); return 1; }
+  int filled = 0, wrong = 0, second = 0;
+  for (int i = 0; i < 160 * 120; ++i) { if (depth[i] != 0) { ++filled; if (std::fabs(depth[i] - 4.0f) > 1e-6f) ++wrong; } if (depth[160 * 120 + i] != 0) ++second; }
+  std::printf("depth ok: %d pixels filled, %d off the wall, %d in the empty-window image\n", filled, wrong, second);
+  return (filled > 10000 && wrong == 0 && second == 0) ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && std::string(argv[1]) == "depth") return depth_case();           // B4, run by tests/test_zz_depth_gpu.py
   if (argc > 1 && std::string(argv[1]) == "surfmap") return surf_map_case();     // B3, run by tests/test_zz_voxel_gpu.py
   const int W = 4;
   std::vector<IMUST> xs(W);

@@ -91,3 +91,18 @@ def test_large_render_properties():
     assert ia["work_chunks"] * 64 >= np.count_nonzero(a)
     g.close()
     """, timeout=600)
+
+
+@pytest.mark.gpu
+def test_shim_depth_renderer(tmp_path):
+    """The C++ mirror (lvba_b200::DepthRenderer, host/lvba_shim.hpp): frames -> grid -> images."""
+    sys.path.insert(0, str(ROOT))
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    exe = tmp_path / "test_shim"
+    cmd = ["g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), str(ROOT / "tests" / "shim" / "test_shim.cpp"),
+           "-o", str(exe), str(pkg.LIB_PATH), f"-Wl,-rpath,{pkg.LIB_PATH.parent}", "-L/usr/local/cuda/lib64", "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), "depth"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "depth ok" in r.stdout, r.stdout + r.stderr
