@@ -36,7 +36,7 @@ EXPORTS = [
     "lvba_visual_get_system", "lvba_visual_reset_lm", "lvba_visual_reset_state", "lvba_visual_iterate", "lvba_visual_counts",
     "lvba_voxel_default_opts", "lvba_voxel_map_create", "lvba_voxel_map_summary", "lvba_voxel_map_export",
     "lvba_voxel_map_lookup", "lvba_voxel_map_lidar_create", "lvba_voxel_map_lidar_lm", "lvba_voxel_map_destroy",
-    "lvba_depth_grid_create", "lvba_depth_render", "lvba_depth_grid_destroy",
+    "lvba_depth_grid_create", "lvba_depth_render", "lvba_depth_backproject", "lvba_depth_grid_destroy",
     "lvba_comm_unique_id", "lvba_comm_init", "lvba_comm_destroy", "lvba_comm_info", "lvba_shard_owner",
 ]
 
@@ -493,6 +493,19 @@ class DepthGrid:
         _chk(self._lib.lvba_depth_render(self._h, C.c_int32(M), _p(cams, C.c_double), _p(its, C.c_double), C.c_double(half_window),
                                          _p(it, C.c_double), C.c_int32(width), C.c_int32(height), _p(out, C.c_float), C.byref(s)))
         return out, s.as_dict()
+
+
+    def backproject(self, cams, image_ts, intr, width, height, kp_ptr, kp_uv, half_window=0.5):
+        """Depth-fused 3-D candidates (lvba_system.cpp:1020-1038) of every keypoint; images never leave the device.
+        Returns (Xw (n, 3), valid (n,) uint8, summary dict)."""
+        cams = _f64(cams).reshape(-1, 12); its = _f64(image_ts); it = _f64(intr)
+        kp = np.ascontiguousarray(kp_ptr, np.int64); uv = np.ascontiguousarray(kp_uv, np.float32).reshape(-1, 2)
+        Xw = np.zeros((len(uv), 3)); valid = np.zeros(len(uv), np.uint8)
+        s = DepthSummary()
+        _chk(self._lib.lvba_depth_backproject(self._h, C.c_int32(len(cams)), _p(cams, C.c_double), _p(its, C.c_double), C.c_double(half_window),
+                                              _p(it, C.c_double), C.c_int32(width), C.c_int32(height), _p(kp, C.c_int64), _p(uv, C.c_float),
+                                              _p(Xw, C.c_double), _p(valid, C.c_uint8), C.byref(s)))
+        return Xw, valid, s.as_dict()
 
 
 # ------------------------------------------------------------------ multi-GPU

@@ -135,6 +135,78 @@ int lvba_depth_render(lvba_depth_grid* g, int32_t n_images, const double* cams, 
   return LVBA_OK;
 }
 
+// The depth-candidate loop of BuildTracksAndFuse3D (src/lvba_system.cpp:1020-1038) for every keypoint of every image: the
+// images are rendered batch by batch and sampled where they are; they never leave the device.
+int lvba_depth_backproject(lvba_depth_grid* g, int32_t n_images, const double* cams, const double* image_ts, double half_window,
+                           const double intr[8], int32_t width, int32_t height, const int64_t* kp_ptr, const float* kp_uv,
+                           double* Xw, uint8_t* valid, lvba_depth_summary* summary) {
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  if (!g || n_images < 0 || !intr || !kp_ptr || (n_images > 0 && (!cams || !image_ts))) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument or negative image count");
+  if (width <= 1 || height <= 1) return lvba::fail(LVBA_ERR_INVALID_ARG, "image size %d x %d", width, height);
+  if (!(half_window >= 0.0)) return lvba::fail(LVBA_ERR_INVALID_ARG, "half_window must be >= 0");
+  if (kp_ptr[0] != 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "kp_ptr[0] != 0");
+  for (int32_t k = 0; k < n_images; ++k)
+    if (kp_ptr[k + 1] < kp_ptr[k]) return lvba::fail(LVBA_ERR_INVALID_ARG, "kp_ptr not monotone at image %d", k);
+  const int64_t n_kp = kp_ptr[n_images];
+  if (n_kp > 0 && (!kp_uv || !Xw || !valid)) return lvba::fail(LVBA_ERR_INVALID_ARG, "null keypoint / output array");
+  for (int64_t k = 0; k < (int64_t)n_images * 12; ++k)
+    if (!std::isfinite(cams[k])) return lvba::fail(LVBA_ERR_INVALID_ARG, "non-finite camera entry %lld", (long long)k);
+  for (int k = 0; k < 8; ++k)
+    if (!std::isfinite(intr[k])) return lvba::fail(LVBA_ERR_INVALID_ARG, "non-finite intrinsic %d", k);
+  LVBA_CUDA(cudaSetDevice(g->device));
+  auto& G = g->grid;
+  lvba::CudaExec& ex = G.ex;
+  const int64_t launches0 = ex.launches;
+  const int64_t pix = (int64_t)width * height;
+  const int64_t batch = std::max<int64_t>(1, ((int64_t)1 << 28) / pix);
+  lvba::DevBuf<double> d_cams, d_ts, d_Xw;
+  lvba::DevBuf<float> d_depth, d_uv;
+  lvba::DevBuf<int64_t> d_kp;
+  lvba::DevBuf<uint8_t> d_valid;
+  int64_t h2d = 0, d2h = 0, pairs = 0, chunks = 0;
+  float ms_dev = 0.f;
+  cudaEvent_t e0, e1;
+  LVBA_CUDA(cudaEventCreate(&e0));
+  LVBA_CUDA(cudaEventCreate(&e1));
+  int rc = LVBA_OK;
+  for (int64_t k0 = 0; k0 < n_images && rc == LVBA_OK; k0 += batch) {
+    const int64_t nb = std::min<int64_t>(batch, n_images - k0);
+    const int64_t q0 = kp_ptr[k0], nq = kp_ptr[k0 + nb] - q0;
+    LVBA_TRY(d_cams.upload(cams + 12 * k0, (size_t)nb * 12, ex.stream, &h2d));
+    LVBA_TRY(d_ts.upload(image_ts + k0, (size_t)nb, ex.stream, &h2d));
+    LVBA_TRY(d_kp.upload(kp_ptr + k0, (size_t)nb + 1, ex.stream, &h2d));
+    if (nq > 0) LVBA_TRY(d_uv.upload(kp_uv + 2 * q0, (size_t)nq * 2, ex.stream, &h2d));
+    if (d_depth.n < (size_t)(nb * pix)) LVBA_TRY(d_depth.alloc((size_t)(nb * pix)));
+    if (d_Xw.n < (size_t)nq * 3) LVBA_TRY(d_Xw.alloc((size_t)nq * 3));
+    if (d_valid.n < (size_t)nq) LVBA_TRY(d_valid.alloc((size_t)nq));
+    LVBA_CUDA(cudaEventRecord(e0, ex.stream));
+    rc = G.render(nb, d_cams.p, d_ts.p, half_window, intr, width, height, d_depth.p);
+    if (rc == LVBA_OK && nq > 0) rc = G.backproject(nb, d_depth.p, d_cams.p, intr, width, height, d_kp.p, nq, d_uv.p, d_Xw.p, d_valid.p);
+    if (rc != LVBA_OK) break;
+    LVBA_CUDA(cudaEventRecord(e1, ex.stream));
+    if (nq > 0) {
+      LVBA_CUDA(cudaMemcpyAsync(Xw + 3 * q0, d_Xw.p, (size_t)nq * 3 * sizeof(double), cudaMemcpyDeviceToHost, ex.stream));
+      LVBA_CUDA(cudaMemcpyAsync(valid + q0, d_valid.p, (size_t)nq, cudaMemcpyDeviceToHost, ex.stream));
+    }
+    LVBA_CUDA(cudaStreamSynchronize(ex.stream));
+    float ms = 0.f;
+    LVBA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    ms_dev += ms; d2h += nq * 25; pairs += G.last_pairs; chunks += G.last_chunks;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  ex.temp.release();
+  if (rc != LVBA_OK) return rc;
+  if (summary) {
+    *summary = g->sum;
+    summary->ms_device = ms_dev; summary->ms_upload = 0.0;
+    summary->ms_total = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+    summary->kernel_launches = ex.launches - launches0; summary->h2d_bytes = h2d; summary->d2h_bytes = d2h;
+    summary->work_pairs = pairs; summary->work_chunks = chunks;
+  }
+  return LVBA_OK;
+}
+
 int lvba_depth_grid_destroy(lvba_depth_grid* g) {
   if (!g) return LVBA_OK;
   cudaSetDevice(g->device);

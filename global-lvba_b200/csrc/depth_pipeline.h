@@ -206,6 +206,68 @@ struct FinalizeF {           // R4
   LVBA_HD void operator()(int64_t i) const { depth[i] = bits[i] == kEmpty ? 0.0f : bits_float(bits[i]); }
 };
 
+// ---------------------------------------------------------------- depth-fused 3-D candidates of the track fusion
+// BuildTracksAndFuse3D, src/lvba_system.cpp:1020-1038, for one keypoint of one image:
+//   fetchDepthBilinear (include/utils.hpp:246-275, float arithmetic)  ->  backProjectPixelDepthDistorted (:235-243,
+//   undistortPixelToNormalized :207-233: 8 fixed-point iterations)    ->  camToWorld (:277-283)
+LVBA_HD bool fetch_depth_bilinear(const float* depth, int w, int h, float u, float v, float* d_out) {
+  if (!(u >= 0.0f) || !(v >= 0.0f) || u >= (float)(w - 1) || v >= (float)(h - 1)) return false;     // (a NaN pixel is refused too)
+  const int x = (int)floorf(u), y = (int)floorf(v);
+  const float du = vox::fadd_(u, -(float)x), dv = vox::fadd_(v, -(float)y);
+  const float d00 = depth[(int64_t)y * w + x], d10 = depth[(int64_t)y * w + x + 1];
+  const float d01 = depth[(int64_t)(y + 1) * w + x], d11 = depth[(int64_t)(y + 1) * w + x + 1];
+  if (d00 <= 0 || d10 <= 0 || d01 <= 0 || d11 <= 0) return false;
+  const float omu = vox::fadd_(1.0f, -du), omv = vox::fadd_(1.0f, -dv);
+  const float a = vox::fmul_(vox::fmul_(omu, omv), d00), b = vox::fmul_(vox::fmul_(du, omv), d10);
+  const float c = vox::fmul_(vox::fmul_(omu, dv), d01), e = vox::fmul_(vox::fmul_(du, dv), d11);
+  *d_out = vox::fadd_(vox::fadd_(vox::fadd_(a, b), c), e);
+  return *d_out > 0.0f;
+}
+LVBA_HD bool undistort_pixel(const double* intr, double u, double v, double* x, double* y) {
+  const double fx = intr[0], fy = intr[1], cx = intr[2], cy = intr[3], k1 = intr[4], k2 = intr[5], p1 = intr[6], p2 = intr[7];
+  if (!finite_(u) || !finite_(v)) return false;
+  if (fabs(fx) < 1e-12 || fabs(fy) < 1e-12) return false;
+  const double xd = vox::sub_(u, cx) / fx, yd = vox::sub_(v, cy) / fy;
+  double xu = xd, yu = yd;
+  for (int it = 0; it < 8; ++it) {
+    const double r2 = add_(mul_(xu, xu), mul_(yu, yu));
+    const double r4 = mul_(r2, r2);
+    const double radial = add_(add_(1.0, mul_(k1, r2)), mul_(k2, r4));
+    if (fabs(radial) < 1e-12 || !finite_(radial)) return false;
+    const double x_tan = add_(mul_(mul_(mul_(2.0, p1), xu), yu), mul_(p2, add_(r2, mul_(mul_(2.0, xu), xu))));
+    const double y_tan = add_(mul_(p1, add_(r2, mul_(mul_(2.0, yu), yu))), mul_(mul_(mul_(2.0, p2), xu), yu));
+    xu = vox::sub_(xd, x_tan) / radial;
+    yu = vox::sub_(yd, y_tan) / radial;
+    if (!finite_(xu) || !finite_(yu)) return false;
+  }
+  *x = xu; *y = yu;
+  return true;
+}
+struct BackprojectF {        // over the keypoints of the images of one batch
+  const float* depth; const double* cams; double intr[8]; int width; int height;
+  const int64_t* kp_ptr; int64_t n_img; const float* kp_uv; double* Xw; uint8_t* valid;
+  LVBA_HD void operator()(int64_t q) const {
+    valid[q] = 0; Xw[3 * q] = 0.0; Xw[3 * q + 1] = 0.0; Xw[3 * q + 2] = 0.0;                  // points3d[t] = Zero, valid_mask[t] = 0
+    const int64_t k = owner_i64(kp_ptr, n_img + 1, q + kp_ptr[0]);
+    const float u = kp_uv[2 * q], v = kp_uv[2 * q + 1];
+    float d;
+    if (!fetch_depth_bilinear(depth + k * (int64_t)width * height, width, height, u, v, &d)) return;   // :1030
+    if (d <= 0.0f) return;                                                                      // :1031
+    const double dd = (double)d;
+    double x, y;
+    if (!(dd > 0.0) || !finite_(dd) || !undistort_pixel(intr, (double)u, (double)v, &x, &y)) return;
+    const double Xc[3] = {mul_(x, dd), mul_(y, dd), dd};
+    if (!(finite_(Xc[0]) && finite_(Xc[1]) && finite_(Xc[2]))) return;
+    const double* R = cams + 12 * k;
+    const double* t = R + 9;
+    for (int i = 0; i < 3; ++i) {                                                               // camToWorld: Rwc = Rcw^T, twc = -(Rwc tcw)
+      const double twc = -add_(add_(mul_(R[i], t[0]), mul_(R[3 + i], t[1])), mul_(R[6 + i], t[2]));
+      Xw[3 * q + i] = add_(add_(add_(mul_(R[i], Xc[0]), mul_(R[3 + i], Xc[1])), mul_(R[6 + i], Xc[2])), twc);
+    }
+    valid[q] = 1;
+  }
+};
+
 // ================================================================ the grid
 template <class Exec>
 struct DepthGrid {
@@ -325,6 +387,16 @@ struct DepthGrid {
       }
     }
     LVBA_VOX_TRY(ex.for_each(n_pix, FinalizeF{bits.p, depth}));
+    return ex.sync();
+  }
+
+  // depth [n_img*height*width] as written by render(); kp_ptr [n_img+1] offsets into the caller's keypoint array (only
+  // differences are used: kp_uv / Xw / valid point at the first keypoint of this batch); all Exec-dereferenceable
+  int backproject(int64_t n_img, const float* depth, const double* cams, const double intr[8], int width, int height,
+                  const int64_t* kp_ptr, int64_t n_kp, const float* kp_uv, double* Xw, uint8_t* valid) {
+    BackprojectF f{depth, cams, {}, width, height, kp_ptr, n_img, kp_uv, Xw, valid};
+    for (int q = 0; q < 8; ++q) f.intr[q] = intr[q];
+    LVBA_VOX_TRY(ex.for_each(n_kp, f));
     return ex.sync();
   }
 };

@@ -314,6 +314,15 @@ int lvba_depth_grid_create(int32_t n_frames, const int64_t* scan_ptr, const floa
 int lvba_depth_render(lvba_depth_grid* g, int32_t n_images, const double* cams, const double* image_ts, double half_window,
                       const double intr[8], int32_t width, int32_t height, float* depth,
                       lvba_depth_summary* summary /* may be NULL */);
+/* The depth-fused 3-D candidates of the track fusion — the loop at src/lvba_system.cpp:1020-1038 of BuildTracksAndFuse3D
+ * (fetchDepthBilinear include/utils.hpp:246-275 -> backProjectPixelDepthDistorted :235-243 -> camToWorld :277-283) for
+ * EVERY keypoint of every image; a pure function of (image, keypoint), so the caller indexes the result by
+ * (component[t].first, component[t].second).  The depth images are rendered and sampled on the device and never copied out.
+ *   kp_ptr  [n_images+1] CSR over images; kp_uv [n_kp*2] float pixel (all_keypoints_[im][kp].x / .y)
+ *   Xw      [n_kp*3] out: points3d (zeros where invalid); valid [n_kp] out: valid_mask */
+int lvba_depth_backproject(lvba_depth_grid* g, int32_t n_images, const double* cams, const double* image_ts, double half_window,
+                           const double intr[8], int32_t width, int32_t height, const int64_t* kp_ptr, const float* kp_uv,
+                           double* Xw, uint8_t* valid, lvba_depth_summary* summary /* may be NULL */);
 int lvba_depth_grid_destroy(lvba_depth_grid* g);
 
 /* ======================================================================================

@@ -150,3 +150,70 @@ def render_literal(scans, poses, frame_ts, cams, image_ts, intr, width, height, 
                 if d == 0 or Z < d:
                     depth[v, u] = np.float32(Z)
     return out
+
+
+def fetch_depth_bilinear(depth, u, v):
+    """fetchDepthBilinear, include/utils.hpp:246-275, CV_32FC1 branch; everything in float32.  Returns (ok, d)."""
+    f = np.float32
+    h, w = depth.shape
+    u = f(u); v = f(v)
+    if u < f(0) or v < f(0) or u >= f(w - 1) or v >= f(h - 1) or not (u == u and v == v):
+        return False, f(0)
+    x = int(np.floor(u)); y = int(np.floor(v))
+    du = f(u - f(x)); dv = f(v - f(y))
+    d00, d10, d01, d11 = depth[y, x], depth[y, x + 1], depth[y + 1, x], depth[y + 1, x + 1]
+    if d00 <= 0 or d10 <= 0 or d01 <= 0 or d11 <= 0:
+        return False, f(0)
+    omu = f(f(1) - du); omv = f(f(1) - dv)
+    d = f(f(f(f(omu * omv) * d00) + f(f(du * omv) * d10)) + f(f(omu * dv) * d01))
+    d = f(d + f(f(du * dv) * d11))
+    return bool(d > 0), d
+
+
+def undistort_pixel(intr, u, v):
+    """undistortPixelToNormalized, include/utils.hpp:207-233 (8 fixed-point iterations)."""
+    fx, fy, cx, cy, k1, k2, p1, p2 = [float(a) for a in intr]
+    if not (np.isfinite(u) and np.isfinite(v)) or abs(fx) < 1e-12 or abs(fy) < 1e-12:
+        return False, 0.0, 0.0
+    xd = (u - cx) / fx; yd = (v - cy) / fy
+    xu, yu = xd, yd
+    for _ in range(8):
+        r2 = xu * xu + yu * yu
+        r4 = r2 * r2
+        radial = (1.0 + k1 * r2) + k2 * r4
+        if abs(radial) < 1e-12 or not np.isfinite(radial):
+            return False, 0.0, 0.0
+        x_tan = ((2.0 * p1) * xu) * yu + p2 * (r2 + (2.0 * xu) * xu)
+        y_tan = p1 * (r2 + (2.0 * yu) * yu) + ((2.0 * p2) * xu) * yu
+        xu = (xd - x_tan) / radial
+        yu = (yd - y_tan) / radial
+        if not (np.isfinite(xu) and np.isfinite(yu)):
+            return False, 0.0, 0.0
+    return True, xu, yu
+
+
+def backproject(depth_images, cams, intr, kp_ptr, kp_uv):
+    """The depth-candidate loop of BuildTracksAndFuse3D (src/lvba_system.cpp:1020-1038) for every keypoint of every image:
+    fetchDepthBilinear -> backProjectPixelDepthDistorted (utils.hpp:235-243) -> camToWorld (:277-283).
+    kp_ptr (M+1,), kp_uv (n, 2) float32.  Returns (Xw (n, 3), valid (n,) uint8)."""
+    n = len(kp_uv)
+    Xw = np.zeros((n, 3)); valid = np.zeros(n, np.uint8)
+    for k in range(len(cams)):
+        R = cams[k][:9].reshape(3, 3); t = cams[k][9:]
+        for q in range(int(kp_ptr[k]), int(kp_ptr[k + 1])):
+            u, v = np.float32(kp_uv[q, 0]), np.float32(kp_uv[q, 1])
+            ok, d = fetch_depth_bilinear(depth_images[k], u, v)
+            if not ok or d <= 0:
+                continue
+            dd = float(d)
+            ok, x, y = undistort_pixel(intr, float(u), float(v))
+            if not ok:
+                continue
+            Xc = np.array([x * dd, y * dd, dd])
+            if not np.all(np.isfinite(Xc)):
+                continue
+            for i in range(3):
+                twc = -((R[0, i] * t[0] + R[1, i] * t[1]) + R[2, i] * t[2])
+                Xw[q, i] = ((R[0, i] * Xc[0] + R[1, i] * Xc[1]) + R[2, i] * Xc[2]) + twc
+            valid[q] = 1
+    return Xw, valid

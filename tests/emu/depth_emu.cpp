@@ -24,6 +24,11 @@ int emu_depth_render(void* h, int64_t n_img, const double* cams, const double* i
   return rc;
 }
 
+int emu_depth_backproject(void* h, int64_t n_img, const float* depth, const double* cams, const double* intr, int32_t width, int32_t height,
+                          const int64_t* kp_ptr, const float* kp_uv, double* Xw, uint8_t* valid) {
+  return ((Grid*)h)->backproject(n_img, depth, cams, intr, width, height, kp_ptr, kp_ptr[n_img] - kp_ptr[0], kp_uv, Xw, valid);
+}
+
 int emu_depth_grid_destroy(void* h) { delete (Grid*)h; return 0; }
 
 }  // extern "C"

@@ -100,3 +100,42 @@ def test_edge_cases(emu):
         R = shifted["cams"][k, :9].reshape(3, 3); shifted["cams"][k, 9:] -= R @ np.array([-91.3, 40.2, -7.7])
     rc, got, _ = emu_render(emu, shifted)
     assert rc == 0 and np.array_equal(got, oracle_render(shifted)) and got.any()
+
+
+def test_backprojected_keypoints_equal_oracle_exactly(emu):
+    """The depth-fused 3-D candidates of the track fusion (lvba_system.cpp:1020-1038): bilinear fetch in float, fixed-point
+    undistortion, camera -> world.  Compared bit for bit; the back-projected points must reproject onto their pixels."""
+    s = synth.make_depth_scene(7, F=8, n_per_scan=6000, M=4)
+    img = oracle_render(s)
+    rng = np.random.default_rng(2)
+    W, H = s["width"], s["height"]
+    counts = [300, 0, 250, 200]
+    uv = np.concatenate([np.column_stack([rng.uniform(-2, W + 1, c), rng.uniform(-2, H + 1, c)]) for c in counts]).astype(np.float32)
+    uv[5] = [W - 1, 3.0]; uv[6] = [3.0, H - 1]; uv[7] = [0.0, 0.0]; uv[8] = [np.nan, 4.0]           # borders of the valid range
+    kp_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    Xw_ref, valid_ref = dep.backproject(img, s["cams"], s["intr"], kp_ptr, uv)
+    assert 20 < valid_ref.sum() < len(uv)
+    # through the pipeline: render on the (emulated) device, then sample there
+    scans = s["scans"]; F = len(scans)
+    sp = np.zeros(F + 1, np.int64); sp[1:] = np.cumsum([len(x) for x in scans])
+    xyz = np.ascontiguousarray(np.concatenate(scans), np.float32)
+    poses = np.ascontiguousarray(s["poses"]); ts = np.ascontiguousarray(s["frame_ts"])
+    h = ctypes.c_void_p(); nv = ctypes.c_int64(); npairs = ctypes.c_int64()
+    assert emu.emu_depth_grid_create(ctypes.c_int32(F), _ptr(sp, ctypes.c_int64), _ptr(xyz, ctypes.c_float), _ptr(poses, ctypes.c_double),
+                                     _ptr(ts, ctypes.c_double), ctypes.c_double(0.5), ctypes.byref(h), ctypes.byref(nv), ctypes.byref(npairs)) == 0
+    cams = np.ascontiguousarray(s["cams"]); its = np.ascontiguousarray(s["image_ts"]); intr = np.ascontiguousarray(s["intr"])
+    depth = np.zeros((4, H, W), np.float32)
+    assert emu.emu_depth_render(h, ctypes.c_int64(4), _ptr(cams, ctypes.c_double), _ptr(its, ctypes.c_double), ctypes.c_double(0.5),
+                                _ptr(intr, ctypes.c_double), ctypes.c_int32(W), ctypes.c_int32(H), _ptr(depth, ctypes.c_float), None) == 0
+    Xw = np.full((len(uv), 3), 9.0); valid = np.full(len(uv), 9, np.uint8)
+    assert emu.emu_depth_backproject(h, ctypes.c_int64(4), _ptr(depth, ctypes.c_float), _ptr(cams, ctypes.c_double), _ptr(intr, ctypes.c_double),
+                                     ctypes.c_int32(W), ctypes.c_int32(H), _ptr(kp_ptr, ctypes.c_int64), _ptr(uv, ctypes.c_float),
+                                     _ptr(Xw, ctypes.c_double), valid.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))) == 0
+    emu.emu_depth_grid_destroy(h)
+    assert np.array_equal(valid, valid_ref) and np.array_equal(Xw, Xw_ref)
+    # size-independent property: a valid candidate projects back onto its keypoint (distortion inverse converged)
+    for q in np.nonzero(valid)[0][:50]:
+        k = int(np.searchsorted(kp_ptr, q, side="right") - 1)
+        R = s["cams"][k][:9].reshape(3, 3); t = s["cams"][k][9:]
+        ok, uu, vv = dep.project((R @ Xw[q] + t)[None, :], s["intr"])
+        assert ok[0] and abs(uu[0] - uv[q, 0]) < 1e-4 and abs(vv[0] - uv[q, 1]) < 1e-4

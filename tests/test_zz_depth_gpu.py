@@ -72,6 +72,25 @@ def test_edge_cases():
 
 
 @pytest.mark.gpu
+def test_backprojected_keypoints_equal_oracle_exactly():
+    _run("""
+    s = synth.make_depth_scene(7, F=8, n_per_scan=6000, M=4)
+    img = oracle_render(s)
+    rng = np.random.default_rng(2)
+    W, H = s["width"], s["height"]
+    counts = [300, 0, 250, 200]
+    uv = np.concatenate([np.column_stack([rng.uniform(-2, W + 1, c), rng.uniform(-2, H + 1, c)]) for c in counts]).astype(np.float32)
+    uv[5] = [W - 1, 3.0]; uv[6] = [3.0, H - 1]; uv[7] = [0.0, 0.0]; uv[8] = [np.nan, 4.0]
+    kp_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    Xw_ref, valid_ref = dep.backproject(img, s["cams"], s["intr"], kp_ptr, uv)
+    g = pkg.DepthGrid(s["scans"], s["poses"], s["frame_ts"])
+    Xw, valid, info = g.backproject(s["cams"], s["image_ts"], s["intr"], W, H, kp_ptr, uv); g.close()
+    assert 20 < valid_ref.sum() < len(uv)
+    assert np.array_equal(valid, valid_ref) and np.array_equal(Xw, Xw_ref) and info["d2h_bytes"] == 25 * len(uv)
+    """)
+
+
+@pytest.mark.gpu
 def test_large_render_properties():
     """Beyond what the oracle follows in seconds: size-independent properties (idempotence, monotonicity in the window,
     splitting the image list, every depth in front of the camera)."""
