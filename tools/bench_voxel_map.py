@@ -93,13 +93,39 @@ def main():
         scans = [xyz[scan_ptr[j]:scan_ptr[j + 1]] for j in range(k)]
         t0 = time.perf_counter(); vox.voxelize(scans, poses[:k], args.voxel_size); tc = time.perf_counter() - t0
         cpu = {"points_per_s": k * args.points / tc, "kind": "port (numpy, 1 thread)", "sample": f"{k} scans x {args.points} points"}
+    # ---- boundary B4 on the same scans: grid of world points + depth images of cameras riding on every 25th pose
+    depth = None
+    try:
+        frame_ts = 0.1 * np.arange(args.scans)
+        t0 = time.perf_counter(); dg = pkg.DepthGrid(xyz, poses, frame_ts, 0.5, scan_ptr=scan_ptr); t_grid = (time.perf_counter() - t0) * 1e3
+        ids = np.arange(0, args.scans, max(1, args.scans // 16))[:16]
+        Rci = np.array([[0.0, -1.0, 0.0], [0.0, 0.0, -1.0], [1.0, 0.0, 0.0]])
+        cams = np.zeros((len(ids), 12))
+        for j, i in enumerate(ids):
+            Rcw = Rci @ poses[i, :9].reshape(3, 3).T
+            cams[j, :9] = Rcw.ravel(); cams[j, 9:] = -Rcw @ poses[i, 9:]
+        intr = np.array([700.0, 700.0, 640.0, 512.0, -0.05, 0.01, 1e-4, -1e-4])
+        dg.render(cams[:2], frame_ts[ids[:2]], intr, 1280, 1024)
+        img, info = dg.render(cams, frame_ts[ids], intr, 1280, 1024)
+        uv = np.column_stack([rng.uniform(0, 1279, 160000), rng.uniform(0, 1023, 160000)]).astype(np.float32)
+        kp_ptr = np.arange(len(ids) + 1, dtype=np.int64) * 10000
+        _, valid, binfo = dg.backproject(cams, frame_ts[ids], intr, 1280, 1024, kp_ptr, uv)
+        depth = {"grid": {"ms_call": t_grid, "ms_device": dg.summary["ms_device"], "n_voxels": dg.summary["n_voxels"], "n_pairs": dg.summary["n_pairs"]},
+                 "render": {"images": int(len(ids)), "size": "1280x1024", "ms_device": info["ms_device"], "ms_call": info["ms_total"],
+                            "points_projected": int(info["work_chunks"]) * 64, "projections_per_s_device": info["work_chunks"] * 64 / max(info["ms_device"], 1e-9) * 1e3,
+                            "filled_fraction": float(np.mean(img > 0)), "kernel_launches": int(info["kernel_launches"])},
+                 "backproject": {"keypoints": 160000, "valid": int(valid.sum()), "ms_call": binfo["ms_total"], "ms_device": binfo["ms_device"],
+                                 "d2h_bytes": int(binfo["d2h_bytes"])}}
+        dg.close()
+    except Exception as e:          # noqa: BLE001
+        depth = {"error": repr(e)[:300]}
     out = {"workload": f"{args.scans} scans x {args.points} points (street scene), root voxel {args.voxel_size} m, layer_limit 2",
            "n_points": int(N), "n_voxels": int(summ["n_voxels"]), "nnz": int(summ["nnz"]), "n_nodes": summ["n_nodes"],
            "ms_device": best_dev, "ms_call": best_call, "points_per_s_device": N / (best_dev * 1e-3), "points_per_s_call": N / (best_call * 1e-3),
            "algorithmic_GBps_device": (12.0 * N + 80.0 * summ["nnz"]) / (best_dev * 1e-3) / 1e9,
            "h2d_bytes": int(summ["h2d_bytes"]), "kernel_launches": int(summ["kernel_launches"]),
            "lookup": {"queries": int(args.queries), "ms_call": t_lookup, "hit_fraction": float(np.mean(np.any(nd != 0, axis=1)))},
-           "checks": checks, "cpu": cpu}
+           "checks": checks, "cpu": cpu, "depth": depth}
     print(json.dumps(out), flush=True)
     return 0 if all(checks.values()) else 1
 
