@@ -34,7 +34,8 @@ EXPORTS = [
     "lvba_visual_lm", "lvba_visual_create", "lvba_visual_destroy", "lvba_visual_set_state",
     "lvba_visual_get_state", "lvba_visual_cost", "lvba_visual_step", "lvba_visual_structure",
     "lvba_visual_get_system", "lvba_visual_reset_lm", "lvba_visual_reset_state", "lvba_visual_iterate", "lvba_visual_counts",
-    "lvba_voxel_default_opts", "lvba_voxel_map_create", "lvba_voxel_map_summary", "lvba_voxel_map_export",
+    "lvba_voxel_default_opts", "lvba_voxel_map_create", "lvba_voxel_map_create_windows", "lvba_voxel_map_windows",
+    "lvba_voxel_map_lidar_lm_batch", "lvba_voxel_map_summary", "lvba_voxel_map_export",
     "lvba_voxel_map_lookup", "lvba_voxel_map_lidar_create", "lvba_voxel_map_lidar_lm", "lvba_voxel_map_destroy",
     "lvba_depth_grid_create", "lvba_depth_render", "lvba_depth_backproject", "lvba_depth_grid_destroy",
     "lvba_comm_unique_id", "lvba_comm_init", "lvba_comm_destroy", "lvba_comm_info", "lvba_shard_owner",
@@ -376,7 +377,7 @@ class VoxelMap:
     scans: list of (n_i, 3) float32 body-frame clouds (or one (N, stride) float32 array with scan_ptr); poses (W, 12)."""
 
     def __init__(self, scans, poses, voxel_size=1.0, eigen_ratio=None, layer_limit=2, min_points=15, device=-1,
-                 scan_ptr=None):
+                 scan_ptr=None, win_ptr=None):
         lib = load_library()
         self._lib = lib
         ps = _f64(poses)
@@ -397,8 +398,14 @@ class VoxelMap:
                 o.eigen_ratio[k] = float(eigen_ratio[k])
         self._h = C.c_void_p()
         s = VoxelSummary()
-        _chk(lib.lvba_voxel_map_create(C.c_int32(W), _p(sp, C.c_int64), _p(xyz, C.c_float), C.c_int32(stride),
-                                       _p(ps, C.c_double), C.byref(o), C.byref(self._h), C.byref(s)))
+        self.win_ptr = None if win_ptr is None else np.ascontiguousarray(win_ptr, np.int32)
+        if self.win_ptr is None:
+            _chk(lib.lvba_voxel_map_create(C.c_int32(W), _p(sp, C.c_int64), _p(xyz, C.c_float), C.c_int32(stride),
+                                           _p(ps, C.c_double), C.byref(o), C.byref(self._h), C.byref(s)))
+        else:       # one independent map per window of scans (runWindowBA)
+            _chk(lib.lvba_voxel_map_create_windows(C.c_int32(len(self.win_ptr) - 1), _p(self.win_ptr, C.c_int32), _p(sp, C.c_int64),
+                                                   _p(xyz, C.c_float), C.c_int32(stride), _p(ps, C.c_double), C.byref(o),
+                                                   C.byref(self._h), C.byref(s)))
         self.summary = s.as_dict()
 
     def close(self):
@@ -432,6 +439,23 @@ class VoxelMap:
         _chk(self._lib.lvba_voxel_map_lidar_lm(self._h, _p(ps, C.c_double), C.c_int32(min_voxels_per_pose),
                                                C.byref(opts) if opts is not None else None, C.byref(s)))
         return ps, s.as_dict()
+
+    def windows(self):
+        """Window index of every voxel (windowed maps)."""
+        w = np.zeros(self.summary["n_voxels"], np.int32)
+        n = C.c_int32()
+        _chk(self._lib.lvba_voxel_map_windows(self._h, C.byref(n), _p(w, C.c_int32)))
+        return w
+
+    def lidar_lm_batch(self, poses, min_voxels_per_pose=3, opts=None):
+        """runWindowBA's window stage from a windowed map.  Returns (poses, [per-window summary], total)."""
+        ps = _f64(poses).copy()
+        nw = len(self.win_ptr) - 1
+        sums = (Summary * max(nw, 1))()
+        tot = Summary()
+        _chk(self._lib.lvba_voxel_map_lidar_lm_batch(self._h, _p(ps, C.c_double), C.c_int32(min_voxels_per_pose),
+                                                     C.byref(opts) if opts is not None else None, sums, C.byref(tot)))
+        return ps, [sums[i].as_dict() for i in range(nw)], tot.as_dict()
 
     def lidar_problem(self, poses):
         """Device-resident LidarProblem of the map's voxels (lvba_voxel_map_lidar_create)."""

@@ -289,7 +289,7 @@ struct DepthGrid {
   int build(const float* xyz, const int64_t* scan_ptr, const double* poses, const double* ts, int F_, int64_t N_, double voxel_size_) {
     F = F_; N = N_; voxel_size = voxel_size_;
     n_voxels = 0; n_pairs = 0;
-    pk = KeyPacking{{0, 0, 0}, {0, 0, 0}, 0};
+    pk = KeyPacking{{0, 0, 0}, {0, 0, 0}, 0, 0};
     LVBA_VOX_TRY(frame_ts.alloc((size_t)F));
     LVBA_VOX_TRY(ex.for_each((int64_t)F, CopyF64F{ts, frame_ts.p}));
     LVBA_VOX_TRY(frame_pair.alloc((size_t)F + 1));

@@ -102,6 +102,7 @@ struct lvba_voxel_map {
   lvba::vox::VoxelMap<lvba::CudaExec> map;
   int device = 0;
   lvba_voxel_summary sum{};
+  std::vector<int32_t> win_ptr;      // windowed maps: [n_windows + 1] over scans
 };
 
 namespace lvba {
@@ -116,7 +117,8 @@ inline int voxel_check_opts(const lvba_voxel_opts* o) {
 }
 
 inline int voxel_map_create_impl(int32_t W, const int64_t* scan_ptr, const float* xyz, int32_t stride, const double* poses,
-                                 const lvba_voxel_opts* opts_in, lvba_voxel_map** out, lvba_voxel_summary* summary) {
+                                 const lvba_voxel_opts* opts_in, lvba_voxel_map** out, lvba_voxel_summary* summary,
+                                 int32_t n_windows = 0, const int32_t* win_ptr = nullptr) {
   using clk = std::chrono::steady_clock;
   const auto t0 = clk::now();
   if (!out) return fail(LVBA_ERR_INVALID_ARG, "null output handle");
@@ -157,13 +159,18 @@ inline int voxel_map_create_impl(int32_t W, const int64_t* scan_ptr, const float
   LVBA_TRY(d_xyz.upload(src, (size_t)N * 3, ex.stream, &h2d));
   LVBA_TRY(d_scan.upload(scan_ptr, (size_t)W + 1, ex.stream, &h2d));
   LVBA_TRY(d_poses.upload(poses, (size_t)W * 12, ex.stream, &h2d));
+  DevBuf<int32_t> d_win;
+  if (n_windows > 0) {
+    LVBA_TRY(d_win.upload(win_ptr, (size_t)n_windows + 1, ex.stream, &h2d));
+    h->win_ptr.assign(win_ptr, win_ptr + n_windows + 1);
+  }
   cudaEvent_t e0, e1;
   LVBA_CUDA(cudaEventCreate(&e0));
   LVBA_CUDA(cudaEventCreate(&e1));
   LVBA_CUDA(cudaEventRecord(e0, ex.stream));
   const auto t1 = clk::now();
   vox::VoxParams prm{o.voxel_size, {o.eigen_ratio[0], o.eigen_ratio[1], o.eigen_ratio[2], o.eigen_ratio[3]}, o.layer_limit, o.min_points};
-  const int rc = h->map.build(d_xyz.p, d_scan.p, d_poses.p, W, N, prm);
+  const int rc = h->map.build(d_xyz.p, d_scan.p, d_poses.p, W, N, prm, n_windows > 0 ? d_win.p : nullptr, n_windows);
   if (rc != LVBA_OK) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (h->map.error[0]) return fail(rc, "%s", h->map.error);
@@ -204,6 +211,28 @@ void lvba_voxel_default_opts(lvba_voxel_opts* o) {
 int lvba_voxel_map_create(int32_t W, const int64_t* scan_ptr, const float* xyz, int32_t xyz_stride_floats, const double* poses,
                           const lvba_voxel_opts* opts, lvba_voxel_map** out, lvba_voxel_summary* summary) {
   return lvba::voxel_map_create_impl(W, scan_ptr, xyz, xyz_stride_floats, poses, opts, out, summary);
+}
+
+// One independent map per window of consecutive scans, built together (runWindowBA, src/lvba_system.cpp:232-258).
+int lvba_voxel_map_create_windows(int32_t n_windows, const int32_t* win_ptr, const int64_t* scan_ptr, const float* xyz,
+                                  int32_t xyz_stride_floats, const double* poses, const lvba_voxel_opts* opts, lvba_voxel_map** out,
+                                  lvba_voxel_summary* summary) {
+  if (n_windows <= 0 || !win_ptr) return lvba::fail(LVBA_ERR_INVALID_ARG, "n_windows=%d must be positive and win_ptr non-null", n_windows);
+  if (win_ptr[0] != 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "win_ptr[0] must be 0");
+  for (int w = 0; w < n_windows; ++w)
+    if (win_ptr[w + 1] < win_ptr[w]) return lvba::fail(LVBA_ERR_INVALID_ARG, "win_ptr must be non-decreasing");
+  return lvba::voxel_map_create_impl(win_ptr[n_windows], scan_ptr, xyz, xyz_stride_floats, poses, opts, out, summary, n_windows, win_ptr);
+}
+
+int lvba_voxel_map_windows(lvba_voxel_map* m, int32_t* n_windows, int32_t* vox_window) {
+  if (!m) return lvba::fail(LVBA_ERR_INVALID_ARG, "null map");
+  if (n_windows) *n_windows = m->map.n_windows;
+  if (vox_window && m->map.V > 0) {
+    LVBA_CUDA(cudaSetDevice(m->device));
+    LVBA_CUDA(cudaMemcpyAsync(vox_window, m->map.vox_window.p, (size_t)m->map.V * sizeof(int32_t), cudaMemcpyDeviceToHost, m->map.ex.stream));
+    LVBA_CUDA(cudaStreamSynchronize(m->map.ex.stream));
+  }
+  return LVBA_OK;
 }
 
 int lvba_voxel_map_summary(const lvba_voxel_map* m, lvba_voxel_summary* summary) {
@@ -254,6 +283,7 @@ int lvba_voxel_map_lidar_create(lvba_voxel_map* m, const double* poses, lvba_lid
   LVBA_CUDA(cudaSetDevice(m->device));
   auto& v = m->map;
   if (v.W <= 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "the map has no scans");
+  if (v.n_windows > 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "windowed map: use lvba_voxel_map_lidar_lm_batch");
   std::vector<int64_t> vox_ptr((size_t)v.V + 1);
   std::vector<int32_t> pose_idx((size_t)v.nnz);
   LVBA_CUDA(cudaMemcpyAsync(vox_ptr.data(), v.vox_ptr.p, vox_ptr.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, v.ex.stream));
@@ -292,6 +322,46 @@ int lvba_voxel_map_lidar_lm(lvba_voxel_map* m, double* poses, int32_t min_voxels
     summary->ms_setup = p->ms_setup;
     summary->kernel_launches = p->launches; summary->h2d_bytes = p->h2d; summary->d2h_bytes = p->d2h;
     summary->ms_total = lvba::wall_ms() - t0;
+  }
+  lvba_lidar_destroy(p);
+  return rc;
+}
+
+// The whole window stage of runWindowBA (src/lvba_system.cpp:232-266) from a windowed map: tras_opt + damping_iter of every
+// window in one batched solve (lvba_lidar_lm_batch), the clusters never leaving the device.
+int lvba_voxel_map_lidar_lm_batch(lvba_voxel_map* m, double* poses, int32_t min_voxels_per_pose, const lvba_lidar_opts* opts,
+                                  lvba_summary* summaries, lvba_summary* total) {
+  if (!m || !poses) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  if (min_voxels_per_pose < 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "min_voxels_per_pose must be >= 0");
+  auto& v = m->map;
+  if (v.n_windows <= 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "not a windowed map: use lvba_voxel_map_lidar_lm");
+  const double t0 = lvba::wall_ms();
+  LVBA_CUDA(cudaSetDevice(m->device));
+  lvba_lidar_opts o;
+  if (opts) o = *opts; else lvba_lidar_default_opts(&o);
+  o.device = m->device;
+  std::vector<int64_t> vox_ptr((size_t)v.V + 1);
+  std::vector<int32_t> pose_idx((size_t)v.nnz);
+  LVBA_CUDA(cudaMemcpyAsync(vox_ptr.data(), v.vox_ptr.p, vox_ptr.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, v.ex.stream));
+  if (v.nnz) LVBA_CUDA(cudaMemcpyAsync(pose_idx.data(), v.vox_pose.p, pose_idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, v.ex.stream));
+  LVBA_CUDA(cudaStreamSynchronize(v.ex.stream));
+  lvba_lidar_problem* p = nullptr;
+  int rc;
+  try { rc = lvba::lidar_create_impl(v.W, v.V, vox_ptr.data(), pose_idx.data(), nullptr, poses, m->device, &p, v.n_windows, m->win_ptr.data(), v.vox_cluster.p); }
+  catch (const std::bad_alloc&) { return lvba::fail(LVBA_ERR_NOMEM, "host allocation failed"); }
+  catch (...) { return lvba::fail(LVBA_ERR_INVALID_ARG, "unexpected exception in lvba_voxel_map_lidar_lm_batch"); }
+  if (rc != LVBA_OK) return rc;
+  p->opts = o;
+  lvba_summary tot;
+  memset(&tot, 0, sizeof tot);
+  try { rc = lvba::lidar_batch_lm_impl(p, min_voxels_per_pose, summaries, &tot); }
+  catch (...) { rc = lvba::fail(LVBA_ERR_NOMEM, "host allocation failed in lvba_voxel_map_lidar_lm_batch"); }
+  if (rc == LVBA_OK) rc = lvba_lidar_get_poses(p, poses);
+  if (rc == LVBA_OK && total) {
+    *total = tot;
+    total->ms_setup = p->ms_setup;
+    total->kernel_launches = p->launches; total->h2d_bytes = p->h2d; total->d2h_bytes = p->d2h;
+    total->ms_total = lvba::wall_ms() - t0;
   }
   lvba_lidar_destroy(p);
   return rc;

@@ -58,6 +58,10 @@ struct KeyPacking {
   int32_t mn[3];
   int bits[3];
   int root_bits;
+  int win_bits;    // > 0: a window index sits above the root key (one independent map per window, see VoxelMap::build)
+  LVBA_HD int key_bits() const { return root_bits + win_bits; }
+  LVBA_HD uint64_t with_window(uint64_t root, uint32_t w) const { return ((uint64_t)w << root_bits) | root; }
+  LVBA_HD uint32_t window_of(uint64_t key) const { return (uint32_t)(key >> root_bits); }
   LVBA_HD uint64_t pack(const int64_t k[3]) const {
     return ((uint64_t)(k[0] - mn[0]) << (bits[1] + bits[2])) | ((uint64_t)(k[1] - mn[1]) << bits[2]) | (uint64_t)(k[2] - mn[2]);
   }
@@ -66,12 +70,12 @@ struct KeyPacking {
       if (k[a] < mn[a] || (k[a] - mn[a]) >> bits[a]) return false;
     return true;
   }
-  LVBA_HD void unpack(uint64_t r, int64_t k[3]) const {
+  LVBA_HD void unpack(uint64_t r, int64_t k[3]) const {        // of the root part; window bits above it are ignored
     k[2] = (int64_t)(r & (((uint64_t)1 << bits[2]) - 1)) + mn[2];
     r >>= bits[2];
     k[1] = (int64_t)(r & (((uint64_t)1 << bits[1]) - 1)) + mn[1];
     r >>= bits[1];
-    k[0] = (int64_t)r + mn[0];
+    k[0] = (int64_t)(r & (((uint64_t)1 << bits[0]) - 1)) + mn[0];
   }
 };
 
@@ -108,10 +112,16 @@ struct PointKeysF {          // pass 1
 
 struct PackKeysF {           // pass 2
   const float* xyz; const double* poses; const int32_t* pose_of; const int32_t* kx; const int32_t* ky; const int32_t* kz;
-  double voxel_size; KeyPacking pk; uint64_t* key2;
+  double voxel_size; KeyPacking pk; uint64_t* key2; const int32_t* win_ptr; int n_windows;
   LVBA_HD void operator()(int64_t i) const {
     double w[3];
     world_point(poses + 12 * (int64_t)pose_of[i], xyz + 3 * i, w);
+    uint32_t win = 0;
+    if (n_windows > 0) {                                  // window of the scan: last w with win_ptr[w] <= scan
+      int lo = 0, hi = n_windows;
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (win_ptr[mid] <= pose_of[i]) lo = mid; else hi = mid; }
+      win = (uint32_t)lo;
+    }
     const int64_t k[3] = {kx[i], ky[i], kz[i]};
     float c0[3], c1[3];
     int b[3];
@@ -119,7 +129,7 @@ struct PackKeysF {           // pass 2
     const int o1 = octant(w, c0, b);
     child_centre(c0, b, root_quater(voxel_size), c1);
     const int o2 = octant(w, c1, b);
-    key2[i] = (pk.pack(k) << 6) | (uint64_t)(o1 << 3 | o2);
+    key2[i] = (pk.with_window(pk.pack(k), win) << 6) | (uint64_t)(o1 << 3 | o2);
   }
 };
 
@@ -218,8 +228,9 @@ struct VoxelCountF {         // pass 4c, over [0, V] (terminator 0)
 };
 struct VoxelFillF {          // pass 4d
   const uint32_t* ref; const uint64_t* ext_key; LayerView lay[kMaxLayers]; KeyPacking pk; const int64_t* vox_ptr;
-  int32_t* pose_idx; double* clusters; int64_t* root_key; int8_t* path; double* centre; double* direct; double* eig;
+  int32_t* pose_idx; double* clusters; int64_t* root_key; int8_t* path; double* centre; double* direct; double* eig; int32_t* window;
   LVBA_HD void operator()(int64_t v) const {
+    window[v] = (int32_t)pk.window_of(ext_key[v] >> 6);
     const int layer = (int)(ref[v] >> 30);
     const LayerView& L = lay[layer];
     const uint32_t m = ref[v] & 0x3fffffffu;
@@ -326,13 +337,21 @@ struct VoxelMap {
   typename Exec::template Buf<int64_t> vox_root;
   typename Exec::template Buf<int8_t> vox_path;
   typename Exec::template Buf<double> vox_centre, vox_direct, vox_eig;
+  typename Exec::template Buf<int32_t> vox_window;   // [V] window of every voxel (all 0 for a single map)
+  int n_windows = 0;                                  // 0: one map over all scans
   const char* error = "";
 
   // xyz [N*3], scan_ptr [W+1], poses [W*12]: pointers the Exec's passes can dereference (device memory under CUDA).
-  int build(const float* xyz, const int64_t* scan_ptr, const double* poses, int W_, int64_t N_, const VoxParams& prm_) {
-    W = W_; N = N_; prm = prm_;
+  // win_ptr [n_windows+1] (Exec-dereferenceable) splits the scans into consecutive windows, each of which gets its OWN map
+  // (the surf_map that runWindowBA builds per window, src/lvba_system.cpp:247-258): the window index becomes the top bits of
+  // every key, so voxels never merge across windows, pose indices stay global, and the emitted CSR is the input of
+  // lvba_lidar_lm_batch as it stands.  n_windows = 0: one map.
+  int build(const float* xyz, const int64_t* scan_ptr, const double* poses, int W_, int64_t N_, const VoxParams& prm_,
+            const int32_t* win_ptr = nullptr, int n_windows_ = 0) {
+    W = W_; N = N_; prm = prm_; n_windows = n_windows_;
     n_layers = 0; V = 0; nnz = 0;
-    pk = KeyPacking{{0, 0, 0}, {0, 0, 0}, 0};
+    pk = KeyPacking{{0, 0, 0}, {0, 0, 0}, 0, 0};
+    pk.win_bits = n_windows > 1 ? bit_length((uint64_t)(n_windows - 1)) : 0;
     if (N > 0) {
       typename Exec::template Buf<int32_t> pose_of;
       typename Exec::template Buf<uint64_t> key2;
@@ -355,8 +374,8 @@ struct VoxelMap {
           pk.bits[a] = bit_length((uint64_t)((int64_t)mx - (int64_t)mn));
         }
         pk.root_bits = pk.bits[0] + pk.bits[1] + pk.bits[2];
-        if (pk.root_bits + 6 > 62) { error = "root voxel keys span more than 56 bits"; return kErrUnsupported; }
-        LVBA_VOX_TRY(ex.for_each(N, PackKeysF{xyz, poses, pose_of.p, kx.p, ky.p, kz.p, prm.voxel_size, pk, key2.p}));
+        if (pk.key_bits() + 6 > 62) { error = "root voxel keys (and window index) span more than 56 bits"; return kErrUnsupported; }
+        LVBA_VOX_TRY(ex.for_each(N, PackKeysF{xyz, poses, pose_of.p, kx.p, ky.p, kz.p, prm.voxel_size, pk, key2.p, win_ptr, n_windows}));
       }
       for (int L = 0; L <= prm.layer_limit; ++L) {
         LVBA_VOX_TRY(build_layer(L, xyz, poses, pose_of.p, key2.p));
@@ -382,7 +401,7 @@ struct VoxelMap {
     LVBA_VOX_TRY(kin.alloc((size_t)N)); LVBA_VOX_TRY(kout.alloc((size_t)N));
     LVBA_VOX_TRY(vin.alloc((size_t)N)); LVBA_VOX_TRY(idx.alloc((size_t)N));
     LVBA_VOX_TRY(ex.for_each(N, LayerKeysF{key2, 3 * (2 - L), kin.p, vin.p}));
-    const int end_bit = pk.root_bits + 3 * L;
+    const int end_bit = pk.key_bits() + 3 * L;
     LVBA_VOX_TRY(ex.sort_pairs(kin.p, kout.p, vin.p, idx.p, N, end_bit > 0 ? end_bit : 1));
     LVBA_VOX_TRY(seg_flag.alloc((size_t)N + 1)); LVBA_VOX_TRY(node_flag.alloc((size_t)N + 1));
     LVBA_VOX_TRY(seg_pos.alloc((size_t)N + 1)); LVBA_VOX_TRY(node_pos.alloc((size_t)N + 1));
@@ -431,7 +450,7 @@ struct VoxelMap {
     LVBA_VOX_TRY(ref_in.alloc((size_t)V)); LVBA_VOX_TRY(ref.alloc((size_t)V));
     for (int L = 0; L < n_layers; ++L)
       LVBA_VOX_TRY(ex.for_each(layer[L].n_nodes, EmitScatterF{flag[L].p, pos[L].p, layer[L].node_key.p, L, base[L], ext_in.p, ref_in.p}));
-    if (V > 0) LVBA_VOX_TRY(ex.sort_pairs(ext_in.p, ext.p, ref_in.p, ref.p, V, pk.root_bits + 6));
+    if (V > 0) LVBA_VOX_TRY(ex.sort_pairs(ext_in.p, ext.p, ref_in.p, ref.p, V, pk.key_bits() + 6));
     typename Exec::template Buf<int64_t> count;
     LVBA_VOX_TRY(count.alloc((size_t)V + 1));
     VoxelCountF cf{ref.p, V, {}, count.p};
@@ -442,7 +461,8 @@ struct VoxelMap {
     LVBA_VOX_TRY(vox_pose.alloc((size_t)nnz)); LVBA_VOX_TRY(vox_cluster.alloc((size_t)nnz * 10));
     LVBA_VOX_TRY(vox_root.alloc((size_t)V * 3)); LVBA_VOX_TRY(vox_path.alloc((size_t)V * 3));
     LVBA_VOX_TRY(vox_centre.alloc((size_t)V * 3)); LVBA_VOX_TRY(vox_direct.alloc((size_t)V * 3)); LVBA_VOX_TRY(vox_eig.alloc((size_t)V * 3));
-    VoxelFillF ff{ref.p, ext.p, {}, pk, vox_ptr.p, vox_pose.p, vox_cluster.p, vox_root.p, vox_path.p, vox_centre.p, vox_direct.p, vox_eig.p};
+    LVBA_VOX_TRY(vox_window.alloc((size_t)V));
+    VoxelFillF ff{ref.p, ext.p, {}, pk, vox_ptr.p, vox_pose.p, vox_cluster.p, vox_root.p, vox_path.p, vox_centre.p, vox_direct.p, vox_eig.p, vox_window.p};
     for (int L = 0; L < kMaxLayers; ++L) ff.lay[L] = cf.lay[L];
     LVBA_VOX_TRY(ex.for_each(V, ff));
     return ex.sync();
@@ -450,6 +470,7 @@ struct VoxelMap {
 
   // X [n*3] -> plane_nd [n*4], pointers the Exec's passes can dereference
   int lookup(int64_t n, const double* X, double* plane_nd) {
+    if (pk.win_bits > 0) { error = "plane lookup needs a single map, not a windowed one"; return kErrUnsupported; }
     PlaneLookupF f{X, prm.voxel_size, prm.layer_limit, n_layers, pk, {}, plane_nd};
     for (int L = 0; L < kMaxLayers; ++L) f.lay[L] = L < n_layers ? layer[L].view() : LayerView{};
     LVBA_VOX_TRY(ex.for_each(n, f));

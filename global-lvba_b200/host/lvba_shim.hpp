@@ -11,6 +11,8 @@
 //   lvba_b200::SurfMap                               replaces the surf_map built by cut_voxel + recut (+ tras_opt) in front of
 //                                                    every solve (src/lvba_system.cpp:247-258, 361-378, 1498-1506) and the
 //                                                    plane lookup of recompute_local_planes (:1529-1566)
+//   lvba_b200::run_window_stage                      the whole window loop of runWindowBA (src/lvba_system.cpp:232-266): one voxel
+//                                                    map per window built together + every window solved in one batched LM
 //   lvba_b200::DepthRenderer                         replaces buildGridMapFromOptimized + generateDepthWithVoxel
 //                                                    (src/lvba_system.cpp:1266-1338, 835-919)
 //
@@ -213,6 +215,57 @@ class SurfMap {
   lvba_voxel_map* map_ = nullptr;
   int win_size_ = 0;
 };
+
+// ---- B3 + B1 batched: the window loop of runWindowBA (src/lvba_system.cpp:232-266) in two library calls.  pl_fulls / x_buf_full
+//      are dataset_io_->pl_fulls_ / x_buf_; windows are the consecutive `window_size` slices of the loop at :232-233.  On return
+//      x_wins[w] holds the optimised x_win of window w (the odometry poses when the window was skipped by the
+//      `plvec_voxels.size() < 3 * x_win.size()` rule, :259-263, which summaries[w].termination == LVBA_TERM_SKIPPED reports).
+template <class CloudPtrVec, class PoseVec>
+inline int run_window_stage(const CloudPtrVec& pl_fulls, const PoseVec& x_buf_full, int window_size, double root_voxel_size,
+                            const float eigen_ratio_array[4], std::vector<PoseVec>& x_wins, std::vector<lvba_summary>* summaries = nullptr,
+                            lvba_summary* total = nullptr, const lvba_lidar_opts* opts = nullptr) {
+  if (window_size <= 0) throw std::runtime_error("lvba_b200::run_window_stage: window_size must be positive");
+  const int total_size = (int)std::min(pl_fulls.size(), x_buf_full.size());
+  std::vector<int32_t> win_ptr{0};
+  for (int start = 0; start < total_size; start += window_size) win_ptr.push_back(std::min(start + window_size, total_size));
+  const int n_windows = (int)win_ptr.size() - 1;
+  x_wins.clear();
+  if (n_windows == 0) return LVBA_OK;
+  std::vector<int64_t> scan_ptr((size_t)total_size + 1, 0);
+  for (int j = 0; j < total_size; ++j) scan_ptr[j + 1] = scan_ptr[j] + (int64_t)pl_fulls[j]->points.size();
+  std::vector<float> xyz((size_t)scan_ptr[total_size] * 3);
+  for (int j = 0; j < total_size; ++j) {
+    float* dst = xyz.data() + 3 * (size_t)scan_ptr[j];
+    for (const auto& pt : pl_fulls[j]->points) { *dst++ = pt.x; *dst++ = pt.y; *dst++ = pt.z; }
+  }
+  std::vector<double> poses((size_t)total_size * 12);
+  for (int i = 0; i < total_size; ++i) {
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) poses[12 * i + 3 * r + c] = x_buf_full[i].R(r, c);
+    for (int r = 0; r < 3; ++r) poses[12 * i + 9 + r] = x_buf_full[i].p(r);
+  }
+  lvba_voxel_opts o;
+  lvba_voxel_default_opts(&o);
+  o.voxel_size = root_voxel_size;
+  for (int k = 0; k < 4; ++k) o.eigen_ratio[k] = eigen_ratio_array[k];
+  lvba_voxel_map* map = nullptr;
+  int rc = lvba_voxel_map_create_windows(n_windows, win_ptr.data(), scan_ptr.data(), xyz.data(), 3, poses.data(), &o, &map, nullptr);
+  if (rc != LVBA_OK) return rc;
+  std::vector<lvba_summary> local((size_t)n_windows);
+  rc = lvba_voxel_map_lidar_lm_batch(map, poses.data(), /*min_voxels_per_pose=*/3, opts, local.data(), total);
+  lvba_voxel_map_destroy(map);
+  if (rc != LVBA_OK) return rc;
+  for (int w = 0; w < n_windows; ++w) {
+    PoseVec x_win(x_buf_full.begin() + win_ptr[w], x_buf_full.begin() + win_ptr[w + 1]);      // :239 (keeps .t and any other member)
+    for (int i = 0; i < win_ptr[w + 1] - win_ptr[w]; ++i) {
+      const double* rec = poses.data() + 12 * (size_t)(win_ptr[w] + i);
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) x_win[i].R(r, c) = rec[3 * r + c];
+      for (int r = 0; r < 3; ++r) x_win[i].p(r) = rec[9 + r];
+    }
+    x_wins.push_back(std::move(x_win));
+  }
+  if (summaries) *summaries = local;
+  return LVBA_OK;
+}
 
 // ---- B4: depth rendering.  buildGridMapFromOptimized() buckets the world points of every LiDAR frame
 //      (dataset_io_->pl_fulls_, x_buf_ with .R .p and the timestamp .t) into 0.5 m voxels and lists, per image, the voxels

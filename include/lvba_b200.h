@@ -258,6 +258,16 @@ void lvba_voxel_default_opts(lvba_voxel_opts* o);
 int lvba_voxel_map_create(int32_t W, const int64_t* scan_ptr, const float* xyz, int32_t xyz_stride_floats,
                           const double* poses, const lvba_voxel_opts* opts, lvba_voxel_map** out,
                           lvba_voxel_summary* summary /* may be NULL */);
+/* One INDEPENDENT map per window of consecutive scans, all built together — the surf_map that runWindowBA creates, recuts
+ * and deletes once per window (src/lvba_system.cpp:232-258).  win_ptr [n_windows+1]: window w owns scans
+ * win_ptr[w] .. win_ptr[w+1]-1; W = win_ptr[n_windows].  Voxels never merge across windows, pose indices are those of the
+ * concatenated scans, voxels are ordered by (window, key, path): the export is the input of lvba_lidar_lm_batch as it
+ * stands.  lvba_voxel_map_lookup is not defined on a windowed map (LVBA_ERR_UNSUPPORTED). */
+int lvba_voxel_map_create_windows(int32_t n_windows, const int32_t* win_ptr, const int64_t* scan_ptr, const float* xyz,
+                                  int32_t xyz_stride_floats, const double* poses, const lvba_voxel_opts* opts,
+                                  lvba_voxel_map** out, lvba_voxel_summary* summary /* may be NULL */);
+/* n_windows (0 for a single map) and, when vox_window != NULL, the window of every voxel [V]. */
+int lvba_voxel_map_windows(lvba_voxel_map* m, int32_t* n_windows, int32_t* vox_window);
 int lvba_voxel_map_summary(const lvba_voxel_map* m, lvba_voxel_summary* summary);
 /* Copy out the plane voxels (sizes from the summary).  Any pointer may be NULL.
  *   vox_ptr [V+1], pose_idx [nnz], clusters [nnz*10]   the arguments of lvba_lidar_lm / lvba_lidar_create
@@ -278,6 +288,10 @@ int lvba_voxel_map_lidar_create(lvba_voxel_map* m, const double* poses, lvba_lid
  * runLidarBA, which has none) or an empty map: LVBA_OK, LVBA_TERM_SKIPPED, poses untouched. */
 int lvba_voxel_map_lidar_lm(lvba_voxel_map* m, double* poses, int32_t min_voxels_per_pose, const lvba_lidar_opts* opts,
                             lvba_summary* summary);
+/* The window stage of runWindowBA (src/lvba_system.cpp:232-266) from a windowed map: tras_opt + damping_iter of EVERY window
+ * in one batched solve (see lvba_lidar_lm_batch for summaries / total / the skip rule), clusters never leaving the device. */
+int lvba_voxel_map_lidar_lm_batch(lvba_voxel_map* m, double* poses, int32_t min_voxels_per_pose, const lvba_lidar_opts* opts,
+                                  lvba_summary* summaries, lvba_summary* total);
 int lvba_voxel_map_destroy(lvba_voxel_map* m);
 
 /* ======================================================================================

@@ -26,6 +26,23 @@ int emu_voxel_map_create(int32_t W, const int64_t* scan_ptr, const float* xyz, c
   return 0;
 }
 
+int emu_voxel_map_create_windows(int32_t n_windows, const int32_t* win_ptr, const int64_t* scan_ptr, const float* xyz, const double* poses,
+                                 double voxel_size, const float* eigen_ratio, int32_t layer_limit, int32_t min_points, void** out) {
+  Map* m = new Map();
+  lvba::vox::VoxParams prm{voxel_size, {eigen_ratio[0], eigen_ratio[1], eigen_ratio[2], eigen_ratio[3]}, layer_limit, min_points};
+  const int W = win_ptr[n_windows];
+  const int rc = m->build(xyz, scan_ptr, poses, W, scan_ptr[W], prm, win_ptr, n_windows);
+  if (rc != 0) { delete m; return rc; }
+  *out = m;
+  return 0;
+}
+
+int emu_voxel_map_windows(void* h, int32_t* vox_window) {
+  Map* m = (Map*)h;
+  std::memcpy(vox_window, m->vox_window.p, (size_t)m->V * sizeof(int32_t));
+  return 0;
+}
+
 int emu_voxel_map_sizes(void* h, int64_t* n_voxels, int64_t* nnz, int64_t* n_nodes) {
   Map* m = (Map*)h;
   *n_voxels = m->V; *nnz = m->nnz;

@@ -55,6 +55,38 @@ static int surf_map_case() {
   return (floor_ok && wall_ok && none_ok) ? 0 : 1;
 }
 
+// B3 + B1 batched: two windows of the surf-map scene through run_window_stage
+static int window_stage_case() {
+  const int W = 6;
+  std::vector<IMUST> xs(W);
+  std::vector<Cloud> store(W);
+  std::vector<Cloud*> clouds;
+  unsigned s = 991;
+  auto rnd = [&] { s = s * 1664525u + 1013904223u; return (double)(s >> 8) / (1u << 24) - 0.5; };
+  for (int i = 0; i < W; ++i) {
+    xs[i].R = M3{{1, 0, 0, 0, 1, 0, 0, 0, 1}}; xs[i].p = V3{{0.3 * i, 0.01 * (i % 3), 0.0}};
+    for (int k = 0; k < 6000; ++k) {
+      double w[3] = {4.0 * rnd() + 0.9, 4.0 * rnd(), 4.0 * rnd()};
+      w[k % 3] = (k % 3 == 0 ? 2.9 : k % 3 == 1 ? -1.7 : -1.2) + 0.01 * rnd();
+      PointXYZINormal p{};
+      p.x = (float)(w[0] - 0.3 * i); p.y = (float)w[1]; p.z = (float)w[2];
+      store[i].points.push_back(p);
+    }
+    clouds.push_back(&store[i]);
+  }
+  const float ratios[4] = {0.3f, 0.1f, 0.06f, 0.03f};
+  std::vector<std::vector<IMUST>> x_wins;
+  std::vector<lvba_summary> sums;
+  const int rc = lvba_b200::run_window_stage(clouds, xs, 3, 1.0, ratios, x_wins, &sums);
+  if (rc == LVBA_ERR_NO_DEVICE) return 2;
+  if (rc != LVBA_OK) { std::printf("window stage error %d: %s\n", rc, lvba_last_error()); return 1; }
+  if (x_wins.size() != 2 || x_wins[0].size() != 3 || x_wins[1].size() != 3) return 1;
+  int solved = 0;
+  for (const auto& sm : sums) if (sm.termination != LVBA_TERM_SKIPPED && sm.cost_last <= sm.cost_first) ++solved;
+  std::printf("window stage ok: %zu windows, %d solved, costs %.3e -> %.3e\n", x_wins.size(), solved, sums[0].cost_first, sums[0].cost_last);
+  return solved == 2 ? 0 : 1;
+}
+
 // B4: three frames of a wall 4 m in front of a forward-looking camera -> every covered pixel reads ~4 m
 struct IMUST_T { M3 R; V3 p; double t; };
 static int depth_case() {
@@ -86,6 +118,7 @@ static int depth_case() {
 }
 
 int main(int argc, char** argv) {
+  if (argc > 1 && std::string(argv[1]) == "windows") return window_stage_case();   // B3 + B1 batched, run by tests/test_zz_voxel_gpu.py
   if (argc > 1 && std::string(argv[1]) == "depth") return depth_case();           // B4, run by tests/test_zz_depth_gpu.py
   if (argc > 1 && std::string(argv[1]) == "surfmap") return surf_map_case();     // B3, run by tests/test_zz_voxel_gpu.py
   const int W = 4;

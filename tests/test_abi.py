@@ -131,3 +131,16 @@ def test_depth_grid_argument_checks_need_no_gpu(pkg):
         with pytest.raises(pkg.LvbaError) as e:
             pkg.DepthGrid(scans, poses, [0.0, 0.1])
         assert e.value.status == -2
+
+
+def test_windowed_voxel_map_argument_checks_need_no_gpu(pkg):
+    scans = [np.zeros((4, 3), np.float32), np.ones((5, 3), np.float32), np.ones((3, 3), np.float32)]
+    poses = np.tile(np.concatenate([np.eye(3).ravel(), np.zeros(3)]), (3, 1))
+    for wp in ([1, 3], [0, 2, 1, 3]):                                   # win_ptr[0] != 0 ; decreasing
+        with pytest.raises(pkg.LvbaError) as e:
+            pkg.VoxelMap(scans, poses, win_ptr=wp)
+        assert e.value.status == -1
+    if pkg.device_count() == 0:
+        with pytest.raises(pkg.LvbaError) as e:
+            pkg.VoxelMap(scans, poses, win_ptr=[0, 2, 3])
+        assert e.value.status == -2

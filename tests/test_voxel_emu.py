@@ -203,3 +203,47 @@ def test_pipeline_equals_golden_fixture(emu, tag):
     compare_with_oracle(m.export(), ref)
     compare_lookup(m.lookup(X), plane_nd)
     m.close()
+
+
+def oracle_windows(scans, poses, sizes, voxel_size):
+    """One oracle map per window (runWindowBA builds a fresh surf_map per window, lvba_system.cpp:247-258), concatenated with
+    global pose indices — the layout lvba_lidar_lm_batch takes."""
+    vps, pis, cls, wins, keys, layers = [np.zeros(1, np.int64)], [], [], [], [], []
+    a = 0; off = 0
+    for w, n in enumerate(sizes):
+        vp, pi, cl, meta = vox.voxelize(scans[a:a + n], poses[a:a + n], voxel_size)
+        vps.append(vp[1:] + off); off += int(vp[-1]); pis.append(pi + a); cls.append(cl)
+        wins.append(np.full(len(vp) - 1, w, np.int32)); keys.append(meta["key"]); layers.append(meta["layer"])
+        a += n
+    return (np.concatenate(vps), np.concatenate(pis).astype(np.int32), np.concatenate(cls), np.concatenate(wins),
+            np.concatenate(keys), np.concatenate(layers))
+
+
+def test_windowed_map_equals_one_oracle_map_per_window(emu):
+    sizes = [5, 4, 1, 6]
+    scans, poses = _scene(13, W=sum(sizes), n_per_scan=1800)
+    win_ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    sp = np.zeros(len(scans) + 1, np.int64); sp[1:] = np.cumsum([len(s) for s in scans])
+    xyz = np.ascontiguousarray(np.concatenate(scans), np.float32)
+    er = np.asarray(vox.EIGEN_RATIO_DEFAULT, np.float32)
+    for voxel_size in (1.0, 2.5):
+        m = EmuMap.__new__(EmuMap); m.lib = emu; m.h = ctypes.c_void_p()
+        rc = emu.emu_voxel_map_create_windows(ctypes.c_int32(len(sizes)), _ptr(win_ptr, ctypes.c_int32), _ptr(sp, ctypes.c_int64),
+                                              _ptr(xyz, ctypes.c_float), _ptr(np.ascontiguousarray(poses), ctypes.c_double),
+                                              ctypes.c_double(voxel_size), _ptr(er, ctypes.c_float), ctypes.c_int32(2), ctypes.c_int32(15),
+                                              ctypes.byref(m.h))
+        assert rc == 0
+        got = m.export()
+        win = np.zeros(len(got["vox_ptr"]) - 1, np.int32)
+        emu.emu_voxel_map_windows(m.h, _ptr(win, ctypes.c_int32))
+        vp, pi, cl, wins, keys, layers = oracle_windows(scans, poses, sizes, voxel_size)
+        assert np.array_equal(got["vox_ptr"], vp) and np.array_equal(got["pose_idx"], pi) and np.array_equal(win, wins)
+        assert np.array_equal(got["key"], keys) and np.array_equal(got["path"][:, 0], layers)
+        assert np.abs(got["clusters"] - cl).max() <= 1e-12 * max(1.0, np.abs(cl).max())
+        assert len(set(wins.tolist())) >= 3 and 2 not in wins          # the one-scan window has no voxel seen from two poses
+        # every voxel lies inside ONE window (what lvba_lidar_lm_batch requires)
+        for v in range(len(vp) - 1):
+            p = pi[vp[v]:vp[v + 1]]
+            assert win_ptr[wins[v]] <= p.min() and p.max() < win_ptr[wins[v] + 1]
+        assert emu.emu_voxel_map_lookup(m.h, ctypes.c_int64(1), _ptr(np.zeros(3), ctypes.c_double), _ptr(np.zeros(4), ctypes.c_double)) == -4
+        m.close()

@@ -169,6 +169,48 @@ def test_scans_to_lm_chain():
 
 
 @pytest.mark.gpu
+def test_windowed_map_and_batched_lm():
+    """runWindowBA's window stage: one map per window built together, then every window solved in one batched LM —
+    against one oracle map + one oracle damping_iter per window."""
+    _run("""
+    sizes = [5, 4, 1, 6]
+    scans, poses = synth.make_scan_scene(13, W=sum(sizes), n_per_scan=3000)
+    rng = np.random.default_rng(4)
+    noisy = poses.copy()
+    for i in range(len(noisy)):
+        noisy[i, :9] = (noisy[i, :9].reshape(3, 3) @ synth.so3_exp(rng.normal(0, 0.004, (1, 3)))[0]).ravel()
+        noisy[i, 9:] += rng.normal(0, 0.01, 3)
+    win_ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    m = pkg.VoxelMap(scans, noisy, 1.0, win_ptr=win_ptr)
+    g = m.export(); wins = m.windows()
+    a = 0; off = 0; refs = []
+    for w, n in enumerate(sizes):
+        vp, pi, cl, meta = vox.voxelize(scans[a:a + n], noisy[a:a + n], 1.0)
+        sel = wins == w
+        assert sel.sum() == len(vp) - 1 and np.array_equal(g["key"][sel], meta["key"])
+        assert np.array_equal(g["pose_idx"][off:off + len(pi)], pi + a)
+        assert np.abs(g["clusters"][off:off + len(pi)] - cl).max(initial=0.0) <= 1e-12 * max(1.0, np.abs(cl).max(initial=0.0))
+        refs.append((vp, pi, cl)); a += n; off += len(pi)
+    out, sums, tot = m.lidar_lm_batch(noisy, min_voxels_per_pose=3)
+    m.close()
+    a = 0
+    for w, n in enumerate(sizes):
+        vp, pi, cl = refs[w]
+        if len(vp) - 1 < 3 * n:
+            assert sums[w]["termination"] == 6 and np.array_equal(out[a:a + n], noisy[a:a + n])      # skipped (:262-266)
+        else:
+            ref_poses, info = lo.damping_iter(vp, pi, cl, noisy[a:a + n])
+            assert abs(sums[w]["cost_last"] - info["r_last"]) <= 1e-6 * info["r_last"]
+            assert np.abs(out[a:a + n] - ref_poses).max() <= 1e-6
+        a += n
+    assert any(s_["termination"] == 6 for s_ in sums) and any(s_["termination"] != 6 for s_ in sums)
+    # the same stage through the host-array entry point gives the same poses
+    out2, _, _ = pkg.lidar_lm_batch(win_ptr, g["vox_ptr"], g["pose_idx"], g["clusters"], noisy, 3)
+    assert np.abs(out - out2).max() <= 1e-9
+    """)
+
+
+@pytest.mark.gpu
 def test_large_map_invariants():
     """A map far beyond what the oracle can follow (2 M points): size-independent properties."""
     _run("""
@@ -212,3 +254,5 @@ def test_shim_surf_map(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe), "surfmap"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "surf map ok" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([str(exe), "windows"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "window stage ok" in r.stdout, r.stdout + r.stderr
