@@ -129,6 +129,7 @@ struct DevBuf {
     if (p) device_pool().give(dev_, bytes_, p);
     p = nullptr; n = 0; bytes_ = 0;
   }
+  void swap(DevBuf& o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(bytes_, o.bytes_); std::swap(dev_, o.dev_); }
   int alloc(size_t count) {
     release();
     n = count;

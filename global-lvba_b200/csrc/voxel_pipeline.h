@@ -133,9 +133,9 @@ struct PackKeysF {           // pass 2
   }
 };
 
-struct LayerKeysF {          // pass 3a
-  const uint64_t* key2; int shift; uint64_t* key; uint32_t* idx;
-  LVBA_HD void operator()(int64_t i) const { key[i] = key2[i] >> shift; idx[i] = (uint32_t)i; }
+struct LayerKeysF {          // pass 3a; `sub` lists the points that take part in this layer (null: all of them)
+  const uint64_t* key2; const uint32_t* sub; int shift; uint64_t* key; uint32_t* idx;
+  LVBA_HD void operator()(int64_t r) const { const uint32_t i = sub ? sub[r] : (uint32_t)r; key[r] = key2[i] >> shift; idx[r] = i; }
 };
 
 struct HeadFlagsF {          // pass 3b, over [0, N] — element N is the terminator (flag 0)
@@ -159,6 +159,15 @@ struct ScatterHeadsF {       // pass 3c, over [0, N]
     if (seg_flag[r]) { seg_start[seg_pos[r]] = (uint32_t)r; seg_pose[seg_pos[r]] = pose_of[idx[r]]; }
     if (node_flag[r]) { node_key[node_pos[r]] = key[r]; node_seg[node_pos[r]] = seg_pos[r]; }
   }
+};
+
+struct SplitFlagF {          // pass 3f, over [0, n] (terminator 0): does the point's node split?  (its children exist then)
+  const uint32_t* node_flag; const uint32_t* node_pos; const uint8_t* state; int64_t n; uint32_t* flag;
+  LVBA_HD void operator()(int64_t r) const { flag[r] = (r < n && state[node_pos[r] + node_flag[r] - 1u] == NS_SPLIT) ? 1u : 0u; }
+};
+struct SplitCompactF {       // pass 3g: the points of split nodes, in this layer's sorted order (equal next-layer keys keep the caller's order)
+  const uint32_t* flag; const uint32_t* pos; const uint32_t* idx; uint32_t* next;
+  LVBA_HD void operator()(int64_t r) const { if (flag[r]) next[pos[r]] = idx[r]; }
 };
 
 struct SegmentSumF {         // pass 3d: PointCluster::push over the segment's points in the caller's order
@@ -194,11 +203,6 @@ struct NodeTestF {           // pass 3e: recut :420-464 for one node
     for (int k = 0; k < 3; ++k) { centre[3 * m + k] = c[k]; direct[3 * m + k] = d[k]; eig[3 * m + k] = lam[k]; }
     state[m] = plane ? NS_PLANE : (layer == prm.layer_limit ? NS_MID : NS_SPLIT);
   }
-};
-
-struct AnyStateF {           // does any node of the layer carry `value`?  (benign race: every writer stores 1)
-  const uint8_t* state; uint8_t value; int32_t* flag;
-  LVBA_HD void operator()(int64_t m) const { if (state[m] == value) *flag = 1; }
 };
 
 struct EmitFlagF {           // pass 4a, over [0, n_nodes] (terminator 0): tras_opt + push_voxel
@@ -377,30 +381,31 @@ struct VoxelMap {
         if (pk.key_bits() + 6 > 62) { error = "root voxel keys (and window index) span more than 56 bits"; return kErrUnsupported; }
         LVBA_VOX_TRY(ex.for_each(N, PackKeysF{xyz, poses, pose_of.p, kx.p, ky.p, kz.p, prm.voxel_size, pk, key2.p, win_ptr, n_windows}));
       }
-      for (int L = 0; L <= prm.layer_limit; ++L) {
-        LVBA_VOX_TRY(build_layer(L, xyz, poses, pose_of.p, key2.p));
+      // Only the points of nodes that split take part in the next layer (the reference hands exactly those to cut_func,
+      // :453-456); layer 0 takes them all.
+      typename Exec::template Buf<uint32_t> sub, next;
+      int64_t n_sub = N;
+      for (int L = 0; L <= prm.layer_limit && n_sub > 0; ++L) {
+        int64_t n_next = 0;
+        LVBA_VOX_TRY(build_layer(L, xyz, poses, pose_of.p, key2.p, L == 0 ? nullptr : sub.p, n_sub, L < prm.layer_limit ? &next : nullptr, &n_next));
         n_layers = L + 1;
-        if (L < prm.layer_limit) {                           // stop early when nothing was split
-          typename Exec::template Buf<int32_t> flag;
-          int32_t any = 0;
-          LVBA_VOX_TRY(flag.alloc(1));
-          LVBA_VOX_TRY(ex.fill_zero(flag.p, 1));
-          LVBA_VOX_TRY(ex.for_each(layer[L].n_nodes, AnyStateF{layer[L].state.p, (uint8_t)NS_SPLIT, flag.p}));
-          LVBA_VOX_TRY(ex.fetch(&any, flag.p, 1));
-          if (!any) break;
-        }
+        sub.swap(next);
+        n_sub = n_next;
       }
     }
     return emit();
   }
 
-  int build_layer(int L, const float* xyz, const double* poses, const int32_t* pose_of, const uint64_t* key2) {
+  // sub [n] (null = all N points, in the caller's order): the points of this layer.  next / n_next (optional): the points of
+  // the nodes that split here, for the next layer.
+  int build_layer(int L, const float* xyz, const double* poses, const int32_t* pose_of, const uint64_t* key2, const uint32_t* sub,
+                  int64_t N, typename Exec::template Buf<uint32_t>* next, int64_t* n_next) {
     Layer<Exec>& Y = layer[L];
     typename Exec::template Buf<uint64_t> kin, kout;
     typename Exec::template Buf<uint32_t> vin, idx, seg_flag, node_flag, seg_pos, node_pos, seg_start;
     LVBA_VOX_TRY(kin.alloc((size_t)N)); LVBA_VOX_TRY(kout.alloc((size_t)N));
     LVBA_VOX_TRY(vin.alloc((size_t)N)); LVBA_VOX_TRY(idx.alloc((size_t)N));
-    LVBA_VOX_TRY(ex.for_each(N, LayerKeysF{key2, 3 * (2 - L), kin.p, vin.p}));
+    LVBA_VOX_TRY(ex.for_each(N, LayerKeysF{key2, sub, 3 * (2 - L), kin.p, vin.p}));
     const int end_bit = pk.key_bits() + 3 * L;
     LVBA_VOX_TRY(ex.sort_pairs(kin.p, kout.p, vin.p, idx.p, N, end_bit > 0 ? end_bit : 1));
     LVBA_VOX_TRY(seg_flag.alloc((size_t)N + 1)); LVBA_VOX_TRY(node_flag.alloc((size_t)N + 1));
@@ -427,6 +432,15 @@ struct VoxelMap {
                                                  has_parent ? layer[L - 1].state.p : nullptr,
                                                  Y.node_key.p, Y.node_seg.p, Y.seg_pose.p, Y.seg_cluster.p,
                                                  Y.state.p, Y.centre.p, Y.direct.p, Y.eig.p}));
+    if (next) {                                            // seg_flag / seg_pos are free again: reuse them for the compaction
+      LVBA_VOX_TRY(ex.for_each(N + 1, SplitFlagF{node_flag.p, node_pos.p, Y.state.p, N, seg_flag.p}));
+      LVBA_VOX_TRY(ex.exclusive_scan(seg_flag.p, seg_pos.p, N + 1));
+      uint32_t n = 0;
+      LVBA_VOX_TRY(ex.fetch(&n, seg_pos.p + N, 1));
+      *n_next = n;
+      LVBA_VOX_TRY(next->alloc(n));
+      LVBA_VOX_TRY(ex.for_each(N, SplitCompactF{seg_flag.p, seg_pos.p, idx.p, next->p}));
+    }
     return 0;
   }
 

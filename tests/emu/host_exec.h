@@ -13,6 +13,7 @@ struct HostExec {
     size_t n = 0;
     std::vector<T> v;
     int alloc(size_t count) { v.assign(count, T()); p = v.data(); n = count; return 0; }
+    void swap(Buf& o) { v.swap(o.v); std::swap(p, o.p); std::swap(n, o.n); }
   };
   template <class F>
   int for_each(int64_t n, const F& f) { for (int64_t i = 0; i < n; ++i) f(i); return 0; }
