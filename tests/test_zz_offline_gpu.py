@@ -1,0 +1,56 @@
+"""The offline tool (tools/lvba_offline.cpp) end to end on a B200: dataset directory in the reference's
+layout -> loader -> for stage 1 and 2: device voxel map (B3) + LiDAR LM (B1) -> TUM poses, against the same chain through
+the oracles (oracle/voxel_oracle.py + oracle/lidar_oracle.py) on the poses the loader reads."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+pytestmark = pytest.mark.xfail(strict=False, reason="off-ROS tool: first hardware run pending (loader and both device stages are tested separately)")
+
+
+@pytest.mark.gpu
+def test_offline_run_matches_oracle_chain(tmp_path):
+    import __graft_entry__ as graft
+    from oracle import dataset_writer as dw, lidar_oracle as lo, synth, voxel_oracle as vox
+    pkg = graft.load_package()
+    exe = tmp_path / "lvba_offline"
+    cmd = ["g++", "-std=c++17", "-O2", "-I", str(ROOT / "include"), str(ROOT / "tools" / "lvba_offline.cpp"), "-o", str(exe),
+           str(pkg.LIB_PATH), f"-Wl,-rpath,{pkg.LIB_PATH.parent}", "-L/usr/local/cuda/lib64", "-lcudart"]
+    assert subprocess.run(cmd, capture_output=True, text=True).returncode == 0
+    scans, poses = synth.make_scan_scene(17, W=6, n_per_scan=4000)
+    rng = np.random.default_rng(5)
+    noisy = poses.copy()
+    for i in range(1, len(noisy)):
+        noisy[i, :9] = (noisy[i, :9].reshape(3, 3) @ synth.so3_exp(rng.normal(0, 0.008, (1, 3)))[0]).ravel()
+        noisy[i, 9:] += rng.normal(0, 0.015, 3)
+    data = tmp_path / "data"
+    dw.write_lidar_dataset(data, scans, noisy)
+    out = tmp_path / "opt.txt"
+    r = subprocess.run([str(exe), "--data", str(data), "--out", str(out), "--stage1-voxel", "1.0", "--stage2-voxel", "0.5"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [json.loads(x) for x in r.stdout.strip().splitlines()]
+    stages = [x for x in lines if "stage" in x]
+    assert len(stages) == 2 and all(s["cost_last"] <= s["cost_first"] for s in stages)
+    # the oracle chain on the poses as the loader sees them (quaternions written with 15 digits, renormalised)
+    start = noisy.copy()
+    for i in range(len(start)):
+        start[i, :9] = dw.quat_to_R(dw.R_to_quat(noisy[i, :9].reshape(3, 3))).ravel()
+    ref = start
+    for k, vs in enumerate((1.0, 0.5)):
+        vp, pi, cl, _ = vox.voxelize(scans, ref, vs)
+        assert stages[k]["voxels"] == len(vp) - 1
+        ref, info = lo.damping_iter(vp, pi, cl, ref)
+        assert abs(stages[k]["cost_last"] - info["r_last"]) <= 1e-5 * info["r_last"]
+    got = np.loadtxt(out)
+    assert got.shape == (6, 8)
+    for i in range(6):
+        R = dw.quat_to_R(np.array([got[i, 7], got[i, 4], got[i, 5], got[i, 6]]))
+        assert np.abs(R - ref[i, :9].reshape(3, 3)).max() <= 1e-5 and np.abs(got[i, 1:4] - ref[i, 9:]).max() <= 1e-5
