@@ -16,9 +16,16 @@
 
 #include "../../include/lvba_b200.h"
 #include "envelope.cuh"
+#include "envelope_wide.h"
 #include "factor_la.cuh"
 
 namespace lvba {
+
+// one pass of the any-width factorisation (envelope_wide.h): grid-stride over its items
+template <class F>
+__global__ void __launch_bounds__(128) env_wide_pass_kernel(int64_t n, F f) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
+}
 
 // ---------------------------------------------------------------- errors
 inline std::string& last_error_ref() {
@@ -314,6 +321,9 @@ struct EnvSolver {
   int dbg_dumped = 0, dbg_max_dumps = 2;
   bool configured = false;
   bool force_generic = false;   // tests: exercise the wide-envelope kernel on narrow problems
+  // ---- any-width path (envelope_wide.h): columns taller than kEnvMaxCol blocks (loop closures), or forced by the tests
+  bool wide = false;
+  DevBuf<double> colT;          // [max_col * 36] unscaled copy of the current pivot column
   // ---- twisted (two-ended) factorisation: top half in natural order on one SM, bottom half reversed on another,
   //      joined at a separator of `tw_bs` rows (see envelope.cuh, FactorJob)
   bool tw = false;
@@ -325,12 +335,13 @@ struct EnvSolver {
   static int pval(int id) { return id == 0 ? 8 : id == 1 ? 12 : id == 2 ? 16 : id == 3 ? 21 : id == 4 ? 24 : 31; }
 
   int prepare(const Envelope& env, cudaStream_t s) {
-    if (env.max_col > kEnvMaxCol)
-      return fail(LVBA_ERR_UNSUPPORTED, "envelope column height %d exceeds the factor kernel limit %d", env.max_col, kEnvMaxCol);
     {
       const char* fg = getenv("LVBA_FORCE_GENERIC_SOLVER");      // tests: run the wide-envelope kernel on narrow problems
       force_generic = fg && fg[0] == '1';
+      const char* fw = getenv("LVBA_FORCE_WIDE_SOLVER");         // tests: run the any-width path on narrow problems
+      wide = env.max_col > kEnvMaxCol || (fw && fw[0] == '1');
     }
+    if (wide) LVBA_TRY(colT.alloc((size_t)std::max(env.max_col, 1) * 36));
     LVBA_TRY(L.alloc((size_t)env.nblocks * 36));
     LVBA_TRY(dinv.alloc((size_t)env.n * 36));
     LVBA_TRY(z.alloc((size_t)env.n * 6));
@@ -353,7 +364,7 @@ struct EnvSolver {
     // ---- twisted split: worthwhile when each half is many pivots long
     tw = false;
     const char* nt = getenv("LVBA_NO_TWIST");
-    const bool reg_ok = env.max_col <= 30 && env.n >= 3 && !force_generic;
+    const bool reg_ok = env.max_col <= 30 && env.n >= 3 && !force_generic && !wide;
     if (reg_ok && env.n >= 256 && !(nt && nt[0] == '1')) {
       const int n = env.n;
       const int m = n / 2;
@@ -440,6 +451,7 @@ struct EnvSolver {
   // Block-diagonal system of independent groups (window BA): group g owns rows grp[g]..grp[g+1]-1; every group
   // must fit the register window (<= 31 rows).  Call after prepare().
   int prepare_batch(const Envelope& env, const std::vector<int>& grp, cudaStream_t s) {
+    wide = false;                 // windows are <= 31 poses: always the register-window kernel, one CTA per window
     n_groups = (int)grp.size() - 1;
     grp_ptr = grp;
     std::vector<int> fr((size_t)env.n);
@@ -500,6 +512,20 @@ struct EnvSolver {
     env_add_diag_kernel<<<(n6 + 255) / 256, 256, 0, s>>>(v, dadd, L.p);
     ++*launches;
     const int mc = env.max_col;
+    if (wide) {
+      // ---------------- any width: every column step spread over the device (envelope_wide.h); 4 launches per block row
+      const wide::View wv{env.n, env.d_first.p, env.d_row_start.p};                                       // z holds the right-hand side (written by the caller)
+      int64_t n_launch = 0;
+      auto launch = [&](int64_t items, const auto& f) {
+        const int grid = (int)std::min<int64_t>((items + 127) / 128, 148 * 16);
+        env_wide_pass_kernel<<<grid, 128, 0, s>>>(items, f);
+        ++n_launch;
+      };
+      wide::factor_and_solve(launch, wv, env.first.data(), env.last.data(), L.p, dinv.p, z.p, colT.p, x, status.p);
+      *launches += n_launch;
+      LVBA_CUDA(cudaGetLastError());
+      return LVBA_OK;
+    }
     const bool reg_path = batch || (mc <= 30 && env.n >= 3 && !force_generic);
     if (reg_path) LVBA_TRY(build_jobs(env, x, s));
     if (batch) {

@@ -158,10 +158,12 @@ def _pick_distinct(rng, centre, half, n_items, counts):
     return cand, order, counts, width
 
 
-def make_lidar(n_poses, n_vox, R_gt, p_gt, rng, k_lo=2, k_hi=12, chunk=60_000):
+def make_lidar(n_poses, n_vox, R_gt, p_gt, rng, k_lo=2, k_hi=12, chunk=60_000, half=15):
+    """half: a voxel is seen from poses within +-half of its centre pose (15 = the band of the headline configs; larger
+    values give the loop-closure couplings that widen the envelope)."""
     c = rng.integers(0, n_poses, n_vox)
     K = rng.integers(k_lo, k_hi + 1, n_vox)
-    cand, order, K, _ = _pick_distinct(rng, c, 15, n_poses, K)
+    cand, order, K, _ = _pick_distinct(rng, c, half, n_poses, K)
     K = np.maximum(K, 2) if n_poses >= 2 else K
     vox_ptr = np.zeros(n_vox + 1, np.int64)
     np.cumsum(K, out=vox_ptr[1:])
@@ -255,7 +257,7 @@ def make_visual(n_cams, n_tracks, R_cw_gt, t_cw_gt, rng):
     return obs_ptr, obs_cam, obs_uv, X0, X_gt, plane_nd
 
 
-def make_problem(n_poses, n_vox, n_tracks, seed, lidar=True, visual=True):
+def make_problem(n_poses, n_vox, n_tracks, seed, lidar=True, visual=True, half=15):
     """Returns a dict of numpy arrays in exactly the layout the C-ABI takes
     (include/lvba_b200.h): CSR voxel->pose clusters; CSR track->camera obs."""
     rng = np.random.Generator(np.random.Philox(key=seed))
@@ -267,7 +269,7 @@ def make_problem(n_poses, n_vox, n_tracks, seed, lidar=True, visual=True):
     out["poses_gt"] = np.concatenate([R_gt.reshape(n_poses, 9), p_gt], 1)
     out["poses"] = np.concatenate([R0.reshape(n_poses, 9), p0], 1)
     if lidar and n_vox:
-        vp, pi, cl = make_lidar(n_poses, n_vox, R_gt, p_gt, rng)
+        vp, pi, cl = make_lidar(n_poses, n_vox, R_gt, p_gt, rng, half=half)
         out.update(vox_ptr=vp, pose_idx=pi, clusters=cl, n_vox=n_vox)
     if visual and n_tracks:
         Rc_gt, tc_gt = body_to_cam(R_gt, p_gt)
