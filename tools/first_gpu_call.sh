@@ -1,0 +1,39 @@
+#!/bin/bash
+# One gpurun call that collects, on a fresh B200 box, everything the set-up rows (B3 / B4), the any-width solver and the
+# off-ROS tool still lack on hardware, plus the standing evidence of the hot path.  Every step runs under its own timeout and
+# writes to gpurun_out/; nothing here changes clocks.  Usage (from the repo root, here):
+#     /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/first_gpu_call.sh'
+# Budget: ~12-15 min of box time.  Read the results here with `ncu -i gpurun_out/<x>.ncu-rep --page raw --csv`.
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+O=gpurun_out
+{
+  echo "== $(date -u +%FT%TZ) nvidia-smi"; nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv
+} > $O/00_env.txt 2>&1
+
+# 1. the GPU test suite, gating cases first, then the staged ones with their reasons (-rxX prints XFAIL / XPASS lines)
+timeout 900 python -m pytest tests -m gpu -q -rxX -p no:cacheprovider > $O/01_pytest_gpu.log 2>&1; echo "rc=$?" >> $O/01_pytest_gpu.log
+# the staged files once more WITHOUT their non-gating markers, so that a failure shows its traceback
+timeout 600 python -m pytest tests/test_zz_depth_gpu.py tests/test_zz_wide_gpu.py tests/test_zz_offline_gpu.py tests/test_zz_voxel_gpu.py \
+    -m gpu -q --runxfail -p no:cacheprovider > $O/02_pytest_staged_runxfail.log 2>&1; echo "rc=$?" >> $O/02_pytest_staged_runxfail.log
+
+# 2. bench line (includes the voxel_map / depth side measurement) and the set-up stages alone
+timeout 600 python bench.py --steps 30 --warmup 3 > $O/03_bench.json 2> $O/03_bench.err
+timeout 300 python tools/bench_voxel_map.py > $O/04_bench_setup_stages.json 2> $O/04_bench_setup_stages.err
+
+# 3. launch lists (durations only; numbers under ncu are never bench values)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/05_launches_setup_stages.csv \
+    python tools/bench_voxel_map.py --scans 200 --points 50000 --repeats 1 --cpu-sample-scans 0 > $O/05_launches_setup_stages.out 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/06_launches_bench.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-voxel-map > $O/06_launches_bench.out 2>&1
+
+# 4. full captures of the set-up stage's heaviest passes (segment sums, splat) — one launch each
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:SegmentSumF -s 1 -c 1 -o $O/07_segment_sum -f \
+    python tools/bench_voxel_map.py --scans 200 --points 50000 --repeats 1 --cpu-sample-scans 0 > $O/07_segment_sum.out 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:SplatF -s 1 -c 1 -o $O/08_splat -f \
+    python tools/bench_voxel_map.py --scans 200 --points 50000 --repeats 1 --cpu-sample-scans 0 > $O/08_splat.out 2>&1
+
+# 5. the four-chunk solve experiment with 10 right-hand sides per spike CTA (tools/lab, not in the product)
+if [ -x tools/lab/chunk_lab ]; then timeout 300 tools/lab/chunk_lab > $O/09_chunk_lab.txt 2>&1; fi
+ls -la $O > $O/99_listing.txt
