@@ -2,8 +2,8 @@
 # One gpurun call that collects, on a fresh B200 box, everything the set-up rows (B3 / B4), the any-width solver and the
 # off-ROS tool still lack on hardware, plus the standing evidence of the hot path.  Every step runs under its own timeout and
 # writes to gpurun_out/; nothing here changes clocks.  Usage (from the repo root, here):
-#     /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/first_gpu_call.sh'
-# Budget: ~12-15 min of box time.  Read the results here with `ncu -i gpurun_out/<x>.ncu-rep --page raw --csv`.
+#     /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/first_gpu_call.sh'
+# Budget: ~20-25 min of box time (the GPU suite alone is several minutes).  Read the results here with `ncu -i gpurun_out/<x>.ncu-rep --page raw --csv`.
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -13,7 +13,7 @@ O=gpurun_out
 } > $O/00_env.txt 2>&1
 
 # 1. the GPU test suite, gating cases first, then the staged ones with their reasons (-rxX prints XFAIL / XPASS lines)
-timeout 900 python -m pytest tests -m gpu -q -rxX -p no:cacheprovider > $O/01_pytest_gpu.log 2>&1; echo "rc=$?" >> $O/01_pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -q -rxX -p no:cacheprovider > $O/01_pytest_gpu.log 2>&1; echo "rc=$?" >> $O/01_pytest_gpu.log
 # the staged files once more WITHOUT their non-gating markers, so that a failure shows its traceback
 timeout 600 python -m pytest tests/test_zz_depth_gpu.py tests/test_zz_wide_gpu.py tests/test_zz_offline_gpu.py tests/test_zz_voxel_gpu.py \
     -m gpu -q --runxfail -p no:cacheprovider > $O/02_pytest_staged_runxfail.log 2>&1; echo "rc=$?" >> $O/02_pytest_staged_runxfail.log
