@@ -6,6 +6,7 @@
 
 #include "comm.cuh"
 #include "lidar.cuh"
+#include "lidar_big.h"
 #include "runtime.cuh"
 
 namespace lvba {
@@ -73,6 +74,15 @@ __global__ void lidar_aos_to_soa_gather_kernel(long long nnz, long long nnz_pad,
 // Pair table of the Hessian build (one word per pose pair of every voxel: li | lj << 8 | lv << 16), generated on the
 // device from the voxel CSR: thread = local slot x of the batch, it writes the pairs (x, y), y > x, of its voxel in the
 // order the build kernel walks them.  (5.2 M words for config C: 6 ms of host loops + a 21 MB upload otherwise.)
+// out[i] = aos[src[i]]   (10-double cluster records)
+__global__ void lidar_gather_aos_kernel(long long n, const int* __restrict__ src, const double* __restrict__ aos, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* a = aos + 10 * (long long)src[i];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) out[10 * i + k] = a[k];
+}
+
 __global__ void __launch_bounds__(kSlots)
 lidar_pairs_kernel(int n_batches, const int* __restrict__ vox_ptr, const int* __restrict__ batch_vox,
                    const long long* __restrict__ batch_pair, unsigned* __restrict__ pairs) {
@@ -135,6 +145,14 @@ struct lvba_lidar_problem {
   lvba::DevBuf<int> d_grp_ptr, d_pose_grp, d_grp_batch, d_accept;
   lvba::DevBuf<double> d_u_grp, d_grp_scal;
   double* h_grp_scal = nullptr;        // pinned [4G]: r1 sum, q1, bad flag, r2 sum per window
+  // ---- voxels seen from more than kSlots poses: outside the batches, through the passes of lidar_big.h
+  long long n_big = 0, n_big_slots = 0, n_big_pairs = 0;
+  lvba::DevBuf<int64_t> big_vox_ptr, big_pair_ptr;
+  lvba::DevBuf<int32_t> big_pose;
+  lvba::DevBuf<double> big_cl, big_params, big_feat;
+  lvba::big::View big_view() const {
+    return lvba::big::View{(int64_t)n_big, big_vox_ptr.p, big_pose.p, big_cl.p, big_pair_ptr.p, env.d_first.p, env.d_row_start.p};
+  }
 
   lvba::LidarView view() const {
     lvba::LidarView v_;
@@ -165,7 +183,6 @@ inline int lidar_validate(int32_t W, int64_t V, const int64_t* vox_ptr, const in
       const int64_t lo = vox_ptr[a], hi = vox_ptr[a + 1];
       int kind = 0; int64_t aux = 0;
       if (hi <= lo) kind = 1;
-      else if (hi - lo > kSlots) { kind = 2; aux = hi - lo; }
       else
         for (int64_t s = lo; s < hi; ++s) {
           const int p = pose_idx[s];
@@ -180,7 +197,6 @@ inline int lidar_validate(int32_t W, int64_t V, const int64_t* vox_ptr, const in
     const long long a = (long long)bad_at[w];
     switch (bad_kind[w]) {
       case 1: return fail(LVBA_ERR_INVALID_ARG, "voxel %lld has no slots (vox_ptr not increasing)", a);
-      case 2: return fail(LVBA_ERR_UNSUPPORTED, "voxel %lld is observed from %lld poses; this build handles <= %d per voxel", a, (long long)bad_aux[w], kSlots);
       case 3: return fail(LVBA_ERR_INVALID_ARG, "pose_idx[%lld]=%d out of [0,%d)", (long long)bad_aux[w], pose_idx[bad_aux[w]], W);
       default: return fail(LVBA_ERR_INVALID_ARG, "pose_idx must be strictly ascending inside voxel %lld", a);
     }
@@ -255,6 +271,16 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
     if (!cm.active() || shard_owner(pose_idx[vox_ptr[a]], W, cm.n_ranks) == cm.rank) mine.push_back(a);
   if (n_groups > 0)      // windows in order: batches and their partial sums become contiguous per window
     std::stable_sort(mine.begin(), mine.end(), [&](int64_t x, int64_t y) { return pose_grp[pose_idx[vox_ptr[x]]] < pose_grp[pose_idx[vox_ptr[y]]]; });
+  // voxels seen from more than kSlots poses do not fit a batch CTA: they leave `mine` and take the passes of lidar_big.h
+  std::vector<int64_t> bigv;
+  {
+    std::vector<int64_t> small;
+    for (int64_t a : mine) if (vox_ptr[a + 1] - vox_ptr[a] > kSlots) bigv.push_back(a);
+    if (!bigv.empty()) {
+      for (int64_t a : mine) if (vox_ptr[a + 1] - vox_ptr[a] <= kSlots) small.push_back(a);
+      mine.swap(small);
+    }
+  }
   const int64_t Vl = (int64_t)mine.size();
   std::vector<int> l_vox_ptr(Vl + 1, 0);
   for (int64_t i = 0; i < Vl; ++i) l_vox_ptr[i + 1] = l_vox_ptr[i] + (int)(vox_ptr[mine[i] + 1] - vox_ptr[mine[i]]);
@@ -345,6 +371,34 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
         lidar_aos_to_soa_gather_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(nnz, nnz_pad, aos_src, d_src.p, P->cl.p);
         ++P->launches;
       }
+      if (!bigv.empty()) {                   // the big voxels' records stay AoS (lidar_big.h reads them slot by slot)
+        std::vector<int64_t> bvp{0}, bpp{0};
+        std::vector<int32_t> bpose;
+        std::vector<int> bsrc;
+        for (int64_t a : bigv) {
+          for (int64_t q = vox_ptr[a]; q < vox_ptr[a + 1]; ++q) { bsrc.push_back((int)q); bpose.push_back(pose_idx[q]); }
+          const int64_t K = vox_ptr[a + 1] - vox_ptr[a];
+          bvp.push_back((int64_t)bsrc.size());
+          bpp.push_back(bpp.back() + K * (K - 1) / 2);
+        }
+        P->n_big = (long long)bigv.size(); P->n_big_slots = (long long)bsrc.size(); P->n_big_pairs = bpp.back();
+        if (!aos_src) {                      // no slot of this rank was small: the records are not on the device yet
+          LVBA_CUDA(cudaMemcpyAsync(aos.p, clusters, (size_t)nnz_all * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
+          P->h2d += nnz_all * 80;
+          aos_src = aos.p;
+        }
+        DevBuf<int> d_bsrc;
+        LVBA_TRY(d_bsrc.upload(bsrc, s, &P->h2d));
+        LVBA_TRY(P->big_vox_ptr.upload(bvp, s, &P->h2d));
+        LVBA_TRY(P->big_pair_ptr.upload(bpp, s, &P->h2d));
+        LVBA_TRY(P->big_pose.upload(bpose, s, &P->h2d));
+        LVBA_TRY(P->big_cl.alloc((size_t)P->n_big_slots * 10));
+        LVBA_TRY(P->big_params.alloc((size_t)P->n_big * big::kParams));
+        LVBA_TRY(P->big_feat.alloc((size_t)P->n_big_slots * big::kFeat));
+        lidar_gather_aos_kernel<<<(unsigned)((P->n_big_slots + 255) / 256), 256, 0, s>>>(P->n_big_slots, d_bsrc.p, aos_src, P->big_cl.p);
+        ++P->launches;
+        LVBA_CUDA(cudaStreamSynchronize(s)); // the host vectors and d_bsrc go out of scope
+      }
       LVBA_CUDA(cudaStreamSynchronize(s));   // aos, src, d_src are freed on scope exit
     }
   }
@@ -366,7 +420,7 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   LVBA_TRY(P->diag.alloc((size_t)W * 6));
   LVBA_TRY(P->dadd.alloc((size_t)W * 6));
   LVBA_TRY(P->dx.alloc((size_t)W * 6));
-  LVBA_TRY(P->batch_res.alloc((size_t)std::max(P->n_batches, 1)));
+  LVBA_TRY(P->batch_res.alloc((size_t)std::max<long long>(P->n_batches + P->n_big, 1)));
   LVBA_TRY(P->scal.alloc(8));
   LVBA_TRY(P->scal.zero(s));
   LVBA_CUDA(cudaFuncSetAttribute(lidar_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lidar_build_smem_bytes()));
@@ -375,6 +429,25 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   lvba_lidar_default_opts(&P->opts);
   P->ms_setup = wall_ms() - t0;
   *out = P.release();
+  return LVBA_OK;
+}
+
+// voxels seen from more than kSlots poses (lidar_big.h): lambda_0 of voxel b -> batch_res[n_batches + b]; with the Hessian,
+// their gradient / diagonal-block / pair-block contributions are added to g and H by atomics
+inline int lidar_big_passes(lvba_lidar_problem* P, const double* d_poses, bool residual_only) {
+  cudaStream_t s = P->stream;
+  const big::View bv = P->big_view();
+  auto launch = [&](int64_t items, const auto& f) {
+    const int grid = (int)std::min<int64_t>((items + 127) / 128, 148 * 16);
+    env_wide_pass_kernel<<<grid, 128, 0, s>>>(items, f);
+    ++P->launches;
+  };
+  launch((int64_t)P->n_big, big::ParamsF{bv, d_poses, P->big_params.p, P->batch_res.p + P->n_batches});
+  if (!residual_only) {
+    launch((int64_t)P->n_big_slots, big::SlotsF{bv, d_poses, P->big_params.p, P->big_feat.p, P->H.p, P->g.p});
+    launch((int64_t)P->n_big_pairs, big::PairsF{bv, P->big_params.p, P->big_feat.p, P->H.p});
+  }
+  LVBA_CUDA(cudaGetLastError());
   return LVBA_OK;
 }
 
@@ -387,7 +460,8 @@ inline int lidar_build_dev(lvba_lidar_problem* P, const double* d_poses, int slo
     lidar_build_kernel<<<P->n_batches, kSlots, lidar_build_smem_bytes(), s>>>(P->view(), P->env.view(), d_poses, P->H.p, P->g.p, P->batch_res.p);
     ++P->launches;
   }
-  reduce_partials_kernel<<<1, 256, 0, s>>>(P->batch_res.p, P->n_batches, P->scal.p + slot);
+  if (P->n_big > 0) LVBA_TRY(lidar_big_passes(P, d_poses, /*residual_only=*/false));
+  reduce_partials_kernel<<<1, 256, 0, s>>>(P->batch_res.p, (int)(P->n_batches + P->n_big), P->scal.p + slot);
   ++P->launches;
   LVBA_CUDA(cudaGetLastError());
   Comm& cm = comm();
@@ -405,7 +479,8 @@ inline int lidar_residual_dev(lvba_lidar_problem* P, const double* d_poses, int 
     lidar_residual_kernel<<<P->n_batches, kSlots, 0, s>>>(P->view(), d_poses, P->batch_res.p);
     ++P->launches;
   }
-  reduce_partials_kernel<<<1, 256, 0, s>>>(P->batch_res.p, P->n_batches, P->scal.p + slot);
+  if (P->n_big > 0) LVBA_TRY(lidar_big_passes(P, d_poses, /*residual_only=*/true));
+  reduce_partials_kernel<<<1, 256, 0, s>>>(P->batch_res.p, (int)(P->n_batches + P->n_big), P->scal.p + slot);
   ++P->launches;
   LVBA_CUDA(cudaGetLastError());
   Comm& cm = comm();

@@ -80,3 +80,37 @@ def test_loop_closure_problem_follows_the_oracle():
     assert abs(s["cost_last"] - info["r_last"]) <= 1e-6 * info["r_last"]
     assert np.abs(out - ref_poses).max() <= 1e-6
     """, timeout=900)
+
+
+@pytest.mark.gpu
+def test_voxels_seen_from_hundreds_of_poses():
+    """K > 128 poses per voxel (csrc/lidar_big.h) together with the any-width solver: H, g, the damped step and the LM
+    against the oracle."""
+    _run("""
+    rng = np.random.Generator(np.random.Philox(key=77))
+    W = 300
+    R_gt, p_gt = synth.make_trajectory(W, rng)
+    vp_b, pi_b, cl_b = synth.make_lidar(W, 5, R_gt, p_gt, rng, k_lo=200, k_hi=260, half=W - 1)       # five big voxels
+    vp_s, pi_s, cl_s = synth.make_lidar(W, 1500, R_gt, p_gt, rng)                                       # and ordinary ones around them
+    vp = np.concatenate([vp_s, vp_b[1:] + vp_s[-1]]); pi = np.concatenate([pi_s, pi_b]); cl = np.concatenate([cl_s, cl_b])
+    order = np.random.default_rng(1).permutation(len(vp) - 1)                                           # big voxels anywhere in the list
+    K = np.diff(vp); starts = vp[:-1]
+    pi = np.concatenate([pi[starts[a]:starts[a] + K[a]] for a in order]); cl = np.concatenate([cl[starts[a]:starts[a] + K[a]] for a in order])
+    vp = np.concatenate([[0], np.cumsum(K[order])])
+    assert np.diff(vp).max() > 128
+    R0 = R_gt @ synth.so3_exp(rng.normal(0, 0.003, (W, 3)))
+    poses = np.concatenate([R0.reshape(W, 9), p_gt + rng.normal(0, 0.02, (W, 3))], 1)
+    P = pkg.LidarProblem(vp, pi, cl, poses)
+    r = P.build()
+    r_ref, g_ref, blocks = lo.acc_evaluate2(vp, pi, cl, poses, W)
+    g, br, bc, bl = P.get_system()
+    H = pkg.env_blocks_to_dense(br, bc, bl, W); H_ref = lo.assemble_dense(blocks, W)
+    assert abs(r - r_ref) <= 1e-8 * abs(r_ref)
+    assert np.abs(g - g_ref).max() <= 1e-7 * np.abs(g_ref).max()
+    assert np.abs(H - H_ref).max() <= 1e-7 * np.abs(H_ref).max()
+    assert abs(P.residual(poses) - lo.only_residual(vp, pi, cl, poses)) <= 1e-8 * abs(r_ref)
+    P.close()
+    out, s = pkg.lidar_lm(vp, pi, cl, poses)
+    ref_poses, info = lo.damping_iter(vp, pi, cl, poses)
+    assert abs(s["cost_last"] - info["r_last"]) <= 1e-6 * info["r_last"] and np.abs(out - ref_poses).max() <= 1e-6
+    """, timeout=900)
