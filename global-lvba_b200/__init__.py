@@ -38,6 +38,7 @@ EXPORTS = [
     "lvba_voxel_map_lidar_lm_batch", "lvba_voxel_map_summary", "lvba_voxel_map_export",
     "lvba_voxel_map_lookup", "lvba_voxel_map_lidar_create", "lvba_voxel_map_lidar_lm", "lvba_voxel_map_destroy",
     "lvba_depth_grid_create", "lvba_depth_render", "lvba_depth_backproject", "lvba_depth_grid_destroy",
+    "lvba_tracks_triangulate", "lvba_tracks_mean_reproj",
     "lvba_comm_unique_id", "lvba_comm_init", "lvba_comm_destroy", "lvba_comm_info", "lvba_shard_owner",
 ]
 
@@ -530,6 +531,34 @@ class DepthGrid:
                                               _p(it, C.c_double), C.c_int32(width), C.c_int32(height), _p(kp, C.c_int64), _p(uv, C.c_float),
                                               _p(Xw, C.c_double), _p(valid, C.c_uint8), C.byref(s)))
         return Xw, valid, s.as_dict()
+
+
+# ------------------------------------------------------------------ B5: per-track numerics of the track fusion
+def _track_args(obs_ptr, obs_cam, obs_uv, cams, intr):
+    return (np.ascontiguousarray(obs_ptr, np.int64), np.ascontiguousarray(obs_cam, np.int32), np.ascontiguousarray(obs_uv, np.float32).reshape(-1, 2),
+            _f64(cams).reshape(-1, 12), _f64(intr))
+
+
+def tracks_triangulate(obs_ptr, obs_cam, obs_uv, cams, intr, device=-1):
+    """TriangulateTrackDLT (lvba_system.cpp:52-111) of every track.  Returns (Xw (T, 3), mean_reproj, count, ok)."""
+    op, oc, uv, cm, it = _track_args(obs_ptr, obs_cam, obs_uv, cams, intr)
+    T = len(op) - 1
+    Xw = np.zeros((T, 3)); mean = np.zeros(T); cnt = np.zeros(T, np.int32); ok = np.zeros(T, np.uint8)
+    _chk(load_library().lvba_tracks_triangulate(C.c_int64(T), _p(op, C.c_int64), _p(oc, C.c_int32), _p(uv, C.c_float), C.c_int32(len(cm)),
+                                                _p(cm, C.c_double), _p(it, C.c_double), C.c_int32(device), _p(Xw, C.c_double),
+                                                _p(mean, C.c_double), _p(cnt, C.c_int32), _p(ok, C.c_uint8)))
+    return Xw, mean, cnt, ok
+
+
+def tracks_mean_reproj(obs_ptr, obs_cam, obs_uv, cams, intr, Xw, min_count, device=-1):
+    """ComputeMeanReproj (lvba_system.cpp:8-50) of one 3-D point per track.  Returns (mean_reproj, count, ok)."""
+    op, oc, uv, cm, it = _track_args(obs_ptr, obs_cam, obs_uv, cams, intr)
+    T = len(op) - 1
+    X = _f64(Xw).reshape(-1, 3); mean = np.zeros(T); cnt = np.zeros(T, np.int32); ok = np.zeros(T, np.uint8)
+    _chk(load_library().lvba_tracks_mean_reproj(C.c_int64(T), _p(op, C.c_int64), _p(oc, C.c_int32), _p(uv, C.c_float), C.c_int32(len(cm)),
+                                                _p(cm, C.c_double), _p(it, C.c_double), C.c_int32(device), _p(X, C.c_double),
+                                                C.c_int32(min_count), _p(mean, C.c_double), _p(cnt, C.c_int32), _p(ok, C.c_uint8)))
+    return mean, cnt, ok
 
 
 # ------------------------------------------------------------------ multi-GPU

@@ -6,6 +6,7 @@
 #include "visual_api.cuh"
 #include "voxel_api.cuh"
 #include "depth_api.cuh"
+#include "track_api.cuh"
 
 extern "C" {
 

@@ -340,6 +340,25 @@ int lvba_depth_backproject(lvba_depth_grid* g, int32_t n_images, const double* c
 int lvba_depth_grid_destroy(lvba_depth_grid* g);
 
 /* ======================================================================================
+ * B5  per-track numerics of the track fusion (BuildTracksAndFuse3D, src/lvba_system.cpp:921-1263), many tracks at once:
+ *       TriangulateTrackDLT   src/lvba_system.cpp:52-111    lvba_tracks_triangulate
+ *       ComputeMeanReproj     src/lvba_system.cpp:8-50      lvba_tracks_mean_reproj
+ *     The caller keeps what is inherently sequential there — connected components over the match graph, one observation
+ * per image, the greedy view-angle filter (its result depends on the iteration order of std::unordered_map) — and passes the
+ * SELECTED observations of every track (`selected_ids`) as a CSR list.
+ *   obs_ptr [n_tracks+1]; obs_cam [n_obs] image id of each selected observation (ids outside [0, n_cams) are skipped, :74-78);
+ *   obs_uv [n_obs*2] float keypoint; cams [n_cams*12] Rcw row-major + tcw (Rcw_all_optimized_ / tcw_all_optimized_)
+ *   triangulate: Xw [n_tracks*3], mean_reproj, count, ok (the function's bool) out; fewer than 4 observations / 8 rows -> ok = 0
+ *   mean_reproj: Xw in (e.g. the depth-fused candidate), min_count = obser_thr_ (:1098) or 4 (:108)
+ * ====================================================================================== */
+int lvba_tracks_triangulate(int64_t n_tracks, const int64_t* obs_ptr, const int32_t* obs_cam, const float* obs_uv, int32_t n_cams,
+                            const double* cams, const double intr[8], int32_t device, double* Xw, double* mean_reproj,
+                            int32_t* count, uint8_t* ok);
+int lvba_tracks_mean_reproj(int64_t n_tracks, const int64_t* obs_ptr, const int32_t* obs_cam, const float* obs_uv, int32_t n_cams,
+                            const double* cams, const double intr[8], int32_t device, const double* Xw, int32_t min_count,
+                            double* mean_reproj, int32_t* count, uint8_t* ok);
+
+/* ======================================================================================
  * Multi-GPU (one process per GPU).  The path shards by contiguous pose-block rows
  * (SURVEY.md §8e): voxel / track -> owner of its lowest pose / camera index.  Every rank
  * passes the FULL problem to *_create; after lvba_comm_init each rank keeps only its shard

@@ -144,3 +144,18 @@ def test_windowed_voxel_map_argument_checks_need_no_gpu(pkg):
         with pytest.raises(pkg.LvbaError) as e:
             pkg.VoxelMap(scans, poses, win_ptr=[0, 2, 3])
         assert e.value.status == -2
+
+
+def test_track_numerics_argument_checks_need_no_gpu(pkg):
+    cams = np.tile(np.concatenate([np.eye(3).ravel(), np.zeros(3)]), (2, 1)); intr = np.array([100.0, 100, 50, 50, 0, 0, 0, 0])
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.tracks_triangulate([0, 3, 2], np.zeros(3, np.int32), np.zeros((3, 2), np.float32), cams, intr)      # non-monotone CSR
+    assert e.value.status == -1
+    bad = intr.copy(); bad[4] = np.nan
+    with pytest.raises(pkg.LvbaError) as e:
+        pkg.tracks_mean_reproj([0, 2], np.zeros(2, np.int32), np.zeros((2, 2), np.float32), cams, bad, np.zeros((1, 3)), 2)
+    assert e.value.status == -1
+    if pkg.device_count() == 0:
+        with pytest.raises(pkg.LvbaError) as e:
+            pkg.tracks_triangulate([0, 2], np.zeros(2, np.int32), np.zeros((2, 2), np.float32), cams, intr)
+        assert e.value.status == -2

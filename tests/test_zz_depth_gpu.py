@@ -130,3 +130,33 @@ def test_shim_depth_renderer(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe), "depth"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "depth ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_track_numerics_equal_numpy_restatement():
+    """Boundary B5 (DLT triangulation + mean reprojection of many tracks) against oracle/track_oracle.py."""
+    _run("""
+    from oracle import dataset_writer as dw, track_oracle as tro
+    p = synth.make_problem(40, 0, 400, seed=9, lidar=False)
+    cams = np.zeros((40, 12))
+    for k in range(40):
+        cams[k, :9] = dw.quat_to_R(p["q_gt"][k]).ravel(); cams[k, 9:] = p["t_gt"][k]
+    op, oc, uv, intr = p["obs_ptr"], p["obs_cam"].copy(), p["obs_uv"], p["intr"]
+    oc[op[7]] = 99
+    Xw, mean, cnt, ok = pkg.tracks_triangulate(op, oc, uv, cams, intr)
+    n_ok = 0
+    for t in range(len(op) - 1):
+        sel = [q for q in range(op[t], op[t + 1]) if 0 <= oc[q] < 40]
+        r_ok, X, m, c = tro.triangulate_dlt(cams[oc[sel]], uv[sel], intr) if op[t + 1] - op[t] >= 4 else (False, np.zeros(3), 0.0, 0)
+        assert bool(ok[t]) == r_ok
+        if r_ok:
+            n_ok += 1
+            assert np.abs(Xw[t] - X).max() <= 1e-7 * max(1.0, np.abs(X).max()) and abs(mean[t] - m) <= 1e-7 and cnt[t] == c
+    assert n_ok > 100
+    X = p["X_gt"] + 0.01
+    mean, cnt, ok = pkg.tracks_mean_reproj(op, p["obs_cam"], uv, cams, intr, X, 5)
+    for t in range(0, len(op) - 1, 7):
+        sel = list(range(op[t], op[t + 1]))
+        r_ok, m, c = tro.mean_reproj(X[t], cams[p["obs_cam"][sel]], uv[sel], intr, 5)
+        assert bool(ok[t]) == r_ok and cnt[t] == c and (not r_ok or abs(mean[t] - m) <= 1e-9)
+    """)
