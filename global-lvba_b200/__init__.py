@@ -39,6 +39,7 @@ EXPORTS = [
     "lvba_voxel_map_lookup", "lvba_voxel_map_lidar_create", "lvba_voxel_map_lidar_lm", "lvba_voxel_map_destroy",
     "lvba_depth_grid_create", "lvba_depth_render", "lvba_depth_backproject", "lvba_depth_grid_destroy",
     "lvba_tracks_triangulate", "lvba_tracks_mean_reproj",
+    "lvba_anchor_clouds_create", "lvba_anchor_clouds_export", "lvba_anchor_clouds_destroy",
     "lvba_comm_unique_id", "lvba_comm_init", "lvba_comm_destroy", "lvba_comm_info", "lvba_shard_owner",
 ]
 
@@ -559,6 +560,26 @@ def tracks_mean_reproj(obs_ptr, obs_cam, obs_uv, cams, intr, Xw, min_count, devi
                                                 _p(cm, C.c_double), _p(it, C.c_double), C.c_int32(device), _p(X, C.c_double),
                                                 C.c_int32(min_count), _p(mean, C.c_double), _p(cnt, C.c_int32), _p(ok, C.c_uint8)))
     return mean, cnt, ok
+
+
+# ------------------------------------------------------------------ B6: anchor clouds
+def anchor_clouds(scans, rel_poses, win_ptr, leaf=0.1, device=-1):
+    """Tail of runWindowBA's window loop (lvba_system.cpp:284-301): returns [one (n_w, 3) float32 cloud per window]."""
+    lib = load_library()
+    S = len(scans)
+    sp = np.zeros(S + 1, np.int64)
+    sp[1:] = np.cumsum([len(s) for s in scans])
+    xyz = np.ascontiguousarray(np.concatenate([np.asarray(s, np.float32).reshape(-1, 3) for s in scans]) if S else np.zeros((0, 3)), np.float32)
+    wp = np.ascontiguousarray(win_ptr, np.int32); rl = _f64(rel_poses)
+    h = C.c_void_p(); n = C.c_int64()
+    _chk(lib.lvba_anchor_clouds_create(C.c_int32(len(wp) - 1), _p(wp, C.c_int32), _p(sp, C.c_int64), _p(xyz, C.c_float), C.c_int32(3),
+                                       _p(rl, C.c_double), C.c_double(leaf), C.c_int32(device), C.byref(h), C.byref(n)))
+    cp = np.zeros(len(wp), np.int64); out = np.zeros((n.value, 3), np.float32)
+    try:
+        _chk(lib.lvba_anchor_clouds_export(h, _p(cp, C.c_int64), _p(out, C.c_float), None))
+    finally:
+        lib.lvba_anchor_clouds_destroy(h)
+    return [out[cp[w]:cp[w + 1]] for w in range(len(wp) - 1)]
 
 
 # ------------------------------------------------------------------ multi-GPU

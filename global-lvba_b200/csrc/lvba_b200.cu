@@ -7,6 +7,7 @@
 #include "voxel_api.cuh"
 #include "depth_api.cuh"
 #include "track_api.cuh"
+#include "anchor_api.cuh"
 
 extern "C" {
 

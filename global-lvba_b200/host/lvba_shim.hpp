@@ -13,6 +13,9 @@
 //                                                    plane lookup of recompute_local_planes (:1529-1566)
 //   lvba_b200::run_window_stage                      the whole window loop of runWindowBA (src/lvba_system.cpp:232-266): one voxel
 //                                                    map per window built together + every window solved in one batched LM
+//   lvba_b200::run_window_ba                         all of runWindowBA (:205-316): the window stage, then the anchors — aligned window
+//                                                    poses, rel_poses_to_anchor_, anchor_index_per_frame_, anchor poses and the
+//                                                    merged + down-sampled anchor clouds (boundary B6)
 //   lvba_b200::DepthRenderer                         replaces buildGridMapFromOptimized + generateDepthWithVoxel
 //                                                    (src/lvba_system.cpp:1266-1338, 835-919)
 //
@@ -264,6 +267,97 @@ inline int run_window_stage(const CloudPtrVec& pl_fulls, const PoseVec& x_buf_fu
     x_wins.push_back(std::move(x_win));
   }
   if (summaries) *summaries = local;
+  return LVBA_OK;
+}
+
+// ---- all of runWindowBA (src/lvba_system.cpp:205-316).  After the window stage (run_window_stage) every window that was
+//      solved becomes an anchor: its poses are re-aligned to the odometry start when use_window_ba_rel is set (:268-278), every
+//      scan is expressed relative to the window's first odometry pose (:284-296) and the scans are merged and down-sampled into the
+//      anchor cloud (:288-298, boundary B6).  Skipped windows produce no anchor, exactly as the `continue` at :265.
+struct AnchorCloud { struct P3 { float x, y, z; }; std::vector<P3> points; };
+template <class PoseVec>
+struct WindowBAResult {
+  PoseVec anchor_poses;                          // one per solved window: x_win_odom[0]
+  std::vector<AnchorCloud> anchor_clouds;        // the merged, down-sampled cloud of each anchor (anchor frame)
+  PoseVec rel_poses_to_anchor;                   // per frame (identity where the frame has no anchor)
+  std::vector<int> anchor_index_per_frame;       // -1 where the frame's window was skipped
+  std::vector<lvba_summary> summaries;           // per window
+  int win_total = 0, win_skipped = 0;
+};
+
+template <class CloudPtrVec, class PoseVec>
+inline int run_window_ba(const CloudPtrVec& pl_fulls, const PoseVec& x_buf_full, int window_size, double root_voxel_size,
+                         const float eigen_ratio_array[4], double anchor_leaf, bool use_window_ba_rel, WindowBAResult<PoseVec>& res,
+                         const lvba_lidar_opts* opts = nullptr) {
+  std::vector<PoseVec> x_wins;
+  int rc = run_window_stage(pl_fulls, x_buf_full, window_size, root_voxel_size, eigen_ratio_array, x_wins, &res.summaries, nullptr, opts);
+  if (rc != LVBA_OK) return rc;
+  const int total_size = (int)std::min(pl_fulls.size(), x_buf_full.size());
+  res.anchor_poses.clear(); res.anchor_clouds.clear();
+  res.rel_poses_to_anchor.assign(x_buf_full.begin(), x_buf_full.begin() + total_size);
+  res.anchor_index_per_frame.assign((size_t)total_size, -1);
+  for (int i = 0; i < total_size; ++i) {                       // rel_poses_to_anchor_[i].setZero() = identity (:223)
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) res.rel_poses_to_anchor[i].R(r, c) = r == c ? 1.0 : 0.0; res.rel_poses_to_anchor[i].p(r) = 0.0; }
+  }
+  res.win_total = (int)x_wins.size(); res.win_skipped = 0;
+  auto mul3 = [](const double* A, const double* B, double* C) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j]; };
+  auto get = [](const auto& x, double* R, double* p) { for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R[3 * r + c] = x.R(r, c); p[r] = x.p(r); } };
+  std::vector<int32_t> win_ptr{0};
+  std::vector<int64_t> scan_ptr{0};
+  std::vector<float> xyz;
+  std::vector<double> rel_all;
+  int start = 0;
+  for (size_t w = 0; w < x_wins.size(); ++w) {
+    const int curr = (int)x_wins[w].size();
+    if (res.summaries[w].termination == LVBA_TERM_SKIPPED) { ++res.win_skipped; start += curr; continue; }
+    double Ro[9], po[3], Rq[9], pq[3], Ralign[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, palign[3] = {0, 0, 0};
+    get(x_buf_full[start], Ro, po);                            // anchor_pose = x_win_odom[0]
+    if (use_window_ba_rel) {                                   // R_align = odom0.R * opt0.R^T ; p_align = odom0.p - R_align * opt0.p
+      get(x_wins[w][0], Rq, pq);
+      const double Rqt[9] = {Rq[0], Rq[3], Rq[6], Rq[1], Rq[4], Rq[7], Rq[2], Rq[5], Rq[8]};
+      mul3(Ro, Rqt, Ralign);
+      for (int i = 0; i < 3; ++i) palign[i] = po[i] - (Ralign[3 * i] * pq[0] + Ralign[3 * i + 1] * pq[1] + Ralign[3 * i + 2] * pq[2]);
+    }
+    const double Rot[9] = {Ro[0], Ro[3], Ro[6], Ro[1], Ro[4], Ro[7], Ro[2], Ro[5], Ro[8]};
+    const int anchor_idx = (int)res.anchor_poses.size();
+    for (int j = 0; j < curr; ++j) {
+      double Ra[9], pa[3];
+      if (use_window_ba_rel) {                                 // x_win_aligned[j] = (R_align x.R, R_align x.p + p_align)
+        double Rx[9], px[3];
+        get(x_wins[w][j], Rx, px);
+        mul3(Ralign, Rx, Ra);
+        for (int i = 0; i < 3; ++i) pa[i] = (Ralign[3 * i] * px[0] + Ralign[3 * i + 1] * px[1] + Ralign[3 * i + 2] * px[2]) + palign[i];
+      } else {
+        get(x_buf_full[start + j], Ra, pa);                    // x_win_aligned = x_win_odom (:277)
+      }
+      double Rr[9], d[3] = {pa[0] - po[0], pa[1] - po[1], pa[2] - po[2]}, pr[3];
+      mul3(Rot, Ra, Rr);                                       // rel.R = anchor.R^T * aligned.R ; rel.p = anchor.R^T (aligned.p - anchor.p)
+      for (int i = 0; i < 3; ++i) pr[i] = Rot[3 * i] * d[0] + Rot[3 * i + 1] * d[1] + Rot[3 * i + 2] * d[2];
+      auto& rel = res.rel_poses_to_anchor[start + j];
+      for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) rel.R(r, c) = Rr[3 * r + c]; rel.p(r) = pr[r]; }
+      res.anchor_index_per_frame[start + j] = anchor_idx;
+      rel_all.insert(rel_all.end(), Rr, Rr + 9); rel_all.insert(rel_all.end(), pr, pr + 3);
+      for (const auto& pt : pl_fulls[start + j]->points) { xyz.push_back(pt.x); xyz.push_back(pt.y); xyz.push_back(pt.z); }
+      scan_ptr.push_back((int64_t)xyz.size() / 3);
+    }
+    win_ptr.push_back((int32_t)scan_ptr.size() - 1);
+    res.anchor_poses.push_back(x_buf_full[start]);
+    start += curr;
+  }
+  const int n_anchor = (int)win_ptr.size() - 1;
+  res.anchor_clouds.assign((size_t)n_anchor, AnchorCloud());
+  if (n_anchor == 0) return LVBA_OK;
+  lvba_anchor_clouds* ac = nullptr;
+  int64_t n_pts = 0;
+  rc = lvba_anchor_clouds_create(n_anchor, win_ptr.data(), scan_ptr.data(), xyz.data(), 3, rel_all.data(), anchor_leaf, -1, &ac, &n_pts);
+  if (rc != LVBA_OK) return rc;
+  std::vector<int64_t> cloud_ptr((size_t)n_anchor + 1);
+  std::vector<float> out((size_t)n_pts * 3);
+  rc = lvba_anchor_clouds_export(ac, cloud_ptr.data(), out.data(), nullptr);
+  lvba_anchor_clouds_destroy(ac);
+  if (rc != LVBA_OK) return rc;
+  for (int a = 0; a < n_anchor; ++a)
+    for (int64_t q = cloud_ptr[a]; q < cloud_ptr[a + 1]; ++q) res.anchor_clouds[a].points.push_back({out[3 * q], out[3 * q + 1], out[3 * q + 2]});
   return LVBA_OK;
 }
 

@@ -295,6 +295,24 @@ int lvba_voxel_map_lidar_lm_batch(lvba_voxel_map* m, double* poses, int32_t min_
 int lvba_voxel_map_destroy(lvba_voxel_map* m);
 
 /* ======================================================================================
+ * B6  anchor clouds — replaces the tail of the window loop of runWindowBA, src/lvba_system.cpp:284-301 (and its twin at
+ *     :1474-1491): every scan of a window transformed into the window's anchor frame (pl_transform, include/BALM/tools.hpp:385-395:
+ *     the result is stored back as float), merged, and down-sampled with down_sampling_voxel2 (tools.hpp:301-359): per voxel of
+ *     edge `leaf` the ORIGINAL point closest to the voxel centre, the first in cloud order among equally close ones.
+ *   win_ptr [n_windows+1] over scans; scan_ptr / xyz / xyz_stride_floats as for B3
+ *   rel_poses [S*12]   pose of every scan in its anchor frame: rel.R = anchor.R^T x.R, rel.p = anchor.R^T (x.p - anchor.p) (:286-289)
+ *   leaf               anchor_leaf_size_ (window_ba/anchor_leaf_size, 0.1); < 0.001 returns the transformed points unsampled (:303)
+ *   export: cloud_ptr [n_windows+1], xyz [n_points*3] float — the anchor_clouds; points of a window are ordered by voxel key
+ *   (the reference's unordered_map order is unspecified)
+ * ====================================================================================== */
+typedef struct lvba_anchor_clouds lvba_anchor_clouds;
+int lvba_anchor_clouds_create(int32_t n_windows, const int32_t* win_ptr, const int64_t* scan_ptr, const float* xyz,
+                              int32_t xyz_stride_floats, const double* rel_poses, double leaf, int32_t device,
+                              lvba_anchor_clouds** out, int64_t* n_points_out);
+int lvba_anchor_clouds_export(lvba_anchor_clouds* a, int64_t* cloud_ptr, float* xyz, double* ms_device /* may be NULL */);
+int lvba_anchor_clouds_destroy(lvba_anchor_clouds* a);
+
+/* ======================================================================================
  * B4  depth rendering — replaces the world point grid and the per-image z-buffer in front of the track fusion:
  *       buildGridMapFromOptimized   src/lvba_system.cpp:1266-1338   (0.5 m voxels of ALL world points, per-frame voxel sets,
  *                                                                    per image the voxels of the frames within +-0.5 s)

@@ -84,7 +84,18 @@ static int window_stage_case() {
   int solved = 0;
   for (const auto& sm : sums) if (sm.termination != LVBA_TERM_SKIPPED && sm.cost_last <= sm.cost_first) ++solved;
   std::printf("window stage ok: %zu windows, %d solved, costs %.3e -> %.3e\n", x_wins.size(), solved, sums[0].cost_first, sums[0].cost_last);
-  return solved == 2 ? 0 : 1;
+  if (solved != 2) return 1;
+  // all of runWindowBA: anchors (B6) for both windows, every frame attached to its anchor
+  lvba_b200::WindowBAResult<std::vector<IMUST>> wba;
+  const int rb = lvba_b200::run_window_ba(clouds, xs, 3, 1.0, ratios, 0.1, /*use_window_ba_rel=*/true, wba);
+  if (rb != LVBA_OK) { std::printf("window BA error %d: %s\n", rb, lvba_last_error()); return 1; }
+  size_t pts = 0;
+  for (const auto& c : wba.anchor_clouds) pts += c.points.size();
+  bool attached = wba.anchor_poses.size() == 2 && wba.anchor_clouds.size() == 2 && pts > 1000 && pts < 6 * 6000;
+  for (int i = 0; i < W; ++i) attached = attached && wba.anchor_index_per_frame[i] == i / 3;
+  attached = attached && std::fabs(wba.rel_poses_to_anchor[0].p(0)) < 1e-12 && std::fabs(wba.rel_poses_to_anchor[1].p(0) - 0.3) < 0.05;
+  std::printf("window BA ok: %zu anchors, %zu anchor points, frames attached %d\n", wba.anchor_poses.size(), pts, (int)attached);
+  return attached ? 0 : 1;
 }
 
 // B4: three frames of a wall 4 m in front of a forward-looking camera -> every covered pixel reads ~4 m

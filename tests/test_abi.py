@@ -159,3 +159,16 @@ def test_track_numerics_argument_checks_need_no_gpu(pkg):
         with pytest.raises(pkg.LvbaError) as e:
             pkg.tracks_triangulate([0, 2], np.zeros(2, np.int32), np.zeros((2, 2), np.float32), cams, intr)
         assert e.value.status == -2
+
+
+def test_anchor_clouds_argument_checks_need_no_gpu(pkg):
+    scans = [np.zeros((4, 3), np.float32), np.ones((5, 3), np.float32)]
+    rel = np.tile(np.concatenate([np.eye(3).ravel(), np.zeros(3)]), (2, 1))
+    for wp, leaf in (([1, 2], 0.1), ([0, 2, 1], 0.1), ([0, 2], -1.0), ([0, 2], float("nan"))):
+        with pytest.raises(pkg.LvbaError) as e:
+            pkg.anchor_clouds(scans, rel, wp, leaf)
+        assert e.value.status == -1
+    if pkg.device_count() == 0:
+        with pytest.raises(pkg.LvbaError) as e:
+            pkg.anchor_clouds(scans, rel, [0, 2], 0.1)
+        assert e.value.status == -2

@@ -54,3 +54,79 @@ def test_offline_run_matches_oracle_chain(tmp_path):
     for i in range(6):
         R = dw.quat_to_R(np.array([got[i, 7], got[i, 4], got[i, 5], got[i, 6]]))
         assert np.abs(R - ref[i, :9].reshape(3, 3)).max() <= 1e-5 and np.abs(got[i, 1:4] - ref[i, 9:]).max() <= 1e-5
+
+
+@pytest.mark.gpu
+def test_anchor_clouds_equal_oracle_exactly():
+    """Boundary B6 through the ABI: the surviving points of every window, bit for bit."""
+    import __graft_entry__ as graft
+    from oracle import anchor_oracle as ao, synth
+    pkg = graft.load_package(); pkg.load_library()
+    sizes = [4, 1, 5, 3]
+    scans, poses = synth.make_scan_scene(15, W=sum(sizes), n_per_scan=1500)
+    scans[6] = scans[6][:0]
+    win_ptr = np.concatenate([[0], np.cumsum(sizes)])
+    rel = ao.rel_poses(poses, win_ptr)
+    for leaf in (0.1, 0.25, 1.0, 0.0005):
+        got = pkg.anchor_clouds(scans, rel, win_ptr, leaf)
+        ref = ao.anchor_clouds(scans, rel, win_ptr, leaf)
+        assert all(np.array_equal(g, r) for g, r in zip(got, ref))
+
+
+@pytest.mark.gpu
+def test_offline_windowed_run_matches_oracle_chain(tmp_path):
+    """--window N: runWindowBA (window stage + anchors) and the global stages on the anchors, against the oracles end to end."""
+    import __graft_entry__ as graft
+    from oracle import anchor_oracle as ao, dataset_writer as dw, lidar_oracle as lo, synth, voxel_oracle as vox
+    pkg = graft.load_package()
+    exe = tmp_path / "lvba_offline"
+    cmd = ["g++", "-std=c++17", "-O2", "-I", str(ROOT / "include"), str(ROOT / "tools" / "lvba_offline.cpp"), "-o", str(exe),
+           str(pkg.LIB_PATH), f"-Wl,-rpath,{pkg.LIB_PATH.parent}", "-L/usr/local/cuda/lib64", "-lcudart"]
+    assert subprocess.run(cmd, capture_output=True, text=True).returncode == 0
+    W, win = 12, 4
+    scans, poses = synth.make_scan_scene(19, W=W, n_per_scan=3000)
+    rng = np.random.default_rng(6)
+    noisy = poses.copy()
+    for i in range(W):
+        noisy[i, :9] = (noisy[i, :9].reshape(3, 3) @ synth.so3_exp(rng.normal(0, 0.004, (1, 3)))[0]).ravel()
+        noisy[i, 9:] += rng.normal(0, 0.01, 3)
+    data = tmp_path / "data"
+    dw.write_lidar_dataset(data, scans, noisy)
+    out = tmp_path / "opt.txt"
+    r = subprocess.run([str(exe), "--data", str(data), "--out", str(out), "--window", str(win), "--stage1-voxel", "1.0", "--stage2-voxel", "1.0",
+                        "--anchor-leaf", "0.1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    start = noisy.copy()
+    for i in range(W):
+        start[i, :9] = dw.quat_to_R(dw.R_to_quat(noisy[i, :9].reshape(3, 3))).ravel()
+    # window stage (oracle): one map + one LM per window, skip rule of :262-266
+    win_ptr = np.arange(0, W + 1, win)
+    solved = []
+    for w in range(len(win_ptr) - 1):
+        a, b = win_ptr[w], win_ptr[w + 1]
+        vp, pi, cl, _ = vox.voxelize(scans[a:b], start[a:b], 1.0)
+        solved.append(len(vp) - 1 >= 3 * (b - a))
+    info = [json.loads(x) for x in r.stdout.strip().splitlines()]
+    wl = [x for x in info if x.get("stage") == "windows"][0]
+    assert wl["windows"] == len(solved) and wl["skipped"] == solved.count(False) and wl["anchors"] == solved.count(True)
+    # anchors (use_window_ba_rel = false: aligned poses are the odometry poses), then the two global stages on them
+    keep = [w for w in range(len(solved)) if solved[w]]
+    a_scans = [s for w in keep for s in scans[win_ptr[w]:win_ptr[w + 1]]]
+    a_poses = np.concatenate([start[win_ptr[w]:win_ptr[w + 1]] for w in keep])
+    a_ptr = np.concatenate([[0], np.cumsum([win_ptr[w + 1] - win_ptr[w] for w in keep])])
+    rel = ao.rel_poses(a_poses, a_ptr)
+    clouds = ao.anchor_clouds(a_scans, rel, a_ptr, 0.1)
+    assert wl["anchor_points"] == sum(len(c) for c in clouds)
+    anchors = np.array([start[win_ptr[w]] for w in keep])
+    for vs in (1.0, 1.0):
+        vp, pi, cl, _ = vox.voxelize(clouds, anchors, vs)
+        anchors, _ = lo.damping_iter(vp, pi, cl, anchors)
+    got = np.loadtxt(out)
+    k = 0
+    for j, w in enumerate(keep):
+        A = anchors[j, :9].reshape(3, 3)
+        for i in range(win_ptr[w], win_ptr[w + 1]):
+            R = A @ rel[k, :9].reshape(3, 3); p = A @ rel[k, 9:] + anchors[j, 9:]
+            Rg = dw.quat_to_R(np.array([got[i, 7], got[i, 4], got[i, 5], got[i, 6]]))
+            assert np.abs(Rg - R).max() <= 1e-5 and np.abs(got[i, 1:4] - p).max() <= 1e-5
+            k += 1

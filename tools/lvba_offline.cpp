@@ -6,8 +6,10 @@
 //
 //   lvba_offline --data DIR [--out FILE] [--stage1-voxel 0.5] [--stage2-voxel 0.5] [--eigen1 a,b,c,d] [--eigen2 a,b,c,d]
 //                [--no-stage1] [--window N] [--check]
-//   --window N   first run the window stage of runWindowBA on consecutive N-scan windows (B3 windowed + batched B1) and take
-//                its poses as the starting point of the global stages
+//   --window N   window_ba/enable = true, window_ba/size = N: all of runWindowBA first (window stage = windowed voxel map + batched
+//                LM; then the anchors: aligned poses, merged and down-sampled anchor clouds, boundary B6), the global stages run on
+//                the ANCHORS, and every frame is placed through its anchor (src/lvba_system.cpp:391-403)
+//   --anchor-leaf L (0.1)   --window-rel   window_ba/anchor_leaf_size, window_ba/use_window_ba_rel
 //   --check      load and summarise the dataset only (no GPU needed)
 #include <cstdio>
 #include <cstdlib>
@@ -25,8 +27,9 @@ int main(int argc, char** argv) {
   std::string data, out;
   double voxel[2] = {0.5, 0.5};                                              // BALM_stage1/2 root_voxel_size defaults (dataset_io.cpp:55-57)
   float eigen[2][4] = {{0.3f, 0.1f, 0.06f, 0.03f}, {0.3f, 0.1f, 0.06f, 0.03f}};   // bavoxel.hpp:17
-  bool stage1 = true, check = false;
+  bool stage1 = true, check = false, window_rel = false;
   int window = 0;
+  double anchor_leaf = 0.1;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto next = [&]() -> const char* { if (i + 1 >= argc) { std::fprintf(stderr, "missing value after %s\n", a.c_str()); std::exit(64); } return argv[++i]; };
@@ -38,6 +41,8 @@ int main(int argc, char** argv) {
     else if (a == "--eigen2") { if (!parse4(next(), eigen[1])) return 64; }
     else if (a == "--no-stage1") stage1 = false;
     else if (a == "--window") window = std::atoi(next());
+    else if (a == "--anchor-leaf") anchor_leaf = std::atof(next());
+    else if (a == "--window-rel") window_rel = true;
     else if (a == "--check") check = true;
     else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 64; }
   }
@@ -55,31 +60,48 @@ int main(int argc, char** argv) {
   std::printf("{\"scans\": %zu, \"poses\": %zu, \"points\": %zu, \"coordinate_sum\": %.6f, \"pose_sum\": %.9f, \"first_ts\": %.6f, \"last_ts\": %.6f}\n",
               ds.clouds.size(), ds.x_buf.size(), points, sum, pose_sum, n ? ds.x_buf[0].t : 0.0, n ? ds.x_buf[n - 1].t : 0.0);
   if (check) return 0;
-  std::vector<Pose> poses(ds.x_buf.begin(), ds.x_buf.begin() + (long)n);
-  std::vector<lvba_b200::dataset::Cloud*> clouds(ds.pl_fulls.begin(), ds.pl_fulls.begin() + (long)n);
-  if (window > 0) {                                                          // runWindowBA's window stage (:232-266)
-    std::vector<std::vector<Pose>> x_wins;
-    std::vector<lvba_summary> sums;
-    lvba_summary tot{};
-    const int rc = lvba_b200::run_window_stage(clouds, poses, window, voxel[0], eigen[0], x_wins, &sums, &tot);
-    if (rc != LVBA_OK) { std::fprintf(stderr, "window stage failed (%d): %s\n", rc, lvba_last_error()); return rc == LVBA_ERR_NO_DEVICE ? 2 : 1; }
-    size_t k = 0, skipped = 0;
-    for (size_t w = 0; w < x_wins.size(); ++w) { skipped += sums[w].termination == LVBA_TERM_SKIPPED; for (const auto& p : x_wins[w]) poses[k++] = p; }
-    std::printf("{\"stage\": \"windows\", \"windows\": %zu, \"skipped\": %zu, \"ms\": %.3f}\n", x_wins.size(), skipped, tot.ms_total);
+  std::vector<Pose> frames(ds.x_buf.begin(), ds.x_buf.begin() + (long)n);              // x_buf_full
+  std::vector<lvba_b200::dataset::Cloud*> frame_clouds(ds.pl_fulls.begin(), ds.pl_fulls.begin() + (long)n);
+  lvba_b200::WindowBAResult<std::vector<Pose>> wba;
+  std::vector<lvba_b200::AnchorCloud*> anchor_clouds;
+  const bool windows = window > 0;
+  if (windows) {                                                             // runWindowBA (:205-316)
+    const int rc = lvba_b200::run_window_ba(frame_clouds, frames, window, voxel[0], eigen[0], anchor_leaf, window_rel, wba);
+    if (rc != LVBA_OK) { std::fprintf(stderr, "window BA failed (%d): %s\n", rc, lvba_last_error()); return rc == LVBA_ERR_NO_DEVICE ? 2 : 1; }
+    size_t pts = 0;
+    for (auto& c : wba.anchor_clouds) { anchor_clouds.push_back(&c); pts += c.points.size(); }
+    std::printf("{\"stage\": \"windows\", \"windows\": %d, \"skipped\": %d, \"anchors\": %zu, \"anchor_points\": %zu}\n",
+                wba.win_total, wba.win_skipped, wba.anchor_poses.size(), pts);
   }
-  for (int idx = stage1 ? 0 : 1; idx < 2; ++idx) {                           // runLidarBA's two passes (:358-389)
-    lvba_b200::SurfMap<std::vector<Pose>> surf;
+  std::vector<Pose>& poses = windows ? wba.anchor_poses : frames;            // anchor_poses / anchor_clouds of runLidarBA (:329-334)
+  for (int idx = stage1 ? 0 : 1; idx < 2 && !poses.empty(); ++idx) {         // the two passes (:358-389)
     lvba_voxel_summary vs{};
-    int rc = surf.build(clouds, poses, voxel[idx], eigen[idx], &vs);
-    if (rc != LVBA_OK) { std::fprintf(stderr, "stage %d voxel map failed (%d): %s\n", idx + 1, rc, lvba_last_error()); return rc == LVBA_ERR_NO_DEVICE ? 2 : 1; }
     lvba_summary s{};
+    int rc;
+    lvba_b200::SurfMap<std::vector<Pose>> surf;
+    rc = windows ? surf.build(anchor_clouds, poses, voxel[idx], eigen[idx], &vs) : surf.build(frame_clouds, poses, voxel[idx], eigen[idx], &vs);
+    if (rc != LVBA_OK) { std::fprintf(stderr, "stage %d voxel map failed (%d): %s\n", idx + 1, rc, lvba_last_error()); return rc == LVBA_ERR_NO_DEVICE ? 2 : 1; }
     rc = surf.damping_iter(poses, 0, nullptr, &s);
     if (rc != LVBA_OK) { std::fprintf(stderr, "stage %d LM failed (%d): %s\n", idx + 1, rc, lvba_last_error()); return 1; }
     std::printf("{\"stage\": %d, \"voxels\": %lld, \"clusters\": %lld, \"map_ms\": %.3f, \"iterations\": %d, \"accepted\": %d, \"cost_first\": %.9e, \"cost_last\": %.9e, \"lm_ms\": %.3f}\n",
                 idx + 1, (long long)vs.n_voxels, (long long)vs.nnz, vs.ms_total, s.iterations, s.accepted, s.cost_first, s.cost_last, s.ms_total);
   }
+  if (windows) {                                                             // optimized_x_buf_ (:391-403): frame = anchor * rel
+    for (size_t i = 0; i < n; ++i) {
+      const int a = wba.anchor_index_per_frame[i];
+      if (a < 0) continue;                                                   // frames of skipped windows keep their odometry pose
+      const Pose& A = wba.anchor_poses[(size_t)a];
+      const Pose& r = wba.rel_poses_to_anchor[i];
+      Pose o = frames[i];
+      for (int x = 0; x < 3; ++x) {
+        for (int y = 0; y < 3; ++y) o.R(x, y) = A.R(x, 0) * r.R(0, y) + A.R(x, 1) * r.R(1, y) + A.R(x, 2) * r.R(2, y);
+        o.p(x) = (A.R(x, 0) * r.p(0) + A.R(x, 1) * r.p(1) + A.R(x, 2) * r.p(2)) + A.p(x);
+      }
+      frames[i] = o;
+    }
+  }
   if (out.empty()) out = data + "all_pcd_body/lidar_poses_optimized.txt";
-  if (!lvba_b200::dataset::save_poses_tum(out, poses)) { std::fprintf(stderr, "cannot write %s\n", out.c_str()); return 1; }
-  std::printf("{\"written\": \"%s\", \"poses\": %zu}\n", out.c_str(), poses.size());
+  if (!lvba_b200::dataset::save_poses_tum(out, frames)) { std::fprintf(stderr, "cannot write %s\n", out.c_str()); return 1; }
+  std::printf("{\"written\": \"%s\", \"poses\": %zu}\n", out.c_str(), frames.size());
   return 0;
 }
