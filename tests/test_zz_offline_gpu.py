@@ -58,19 +58,27 @@ def test_offline_run_matches_oracle_chain(tmp_path):
 
 @pytest.mark.gpu
 def test_anchor_clouds_equal_oracle_exactly():
-    """Boundary B6 through the ABI: the surviving points of every window, bit for bit."""
-    import __graft_entry__ as graft
-    from oracle import anchor_oracle as ao, synth
-    pkg = graft.load_package(); pkg.load_library()
-    sizes = [4, 1, 5, 3]
-    scans, poses = synth.make_scan_scene(15, W=sum(sizes), n_per_scan=1500)
-    scans[6] = scans[6][:0]
-    win_ptr = np.concatenate([[0], np.cumsum(sizes)])
-    rel = ao.rel_poses(poses, win_ptr)
-    for leaf in (0.1, 0.25, 1.0, 0.0005):
-        got = pkg.anchor_clouds(scans, rel, win_ptr, leaf)
-        ref = ao.anchor_clouds(scans, rel, win_ptr, leaf)
-        assert all(np.array_equal(g, r) for g, r in zip(got, ref))
+    """Boundary B6 through the ABI: the surviving points of every window, bit for bit (in a child process)."""
+    code = """
+import sys
+import numpy as np
+sys.path.insert(0, %r)
+import __graft_entry__ as graft
+from oracle import anchor_oracle as ao, synth
+pkg = graft.load_package(); pkg.load_library()
+sizes = [4, 1, 5, 3]
+scans, poses = synth.make_scan_scene(15, W=sum(sizes), n_per_scan=1500)
+scans[6] = scans[6][:0]
+win_ptr = np.concatenate([[0], np.cumsum(sizes)])
+rel = ao.rel_poses(poses, win_ptr)
+for leaf in (0.1, 0.25, 1.0, 0.0005):
+    got = pkg.anchor_clouds(scans, rel, win_ptr, leaf)
+    ref = ao.anchor_clouds(scans, rel, win_ptr, leaf)
+    assert all(np.array_equal(g, r) for g, r in zip(got, ref)), leaf
+print('CHILD-OK')
+""" % str(ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=str(ROOT))
+    assert r.returncode == 0 and "CHILD-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
 
 
 @pytest.mark.gpu
