@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "../../global-lvba_b200/csrc/lidar_big.h"
+#include "host_exec.h"
 
 extern "C" double emu_big_accumulate(int64_t V, const int64_t* vox_ptr, const int32_t* pose_idx, const double* clusters, const double* poses,
                                      const int* first, const long long* row_start, double* H, double* g, int residual_only) {
@@ -13,13 +14,14 @@ extern "C" double emu_big_accumulate(int64_t V, const int64_t* vox_ptr, const in
   View bv{V, vox_ptr, pose_idx, clusters, pair_ptr.data(), first, row_start};
   std::vector<double> params((size_t)V * kParams), res((size_t)V), feat((size_t)vox_ptr[V] * kFeat);
   ParamsF pf{bv, poses, params.data(), res.data()};
-  for (int64_t b = 0; b < V; ++b) pf(b);
+  HostExec ex;
+  ex.for_each(V, pf);
   double sum = 0.0;
   for (double r : res) sum += r;
   if (residual_only) return sum;
   SlotsF sf{bv, poses, params.data(), feat.data(), H, g};
-  for (int64_t s = 0; s < vox_ptr[V]; ++s) sf(s);
+  ex.for_each(vox_ptr[V], sf);
   PairsF qf{bv, params.data(), feat.data(), H};
-  for (int64_t p = 0; p < pair_ptr[V]; ++p) qf(p);
+  ex.for_each(pair_ptr[V], qf);
   return sum;
 }

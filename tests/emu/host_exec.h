@@ -2,8 +2,10 @@
 // pipelines with (voxel_pipeline.h, depth_pipeline.h).  Never part of liblvba_b200.so.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <random>
 #include <vector>
 
 struct HostExec {
@@ -15,8 +17,20 @@ struct HostExec {
     int alloc(size_t count) { v.assign(count, T()); p = v.data(); n = count; return 0; }
     void swap(Buf& o) { v.swap(o.v); std::swap(p, o.p); std::swap(n, o.n); }
   };
+  // On the device the items of a pass run concurrently in no particular order.  With LVBA_EMU_SHUFFLE=<seed> the items are
+  // visited in a pseudo-random order instead of 0..n-1, so a pass that silently relied on sequential execution (reading what
+  // an earlier item of the SAME pass wrote) gives different results and the tests that compare against the oracle catch it.
   template <class F>
-  int for_each(int64_t n, const F& f) { for (int64_t i = 0; i < n; ++i) f(i); return 0; }
+  int for_each(int64_t n, const F& f) {
+    static const char* env = std::getenv("LVBA_EMU_SHUFFLE");
+    if (!env || n < 2) { for (int64_t i = 0; i < n; ++i) f(i); return 0; }
+    std::vector<int64_t> order((size_t)n);
+    std::iota(order.begin(), order.end(), 0);
+    std::mt19937_64 rng((uint64_t)std::atoll(env) * 0x9E3779B97F4A7C15ull + (uint64_t)n);
+    std::shuffle(order.begin(), order.end(), rng);
+    for (int64_t i : order) f(i);
+    return 0;
+  }
   template <class T>
   int fill_zero(T* p, size_t n) { std::memset(p, 0, n * sizeof(T)); return 0; }
   template <class T>

@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "../../global-lvba_b200/csrc/envelope_wide.h"
+#include "host_exec.h"
 
 extern "C" int emu_wide_solve(int n, const int* first, const int* last, const long long* row_start, double* L, double* z, double* x,
                               double* dinv) {
@@ -12,7 +13,8 @@ extern "C" int emu_wide_solve(int n, const int* first, const int* last, const lo
   for (int k = 0; k < n; ++k) if (last[k] - k > max_col) max_col = last[k] - k;
   std::vector<double> colT((size_t)(max_col > 0 ? max_col : 1) * 36);
   int status = 0;
-  auto launch = [](int64_t items, const auto& f) { for (int64_t i = 0; i < items; ++i) f(i); };
+  HostExec ex;
+  auto launch = [&](int64_t items, const auto& f) { ex.for_each(items, f); };
   lvba::wide::factor_and_solve(launch, e, first, last, L, dinv, z, colT.data(), x, &status);
   return status;
 }
