@@ -14,7 +14,9 @@ struct HostExec {
     T* p = nullptr;
     size_t n = 0;
     std::vector<T> v;
-    int alloc(size_t count) { v.assign(count, T()); p = v.data(); n = count; return 0; }
+    // device allocations come back uninitialised (and recycled through the pool): poison the host copy the same way, so that a
+    // pass relying on zero-filled memory cannot pass here
+    int alloc(size_t count) { v.resize(count); if (count) std::memset((void*)v.data(), 0xA5, count * sizeof(T)); p = v.data(); n = count; return 0; }
     void swap(Buf& o) { v.swap(o.v); std::swap(p, o.p); std::swap(n, o.n); }
   };
   // On the device the items of a pass run concurrently in no particular order.  With LVBA_EMU_SHUFFLE=<seed> the items are
