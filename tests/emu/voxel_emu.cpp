@@ -14,6 +14,9 @@ using Map = lvba::vox::VoxelMap<HostExec>;
 
 }  // namespace
 
+// memcpy with a null source is undefined even for zero bytes (empty maps have unallocated buffers)
+static void copy_n_bytes(void* dst, const void* src, size_t n) { if (n) std::memcpy(dst, src, n); }
+
 extern "C" {
 
 int emu_voxel_map_create(int32_t W, const int64_t* scan_ptr, const float* xyz, const double* poses, double voxel_size,
@@ -39,7 +42,7 @@ int emu_voxel_map_create_windows(int32_t n_windows, const int32_t* win_ptr, cons
 
 int emu_voxel_map_windows(void* h, int32_t* vox_window) {
   Map* m = (Map*)h;
-  std::memcpy(vox_window, m->vox_window.p, (size_t)m->V * sizeof(int32_t));
+  copy_n_bytes(vox_window, m->vox_window.p, (size_t)m->V * sizeof(int32_t));
   return 0;
 }
 
@@ -53,14 +56,14 @@ int emu_voxel_map_sizes(void* h, int64_t* n_voxels, int64_t* nnz, int64_t* n_nod
 int emu_voxel_map_export(void* h, int64_t* vox_ptr, int32_t* pose_idx, double* clusters, int64_t* root_key, int8_t* path,
                          double* centre, double* normal, double* eigenvalues) {
   Map* m = (Map*)h;
-  std::memcpy(vox_ptr, m->vox_ptr.p, (size_t)(m->V + 1) * sizeof(int64_t));
-  std::memcpy(pose_idx, m->vox_pose.p, (size_t)m->nnz * sizeof(int32_t));
-  std::memcpy(clusters, m->vox_cluster.p, (size_t)m->nnz * 10 * sizeof(double));
-  std::memcpy(root_key, m->vox_root.p, (size_t)m->V * 3 * sizeof(int64_t));
-  std::memcpy(path, m->vox_path.p, (size_t)m->V * 3);
-  std::memcpy(centre, m->vox_centre.p, (size_t)m->V * 3 * sizeof(double));
-  std::memcpy(normal, m->vox_direct.p, (size_t)m->V * 3 * sizeof(double));
-  std::memcpy(eigenvalues, m->vox_eig.p, (size_t)m->V * 3 * sizeof(double));
+  copy_n_bytes(vox_ptr, m->vox_ptr.p, (size_t)(m->V + 1) * sizeof(int64_t));
+  copy_n_bytes(pose_idx, m->vox_pose.p, (size_t)m->nnz * sizeof(int32_t));
+  copy_n_bytes(clusters, m->vox_cluster.p, (size_t)m->nnz * 10 * sizeof(double));
+  copy_n_bytes(root_key, m->vox_root.p, (size_t)m->V * 3 * sizeof(int64_t));
+  copy_n_bytes(path, m->vox_path.p, (size_t)m->V * 3);
+  copy_n_bytes(centre, m->vox_centre.p, (size_t)m->V * 3 * sizeof(double));
+  copy_n_bytes(normal, m->vox_direct.p, (size_t)m->V * 3 * sizeof(double));
+  copy_n_bytes(eigenvalues, m->vox_eig.p, (size_t)m->V * 3 * sizeof(double));
   return 0;
 }
 

@@ -2,6 +2,7 @@
 anchor frame + down_sampling_voxel2) without a GPU: the device passes through the sequential host policy against
 oracle/anchor_oracle.py — the surviving points EXACTLY (float32), ordered by voxel key."""
 import ctypes
+import os
 import subprocess
 from pathlib import Path
 
@@ -17,7 +18,7 @@ ROOT = Path(__file__).resolve().parents[1]
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     so = tmp_path_factory.mktemp("emu") / "libanchor_emu.so"
-    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "anchor_emu.cpp"), "-o", str(so)]
+    cmd = ["g++", "-std=c++17", "-O2", *(["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-g"] if os.environ.get("LVBA_EMU_SANITIZE") else []), "-ffp-contract=off", "-Wall", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "anchor_emu.cpp"), "-o", str(so)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return ctypes.CDLL(str(so))

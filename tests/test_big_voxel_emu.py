@@ -3,6 +3,7 @@ GPU: the three passes (voxel parameters, slots, slot pairs) run by plain loops o
 (tests/emu/big_emu.cpp) against oracle/lidar_oracle.acc_evaluate2 — residual, gradient and every Hessian block, including
 a voxel seen from 300 poses."""
 import ctypes
+import os
 import subprocess
 from pathlib import Path
 
@@ -18,7 +19,7 @@ ROOT = Path(__file__).resolve().parents[1]
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     so = tmp_path_factory.mktemp("emu") / "libbig_emu.so"
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "big_emu.cpp"), "-o", str(so)]
+    cmd = ["g++", "-std=c++17", "-O2", *(["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-g"] if os.environ.get("LVBA_EMU_SANITIZE") else []), "-Wall", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "big_emu.cpp"), "-o", str(so)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     lib = ctypes.CDLL(str(so))

@@ -3,6 +3,7 @@ a GPU: the pass functors the CUDA kernels run, instantiated with the sequential 
 infrastructure only), against oracle/depth_oracle.py.  The z-buffer is order independent, so images are compared
 EXACTLY.  tests/test_zz_depth_gpu.py runs the same comparisons through the C ABI."""
 import ctypes
+import os
 import subprocess
 from pathlib import Path
 
@@ -18,7 +19,7 @@ ROOT = Path(__file__).resolve().parents[1]
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     so = tmp_path_factory.mktemp("emu") / "libdepth_emu.so"
-    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-fPIC", "-shared",
+    cmd = ["g++", "-std=c++17", "-O2", *(["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-g"] if os.environ.get("LVBA_EMU_SANITIZE") else []), "-ffp-contract=off", "-Wall", "-fPIC", "-shared",
            str(ROOT / "tests" / "emu" / "depth_emu.cpp"), "-o", str(so)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr

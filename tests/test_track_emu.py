@@ -2,6 +2,7 @@
 reprojection error, src/lvba_system.cpp:8-111) without a GPU: the device functors run by plain loops (tests/emu/track_emu.cpp)
 against the numpy restatement oracle/track_oracle.py, on the tracks of a synthetic visual problem."""
 import ctypes
+import os
 import subprocess
 from pathlib import Path
 
@@ -18,7 +19,7 @@ ROOT = Path(__file__).resolve().parents[1]
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     so = tmp_path_factory.mktemp("emu") / "libtrack_emu.so"
-    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "track_emu.cpp"), "-o", str(so)]
+    cmd = ["g++", "-std=c++17", "-O2", *(["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-g"] if os.environ.get("LVBA_EMU_SANITIZE") else []), "-ffp-contract=off", "-Wall", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "track_emu.cpp"), "-o", str(so)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return ctypes.CDLL(str(so))

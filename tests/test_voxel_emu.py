@@ -4,6 +4,7 @@ test infrastructure only) and compared with oracle/voxel_oracle.py — structure
 cluster sums / centres / eigenvalues to rounding, normals up to sign.  The GPU tests (test_zz_voxel_gpu.py) run the
 same comparisons through the C ABI."""
 import ctypes
+import os
 import subprocess
 from pathlib import Path
 
@@ -21,7 +22,7 @@ ROOT = Path(__file__).resolve().parents[1]
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     so = tmp_path_factory.mktemp("emu") / "libvoxel_emu.so"
-    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-fPIC", "-shared",
+    cmd = ["g++", "-std=c++17", "-O2", *(["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-g"] if os.environ.get("LVBA_EMU_SANITIZE") else []), "-ffp-contract=off", "-Wall", "-fPIC", "-shared",
            str(ROOT / "tests" / "emu" / "voxel_emu.cpp"), "-o", str(so)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr

@@ -3,6 +3,7 @@ envelope wider than the in-SM solvers hold) checked without a GPU: the same pass
 (tests/emu/wide_emu.cpp), against a dense numpy solve of the same symmetric INDEFINITE block system (the BALM2 Newton
 Hessian is indefinite, SURVEY.md Q5: LDL^T without pivoting, as SimplicialLDLT)."""
 import ctypes
+import os
 import subprocess
 from pathlib import Path
 
@@ -15,7 +16,7 @@ ROOT = Path(__file__).resolve().parents[1]
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     so = tmp_path_factory.mktemp("emu") / "libwide_emu.so"
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "wide_emu.cpp"), "-o", str(so)]
+    cmd = ["g++", "-std=c++17", "-O2", *(["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-g"] if os.environ.get("LVBA_EMU_SANITIZE") else []), "-Wall", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "wide_emu.cpp"), "-o", str(so)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return ctypes.CDLL(str(so))
