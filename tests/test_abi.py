@@ -172,3 +172,13 @@ def test_anchor_clouds_argument_checks_need_no_gpu(pkg):
         with pytest.raises(pkg.LvbaError) as e:
             pkg.anchor_clouds(scans, rel, [0, 2], 0.1)
         assert e.value.status == -2
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The drop-in boundary is a C ABI: include/lvba_b200.h must compile as C99 without extensions."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "lvba_b200.h"\nint main(void) { lvba_voxel_opts o; lvba_voxel_default_opts(&o); return lvba_version() > 0 ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(ROOT / "include"), "-c", str(src), "-o", str(tmp_path / "hdr.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
