@@ -248,3 +248,17 @@ def test_windowed_map_equals_one_oracle_map_per_window(emu):
             assert win_ptr[wins[v]] <= p.min() and p.max() < win_ptr[wins[v] + 1]
         assert emu.emu_voxel_map_lookup(m.h, ctypes.c_int64(1), _ptr(np.zeros(3), ctypes.c_double), _ptr(np.zeros(4), ctypes.c_double)) == -4
         m.close()
+
+
+def test_randomised_scenes_and_options(emu):
+    """Forty random combinations of scan count, density, root size, layer limit, min_ps and a random offset of the scene."""
+    rng = np.random.default_rng(123)
+    for seed in range(100, 140):
+        W = int(rng.integers(2, 8)); npts = int(rng.integers(300, 3000))
+        vs = float(rng.choice([0.3, 0.5, 0.8, 1.0, 1.7, 2.5, 4.0])); ll = int(rng.integers(0, 3)); mp = int(rng.choice([5, 15, 30]))
+        scans, poses = _scene(seed, W=W, n_per_scan=npts)
+        poses = poses.copy(); poses[:, 9:] += rng.uniform(-50, 50, 3)
+        m = EmuMap(emu, scans, poses, vs, layer_limit=ll, min_ps=mp)
+        assert m.rc == 0
+        compare_with_oracle(m.export(), vox.voxelize(scans, poses, vs, layer_limit=ll, min_ps=mp))
+        m.close()
