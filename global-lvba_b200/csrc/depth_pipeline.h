@@ -201,9 +201,9 @@ struct SplatF {              // R3, over the T2 chunks
     }
   }
 };
-struct FinalizeF {           // R4
+struct FinalizeF {           // R4 (bits and depth are the same words)
   const uint32_t* bits; float* depth;
-  LVBA_HD void operator()(int64_t i) const { depth[i] = bits[i] == kEmpty ? 0.0f : bits_float(bits[i]); }
+  LVBA_HD void operator()(int64_t i) const { const uint32_t b = bits[i]; depth[i] = b == kEmpty ? 0.0f : bits_float(b); }
 };
 
 // ---------------------------------------------------------------- depth-fused 3-D candidates of the track fusion
@@ -360,9 +360,8 @@ struct DepthGrid {
     last_pairs = 0; last_chunks = 0;
     if (n_img <= 0) return 0;
     const int64_t n_pix = n_img * (int64_t)width * height;
-    typename Exec::template Buf<uint32_t> bits;
-    LVBA_VOX_TRY(bits.alloc((size_t)n_pix));
-    LVBA_VOX_TRY(ex.for_each(n_pix, FillU32F{bits.p, kEmpty}));
+    uint32_t* const bits = reinterpret_cast<uint32_t*>(depth);      // the z-buffer of bit patterns lives in the output images
+    LVBA_VOX_TRY(ex.for_each(n_pix, FillU32F{bits, kEmpty}));
     if (N > 0 && n_pairs > 0) {
       typename Exec::template Buf<int32_t> f_lo;
       typename Exec::template Buf<int64_t> pair_lo, count, off1;
@@ -381,12 +380,12 @@ struct DepthGrid {
         int64_t T2 = 0;
         LVBA_VOX_TRY(ex.fetch(&T2, off2.p + T1, 1));
         last_chunks = T2;
-        SplatF sf{off2.p, T1, off1.p, n_img, pair_lo.p, pair_vox.p, vox_start.p, pw.p, cams, {}, width, height, bits.p};
+        SplatF sf{off2.p, T1, off1.p, n_img, pair_lo.p, pair_vox.p, vox_start.p, pw.p, cams, {}, width, height, bits};
         for (int q = 0; q < 8; ++q) sf.intr[q] = intr[q];
         LVBA_VOX_TRY(ex.for_each(T2, sf));
       }
     }
-    LVBA_VOX_TRY(ex.for_each(n_pix, FinalizeF{bits.p, depth}));
+    LVBA_VOX_TRY(ex.for_each(n_pix, FinalizeF{bits, depth}));                // in place: every item reads and writes its own word
     return ex.sync();
   }
 
