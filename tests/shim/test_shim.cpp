@@ -55,8 +55,8 @@ static int surf_map_case() {
   return (floor_ok && wall_ok && none_ok) ? 0 : 1;
 }
 
-// B3 + B1 batched: two windows of the surf-map scene through run_window_stage
-static int window_stage_case() {
+// B3 + B1 batched: two windows of the surf-map scene through run_window_stage; with_anchors: all of runWindowBA (B6 as well)
+static int window_stage_case(bool with_anchors) {
   const int W = 6;
   std::vector<IMUST> xs(W);
   std::vector<Cloud> store(W);
@@ -85,6 +85,7 @@ static int window_stage_case() {
   for (const auto& sm : sums) if (sm.termination != LVBA_TERM_SKIPPED && sm.cost_last <= sm.cost_first) ++solved;
   std::printf("window stage ok: %zu windows, %d solved, costs %.3e -> %.3e\n", x_wins.size(), solved, sums[0].cost_first, sums[0].cost_last);
   if (solved != 2) return 1;
+  if (!with_anchors) return 0;
   // all of runWindowBA: anchors (B6) for both windows, every frame attached to its anchor
   lvba_b200::WindowBAResult<std::vector<IMUST>> wba;
   const int rb = lvba_b200::run_window_ba(clouds, xs, 3, 1.0, ratios, 0.1, /*use_window_ba_rel=*/true, wba);
@@ -129,7 +130,8 @@ static int depth_case() {
 }
 
 int main(int argc, char** argv) {
-  if (argc > 1 && std::string(argv[1]) == "windows") return window_stage_case();   // B3 + B1 batched, run by tests/test_zz_voxel_gpu.py
+  if (argc > 1 && std::string(argv[1]) == "windows") return window_stage_case(false);   // B3 + B1 batched, run by tests/test_zz_voxel_gpu.py
+  if (argc > 1 && std::string(argv[1]) == "windowba") return window_stage_case(true);   // ... and the anchors (B6), tests/test_zz_offline_gpu.py
   if (argc > 1 && std::string(argv[1]) == "depth") return depth_case();           // B4, run by tests/test_zz_depth_gpu.py
   if (argc > 1 && std::string(argv[1]) == "surfmap") return surf_map_case();     // B3, run by tests/test_zz_voxel_gpu.py
   const int W = 4;

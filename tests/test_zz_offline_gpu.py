@@ -138,3 +138,17 @@ def test_offline_windowed_run_matches_oracle_chain(tmp_path):
             Rg = dw.quat_to_R(np.array([got[i, 7], got[i, 4], got[i, 5], got[i, 6]]))
             assert np.abs(Rg - R).max() <= 1e-5 and np.abs(got[i, 1:4] - p).max() <= 1e-5
             k += 1
+
+
+@pytest.mark.gpu
+def test_shim_run_window_ba(tmp_path):
+    """lvba_b200::run_window_ba (host/lvba_shim.hpp): window stage + anchors (B6) through the C++ mirror."""
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    exe = tmp_path / "test_shim"
+    cmd = ["g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), str(ROOT / "tests" / "shim" / "test_shim.cpp"),
+           "-o", str(exe), str(pkg.LIB_PATH), f"-Wl,-rpath,{pkg.LIB_PATH.parent}", "-L/usr/local/cuda/lib64", "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), "windowba"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "window BA ok" in r.stdout, r.stdout + r.stderr

@@ -256,4 +256,4 @@ def test_shim_surf_map(tmp_path):
     r = subprocess.run([str(exe), "surfmap"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "surf map ok" in r.stdout, r.stdout + r.stderr
     r = subprocess.run([str(exe), "windows"], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "window stage ok" in r.stdout and "window BA ok" in r.stdout, r.stdout + r.stderr
+    assert r.returncode == 0 and "window stage ok" in r.stdout, r.stdout + r.stderr
