@@ -29,9 +29,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-voxel-map > $O/06_launches_bench.out 2>&1
 
 # 4. full captures of the set-up stage's heaviest passes (segment sums, splat) — one launch each
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:SegmentSumF -s 1 -c 1 -o $O/07_segment_sum -f \
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:SegmentSumF -s 1 -c 1 -o $O/07_segment_sum -f \
     python tools/bench_voxel_map.py --scans 200 --points 50000 --repeats 1 --cpu-sample-scans 0 > $O/07_segment_sum.out 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:SplatF -s 1 -c 1 -o $O/08_splat -f \
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:SplatF -s 1 -c 1 -o $O/08_splat -f \
     python tools/bench_voxel_map.py --scans 200 --points 50000 --repeats 1 --cpu-sample-scans 0 > $O/08_splat.out 2>&1
 
 # 5. the four-chunk solve experiment with 10 right-hand sides per spike CTA (tools/lab, not in the product)
