@@ -5,8 +5,8 @@
 // octant path of a point is a pure function of its world position, so every point gets its whole key up front and the
 // tree becomes three sorted arrays of nodes (one per layer):
 //
-//   1  point keys       world = R p + t, root key per axis, min/max per axis        (one pass over the points)
-//   2  packed keys      key2 = (packed root key) << 6 | octant1 << 3 | octant2      (one pass over the points)
+//   1  point keys       world = R p + t, root key per axis, the two octants; min/max per axis   (the only pass over xyz besides the sums)
+//   2  packed keys      key2 = (packed root key) << 6 | octant1 << 3 | octant2                  (17 B in, 8 B out per point)
 //   3  per layer L      STABLE radix sort of the points by key2 >> 3(2-L): inside a node the points keep the caller's
 //                       order (scan by scan, point by point), which is the order the reference pushes them in, so the
 //                       sequential per-(node, pose) sums below reproduce its PointCluster sums term by term;
@@ -93,9 +93,9 @@ struct LayerView {
 };
 
 // ================================================================ pass functors
-struct PointKeysF {          // pass 1
+struct PointKeysF {          // pass 1: everything that needs the point itself — its pose, root key and the two octants
   const float* xyz; const int64_t* scan_ptr; const double* poses; int W; double voxel_size;
-  int32_t* pose_of; int32_t* kx; int32_t* ky; int32_t* kz; int32_t* bad;
+  int32_t* pose_of; int32_t* kx; int32_t* ky; int32_t* kz; uint8_t* oct; int32_t* bad;
   LVBA_HD void operator()(int64_t i) const {
     int lo = 0, hi = W;                                   // last j with scan_ptr[j] <= i  (empty scans are skipped)
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (scan_ptr[mid] <= i) lo = mid; else hi = mid; }
@@ -107,15 +107,20 @@ struct PointKeysF {          // pass 1
     for (int a = 0; a < 3; ++a) ok = root_key_axis(w[a], voxel_size, &k[a]) && ok;
     if (!ok) { *bad = 1; k[0] = k[1] = k[2] = 0; }
     kx[i] = (int32_t)k[0]; ky[i] = (int32_t)k[1]; kz[i] = (int32_t)k[2];
+    float c0[3], c1[3];                                   // octant path: a function of the world point and the root key only
+    int b[3];
+    for (int a = 0; a < 3; ++a) c0[a] = root_centre_axis(k[a], voxel_size);
+    const int o1 = octant(w, c0, b);
+    child_centre(c0, b, root_quater(voxel_size), c1);
+    const int o2 = octant(w, c1, b);
+    oct[i] = (uint8_t)(o1 << 3 | o2);
   }
 };
 
-struct PackKeysF {           // pass 2
-  const float* xyz; const double* poses; const int32_t* pose_of; const int32_t* kx; const int32_t* ky; const int32_t* kz;
-  double voxel_size; KeyPacking pk; uint64_t* key2; const int32_t* win_ptr; int n_windows;
+struct PackKeysF {           // pass 2 (after the key range is known): no access to the points any more
+  const int32_t* pose_of; const int32_t* kx; const int32_t* ky; const int32_t* kz; const uint8_t* oct;
+  KeyPacking pk; uint64_t* key2; const int32_t* win_ptr; int n_windows;
   LVBA_HD void operator()(int64_t i) const {
-    double w[3];
-    world_point(poses + 12 * (int64_t)pose_of[i], xyz + 3 * i, w);
     uint32_t win = 0;
     if (n_windows > 0) {                                  // window of the scan: last w with win_ptr[w] <= scan
       int lo = 0, hi = n_windows;
@@ -123,13 +128,7 @@ struct PackKeysF {           // pass 2
       win = (uint32_t)lo;
     }
     const int64_t k[3] = {kx[i], ky[i], kz[i]};
-    float c0[3], c1[3];
-    int b[3];
-    for (int a = 0; a < 3; ++a) c0[a] = root_centre_axis(k[a], voxel_size);
-    const int o1 = octant(w, c0, b);
-    child_centre(c0, b, root_quater(voxel_size), c1);
-    const int o2 = octant(w, c1, b);
-    key2[i] = (pk.with_window(pk.pack(k), win) << 6) | (uint64_t)(o1 << 3 | o2);
+    key2[i] = (pk.with_window(pk.pack(k), win) << 6) | (uint64_t)oct[i];
   }
 };
 
@@ -363,10 +362,12 @@ struct VoxelMap {
       LVBA_VOX_TRY(key2.alloc((size_t)N));
       {
         typename Exec::template Buf<int32_t> kx, ky, kz, bad;
+        typename Exec::template Buf<uint8_t> oct;
         LVBA_VOX_TRY(kx.alloc((size_t)N)); LVBA_VOX_TRY(ky.alloc((size_t)N)); LVBA_VOX_TRY(kz.alloc((size_t)N));
+        LVBA_VOX_TRY(oct.alloc((size_t)N));
         LVBA_VOX_TRY(bad.alloc(1));
         LVBA_VOX_TRY(ex.fill_zero(bad.p, 1));
-        LVBA_VOX_TRY(ex.for_each(N, PointKeysF{xyz, scan_ptr, poses, W, prm.voxel_size, pose_of.p, kx.p, ky.p, kz.p, bad.p}));
+        LVBA_VOX_TRY(ex.for_each(N, PointKeysF{xyz, scan_ptr, poses, W, prm.voxel_size, pose_of.p, kx.p, ky.p, kz.p, oct.p, bad.p}));
         int32_t h_bad = 0;
         LVBA_VOX_TRY(ex.fetch(&h_bad, bad.p, 1));
         if (h_bad) { error = "a point is non-finite or more than 2^30 root voxels from the origin"; return kErrInvalid; }
@@ -379,7 +380,7 @@ struct VoxelMap {
         }
         pk.root_bits = pk.bits[0] + pk.bits[1] + pk.bits[2];
         if (pk.key_bits() + 6 > 62) { error = "root voxel keys (and window index) span more than 56 bits"; return kErrUnsupported; }
-        LVBA_VOX_TRY(ex.for_each(N, PackKeysF{xyz, poses, pose_of.p, kx.p, ky.p, kz.p, prm.voxel_size, pk, key2.p, win_ptr, n_windows}));
+        LVBA_VOX_TRY(ex.for_each(N, PackKeysF{pose_of.p, kx.p, ky.p, kz.p, oct.p, pk, key2.p, win_ptr, n_windows}));
       }
       // Only the points of nodes that split take part in the next layer (the reference hands exactly those to cut_func,
       // :453-456); layer 0 takes them all.
