@@ -182,3 +182,44 @@ def test_header_is_plain_c99(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(ROOT / "include"), "-c", str(src), "-o", str(tmp_path / "hdr.o")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_null_handles_and_pointers_are_refused_not_dereferenced(pkg):
+    """Every handle-taking entry point of the set-up boundaries with NULL where a pointer is required: a status, never a crash."""
+    import ctypes as C
+    lib = pkg.load_library()
+    null = C.c_void_p()
+    i64 = C.c_int64(); vs = pkg.VoxelSummary(); ds = pkg.DepthSummary(); s = pkg.Summary()
+    poses = (C.c_double * 12)(*([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]))
+    intr = (C.c_double * 8)(100, 100, 50, 50, 0, 0, 0, 0)
+    sp = (C.c_int64 * 2)(0, 0)
+    wp = (C.c_int32 * 2)(0, 1)
+    out = C.c_void_p()
+    calls = [
+        lambda: lib.lvba_voxel_map_create(C.c_int32(1), None, None, C.c_int32(3), poses, None, C.byref(out), None),
+        lambda: lib.lvba_voxel_map_create(C.c_int32(1), sp, None, C.c_int32(3), poses, None, None, None),
+        lambda: lib.lvba_voxel_map_create(C.c_int32(-1), sp, None, C.c_int32(3), poses, None, C.byref(out), None),
+        lambda: lib.lvba_voxel_map_create(C.c_int32(1), sp, None, C.c_int32(2), poses, None, C.byref(out), None),
+        lambda: lib.lvba_voxel_map_create_windows(C.c_int32(0), wp, sp, None, C.c_int32(3), poses, None, C.byref(out), None),
+        lambda: lib.lvba_voxel_map_create_windows(C.c_int32(1), None, sp, None, C.c_int32(3), poses, None, C.byref(out), None),
+        lambda: lib.lvba_voxel_map_summary(null, C.byref(vs)),
+        lambda: lib.lvba_voxel_map_export(null, None, None, None, None, None, None, None, None),
+        lambda: lib.lvba_voxel_map_lookup(null, C.c_int64(1), poses, poses),
+        lambda: lib.lvba_voxel_map_windows(null, None, None),
+        lambda: lib.lvba_voxel_map_lidar_create(null, poses, C.byref(out)),
+        lambda: lib.lvba_voxel_map_lidar_lm(null, poses, C.c_int32(0), None, C.byref(s)),
+        lambda: lib.lvba_voxel_map_lidar_lm_batch(null, poses, C.c_int32(3), None, None, None),
+        lambda: lib.lvba_depth_grid_create(C.c_int32(1), None, None, C.c_int32(3), poses, poses, C.c_double(0.5), C.c_int32(-1), C.byref(out), None),
+        lambda: lib.lvba_depth_grid_create(C.c_int32(1), sp, None, C.c_int32(3), poses, poses, C.c_double(0.5), C.c_int32(-1), None, None),
+        lambda: lib.lvba_depth_render(null, C.c_int32(1), poses, poses, C.c_double(0.5), intr, C.c_int32(4), C.c_int32(4), None, C.byref(ds)),
+        lambda: lib.lvba_depth_backproject(null, C.c_int32(1), poses, poses, C.c_double(0.5), intr, C.c_int32(4), C.c_int32(4), sp, None, None, None, None),
+        lambda: lib.lvba_anchor_clouds_create(C.c_int32(1), wp, None, None, C.c_int32(3), poses, C.c_double(0.1), C.c_int32(-1), C.byref(out), C.byref(i64)),
+        lambda: lib.lvba_anchor_clouds_create(C.c_int32(1), wp, sp, None, C.c_int32(3), poses, C.c_double(0.1), C.c_int32(-1), None, C.byref(i64)),
+        lambda: lib.lvba_anchor_clouds_export(null, None, None, None),
+        lambda: lib.lvba_tracks_triangulate(C.c_int64(1), None, None, None, C.c_int32(1), poses, intr, C.c_int32(-1), None, None, None, None),
+        lambda: lib.lvba_tracks_mean_reproj(C.c_int64(-1), sp, None, None, C.c_int32(1), poses, intr, C.c_int32(-1), None, C.c_int32(1), None, None, None),
+    ]
+    for k, call in enumerate(calls):
+        assert call() == -1, k                                       # LVBA_ERR_INVALID_ARG
+    for destroy in (lib.lvba_voxel_map_destroy, lib.lvba_depth_grid_destroy, lib.lvba_anchor_clouds_destroy):
+        assert destroy(null) == 0                                    # destroying nothing is fine
