@@ -13,16 +13,9 @@
 // pivot column k is the contiguous range k+1..last[k]; all LDL^T fill stays inside the envelope.
 #pragma once
 #include "common.cuh"
+#include "env_types.h"
 
 namespace lvba {
-
-struct EnvView {
-  int n;                       // block rows
-  const int* first;            // [n]
-  const long long* row_start;  // [n+1] in blocks
-  const int* last;             // [n]   last[k] = max row i with first[i] <= k
-  long long nblocks;
-};
 
 LVBA_DEV long long env_block(const EnvView& e, int r, int c) { return e.row_start[r] + (c - e.first[r]); }
 
@@ -204,21 +197,6 @@ template <int N> LVBA_DEV void reg_alloc() { asm volatile("setmaxnreg.inc.sync.a
 template <int N> LVBA_DEV void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N)); }
 #define LVBA_T(i, j) ((i) * ((i) + 1) / 2 + (j))
 
-// One factorisation instance.  The twisted solve (runtime.cuh) runs two at once (gridDim.x = 2): the top half of
-// the pose system in natural order and the bottom half in REVERSED order, each on its own SM; both stop at the
-// separator (n_stop < n) and dump their Schur-updated trailing window + forward-substituted rhs.
-struct FactorJob {
-  EnvView e;
-  double* L;       // in: matrix (H + damping) in envelope layout; out: L_ik below the pivots
-  double* dinv;    // out: D_k^-1 of every pivot block (36 doubles, full symmetric)
-  double* z;       // in: rhs ; out: forward-substituted rhs of the pivots
-  int n_stop;      // number of pivots to eliminate (== e.n for a complete factorisation)
-  double* wdump;   // [bs*bs*36] trailing window at n_stop, block (i,j) at ((i-n_stop)*bs + (j-n_stop))*36, bs = e.n - n_stop
-  double* zdump;   // [bs*6]
-  int* status;     // set to 1 when a pivot block is singular / non-finite
-};
-// Jobs live in device memory (one per CTA): two for the twisted solve, one per window for the batched window BA.
-
 // x = D^-1 z  (block diagonal solve, fully parallel)
 __global__ void env_dinv_apply_kernel(int n, const double* __restrict__ dinv, const double* __restrict__ z, double* __restrict__ x) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,13 +209,6 @@ __global__ void env_dinv_apply_kernel(int n, const double* __restrict__ dinv, co
   for (int q = 0; q < 6; ++q) s += K[q] * zz[q];
   x[i] = s;
 }
-
-struct BacksolveJob {
-  EnvView e;
-  const double* L;
-  double* x;        // in: D^-1 z for the pivots (rows < n_given) and the FINAL solution for rows >= n_given ; out: solution
-  int n_given;      // rows >= n_given are given (separator of the twisted solve); == e.n for a plain solve
-};
 
 // status[0] |= status[1..n-1]  (the twisted solve has one flag per factorisation instance)
 __global__ void env_status_or_kernel(int* __restrict__ status, int n) {

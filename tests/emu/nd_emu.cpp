@@ -1,0 +1,252 @@
+// nd_emu.cpp — TEST INFRASTRUCTURE (never part of liblvba_b200.so): the substructured block LDL^T of
+// global-lvba_b200/csrc/nd_plan.h + nd_passes.h run on the CPU.  The plan builder, the job tables, the order of the
+// steps (nd::run) and every data-layout pass are the very code the device runs; the four heavy steps the device does with
+// kernels (factor_la.cuh, nd_kernels.cuh) are plain reference loops here that implement the documented semantics of
+// FactorJob / SpikeJob / SyrkSeg / BacksolveJob.  tests/test_nd_solver_emu.py compares the result with dense numpy solves.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../global-lvba_b200/csrc/nd_passes.h"
+#include "host_exec.h"
+
+using namespace lvba;
+
+namespace {
+
+inline long long blk(const EnvView& e, int r, int c) { return e.row_start[r] + (c - e.first[r]); }
+
+void inv6_sym_lower(const double* A, double* K) {        // inverse of the symmetric matrix given by the lower triangle of A
+  double M[6][12];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) { M[i][j] = (i >= j) ? A[i * 6 + j] : A[j * 6 + i]; M[i][6 + j] = (i == j) ? 1.0 : 0.0; }
+  for (int p = 0; p < 6; ++p) {                            // Gauss-Jordan without pivoting (LDL^T without pivoting)
+    const double ip = 1.0 / M[p][p];
+    for (int j = 0; j < 12; ++j) M[p][j] *= ip;
+    for (int i = 0; i < 6; ++i)
+      if (i != p) { const double f = M[i][p]; for (int j = 0; j < 12; ++j) M[i][j] -= f * M[p][j]; }
+  }
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) K[i * 6 + j] = M[i][6 + j];
+}
+
+struct NdHostExec {
+  HostExec base;
+  template <class F> void pass(long long n, const F& f) { base.for_each(n, f); }
+  void zero(double* p, long long n) { std::memset(p, 0, (size_t)n * sizeof(double)); }
+
+  void factor(const FactorJob* jobs, int nj, int /*max_col*/) {
+    for (int q = 0; q < nj; ++q) {
+      const FactorJob& J = jobs[q];
+      const EnvView& e = J.e;
+      const int n = e.n, ns = J.n_stop;
+      // local copy of the view (rows x their envelope columns)
+      std::vector<std::vector<double>> A((size_t)n);
+      for (int i = 0; i < n; ++i) {
+        A[i].resize((size_t)(i - e.first[i] + 1) * 36);
+        std::memcpy(A[i].data(), J.L + blk(e, i, e.first[i]) * 36, A[i].size() * sizeof(double));
+      }
+      auto at = [&](int i, int j) -> double* { return A[i].data() + (size_t)(j - e.first[i]) * 36; };
+      std::vector<double> z((size_t)n * 6);
+      std::memcpy(z.data(), J.z, z.size() * sizeof(double));
+      std::vector<double> T((size_t)n * 36), Lc((size_t)n * 36);
+      for (int k = 0; k < ns; ++k) {
+        double K[36];
+        inv6_sym_lower(at(k, k), K);
+        double chk = 0.0;
+        for (int i = 0; i < 36; ++i) chk += K[i];
+        if (!std::isfinite(chk)) J.status[0] = 1;
+        std::memcpy(J.dinv + (long long)k * 36, K, sizeof K);
+        int hi = k;
+        for (int i = k + 1; i < n && e.first[i] <= k; ++i) {
+          hi = i;
+          std::memcpy(&T[(size_t)i * 36], at(i, k), 36 * sizeof(double));
+          for (int a = 0; a < 6; ++a)
+            for (int b = 0; b < 6; ++b) {
+              double s = 0.0;
+              for (int c = 0; c < 6; ++c) s += T[(size_t)i * 36 + a * 6 + c] * K[c * 6 + b];
+              Lc[(size_t)i * 36 + a * 6 + b] = s;
+            }
+          std::memcpy(at(i, k), &Lc[(size_t)i * 36], 36 * sizeof(double));
+          for (int a = 0; a < 6; ++a) {
+            double s = 0.0;
+            for (int c = 0; c < 6; ++c) s += Lc[(size_t)i * 36 + a * 6 + c] * z[6 * k + c];
+            z[6 * i + a] -= s;
+          }
+        }
+        for (int i = k + 1; i <= hi; ++i)
+          for (int j = k + 1; j <= i; ++j) {
+            double* d = at(i, j);
+            for (int a = 0; a < 6; ++a)
+              for (int b = 0; b < 6; ++b) {
+                double s = 0.0;
+                for (int c = 0; c < 6; ++c) s += Lc[(size_t)i * 36 + a * 6 + c] * T[(size_t)j * 36 + b * 6 + c];
+                d[a * 6 + b] -= s;
+              }
+          }
+      }
+      // what the kernel leaves behind: L_ik below the pivots, z of the pivots, the trailing window and its rhs in the dumps;
+      // the diagonal blocks and the trailing part of L / z stay as they were
+      for (int i = 0; i < n; ++i)
+        for (int j = e.first[i]; j < i && j < ns; ++j) std::memcpy(J.L + blk(e, i, j) * 36, at(i, j), 36 * sizeof(double));
+      for (int k = 0; k < ns; ++k) for (int a = 0; a < 6; ++a) J.z[6 * k + a] = z[6 * k + a];
+      const int bs = n - ns;
+      if (bs > 0 && J.wdump) {
+        for (int hi = 0; hi < bs; ++hi)
+          for (int lo = 0; lo <= hi; ++lo) {
+            double* dst = J.wdump + ((long long)hi * bs + lo) * 36;
+            const int i = ns + hi, j = ns + lo;
+            if (j >= e.first[i]) std::memcpy(dst, at(i, j), 36 * sizeof(double));
+            else std::memset(dst, 0, 36 * sizeof(double));
+          }
+        if (J.zdump) for (int o = 0; o < bs * 6; ++o) J.zdump[o] = z[6 * ns + o];
+      }
+    }
+  }
+
+  void spike(const nd::SpikeJob* jobs, int nj, int, int) {
+    for (int q = 0; q < nj; ++q) {
+      const nd::SpikeJob& J = jobs[q];
+      const EnvView& e = J.e;
+      const int KS = J.KS;
+      for (int k = 0; k < e.n; ++k) {
+        const int jend = k < J.n_stop ? k : J.n_stop;
+        for (int x = 0; x < 6; ++x)
+          for (int c = 0; c < KS; ++c) {
+            double acc = (k < J.nE && k < J.n_stop) ? J.E[((long long)k * 6 + x) * KS + c] : 0.0;
+            for (int j = e.first[k]; j < jend; ++j) {
+              const double* b = J.L + blk(e, k, j) * 36 + x * 6;
+              for (int y = 0; y < 6; ++y) acc -= b[y] * J.Z[((long long)j * 6 + y) * KS + c];
+            }
+            J.Z[((long long)k * 6 + x) * KS + c] = acc;
+          }
+      }
+    }
+  }
+
+  void syrk(const nd::SyrkSeg* segs, int ns, int, int) {
+    for (int q = 0; q < ns; ++q) {
+      const nd::SyrkSeg& G = segs[q];
+      const int KS = G.KS;
+      std::vector<double> KZ((size_t)6 * KS);
+      for (int k = 0; k < G.rows; ++k) {
+        const double* Kk = G.K + (long long)k * 36;
+        const double* Zk = G.Z + (long long)k * 6 * KS;
+        double Kw[6];
+        for (int p = 0; p < 6; ++p) {
+          double s = 0.0;
+          for (int r = 0; r < 6; ++r) s += Kk[p * 6 + r] * G.w[(long long)k * 6 + r];
+          Kw[p] = s;
+          for (int c = 0; c < KS; ++c) {
+            double t = 0.0;
+            for (int r = 0; r < 6; ++r) t += Kk[p * 6 + r] * Zk[(long long)r * KS + c];
+            KZ[(size_t)p * KS + c] = t;
+          }
+        }
+        for (int ga = 0; ga < KS; ++ga) {
+          const int bi = ga / 6;
+          for (int gb = 0; gb < KS; ++gb) {
+            const int bj = gb / 6;
+            if (bj > bi) continue;
+            double s = 0.0;
+            for (int p = 0; p < 6; ++p) s += KZ[(size_t)p * KS + ga] * Zk[(long long)p * KS + gb];
+            G.U[nd::tri_off(bi, bj) + (ga - 6 * bi) * 6 + (gb - 6 * bj)] -= s;
+          }
+          double s = 0.0;
+          for (int p = 0; p < 6; ++p) s += Zk[(long long)p * KS + ga] * Kw[p];
+          G.u[ga] -= s;
+        }
+      }
+    }
+  }
+
+  void backsolve(const BacksolveJob* jobs, int nj) {
+    for (int q = 0; q < nj; ++q) {
+      const BacksolveJob& J = jobs[q];
+      const EnvView& e = J.e;
+      for (int i = e.n - 1; i >= 0; --i) {
+        const int upto = i < J.n_given ? i : J.n_given;
+        for (int j = e.first[i]; j < upto; ++j) {
+          const double* b = J.L + blk(e, i, j) * 36;
+          for (int c = 0; c < 6; ++c) {
+            double s = 0.0;
+            for (int a = 0; a < 6; ++a) s += b[a * 6 + c] * J.x[6 * (long long)i + a];
+            J.x[6 * (long long)j + c] -= s;
+          }
+        }
+      }
+    }
+  }
+};
+
+template <class T>
+T* poisoned(std::vector<T>& v, size_t n) {
+  v.resize(n + 1);
+  std::memset((void*)v.data(), 0xA5, (n + 1) * sizeof(T));
+  return v.data();
+}
+
+}  // namespace
+
+// Solves (H + diag(dadd)) x = rhs with p_want chunks (fewer when the structure does not allow as many).
+// first[] must be monotone (Envelope::build); H is the envelope storage for it.  Returns the number of chunks used, 0 when
+// no plan exists.  info: [0] tree depth (levels), [1] nodes, [2] longest interior, [3] widest separator
+extern "C" int nd_emu_solve(int n, const int* first, const double* H, const double* dadd, const double* rhs, double* x,
+                            int p_want, int* info) {
+  std::vector<long long> row_start((size_t)n + 1, 0);
+  for (int r = 0; r < n; ++r) row_start[r + 1] = row_start[r] + (r - first[r] + 1);
+  const long long nblocks = row_start[n];
+  std::vector<int> last((size_t)n, 0);
+  int max_col = 0;
+  {
+    int i = 0;
+    for (int k = 0; k < n; ++k) {
+      if (i < k) i = k;
+      while (i + 1 < n && first[i + 1] <= k) ++i;
+      last[k] = i;
+      max_col = std::max(max_col, i - k);
+    }
+  }
+  nd::Plan P;
+  const int p = nd::choose_chunks(n, first, last.data(), row_start.data(), max_col, p_want, P);
+  if (p == 0) return 0;
+  std::vector<nd::NodeDev> nodes;
+  for (const nd::Node& v : P.nodes) nodes.push_back(nd::to_dev(v));
+  std::vector<double> vL, vz, vzs, vd, vU, vu, vZ, vE, vT, vW, vw;
+  nd::Tables t{};
+  t.n = n; t.first = first; t.row_start = row_start.data(); t.nodes = nodes.data(); t.H = H; t.dadd = dadd;
+  t.L = poisoned(vL, (size_t)nblocks * 36);
+  t.z = poisoned(vz, (size_t)n * 6);
+  std::memcpy(t.z, rhs, (size_t)n * 6 * sizeof(double));
+  t.zs = poisoned(vzs, (size_t)n * 6);
+  t.dinv = poisoned(vd, (size_t)n * 36);
+  t.x = x;
+  t.U = poisoned(vU, (size_t)P.sizeU); t.u = poisoned(vu, (size_t)P.sizeu); t.Z = poisoned(vZ, (size_t)P.sizeZ);
+  t.E = poisoned(vE, (size_t)P.sizeE); t.T = poisoned(vT, (size_t)P.sizeT); t.W = poisoned(vW, (size_t)P.sizeW);
+  t.w = poisoned(vw, (size_t)P.sizew);
+  std::vector<int> zeros(32, 0), last_by_w(32 * 32, 0);
+  std::vector<long long> tri(33, 0);
+  for (int i = 0; i < 33; ++i) tri[i] = (long long)i * (i + 1) / 2;
+  for (int w = 0; w < 32; ++w) for (int i = 0; i < 32; ++i) last_by_w[w * 32 + i] = w - 1;
+  nd::DenseViewArrays dv{zeros.data(), tri.data(), last_by_w.data()};
+  std::vector<int> status(P.nodes.size(), 0);
+  std::vector<nd::LevelJobs> jobs;
+  nd::build_level_jobs(P, t, P.first_rel.data(), P.rs_adj.data(), P.last_rel.data(), nblocks, dv, status.data(), jobs);
+  std::vector<nd::LevelDev> lv;
+  for (auto& J : jobs)
+    lv.push_back(nd::LevelDev{J.ids.data(), (int)J.ids.size(), J.factor.data(), (int)J.factor.size(), J.spike.data(), (int)J.spike.size(),
+                              J.syrk.data(), (int)J.syrk.size(), J.back.data(), (int)J.back.size(), J.asm_stride, J.corr_stride,
+                              J.max_ks, J.max_rows, J.max_col});
+  NdHostExec ex;
+  nd::run(ex, P, t, lv.data(), (int)lv.size(), nblocks, nd::leaf_e_stride(P), nd::leaf_final_stride(P));
+  if (info) {
+    info[0] = (int)P.levels.size(); info[1] = (int)P.nodes.size();
+    int mi = 0, mw = 0;
+    for (int c = 0; c < P.p; ++c) mi = std::max(mi, P.nodes[c].npiv);
+    for (int j = 1; j < P.p; ++j) mw = std::max(mw, P.sep_width[j]);
+    info[2] = mi; info[3] = mw;
+  }
+  int bad = 0;
+  for (int s : status) bad |= s;
+  return bad ? -p : p;
+}

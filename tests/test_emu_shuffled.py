@@ -17,7 +17,7 @@ def test_host_policy_suites_pass_with_shuffled_items(seed):
     env = dict(os.environ, LVBA_EMU_SHUFFLE=seed)
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider",
                         "tests/test_voxel_emu.py", "tests/test_depth_emu.py", "tests/test_anchor_emu.py",
-                        "tests/test_wide_solver_emu.py", "tests/test_big_voxel_emu.py", "tests/test_track_emu.py"],
+                        "tests/test_wide_solver_emu.py", "tests/test_big_voxel_emu.py", "tests/test_track_emu.py", "tests/test_nd_solver_emu.py"],
                        capture_output=True, text=True, cwd=str(ROOT), env=env, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "passed" in r.stdout
@@ -32,6 +32,6 @@ def test_host_policy_suites_pass_under_address_and_ub_sanitizers():
     env = dict(os.environ, LVBA_EMU_SANITIZE="1", LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1", LVBA_EMU_SHUFFLE="7")
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider",
                         "tests/test_voxel_emu.py", "tests/test_depth_emu.py", "tests/test_anchor_emu.py",
-                        "tests/test_wide_solver_emu.py", "tests/test_big_voxel_emu.py", "tests/test_track_emu.py"],
+                        "tests/test_wide_solver_emu.py", "tests/test_big_voxel_emu.py", "tests/test_track_emu.py", "tests/test_nd_solver_emu.py"],
                        capture_output=True, text=True, cwd=str(ROOT), env=env, timeout=1800)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

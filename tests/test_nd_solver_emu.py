@@ -1,0 +1,148 @@
+"""The substructured block LDL^T (global-lvba_b200/csrc/nd_plan.h + nd_passes.h — what the device runs for the pose / camera
+system: chunk interiors and separators eliminated by independent CTAs) checked without a GPU.
+The plan builder, the job tables, the step order and all layout passes are the device's own code (tests/emu/nd_emu.cpp runs
+them with a sequential host policy and reference loops for the four kernels); the result is compared with a dense numpy solve
+of the same symmetric INDEFINITE block system (LDL^T without pivoting, as SimplicialLDLT,
+reference include/BALM/bavoxel.hpp:695-710)."""
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    so = tmp_path_factory.mktemp("emu") / "libnd_emu.so"
+    san = ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-g"] if os.environ.get("LVBA_EMU_SANITIZE") else []
+    cmd = ["g++", "-std=c++17", "-O2", *san, "-Wall", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "nd_emu.cpp"), "-o", str(so)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = ctypes.CDLL(str(so))
+    lib.nd_emu_solve.restype = ctypes.c_int
+    return lib
+
+
+def envelope(first_raw):
+    """Envelope::build (csrc/runtime.cuh): first made monotone, row offsets."""
+    n = len(first_raw)
+    first = np.minimum(np.asarray(first_raw), np.arange(n))
+    for r in range(n - 2, -1, -1):
+        first[r] = min(first[r], first[r + 1])
+    row_start = np.zeros(n + 1, np.int64)
+    row_start[1:] = np.cumsum(np.arange(n) - first + 1)
+    return first.astype(np.int32), row_start
+
+
+def random_system(n, first, row_start, rng, indefinite, fill=0.8):
+    M = np.zeros((6 * n, 6 * n))
+    for r in range(n):
+        for c in range(first[r], r):
+            if rng.random() < fill:
+                M[6 * r:6 * r + 6, 6 * c:6 * c + 6] = rng.normal(0, 1, (6, 6))
+    M = M + M.T
+    for r in range(n):
+        D = rng.normal(0, 1, (6, 6)); D = D @ D.T + (14.0 * (r - first[r] + 2)) * np.eye(6)
+        if indefinite and r % 3 == 1:
+            D = -D
+        M[6 * r:6 * r + 6, 6 * r:6 * r + 6] = D
+    L = np.zeros((row_start[-1], 36))
+    for r in range(n):
+        for c in range(first[r], r + 1):
+            b = M[6 * r:6 * r + 6, 6 * c:6 * c + 6].copy()
+            if c == r:
+                b = np.tril(b) + np.triu(rng.normal(0, 99, (6, 6)), 1)      # the upper triangle of a diagonal block is never read
+            L[row_start[r] + c - first[r]] = b.ravel()
+    return M, L
+
+
+def solve(emu, n, first, H, dadd, rhs, p):
+    x = np.full(6 * n, np.nan)
+    info = np.zeros(4, np.int32)
+    c = lambda a, t: a.ctypes.data_as(ctypes.POINTER(t))
+    used = emu.nd_emu_solve(n, c(first, ctypes.c_int), c(H, ctypes.c_double), c(dadd, ctypes.c_double), c(rhs, ctypes.c_double),
+                            c(x, ctypes.c_double), p, c(info, ctypes.c_int))
+    return used, x, info
+
+
+CASES = [
+    # n, half-bandwidth (blocks), chunks wanted, indefinite
+    (64, 5, 2, False), (64, 5, 4, True), (200, 12, 4, True), (203, 12, 7, True), (400, 30, 8, True), (397, 30, 5, True),
+    (700, 20, 16, True), (701, 7, 32, True), (1000, 30, 16, True),
+]
+
+
+@pytest.mark.parametrize("n,b,p,indef", CASES)
+def test_banded_systems_match_dense_solve(emu, n, b, p, indef):
+    rng = np.random.default_rng(1000 * n + p)
+    first, rs = envelope([max(0, r - b) for r in range(n)])
+    M, H = random_system(n, first, rs, rng, indef)
+    dadd = rng.uniform(0.05, 0.2, 6 * n)
+    rhs = rng.normal(0, 1, 6 * n)
+    used, x, info = solve(emu, n, first, H, dadd, rhs, p)
+    assert used == p, (used, info)
+    xr = np.linalg.solve(M + np.diag(dadd), rhs)
+    assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max(), np.abs(x - xr).max()
+
+
+def test_ragged_envelope_and_narrow_places(emu):
+    """Band width varying along the trajectory (including stretches narrower than a chunk and nearly decoupled poses)."""
+    rng = np.random.default_rng(77)
+    n = 520
+    width = np.concatenate([np.full(130, 30), np.full(130, 3), np.full(130, 17), np.full(130, 9)])
+    first_raw = [max(0, r - int(width[r])) for r in range(n)]
+    first, rs = envelope(first_raw)
+    M, H = random_system(n, first, rs, rng, True, fill=0.6)
+    dadd = rng.uniform(0.05, 0.2, 6 * n)
+    rhs = rng.normal(0, 1, 6 * n)
+    xr = np.linalg.solve(M + np.diag(dadd), rhs)
+    for p in (2, 3, 4, 8, 11):
+        used, x, info = solve(emu, n, first, H, dadd, rhs, p)
+        assert used == p
+        assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max(), (p, np.abs(x - xr).max())
+
+
+def test_short_interiors_with_direct_separator_coupling(emu):
+    """Chunks shorter than the band: consecutive separators couple directly through the original matrix."""
+    rng = np.random.default_rng(5)
+    n, b = 300, 30
+    first, rs = envelope([max(0, r - b) for r in range(n)])
+    M, H = random_system(n, first, rs, rng, True)
+    dadd = rng.uniform(0.05, 0.2, 6 * n)
+    rhs = rng.normal(0, 1, 6 * n)
+    xr = np.linalg.solve(M + np.diag(dadd), rhs)
+    used, x, info = solve(emu, n, first, H, dadd, rhs, 8)       # 8 chunks of ~11 interior rows + 7 separators of 30
+    assert used >= 6 and info[2] < b, (used, info)
+    assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max()
+
+
+def test_refuses_what_it_cannot_cut(emu):
+    rng = np.random.default_rng(6)
+    # band wider than a separator can be
+    n = 200
+    first, rs = envelope([max(0, r - 40) for r in range(n)])
+    M, H = random_system(n, first, rs, rng, False)
+    used, _, _ = solve(emu, n, first, H, np.zeros(6 * n), np.zeros(6 * n), 4)
+    assert used == 0
+    # too short for two chunks
+    n = 16
+    first, rs = envelope([max(0, r - 10) for r in range(n)])
+    M, H = random_system(n, first, rs, rng, False)
+    used, _, _ = solve(emu, n, first, H, np.zeros(6 * n), np.zeros(6 * n), 4)
+    assert used == 0
+    # block diagonal in the middle (band vanishes at the cut): fewer chunks or none, never a wrong answer
+    n = 120
+    fr = [max(0, r - 6) for r in range(n)]
+    for r in range(60, n):
+        fr[r] = max(fr[r], 60)
+    first, rs = envelope(fr)
+    M, H = random_system(n, first, rs, rng, True)
+    dadd = rng.uniform(0.05, 0.2, 6 * n); rhs = rng.normal(0, 1, 6 * n)
+    used, x, _ = solve(emu, n, first, H, dadd, rhs, 2)
+    if used:
+        xr = np.linalg.solve(M + np.diag(dadd), rhs)
+        assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max()
