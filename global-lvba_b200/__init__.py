@@ -40,6 +40,7 @@ EXPORTS = [
     "lvba_depth_grid_create", "lvba_depth_render", "lvba_depth_backproject", "lvba_depth_grid_destroy",
     "lvba_tracks_triangulate", "lvba_tracks_mean_reproj",
     "lvba_anchor_clouds_create", "lvba_anchor_clouds_export", "lvba_anchor_clouds_destroy",
+    "lvba_env_solve",
     "lvba_comm_unique_id", "lvba_comm_init", "lvba_comm_destroy", "lvba_comm_info", "lvba_shard_owner",
 ]
 
@@ -268,6 +269,34 @@ class LidarProblem:
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         _chk(self._lib.lvba_lidar_counts(self._h, C.byref(a), C.byref(b), C.byref(c) if nonzero else None, C.byref(d)))
         return dict(nnz=a.value, n_blocks_env=b.value, n_blocks_nonzero=c.value if nonzero else None, n_pairs=d.value)
+
+
+SOLVE_AUTO, SOLVE_ONE_CTA, SOLVE_TWISTED, SOLVE_CHUNKED, SOLVE_SHARED_WINDOW, SOLVE_ANY_WIDTH = range(6)
+
+
+def env_layout(first_raw):
+    """Monotone first[] and row offsets of the block envelope (Envelope::build, csrc/runtime.cuh)."""
+    n = len(first_raw)
+    first = np.minimum(np.asarray(first_raw, np.int64), np.arange(n))
+    first = np.minimum.accumulate(first[::-1])[::-1]
+    row_start = np.zeros(n + 1, np.int64)
+    row_start[1:] = np.cumsum(np.arange(n) - first + 1)
+    return first.astype(np.int32), row_start
+
+
+def env_solve(first, blocks, dadd, rhs, path=SOLVE_AUTO, chunks=0, reps=1, device=-1):
+    """lvba_env_solve: (A + diag(dadd)) x = rhs through one of the block LDL^T paths; returns x, ms, info dict."""
+    lib = load_library()
+    first = np.ascontiguousarray(first, np.int32)
+    n = len(first)
+    blocks = _f64(blocks); dadd = _f64(dadd); rhs = _f64(rhs)
+    x = np.zeros(6 * n)
+    ms = C.c_double(0.0)
+    info = np.zeros(4, np.int32)
+    _chk(lib.lvba_env_solve(C.c_int32(n), _p(first, C.c_int32), _p(blocks, C.c_double), _p(dadd, C.c_double), _p(rhs, C.c_double),
+                            _p(x, C.c_double), C.c_int32(path), C.c_int32(chunks), C.c_int32(reps), C.c_int32(device),
+                            C.byref(ms), _p(info, C.c_int32)))
+    return x, ms.value, {"path": int(info[0]), "chunks": int(info[1]), "levels": int(info[2]), "launches": int(info[3])}
 
 
 def env_blocks_to_dense(br, bc, blocks, n):

@@ -29,6 +29,69 @@ const char* lvba_status_string(int status) {
   }
 }
 
+// ---------------------------------------------------------------- the block LDL^T on its own (diagnostics / tests)
+int lvba_env_solve(int32_t n, const int32_t* first, const double* blocks, const double* dadd, const double* rhs,
+                   double* x, int32_t path, int32_t chunks, int32_t reps, int32_t device, double* ms, int32_t* info) {
+  using namespace lvba;
+  if (n <= 0 || !first || !blocks || !dadd || !rhs || !x) return fail(LVBA_ERR_INVALID_ARG, "null argument or n <= 0");
+  if (path < LVBA_SOLVE_AUTO || path > LVBA_SOLVE_ANY_WIDTH) return fail(LVBA_ERR_INVALID_ARG, "unknown path %d", path);
+  for (int r = 0; r < n; ++r) {
+    if (first[r] < 0 || first[r] > r) return fail(LVBA_ERR_INVALID_ARG, "first[%d] = %d outside [0, %d]", r, first[r], r);
+    if (r > 0 && first[r] < first[r - 1]) return fail(LVBA_ERR_INVALID_ARG, "first[] must be non-decreasing (row %d)", r);
+  }
+  LVBA_TRY(select_device(device));
+  cudaStream_t s = nullptr;
+  LVBA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } guard{s};
+  int rc = LVBA_OK;
+  {
+    Envelope env;
+    int64_t bytes = 0;
+    std::vector<int> fr(first, first + n);
+    LVBA_TRY(env.build(fr, s, &bytes));
+    EnvSolver sol;
+    LVBA_TRY(sol.prepare(env, s, path, chunks));
+    int taken;
+    if (sol.wide) taken = LVBA_SOLVE_ANY_WIDTH;
+    else if (sol.nd_on) taken = LVBA_SOLVE_CHUNKED;
+    else if (sol.tw) taken = LVBA_SOLVE_TWISTED;
+    else if (env.max_col <= 30 && env.n >= 3 && !sol.force_generic) taken = LVBA_SOLVE_ONE_CTA;
+    else taken = LVBA_SOLVE_SHARED_WINDOW;
+    if (path != LVBA_SOLVE_AUTO && taken != path)
+      return fail(LVBA_ERR_UNSUPPORTED, "path %d is not available for this structure (n = %d, tallest column %d blocks): would take path %d", path, n, env.max_col, taken);
+    DevBuf<double> dH, dD, dR, dX;
+    LVBA_TRY(dH.upload(blocks, (size_t)env.nblocks * 36, s)); LVBA_TRY(dD.upload(dadd, (size_t)n * 6, s));
+    LVBA_TRY(dR.upload(rhs, (size_t)n * 6, s)); LVBA_TRY(dX.alloc((size_t)n * 6));
+    cudaEvent_t e0, e1;
+    LVBA_CUDA(cudaEventCreate(&e0)); LVBA_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    int64_t launches = 0, per = 0;
+    for (int rep = 0; rep < std::max(reps, 1) && rc == LVBA_OK; ++rep) {
+      cudaMemcpyAsync(sol.z.p, dR.p, (size_t)n * 6 * sizeof(double), cudaMemcpyDeviceToDevice, s);
+      cudaMemsetAsync(dX.p, 0, (size_t)n * 6 * sizeof(double), s);
+      const int64_t l0 = launches;
+      cudaEventRecord(e0, s);
+      rc = sol.solve(env, dH.p, dD.p, dX.p, s, &launches);
+      cudaEventRecord(e1, s);
+      per = launches - l0;
+      if (rc == LVBA_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = fail(LVBA_ERR_CUDA, "solve: %s", cudaGetErrorString(cudaGetLastError()));
+      float t = 0.f;
+      if (rc == LVBA_OK && cudaEventElapsedTime(&t, e0, e1) == cudaSuccess) best = std::min(best, t);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc == LVBA_OK) {
+      int st = 0;
+      LVBA_CUDA(cudaMemcpy(&st, sol.status.p, sizeof(int), cudaMemcpyDeviceToHost));
+      LVBA_CUDA(cudaMemcpy(x, dX.p, (size_t)n * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+      if (st) rc = fail(LVBA_ERR_NUMERIC, "singular / non-finite pivot block");
+    }
+    if (ms) *ms = best;
+    if (info) { info[0] = taken; info[1] = sol.nd_on ? sol.nd.chunks : 0; info[2] = sol.nd_on ? (int)sol.nd.plan.levels.size() : 0; info[3] = (int)per; }
+    cudaStreamSynchronize(s);       // nothing of `sol` / the buffers may be in flight when they go back to the pool
+  }
+  return rc;
+}
+
 // ---------------------------------------------------------------- multi-GPU
 int lvba_comm_unique_id(void* id_out) {
   if (!id_out) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");

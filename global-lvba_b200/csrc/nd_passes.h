@@ -99,12 +99,8 @@ LVBA_NHD double upd_elem(const double* U, int i, int j, int x, int y) {
   return (i >= j) ? U[tri_off(i, j) + x * 6 + y] : U[tri_off(j, i) + y * 6 + x];
 }
 
-// ---- L = H + diag(dadd): items = blocks * 36
-struct CopyDampF {
-  Tables t; long long n_elems;
-  LVBA_NHD void operator()(int64_t i) const { t.L[i] = t.H[i]; }
-};
-struct AddDiagF {            // items = 6 n
+// ---- L = H + diag(dadd): a plain copy, then items = 6 n
+struct AddDiagF {
   Tables t;
   LVBA_NHD void operator()(int64_t i) const {
     const int r = (int)(i / 6), a = (int)(i % 6);
@@ -337,6 +333,7 @@ struct LevelDev {
 // The whole solve.  Exec provides:
 //   pass(n_items, functor)                         item-parallel pass
 //   zero(ptr, count)                               fill doubles with 0
+//   copy(dst, src, count)                          copy doubles
 //   factor(jobs, n, max_col)                       block LDL^T instances (FactorJob semantics, env_types.h)
 //   spike(jobs, n, max_ks, max_rows)               SpikeJob semantics
 //   syrk(segs, n, max_ks, max_rows)                SyrkSeg semantics
@@ -344,7 +341,7 @@ struct LevelDev {
 template <class Exec>
 inline void run(Exec& ex, const Plan& P, const Tables& t, const LevelDev* lv, int n_levels, long long nblocks,
                 long long leaf_e, long long leaf_fin) {
-  ex.pass(nblocks * 36, CopyDampF{t, nblocks * 36});
+  ex.copy(t.L, t.H, nblocks * 36);
   ex.pass((long long)6 * t.n, AddDiagF{t});
   ex.zero(t.U, P.sizeU);
   ex.zero(t.u, P.sizeu);

@@ -1,0 +1,179 @@
+// nd_solver.cuh — device side of the substructured block LDL^T: buffers, job tables and the CUDA executor of nd::run
+// (nd_passes.h).  The banded / dense factorisations and the backward substitutions are the register-window kernels of
+// factor_la.cuh (one CTA per chunk interior / separator: grid = number of nodes of a tree level), launched through the
+// callbacks EnvSolver passes in; the whole solve (~10 launches per tree level) is captured once per structure into a CUDA
+// graph and replayed per LM pass.
+//
+// Replaces Eigen::SimplicialLDLT in BALM2::damping_iter (reference include/BALM/bavoxel.hpp:695-710) and the DENSE_SCHUR
+// Cholesky of ceres::Solve (src/lvba_system.cpp:1573-1575, 1643) for systems long enough to be cut.
+#pragma once
+#include <functional>
+
+#include "nd_kernels.cuh"
+
+namespace lvba {
+
+struct NdDevice {
+  nd::Plan plan;
+  bool ready = false;
+  int chunks = 0;
+  // structure
+  DevBuf<int> d_first_rel, d_last_rel, d_zeros, d_last_by_w, d_ids;
+  DevBuf<long long> d_rs_adj, d_tri;
+  DevBuf<nd::NodeDev> d_nodes;
+  // numeric pools
+  DevBuf<double> zs, U, u, Z, E, T, W, w;
+  // job tables (rebuilt when the caller's pointers change)
+  DevBuf<FactorJob> d_factor;
+  DevBuf<nd::SpikeJob> d_spike;
+  DevBuf<nd::SyrkSeg> d_syrk;
+  DevBuf<BacksolveJob> d_back;
+  std::vector<nd::LevelDev> lv;
+  nd::Tables tab{};
+  long long leaf_e = 1, leaf_fin = 1;
+  const double* key_H = nullptr; const double* key_dadd = nullptr; const double* key_x = nullptr; const double* key_z = nullptr;
+  // CUDA graph of one solve
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  bool use_graph = true;
+  int64_t launches_per_solve = 0;
+
+  ~NdDevice() { drop_graph(); }
+  void drop_graph() {
+    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+    if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+  }
+
+  // number of chunks for a system of n block rows with columns of at most max_col blocks: the chain is
+  // (interior) + (tree depth) x (separator width) pivot columns; more chunks shorten the first term and lengthen the second
+  static int default_chunks(int n, int max_col) {
+    const char* ev = getenv("LVBA_ND_CHUNKS");
+    if (ev && ev[0]) return atoi(ev);
+    if (n < 384) return 0;                                  // the twisted pair is faster for short chains
+    int best = 0; long long best_cost = (long long)n / 2 + max_col;     // twisted: n/2 + separator
+    for (int p = 4; p <= 128; p *= 2) {
+      const long long interior = ((long long)n - (long long)(p - 1) * max_col) / p;
+      if (interior < 2 * nd::kMinInterior) break;
+      int depth = 0; while ((1 << depth) < p) ++depth;
+      const long long cost = interior + (long long)depth * max_col;
+      if (cost < best_cost) { best_cost = cost; best = p; }
+    }
+    return best;
+  }
+
+  int prepare(int n, const std::vector<int>& first, const std::vector<int>& last, const std::vector<long long>& row_start, int max_col,
+              int p_want, cudaStream_t s) {
+    ready = false; chunks = 0;
+    drop_graph();
+    key_H = key_dadd = key_x = key_z = nullptr;
+    if (p_want < 2) return LVBA_OK;
+    const int p = nd::choose_chunks(n, first.data(), last.data(), row_start.data(), max_col, p_want, plan);
+    if (p < 2) return LVBA_OK;                               // structure cannot be cut: the caller keeps its other paths
+    {
+      const char* g = getenv("LVBA_ND_GRAPH");
+      use_graph = !(g && g[0] == '0');
+    }
+    int64_t dummy = 0;
+    LVBA_TRY(d_first_rel.upload(plan.first_rel, s, &dummy));
+    LVBA_TRY(d_last_rel.upload(plan.last_rel, s, &dummy));
+    LVBA_TRY(d_rs_adj.upload(plan.rs_adj, s, &dummy));
+    std::vector<int> zeros(32, 0), last_by_w(32 * 32, 0);
+    std::vector<long long> tri(33, 0);
+    for (int i = 0; i < 33; ++i) tri[i] = (long long)i * (i + 1) / 2;
+    for (int w_ = 0; w_ < 32; ++w_) for (int i = 0; i < 32; ++i) last_by_w[w_ * 32 + i] = w_ - 1;
+    LVBA_TRY(d_zeros.upload(zeros, s, &dummy));
+    LVBA_TRY(d_last_by_w.upload(last_by_w, s, &dummy));
+    LVBA_TRY(d_tri.upload(tri, s, &dummy));
+    std::vector<nd::NodeDev> nodes;
+    for (const nd::Node& v : plan.nodes) nodes.push_back(nd::to_dev(v));
+    LVBA_TRY(d_nodes.upload(nodes, s, &dummy));
+    LVBA_TRY(zs.alloc((size_t)n * 6));
+    LVBA_TRY(U.alloc((size_t)std::max<long long>(plan.sizeU, 1))); LVBA_TRY(u.alloc((size_t)std::max<long long>(plan.sizeu, 1)));
+    LVBA_TRY(Z.alloc((size_t)std::max<long long>(plan.sizeZ, 1))); LVBA_TRY(E.alloc((size_t)std::max<long long>(plan.sizeE, 1)));
+    LVBA_TRY(T.alloc((size_t)std::max<long long>(plan.sizeT, 1))); LVBA_TRY(W.alloc((size_t)std::max<long long>(plan.sizeW, 1)));
+    LVBA_TRY(w.alloc((size_t)std::max<long long>(plan.sizew, 1)));
+    LVBA_CUDA(cudaFuncSetAttribute(nd_spike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpikeSmem));
+    LVBA_CUDA(cudaStreamSynchronize(s));                     // local vectors
+    leaf_e = nd::leaf_e_stride(plan); leaf_fin = nd::leaf_final_stride(plan);
+    chunks = p; ready = true;
+    return LVBA_OK;
+  }
+
+  // job tables for the caller's buffers: L (working copy, envelope layout), dinv [n][36], z [6n] (rhs in / scratch), status
+  // [1 + nodes], H, dadd, x
+  int build_tables(const EnvView& genv, const double* H, const double* dadd, double* L, double* dinv, double* z, double* x,
+                   int* status, cudaStream_t s) {
+    if (key_H == H && key_dadd == dadd && key_x == x && key_z == z && !lv.empty()) return LVBA_OK;
+    drop_graph();
+    tab = nd::Tables{};
+    tab.n = plan.n; tab.first = genv.first; tab.row_start = genv.row_start; tab.nodes = d_nodes.p;
+    tab.H = H; tab.dadd = dadd; tab.L = L; tab.z = z; tab.zs = zs.p; tab.dinv = dinv; tab.x = x;
+    tab.U = U.p; tab.u = u.p; tab.Z = Z.p; tab.E = E.p; tab.T = T.p; tab.W = W.p; tab.w = w.p;
+    std::vector<nd::LevelJobs> jobs;
+    nd::DenseViewArrays dv{d_zeros.p, d_tri.p, d_last_by_w.p};
+    nd::build_level_jobs(plan, tab, d_first_rel.p, d_rs_adj.p, d_last_rel.p, genv.nblocks, dv, status + 1, jobs);
+    std::vector<int> ids; std::vector<FactorJob> fj; std::vector<nd::SpikeJob> sj; std::vector<nd::SyrkSeg> yj; std::vector<BacksolveJob> bj;
+    struct Off { size_t ids, f, s, y, b; };
+    std::vector<Off> off;
+    for (auto& J : jobs) {
+      off.push_back(Off{ids.size(), fj.size(), sj.size(), yj.size(), bj.size()});
+      ids.insert(ids.end(), J.ids.begin(), J.ids.end());
+      fj.insert(fj.end(), J.factor.begin(), J.factor.end());
+      sj.insert(sj.end(), J.spike.begin(), J.spike.end());
+      yj.insert(yj.end(), J.syrk.begin(), J.syrk.end());
+      bj.insert(bj.end(), J.back.begin(), J.back.end());
+    }
+    LVBA_TRY(d_ids.upload(ids, s)); LVBA_TRY(d_factor.upload(fj, s)); LVBA_TRY(d_back.upload(bj, s));
+    if (!sj.empty()) { LVBA_TRY(d_spike.upload(sj, s)); LVBA_TRY(d_syrk.upload(yj, s)); }
+    LVBA_CUDA(cudaStreamSynchronize(s));                     // local vectors
+    lv.clear();
+    for (size_t l = 0; l < jobs.size(); ++l) {
+      const auto& J = jobs[l];
+      lv.push_back(nd::LevelDev{d_ids.p + off[l].ids, (int)J.ids.size(), d_factor.p + off[l].f, (int)J.factor.size(),
+                                d_spike.p + off[l].s, (int)J.spike.size(), d_syrk.p + off[l].y, (int)J.syrk.size(),
+                                d_back.p + off[l].b, (int)J.back.size(), J.asm_stride, J.corr_stride, J.max_ks, J.max_rows, J.max_col});
+    }
+    key_H = H; key_dadd = dadd; key_x = x; key_z = z;
+    return LVBA_OK;
+  }
+};
+
+// CUDA executor of nd::run
+struct NdCudaExec {
+  cudaStream_t s;
+  std::function<int(int, int, const FactorJob*)> factor_fn;        // (max_col, n_jobs, jobs)
+  std::function<void(int, const BacksolveJob*)> back_fn;           // (n_jobs, jobs)
+  int64_t launches = 0;
+  int rc = LVBA_OK;
+  template <class F> void pass(long long n, const F& f) {
+    if (n <= 0) return;
+    const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+    nd_pass_kernel<<<grid, 256, 0, s>>>(n, f);
+    ++launches;
+  }
+  void copy(double* dst, const double* src, long long n) { cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s); }
+  void zero(double* p, long long n) { if (n > 0) cudaMemsetAsync(p, 0, (size_t)n * sizeof(double), s); }
+  void factor(const FactorJob* jobs, int n, int max_col) {
+    if (n <= 0) return;
+    const int r = factor_fn(max_col, n, jobs);
+    if (r != LVBA_OK) rc = r;
+  }
+  void spike(const nd::SpikeJob* jobs, int n, int max_ks, int) {
+    if (n <= 0 || max_ks <= 0) return;
+    nd_spike_kernel<<<dim3((max_ks + kSpikeCols - 1) / kSpikeCols, n), kSpikeThreads, kSpikeSmem, s>>>(jobs);
+    ++launches;
+  }
+  void syrk(const nd::SyrkSeg* segs, int n, int max_ks, int max_rows) {
+    if (n <= 0 || max_ks <= 0) return;
+    const int nt1 = (max_ks + kSyrkTile - 1) / kSyrkTile, nt = nt1 * (nt1 + 1) / 2;
+    nd_syrk_kernel<<<dim3(nt, (max_rows + kSyrkRows - 1) / kSyrkRows, n), 256, 0, s>>>(segs);
+    ++launches;
+  }
+  void backsolve(const BacksolveJob* jobs, int n) {
+    if (n <= 0) return;
+    back_fn(n, jobs);
+    ++launches;
+  }
+};
+
+}  // namespace lvba

@@ -299,6 +299,10 @@ inline std::vector<unsigned> build_pair_map32(int P, bool tile2, int n_threads) 
   return map;
 }
 
+}  // namespace lvba
+#include "nd_solver.cuh"
+namespace lvba {
+
 // ---------------------------------------------------------------- LDL^T solve driver
 struct EnvSolver {
   DevBuf<double> L, dinv, z;
@@ -326,6 +330,10 @@ struct EnvSolver {
   DevBuf<double> colT;          // [max_col * 36] unscaled copy of the current pivot column
   // ---- twisted (two-ended) factorisation: top half in natural order on one SM, bottom half reversed on another,
   //      joined at a separator of `tw_bs` rows (see envelope.cuh, FactorJob)
+  // ---- substructured solve (nd_solver.cuh): p chunk interiors + a tree of separators, one CTA per node; chosen for
+  //      systems long enough that  interior + depth x separator  pivot columns beat the two halves of the twisted solve
+  NdDevice nd;
+  bool nd_on = false;
   bool tw = false;
   int tw_m = 0, tw_send = 0, tw_bs = 0, tw_nb = 0, tw_nbstop = 0;
   Envelope env_bot, env_sep;
@@ -334,12 +342,13 @@ struct EnvSolver {
   static int pid(int mc) { return mc <= 7 ? 0 : mc <= 11 ? 1 : mc <= 15 ? 2 : mc <= 20 ? 3 : mc <= 23 ? 4 : 5; }
   static int pval(int id) { return id == 0 ? 8 : id == 1 ? 12 : id == 2 ? 16 : id == 3 ? 21 : id == 4 ? 24 : 31; }
 
-  int prepare(const Envelope& env, cudaStream_t s) {
+  // path: LVBA_SOLVE_AUTO picks by structure; the others pin one path (lvba_env_solve, tests): see include/lvba_b200.h
+  int prepare(const Envelope& env, cudaStream_t s, int path = LVBA_SOLVE_AUTO, int chunks = 0) {
     {
       const char* fg = getenv("LVBA_FORCE_GENERIC_SOLVER");      // tests: run the wide-envelope kernel on narrow problems
-      force_generic = fg && fg[0] == '1';
+      force_generic = (fg && fg[0] == '1') || path == LVBA_SOLVE_SHARED_WINDOW;
       const char* fw = getenv("LVBA_FORCE_WIDE_SOLVER");         // tests: run the any-width path on narrow problems
-      wide = env.max_col > kEnvMaxCol || (fw && fw[0] == '1');
+      wide = env.max_col > kEnvMaxCol || (fw && fw[0] == '1') || path == LVBA_SOLVE_ANY_WIDTH;
     }
     if (wide) LVBA_TRY(colT.alloc((size_t)std::max(env.max_col, 1) * 36));
     LVBA_TRY(L.alloc((size_t)env.nblocks * 36));
@@ -365,7 +374,8 @@ struct EnvSolver {
     tw = false;
     const char* nt = getenv("LVBA_NO_TWIST");
     const bool reg_ok = env.max_col <= 30 && env.n >= 3 && !force_generic && !wide;
-    if (reg_ok && env.n >= 256 && !(nt && nt[0] == '1')) {
+    const bool want_tw = path == LVBA_SOLVE_AUTO ? (env.n >= 256 && !(nt && nt[0] == '1')) : path == LVBA_SOLVE_TWISTED;
+    if (reg_ok && want_tw && env.n >= 8) {
       const int n = env.n;
       const int m = n / 2;
       const int send = env.last[m - 1] + 1;            // rows >= send do not couple to rows < m
@@ -388,6 +398,16 @@ struct EnvSolver {
           LVBA_TRY(wtop.zero(s)); LVBA_TRY(wbot.zero(s));
           tw = true;
         }
+      }
+    }
+    // ---- substructured split
+    nd_on = false;
+    if (reg_ok && (path == LVBA_SOLVE_AUTO || path == LVBA_SOLVE_CHUNKED)) {
+      const int pw = (path == LVBA_SOLVE_CHUNKED && chunks >= 2) ? chunks : NdDevice::default_chunks(env.n, std::max(env.max_col, 1));
+      if (pw >= 2) {
+        LVBA_TRY(nd.prepare(env.n, env.first, env.last, env.row_start, env.max_col, pw, s));
+        nd_on = nd.ready;
+        if (nd_on) LVBA_TRY(status.alloc((size_t)std::max<size_t>(4, nd.plan.nodes.size() + 1)));
       }
     }
     return LVBA_OK;
@@ -466,7 +486,7 @@ struct EnvSolver {
     LVBA_TRY(first_rel.upload(fr, s));
     LVBA_TRY(status.alloc((size_t)std::max(n_groups, 4)));
     LVBA_CUDA(cudaStreamSynchronize(s));
-    batch = true; tw = false; jobs_x = nullptr;
+    batch = true; tw = false; nd_on = false; jobs_x = nullptr;
     return LVBA_OK;
   }
 
@@ -502,9 +522,51 @@ struct EnvSolver {
     return LVBA_OK;
   }
 
+  // Substructured solve: nd::run (nd_passes.h) through the CUDA executor, captured into a graph at its first use
+  int solve_nd(const Envelope& env, const double* H, const double* dadd, double* x, cudaStream_t s, int64_t* launches) {
+    const EnvView v = env.view();
+    LVBA_TRY(nd.build_tables(v, H, dadd, L.p, dinv.p, z.p, x, status.p, s));
+    for (const auto& J : nd.lv) LVBA_TRY(ensure_map(pid(J.max_col), s));           // uploads + syncs: not inside a capture
+    auto record = [&](int64_t* n_launch) -> int {
+      NdCudaExec ex;
+      ex.s = s;
+      ex.factor_fn = [&](int max_col, int nj, const FactorJob* jobs) { return launch_factor(pid(max_col), nj, jobs, s, &ex.launches); };
+      ex.back_fn = [&](int nj, const BacksolveJob* jobs) { launch_backsolve(nj, jobs, s); };
+      cudaMemsetAsync(status.p, 0, status.n * sizeof(int), s);
+      nd::run(ex, nd.plan, nd.tab, nd.lv.data(), (int)nd.lv.size(), env.nblocks, nd.leaf_e, nd.leaf_fin);
+      env_status_or_kernel<<<1, 32, 0, s>>>(status.p, (int)nd.plan.nodes.size() + 1);
+      *n_launch = ex.launches + 1;
+      return ex.rc;
+    };
+    if (nd.use_graph && !nd.graph_exec) {
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+        const int rc = record(&nd.launches_per_solve);
+        cudaGraph_t g = nullptr;
+        const cudaError_t e1 = cudaStreamEndCapture(s, &g);
+        if (rc == LVBA_OK && e1 == cudaSuccess && g && cudaGraphInstantiate(&nd.graph_exec, g, 0) == cudaSuccess) nd.graph = g;
+        else {
+          if (g) cudaGraphDestroy(g);
+          nd.graph_exec = nullptr; nd.use_graph = false;
+          cudaGetLastError();
+        }
+      } else { nd.use_graph = false; cudaGetLastError(); }
+    }
+    if (nd.use_graph && nd.graph_exec) {
+      LVBA_CUDA(cudaGraphLaunch(nd.graph_exec, s));
+      *launches += nd.launches_per_solve;
+    } else {
+      int64_t nl = 0;
+      LVBA_TRY(record(&nl));
+      *launches += nl;
+    }
+    LVBA_CUDA(cudaGetLastError());
+    return LVBA_OK;
+  }
+
   // Solves (H + diag(dadd)) x = z_in where z already holds the right-hand side.  status[0] != 0 afterwards flags a
   // singular pivot (batched mode: status[g] per group).
   int solve(const Envelope& env, const double* H, const double* dadd, double* x, cudaStream_t s, int64_t* launches) {
+    if (nd_on && !batch) return solve_nd(env, H, dadd, x, s, launches);
     const EnvView v = env.view();
     LVBA_CUDA(cudaMemcpyAsync(L.p, H, (size_t)env.nblocks * 36 * sizeof(double), cudaMemcpyDeviceToDevice, s));
     LVBA_CUDA(cudaMemsetAsync(status.p, 0, status.n * sizeof(int), s));

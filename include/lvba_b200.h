@@ -377,6 +377,30 @@ int lvba_tracks_mean_reproj(int64_t n_tracks, const int64_t* obs_ptr, const int3
                             double* mean_reproj, int32_t* count, uint8_t* ok);
 
 /* ======================================================================================
+ * The block LDL^T of the pose / camera system on its own (diagnostics, solver tests and the
+ * solver line of bench.py).  Solves (A + diag(dadd)) x = rhs for a symmetric matrix of 6x6
+ * blocks stored as a block envelope: row r keeps the blocks of columns first[r]..r
+ * contiguously, row after row, each block row-major; first[] must be non-decreasing (what the
+ * library builds from the voxel / track structure); only the lower triangle of the diagonal
+ * blocks is read.  LDL^T without pivoting (A may be indefinite), as Eigen::SimplicialLDLT in
+ * BALM2::damping_iter (reference include/BALM/bavoxel.hpp:695-710) and the DENSE_SCHUR
+ * Cholesky of ceres::Solve (src/lvba_system.cpp:1573-1575).
+ *   path  LVBA_SOLVE_AUTO: what lvba_lidar_lm / lvba_visual_lm pick for this structure;
+ *         the other values pin one path and fail with LVBA_ERR_UNSUPPORTED if the structure
+ *         does not allow it.  chunks: for LVBA_SOLVE_CHUNKED (0 = library default).
+ *   reps  >= 1 solves; ms (may be NULL) = fastest of them, device time by CUDA events.
+ *   info  (may be NULL) int32[4]: path taken, chunks, tree levels, kernel launches per solve.
+ * ====================================================================================== */
+#define LVBA_SOLVE_AUTO 0
+#define LVBA_SOLVE_ONE_CTA 1        /* one register-window factorisation (columns of <= 30 blocks) */
+#define LVBA_SOLVE_TWISTED 2        /* two-ended elimination on two SMs, joined at one separator */
+#define LVBA_SOLVE_CHUNKED 3        /* substructured: chunk interiors + tree of separators, one CTA per node */
+#define LVBA_SOLVE_SHARED_WINDOW 4  /* shared-memory window (columns of <= 320 blocks) */
+#define LVBA_SOLVE_ANY_WIDTH 5      /* device-wide passes, any envelope */
+int lvba_env_solve(int32_t n, const int32_t* first, const double* blocks, const double* dadd, const double* rhs,
+                   double* x, int32_t path, int32_t chunks, int32_t reps, int32_t device, double* ms, int32_t* info);
+
+/* ======================================================================================
  * Multi-GPU (one process per GPU).  The path shards by contiguous pose-block rows
  * (SURVEY.md §8e): voxel / track -> owner of its lowest pose / camera index.  Every rank
  * passes the FULL problem to *_create; after lvba_comm_init each rank keeps only its shard

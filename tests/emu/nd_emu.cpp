@@ -34,6 +34,7 @@ struct NdHostExec {
   HostExec base;
   template <class F> void pass(long long n, const F& f) { base.for_each(n, f); }
   void zero(double* p, long long n) { std::memset(p, 0, (size_t)n * sizeof(double)); }
+  void copy(double* d, const double* s, long long n) { std::memcpy(d, s, (size_t)n * sizeof(double)); }
 
   void factor(const FactorJob* jobs, int nj, int /*max_col*/) {
     for (int q = 0; q < nj; ++q) {
