@@ -229,8 +229,10 @@ __global__ void env_reverse_gather_kernel(EnvView eo, EnvView eb, const double* 
     for (int o = threadIdx.x; o < nblk * 36; o += blockDim.x) {
       const int cb = o / 36, el = o - cb * 36, a = el / 6, b2 = el - a * 6;
       const int ic = n - 1 - (f + cb);                    // original row of the coupled pose (ic >= ir)
-      // reversed block (rp, f+cb)[a][b2] = original block (ic, ir)[b2][a]
-      Lb[base + o] = Lo[(eo.row_start[ic] + (ir - eo.first[ic])) * 36 + b2 * 6 + a];
+      // reversed block (rp, f+cb)[a][b2] = original block (ic, ir)[b2][a]; a diagonal block is read through its lower
+      // triangle only (its upper triangle is unspecified)
+      const int ra = (ic == ir && a > b2) ? a : b2, rb = (ic == ir && a > b2) ? b2 : a;
+      Lb[base + o] = Lo[(eo.row_start[ic] + (ir - eo.first[ic])) * 36 + ra * 6 + rb];
     }
     if (threadIdx.x < 6) zb[6 * (long long)rp + threadIdx.x] = zo[6 * (long long)ir + threadIdx.x];
   }

@@ -20,135 +20,375 @@ __global__ void __launch_bounds__(256) nd_pass_kernel(long long n, F f) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Spike: Z = L^-1 E for KS right-hand sides (SpikeJob, nd_passes.h).  blockIdx.x = group of kSpikeCols right-hand sides,
-// blockIdx.y = job.  Thread (x, col) owns component x of block row k for one right-hand side; row k of L (its blocks are
-// contiguous in the envelope) is staged by cp.async one row ahead, the last 32 block rows of Z live in shared memory
-// (column height <= 30).  Per row and CTA: ~30 x (3 LDS.128 + 6 LDS.64 + 6 DFMA) per thread, two block barriers.
-constexpr int kSpikeCols = 10;           // right-hand sides per CTA
-constexpr int kSpikeThreads = 64;        // 6 x 10 outputs per row (+ 4 idle)
-constexpr size_t kSpikeSmem = sizeof(double) * (2 * 31 * 36 + 32 * 6 * kSpikeCols);
+// blockIdx.y = job.
+//
+// A warp owns 8 right-hand sides for the whole job: lane = col + 8 jq; the four lanes jq = 0..3 of a column split the
+// <= 30 blocks L_kj of row k among them (j = first + jq, + 4, ...), each accumulating all six components
+// sum_j L_kj z_j of ITS blocks (36 DFMA per block: the 6x6 block is fetched once for six outputs, 18 broadcast LDS.128),
+// two xor-shuffles add the four partial sums.  The last 32 block rows of Z of the warp's columns live in shared memory
+// private to the warp (column height <= 30), so the only block-wide hand-shake per row is the one that publishes the next
+// row of L: its blocks are contiguous in the envelope and are staged by cp.async one row ahead.  Row labels
+// (first / row_start) and the entering rows of E are fetched two / one rows ahead, so no global-memory latency sits on
+// the row-to-row chain.
+constexpr int kSpikeWarps = 2;
+constexpr int kSpikeCols = 8 * kSpikeWarps;      // right-hand sides per CTA
+constexpr int kSpikeThreads = 32 * kSpikeWarps;
+constexpr int kSpikeZStride = 56;                // doubles per block row of a warp's Z window: [6][8] + 8 padding (bank spread)
+constexpr int kSpikeBufs = 3;                   // rows of L in flight (cp.async, two rows ahead)
+constexpr size_t kSpikeSmem = sizeof(double) * (kSpikeBufs * 31 * 36 + kSpikeWarps * 32 * kSpikeZStride);
 
 __global__ void __launch_bounds__(kSpikeThreads)
 nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
-  constexpr int CW = kSpikeCols;
   extern __shared__ __align__(16) double smem_spike[];
-  double (*sRow)[31 * 36] = reinterpret_cast<double (*)[31 * 36]>(smem_spike);            // [2] blocks of row k (double buffered)
-  double (*sZ)[6][CW] = reinterpret_cast<double (*)[6][CW]>(smem_spike + 2 * 31 * 36);   // [32] the last 32 rows of Z of this group
+  double* sRow = smem_spike;                                   // [kSpikeBufs][31*36] blocks of rows k, k+1, k+2
   const nd::SpikeJob J = jobs[blockIdx.y];
   const EnvView e = J.e;
-  const int c0 = blockIdx.x * CW;
+  const int c0 = blockIdx.x * kSpikeCols;
   if (c0 >= J.KS) return;
-  const int tid = threadIdx.x;
-  const int x = tid / CW, col = tid - x * CW;               // output (component x of the row, right-hand side c0+col)
-  const bool act = tid < 6 * CW && c0 + col < J.KS;
-  auto stage_row = [&](int k) {                             // blocks (k, f .. min(k, n_stop)-1) -> sRow[k & 1]
-    if (k >= e.n) return;
-    const int f = e.first[k];
-    const int jend = k < J.n_stop ? k : J.n_stop;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int col8 = lane & 7, jq = lane >> 3;
+  const int c = c0 + warp * 8 + col8;                          // this lane's right-hand side
+  const bool act = c < J.KS;
+  double* sZw = smem_spike + kSpikeBufs * 31 * 36 + warp * 32 * kSpikeZStride;
+  const int n = e.n, n_stop = J.n_stop, KS = J.KS;
+  auto stage_row = [&](int k, int f, long long rs) {           // blocks (k, f .. min(k, n_stop)-1) -> sRow[k % 3]
+    if (k >= n) return;
+    const int jend = k < n_stop ? k : n_stop;
     const int nb = jend > f ? jend - f : 0;
-    const double* src = J.L + e.row_start[k] * 36;
-    for (int o = tid; o < nb * 18; o += kSpikeThreads) cp_async16_zfill(&sRow[k & 1][2 * o], src + 2 * o, true);
+    const double* src = J.L + rs * 36;
+    double* dst = sRow + (k % kSpikeBufs) * (31 * 36);
+    for (int o = tid; o < nb * 18; o += kSpikeThreads) cp_async16_zfill(dst + 2 * o, src + 2 * o, true);
   };
-  stage_row(0);
+  // labels: row k (f0), rows k+1 .. k+3 (f1..f3, rs2, rs3): fetched four rows ahead of their use in the chain
+  int f0 = e.first[0];
+  int f1 = n > 1 ? e.first[1] : 0; long long rs1 = n > 1 ? e.row_start[1] : 0;
+  int f2 = n > 2 ? e.first[2] : 0; long long rs2 = n > 2 ? e.row_start[2] : 0;
+  int f3 = n > 3 ? e.first[3] : 0; long long rs3 = n > 3 ? e.row_start[3] : 0;
+  double en[6];                                                // E of the next row (lanes jq == 0)
+#pragma unroll
+  for (int x = 0; x < 6; ++x) en[x] = (jq == 0 && act && 0 < J.nE) ? J.E[((long long)x) * KS + c] : 0.0;
+  stage_row(0, f0, e.row_start[0]);
   asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int k = 0; k < e.n; ++k) {
-    stage_row(k + 1);
+  stage_row(1, f1, rs1);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int k = 0; k < n; ++k) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");       // everything but the newest group (row k+1): row k has landed
+    __syncthreads();                                           // row k of L staged by everybody; everybody is done with row k-1
+    stage_row(k + 2, f2, rs2);                                 // into the buffer row k-1 used
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncthreads();                                        // row k staged; Z rows < k complete
-    const int f = e.first[k];
-    const int jend = k < J.n_stop ? k : J.n_stop;
-    if (act) {
-      double acc = (k < J.nE) ? J.E[((long long)k * 6 + x) * J.KS + c0 + col] : 0.0;
-      double acc2 = 0.0;
-      for (int j = f; j < jend; ++j) {
-        const double* b = &sRow[k & 1][(j - f) * 36 + x * 6];
-        const double (*zj)[CW] = sZ[j & 31];
-        acc -= b[0] * zj[0][col] + b[2] * zj[2][col] + b[4] * zj[4][col];
-        acc2 += b[1] * zj[1][col] + b[3] * zj[3][col] + b[5] * zj[5][col];
-      }
-      acc -= acc2;
-      J.Z[((long long)k * 6 + x) * J.KS + c0 + col] = acc;
-      sZ[k & 31][x][col] = acc;                             // row k-32 is no longer needed (column height <= 30)
+    const int f4 = (k + 4 < n) ? e.first[k + 4] : 0;
+    const long long rs4 = (k + 4 < n) ? e.row_start[k + 4] : 0;
+    double ecur[6];
+#pragma unroll
+    for (int x = 0; x < 6; ++x) ecur[x] = en[x];
+    if (jq == 0 && act && k + 1 < J.nE) {
+#pragma unroll
+      for (int x = 0; x < 6; ++x) en[x] = J.E[((long long)(k + 1) * 6 + x) * KS + c];
+    } else {
+#pragma unroll
+      for (int x = 0; x < 6; ++x) en[x] = 0.0;
     }
-    __syncthreads();
+    const int jend = k < n_stop ? k : n_stop;
+    const double* rowb = sRow + (k % kSpikeBufs) * (31 * 36);
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = f0 + jq; j < jend; j += 4) {
+      const double2* b2 = reinterpret_cast<const double2*>(rowb + (j - f0) * 36);
+      const double* zj = sZw + (j & 31) * kSpikeZStride + col8;
+      const double z0 = zj[0], z1 = zj[8], z2 = zj[16], z3 = zj[24], z4 = zj[32], z5 = zj[40];
+#pragma unroll
+      for (int x = 0; x < 6; ++x) {
+        const double2 p0 = b2[3 * x], p1 = b2[3 * x + 1], p2 = b2[3 * x + 2];
+        acc[x] += p0.x * z0; acc[x] += p0.y * z1; acc[x] += p1.x * z2; acc[x] += p1.y * z3; acc[x] += p2.x * z4; acc[x] += p2.y * z5;
+      }
+    }
+#pragma unroll
+    for (int x = 0; x < 6; ++x) {
+      acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 8);
+      acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 16);
+    }
+    __syncwarp();                                              // every lane has read the window entries it needs of row k-32
+    if (jq == 0) {
+#pragma unroll
+      for (int x = 0; x < 6; ++x) {
+        const double v = ecur[x] - acc[x];
+        sZw[(k & 31) * kSpikeZStride + x * 8 + col8] = v;      // row k-32 is no longer needed (column height <= 30)
+        if (act) J.Z[((long long)k * 6 + x) * KS + c] = v;
+      }
+    }
+    __syncwarp();
+    f0 = f1; f1 = f2; f2 = f3; rs2 = rs3; f3 = f4; rs3 = rs4;
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// SYRK: U -= sum_k Z_k^T K_k Z_k, u -= sum_k Z_k^T K_k w_k over the pivot rows of a node (SyrkSeg, nd_passes.h).
-// grid = (tiles of 30 x 30 scalars of the lower triangle, chunks of kSyrkRows rows, segments); partial sums of the row
-// chunks meet in U by RED.ADD.F64.
-constexpr int kSyrkTile = 30;            // scalar columns per tile side (5 blocks)
-constexpr int kSyrkRows = 32;            // rows of Z per CTA
+// SYRK: U -= sum_k Z_k^T K_k Z_k, u -= sum_k Z_k^T K_k w_k over the pivot rows of a node (SyrkSeg, nd_passes.h): the
+// product (KS x R)(R x KS), R = 6 rows, of Z^T with Y = K Z.  grid = (tiles of 64 x 64 scalars of the lower triangle,
+// groups of kSyrkSplit block rows, segments); a CTA walks its rows in chunks of 4 block rows: Z for the tile's row and
+// column side goes to shared memory (coalesced), Y = K Z is formed there, each thread accumulates a 4 x 4 register tile.
+// Partial sums of the row groups meet in U by RED.ADD.F64.  FP64-FMA bound.
+constexpr int kSyrkTile = 64;            // scalar columns per tile side
+constexpr int kSyrkChunk = 4;            // block rows per shared-memory chunk (24 scalar rows; three tiles of it stay below 48 kB)
+constexpr int kSyrkSplit = 30;           // block rows per CTA
+constexpr int kSyrkLd = kSyrkTile + 4;   // leading dimension of the shared tiles
 
 __global__ void __launch_bounds__(256)
 nd_syrk_kernel(const nd::SyrkSeg* __restrict__ segs) {
-  constexpr int TW = kSyrkTile;
-  __shared__ double sKZ[6][TW];          // (K_k Z_k)[p][a] for the tile's row side
-  __shared__ double sZb[6][TW];          // Z_k[p][b] for the tile's column side
-  __shared__ double sKw[6];
+  constexpr int TS = kSyrkTile, RC = kSyrkChunk * 6, LD = kSyrkLd;
+  __shared__ __align__(16) double sA[RC][LD];       // Z[r][tile row side]
+  __shared__ __align__(16) double sB[RC][LD];       // Z[r][tile column side]
+  __shared__ __align__(16) double sY[RC][LD];       // (K Z)[r][tile column side]
+  __shared__ double sK[kSyrkChunk][36];
+  __shared__ double sKw[RC];
   const nd::SyrkSeg G = segs[blockIdx.z];
-  int ti = 0, tj = 0;                    // tile (ti, tj), tj <= ti, from the linear index
+  int ti = 0, tj = 0;                                // tile (ti, tj), tj <= ti, from the linear index
   { int t = blockIdx.x; while ((ti + 1) * (ti + 2) / 2 <= t) ++ti; tj = t - ti * (ti + 1) / 2; }
-  if (ti * TW >= G.KS) return;
-  const int k0 = blockIdx.y * kSyrkRows;
+  if (ti * TS >= G.KS) return;
+  const int k0 = blockIdx.y * kSyrkSplit;
   if (k0 >= G.rows) return;
-  const int k1 = min(G.rows, k0 + kSyrkRows);
-  const int tid = threadIdx.x;
-  double acc[4] = {0, 0, 0, 0};          // outputs (a, b) of the TW x TW tile: 900 over 256 threads
+  const int k1 = min(G.rows, k0 + kSyrkSplit);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int KS = G.KS;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
   double racc = 0.0;
-  for (int k = k0; k < k1; ++k) {
-    __syncthreads();
-    if (tid < 6 * TW) {
-      const int p = tid / TW, a = tid - p * TW;
-      const double* Kk = G.K + (long long)k * 36 + p * 6;
-      const double* Zk = G.Z + (long long)k * 6 * G.KS;
-      double s = 0.0;
-      const bool ina = ti * TW + a < G.KS, inb = tj * TW + a < G.KS;
-      if (ina) {
-#pragma unroll
-        for (int q = 0; q < 6; ++q) s += Kk[q] * Zk[(long long)q * G.KS + ti * TW + a];
+  for (int kc = k0; kc < k1; kc += kSyrkChunk) {
+    const int nbk = min(kSyrkChunk, k1 - kc), nr = nbk * 6;
+    __syncthreads();                                 // previous chunk consumed
+    for (int o = tid; o < RC * TS; o += 256) {
+      const int r = o / TS, a = o - r * TS;
+      double va = 0.0, vb = 0.0;
+      if (r < nr) {
+        const double* zr = G.Z + ((long long)kc * 6 + r) * KS;
+        if (ti * TS + a < KS) va = zr[ti * TS + a];
+        if (tj * TS + a < KS) vb = zr[tj * TS + a];
       }
-      sKZ[p][a] = s;
-      sZb[p][a] = inb ? Zk[(long long)p * G.KS + tj * TW + a] : 0.0;
-    } else if (tid < 6 * TW + 6) {
-      const int p = tid - 6 * TW;
-      const double* Kk = G.K + (long long)k * 36 + p * 6;
-      double s = 0.0;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) s += Kk[q] * G.w[(long long)k * 6 + q];
-      sKw[p] = s;
+      sA[r][a] = va; sB[r][a] = vb;
+    }
+    for (int o = tid; o < kSyrkChunk * 36; o += 256) {
+      const int bk = o / 36;
+      sK[bk][o - bk * 36] = (bk < nbk) ? G.K[(long long)(kc + bk) * 36 + (o - bk * 36)] : 0.0;
     }
     __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int o = tid + 256 * u;
-      if (o < TW * TW) {
-        const int a = o / TW, b = o - a * TW;
-        double s = 0.0;
-#pragma unroll
-        for (int p = 0; p < 6; ++p) s += sKZ[p][a] * sZb[p][b];
-        acc[u] += s;
-      }
-    }
-    if (tj == 0 && tid < TW && ti * TW + tid < G.KS) {           // u rows of tile row ti: sum_p Z_k[p][a] (K w)[p]
+    for (int o = tid; o < RC * TS; o += 256) {       // Y = K Z on the column side
+      const int r = o / TS, b = o - r * TS, bk = r / 6, x = r - bk * 6;
+      const double* Kx = &sK[bk][x * 6];
       double s = 0.0;
 #pragma unroll
-      for (int p = 0; p < 6; ++p) s += G.Z[((long long)k * 6 + p) * G.KS + ti * TW + tid] * sKw[p];
+      for (int q = 0; q < 6; ++q) s += Kx[q] * sB[bk * 6 + q][b];
+      sY[r][b] = s;
+    }
+    if (tj == 0 && tid < RC) {                       // (K w)[r]
+      const int bk = tid / 6, x = tid - bk * 6;
+      double s = 0.0;
+      if (bk < nbk) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) s += sK[bk][x * 6 + q] * G.w[(long long)(kc + bk) * 6 + q];
+      }
+      sKw[tid] = s;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < RC; ++r) {
+      const double2 a01 = *reinterpret_cast<const double2*>(&sA[r][4 * ty]), a23 = *reinterpret_cast<const double2*>(&sA[r][4 * ty + 2]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&sY[r][4 * tx]), b23 = *reinterpret_cast<const double2*>(&sY[r][4 * tx + 2]);
+      const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+    }
+    if (tj == 0 && tid < TS) {
+      double s = 0.0;
+      for (int r = 0; r < RC; ++r) s += sA[r][tid] * sKw[r];
       racc += s;
     }
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int o = tid + 256 * u;
-    if (o < TW * TW) {
-      const int a = o / TW, b = o - a * TW;
-      const int ga = ti * TW + a, gb = tj * TW + b;             // scalar row / column inside the boundary
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ga = ti * TS + 4 * ty + i, gb = tj * TS + 4 * tx + j;       // scalar row / column inside the boundary
       const int bi = ga / 6, bj = gb / 6;
-      if (bj <= bi && ga < G.KS && gb < G.KS) atomicAdd(&G.U[((long long)bi * (bi + 1) / 2 + bj) * 36 + (ga - 6 * bi) * 6 + (gb - 6 * bj)], -acc[u]);
+      if (bj <= bi && ga < KS && gb < KS) atomicAdd(&G.U[((long long)bi * (bi + 1) / 2 + bj) * 36 + (ga - 6 * bi) * 6 + (gb - 6 * bj)], -acc[i][j]);
     }
+  if (tj == 0 && tid < TS && ti * TS + tid < KS) atomicAdd(&G.u[ti * TS + tid], -racc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Downwards: x_K = D^-1 (w_K - Z x_boundary) for the pivot rows of the nodes of one level (CorrectApplyF of nd_passes.h
+// with a CTA per block row: warp q forms the dot product of row (k, q) of Z with the boundary solution, coalesced).
+__global__ void __launch_bounds__(192)
+nd_correct_apply_kernel(nd::Tables t, const int* __restrict__ ids, int stride) {
+  __shared__ double sc[6];
+  const nd::NodeDev v = t.nodes[ids[blockIdx.x / stride]];
+  const int k = blockIdx.x % stride;
+  if (k >= v.npiv) return;
+  const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
+  const double* wv = (v.kind == 0 ? t.z : t.zs) + 6 * (long long)(v.r0 + k);
+  const double* zr = t.Z + v.offZ + ((long long)k * 6 + q) * v.ks;
+  const int na = 6 * v.wa;
+  const double* xa = t.x + 6 * (long long)v.sa;
+  const double* xc = t.x + 6 * (long long)v.sc;
+  double s = 0.0;
+  for (int col = lane; col < v.ks; col += 32) s += zr[col] * (col < na ? xa[col] : xc[col - na]);
+  s = warp_sum(s);
+  if (lane == 0) sc[q] = wv[q] - s;
+  __syncthreads();
+  if (tid < 6) {
+    const double* K = t.dinv + (long long)(v.r0 + k) * 36 + tid * 6;
+    double o = 0.0;
+#pragma unroll
+    for (int qq = 0; qq < 6; ++qq) o += K[qq] * sc[qq];
+    t.x[6 * (long long)(v.r0 + k) + tid] = o;
   }
-  if (tj == 0 && tid < TW && ti * TW + tid < G.KS) atomicAdd(&G.u[ti * TW + tid], -racc);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dense block LDL^T of a separator (<= 30 x 30 blocks, every block inside the envelope): FactorJob semantics for a complete
+// factorisation (n_stop == n, no dump) of a matrix in the dense lower layout (block (i,j) at (i(i+1)/2 + j)*36).
+//
+// The register-window kernel of factor_la.cuh slides a 31-row window along a band and pays ~4 900 cycles per pivot column
+// whatever the column holds; a separator is dense and SHRINKS (the trailing matrix of pivot k has (29-k)(30-k)/2 blocks),
+// and its 30 pivots sit on the critical path of every tree level.  Here every block of the lower triangle lives in the
+// registers of one thread for the whole factorisation (thread <-> (i, j)); per pivot k:
+//   phase B  the owners of column k (blocks (i,k), i >= k) each invert D_k themselves (the pivot block was published at the
+//            end of the previous update; two reciprocals on the dependent chain, factor_la.cuh) and scale their block:
+//            T_ik = block, L_ik = T_ik D_k^-1, both to shared memory (transposed layout not needed: operands are read
+//            row-wise), L_ik to global memory, z_i -= L_ik z_k;
+//   phase C  every live block (i, j), i >= j > k:  G -= L_ik T_jk^T  (216 DFMA, operands by LDS.128; the thread map
+//            groups 8 x 4 patches of blocks into a warp so that a warp touches <= 8 + 4 distinct operand blocks).
+// Two block barriers per pivot.  One CTA per separator; grid = separators of the tree level.
+constexpr int kDenseMax = 30;
+constexpr int kDenseThreads = 480;           // 465 blocks of the 30 x 30 lower triangle
+constexpr int kDenseS = 38;                  // doubles per operand block in shared memory (bank spread, 16 B aligned)
+
+__global__ void __launch_bounds__(kDenseThreads, 1)
+nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short* __restrict__ tmap) {
+  __shared__ __align__(16) double sL[kDenseMax * kDenseS];
+  __shared__ __align__(16) double sT[kDenseMax * kDenseS];
+  __shared__ __align__(16) double sD[36];
+  __shared__ double sZ[kDenseMax * 6];
+  const FactorJob J = jobs[blockIdx.x];
+  const int n = J.e.n;
+  const int tid = threadIdx.x;
+  const unsigned short tm = tmap[tid];
+  const int i = tm & 0xff, j = tm >> 8;                       // block (i, j), j <= i ; 0xffff: idle thread
+  const bool live = tm != 0xffff && i < n;
+  double G[36];
+  if (live) {
+    const double2* src = reinterpret_cast<const double2*>(J.L + ((long long)i * (i + 1) / 2 + j) * 36);
+#pragma unroll
+    for (int q = 0; q < 18; ++q) { const double2 v = src[q]; G[2 * q] = v.x; G[2 * q + 1] = v.y; }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 36; ++q) G[q] = 0.0;
+  }
+  for (int o = tid; o < n * 6; o += kDenseThreads) sZ[o] = J.z[o];
+  if (live && i == 0 && j == 0) {
+#pragma unroll
+    for (int q = 0; q < 36; ++q) sD[q] = G[q];
+  }
+  __syncthreads();
+  int bad = 0;
+  for (int k = 0; k < n; ++k) {
+    // ---------------- phase B: column k
+    if (live && j == k) {
+      // this block is finished after the pivot: park it in shared memory (its T_ik slot) and free its registers for the inverse
+      double2* t2 = reinterpret_cast<double2*>(sT + i * kDenseS);
+      if (i != k) {
+#pragma unroll
+        for (int q = 0; q < 18; ++q) t2[q] = make_double2(G[2 * q], G[2 * q + 1]);
+      }
+#pragma unroll
+      for (int q = 0; q < 36; ++q) G[q] = 0.0;
+      double xl[21], K[21];
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) xl[LVBA_T(a, b)] = sD[a * 6 + b];
+      sym6_block_inverse(xl, K);
+      auto kk = [&](int r, int c) -> double { return r >= c ? K[LVBA_T(r, c)] : K[LVBA_T(c, r)]; };
+      if (i == k) {
+        if (!isfinite((K[LVBA_T(0, 0)] + K[LVBA_T(5, 5)]) + (K[LVBA_T(3, 0)] + K[LVBA_T(2, 1)]))) bad = 1;
+        double* dk = J.dinv + (long long)k * 36;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c = 0; c < 6; ++c) dk[r * 6 + c] = kk(r, c);
+      } else {
+        double2* l2 = reinterpret_cast<double2*>(sL + i * kDenseS);
+        double2* g2 = reinterpret_cast<double2*>(J.L + ((long long)i * (i + 1) / 2 + k) * 36);
+        double zk[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) zk[q] = sZ[k * 6 + q];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {                          // row r of L_ik = T_ik D_k^-1, straight to its destinations
+          const double2 g0 = t2[3 * r], g1 = t2[3 * r + 1], g2v = t2[3 * r + 2];
+          const double gr[6] = {g0.x, g0.y, g1.x, g1.y, g2v.x, g2v.y};
+          double lr[6];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) s += gr[q] * kk(q, c);
+            lr[c] = s;
+          }
+#pragma unroll
+          for (int h = 0; h < 3; ++h) {
+            const double2 lv = make_double2(lr[2 * h], lr[2 * h + 1]);
+            l2[3 * r + h] = lv; g2[3 * r + h] = lv;
+          }
+          double zs = 0.0;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) zs += lr[q] * zk[q];
+          sZ[i * 6 + r] -= zs;
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------- phase C: trailing update
+    if (live && j > k) {
+      const double2* l2 = reinterpret_cast<const double2*>(sL + i * kDenseS);
+      const double2* t2 = reinterpret_cast<const double2*>(sT + j * kDenseS);
+#pragma unroll
+      for (int y = 0; y < 6; ++y) {
+        const double2 t0 = t2[3 * y], t1 = t2[3 * y + 1], t2v = t2[3 * y + 2];
+#pragma unroll
+        for (int x = 0; x < 6; ++x) {
+          const double2 a0 = l2[3 * x], a1 = l2[3 * x + 1], a2 = l2[3 * x + 2];
+          double s = G[x * 6 + y];
+          s -= a0.x * t0.x; s -= a0.y * t0.y; s -= a1.x * t1.x; s -= a1.y * t1.y; s -= a2.x * t2v.x; s -= a2.y * t2v.y;
+          G[x * 6 + y] = s;
+        }
+      }
+      if (i == k + 1 && j == k + 1) {
+#pragma unroll
+        for (int q = 0; q < 36; ++q) sD[q] = G[q];
+      }
+    }
+    __syncthreads();
+  }
+  for (int o = tid; o < n * 6; o += kDenseThreads) J.z[o] = sZ[o];
+  if (bad) J.status[0] = 1;
+}
+
+// thread -> block map of nd_dense_factor_kernel: blocks of the 30 x 30 lower triangle grouped by 8 x 4 patches
+inline std::vector<unsigned short> dense_thread_map() {
+  struct B { int i, j; };
+  std::vector<B> v;
+  for (int i = 0; i < kDenseMax; ++i) for (int j = 0; j <= i; ++j) v.push_back(B{i, j});
+  std::stable_sort(v.begin(), v.end(), [](const B& a, const B& b) {
+    const int ka[4] = {a.i / 8, a.j / 4, a.i, a.j}, kb[4] = {b.i / 8, b.j / 4, b.i, b.j};
+    for (int q = 0; q < 4; ++q) if (ka[q] != kb[q]) return ka[q] < kb[q];
+    return false;
+  });
+  std::vector<unsigned short> m((size_t)kDenseThreads, (unsigned short)0xffff);
+  for (size_t t = 0; t < v.size(); ++t) m[t] = (unsigned short)(v[t].i | (v[t].j << 8));
+  return m;
 }
 
 }  // namespace lvba

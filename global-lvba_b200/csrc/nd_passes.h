@@ -335,9 +335,11 @@ struct LevelDev {
 //   zero(ptr, count)                               fill doubles with 0
 //   copy(dst, src, count)                          copy doubles
 //   factor(jobs, n, max_col)                       block LDL^T instances (FactorJob semantics, env_types.h)
+//   factor_dense(jobs, n, max_col)                 the same for complete factorisations of dense lower matrices (separators)
 //   spike(jobs, n, max_ks, max_rows)               SpikeJob semantics
 //   syrk(segs, n, max_ks, max_rows)                SyrkSeg semantics
 //   backsolve(jobs, n)                             BacksolveJob semantics
+//   correct_apply(tables, ids, n_ids, stride)      CorrectApplyF over n_ids x stride rows
 template <class Exec>
 inline void run(Exec& ex, const Plan& P, const Tables& t, const LevelDev* lv, int n_levels, long long nblocks,
                 long long leaf_e, long long leaf_fin) {
@@ -358,7 +360,7 @@ inline void run(Exec& ex, const Plan& P, const Tables& t, const LevelDev* lv, in
   for (int l = 1; l < n_levels; ++l) {
     const LevelDev& J = lv[l];
     ex.pass((long long)J.n_ids * J.asm_stride, SepAssembleF{t, J.ids, J.asm_stride});
-    ex.factor(J.factor, J.n_factor, J.max_col);
+    ex.factor_dense(J.factor, J.n_factor, J.max_col);
     if (J.n_spike) {
       ex.spike(J.spike, J.n_spike, J.max_ks, J.max_rows);
       ex.syrk(J.syrk, J.n_syrk, J.max_ks, J.max_rows);
@@ -367,7 +369,7 @@ inline void run(Exec& ex, const Plan& P, const Tables& t, const LevelDev* lv, in
   // ---- downwards
   for (int l = n_levels - 1; l >= 0; --l) {
     const LevelDev& J = lv[l];
-    ex.pass((long long)J.n_ids * J.corr_stride, CorrectApplyF{t, J.ids, J.corr_stride});
+    ex.correct_apply(t, J.ids, J.n_ids, J.corr_stride);
     ex.backsolve(J.back, J.n_back);
   }
 }

@@ -21,6 +21,8 @@ struct NdDevice {
   DevBuf<int> d_first_rel, d_last_rel, d_zeros, d_last_by_w, d_ids;
   DevBuf<long long> d_rs_adj, d_tri;
   DevBuf<nd::NodeDev> d_nodes;
+  DevBuf<unsigned short> d_dense_map;      // thread -> block of nd_dense_factor_kernel
+  bool dense_sep = true;                   // separators by nd_dense_factor_kernel (LVBA_ND_DENSE=0: register-window kernel)
   // numeric pools
   DevBuf<double> zs, U, u, Z, E, T, W, w;
   // job tables (rebuilt when the caller's pointers change)
@@ -87,6 +89,12 @@ struct NdDevice {
     std::vector<nd::NodeDev> nodes;
     for (const nd::Node& v : plan.nodes) nodes.push_back(nd::to_dev(v));
     LVBA_TRY(d_nodes.upload(nodes, s, &dummy));
+    const std::vector<unsigned short> dmap = dense_thread_map();
+    LVBA_TRY(d_dense_map.upload(dmap, s, &dummy));
+    {
+      const char* g = getenv("LVBA_ND_DENSE");
+      dense_sep = !(g && g[0] == '0');
+    }
     LVBA_TRY(zs.alloc((size_t)n * 6));
     LVBA_TRY(U.alloc((size_t)std::max<long long>(plan.sizeU, 1))); LVBA_TRY(u.alloc((size_t)std::max<long long>(plan.sizeu, 1)));
     LVBA_TRY(Z.alloc((size_t)std::max<long long>(plan.sizeZ, 1))); LVBA_TRY(E.alloc((size_t)std::max<long long>(plan.sizeE, 1)));
@@ -143,6 +151,7 @@ struct NdCudaExec {
   cudaStream_t s;
   std::function<int(int, int, const FactorJob*)> factor_fn;        // (max_col, n_jobs, jobs)
   std::function<void(int, const BacksolveJob*)> back_fn;           // (n_jobs, jobs)
+  const unsigned short* dense_map = nullptr;                       // non-null: separators by nd_dense_factor_kernel
   int64_t launches = 0;
   int rc = LVBA_OK;
   template <class F> void pass(long long n, const F& f) {
@@ -158,6 +167,12 @@ struct NdCudaExec {
     const int r = factor_fn(max_col, n, jobs);
     if (r != LVBA_OK) rc = r;
   }
+  void factor_dense(const FactorJob* jobs, int n, int max_col) {
+    if (n <= 0) return;
+    if (!dense_map) { factor(jobs, n, max_col); return; }
+    nd_dense_factor_kernel<<<n, kDenseThreads, 0, s>>>(jobs, dense_map);
+    ++launches;
+  }
   void spike(const nd::SpikeJob* jobs, int n, int max_ks, int) {
     if (n <= 0 || max_ks <= 0) return;
     nd_spike_kernel<<<dim3((max_ks + kSpikeCols - 1) / kSpikeCols, n), kSpikeThreads, kSpikeSmem, s>>>(jobs);
@@ -166,7 +181,12 @@ struct NdCudaExec {
   void syrk(const nd::SyrkSeg* segs, int n, int max_ks, int max_rows) {
     if (n <= 0 || max_ks <= 0) return;
     const int nt1 = (max_ks + kSyrkTile - 1) / kSyrkTile, nt = nt1 * (nt1 + 1) / 2;
-    nd_syrk_kernel<<<dim3(nt, (max_rows + kSyrkRows - 1) / kSyrkRows, n), 256, 0, s>>>(segs);
+    nd_syrk_kernel<<<dim3(nt, (max_rows + kSyrkSplit - 1) / kSyrkSplit, n), 256, 0, s>>>(segs);
+    ++launches;
+  }
+  void correct_apply(const nd::Tables& t, const int* ids, int n_ids, int stride) {
+    if (n_ids <= 0 || stride <= 0) return;
+    nd_correct_apply_kernel<<<n_ids * stride, 192, 0, s>>>(t, ids, stride);
     ++launches;
   }
   void backsolve(const BacksolveJob* jobs, int n) {

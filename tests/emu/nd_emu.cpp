@@ -34,6 +34,7 @@ struct NdHostExec {
   HostExec base;
   template <class F> void pass(long long n, const F& f) { base.for_each(n, f); }
   void zero(double* p, long long n) { std::memset(p, 0, (size_t)n * sizeof(double)); }
+  void correct_apply(const nd::Tables& t, const int* ids, int n_ids, int stride) { base.for_each((long long)n_ids * stride, nd::CorrectApplyF{t, ids, stride}); }
   void copy(double* d, const double* s, long long n) { std::memcpy(d, s, (size_t)n * sizeof(double)); }
 
   void factor(const FactorJob* jobs, int nj, int /*max_col*/) {
@@ -104,6 +105,8 @@ struct NdHostExec {
       }
     }
   }
+
+  void factor_dense(const FactorJob* jobs, int nj, int mc) { factor(jobs, nj, mc); }
 
   void spike(const nd::SpikeJob* jobs, int nj, int, int) {
     for (int q = 0; q < nj; ++q) {
