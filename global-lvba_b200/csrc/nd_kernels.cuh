@@ -22,42 +22,47 @@ __global__ void __launch_bounds__(256) nd_pass_kernel(long long n, F f) {
 // Spike: Z = L^-1 E for KS right-hand sides (SpikeJob, nd_passes.h).  blockIdx.x = group of kSpikeCols right-hand sides,
 // blockIdx.y = job.
 //
-// A warp owns 8 right-hand sides for the whole job: lane = col + 8 jq; the four lanes jq = 0..3 of a column split the
-// <= 30 blocks L_kj of row k among them (j = first + jq, + 4, ...), each accumulating all six components
-// sum_j L_kj z_j of ITS blocks (36 DFMA per block: the 6x6 block is fetched once for six outputs, 18 broadcast LDS.128),
-// two xor-shuffles add the four partial sums.  The last 32 block rows of Z of the warp's columns live in shared memory
-// private to the warp (column height <= 30), so the only block-wide hand-shake per row is the one that publishes the next
-// row of L: its blocks are contiguous in the envelope and are staged by cp.async one row ahead.  Row labels
-// (first / row_start) and the entering rows of E are fetched two / one rows ahead, so no global-memory latency sits on
-// the row-to-row chain.
-constexpr int kSpikeWarps = 2;
-constexpr int kSpikeCols = 8 * kSpikeWarps;      // right-hand sides per CTA
+// A warp owns 4 right-hand sides for the whole job: lane = col + 4 jq; the eight lanes jq = 0..7 of a column split the
+// <= 30 blocks L_kj of row k among them (j = first + jq, + 8, ...: at most four blocks per lane and row), each
+// accumulating all six components of sum_j L_kj z_j over ITS blocks (36 DFMA per block: the 6x6 block is fetched once for
+// six outputs), three xor-shuffles add the eight partial sums.  The last 32 block rows of Z of the warp's columns live in
+// shared memory private to the warp (column height <= 30), so the only block-wide hand-shake per row is the one that
+// publishes the next row of L: its blocks are contiguous in the envelope and are staged by cp.async two rows ahead, into
+// slots of 38 doubles so that the eight blocks a warp reads at once fall into distinct banks.  Row labels
+// (first / row_start) and the entering rows of E are fetched four / one rows ahead: no global-memory latency sits on the
+// row-to-row chain.
+constexpr int kSpikeWarps = 4;
+constexpr int kSpikeCols = 4 * kSpikeWarps;      // right-hand sides per CTA
 constexpr int kSpikeThreads = 32 * kSpikeWarps;
-constexpr int kSpikeZStride = 56;                // doubles per block row of a warp's Z window: [6][8] + 8 padding (bank spread)
-constexpr int kSpikeBufs = 3;                   // rows of L in flight (cp.async, two rows ahead)
-constexpr size_t kSpikeSmem = sizeof(double) * (kSpikeBufs * 31 * 36 + kSpikeWarps * 32 * kSpikeZStride);
+constexpr int kSpikeZStride = 28;                // doubles per block row of a warp's Z window: [6][4] + 4 padding (bank spread)
+constexpr int kSpikeBS = 38;                     // doubles per staged block of L
+constexpr int kSpikeBufs = 3;                    // rows of L in flight (cp.async, two rows ahead)
+constexpr size_t kSpikeSmem = sizeof(double) * (kSpikeBufs * 31 * kSpikeBS + kSpikeWarps * 32 * kSpikeZStride);
 
 __global__ void __launch_bounds__(kSpikeThreads)
 nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
   extern __shared__ __align__(16) double smem_spike[];
-  double* sRow = smem_spike;                                   // [kSpikeBufs][31*36] blocks of rows k, k+1, k+2
+  double* sRow = smem_spike;                                   // [kSpikeBufs][31][kSpikeBS] blocks of rows k, k+1, k+2
   const nd::SpikeJob J = jobs[blockIdx.y];
   const EnvView e = J.e;
   const int c0 = blockIdx.x * kSpikeCols;
   if (c0 >= J.KS) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int col8 = lane & 7, jq = lane >> 3;
-  const int c = c0 + warp * 8 + col8;                          // this lane's right-hand side
+  const int col4 = lane & 3, jq = lane >> 2;
+  const int c = c0 + warp * 4 + col4;                          // this lane's right-hand side
   const bool act = c < J.KS;
-  double* sZw = smem_spike + kSpikeBufs * 31 * 36 + warp * 32 * kSpikeZStride;
+  double* sZw = smem_spike + kSpikeBufs * 31 * kSpikeBS + warp * 32 * kSpikeZStride;
   const int n = e.n, n_stop = J.n_stop, KS = J.KS;
   auto stage_row = [&](int k, int f, long long rs) {           // blocks (k, f .. min(k, n_stop)-1) -> sRow[k % 3]
     if (k >= n) return;
     const int jend = k < n_stop ? k : n_stop;
     const int nb = jend > f ? jend - f : 0;
     const double* src = J.L + rs * 36;
-    double* dst = sRow + (k % kSpikeBufs) * (31 * 36);
-    for (int o = tid; o < nb * 18; o += kSpikeThreads) cp_async16_zfill(dst + 2 * o, src + 2 * o, true);
+    double* dst = sRow + (k % kSpikeBufs) * (31 * kSpikeBS);
+    for (int o = tid; o < nb * 18; o += kSpikeThreads) {
+      const int b = o / 18, h = o - b * 18;
+      cp_async16_zfill(dst + b * kSpikeBS + 2 * h, src + 2 * o, true);
+    }
   };
   // labels: row k (f0), rows k+1 .. k+3 (f1..f3, rs2, rs3): fetched four rows ahead of their use in the chain
   int f0 = e.first[0];
@@ -89,20 +94,24 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
       for (int x = 0; x < 6; ++x) en[x] = 0.0;
     }
     const int jend = k < n_stop ? k : n_stop;
-    const double* rowb = sRow + (k % kSpikeBufs) * (31 * 36);
+    const double* rowb = sRow + (k % kSpikeBufs) * (31 * kSpikeBS);
     double acc[6] = {0, 0, 0, 0, 0, 0};
-    for (int j = f0 + jq; j < jend; j += 4) {
-      const double2* b2 = reinterpret_cast<const double2*>(rowb + (j - f0) * 36);
-      const double* zj = sZw + (j & 31) * kSpikeZStride + col8;
-      const double z0 = zj[0], z1 = zj[8], z2 = zj[16], z3 = zj[24], z4 = zj[32], z5 = zj[40];
+#pragma unroll 2
+    for (int j = f0 + jq; j < jend; j += 8) {
+      const double2* b2 = reinterpret_cast<const double2*>(rowb + (j - f0) * kSpikeBS);
+      const double* zj = sZw + (j & 31) * kSpikeZStride + col4;
+      const double z0 = zj[0], z1 = zj[4], z2 = zj[8], z3 = zj[12], z4 = zj[16], z5 = zj[20];
 #pragma unroll
       for (int x = 0; x < 6; ++x) {
         const double2 p0 = b2[3 * x], p1 = b2[3 * x + 1], p2 = b2[3 * x + 2];
-        acc[x] += p0.x * z0; acc[x] += p0.y * z1; acc[x] += p1.x * z2; acc[x] += p1.y * z3; acc[x] += p2.x * z4; acc[x] += p2.y * z5;
+        double s0 = p0.x * z0, s1 = p0.y * z1;
+        s0 += p1.x * z2; s1 += p1.y * z3; s0 += p2.x * z4; s1 += p2.y * z5;
+        acc[x] += s0 + s1;
       }
     }
 #pragma unroll
     for (int x = 0; x < 6; ++x) {
+      acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 4);
       acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 8);
       acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 16);
     }
@@ -111,7 +120,7 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
 #pragma unroll
       for (int x = 0; x < 6; ++x) {
         const double v = ecur[x] - acc[x];
-        sZw[(k & 31) * kSpikeZStride + x * 8 + col8] = v;      // row k-32 is no longer needed (column height <= 30)
+        sZw[(k & 31) * kSpikeZStride + x * 4 + col4] = v;      // row k-32 is no longer needed (column height <= 30)
         if (act) J.Z[((long long)k * 6 + x) * KS + c] = v;
       }
     }
@@ -124,23 +133,27 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
 // SYRK: U -= sum_k Z_k^T K_k Z_k, u -= sum_k Z_k^T K_k w_k over the pivot rows of a node (SyrkSeg, nd_passes.h): the
 // product (KS x R)(R x KS), R = 6 rows, of Z^T with Y = K Z.  grid = (tiles of 64 x 64 scalars of the lower triangle,
 // groups of kSyrkSplit block rows, segments); a CTA walks its rows in chunks of 4 block rows: Z for the tile's row and
-// column side goes to shared memory (coalesced), Y = K Z is formed there, each thread accumulates a 4 x 4 register tile.
-// Partial sums of the row groups meet in U by RED.ADD.F64.  FP64-FMA bound.
+// column side is brought to shared memory by cp.async one chunk ahead, Y = K Z is formed there, each thread accumulates a
+// 4 x 4 register tile.  Partial sums of the row groups meet in U by RED.ADD.F64.  FP64-FMA bound.
 constexpr int kSyrkTile = 64;            // scalar columns per tile side
-constexpr int kSyrkChunk = 4;            // block rows per shared-memory chunk (24 scalar rows; three tiles of it stay below 48 kB)
-constexpr int kSyrkSplit = 30;           // block rows per CTA
+constexpr int kSyrkChunk = 4;            // block rows per shared-memory chunk (24 scalar rows)
+constexpr int kSyrkSplit = 32;           // block rows per CTA
 constexpr int kSyrkLd = kSyrkTile + 4;   // leading dimension of the shared tiles
+constexpr int kSyrkTileDoubles = kSyrkChunk * 6 * kSyrkLd;
+constexpr size_t kSyrkSmem = sizeof(double) * (5 * kSyrkTileDoubles + 2 * kSyrkChunk * 36 + 2 * kSyrkChunk * 6 + kSyrkChunk * 6);
 
 __global__ void __launch_bounds__(256)
 nd_syrk_kernel(const nd::SyrkSeg* __restrict__ segs) {
   constexpr int TS = kSyrkTile, RC = kSyrkChunk * 6, LD = kSyrkLd;
-  __shared__ __align__(16) double sA[RC][LD];       // Z[r][tile row side]
-  __shared__ __align__(16) double sB[RC][LD];       // Z[r][tile column side]
-  __shared__ __align__(16) double sY[RC][LD];       // (K Z)[r][tile column side]
-  __shared__ double sK[kSyrkChunk][36];
-  __shared__ double sKw[RC];
+  extern __shared__ __align__(16) double smem_syrk[];
+  double* sA = smem_syrk;                             // [2][RC][LD] Z[r][tile row side]
+  double* sB = sA + 2 * kSyrkTileDoubles;             // [2][RC][LD] Z[r][tile column side]
+  double* sY = sB + 2 * kSyrkTileDoubles;             // [RC][LD]    (K Z)[r][tile column side]
+  double* sK = sY + kSyrkTileDoubles;                 // [2][chunk][36]
+  double* sW = sK + 2 * kSyrkChunk * 36;              // [2][RC] w
+  double* sKw = sW + 2 * RC;                          // [RC]
   const nd::SyrkSeg G = segs[blockIdx.z];
-  int ti = 0, tj = 0;                                // tile (ti, tj), tj <= ti, from the linear index
+  int ti = 0, tj = 0;                                 // tile (ti, tj), tj <= ti, from the linear index
   { int t = blockIdx.x; while ((ti + 1) * (ti + 2) / 2 <= t) ++ti; tj = t - ti * (ti + 1) / 2; }
   if (ti * TS >= G.KS) return;
   const int k0 = blockIdx.y * kSyrkSplit;
@@ -148,52 +161,66 @@ nd_syrk_kernel(const nd::SyrkSeg* __restrict__ segs) {
   const int k1 = min(G.rows, k0 + kSyrkSplit);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int KS = G.KS;
+  // chunk kc -> buffer par: 16-byte pieces (KS is even, the tiles start at even columns); rows / columns beyond the data are zero-filled
+  auto prefetch = [&](int kc, int par) {
+    const int nr = min(kSyrkChunk, k1 - kc) * 6;
+    double* dA = sA + par * kSyrkTileDoubles;
+    double* dB = sB + par * kSyrkTileDoubles;
+    for (int o = tid; o < RC * (TS / 2); o += 256) {
+      const int r = o / (TS / 2), a2 = (o - r * (TS / 2)) * 2;
+      const double* zr = G.Z + ((long long)kc * 6 + (r < nr ? r : 0)) * KS;
+      const bool va = r < nr && ti * TS + a2 < KS, vb = r < nr && tj * TS + a2 < KS;
+      cp_async16_zfill(dA + r * LD + a2, va ? zr + ti * TS + a2 : G.Z, va);
+      cp_async16_zfill(dB + r * LD + a2, vb ? zr + tj * TS + a2 : G.Z, vb);
+    }
+    for (int o = tid; o < kSyrkChunk * 18; o += 256) {
+      const int bk = o / 18;
+      const bool v = kc + bk < k1;
+      cp_async16_zfill(sK + par * kSyrkChunk * 36 + 2 * o, v ? G.K + (long long)kc * 36 + 2 * o : G.K, v);
+    }
+    for (int o = tid; o < kSyrkChunk * 3; o += 256) {
+      const int bk = o / 3;
+      const bool v = kc + bk < k1;
+      cp_async16_zfill(sW + par * RC + 2 * o, v ? G.w + (long long)kc * 6 + 2 * o : G.w, v);
+    }
+  };
   double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
   double racc = 0.0;
-  for (int kc = k0; kc < k1; kc += kSyrkChunk) {
-    const int nbk = min(kSyrkChunk, k1 - kc), nr = nbk * 6;
-    __syncthreads();                                 // previous chunk consumed
-    for (int o = tid; o < RC * TS; o += 256) {
-      const int r = o / TS, a = o - r * TS;
-      double va = 0.0, vb = 0.0;
-      if (r < nr) {
-        const double* zr = G.Z + ((long long)kc * 6 + r) * KS;
-        if (ti * TS + a < KS) va = zr[ti * TS + a];
-        if (tj * TS + a < KS) vb = zr[tj * TS + a];
-      }
-      sA[r][a] = va; sB[r][a] = vb;
-    }
-    for (int o = tid; o < kSyrkChunk * 36; o += 256) {
-      const int bk = o / 36;
-      sK[bk][o - bk * 36] = (bk < nbk) ? G.K[(long long)(kc + bk) * 36 + (o - bk * 36)] : 0.0;
-    }
-    __syncthreads();
-    for (int o = tid; o < RC * TS; o += 256) {       // Y = K Z on the column side
+  prefetch(k0, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int par = 0;
+  for (int kc = k0; kc < k1; kc += kSyrkChunk, par ^= 1) {
+    if (kc + kSyrkChunk < k1) prefetch(kc + kSyrkChunk, par ^ 1);        // its buffer was consumed before the last barrier of the previous chunk
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();                                                     // chunk kc landed
+    const double* cA = sA + par * kSyrkTileDoubles;
+    const double* cB = sB + par * kSyrkTileDoubles;
+    const double* cK = sK + par * kSyrkChunk * 36;
+    for (int o = tid; o < RC * TS; o += 256) {                           // Y = K Z on the column side
       const int r = o / TS, b = o - r * TS, bk = r / 6, x = r - bk * 6;
-      const double* Kx = &sK[bk][x * 6];
+      const double* Kx = cK + bk * 36 + x * 6;
       double s = 0.0;
 #pragma unroll
-      for (int q = 0; q < 6; ++q) s += Kx[q] * sB[bk * 6 + q][b];
-      sY[r][b] = s;
+      for (int q = 0; q < 6; ++q) s += Kx[q] * cB[(bk * 6 + q) * LD + b];
+      sY[r * LD + b] = s;
     }
-    if (tj == 0 && tid < RC) {                       // (K w)[r]
+    if (tj == 0 && tid < RC) {                                           // (K w)[r]
       const int bk = tid / 6, x = tid - bk * 6;
       double s = 0.0;
-      if (bk < nbk) {
 #pragma unroll
-        for (int q = 0; q < 6; ++q) s += sK[bk][x * 6 + q] * G.w[(long long)(kc + bk) * 6 + q];
-      }
+      for (int q = 0; q < 6; ++q) s += cK[bk * 36 + x * 6 + q] * sW[par * RC + bk * 6 + q];
       sKw[tid] = s;
     }
     __syncthreads();
 #pragma unroll 4
     for (int r = 0; r < RC; ++r) {
-      const double2 a01 = *reinterpret_cast<const double2*>(&sA[r][4 * ty]), a23 = *reinterpret_cast<const double2*>(&sA[r][4 * ty + 2]);
-      const double2 b01 = *reinterpret_cast<const double2*>(&sY[r][4 * tx]), b23 = *reinterpret_cast<const double2*>(&sY[r][4 * tx + 2]);
+      const double2 a01 = *reinterpret_cast<const double2*>(cA + r * LD + 4 * ty), a23 = *reinterpret_cast<const double2*>(cA + r * LD + 4 * ty + 2);
+      const double2 b01 = *reinterpret_cast<const double2*>(sY + r * LD + 4 * tx), b23 = *reinterpret_cast<const double2*>(sY + r * LD + 4 * tx + 2);
       const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -202,9 +229,10 @@ nd_syrk_kernel(const nd::SyrkSeg* __restrict__ segs) {
     }
     if (tj == 0 && tid < TS) {
       double s = 0.0;
-      for (int r = 0; r < RC; ++r) s += sA[r][tid] * sKw[r];
+      for (int r = 0; r < RC; ++r) s += cA[r * LD + tid] * sKw[r];
       racc += s;
     }
+    __syncthreads();                                                     // sY, sKw and this chunk's buffers are free again
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -254,79 +282,61 @@ nd_correct_apply_kernel(nd::Tables t, const int* __restrict__ ids, int stride) {
 // The register-window kernel of factor_la.cuh slides a 31-row window along a band and pays ~4 900 cycles per pivot column
 // whatever the column holds; a separator is dense and SHRINKS (the trailing matrix of pivot k has (29-k)(30-k)/2 blocks),
 // and its 30 pivots sit on the critical path of every tree level.  Here every block of the lower triangle lives in the
-// registers of one thread for the whole factorisation (thread <-> (i, j)); per pivot k:
-//   phase B  the owners of column k (blocks (i,k), i >= k) each invert D_k themselves (the pivot block was published at the
-//            end of the previous update; two reciprocals on the dependent chain, factor_la.cuh) and scale their block:
-//            T_ik = block, L_ik = T_ik D_k^-1, both to shared memory (transposed layout not needed: operands are read
-//            row-wise), L_ik to global memory, z_i -= L_ik z_k;
-//   phase C  every live block (i, j), i >= j > k:  G -= L_ik T_jk^T  (216 DFMA, operands by LDS.128; the thread map
-//            groups 8 x 4 patches of blocks into a warp so that a warp touches <= 8 + 4 distinct operand blocks).
+// registers of one PAIR thread for the whole factorisation (thread <-> (i, j)), and ONE extra warp owns the pivot column:
+//   phase B  (column warp, lane <-> row i = k+1+lane)  every lane inverts D_k (the same instruction stream for all lanes:
+//            one warp's worth of FP64 issue slots; two reciprocals on the dependent chain, factor_la.cuh), then scales its
+//            own block: L_ik = T_ik D_k^-1 -> shared memory and global memory, z_i -= L_ik z_k;
+//   phase C  (pair threads) every live block (i, j), i >= j > k:  G -= L_ik T_jk^T  (216 DFMA, operands by LDS.128; the
+//            thread map groups 8 x 4 patches of blocks into a warp so that a warp touches <= 8 + 4 distinct operand
+//            blocks); the blocks of column k+1 are final after it and go to shared memory (T_{i,k+1}, D_{k+1}).
 // Two block barriers per pivot.  One CTA per separator; grid = separators of the tree level.
 constexpr int kDenseMax = 30;
-constexpr int kDenseThreads = 480;           // 465 blocks of the 30 x 30 lower triangle
+constexpr int kDensePairThreads = 480;       // 465 blocks of the 30 x 30 lower triangle
+constexpr int kDenseThreads = kDensePairThreads + 32;
 constexpr int kDenseS = 38;                  // doubles per operand block in shared memory (bank spread, 16 B aligned)
 
 __global__ void __launch_bounds__(kDenseThreads, 1)
 nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short* __restrict__ tmap) {
   __shared__ __align__(16) double sL[kDenseMax * kDenseS];
-  __shared__ __align__(16) double sT[kDenseMax * kDenseS];
-  __shared__ __align__(16) double sD[36];
+  __shared__ __align__(16) double sT[2][kDenseMax * kDenseS];       // T_{i,k}: parity k & 1
+  __shared__ __align__(16) double sD[2][36];
   __shared__ double sZ[kDenseMax * 6];
   const FactorJob J = jobs[blockIdx.x];
   const int n = J.e.n;
   const int tid = threadIdx.x;
-  const unsigned short tm = tmap[tid];
-  const int i = tm & 0xff, j = tm >> 8;                       // block (i, j), j <= i ; 0xffff: idle thread
-  const bool live = tm != 0xffff && i < n;
-  double G[36];
-  if (live) {
-    const double2* src = reinterpret_cast<const double2*>(J.L + ((long long)i * (i + 1) / 2 + j) * 36);
-#pragma unroll
-    for (int q = 0; q < 18; ++q) { const double2 v = src[q]; G[2 * q] = v.x; G[2 * q + 1] = v.y; }
-  } else {
-#pragma unroll
-    for (int q = 0; q < 36; ++q) G[q] = 0.0;
-  }
   for (int o = tid; o < n * 6; o += kDenseThreads) sZ[o] = J.z[o];
-  if (live && i == 0 && j == 0) {
-#pragma unroll
-    for (int q = 0; q < 36; ++q) sD[q] = G[q];
-  }
-  __syncthreads();
-  int bad = 0;
-  for (int k = 0; k < n; ++k) {
-    // ---------------- phase B: column k
-    if (live && j == k) {
-      // this block is finished after the pivot: park it in shared memory (its T_ik slot) and free its registers for the inverse
-      double2* t2 = reinterpret_cast<double2*>(sT + i * kDenseS);
-      if (i != k) {
-#pragma unroll
-        for (int q = 0; q < 18; ++q) t2[q] = make_double2(G[2 * q], G[2 * q + 1]);
-      }
-#pragma unroll
-      for (int q = 0; q < 36; ++q) G[q] = 0.0;
+  if (tid >= kDensePairThreads) {
+    // ================================================= column warp
+    const int lane = tid - kDensePairThreads;
+    int bad = 0;
+    __syncthreads();                                               // (0) column 0 and D_0 published
+    for (int k = 0; k < n; ++k) {
+      const int par = k & 1;
+      const int i = k + 1 + lane;
       double xl[21], K[21];
 #pragma unroll
       for (int a = 0; a < 6; ++a)
 #pragma unroll
-        for (int b = 0; b <= a; ++b) xl[LVBA_T(a, b)] = sD[a * 6 + b];
+        for (int b = 0; b <= a; ++b) xl[LVBA_T(a, b)] = sD[par][a * 6 + b];
       sym6_block_inverse(xl, K);
       auto kk = [&](int r, int c) -> double { return r >= c ? K[LVBA_T(r, c)] : K[LVBA_T(c, r)]; };
-      if (i == k) {
-        if (!isfinite((K[LVBA_T(0, 0)] + K[LVBA_T(5, 5)]) + (K[LVBA_T(3, 0)] + K[LVBA_T(2, 1)]))) bad = 1;
+      if (!isfinite((K[LVBA_T(0, 0)] + K[LVBA_T(5, 5)]) + (K[LVBA_T(3, 0)] + K[LVBA_T(2, 1)]))) bad = 1;
+      if (lane == 31 || (lane == 0 && n - k - 1 <= 0)) {           // an idle lane (or lane 0 of the last pivot) stores D_k^-1
         double* dk = J.dinv + (long long)k * 36;
 #pragma unroll
         for (int r = 0; r < 6; ++r)
 #pragma unroll
           for (int c = 0; c < 6; ++c) dk[r * 6 + c] = kk(r, c);
-      } else {
+      }
+      if (i < n) {
+        const double2* t2 = reinterpret_cast<const double2*>(&sT[par][i * kDenseS]);
         double2* l2 = reinterpret_cast<double2*>(sL + i * kDenseS);
         double2* g2 = reinterpret_cast<double2*>(J.L + ((long long)i * (i + 1) / 2 + k) * 36);
         double zk[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) zk[q] = sZ[k * 6 + q];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {                          // row r of L_ik = T_ik D_k^-1, straight to its destinations
+        for (int r = 0; r < 6; ++r) {                              // row r of L_ik = T_ik D_k^-1, straight to its destinations
           const double2 g0 = t2[3 * r], g1 = t2[3 * r + 1], g2v = t2[3 * r + 2];
           const double gr[6] = {g0.x, g0.y, g1.x, g1.y, g2v.x, g2v.y};
           double lr[6];
@@ -348,32 +358,55 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
           sZ[i * 6 + r] -= zs;
         }
       }
+      __syncthreads();                                             // (1) L_{.,k} published
+      __syncthreads();                                             // (2) column k+1 and D_{k+1} published by the pair threads
     }
-    __syncthreads();
-    // ---------------- phase C: trailing update
-    if (live && j > k) {
-      const double2* l2 = reinterpret_cast<const double2*>(sL + i * kDenseS);
-      const double2* t2 = reinterpret_cast<const double2*>(sT + j * kDenseS);
+    if (bad && lane == 0) J.status[0] = 1;
+  } else {
+    // ================================================= pair threads
+    const unsigned short tm = tmap[tid];
+    const int i = tm & 0xff, j = tm >> 8;                          // block (i, j), j <= i ; 0xffff: idle thread
+    const bool live = tm != 0xffff && i < n;
+    double G[36];
+    if (live) {
+      const double2* src = reinterpret_cast<const double2*>(J.L + ((long long)i * (i + 1) / 2 + j) * 36);
 #pragma unroll
-      for (int y = 0; y < 6; ++y) {
-        const double2 t0 = t2[3 * y], t1 = t2[3 * y + 1], t2v = t2[3 * y + 2];
+      for (int q = 0; q < 18; ++q) { const double2 v = src[q]; G[2 * q] = v.x; G[2 * q + 1] = v.y; }
+    } else {
 #pragma unroll
-        for (int x = 0; x < 6; ++x) {
-          const double2 a0 = l2[3 * x], a1 = l2[3 * x + 1], a2 = l2[3 * x + 2];
-          double s = G[x * 6 + y];
-          s -= a0.x * t0.x; s -= a0.y * t0.y; s -= a1.x * t1.x; s -= a1.y * t1.y; s -= a2.x * t2v.x; s -= a2.y * t2v.y;
-          G[x * 6 + y] = s;
+      for (int q = 0; q < 36; ++q) G[q] = 0.0;
+    }
+    // a block of column c is final after pivot c-1: it goes to shared memory (T_{i,c} or D_c) for the column warp
+    auto publish = [&](int c) {
+      double2* d2 = (i == c) ? reinterpret_cast<double2*>(sD[c & 1]) : reinterpret_cast<double2*>(&sT[c & 1][i * kDenseS]);
+#pragma unroll
+      for (int q = 0; q < 18; ++q) d2[q] = make_double2(G[2 * q], G[2 * q + 1]);
+    };
+    if (live && j == 0) publish(0);
+    __syncthreads();                                               // (0)
+    for (int k = 0; k < n; ++k) {
+      __syncthreads();                                             // (1) L_{.,k} published
+      if (live && j > k) {
+        const double2* l2 = reinterpret_cast<const double2*>(sL + i * kDenseS);
+        const double2* t2 = reinterpret_cast<const double2*>(&sT[k & 1][j * kDenseS]);
+#pragma unroll
+        for (int y = 0; y < 6; ++y) {
+          const double2 t0 = t2[3 * y], t1 = t2[3 * y + 1], t2v = t2[3 * y + 2];
+#pragma unroll
+          for (int x = 0; x < 6; ++x) {
+            const double2 a0 = l2[3 * x], a1 = l2[3 * x + 1], a2 = l2[3 * x + 2];
+            double s = G[x * 6 + y];
+            s -= a0.x * t0.x; s -= a0.y * t0.y; s -= a1.x * t1.x; s -= a1.y * t1.y; s -= a2.x * t2v.x; s -= a2.y * t2v.y;
+            G[x * 6 + y] = s;
+          }
         }
+        if (j == k + 1) publish(k + 1);
       }
-      if (i == k + 1 && j == k + 1) {
-#pragma unroll
-        for (int q = 0; q < 36; ++q) sD[q] = G[q];
-      }
+      __syncthreads();                                             // (2)
     }
-    __syncthreads();
   }
+  __syncthreads();
   for (int o = tid; o < n * 6; o += kDenseThreads) J.z[o] = sZ[o];
-  if (bad) J.status[0] = 1;
 }
 
 // thread -> block map of nd_dense_factor_kernel: blocks of the 30 x 30 lower triangle grouped by 8 x 4 patches
@@ -386,7 +419,7 @@ inline std::vector<unsigned short> dense_thread_map() {
     for (int q = 0; q < 4; ++q) if (ka[q] != kb[q]) return ka[q] < kb[q];
     return false;
   });
-  std::vector<unsigned short> m((size_t)kDenseThreads, (unsigned short)0xffff);
+  std::vector<unsigned short> m((size_t)kDensePairThreads, (unsigned short)0xffff);
   for (size_t t = 0; t < v.size(); ++t) m[t] = (unsigned short)(v[t].i | (v[t].j << 8));
   return m;
 }

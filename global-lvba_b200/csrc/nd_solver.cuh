@@ -101,6 +101,7 @@ struct NdDevice {
     LVBA_TRY(T.alloc((size_t)std::max<long long>(plan.sizeT, 1))); LVBA_TRY(W.alloc((size_t)std::max<long long>(plan.sizeW, 1)));
     LVBA_TRY(w.alloc((size_t)std::max<long long>(plan.sizew, 1)));
     LVBA_CUDA(cudaFuncSetAttribute(nd_spike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpikeSmem));
+    LVBA_CUDA(cudaFuncSetAttribute(nd_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
     LVBA_CUDA(cudaStreamSynchronize(s));                     // local vectors
     leaf_e = nd::leaf_e_stride(plan); leaf_fin = nd::leaf_final_stride(plan);
     chunks = p; ready = true;
@@ -181,7 +182,7 @@ struct NdCudaExec {
   void syrk(const nd::SyrkSeg* segs, int n, int max_ks, int max_rows) {
     if (n <= 0 || max_ks <= 0) return;
     const int nt1 = (max_ks + kSyrkTile - 1) / kSyrkTile, nt = nt1 * (nt1 + 1) / 2;
-    nd_syrk_kernel<<<dim3(nt, (max_rows + kSyrkSplit - 1) / kSyrkSplit, n), 256, 0, s>>>(segs);
+    nd_syrk_kernel<<<dim3(nt, (max_rows + kSyrkSplit - 1) / kSyrkSplit, n), 256, kSyrkSmem, s>>>(segs);
     ++launches;
   }
   void correct_apply(const nd::Tables& t, const int* ids, int n_ids, int stride) {
