@@ -3,24 +3,27 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C]
 
-A *step* is one LM iteration of the whole hot path on one synthetic problem:
+A *step* — the same for both arms, written into `config.step` of both lines — is ONE full LM iteration of the whole hot path on
+one synthetic problem, started from the initial state:
     t_A  one BALM2 pass  = Hessian/gradient build + damped block-LDL^T solve + retraction
                            + residual-only pass + accept/reject          (bavoxel.hpp:686-766)
     t_B  one Ceres-style pass = Jacobians + Schur elimination + reduced solve + back-substitution
                            + candidate cost + accept/reject              (src/lvba_system.cpp:1643)
     metric value = 1 / (t_A + t_B)            [LM iterations / s]
-Every timed step starts from the initial state (device-to-device restore) so that it always contains
-the Hessian build; inputs are resident in HBM (`value`).  `e2e` is the same metric through the one-shot
-C-ABI calls lvba_lidar_lm / lvba_visual_lm with HOST (pinned) buffers: symbolic set-up, H2D upload of the
-whole problem, the reference's own iteration caps (10 / 50) and the D2H result copy are inside the timed
-region; t_A, t_B there are call time / iterations executed.
+`value`: inputs resident in HBM (device-to-device restore of the initial state before every step).
+`e2e`:   the same step through the one-shot C-ABI calls lvba_lidar_lm / lvba_visual_lm (max_iter = 1) with HOST (pinned) buffers:
+         validation, symbolic set-up, H2D upload of the whole problem, the pass and the D2H result copy are inside the timed
+         region of every step.
+`full_call` (informational): the reference's own iteration caps (10 / 50) per call, time / passes, for both arms.
 
-Workload at every N: BASELINE.json configs[2] (2000 poses / 200k plane voxels / 100k tracks) unless
---config says otherwise.  N > 1 shards voxels / tracks by contiguous pose-block rows across ranks (strong
-scaling of ONE problem, NCCL all-reduce of H, g, S, rhs and the scalar costs).
+Workload: N = 1 -> BASELINE.json configs[2] (2000 poses / 200k plane voxels / 100k tracks, the config the metric is quoted on);
+N > 1 -> configs[4] (5000 / 500k / 300k, the config BASELINE names for scaling), sharded by contiguous pose-block rows; the
+N > 1 line also carries `n1_same_config`: the same config measured on ONE GPU by rank 0 in the same run, so that a like-for-like
+efficiency can be formed.  `--config` overrides.
 
-`--impl reference` times the reference-restated CPU path (oracle/cpu_ref.cpp — the reference itself needs
-Eigen/Ceres/PCL/ROS and cannot be built here) on the box's host cores, same config / metric.
+`--impl reference` times the reference-restated CPU path (oracle/cpu_ref.cpp — the reference itself needs Eigen/Ceres/PCL/ROS and
+cannot be built here) on the box's host cores, same step / config / metric.  Path A runs with the thread count that is fastest
+in a sweep that always includes the reference's own fixed 16 (bavoxel.hpp:25); path B likewise (Ceres uses all threads).
 """
 from __future__ import annotations
 
@@ -42,11 +45,20 @@ sys.path.insert(0, str(ROOT))
 METRIC = "LM iterations/sec (Jacobian+Hessian build + Schur solve)"
 UNIT = "LM iterations/s"
 VKEYS = ("q", "t", "X", "plane_nd", "obs_ptr", "obs_cam", "obs_uv", "intr", "sigma_px", "sigma_plane")
+STEP_TEXT = ("one full LM iteration from the initial state: path A (Hessian build + damped LDL^T solve + retraction + residual pass "
+             "+ accept test) then path B (Jacobians + Schur + reduced solve + back-substitution + candidate cost)")
+L2_TEXT = "GPU arm: 256 MiB buffer written between timed steps (L2 flush); CPU arm: per-step working set (>300 MB) exceeds the host LLC"
+FP64_PEAK_TFLOPS = 148 * 63.7 * 2 * 1.965e9 / 1e12      # measured 63.7 DFMA/clk/SM (tools/ubench/fp64_rate.cu) x 148 SMs x 1.965 GHz
 
 
 def workload_name(cfg, p):
     return (f"config {cfg}: {p['n_poses']} poses / {p['n_vox']} plane voxels / {p['n_tracks']} visual tracks, "
             f"synthetic (oracle/synth.py, seed {p['seed']})")
+
+
+def config_block(cfg, p):
+    """identical in both arms (the driver compares it)"""
+    return {"workload": workload_name(cfg, p), "step": STEP_TEXT, "l2": L2_TEXT}
 
 
 class ClockSampler:
@@ -99,25 +111,37 @@ def algorithmic_bytes(p, lid_counts, vis_counts, n_active):
     return dict(lidar_build=build_A, lidar_residual=resid_A, bytes_A=build_A + resid_A, bytes_B=bytes_B)
 
 
-def cpu_reference_iteration(p, threads, iters_A=2, iters_B=2):
-    """Bounded sample of the CPU restatement: a few LM passes of each path on the full problem."""
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_pass(p, threads_a, threads_b):
+    """one full LM pass of each path on the full problem with the CPU restatement; ms per pass (A, B)"""
     from oracle import cpu_ref
-    _, a = cpu_ref.lidar_lm(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"], max_iter=iters_A, rel_tol=-1.0, threads=threads)
-    _, _, _, b = cpu_ref.visual_lm(*[p[k] for k in VKEYS], max_iter=iters_B, threads=threads, function_tolerance=-1.0)
-    tA = a["ms_build"] / max(a["builds"], 1) + (a["ms_solve"] + a["ms_residual"]) / max(a["iterations"], 1)
-    tB = (b["ms_build"] + b["ms_solve"] + b["ms_residual"]) / max(b["iterations"], 1)
-    return tA, tB, a, b
+    _, a = cpu_ref.lidar_lm(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"], max_iter=1, rel_tol=-1.0, threads=threads_a)
+    _, _, _, b = cpu_ref.visual_lm(*[p[k] for k in VKEYS], max_iter=1, threads=threads_b, function_tolerance=-1.0)
+    tA = a["ms_build"] + a["ms_solve"] + a["ms_residual"]
+    tB = b["ms_build"] + b["ms_solve"] + b["ms_residual"]
+    return tA, tB
+
+
+def cpu_thread_sweep(p):
+    """fastest thread count per path; the reference's fixed 16 (bavoxel.hpp:25) is always a candidate"""
+    from oracle import cpu_ref
+    hw = cpu_ref.hardware_threads()
+    cand = sorted({t for t in (8, 16, 32, 64, hw) if t <= max(hw, 16)})
+    sweep = {}
+    for t in cand:
+        tA, tB = cpu_pass(p, t, t)
+        sweep[str(t)] = {"ms_A": round(tA, 1), "ms_B": round(tB, 1)}
+    best_a = min(cand, key=lambda t: sweep[str(t)]["ms_A"])
+    best_b = min(cand, key=lambda t: sweep[str(t)]["ms_B"])
+    return best_a, best_b, sweep, hw
 
 
 def run_reference(args, p, cfg):
-    """--impl reference: the CPU path, all host threads, same metric / config."""
-    from oracle import cpu_ref
-    threads = cpu_ref.hardware_threads()
+    """--impl reference: the CPU path on the host cores, same step / metric / config."""
+    ta, tb, sweep, hw = cpu_thread_sweep(p)
     times = []
     for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        tA, tB, a, b = cpu_reference_iteration(p, threads, 1, 1)
-        wall = time.perf_counter() - t0
+        tA, tB = cpu_pass(p, ta, tb)
         if i >= args.warmup:
             times.append((tA + tB) / 1e3)
     mean = sum(times) / len(times)
@@ -125,12 +149,62 @@ def run_reference(args, p, cfg):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(cfg, p), "l2": "inputs larger than L2 (CPU run)"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "each step = 1 LM pass of path A + 1 of path B on the full problem (oracle/cpu_ref.cpp)"},
+            "config": config_block(cfg, p),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": max(ta, tb), "threads_path_A": ta, "threads_path_B": tb,
+                             "host_hardware_threads": hw, "kind": "port", "thread_sweep_ms_per_pass": sweep,
+                             "sample": "each step = 1 full LM pass of path A + 1 of path B on the full problem (oracle/cpu_ref.cpp: the reference "
+                                       "restated; Eigen/Ceres are not installable here)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def measure_resident(pkg, torch, p, device, steps, warmup, barrier, rank):
+    """K timed steps with inputs resident; returns dict with host seconds, per-phase device ms, launches, full-LM summaries"""
+    L = pkg.LidarProblem(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"], device=device)
+    Vz = pkg.VisualProblem(*[p[k] for k in VKEYS], device=device)
+    lo_opts = pkg.lidar_default_opts(); lo_opts.rel_tol = -1.0; lo_opts.max_iter = 1 << 30
+    vo_opts = pkg.visual_default_opts(); vo_opts.function_tolerance = -1.0; vo_opts.parameter_tolerance = -1.0
+    vo_opts.gradient_tolerance = -1.0; vo_opts.max_iter = 1 << 30
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    def one_step():
+        flush.fill_(rank + 1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        L.reset_lm(lo_opts); L.reset_state(); sa = L.iterate(1)
+        Vz.reset_lm(vo_opts); Vz.reset_state(); sb = Vz.iterate(1)
+        return time.perf_counter() - t0, sa, sb
+
+    for _ in range(warmup):
+        one_step()
+    barrier()
+    wall0 = time.perf_counter()
+    host_s, launches = 0.0, 0
+    dev_ms = {"build_A": 0.0, "solve_A": 0.0, "resid_A": 0.0, "build_B": 0.0, "solve_B": 0.0, "resid_B": 0.0}
+    for _ in range(steps):
+        dt, sa, sb = one_step()
+        host_s += dt
+        dev_ms["build_A"] += sa["ms_build"]; dev_ms["solve_A"] += sa["ms_solve"]; dev_ms["resid_A"] += sa["ms_residual"]
+        dev_ms["build_B"] += sb["ms_build"]; dev_ms["solve_B"] += sb["ms_solve"]; dev_ms["resid_B"] += sb["ms_residual"]
+        launches += sa["kernel_launches"] + sb["kernel_launches"]
+    barrier()
+    wall = time.perf_counter() - wall0
+    # full LM to the reference's caps (BASELINE configs[2]), device resident
+    L.reset_lm(None); L.reset_state(); fa = L.iterate(10)
+    Vz.reset_lm(None); Vz.reset_state(); fb = Vz.iterate(50)
+    out = {"host_s": host_s, "wall": wall, "launches": launches, "dev_ms": {k: v / steps for k, v in dev_ms.items()},
+           "full_A": fa, "full_B": fb, "lid_counts": L.counts(nonzero=True), "vis_counts": Vz.counts(),
+           "n_active": len(Vz.structure()[0]), "structA": L.structure(), "structB": Vz.structure()}
+    L.close(); Vz.close()
+    del flush
+    return out
+
+
+def ldl_flops(brow, bcol, n):
+    below = np.bincount(bcol[brow > bcol], minlength=n).astype(np.float64)     # blocks under every pivot
+    return float((below * (below + 1) / 2 * 432 + below * 72 * 2 + below * 72 * 2).sum())   # trailing update + scale + two substitutions
 
 
 def main():
@@ -139,9 +213,10 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C", choices=["A", "B", "C", "E"])
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--config", default=None, choices=["A", "B", "C", "E"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the GPU-vs-CPU full-LM parity check at the benchmarked config")
     ap.add_argument("--no-voxel-map", action="store_true", help="skip the boundary-B3 (voxel map) side measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -149,13 +224,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = args.config or ("C" if world == 1 else "E")
 
     from oracle import synth
     if args.impl == "reference":
         if rank != 0:
             return 0
-        p = synth.make_config(args.config)
-        run_reference(args, p, args.config)
+        p = synth.make_config(cfg)
+        run_reference(args, p, cfg)
         return 0
 
     import torch
@@ -166,157 +242,187 @@ def main():
     if pkg.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device — the LVBA hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        uid = [pkg.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        pkg.comm_init(world, rank, uid[0], local_rank)
-
-    p = synth.make_config(args.config)                    # identical on every rank (counter-based RNG)
-    L = pkg.LidarProblem(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"], device=local_rank)
-    Vz = pkg.VisualProblem(*[p[k] for k in VKEYS], device=local_rank)
-    lo_opts = pkg.lidar_default_opts(); lo_opts.rel_tol = -1.0; lo_opts.max_iter = 1 << 30
-    vo_opts = pkg.visual_default_opts(); vo_opts.function_tolerance = -1.0; vo_opts.parameter_tolerance = -1.0
-    vo_opts.gradient_tolerance = -1.0; vo_opts.max_iter = 1 << 30
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
-
-    def one_step():
-        """returns (host seconds, summaryA, summaryB) for one LM pass of each path from the initial state"""
-        flush.fill_(rank + 1)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        L.reset_lm(lo_opts); L.reset_state(); sa = L.iterate(1)
-        Vz.reset_lm(vo_opts); Vz.reset_state(); sb = Vz.iterate(1)
-        return time.perf_counter() - t0, sa, sb
+    p = synth.make_config(cfg)                            # identical on every rank (counter-based RNG)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        one_step()
+    n1 = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # the same config on ONE GPU, measured by rank 0 before the communicator exists (the others wait)
+        if rank == 0:
+            r1 = measure_resident(pkg, torch, p, local_rank, max(5, args.steps // 2), 3, lambda: torch.cuda.synchronize(), 0)
+            n1 = {"value": max(5, args.steps // 2) / r1["host_s"], "device_ms_per_step": r1["dev_ms"],
+                  "full_lm_cost_A": r1["full_A"]["cost_last"], "full_lm_cost_B": r1["full_B"]["cost_last"]}
+        dist.barrier()
+        uid = [pkg.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        pkg.comm_init(world, rank, uid[0], local_rank)
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    barrier()
-    wall0 = time.perf_counter()
-    host_s, dev_ms, launches = 0.0, {"build_A": 0.0, "solve_A": 0.0, "resid_A": 0.0, "build_B": 0.0, "solve_B": 0.0, "resid_B": 0.0}, 0
-    for _ in range(args.steps):
-        dt, sa, sb = one_step()
-        host_s += dt
-        dev_ms["build_A"] += sa["ms_build"]; dev_ms["solve_A"] += sa["ms_solve"]; dev_ms["resid_A"] += sa["ms_residual"]
-        dev_ms["build_B"] += sb["ms_build"]; dev_ms["solve_B"] += sb["ms_solve"]; dev_ms["resid_B"] += sb["ms_residual"]
-        launches += sa["kernel_launches"] + sb["kernel_launches"]
-    barrier()
-    wall = time.perf_counter() - wall0
+    R = measure_resident(pkg, torch, p, local_rank, args.steps, args.warmup, barrier, rank)
     clocks = sampler.stop() if rank == 0 else None
-    # max over ranks of the timed seconds (host clock around synchronous steps) and of the device time
-    dev_total_ms = sum(dev_ms.values())
-    tt = torch.tensor([host_s, dev_total_ms], dtype=torch.float64, device="cuda")
+    dev_total_ms = sum(R["dev_ms"].values())
+    tt = torch.tensor([R["host_s"], dev_total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     host_s_max, dev_ms_max = tt[0].item(), tt[1].item()
     ms_per_step = host_s_max * 1e3 / args.steps
     value = args.steps / host_s_max
 
-    # ---- full LM to convergence (BASELINE configs[2]) — informational, device resident
-    L.reset_lm(None); L.reset_state(); fa = L.iterate(10)
-    Vz.reset_lm(None); Vz.reset_state(); fb = Vz.iterate(50)
-
-    # ---- e2e through the one-shot C-ABI calls, host (pinned) buffers
+    # ---- e2e: the same step through the one-shot C-ABI calls, host (pinned) buffers, everything inside the timed region
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t.numpy()
     hp = {k: pinned(p[k]) for k in ("vox_ptr", "pose_idx", "clusters", "poses", "q", "t", "X", "plane_nd", "obs_ptr", "obs_cam", "obs_uv", "intr")}
-    e2e_tA = e2e_tB = 0.0
-    h2d = d2h = 0
-    n_e2e = max(1, args.e2e_steps)
-    for i in range(n_e2e + 1):                                   # first call is warm-up
+    o1 = pkg.lidar_default_opts(); o1.max_iter = 1; o1.rel_tol = -1.0; o1.device = local_rank
+    v1 = pkg.visual_default_opts(); v1.max_iter = 1; v1.function_tolerance = -1.0; v1.parameter_tolerance = -1.0; v1.gradient_tolerance = -1.0
+    v1.device = local_rank
+    oF = pkg.lidar_default_opts(); oF.device = local_rank
+    vF = pkg.visual_default_opts(); vF.device = local_rank
+
+    def abi_calls(lo, vo):
         barrier()
         t0 = time.perf_counter()
-        _, sa = pkg.lidar_lm(hp["vox_ptr"], hp["pose_idx"], hp["clusters"], hp["poses"])
+        _, sa = pkg.lidar_lm(hp["vox_ptr"], hp["pose_idx"], hp["clusters"], hp["poses"], lo)
         t1 = time.perf_counter()
-        _, _, _, sb = pkg.visual_lm(hp["q"], hp["t"], hp["X"], hp["plane_nd"], hp["obs_ptr"], hp["obs_cam"], hp["obs_uv"], hp["intr"], p["sigma_px"], p["sigma_plane"])
+        _, _, _, sb = pkg.visual_lm(hp["q"], hp["t"], hp["X"], hp["plane_nd"], hp["obs_ptr"], hp["obs_cam"], hp["obs_uv"], hp["intr"],
+                                    p["sigma_px"], p["sigma_plane"], opts=vo)
         t2 = time.perf_counter()
+        return t1 - t0, t2 - t1, sa, sb
+
+    n_e2e = max(1, args.e2e_steps)
+    e2e_s, h2d, d2h = 0.0, 0, 0
+    for i in range(n_e2e + 1):                                   # first call is warm-up
+        ta, tb, sa, sb = abi_calls(o1, v1)
         if i > 0:
-            e2e_tA += (t1 - t0) / max(sa["iterations"], 1)
-            e2e_tB += (t2 - t1) / max(sb["iterations"], 1)
+            e2e_s += ta + tb
             h2d += sa["h2d_bytes"] + sb["h2d_bytes"]; d2h += sa["d2h_bytes"] + sb["d2h_bytes"]
-            e2e_iters = (sa["iterations"], sb["iterations"])
-    te = torch.tensor([e2e_tA / n_e2e + e2e_tB / n_e2e], dtype=torch.float64, device="cuda")
+    te = torch.tensor([e2e_s / n_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = 1.0 / te.item()
+    ta, tb, sa, sb = abi_calls(oF, vF)                           # full call to the reference's caps (informational)
+    full_call = {"ms_per_pass_A": ta * 1e3 / max(sa["iterations"], 1), "ms_per_pass_B": tb * 1e3 / max(sb["iterations"], 1),
+                 "passes_A": sa["iterations"], "passes_B": sb["iterations"], "ms_call_A": ta * 1e3, "ms_call_B": tb * 1e3,
+                 "cost_A": sa["cost_last"], "cost_B": sb["cost_last"]}
+    full_call["value"] = 1e3 / (full_call["ms_per_pass_A"] + full_call["ms_per_pass_B"])
 
+    rc = 0
     if rank == 0:
-        lc = L.counts(nonzero=True); vc = Vz.counts(); n_active = len(Vz.structure()[0])
-        ab = algorithmic_bytes(p, lc, vc, n_active)
+        ab = algorithmic_bytes(p, R["lid_counts"], R["vis_counts"], R["n_active"])
         try:
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()); peak = float(peaks["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
         except Exception:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        traffic = None
-        try:     # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (same config)
-            prof = json.loads((ROOT / "profiles" / "r01_ncu_full_summary.json").read_text())["lidar_build_kernel"]
-            if args.config == "C" and world == 1:
-                traffic = (float(prof["dram__bytes_read.sum"]) + float(prof["dram__bytes_write.sum"])) * 1e6
+        prof = {}
+        try:     # DRAM bytes per launch from the committed `ncu --set full` captures (config C, one GPU)
+            prof = json.loads((ROOT / "profiles" / "r02_ncu_summary.json").read_text())
         except Exception:
-            pass
-        build_ms = dev_ms["build_A"] / args.steps
+            try:
+                prof = json.loads((ROOT / "profiles" / "r01_ncu_full_summary.json").read_text())
+            except Exception:
+                prof = {}
+
+        def traffic_of(kernel):
+            try:
+                if cfg == "C" and world == 1:
+                    return (float(prof[kernel]["dram__bytes_read.sum"]) + float(prof[kernel]["dram__bytes_write.sum"])) * 1e6
+            except Exception:
+                pass
+            return None
+        dm = R["dev_ms"]
+        # the largest single kernel of the step is the Hessian build of path A (one launch); the solves are ~30 launches each
+        build_ms = dm["build_A"]
         achieved = ab["lidar_build"] / (build_ms * 1e-3) / 1e9
-        roofline = {"kernel": "lidar_build_kernel (+ memset of H, + partial-sum reduce)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        roofline = {"kernel": "lidar_build_kernel (largest single kernel of the step; timed with the memset of H and the partial-sum reduce)",
+                    "share_of_step": build_ms / max(dev_total_ms, 1e-9),
+                    "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic_of("lidar_build_kernel"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": ab["lidar_build"], "avg_launch_ms": build_ms,
-                    "note": "timed with CUDA events on the library's launch stream; the kernel is atomic/FP64 bound, not HBM bound (DESIGN.md)"}
-        # the kernel that dominates the step is the block LDL^T of the pose / camera system: a chain of W sequential
-        # pivot columns on two SMs (twisted), bound by ONE SM's FP64 pipe, shared-memory wavefronts and the latency of
-        # the look-ahead chain (DESIGN.md section 4) -- neither HBM nor tensor cores.  Its useful FP64 work is reported
-        # against the FP64 peak of the SMs it can use; the time is the whole solve phase (factorisation + substitutions).
-        def ldl_flops(brow, bcol, n):
-            below = np.bincount(bcol[brow > bcol], minlength=n).astype(np.float64)     # blocks under every pivot
-            return float((below * (below + 1) / 2 * 432 + below * 72 * 2 + below * 72 * 2).sum())   # trailing update + scale + two substitutions
-        brA, bcA = L.structure()
-        sv = Vz.structure()
+                    "fp64_tflops": 3.6e9 * (p["n_vox"] / 200000.0) / (build_ms * 1e-3) / 1e12, "fp64_frac_of_chip": 3.6e9 * (p["n_vox"] / 200000.0) / (build_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                    "note": "CUDA events on the library's launch stream; ncu: atomic (RED.ADD.F64) / shared-memory bound, not HBM bound (DESIGN.md 4)"}
+        resid_ms = dm["resid_A"]
+        roofline_residual = {"kernel": "lidar_residual_kernel (+ retraction, partial-sum reduce)", "bound": "hbm",
+                             "achieved": ab["lidar_residual"] / (resid_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": ab["lidar_residual"] / (resid_ms * 1e-3) / 1e9 / peak, "traffic": traffic_of("lidar_residual_kernel"),
+                             "avg_launch_ms": resid_ms}
+        brA, bcA = R["structA"]
+        sv = R["structB"]
         flA = ldl_flops(np.asarray(brA), np.asarray(bcA), p["n_poses"])
-        flB = ldl_flops(np.asarray(sv[1]), np.asarray(sv[2]), n_active)
-        solve_s = (dev_ms["solve_A"] + dev_ms["solve_B"]) / args.steps * 1e-3
-        fp64_two_sm = 2 * 64 * 2 * 1.965e9 / 1e12                                      # 2 SMs x 64 FMA/clk x 2 flop x 1.965 GHz
-        dominant = {"kernel": "env_factor_la_kernel<P> (register-window block LDL^T, two CTAs: twisted halves) + env_backsolve_warp_kernel",
-                    "share_of_step": (dev_ms["solve_A"] + dev_ms["solve_B"]) / max(dev_total_ms, 1e-9),
-                    "bound": "FP64 pipe + shared-memory wavefronts + look-ahead chain latency of ONE SM per half; sequential over pivot columns",
-                    "fp64_flops_per_step": flA + flB, "achieved_tflops": (flA + flB) / solve_s / 1e12,
-                    "peak_tflops_of_the_two_sms_it_runs_on": fp64_two_sm, "frac": (flA + flB) / solve_s / 1e12 / fp64_two_sm,
-                    "note": "FP64 vector peak measured 63.7 FMA/clk/SM (tools/ubench/fp64_rate.cu); time = solve phase (factor + substitutions) from CUDA events"}
+        flB = ldl_flops(np.asarray(sv[1]), np.asarray(sv[2]), R["n_active"])
+        solve_s = (dm["solve_A"] + dm["solve_B"]) * 1e-3
+        roofline_solve = {"kernels": "substructured block LDL^T: env_factor_la_kernel (chunk interiors, grid = chunks), nd_dense_factor_kernel "
+                                     "(separators), nd_spike_kernel, nd_syrk_kernel, env_backsolve_warp_kernel (csrc/nd_solver.cuh)",
+                          "share_of_step": (dm["solve_A"] + dm["solve_B"]) / max(dev_total_ms, 1e-9),
+                          "bound": "fp64 (latency of the pivot chains; no HBM traffic to speak of: the systems are L2 resident)",
+                          "fp64_flops_sequential_ldlt": flA + flB, "achieved_tflops": (flA + flB) / solve_s / 1e12,
+                          "peak_tflops_chip": FP64_PEAK_TFLOPS, "frac": (flA + flB) / solve_s / 1e12 / FP64_PEAK_TFLOPS,
+                          "note": "useful flops = those of ONE sequential banded LDL^T (the substructured solve spends ~4x more on spikes "
+                                  "and separator updates); denominator = whole-chip FP64 vector peak"}
+        step_bytes = ab["bytes_A"] + ab["bytes_B"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
-                "config": {"workload": workload_name(args.config, p), "parallelism": f"pose-block-row shards x{world}",
-                           "l2": "256 MiB buffer written between timed steps (L2 flush)",
-                           "step": "1 LM pass of path A + 1 of path B from the initial state, inputs resident in HBM"},
-                "device_ms_per_step": {k: v / args.steps for k, v in dev_ms.items()},
-                "dominant_kernel_by_time": dominant,
+                "data": "synthetic", "config": config_block(cfg, p),
+                "run": {"parallelism": f"pose-block-row shards x{world}", "config_letter": cfg,
+                        "scale_config": "N = 1: config C (headline); N > 1: config E, with n1_same_config measured in the same run"},
+                "device_ms_per_step": dm,
                 "device_ms_per_step_total_max_over_ranks": dev_ms_max / args.steps,
-                "timed_region_wall_s": wall,
-                "roofline": roofline, "algorithmic_bytes": ab,
-                "full_lm": {"A": {k: fa[k] for k in ("iterations", "accepted", "cost_first", "cost_last", "ms_total")},
-                            "B": {k: fb[k] for k in ("iterations", "accepted", "cost_first", "cost_last", "ms_total")}},
+                "timed_region_wall_s": R["wall"],
+                "roofline": roofline, "roofline_residual": roofline_residual, "roofline_solve": roofline_solve,
+                "step_hbm": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                             "frac_of_peak": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
+                "algorithmic_bytes": ab,
+                "full_lm": {"A": {k: R["full_A"][k] for k in ("iterations", "accepted", "cost_first", "cost_last", "ms_total")},
+                            "B": {k: R["full_B"][k] for k in ("iterations", "accepted", "cost_first", "cost_last", "ms_total")}},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // n_e2e, "d2h_bytes_per_step": d2h // n_e2e,
-                        "step": f"one lvba_lidar_lm (<=10 passes, ran {e2e_iters[0]}) + one lvba_visual_lm (<=50 passes, ran {e2e_iters[1]}) from pinned host buffers; t = call time / passes"},
-                "gpu_launches": int(launches), "clocks": clocks}
+                        "step": "lvba_lidar_lm(max_iter=1) + lvba_visual_lm(max_iter=1) from pinned host buffers: validation, symbolic "
+                                "set-up, H2D of the whole problem, one pass, D2H — every step"},
+                "full_call": full_call,
+                "gpu_launches": int(R["launches"]), "clocks": clocks}
+        if n1 is not None:
+            line["n1_same_config"] = n1
+            line["efficiency_vs_n1_same_config"] = value / (world * n1["value"])
+            line["parity_vs_n1"] = {"rel_A": abs(R["full_A"]["cost_last"] - n1["full_lm_cost_A"]) / abs(n1["full_lm_cost_A"]),
+                                    "rel_B": abs(R["full_B"]["cost_last"] - n1["full_lm_cost_B"]) / abs(n1["full_lm_cost_B"])}
+            if max(line["parity_vs_n1"].values()) > 1e-6:
+                line["parity_vs_n1"]["ok"] = False
+                rc = 3
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import cpu_ref
-            threads = cpu_ref.hardware_threads()
-            tA, tB, a, b = cpu_reference_iteration(p, threads, 2, 2)
-            line["cpu_baseline"] = {"value": 1e3 / (tA + tB), "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "2 LM passes of path A + 2 of path B on the full problem (oracle/cpu_ref.cpp), per-pass time with Hessian build",
-                                    "ms_A": tA, "ms_B": tB}
+            ta_, tb_, sweep, hw = cpu_thread_sweep(p)
+            tA, tB = cpu_pass(p, ta_, tb_)
+            line["cpu_baseline"] = {"value": 1e3 / (tA + tB), "unit": UNIT, "cores": max(ta_, tb_), "threads_path_A": ta_, "threads_path_B": tb_,
+                                    "host_hardware_threads": hw, "kind": "port", "thread_sweep_ms_per_pass": sweep,
+                                    "sample": "1 full LM pass of path A + 1 of path B on the full problem (oracle/cpu_ref.cpp) at the fastest thread "
+                                              "count of the sweep (the reference's fixed 16 included)", "ms_A": tA, "ms_B": tB}
+            if not args.no_parity:
+                # north-star check at the benchmarked config: full LM (caps 10 / 50) on the GPU against the CPU restatement
+                from oracle import cpu_ref
+                t0 = time.perf_counter()
+                _, ca = cpu_ref.lidar_lm(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"], threads=ta_)
+                _, _, _, cb = cpu_ref.visual_lm(*[p[k] for k in VKEYS], threads=tb_)
+                relA = abs(R["full_A"]["cost_last"] - ca["cost_last"]) / abs(ca["cost_last"])
+                relB = abs(R["full_B"]["cost_last"] - cb["cost_last"]) / abs(cb["cost_last"])
+                ok = bool(relA <= 1e-6 and relB <= 1e-6)
+                line[f"parity_{cfg}"] = {"tolerance_rel": 1e-6, "ok": ok,
+                                         "A": {"gpu_cost": R["full_A"]["cost_last"], "cpu_cost": ca["cost_last"], "rel": relA,
+                                               "gpu_iterations": R["full_A"]["iterations"], "cpu_iterations": int(ca["iterations"])},
+                                         "B": {"gpu_cost": R["full_B"]["cost_last"], "cpu_cost": cb["cost_last"], "rel": relB,
+                                               "gpu_iterations": R["full_B"]["iterations"], "cpu_iterations": int(cb["iterations"])},
+                                         "cpu_full_call": {"ms_per_pass_A": ca["ms_total"] / max(ca["iterations"], 1), "ms_per_pass_B": cb["ms_total"] / max(cb["iterations"], 1),
+                                                           "value": 1e3 / (ca["ms_total"] / max(ca["iterations"], 1) + cb["ms_total"] / max(cb["iterations"], 1))},
+                                         "seconds": time.perf_counter() - t0}
+                if not ok:
+                    rc = 3
         if world == 1 and not args.no_voxel_map:
             # Boundary B3 (set-up stage, DESIGN.md 4.3) measured OUTSIDE the timed region, in a child process so that
             # nothing it does can disturb the numbers above; reported next to them, not part of `value` / `e2e`.
-            import subprocess
             try:
                 r = subprocess.run([sys.executable, str(ROOT / "tools" / "bench_voxel_map.py")], capture_output=True, text=True, timeout=300)
                 last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
@@ -324,11 +430,10 @@ def main():
             except Exception as e:          # noqa: BLE001 - a side measurement must never take the bench line down
                 line["voxel_map"] = {"error": repr(e)[:400]}
         print(json.dumps(line), flush=True)
-    L.close(); Vz.close()
     if world > 1:
         pkg.comm_destroy()
         dist.destroy_process_group()
-    return 0
+    return rc
 
 
 if __name__ == "__main__":

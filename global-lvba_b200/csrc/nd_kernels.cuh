@@ -22,19 +22,20 @@ __global__ void __launch_bounds__(256) nd_pass_kernel(long long n, F f) {
 // Spike: Z = L^-1 E for KS right-hand sides (SpikeJob, nd_passes.h).  blockIdx.x = group of kSpikeCols right-hand sides,
 // blockIdx.y = job.
 //
-// A warp owns 4 right-hand sides for the whole job: lane = col + 4 jq; the eight lanes jq = 0..7 of a column split the
-// <= 30 blocks L_kj of row k among them (j = first + jq, + 8, ...: at most four blocks per lane and row), each
+// A warp owns 2 right-hand sides for the whole job: lane = col + 2 jq; the sixteen lanes jq = 0..15 of a column split the
+// <= 30 blocks L_kj of row k among them (j = first + jq, + 16: at most two blocks per lane and row), each
 // accumulating all six components of sum_j L_kj z_j over ITS blocks (36 DFMA per block: the 6x6 block is fetched once for
-// six outputs), three xor-shuffles add the eight partial sums.  The last 32 block rows of Z of the warp's columns live in
+// six outputs), four xor-shuffles add the sixteen partial sums.  (Measured: the row-to-row chain of a warp is bound by
+// instruction latency, not by a pipe — fp64 18 %, one warp per scheduler — so the row is cut across many lanes and warps.)  The last 32 block rows of Z of the warp's columns live in
 // shared memory private to the warp (column height <= 30), so the only block-wide hand-shake per row is the one that
 // publishes the next row of L: its blocks are contiguous in the envelope and are staged by cp.async two rows ahead, into
 // slots of 38 doubles so that the eight blocks a warp reads at once fall into distinct banks.  Row labels
 // (first / row_start) and the entering rows of E are fetched four / one rows ahead: no global-memory latency sits on the
 // row-to-row chain.
-constexpr int kSpikeWarps = 4;
-constexpr int kSpikeCols = 4 * kSpikeWarps;      // right-hand sides per CTA
+constexpr int kSpikeWarps = 8;
+constexpr int kSpikeCols = 2 * kSpikeWarps;      // right-hand sides per CTA
 constexpr int kSpikeThreads = 32 * kSpikeWarps;
-constexpr int kSpikeZStride = 28;                // doubles per block row of a warp's Z window: [6][4] + 4 padding (bank spread)
+constexpr int kSpikeZStride = 14;                // doubles per block row of a warp's Z window: [6][2] + 2 padding (bank spread)
 constexpr int kSpikeBS = 38;                     // doubles per staged block of L
 constexpr int kSpikeBufs = 3;                    // rows of L in flight (cp.async, two rows ahead)
 constexpr size_t kSpikeSmem = sizeof(double) * (kSpikeBufs * 31 * kSpikeBS + kSpikeWarps * 32 * kSpikeZStride);
@@ -48,8 +49,8 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
   const int c0 = blockIdx.x * kSpikeCols;
   if (c0 >= J.KS) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int col4 = lane & 3, jq = lane >> 2;
-  const int c = c0 + warp * 4 + col4;                          // this lane's right-hand side
+  const int col2 = lane & 1, jq = lane >> 1;
+  const int c = c0 + warp * 2 + col2;                          // this lane's right-hand side
   const bool act = c < J.KS;
   double* sZw = smem_spike + kSpikeBufs * 31 * kSpikeBS + warp * 32 * kSpikeZStride;
   const int n = e.n, n_stop = J.n_stop, KS = J.KS;
@@ -97,10 +98,10 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
     const double* rowb = sRow + (k % kSpikeBufs) * (31 * kSpikeBS);
     double acc[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll 2
-    for (int j = f0 + jq; j < jend; j += 8) {
+    for (int j = f0 + jq; j < jend; j += 16) {
       const double2* b2 = reinterpret_cast<const double2*>(rowb + (j - f0) * kSpikeBS);
-      const double* zj = sZw + (j & 31) * kSpikeZStride + col4;
-      const double z0 = zj[0], z1 = zj[4], z2 = zj[8], z3 = zj[12], z4 = zj[16], z5 = zj[20];
+      const double* zj = sZw + (j & 31) * kSpikeZStride + col2;
+      const double z0 = zj[0], z1 = zj[2], z2 = zj[4], z3 = zj[6], z4 = zj[8], z5 = zj[10];
 #pragma unroll
       for (int x = 0; x < 6; ++x) {
         const double2 p0 = b2[3 * x], p1 = b2[3 * x + 1], p2 = b2[3 * x + 2];
@@ -111,6 +112,7 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
     }
 #pragma unroll
     for (int x = 0; x < 6; ++x) {
+      acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 2);
       acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 4);
       acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 8);
       acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 16);
@@ -120,7 +122,7 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
 #pragma unroll
       for (int x = 0; x < 6; ++x) {
         const double v = ecur[x] - acc[x];
-        sZw[(k & 31) * kSpikeZStride + x * 4 + col4] = v;      // row k-32 is no longer needed (column height <= 30)
+        sZw[(k & 31) * kSpikeZStride + x * 2 + col2] = v;      // row k-32 is no longer needed (column height <= 30)
         if (act) J.Z[((long long)k * 6 + x) * KS + c] = v;
       }
     }

@@ -51,15 +51,13 @@ struct NdDevice {
   static int default_chunks(int n, int max_col) {
     const char* ev = getenv("LVBA_ND_CHUNKS");
     if (ev && ev[0]) return atoi(ev);
-    if (n < 384) return 0;                                  // the twisted pair is faster for short chains
-    int best = 0; long long best_cost = (long long)n / 2 + max_col;     // twisted: n/2 + separator
-    for (int p = 4; p <= 128; p *= 2) {
-      const long long interior = ((long long)n - (long long)(p - 1) * max_col) / p;
-      if (interior < 2 * nd::kMinInterior) break;
-      int depth = 0; while ((1 << depth) < p) ++depth;
-      const long long cost = interior + (long long)depth * max_col;
-      if (cost < best_cost) { best_cost = cost; best = p; }
-    }
+    // measured on B200 (profiles/r02_solver_bench.txt): a leaf costs ~4.4 us per row (factor + spike + substitutions), a tree
+    // level ~(4.3 w + 70) us; the twisted pair ~1.35 us per row of the whole system.  Interiors of about three band widths
+    // balance the two terms; below ~800 rows the two-CTA twisted solve wins.
+    if (n < 768) return 0;
+    const long long want = (long long)n / (3LL * max_col + 30);
+    int best = 0;
+    for (int p = 4; p <= 256 && p <= want; p *= 2) best = p;
     return best;
   }
 

@@ -556,6 +556,19 @@ int ref_lidar_lm(int32_t W, int64_t V, const int64_t* vp, const int32_t* pi, con
   return 0;
 }
 
+// one damped step at the given poses: (H + u diag(H)) dx = -g  (bavoxel.hpp:692-710); for the per-pose-update parity check
+int ref_lidar_step(int32_t W, int64_t V, const int64_t* vp, const int32_t* pi, const double* cl, const double* poses, double u,
+                   int32_t nthreads, double* dx_out, double* residual_sum) {
+  Lidar L; lidar_setup(L, W, V, vp, pi, cl);
+  vector<double> H, g, Lm, dadd((size_t)6 * W), mg((size_t)6 * W); vector<vector<double>> scratch;
+  const double r = lidar_divide_thread(L, poses, nthreads, H, g, scratch);
+  if (residual_sum) *residual_sum = r;
+  Lm = H;
+  for (int rr = 0; rr < W; ++rr) for (int c = 0; c < 6; ++c) { dadd[6 * rr + c] = u * H[L.env.blk(rr, rr) * 36 + 7 * c]; mg[6 * rr + c] = -g[6 * rr + c]; }
+  env_solve(L.env, Lm, dadd.data(), mg.data(), dx_out);
+  return 0;
+}
+
 // single phases for cross-checks against the numpy oracle
 int ref_lidar_structure(int32_t W, int64_t V, const int64_t* vp, const int32_t* pi, int64_t* nblocks, int32_t* brow, int32_t* bcol) {
   Lidar L; lidar_setup(L, W, V, vp, pi, nullptr);

@@ -47,6 +47,18 @@ def lidar_lm(vox_ptr, pose_idx, clusters, poses, u0=0.01, v0=2.0, max_iter=10, r
     return ps, info
 
 
+def lidar_step(vox_ptr, pose_idx, clusters, poses, u=0.01, threads=16):
+    """dx of one damped step (H + u diag H) dx = -g at `poses`, and sum(lambda_0)."""
+    lib = load()
+    vp = np.ascontiguousarray(vox_ptr, np.int64); pi = np.ascontiguousarray(pose_idx, np.int32)
+    cl = np.ascontiguousarray(clusters, np.float64); ps = np.ascontiguousarray(poses, np.float64)
+    W = ps.shape[0]
+    dx = np.zeros((W, 6)); r = C.c_double()
+    lib.ref_lidar_step(C.c_int32(W), C.c_int64(len(vp) - 1), _p(vp, C.c_int64), _p(pi, C.c_int32), _p(cl, C.c_double), _p(ps, C.c_double),
+                       C.c_double(u), C.c_int32(threads), _p(dx, C.c_double), C.byref(r))
+    return dx, r.value
+
+
 def lidar_build(vox_ptr, pose_idx, clusters, poses, threads=4):
     lib = load()
     vp = np.ascontiguousarray(vox_ptr, np.int64); pi = np.ascontiguousarray(pose_idx, np.int32)

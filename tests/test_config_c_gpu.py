@@ -1,0 +1,87 @@
+"""North-star check at the config the metric is quoted on (BASELINE.json configs[2]: 2000 poses / 200k plane voxels / 100k tracks):
+the GPU path against the CPU restatement of the reference (oracle/cpu_ref.cpp — parity unpinned: the reference itself needs
+Eigen / Ceres and cannot be built here).
+  * per-pose update of the first LM iteration (BALM2::damping_iter, reference include/BALM/bavoxel.hpp:692-710):
+      backward error  |(H + u diag H) dx + g|_inf <= 1e-12 |g|_inf  with the GPU's own H, g  (what the block LDL^T owes), and
+      |dx_gpu - dx_cpu|_inf <= 1e-8 |dx_cpu|_inf  (BASELINE north star; H itself agrees to ~1e-9 — lambda_0 is a difference of
+      O(1e4) terms, SURVEY.md Q7 — and the damped system is well conditioned at u = 0.01, so the step inherits that accuracy);
+  * final cost of the full LM (caps 10 / 50 iterations) within 1e-6 relative for both paths."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from oracle import synth, cpu_ref  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+VKEYS = ("q", "t", "X", "plane_nd", "obs_ptr", "obs_cam", "obs_uv", "intr", "sigma_px", "sigma_plane")
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as graft
+    p = graft.load_package()
+    p.load_library()
+    if p.device_count() < 1:
+        pytest.fail("no CUDA device: the LVBA hot path has no CPU fallback")
+    return p
+
+
+@pytest.fixture(scope="module")
+def cfg_c():
+    return synth.make_config("C")
+
+
+def _sparse(br, bc, bl, n):
+    """symmetric sparse matrix from the lower block list (diagonal blocks: lower triangle valid)"""
+    br = np.asarray(br); bc = np.asarray(bc); bl = np.asarray(bl).reshape(-1, 6, 6).copy()
+    d = br == bc
+    bl[d] = np.tril(bl[d]) + np.tril(bl[d], -1).transpose(0, 2, 1)
+    r = (6 * br[:, None, None] + np.arange(6)[None, :, None]) + np.zeros((1, 1, 6), np.int64)
+    c = (6 * bc[:, None, None] + np.arange(6)[None, None, :]) + np.zeros((1, 6, 1), np.int64)
+    lower = sp.coo_matrix((bl.ravel(), (r.ravel(), c.ravel())), shape=(6 * n, 6 * n))
+    off = ~d
+    upper = sp.coo_matrix((bl[off].ravel(), (c[off].ravel(), r[off].ravel())), shape=(6 * n, 6 * n))
+    return (lower + upper).tocsr()
+
+
+def test_first_step_update_config_C(pkg, cfg_c):
+    p = cfg_c
+    W = p["n_poses"]
+    u = 0.01
+    P = pkg.LidarProblem(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"])
+    r_gpu = P.build()
+    dx = np.asarray(P.solve(u)).reshape(W, 6)
+    g, br, bc, bl = P.get_system()
+    P.close()
+    H = _sparse(br, bc, bl, W)
+    A = H + u * sp.diags(H.diagonal())
+    g = np.asarray(g).ravel()
+    backward = np.abs(A @ dx.ravel() + g).max() / np.abs(g).max()
+    dx_cpu, r_cpu = cpu_ref.lidar_step(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"], u, threads=16)
+    forward = np.abs(dx - dx_cpu).max() / np.abs(dx_cpu).max()
+    print(f"config C first step: backward error {backward:.3e}, |dx_gpu - dx_cpu| / |dx_cpu| = {forward:.3e}, residual rel {abs(r_gpu - r_cpu) / abs(r_cpu):.3e}")
+    assert abs(r_gpu - r_cpu) <= 1e-8 * abs(r_cpu)
+    assert backward <= 1e-12
+    assert forward <= 1e-8
+
+
+def test_final_costs_config_C(pkg, cfg_c):
+    p = cfg_c
+    _, sa = pkg.lidar_lm(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"])
+    _, ca = cpu_ref.lidar_lm(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"], threads=16)
+    relA = abs(sa["cost_last"] - ca["cost_last"]) / abs(ca["cost_last"])
+    print(f"config C path A: gpu {sa['cost_last']:.12e} ({sa['iterations']} it) cpu {ca['cost_last']:.12e} ({int(ca['iterations'])} it) rel {relA:.2e}")
+    assert relA <= 1e-6
+    assert sa["iterations"] == int(ca["iterations"]) and sa["accepted"] == int(ca["accepted"])
+    _, _, _, sb = pkg.visual_lm(*[p[k] for k in VKEYS])
+    _, _, _, cb = cpu_ref.visual_lm(*[p[k] for k in VKEYS], threads=16)
+    relB = abs(sb["cost_last"] - cb["cost_last"]) / abs(cb["cost_last"])
+    print(f"config C path B: gpu {sb['cost_last']:.12e} ({sb['iterations']} it) cpu {cb['cost_last']:.12e} ({int(cb['iterations'])} it) rel {relB:.2e}")
+    assert relB <= 1e-6
+    assert sb["iterations"] == int(cb["iterations"])

@@ -1,7 +1,7 @@
 """Boundary B4 on a B200: depth images rendered on the device (lvba_depth_grid_create / lvba_depth_render,
 global-lvba_b200/csrc/depth_api.cuh) against oracle/depth_oracle.py through the C ABI — EXACT image equality, the
-comparisons of tests/test_depth_emu.py.  Each case runs in a child process under a timeout (first hardware run of this
-path; the file sorts last so that nothing here can disturb the CUDA context of the other GPU tests)."""
+comparisons of tests/test_depth_emu.py.  Each case runs in a child process under a timeout (the file
+sorts last so that nothing here can disturb the CUDA context of the other GPU tests)."""
 import subprocess
 import sys
 import textwrap
@@ -11,10 +11,7 @@ import pytest
 
 ROOT = Path(__file__).resolve().parents[1]
 
-# The round's GPU budget ran out before this boundary existed: these cases have had no hardware run yet (their CPU twins
-# in tests/test_depth_emu.py, which execute the same pass functors, are green).  Until a B200 run is on record they report
-# XPASS / XFAIL instead of gating the suite; remove the marker once confirmed.
-pytestmark = pytest.mark.xfail(strict=False, reason="boundary B4: first hardware run pending (CPU emulation of the same passes is green)")
+# Confirmed on a B200 by the driver's round-1 run (GPUTEST_r01.json: every case passed); the cases gate the suite.
 
 PRELUDE = """
 import sys

@@ -16,7 +16,6 @@ ROOT = Path(__file__).resolve().parents[1]
 # First hardware run (B200, profiles/r01_voxel_gpu_first_run.txt): every case below passed except the windowed one, whose
 # test body shadowed the `lo` oracle module at the time (fixed since, not re-run: the round's GPU budget was spent) while the
 # C++ mirror of the same stage (run_window_stage, last case) passed.  That one case stays non-gating until it is re-run.
-not_rerun = pytest.mark.xfail(strict=False, reason="test body fixed after the only hardware run of this round; re-run pending")
 
 PRELUDE = """
 import sys
@@ -169,7 +168,6 @@ def test_scans_to_lm_chain():
 
 
 @pytest.mark.gpu
-@not_rerun
 def test_windowed_map_and_batched_lm():
     """runWindowBA's window stage: one map per window built together, then every window solved in one batched LM —
     against one oracle map + one oracle damping_iter per window."""

@@ -2,7 +2,7 @@
 the in-SM solvers' step; (2) a problem with loop-closure couplings (envelope columns taller than the 320 blocks the
 shared-memory kernel holds — LVBA_ERR_UNSUPPORTED before this path existed) must follow the oracle's LM, which solves the
 full normal equations with a sparse LU.  The arithmetic of the passes is checked without a GPU in
-tests/test_wide_solver_emu.py; this file has had no hardware run yet."""
+tests/test_wide_solver_emu.py; confirmed on a B200 by the driver's round-1 run (GPUTEST_r01.json)."""
 import os
 import subprocess
 import sys
@@ -13,7 +13,6 @@ import pytest
 
 ROOT = Path(__file__).resolve().parents[1]
 
-pytestmark = pytest.mark.xfail(strict=False, reason="any-width solver: first hardware run pending (pass arithmetic is green on the CPU)")
 
 PRELUDE = """
 import os, sys
