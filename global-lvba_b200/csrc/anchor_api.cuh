@@ -8,6 +8,7 @@ struct lvba_anchor_clouds {
   lvba::anchor::AnchorClouds<lvba::CudaExec> ac;
   int device = 0;
   double ms_device = 0.0;
+  ~lvba_anchor_clouds() { cudaStreamSynchronize(ac.ex.stream); }     // members are parked in the pool after this body: they must be idle
 };
 
 extern "C" {
@@ -39,6 +40,7 @@ int lvba_anchor_clouds_create(int32_t n_windows, const int32_t* win_ptr, const i
   lvba::DevBuf<int64_t> d_scan;
   lvba::DevBuf<double> d_rel;
   lvba::DevBuf<int32_t> d_win;
+  lvba::StreamDrain drain(nullptr);      // every path of this handle runs on the NULL stream
   std::vector<float> packed;
   const float* src = xyz;
   if (xyz_stride_floats != 3 && N > 0) {
@@ -54,13 +56,12 @@ int lvba_anchor_clouds_create(int32_t n_windows, const int32_t* win_ptr, const i
   LVBA_TRY(d_scan.upload(scan_ptr, (size_t)S + 1, ex.stream));
   LVBA_TRY(d_rel.upload(rel_poses, (size_t)S * 12, ex.stream));
   LVBA_TRY(d_win.upload(win_ptr, (size_t)n_windows + 1, ex.stream));
-  cudaEvent_t e0, e1;
-  LVBA_CUDA(cudaEventCreate(&e0));
-  LVBA_CUDA(cudaEventCreate(&e1));
+  lvba::EventPair ev;
+  LVBA_TRY(ev.create());
+  const cudaEvent_t e0 = ev.a, e1 = ev.b;
   LVBA_CUDA(cudaEventRecord(e0, ex.stream));
   const int rc = h->ac.build(d_xyz.p, d_scan.p, d_rel.p, d_win.p, S, n_windows, N, leaf);
   if (rc != LVBA_OK) {
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (h->ac.error[0]) return lvba::fail(rc, "%s", h->ac.error);
     return rc;
   }
@@ -68,7 +69,6 @@ int lvba_anchor_clouds_create(int32_t n_windows, const int32_t* win_ptr, const i
   LVBA_CUDA(cudaEventSynchronize(e1));
   float ms = 0.f;
   LVBA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   ex.temp.release();
   h->ms_device = ms;
   if (n_points_out) *n_points_out = h->ac.n_out;

@@ -8,6 +8,7 @@ struct lvba_depth_grid {
   lvba::depth::DepthGrid<lvba::CudaExec> grid;
   int device = 0;
   lvba_depth_summary sum{};
+  ~lvba_depth_grid() { cudaStreamSynchronize(grid.ex.stream); }     // members are parked in the pool after this body: they must be idle
 };
 
 extern "C" {
@@ -40,6 +41,7 @@ int lvba_depth_grid_create(int32_t n_frames, const int64_t* scan_ptr, const floa
   lvba::DevBuf<float> d_xyz;
   lvba::DevBuf<int64_t> d_scan;
   lvba::DevBuf<double> d_poses, d_ts;
+  lvba::StreamDrain drain(nullptr);      // every path of this handle runs on the NULL stream
   int64_t h2d = 0;
   std::vector<float> packed;
   const float* src = xyz;
@@ -56,14 +58,13 @@ int lvba_depth_grid_create(int32_t n_frames, const int64_t* scan_ptr, const floa
   LVBA_TRY(d_scan.upload(scan_ptr, (size_t)n_frames + 1, ex.stream, &h2d));
   LVBA_TRY(d_poses.upload(poses, (size_t)n_frames * 12, ex.stream, &h2d));
   LVBA_TRY(d_ts.upload(frame_ts, (size_t)n_frames, ex.stream, &h2d));
-  cudaEvent_t e0, e1;
-  LVBA_CUDA(cudaEventCreate(&e0));
-  LVBA_CUDA(cudaEventCreate(&e1));
+  lvba::EventPair ev;
+  LVBA_TRY(ev.create());
+  const cudaEvent_t e0 = ev.a, e1 = ev.b;
   LVBA_CUDA(cudaEventRecord(e0, ex.stream));
   const auto t1 = clk::now();
   const int rc = h->grid.build(d_xyz.p, d_scan.p, d_poses.p, d_ts.p, n_frames, N, voxel_size);
   if (rc != LVBA_OK) {
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (h->grid.error[0]) return lvba::fail(rc, "%s", h->grid.error);
     return rc;
   }
@@ -71,7 +72,6 @@ int lvba_depth_grid_create(int32_t n_frames, const int64_t* scan_ptr, const floa
   LVBA_CUDA(cudaEventSynchronize(e1));
   float ms = 0.f;
   LVBA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   ex.temp.release();
   lvba_depth_summary& s = h->sum;
   s.n_points = N; s.n_voxels = h->grid.n_voxels; s.n_pairs = h->grid.n_pairs;
@@ -103,11 +103,12 @@ int lvba_depth_render(lvba_depth_grid* g, int32_t n_images, const double* cams, 
   const int64_t batch = std::max<int64_t>(1, ((int64_t)1 << 28) / pix);          // <= 2^28 pixels (1 GiB of floats) per pass
   lvba::DevBuf<double> d_cams, d_ts;
   lvba::DevBuf<float> d_depth;
+  lvba::StreamDrain drain(nullptr);
   int64_t h2d = 0, d2h = 0, pairs = 0, chunks = 0;
   float ms_dev = 0.f;
-  cudaEvent_t e0, e1;
-  LVBA_CUDA(cudaEventCreate(&e0));
-  LVBA_CUDA(cudaEventCreate(&e1));
+  lvba::EventPair ev;
+  LVBA_TRY(ev.create());
+  const cudaEvent_t e0 = ev.a, e1 = ev.b;
   for (int64_t k0 = 0; k0 < n_images; k0 += batch) {
     const int64_t nb = std::min<int64_t>(batch, n_images - k0);
     LVBA_TRY(d_cams.upload(cams + 12 * k0, (size_t)nb * 12, ex.stream, &h2d));
@@ -115,7 +116,7 @@ int lvba_depth_render(lvba_depth_grid* g, int32_t n_images, const double* cams, 
     if (d_depth.n < (size_t)(nb * pix)) LVBA_TRY(d_depth.alloc((size_t)(nb * pix)));
     LVBA_CUDA(cudaEventRecord(e0, ex.stream));
     const int rc = G.render(nb, d_cams.p, d_ts.p, half_window, intr, width, height, d_depth.p);
-    if (rc != LVBA_OK) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    if (rc != LVBA_OK) return rc;
     LVBA_CUDA(cudaEventRecord(e1, ex.stream));
     LVBA_CUDA(cudaMemcpyAsync(depth + k0 * pix, d_depth.p, (size_t)(nb * pix) * sizeof(float), cudaMemcpyDeviceToHost, ex.stream));
     LVBA_CUDA(cudaStreamSynchronize(ex.stream));
@@ -123,7 +124,6 @@ int lvba_depth_render(lvba_depth_grid* g, int32_t n_images, const double* cams, 
     LVBA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     ms_dev += ms; d2h += nb * pix * 4; pairs += G.last_pairs; chunks += G.last_chunks;
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   ex.temp.release();
   if (summary) {
     *summary = g->sum;
@@ -164,11 +164,12 @@ int lvba_depth_backproject(lvba_depth_grid* g, int32_t n_images, const double* c
   lvba::DevBuf<float> d_depth, d_uv;
   lvba::DevBuf<int64_t> d_kp;
   lvba::DevBuf<uint8_t> d_valid;
+  lvba::StreamDrain drain(nullptr);
   int64_t h2d = 0, d2h = 0, pairs = 0, chunks = 0;
   float ms_dev = 0.f;
-  cudaEvent_t e0, e1;
-  LVBA_CUDA(cudaEventCreate(&e0));
-  LVBA_CUDA(cudaEventCreate(&e1));
+  lvba::EventPair ev;
+  LVBA_TRY(ev.create());
+  const cudaEvent_t e0 = ev.a, e1 = ev.b;
   int rc = LVBA_OK;
   for (int64_t k0 = 0; k0 < n_images && rc == LVBA_OK; k0 += batch) {
     const int64_t nb = std::min<int64_t>(batch, n_images - k0);
@@ -194,7 +195,6 @@ int lvba_depth_backproject(lvba_depth_grid* g, int32_t n_images, const double* c
     LVBA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     ms_dev += ms; d2h += nq * 25; pairs += G.last_pairs; chunks += G.last_chunks;
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   ex.temp.release();
   if (rc != LVBA_OK) return rc;
   if (summary) {

@@ -164,7 +164,7 @@ struct lvba_lidar_problem {
   ~lvba_lidar_problem() {
     if (h_scal) cudaFreeHost(h_scal);
     if (h_grp_scal) cudaFreeHost(h_grp_scal);
-    if (stream) cudaStreamDestroy(stream);
+    if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }     // buffers (members, destroyed after this body) must be idle when parked
   }
 };
 
@@ -280,6 +280,12 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
       for (int64_t a : mine) if (vox_ptr[a + 1] - vox_ptr[a] <= kSlots) small.push_back(a);
       mine.swap(small);
     }
+    // the batched window LM (lidar_batch_lm_impl) has no big-voxel passes: such a voxel would silently drop out of H, g and the
+    // residual sums while still counting in the AVG_THR divisor.  A window holds <= 31 poses (prepare_batch), so this cannot
+    // happen today; refuse loudly if that ever changes.
+    if (n_groups > 0 && !bigv.empty())
+      return fail(LVBA_ERR_UNSUPPORTED, "batched window BA: voxel %lld is seen from %lld poses (more than %d)", (long long)bigv[0],
+                  (long long)(vox_ptr[bigv[0] + 1] - vox_ptr[bigv[0]]), kSlots);
   }
   const int64_t Vl = (int64_t)mine.size();
   std::vector<int> l_vox_ptr(Vl + 1, 0);

@@ -194,6 +194,28 @@ struct PhaseTimers {
     for (auto e : pool) cudaEventDestroy(e);
   }
 };
+// two CUDA events that cannot leak on an early return (LVBA_TRY / LVBA_CUDA inside a timed section)
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  EventPair() = default;
+  EventPair(const EventPair&) = delete;
+  EventPair& operator=(const EventPair&) = delete;
+  int create() {
+    LVBA_CUDA(cudaEventCreate(&a));
+    LVBA_CUDA(cudaEventCreate(&b));
+    return LVBA_OK;
+  }
+  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+// Device buffers go back to the pool when they leave scope, and the pool hands them to whatever stream asks next; work
+// queued on `stream` may still be using them (an error exit between an upload and its consumer, a handle destroyed right
+// after an asynchronous call).  Declared AFTER the buffers of a scope — destruction runs in reverse order of declaration —
+// this waits for the stream first, so every buffer of the scope is idle when it is parked.
+struct StreamDrain {
+  cudaStream_t s;
+  explicit StreamDrain(cudaStream_t s_) : s(s_) {}
+  ~StreamDrain() { cudaStreamSynchronize(s); }
+};
 inline double wall_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();

@@ -36,6 +36,7 @@ inline int tracks_run(int64_t n_tracks, const int64_t* obs_ptr, const int32_t* o
   DevBuf<float> d_uv;
   DevBuf<double> d_cams, d_X, d_mean;
   DevBuf<uint8_t> d_ok;
+  StreamDrain drain(nullptr);            // NULL stream
   LVBA_TRY(d_ptr.upload(obs_ptr, (size_t)n_tracks + 1, ex.stream));
   LVBA_TRY(d_cam.upload(obs_cam, (size_t)n_obs, ex.stream));
   LVBA_TRY(d_uv.upload(obs_uv, (size_t)n_obs * 2, ex.stream));

@@ -52,7 +52,7 @@ struct lvba_visual_problem {
   lvba::VisualState cand() const { return lvba::VisualState{qc.p, tc.p, Xc.p}; }
   ~lvba_visual_problem() {
     if (h_scal) cudaFreeHost(h_scal);
-    if (stream) cudaStreamDestroy(stream);
+    if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }     // buffers (members) must be idle when parked
   }
 };
 

@@ -103,6 +103,7 @@ struct lvba_voxel_map {
   int device = 0;
   lvba_voxel_summary sum{};
   std::vector<int32_t> win_ptr;      // windowed maps: [n_windows + 1] over scans
+  ~lvba_voxel_map() { cudaStreamSynchronize(map.ex.stream); }     // members are parked in the pool after this body: they must be idle
 };
 
 namespace lvba {
@@ -160,19 +161,19 @@ inline int voxel_map_create_impl(int32_t W, const int64_t* scan_ptr, const float
   LVBA_TRY(d_scan.upload(scan_ptr, (size_t)W + 1, ex.stream, &h2d));
   LVBA_TRY(d_poses.upload(poses, (size_t)W * 12, ex.stream, &h2d));
   DevBuf<int32_t> d_win;
+  StreamDrain drain(nullptr);            // every path of this handle runs on the NULL stream
   if (n_windows > 0) {
     LVBA_TRY(d_win.upload(win_ptr, (size_t)n_windows + 1, ex.stream, &h2d));
     h->win_ptr.assign(win_ptr, win_ptr + n_windows + 1);
   }
-  cudaEvent_t e0, e1;
-  LVBA_CUDA(cudaEventCreate(&e0));
-  LVBA_CUDA(cudaEventCreate(&e1));
+  lvba::EventPair ev;
+  LVBA_TRY(ev.create());
+  const cudaEvent_t e0 = ev.a, e1 = ev.b;
   LVBA_CUDA(cudaEventRecord(e0, ex.stream));
   const auto t1 = clk::now();
   vox::VoxParams prm{o.voxel_size, {o.eigen_ratio[0], o.eigen_ratio[1], o.eigen_ratio[2], o.eigen_ratio[3]}, o.layer_limit, o.min_points};
   const int rc = h->map.build(d_xyz.p, d_scan.p, d_poses.p, W, N, prm, n_windows > 0 ? d_win.p : nullptr, n_windows);
   if (rc != LVBA_OK) {
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (h->map.error[0]) return fail(rc, "%s", h->map.error);
     return rc;
   }
@@ -180,7 +181,6 @@ inline int voxel_map_create_impl(int32_t W, const int64_t* scan_ptr, const float
   LVBA_CUDA(cudaEventSynchronize(e1));
   float ms = 0.f;
   LVBA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   ex.temp.release();
   lvba_voxel_summary& s = h->sum;
   s.n_points = N; s.n_voxels = h->map.V; s.nnz = h->map.nnz;
@@ -266,6 +266,7 @@ int lvba_voxel_map_lookup(lvba_voxel_map* m, int64_t n, const double* X, double*
   LVBA_CUDA(cudaSetDevice(m->device));
   auto& v = m->map;
   lvba::DevBuf<double> dX, dout;
+  lvba::StreamDrain drain(nullptr);
   LVBA_TRY(dX.upload(X, (size_t)n * 3, v.ex.stream));
   LVBA_TRY(dout.alloc((size_t)n * 4));
   LVBA_TRY(v.lookup(n, dX.p, dout.p));

@@ -20,6 +20,7 @@
 #include <fstream>
 #include <regex>
 #include <sstream>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -171,18 +172,44 @@ inline bool load_pcd_xyz(const std::string& file, Cloud& cloud, std::string* err
     else if (key == "DATA") { iss >> data; break; }
   }
   if (data.empty() || fields.empty()) return fail("not a PCD header");
-  if (n_points == 0) n_points = width * height;
+  // the header is untrusted input: sizes / counts / point counts are checked before they size a buffer or an offset
+  for (const PcdField& f : fields) {
+    if (f.size != 1 && f.size != 2 && f.size != 4 && f.size != 8) return fail("field '" + f.name + "': SIZE must be 1, 2, 4 or 8");
+    if (f.count < 1 || f.count > (1 << 20)) return fail("field '" + f.name + "': COUNT out of range");
+  }
+  if (n_points == 0) {
+    if (height != 0 && width > std::numeric_limits<size_t>::max() / height) return fail("WIDTH x HEIGHT overflows");
+    n_points = width * height;
+  }
   size_t rec = 0;
   int ix = -1, iy = -1, iz = -1;
   for (size_t k = 0; k < fields.size(); ++k) {
     fields[k].offset = rec;
-    rec += (size_t)fields[k].size * fields[k].count;
+    rec += (size_t)fields[k].size * (size_t)fields[k].count;
+    if (rec > (size_t(1) << 30)) return fail("record size out of range");
     if (fields[k].name == "x") ix = (int)k; else if (fields[k].name == "y") iy = (int)k; else if (fields[k].name == "z") iz = (int)k;
   }
   if (ix < 0 || iy < 0 || iz < 0) return fail("no x / y / z fields");
   for (int k : {ix, iy, iz})
-    if (fields[k].size != 4 || fields[k].type != 'F' || fields[k].count != 1) return fail("x / y / z must be float32");
-  cloud.points.resize(n_points);
+    if (fields[k].size != 4 || fields[k].type != 'F' || fields[k].count != 1 || fields[k].offset + 4 > rec) return fail("x / y / z must be float32");
+  // plausibility against what is left of the file: an ascii point needs >= 2 bytes per field, a binary one `rec` bytes, a
+  // compressed stream cannot expand more than ~256x (LZF back references)
+  {
+    const std::streampos here = fin.tellg();
+    fin.seekg(0, std::ios::end);
+    const std::streampos end = fin.tellg();
+    fin.seekg(here);
+    const size_t left = (here >= 0 && end >= here) ? (size_t)(end - here) : 0;
+    if (rec != 0 && n_points > std::numeric_limits<size_t>::max() / rec) return fail("POINTS x record size overflows");
+    const size_t need = data == "ascii" ? n_points * 2 : data == "binary" ? n_points * rec : (n_points * rec) / 256;
+    if (need > left) return fail("POINTS (" + std::to_string(n_points) + ") does not fit the file");
+  }
+  try {
+    cloud.points.resize(n_points);
+  } catch (const std::exception&) {
+    cloud.points.clear();
+    return fail("cannot allocate " + std::to_string(n_points) + " points");
+  }
   if (data == "ascii") {
     for (size_t i = 0; i < n_points; ++i) {
       if (!std::getline(fin, line)) return fail("truncated ascii data");
@@ -198,7 +225,8 @@ inline bool load_pcd_xyz(const std::string& file, Cloud& cloud, std::string* err
     return true;
   }
   if (data == "binary") {
-    std::vector<uint8_t> buf(rec * n_points);
+    std::vector<uint8_t> buf;
+    try { buf.resize(rec * n_points); } catch (const std::exception&) { return fail("cannot allocate the binary records"); }
     fin.read((char*)buf.data(), (std::streamsize)buf.size());
     if ((size_t)fin.gcount() != buf.size()) return fail("truncated binary data");
     for (size_t i = 0; i < n_points; ++i) {
@@ -212,8 +240,9 @@ inline bool load_pcd_xyz(const std::string& file, Cloud& cloud, std::string* err
   if (data == "binary_compressed") {
     uint32_t csize = 0, usize = 0;
     fin.read((char*)&csize, 4); fin.read((char*)&usize, 4);
-    if (!fin || usize != rec * n_points) return fail("bad compressed header");
-    std::vector<uint8_t> comp(csize), buf(usize);
+    if (!fin || (size_t)usize != rec * n_points) return fail("bad compressed header");
+    std::vector<uint8_t> comp, buf;
+    try { comp.resize(csize); buf.resize(usize); } catch (const std::exception&) { return fail("cannot allocate the compressed stream"); }
     fin.read((char*)comp.data(), csize);
     if ((size_t)fin.gcount() != csize) return fail("truncated compressed data");
     if (!lzf_decompress(comp.data(), csize, buf.data(), usize)) return fail("LZF stream corrupt");

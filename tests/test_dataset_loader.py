@@ -68,4 +68,22 @@ def test_loader_failures(tool, tmp_path):
     assert r.returncode == 1 and "no pcd files" in r.stderr
     (d / "1.5.pcd").write_bytes(b"VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 2\nHEIGHT 1\nPOINTS 2\nDATA binary\n" + bytes(10))
     r = subprocess.run([str(tool), "--data", str(tmp_path), "--check"], capture_output=True, text=True)
-    assert r.returncode == 0 and "truncated binary data" in r.stderr and json.loads(r.stdout.strip().splitlines()[-1])["scans"] == 0
+    assert r.returncode == 0 and "does not fit the file" in r.stderr and json.loads(r.stdout.strip().splitlines()[-1])["scans"] == 0
+
+
+@pytest.mark.parametrize("header,msg", [
+    (b"FIELDS x y z\nSIZE -4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 2\nHEIGHT 1\nPOINTS 2\nDATA binary\n", "SIZE must be"),
+    (b"FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 0 1\nWIDTH 2\nHEIGHT 1\nPOINTS 2\nDATA binary\n", "COUNT out of range"),
+    (b"FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 2\nHEIGHT 1\nPOINTS 18446744073709551615\nDATA binary\n", "overflows"),
+    (b"FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 40000000\nHEIGHT 4000\nDATA binary_compressed\n", "does not fit"),
+    (b"FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 99999999999\nHEIGHT 1\nPOINTS 99999999999\nDATA ascii\n1 2 3\n", "does not fit"),
+])
+def test_hostile_pcd_headers_are_refused_not_trusted(tool, tmp_path, header, msg):
+    """SIZE / COUNT / POINTS come from the file; a bad one must fail that file, never index outside a buffer or throw."""
+    d = tmp_path / "all_pcd_body"; d.mkdir()
+    (d / "lidar_poses.txt").write_text("0 0 0 0 0 0 0 1\n")
+    (d / "1.5.pcd").write_bytes(b"VERSION 0.7\n" + header + bytes(64))
+    r = subprocess.run([str(tool), "--data", str(tmp_path), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert msg in r.stderr, r.stderr
+    assert json.loads(r.stdout.strip().splitlines()[-1])["scans"] == 0
