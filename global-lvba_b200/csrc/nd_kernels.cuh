@@ -22,48 +22,50 @@ __global__ void __launch_bounds__(256) nd_pass_kernel(long long n, F f) {
 // Spike: Z = L^-1 E for KS right-hand sides (SpikeJob, nd_passes.h).  blockIdx.x = group of kSpikeCols right-hand sides,
 // blockIdx.y = job.
 //
-// A warp owns 2 right-hand sides for the whole job: lane = col + 2 jq; the sixteen lanes jq = 0..15 of a column split the
-// <= 30 blocks L_kj of row k among them (j = first + jq, + 16: at most two blocks per lane and row), each
-// accumulating all six components of sum_j L_kj z_j over ITS blocks (36 DFMA per block: the 6x6 block is fetched once for
-// six outputs), four xor-shuffles add the sixteen partial sums.  (Measured: the row-to-row chain of a warp is bound by
-// instruction latency, not by a pipe — fp64 18 %, one warp per scheduler — so the row is cut across many lanes and warps.)  The last 32 block rows of Z of the warp's columns live in
-// shared memory private to the warp (column height <= 30), so the only block-wide hand-shake per row is the one that
-// publishes the next row of L: its blocks are contiguous in the envelope and are staged by cp.async two rows ahead, into
-// slots of 38 doubles so that the eight blocks a warp reads at once fall into distinct banks.  Row labels
-// (first / row_start) and the entering rows of E are fetched four / one rows ahead: no global-memory latency sits on the
-// row-to-row chain.
-constexpr int kSpikeWarps = 8;
-constexpr int kSpikeCols = 2 * kSpikeWarps;      // right-hand sides per CTA
+// A warp owns 4 right-hand sides for the whole job: lane = col + 4 jq; the eight lanes jq = 0..7 of a column split the
+// <= 30 blocks L_kj of row k among them (j = first + jq + 8 it, it = 0..3), each accumulating all six components of
+// sum_j L_kj z_j over ITS blocks (36 DFMA per block: the 6x6 block is fetched once for six outputs), three xor-shuffles
+// add the eight partial sums.  The last 32 block rows of Z of the warp's columns live in shared memory private to the warp
+// (column height <= 30), so the only block-wide hand-shake per row is the one that publishes the next row of L: its blocks
+// are contiguous in the envelope and are staged by cp.async two rows ahead, into slots of 38 doubles so that the eight
+// blocks a warp reads at once fall into distinct banks.  Row labels (first / row_start) and the entering rows of E are
+// fetched four / one rows ahead: no global-memory latency sits on the row-to-row chain.
+// Measured (ncu, profiles/r02_*): the row-to-row chain of a warp is bound by instruction count and latency (fp64 pipe 18 %,
+// ~1 warp per scheduler), so the block loop is fully unrolled with predicated (zero-weight) tails and pure DFMA chains.
+constexpr int kSpikeWarps = 4;
+constexpr int kSpikeCols = 4 * kSpikeWarps;      // right-hand sides per CTA
 constexpr int kSpikeThreads = 32 * kSpikeWarps;
-constexpr int kSpikeZStride = 14;                // doubles per block row of a warp's Z window: [6][2] + 2 padding (bank spread)
+constexpr int kSpikeZStride = 28;                // doubles per block row of a warp's Z window: [6][4] + 4 padding (bank spread)
 constexpr int kSpikeBS = 38;                     // doubles per staged block of L
 constexpr int kSpikeBufs = 3;                    // rows of L in flight (cp.async, two rows ahead)
-constexpr size_t kSpikeSmem = sizeof(double) * (kSpikeBufs * 31 * kSpikeBS + kSpikeWarps * 32 * kSpikeZStride);
+constexpr size_t kSpikeSmem = sizeof(double) * (kSpikeBufs * 32 * kSpikeBS + kSpikeWarps * 33 * kSpikeZStride);
 
 __global__ void __launch_bounds__(kSpikeThreads)
 nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
   extern __shared__ __align__(16) double smem_spike[];
-  double* sRow = smem_spike;                                   // [kSpikeBufs][31][kSpikeBS] blocks of rows k, k+1, k+2
+  double* sRow = smem_spike;                                   // [kSpikeBufs][32][kSpikeBS] blocks of rows k, k+1, k+2
   const nd::SpikeJob J = jobs[blockIdx.y];
   const EnvView e = J.e;
   const int c0 = blockIdx.x * kSpikeCols;
   if (c0 >= J.KS) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int col2 = lane & 1, jq = lane >> 1;
-  const int c = c0 + warp * 2 + col2;                          // this lane's right-hand side
+  const int col4 = lane & 3, jq = lane >> 2;
+  const int c = c0 + warp * 4 + col4;                          // this lane's right-hand side
   const bool act = c < J.KS;
-  double* sZw = smem_spike + kSpikeBufs * 31 * kSpikeBS + warp * 32 * kSpikeZStride;
+  double* sZw = smem_spike + kSpikeBufs * 32 * kSpikeBS + warp * 33 * kSpikeZStride;   // [32 rows + 1 zero row][6][4]
   const int n = e.n, n_stop = J.n_stop, KS = J.KS;
+  if (lane < kSpikeZStride) sZw[32 * kSpikeZStride + lane] = 0.0;        // row 32: zeros (operand of the predicated-off blocks)
+  for (int o = tid; o < kSpikeBufs * 32 * kSpikeBS; o += kSpikeThreads) sRow[o] = 0.0;   // L slots never hold non-finite garbage
+  const int sb0 = tid / 18, sh = tid - sb0 * 18;
+  __syncthreads();
   auto stage_row = [&](int k, int f, long long rs) {           // blocks (k, f .. min(k, n_stop)-1) -> sRow[k % 3]
     if (k >= n) return;
     const int jend = k < n_stop ? k : n_stop;
     const int nb = jend > f ? jend - f : 0;
     const double* src = J.L + rs * 36;
-    double* dst = sRow + (k % kSpikeBufs) * (31 * kSpikeBS);
-    for (int o = tid; o < nb * 18; o += kSpikeThreads) {
-      const int b = o / 18, h = o - b * 18;
-      cp_async16_zfill(dst + b * kSpikeBS + 2 * h, src + 2 * o, true);
-    }
+    double* dst = sRow + (k % kSpikeBufs) * (32 * kSpikeBS);
+    if (tid < 126)                                             // thread -> (block, 16-byte piece): 7 blocks per sweep
+      for (int b = sb0; b < nb; b += 7) cp_async16_zfill(dst + b * kSpikeBS + 2 * sh, src + b * 36 + 2 * sh, true);
   };
   // labels: row k (f0), rows k+1 .. k+3 (f1..f3, rs2, rs3): fetched four rows ahead of their use in the chain
   int f0 = e.first[0];
@@ -95,24 +97,27 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
       for (int x = 0; x < 6; ++x) en[x] = 0.0;
     }
     const int jend = k < n_stop ? k : n_stop;
-    const double* rowb = sRow + (k % kSpikeBufs) * (31 * kSpikeBS);
+    const double2* rowb = reinterpret_cast<const double2*>(sRow + (k % kSpikeBufs) * (32 * kSpikeBS) + jq * kSpikeBS);
     double acc[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll 2
-    for (int j = f0 + jq; j < jend; j += 16) {
-      const double2* b2 = reinterpret_cast<const double2*>(rowb + (j - f0) * kSpikeBS);
-      const double* zj = sZw + (j & 31) * kSpikeZStride + col2;
-      const double z0 = zj[0], z1 = zj[2], z2 = zj[4], z3 = zj[6], z4 = zj[8], z5 = zj[10];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int j = f0 + jq + 8 * it;
+      // a block beyond the row's end multiplies the zero row of the window (its L slot holds stale but finite data or
+      // zeros from an earlier row; 0 x finite = 0 — slots are zero-filled once below so that they are never NaN)
+      const int zr = (j < jend) ? (j & 31) : 32;
+      const double2* b2 = rowb + it * (8 * kSpikeBS / 2);
+      const double* zj = sZw + zr * kSpikeZStride + col4;
+      const double z0 = zj[0], z1 = zj[4], z2 = zj[8], z3 = zj[12], z4 = zj[16], z5 = zj[20];
 #pragma unroll
       for (int x = 0; x < 6; ++x) {
         const double2 p0 = b2[3 * x], p1 = b2[3 * x + 1], p2 = b2[3 * x + 2];
-        double s0 = p0.x * z0, s1 = p0.y * z1;
-        s0 += p1.x * z2; s1 += p1.y * z3; s0 += p2.x * z4; s1 += p2.y * z5;
-        acc[x] += s0 + s1;
+        double a = acc[x];
+        a = fma(p0.x, z0, a); a = fma(p0.y, z1, a); a = fma(p1.x, z2, a); a = fma(p1.y, z3, a); a = fma(p2.x, z4, a); a = fma(p2.y, z5, a);
+        acc[x] = a;
       }
     }
 #pragma unroll
     for (int x = 0; x < 6; ++x) {
-      acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 2);
       acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 4);
       acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 8);
       acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 16);
@@ -122,7 +127,7 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
 #pragma unroll
       for (int x = 0; x < 6; ++x) {
         const double v = ecur[x] - acc[x];
-        sZw[(k & 31) * kSpikeZStride + x * 2 + col2] = v;      // row k-32 is no longer needed (column height <= 30)
+        sZw[(k & 31) * kSpikeZStride + x * 4 + col4] = v;      // row k-32 is no longer needed (column height <= 30)
         if (act) J.Z[((long long)k * 6 + x) * KS + c] = v;
       }
     }
