@@ -198,6 +198,7 @@ def measure_resident(pkg, torch, p, device, steps, warmup, barrier, rank):
     for _ in range(warmup):
         one_step()
     barrier()
+    pkg.comm_bytes_sent()                                            # reset the NCCL payload counter
     wall0 = time.perf_counter()
     host_s, launches = 0.0, 0
     dev_ms = {"build_A": 0.0, "solve_A": 0.0, "resid_A": 0.0, "build_B": 0.0, "solve_B": 0.0, "resid_B": 0.0}
@@ -209,12 +210,15 @@ def measure_resident(pkg, torch, p, device, steps, warmup, barrier, rank):
         launches += sa["kernel_launches"] + sb["kernel_launches"]
     barrier()
     wall = time.perf_counter() - wall0
+    nccl_bytes = pkg.comm_bytes_sent() / steps
+    ra, rb = L.owned_rows(), Vz.owned_rows()
     # full LM to the reference's caps (BASELINE configs[2]), device resident
     L.reset_lm(None); L.reset_state(); fa = L.iterate(10)
     Vz.reset_lm(None); Vz.reset_state(); fb = Vz.iterate(50)
     out = {"host_s": host_s, "wall": wall, "launches": launches, "dev_ms": {k: v / steps for k, v in dev_ms.items()},
            "full_A": fa, "full_B": fb, "lid_counts": L.counts(nonzero=True), "vis_counts": Vz.counts(),
-           "n_active": len(Vz.structure()[0]), "structA": L.structure(), "structB": Vz.structure()}
+           "n_active": len(Vz.structure()[0]), "structA": L.structure(), "structB": Vz.structure(),
+           "nccl_bytes_per_step": nccl_bytes, "owned_rows_A": ra, "owned_rows_B": rb}
     L.close(); Vz.close()
     del flush
     return out
@@ -393,6 +397,8 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config_block(cfg, p),
                 "run": {"parallelism": f"pose-block-row shards x{world}", "config_letter": cfg,
+                        "row_owned_system": bool(R["owned_rows_A"][2]), "rank0_rows_A": list(R["owned_rows_A"][:2]), "rank0_rows_B": list(R["owned_rows_B"][:2]),
+                        "nccl_payload_bytes_per_step_rank0": R["nccl_bytes_per_step"],
                         "scale_config": "N = 1: config C (headline); N > 1: config E, with n1_same_config measured in the same run"},
                 "device_ms_per_step": dm,
                 "device_ms_per_step_total_max_over_ranks": dev_ms_max / args.steps,

@@ -40,7 +40,7 @@ EXPORTS = [
     "lvba_depth_grid_create", "lvba_depth_render", "lvba_depth_backproject", "lvba_depth_grid_destroy",
     "lvba_tracks_triangulate", "lvba_tracks_mean_reproj",
     "lvba_anchor_clouds_create", "lvba_anchor_clouds_export", "lvba_anchor_clouds_destroy",
-    "lvba_env_solve",
+    "lvba_env_solve", "lvba_lidar_owned_rows", "lvba_visual_owned_rows", "lvba_comm_bytes_sent",
     "lvba_comm_unique_id", "lvba_comm_init", "lvba_comm_destroy", "lvba_comm_info", "lvba_shard_owner",
 ]
 
@@ -265,6 +265,12 @@ class LidarProblem:
     def iterate(self, n):
         s = Summary(); _chk(self._lib.lvba_lidar_iterate(self._h, C.c_int32(n), C.byref(s))); return s.as_dict()
 
+    def owned_rows(self):
+        """(row_begin, row_end, sharded): block rows of H this rank holds (multi-GPU, include/lvba_b200.h)"""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        _chk(self._lib.lvba_lidar_owned_rows(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, bool(c.value)
+
     def counts(self, nonzero=True):
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         _chk(self._lib.lvba_lidar_counts(self._h, C.byref(a), C.byref(b), C.byref(c) if nonzero else None, C.byref(d)))
@@ -389,6 +395,11 @@ class VisualProblem:
 
     def iterate(self, n):
         s = Summary(); _chk(self._lib.lvba_visual_iterate(self._h, C.c_int32(n), C.byref(s))); return s.as_dict()
+
+    def owned_rows(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        _chk(self._lib.lvba_visual_owned_rows(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, bool(c.value)
 
     def counts(self):
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
@@ -619,6 +630,12 @@ def comm_unique_id():
 def comm_init(n_ranks, rank, uid, device):
     buf = (C.c_ubyte * 128).from_buffer_copy(uid) if uid is not None else None
     _chk(load_library().lvba_comm_init(C.c_int32(n_ranks), C.c_int32(rank), buf, C.c_int32(device)))
+
+
+def comm_bytes_sent():
+    lib = load_library()
+    lib.lvba_comm_bytes_sent.restype = C.c_int64
+    return int(lib.lvba_comm_bytes_sent())
 
 
 def comm_destroy():

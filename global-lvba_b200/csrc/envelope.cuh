@@ -30,6 +30,11 @@ __global__ void env_add_diag_kernel(EnvView e, const double* __restrict__ dadd, 
     L[env_block(e, r, r) * 36 + a * 7] += dadd[i];
   }
 }
+// y += x
+__global__ void env_axpy_kernel(long long n, const double* __restrict__ x, double* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += x[i];
+}
 // diag[6r+a] = H[(r,r)][a][a]
 __global__ void env_get_diag_kernel(EnvView e, const double* __restrict__ H, double* __restrict__ diag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -4,7 +4,7 @@
 #include <cmath>
 #include <unordered_set>
 
-#include "comm.cuh"
+#include "runtime.cuh"   // (pulls comm.cuh in)
 #include "lidar.cuh"
 #include "lidar_big.h"
 #include "runtime.cuh"
@@ -268,7 +268,8 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   std::vector<int64_t> mine;
   mine.reserve((size_t)V);
   for (int64_t a = 0; a < V; ++a)
-    if (!cm.active() || shard_owner(pose_idx[vox_ptr[a]], W, cm.n_ranks) == cm.rank) mine.push_back(a);
+    if (!cm.active() || (P->solver.dist() ? P->solver.dist_owner(pose_idx[vox_ptr[a]]) : shard_owner(pose_idx[vox_ptr[a]], W, cm.n_ranks)) == cm.rank)
+      mine.push_back(a);
   if (n_groups > 0)      // windows in order: batches and their partial sums become contiguous per window
     std::stable_sort(mine.begin(), mine.end(), [&](int64_t x, int64_t y) { return pose_grp[pose_idx[vox_ptr[x]]] < pose_grp[pose_idx[vox_ptr[y]]]; });
   // voxels seen from more than kSlots poses do not fit a batch CTA: they leave `mine` and take the passes of lidar_big.h
@@ -472,7 +473,10 @@ inline int lidar_build_dev(lvba_lidar_problem* P, const double* d_poses, int slo
   LVBA_CUDA(cudaGetLastError());
   Comm& cm = comm();
   if (cm.active()) {
-    LVBA_TRY(cm.allreduce_sum(P->H.p, (size_t)P->env.nblocks * 36, s));
+    // row-owned H: only the <= max_col block rows a rank's voxels reach into its right neighbour's range travel
+    // (one ncclSend / ncclRecv pair); the full-matrix all-reduce remains for structures the chunked solver cannot cut per rank
+    if (P->solver.dist()) LVBA_TRY(P->solver.exchange_rows(P->env, P->H.p, s, &P->launches));
+    else LVBA_TRY(cm.allreduce_sum(P->H.p, (size_t)P->env.nblocks * 36, s));
     LVBA_TRY(cm.allreduce_sum(P->g.p, (size_t)P->W * 6, s));
     LVBA_TRY(cm.allreduce_sum(P->scal.p + slot, 1, s));
   }
@@ -500,6 +504,11 @@ inline int lidar_solve_dev(lvba_lidar_problem* P, double u) {
   const int n6 = 6 * P->W;
   const EnvView ev = P->env.view();
   env_get_diag_kernel<<<(n6 + 255) / 256, 256, 0, s>>>(ev, P->H.p, P->diag.p);
+  if (P->solver.dist()) {                                    // a rank holds the rows it owns: the diagonal of the others arrives by all-reduce
+    nd_pass_kernel<<<(n6 + 255) / 256, 256, 0, s>>>((long long)n6, nd::ZeroForeignF{P->diag.p, P->solver.dist_begin(), P->solver.dist_end()});
+    ++P->launches;
+    LVBA_TRY(comm().allreduce_sum(P->diag.p, (size_t)n6, s));
+  }
   lidar_rhs_kernel<<<(n6 + 255) / 256, 256, 0, s>>>(n6, P->g.p, P->diag.p, u, P->solver.z.p, P->dadd.p);
   P->launches += 2;
   LVBA_TRY(P->solver.solve(P->env, P->H.p, P->dadd.p, P->dx.p, s, &P->launches));

@@ -135,6 +135,29 @@ int lvba_comm_info(int32_t* n_ranks, int32_t* rank) {
   return LVBA_OK;
 }
 
+int64_t lvba_comm_bytes_sent(void) {
+  lvba::Comm& c = lvba::comm();
+  const int64_t b = c.bytes_sent;
+  c.bytes_sent = 0;
+  return b;
+}
+int lvba_lidar_owned_rows(lvba_lidar_problem* p, int32_t* row_begin, int32_t* row_end, int32_t* sharded) {
+  if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null problem");
+  const bool d = p->solver.dist();
+  if (row_begin) *row_begin = d ? p->solver.dist_begin() : 0;
+  if (row_end) *row_end = d ? p->solver.dist_end() : p->W;
+  if (sharded) *sharded = d ? 1 : 0;
+  return LVBA_OK;
+}
+int lvba_visual_owned_rows(lvba_visual_problem* p, int32_t* row_begin, int32_t* row_end, int32_t* sharded) {
+  if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null problem");
+  const bool d = p->n_rows > 0 && p->solver.dist();
+  if (row_begin) *row_begin = d ? p->solver.dist_begin() : 0;
+  if (row_end) *row_end = d ? p->solver.dist_end() : p->n_rows;
+  if (sharded) *sharded = d ? 1 : 0;
+  return LVBA_OK;
+}
+
 int32_t lvba_shard_owner(int32_t min_pose, int32_t n_rows, int32_t n_ranks) { return lvba::shard_owner(min_pose, n_rows, n_ranks); }
 
 }  // extern "C"

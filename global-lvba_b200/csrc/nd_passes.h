@@ -72,7 +72,9 @@ struct Tables {
   double* zs;                     // [6n] separator rows: assembled right-hand side, forward-substituted in place
   double* dinv;                   // [n][36]
   double* x;                      // [6n] solution
-  double* U; double* u; double* Z; double* E; double* T; double* W; double* w;     // pools (offsets in NodeDev)
+  double* U; double* u; double* Z; double* E; double* T; double* W; double* w;     // pools (offsets in NodeDev); u == U (one pool)
+  // multi-GPU only: writable views of H / dadd (the rows of the other ranks' rank separators arrive through the exchange region)
+  double* Hw; double* daddw;
 };
 
 LVBA_NHD void tri_dec(long long t, int& a, int& b) {
@@ -264,6 +266,67 @@ struct CorrectApplyF {
   }
 };
 
+// ---- multi-GPU exchange (nd_plan.h): every rank owns one slot of the region [U root][u root][rows of its rank separator][dadd]
+struct RegionDev {
+  int n_ranks, my_rank, slot_rows, max_col;
+  long long region0, slot, slotU, slotu, slotH;
+  const int* sep_row0;          // [n_ranks] first row of the rank separator owned by rank r (right of its range), -1: none
+  const int* sep_rows;          // [n_ranks] its width
+};
+// own rank separator -> own slot.  items = slotH + slot_rows * 6
+struct PackF {
+  Tables t; RegionDev g;
+  LVBA_NHD void operator()(int64_t e) const {
+    const int s0 = g.sep_row0[g.my_rank];
+    if (s0 < 0) return;
+    double* slot = t.U + g.region0 + (long long)g.my_rank * g.slot + g.slotU + g.slotu;
+    if (e < g.slotH) {
+      const int per_row = (g.max_col + 1) * 36;
+      const int ri = (int)(e / per_row), rem = (int)(e % per_row), b = rem / 36, el = rem % 36;
+      double v = 0.0;
+      if (ri < g.sep_rows[g.my_rank]) {
+        const int r = s0 + ri;
+        if (b <= r - t.first[r]) v = t.H[(t.row_start[r] + b) * 36 + el];
+      }
+      slot[e] = v;
+    } else {
+      const int o = (int)(e - g.slotH);
+      slot[e] = (o < g.sep_rows[g.my_rank] * 6) ? t.dadd[6 * (long long)s0 + o] : 0.0;
+    }
+  }
+};
+// the other ranks' rank separators: slot -> H, dadd.  items = n_ranks x (slotH + slot_rows * 6)
+struct UnpackF {
+  Tables t; RegionDev g;
+  LVBA_NHD void operator()(int64_t it) const {
+    const long long per = g.slotH + (long long)g.slot_rows * 6;
+    const int r_src = (int)(it / per);
+    const long long e = it % per;
+    if (r_src == g.my_rank) return;
+    const int s0 = g.sep_row0[r_src];
+    if (s0 < 0) return;
+    const double* slot = t.U + g.region0 + (long long)r_src * g.slot + g.slotU + g.slotu;
+    if (e < g.slotH) {
+      const int per_row = (g.max_col + 1) * 36;
+      const int ri = (int)(e / per_row), rem = (int)(e % per_row), b = rem / 36, el = rem % 36;
+      if (ri >= g.sep_rows[r_src]) return;
+      const int r = s0 + ri;
+      if (b <= r - t.first[r]) t.Hw[(t.row_start[r] + b) * 36 + el] = slot[e];
+    } else {
+      const int o = (int)(e - g.slotH);
+      if (o < g.sep_rows[r_src] * 6) t.daddw[6 * (long long)s0 + o] = slot[e];
+    }
+  }
+};
+// x := 0 outside the rows this rank owns (the all-reduce that follows then assembles the solution).  items = 6 n
+struct ZeroForeignF {
+  double* x; int row_begin, row_end;
+  LVBA_NHD void operator()(int64_t i) const {
+    const int r = (int)(i / 6);
+    if (r < row_begin || r >= row_end) x[i] = 0.0;
+  }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // Per-level job tables (host side; uploaded once per structure).  Dense views of the separator nodes share three small
 // arrays: first = 0, row_start[i] = i(i+1)/2, last = w - 1.
@@ -286,11 +349,12 @@ struct DenseViewArrays {
 };
 
 inline void build_level_jobs(const Plan& P, const Tables& t, const int* first_rel, const long long* rs_adj, const int* last_rel,
-                             long long nblocks, const DenseViewArrays& dv, int* status, std::vector<LevelJobs>& out) {
+                             long long nblocks, const DenseViewArrays& dv, int* status, std::vector<LevelJobs>& out, int my_rank = 0) {
   out.assign(P.levels.size(), LevelJobs());
   for (size_t lv = 0; lv < P.levels.size(); ++lv) {
     LevelJobs& J = out[lv];
-    J.ids = P.levels[lv];
+    for (int id : P.levels[lv])
+      if (P.nodes[id].owner < 0 || P.nodes[id].owner == my_rank) J.ids.push_back(id);   // own nodes + the replicated top tree
     for (int id : J.ids) {
       const Node& v = P.nodes[id];
       EnvView e;
@@ -340,14 +404,15 @@ struct LevelDev {
 //   syrk(segs, n, max_ks, max_rows)                SyrkSeg semantics
 //   backsolve(jobs, n)                             BacksolveJob semantics
 //   correct_apply(tables, ids, n_ids, stride)      CorrectApplyF over n_ids x stride rows
+// upwards through the levels this rank owns (single GPU: all of them); multi-GPU: ends with the rank's slot of the exchange
+// region filled (the SYRK / LeafFinal of the subtree root wrote U, u into it; PackF adds the rank separator's rows)
 template <class Exec>
-inline void run(Exec& ex, const Plan& P, const Tables& t, const LevelDev* lv, int n_levels, long long nblocks,
-                long long leaf_e, long long leaf_fin) {
+inline void run_up_local(Exec& ex, const Plan& P, const Tables& t, const LevelDev* lv, int n_levels, long long nblocks,
+                         long long leaf_e, long long leaf_fin, const RegionDev* reg) {
   ex.copy(t.L, t.H, nblocks * 36);
   ex.pass((long long)6 * t.n, AddDiagF{t});
   ex.zero(t.U, P.sizeU);
-  ex.zero(t.u, P.sizeu);
-  // ---- upwards: leaves
+  // ---- leaves
   const LevelDev& L0 = lv[0];
   if (L0.n_spike) ex.pass((long long)L0.n_ids * leaf_e, LeafEF{t, L0.ids, leaf_e});
   ex.factor(L0.factor, L0.n_factor, L0.max_col);
@@ -356,9 +421,11 @@ inline void run(Exec& ex, const Plan& P, const Tables& t, const LevelDev* lv, in
     ex.syrk(L0.syrk, L0.n_syrk, L0.max_ks, L0.max_rows);
   }
   ex.pass((long long)L0.n_ids * leaf_fin, LeafFinalF{t, L0.ids, leaf_fin});
-  // ---- upwards: separator levels
-  for (int l = 1; l < n_levels; ++l) {
+  // ---- separator levels of the own subtree
+  const int n_local = P.n_ranks > 1 ? P.local_levels : n_levels;
+  for (int l = 1; l < n_local; ++l) {
     const LevelDev& J = lv[l];
+    if (J.n_ids == 0) continue;
     ex.pass((long long)J.n_ids * J.asm_stride, SepAssembleF{t, J.ids, J.asm_stride});
     ex.factor_dense(J.factor, J.n_factor, J.max_col);
     if (J.n_spike) {
@@ -366,12 +433,39 @@ inline void run(Exec& ex, const Plan& P, const Tables& t, const LevelDev* lv, in
       ex.syrk(J.syrk, J.n_syrk, J.max_ks, J.max_rows);
     }
   }
-  // ---- downwards
+  if (P.n_ranks > 1 && reg) ex.pass(reg->slotH + (long long)reg->slot_rows * 6, PackF{t, *reg});
+}
+
+// multi-GPU: after the all-gather of the exchange region — the top tree upwards (every rank the same), then everything
+// downwards; single GPU: just the downward sweep
+template <class Exec>
+inline void run_top_down(Exec& ex, const Plan& P, const Tables& t, const LevelDev* lv, int n_levels, const RegionDev* reg) {
+  if (P.n_ranks > 1 && reg) {
+    ex.pass((long long)reg->n_ranks * (reg->slotH + (long long)reg->slot_rows * 6), UnpackF{t, *reg});
+    for (int l = P.local_levels; l < n_levels; ++l) {
+      const LevelDev& J = lv[l];
+      if (J.n_ids == 0) continue;
+      ex.pass((long long)J.n_ids * J.asm_stride, SepAssembleF{t, J.ids, J.asm_stride});
+      ex.factor_dense(J.factor, J.n_factor, J.max_col);
+      if (J.n_spike) {
+        ex.spike(J.spike, J.n_spike, J.max_ks, J.max_rows);
+        ex.syrk(J.syrk, J.n_syrk, J.max_ks, J.max_rows);
+      }
+    }
+  }
   for (int l = n_levels - 1; l >= 0; --l) {
     const LevelDev& J = lv[l];
+    if (J.n_ids == 0) continue;
     ex.correct_apply(t, J.ids, J.n_ids, J.corr_stride);
     ex.backsolve(J.back, J.n_back);
   }
+}
+
+template <class Exec>
+inline void run(Exec& ex, const Plan& P, const Tables& t, const LevelDev* lv, int n_levels, long long nblocks,
+                long long leaf_e, long long leaf_fin) {
+  run_up_local(ex, P, t, lv, n_levels, nblocks, leaf_e, leaf_fin, nullptr);
+  run_top_down(ex, P, t, lv, n_levels, nullptr);
 }
 
 }  // namespace nd

@@ -48,6 +48,7 @@ struct Node {
   // offsets (in doubles) into the pooled buffers
   long long offU = 0, offu = 0, offZ = 0, offE = 0, offT = 0, offW = 0, offw = 0;
   int zrows = 0;             // rows of Z: npiv + ntrail
+  int owner = 0;             // rank that eliminates this node; -1: a node of the top tree, eliminated by every rank (replicated)
 };
 
 struct Plan {
@@ -61,12 +62,25 @@ struct Plan {
   std::vector<long long> rs_adj;
   long long sizeU = 0, sizeu = 0, sizeZ = 0, sizeE = 0, sizeT = 0, sizeW = 0, sizew = 0;
   int max_ks = 0, max_zrows_leaf = 0;
+  // ---- multi-GPU: rank r eliminates the q = p / n_ranks consecutive chunks r q .. (r+1) q - 1 and the
+  //      separators between them (a complete subtree); the n_ranks - 1 separators between rank ranges ("rank separators",
+  //      rows owned by the rank on their left) form the top tree, eliminated redundantly by everybody after ONE all-gather of
+  //      a fixed-size slot per rank: the update matrix of the rank's subtree root, and the rows of its rank separator
+  int n_ranks = 1, q = 0;
+  int local_levels = 0;                        // levels 0 .. local_levels-1 hold rank-owned nodes, the rest the top tree
+  std::vector<int> rank_row_begin, rank_row_end;   // rows owned by rank r (its chunks, inner separators and its right rank separator)
+  std::vector<int> rank_root;                  // node id of the subtree root of rank r
+  long long slot = 0;                          // doubles per rank in the exchange region (at offset region0 of the U pool)
+  long long region0 = 0, slotU = 0, slotu = 0, slotH = 0;
+  int slot_rows = 0;                           // block rows of a rank separator carried in a slot (<= kMaxSepWidth)
 };
 
 // Builds the plan for `p_want` chunks; returns false (plan untouched apart from scratch) when the structure does not
 // allow it: envelope wider than the separator kernel, chunks shorter than kMinInterior, a band that vanishes at a cut.
-inline bool build_plan(int n, const int* first, const int* last, const long long* row_start, int max_col, int p_want, Plan& P) {
+inline bool build_plan(int n, const int* first, const int* last, const long long* row_start, int max_col, int p_want, Plan& P,
+                       int n_ranks = 1) {
   if (p_want < 2 || max_col > kMaxSepWidth || max_col < 1 || n < 2 * kMinInterior + max_col) return false;
+  if (n_ranks < 1 || p_want % n_ranks != 0) return false;
   // ---- cuts: equal interiors, separators as wide as the band where they start
   std::vector<int> ss(p_want + 1, 0), sw(p_want + 1, 0), i0(p_want, 0), i1(p_want, 0);
   {
@@ -90,6 +104,7 @@ inline bool build_plan(int n, const int* first, const int* last, const long long
   }
   P = Plan();
   P.n = n; P.p = p_want; P.max_col = max_col;
+  P.n_ranks = n_ranks; P.q = p_want / n_ranks;
   P.sep_start = ss; P.sep_width = sw;
   const int p = p_want;
   // ---- leaves
@@ -105,6 +120,7 @@ inline bool build_plan(int n, const int* first, const int* last, const long long
     v.nE = 0;
     if (c > 0) v.nE = std::min(v.npiv, std::max(0, last[v.r0 - 1] - v.r0 + 1));
     v.level = 0;
+    v.owner = c / P.q;
   }
   // ---- balanced tree over the separators lo..hi (1-based), children = sub-ranges or leaves
   struct Rec {
@@ -125,6 +141,7 @@ inline bool build_plan(int n, const int* first, const int* last, const long long
       v.ks = 6 * (v.wa + v.wc);
       v.nb = v.wa + v.wc;
       v.zrows = v.npiv;
+      v.owner = ((lo - 1) / P.q == hi / P.q) ? (lo - 1) / P.q : -1;      // chunks lo-1 .. hi all belong to one rank?
       return id;
     }
   } rec{P, ss, sw, p};
@@ -134,10 +151,29 @@ inline bool build_plan(int n, const int* first, const int* last, const long long
   for (const Node& v : P.nodes) max_level = std::max(max_level, v.level);
   P.levels.assign((size_t)max_level + 1, {});
   for (int id = 0; id < (int)P.nodes.size(); ++id) P.levels[P.nodes[id].level].push_back(id);
-  // ---- pooled buffers
-  for (Node& v : P.nodes) {
-    v.offU = P.sizeU; P.sizeU += (long long)v.nb * (v.nb + 1) / 2 * 36;
-    v.offu = P.sizeu; P.sizeu += (long long)v.nb * 6;
+  // ---- rank subtree roots, row ownership, levels of the top tree
+  P.rank_root.assign((size_t)n_ranks, -1);
+  P.rank_row_begin.assign((size_t)n_ranks, 0); P.rank_row_end.assign((size_t)n_ranks, n);
+  for (int id = 0; id < (int)P.nodes.size(); ++id) {
+    const Node& v = P.nodes[id];
+    if (v.owner < 0) continue;
+    if (P.rank_root[v.owner] < 0 || v.level > P.nodes[P.rank_root[v.owner]].level) P.rank_root[v.owner] = id;
+  }
+  for (int r = 0; r < n_ranks; ++r) {
+    P.rank_row_begin[r] = P.nodes[r * P.q].r0;
+    if (r > 0) P.rank_row_begin[r] = P.rank_row_end[r - 1];
+    P.rank_row_end[r] = (r + 1 < n_ranks) ? ss[(r + 1) * P.q] + sw[(r + 1) * P.q] : n;
+  }
+  P.local_levels = 1;
+  for (const Node& v : P.nodes) if (v.owner >= 0) P.local_levels = std::max(P.local_levels, v.level + 1);
+  for (const Node& v : P.nodes) if (v.owner < 0 && v.level < P.local_levels) return false;     // (cannot happen: equal subtrees)
+  // ---- pooled buffers.  U and u share one pool (offU / offu are offsets into the same array); the update matrices of the
+  //      rank roots live in the exchange region at its end: one fixed-size slot per rank = [U][u][rows of its rank separator][dadd]
+  std::vector<char> is_root(P.nodes.size(), 0);
+  if (n_ranks > 1) for (int r = 0; r < n_ranks; ++r) is_root[P.rank_root[r]] = 1;
+  for (size_t id = 0; id < P.nodes.size(); ++id) {
+    Node& v = P.nodes[id];
+    if (!is_root[id]) { v.offU = P.sizeU; P.sizeU += (long long)v.nb * (v.nb + 1) / 2 * 36; }
     v.offZ = P.sizeZ; P.sizeZ += (long long)v.zrows * 6 * v.ks;
     if (v.kind == 0) {
       v.offE = P.sizeE; P.sizeE += (long long)v.nE * 6 * v.ks;
@@ -150,6 +186,30 @@ inline bool build_plan(int n, const int* first, const int* last, const long long
     }
     P.max_ks = std::max(P.max_ks, v.ks);
   }
+  for (size_t id = 0; id < P.nodes.size(); ++id) {
+    Node& v = P.nodes[id];
+    if (!is_root[id]) { v.offu = P.sizeU; P.sizeU += (long long)v.nb * 6; }
+  }
+  if (n_ranks > 1) {
+    for (int r = 0; r < n_ranks; ++r) {
+      const Node& v = P.nodes[P.rank_root[r]];
+      P.slotU = std::max(P.slotU, (long long)v.nb * (v.nb + 1) / 2 * 36);
+      P.slotu = std::max(P.slotu, (long long)v.nb * 6);
+    }
+    P.slot_rows = 0;
+    for (int r = 0; r + 1 < n_ranks; ++r) P.slot_rows = std::max(P.slot_rows, sw[(r + 1) * P.q]);
+    P.slotH = (long long)P.slot_rows * (max_col + 1) * 36;
+    P.slot = P.slotU + P.slotu + P.slotH + (long long)P.slot_rows * 6;
+    P.slot = (P.slot + 1) & ~1LL;
+    P.region0 = (P.sizeU + 1) & ~1LL;
+    for (int r = 0; r < n_ranks; ++r) {
+      Node& v = P.nodes[P.rank_root[r]];
+      v.offU = P.region0 + (long long)r * P.slot;
+      v.offu = v.offU + P.slotU;
+    }
+    P.sizeU = P.region0 + (long long)n_ranks * P.slot;
+  }
+  P.sizeu = 0;       // (u lives in the U pool)
   // ---- leaf views: a leaf sees rows r0 .. r0+npiv+ntrail-1, columns >= r0 (the couplings to the left boundary are the
   //      spike's right-hand sides, not part of the banded factorisation)
   P.first_rel.assign((size_t)n, 0); P.last_rel.assign((size_t)n, 0); P.rs_adj.assign((size_t)n + 1, 0);
@@ -171,9 +231,10 @@ inline bool build_plan(int n, const int* first, const int* last, const long long
 }
 
 // largest number of chunks (a power of two is not required) not above p_want for which a plan exists
-inline int choose_chunks(int n, const int* first, const int* last, const long long* row_start, int max_col, int p_want, Plan& P) {
-  for (int p = p_want; p >= 2; --p)
-    if (build_plan(n, first, last, row_start, max_col, p, P)) return p;
+inline int choose_chunks(int n, const int* first, const int* last, const long long* row_start, int max_col, int p_want, Plan& P,
+                         int n_ranks = 1) {
+  for (int p = p_want - p_want % n_ranks; p >= 2 && p >= n_ranks; p -= n_ranks)
+    if (build_plan(n, first, last, row_start, max_col, p, P, n_ranks)) return p;
   return 0;
 }
 

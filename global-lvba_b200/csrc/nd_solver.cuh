@@ -21,6 +21,10 @@ struct NdDevice {
   DevBuf<int> d_first_rel, d_last_rel, d_zeros, d_last_by_w, d_ids;
   DevBuf<long long> d_rs_adj, d_tri;
   DevBuf<nd::NodeDev> d_nodes;
+  DevBuf<int> d_sep_row0, d_sep_rows;      // multi-GPU: rank separators (nd::RegionDev)
+  nd::RegionDev reg{};
+  int n_ranks = 1, my_rank = 0;
+  DevBuf<double> xchg;                     // multi-GPU: rows received from the left neighbour (exchange_rows)
   DevBuf<unsigned short> d_dense_map;      // thread -> block of nd_dense_factor_kernel
   bool dense_sep = true;                   // separators by nd_dense_factor_kernel (LVBA_ND_DENSE=0: register-window kernel)
   // numeric pools
@@ -61,14 +65,22 @@ struct NdDevice {
     return best;
   }
 
+  // n_ranks_ > 1: the plan is cut so that rank r owns p / n_ranks consecutive chunks (nd_plan.h); p_want is rounded up to a
+  // multiple of n_ranks
   int prepare(int n, const std::vector<int>& first, const std::vector<int>& last, const std::vector<long long>& row_start, int max_col,
-              int p_want, cudaStream_t s) {
+              int p_want, cudaStream_t s, int n_ranks_ = 1, int my_rank_ = 0) {
     ready = false; chunks = 0;
     drop_graph();
     key_H = key_dadd = key_x = key_z = nullptr;
+    n_ranks = n_ranks_; my_rank = my_rank_;
+    if (n_ranks > 1) p_want = std::max(n_ranks, ((p_want + n_ranks - 1) / n_ranks) * n_ranks);
     if (p_want < 2) return LVBA_OK;
-    const int p = nd::choose_chunks(n, first.data(), last.data(), row_start.data(), max_col, p_want, plan);
+    const int p = nd::choose_chunks(n, first.data(), last.data(), row_start.data(), max_col, p_want, plan, n_ranks);
     if (p < 2) return LVBA_OK;                               // structure cannot be cut: the caller keeps its other paths
+    if (n_ranks > 1) {
+      for (int r = 0; r < n_ranks; ++r)                        // the overflow of a rank's Hessian rows must stay inside the next rank
+        if (plan.rank_row_end[r] - plan.rank_row_begin[r] < max_col + 1) return LVBA_OK;
+    }
     {
       const char* g = getenv("LVBA_ND_GRAPH");
       use_graph = !(g && g[0] == '0');
@@ -98,6 +110,19 @@ struct NdDevice {
     LVBA_TRY(Z.alloc((size_t)std::max<long long>(plan.sizeZ, 1))); LVBA_TRY(E.alloc((size_t)std::max<long long>(plan.sizeE, 1)));
     LVBA_TRY(T.alloc((size_t)std::max<long long>(plan.sizeT, 1))); LVBA_TRY(W.alloc((size_t)std::max<long long>(plan.sizeW, 1)));
     LVBA_TRY(w.alloc((size_t)std::max<long long>(plan.sizew, 1)));
+    if (n_ranks > 1) {
+      std::vector<int> s0((size_t)n_ranks, -1), sr((size_t)n_ranks, 0);
+      for (int r = 0; r + 1 < n_ranks; ++r) { s0[r] = plan.sep_start[(r + 1) * plan.q]; sr[r] = plan.sep_width[(r + 1) * plan.q]; }
+      LVBA_TRY(d_sep_row0.upload(s0, s, &dummy)); LVBA_TRY(d_sep_rows.upload(sr, s, &dummy));
+      reg = nd::RegionDev{n_ranks, my_rank, plan.slot_rows, plan.max_col, plan.region0, plan.slot, plan.slotU, plan.slotu, plan.slotH,
+                          d_sep_row0.p, d_sep_rows.p};
+      long long mx = 0;
+      for (int r = 0; r < n_ranks; ++r) {
+        const int b = plan.rank_row_begin[r], e2 = std::min(n, b + max_col);
+        mx = std::max(mx, (row_start[e2] - row_start[b]) * 36);
+      }
+      LVBA_TRY(xchg.alloc((size_t)std::max<long long>(mx, 1)));
+    }
     LVBA_CUDA(cudaFuncSetAttribute(nd_spike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpikeSmem));
     LVBA_CUDA(cudaFuncSetAttribute(nd_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
     LVBA_CUDA(cudaStreamSynchronize(s));                     // local vectors
@@ -115,10 +140,12 @@ struct NdDevice {
     tab = nd::Tables{};
     tab.n = plan.n; tab.first = genv.first; tab.row_start = genv.row_start; tab.nodes = d_nodes.p;
     tab.H = H; tab.dadd = dadd; tab.L = L; tab.z = z; tab.zs = zs.p; tab.dinv = dinv; tab.x = x;
-    tab.U = U.p; tab.u = u.p; tab.Z = Z.p; tab.E = E.p; tab.T = T.p; tab.W = W.p; tab.w = w.p;
+    tab.U = U.p; tab.u = U.p; tab.Z = Z.p; tab.E = E.p; tab.T = T.p; tab.W = W.p; tab.w = w.p;
+    tab.Hw = n_ranks > 1 ? const_cast<double*>(H) : nullptr;       // multi-GPU: the other ranks' rank-separator rows are written into
+    tab.daddw = n_ranks > 1 ? const_cast<double*>(dadd) : nullptr; // the caller's H / dadd (documented at EnvSolver::solve)
     std::vector<nd::LevelJobs> jobs;
     nd::DenseViewArrays dv{d_zeros.p, d_tri.p, d_last_by_w.p};
-    nd::build_level_jobs(plan, tab, d_first_rel.p, d_rs_adj.p, d_last_rel.p, genv.nblocks, dv, status + 1, jobs);
+    nd::build_level_jobs(plan, tab, d_first_rel.p, d_rs_adj.p, d_last_rel.p, genv.nblocks, dv, status + 1, jobs, my_rank);
     std::vector<int> ids; std::vector<FactorJob> fj; std::vector<nd::SpikeJob> sj; std::vector<nd::SyrkSeg> yj; std::vector<BacksolveJob> bj;
     struct Off { size_t ids, f, s, y, b; };
     std::vector<Off> off;

@@ -322,6 +322,8 @@ inline std::vector<unsigned> build_pair_map32(int P, bool tile2, int n_threads) 
 }
 
 }  // namespace lvba
+#define LVBA_RUNTIME_PRELUDE 1
+#include "comm.cuh"
 #include "nd_solver.cuh"
 namespace lvba {
 
@@ -356,6 +358,34 @@ struct EnvSolver {
   //      systems long enough that  interior + depth x separator  pivot columns beat the two halves of the twisted solve
   NdDevice nd;
   bool nd_on = false;
+  bool shard = true;            // with an active communicator: cut the system so that its chunks are the multi-GPU unit
+  // multi-GPU, row-owned system: rank r owns the rows dist_begin() .. dist_end()-1 of H / S (its chunks, inner separators and
+  // its right rank separator); voxels / tracks are assigned to the owner of their lowest row, so a rank's contributions reach
+  // at most max_col rows into the next rank's range: exchange_rows() ships exactly those rows
+  bool dist() const { return nd_on && nd.n_ranks > 1; }
+  int dist_begin() const { return nd.plan.rank_row_begin[nd.my_rank]; }
+  int dist_end() const { return nd.plan.rank_row_end[nd.my_rank]; }
+  int dist_owner(int row) const {
+    const auto& e = nd.plan.rank_row_end;
+    return (int)(std::upper_bound(e.begin(), e.end(), row) - e.begin());
+  }
+  // adds the left neighbour's contributions to this rank's first rows and ships this rank's contributions to the right
+  // neighbour's first rows (block rows of M in envelope storage are contiguous: one send, one receive, one add kernel)
+  int exchange_rows(const Envelope& env, double* M, cudaStream_t s, int64_t* launches) {
+    if (!dist()) return LVBA_OK;
+    Comm& cm = comm();
+    const int n = env.n, ov = env.max_col;
+    const int sb = dist_end(), se = std::min(n, sb + ov);                  // rows I contributed to but do not own
+    const int rb = dist_begin(), re = std::min(n, rb + ov);                // my rows the left neighbour contributed to
+    const size_t n_send = (nd.my_rank + 1 < nd.n_ranks) ? (size_t)(env.row_start[se] - env.row_start[sb]) * 36 : 0;
+    const size_t n_recv = (nd.my_rank > 0) ? (size_t)(env.row_start[re] - env.row_start[rb]) * 36 : 0;
+    LVBA_TRY(cm.shift_right(M + env.row_start[sb] * 36, n_send, nd.xchg.p, n_recv, s));
+    if (n_recv > 0) {
+      env_axpy_kernel<<<(unsigned)((n_recv + 255) / 256), 256, 0, s>>>((long long)n_recv, nd.xchg.p, M + env.row_start[rb] * 36);
+      ++*launches;
+    }
+    return LVBA_OK;
+  }
   bool tw = false;
   int tw_m = 0, tw_send = 0, tw_bs = 0, tw_nb = 0, tw_nbstop = 0;
   Envelope env_bot, env_sep;
@@ -425,9 +455,13 @@ struct EnvSolver {
     // ---- substructured split
     nd_on = false;
     if (reg_ok && (path == LVBA_SOLVE_AUTO || path == LVBA_SOLVE_CHUNKED)) {
-      const int pw = (path == LVBA_SOLVE_CHUNKED && chunks >= 2) ? chunks : NdDevice::default_chunks(env.n, std::max(env.max_col, 1));
+      const int pw1 = (path == LVBA_SOLVE_CHUNKED && chunks >= 2) ? chunks : NdDevice::default_chunks(env.n, std::max(env.max_col, 1));
+      Comm& cm = comm();
+      const int nr = (cm.active() && shard) ? cm.n_ranks : 1;
+      const int pw = (nr > 1 && pw1 < nr) ? nr : pw1;            // one chunk per rank at least: the chunks are the multi-GPU unit
       if (pw >= 2) {
-        LVBA_TRY(nd.prepare(env.n, env.first, env.last, env.row_start, env.max_col, pw, s));
+        LVBA_TRY(nd.prepare(env.n, env.first, env.last, env.row_start, env.max_col, pw, s, nr, nr > 1 ? cm.rank : 0));
+        if (nr > 1 && !nd.ready && pw1 >= 2) LVBA_TRY(nd.prepare(env.n, env.first, env.last, env.row_start, env.max_col, pw1, s, 1, 0));   // not cuttable per rank
         nd_on = nd.ready;
         if (nd_on) LVBA_TRY(status.alloc((size_t)std::max<size_t>(4, nd.plan.nodes.size() + 1)));
       }
@@ -561,6 +595,27 @@ struct EnvSolver {
       *n_launch = ex.launches + 1;
       return ex.rc;
     };
+    if (dist()) {
+      // ---- multi-GPU: own subtree, ONE all-gather of the fixed-size slots, top tree (replicated), downwards, x assembled
+      Comm& cm = comm();
+      NdCudaExec ex;
+      ex.s = s;
+      ex.dense_map = nd.dense_sep ? nd.d_dense_map.p : nullptr;
+      ex.factor_fn = [&](int max_col, int nj, const FactorJob* jobs) { return launch_factor(pid(max_col), nj, jobs, s, &ex.launches); };
+      ex.back_fn = [&](int nj, const BacksolveJob* jobs) { launch_backsolve(nj, jobs, s); };
+      cudaMemsetAsync(status.p, 0, status.n * sizeof(int), s);
+      nd::run_up_local(ex, nd.plan, nd.tab, nd.lv.data(), (int)nd.lv.size(), env.nblocks, nd.leaf_e, nd.leaf_fin, &nd.reg);
+      LVBA_TRY(cm.allgather_inplace(nd.U.p + nd.plan.region0, (size_t)nd.plan.slot, s));
+      nd::run_top_down(ex, nd.plan, nd.tab, nd.lv.data(), (int)nd.lv.size(), &nd.reg);
+      ex.pass((long long)6 * env.n, nd::ZeroForeignF{x, dist_begin(), dist_end()});
+      LVBA_TRY(cm.allreduce_sum(x, (size_t)6 * env.n, s));
+      env_status_or_kernel<<<1, 32, 0, s>>>(status.p, (int)nd.plan.nodes.size() + 1);
+      LVBA_TRY(cm.allreduce_max_int(status.p, 1, s));
+      *launches += ex.launches + 1;
+      if (ex.rc != LVBA_OK) return ex.rc;
+      LVBA_CUDA(cudaGetLastError());
+      return LVBA_OK;
+    }
     if (nd.use_graph && !nd.graph_exec) {
       if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
         const int rc = record(&nd.launches_per_solve);
@@ -586,7 +641,9 @@ struct EnvSolver {
     return LVBA_OK;
   }
 
-  // Solves (H + diag(dadd)) x = z_in where z already holds the right-hand side.  status[0] != 0 afterwards flags a
+  // Solves (H + diag(dadd)) x = z_in where z already holds the right-hand side.  Multi-GPU (dist()): H and dadd need to be valid
+  // on the rows this rank owns only (exchange_rows() done); the rows of the other ranks' rank separators are WRITTEN into H and
+  // dadd (const is cast away for that), z must be valid everywhere, x comes back complete on every rank.  status[0] != 0 afterwards flags a
   // singular pivot (batched mode: status[g] per group).
   int solve(const Envelope& env, const double* H, const double* dadd, double* x, cudaStream_t s, int64_t* launches) {
     if (nd_on && !batch) return solve_nd(env, H, dadd, x, s, launches);

@@ -5,7 +5,7 @@
 #include <cmath>
 #include <memory>
 
-#include "comm.cuh"
+#include "runtime.cuh"   // (pulls comm.cuh in)
 #include "runtime.cuh"
 #include "visual.cuh"
 
@@ -120,7 +120,7 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   // ---- envelope of the reduced camera system over ALL valid landmarks
   std::vector<int> first_raw(std::max(P->n_rows, 1));
   for (int r = 0; r < P->n_rows; ++r) first_raw[r] = r;
-  std::vector<int> min_row(Tv_all, 0);
+  std::vector<int> min_row(Tv_all, 0), min_sys_row(Tv_all, 0);
   for (int64_t k = 0; k < Tv_all; ++k) {
     const int64_t i = valid[k];
     int m = INT32_MAX, mcam = INT32_MAX;
@@ -130,6 +130,7 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
       mcam = std::min(mcam, (int)obs_cam[q_]);
     }
     min_row[k] = (mcam == INT32_MAX) ? 0 : mcam;      // shard key: lowest camera index
+    min_sys_row[k] = (m == INT32_MAX) ? 0 : m;        // row-owned reduced system: lowest row of the landmark's clique
     if (m == INT32_MAX) continue;
     for (int64_t q_ = obs_ptr[i]; q_ < obs_ptr[i + 1]; ++q_) {
       const int r = row_of_cam[obs_cam[q_]];
@@ -146,7 +147,8 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   Comm& cm = comm();
   std::vector<int64_t> mine;
   for (int64_t k = 0; k < Tv_all; ++k)
-    if (!cm.active() || shard_owner(min_row[k], M, cm.n_ranks) == cm.rank) mine.push_back(valid[k]);
+    if (!cm.active() || (P->solver.dist() ? P->solver.dist_owner(min_sys_row[k]) : shard_owner(min_row[k], M, cm.n_ranks)) == cm.rank)
+      mine.push_back(valid[k]);
   const int64_t Tv = (int64_t)mine.size();
   P->Tv = Tv;
   std::vector<int> trk_ptr(Tv + 1, 0), trk_id(Tv);
@@ -299,7 +301,9 @@ inline int visual_linearize_solve(lvba_visual_problem* P, double radius, bool wa
   reduce_max_kernel<<<1, 256, 0, s>>>(P->batch_gmax.p, P->n_batches, P->scal.p + 1);
   P->launches += 2;
   if (cm.active()) {
-    LVBA_TRY(cm.allreduce_sum(P->S.p, (size_t)P->env.nblocks * 36, s));
+    // row-owned reduced camera system: see lidar_build_dev
+    if (P->solver.dist()) LVBA_TRY(P->solver.exchange_rows(P->env, P->S.p, s, &P->launches));
+    else LVBA_TRY(cm.allreduce_sum(P->S.p, (size_t)P->env.nblocks * 36, s));
     LVBA_TRY(cm.allreduce_sum(P->rhs.p, (size_t)P->n_rows * 6, s));
     LVBA_TRY(cm.allreduce_sum(P->cam_colsq.p, (size_t)P->n_rows * 6, s));
     LVBA_TRY(cm.allreduce_sum(P->cam_grad.p, (size_t)P->n_rows * 6, s));

@@ -404,11 +404,27 @@ int lvba_env_solve(int32_t n, const int32_t* first, const double* blocks, const 
  * Multi-GPU (one process per GPU).  The path shards by contiguous pose-block rows
  * (SURVEY.md §8e): voxel / track -> owner of its lowest pose / camera index.  Every rank
  * passes the FULL problem to *_create; after lvba_comm_init each rank keeps only its shard
- * of voxels / tracks on its GPU and H, g, S, rhs and the scalar costs are summed with
- * ncclAllReduce over NVLink.  NCCL is dlopen()ed (libnccl.so.2) on first use.
+ * of voxels / tracks on its GPU.  The pose / camera system is ROW-OWNED: the substructured
+ * solver's chunks are the multi-GPU unit, a rank builds and factorises the rows of its own
+ * chunks, only the <= band-width block rows a rank's voxels reach into its right neighbour's
+ * range travel (ncclSend/ncclRecv), the ranks' separator complements meet in one
+ * ncclAllGather (~0.8 MB per rank), the small top tree is solved redundantly and the update
+ * is assembled by an all-reduce of 48 bytes per pose; g, the right-hand sides, diagonals
+ * and the scalar costs (O(poses) data) use ncclAllReduce.  Structures the solver cannot
+ * cut per rank fall back to an all-reduce of the full matrix.  NCCL is dlopen()ed
+ * (libnccl.so.2) on first use.
  * ====================================================================================== */
 #define LVBA_NCCL_ID_BYTES 128
 int lvba_comm_unique_id(void* id_out /* LVBA_NCCL_ID_BYTES */);
+/* Row ownership of a problem created after lvba_comm_init: this rank holds the block rows [row_begin, row_end) of H (pose rows)
+ * / of the reduced camera system; *sharded = 1 when the system is row-owned and solved by the substructured solver with its
+ * chunks spread over the ranks (only <= band-width boundary rows travel between neighbours), 0 when every rank
+ * holds the all-reduced full system (one GPU, or a structure that cannot be cut per rank).  lvba_*_get_system returns the
+ * owned rows only when sharded. */
+int lvba_lidar_owned_rows(lvba_lidar_problem* p, int32_t* row_begin, int32_t* row_end, int32_t* sharded);
+int lvba_visual_owned_rows(lvba_visual_problem* p, int32_t* row_begin, int32_t* row_end, int32_t* sharded);
+/* NCCL payload (bytes handed to send-type calls by this rank) since the previous call of this function */
+int64_t lvba_comm_bytes_sent(void);
 int lvba_comm_init(int32_t n_ranks, int32_t rank, const void* id /* LVBA_NCCL_ID_BYTES */, int32_t device);
 int lvba_comm_destroy(void);
 int lvba_comm_info(int32_t* n_ranks, int32_t* rank);

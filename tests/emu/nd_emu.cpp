@@ -190,13 +190,72 @@ T* poisoned(std::vector<T>& v, size_t n) {
   return v.data();
 }
 
+// one rank's buffers and tables
+struct RankState {
+  std::vector<long long> row_start;
+  std::vector<int> last;
+  std::vector<nd::NodeDev> nodes;
+  std::vector<double> vH, vdadd, vL, vz, vzs, vd, vU, vZ, vE, vT, vW, vw, vx;
+  std::vector<int> zeros, last_by_w, status, sep_row0, sep_rows;
+  std::vector<long long> tri;
+  std::vector<nd::LevelJobs> jobs;
+  std::vector<nd::LevelDev> lv;
+  nd::Tables t{};
+  nd::RegionDev reg{};
+};
+
+static void setup_rank(RankState& S, const nd::Plan& P, int n, const int* first, const double* H, const double* dadd, const double* rhs,
+                       long long nblocks, int rank) {
+  S.nodes.clear();
+  for (const nd::Node& v : P.nodes) S.nodes.push_back(nd::to_dev(v));
+  S.vH.assign(H, H + (size_t)nblocks * 36);
+  S.vdadd.assign(dadd, dadd + (size_t)n * 6);
+  if (P.n_ranks > 1) {                                     // a rank only has the rows it owns: poison everything else
+    const double nan = std::nan("");
+    for (int r = 0; r < n; ++r)
+      if (r < P.rank_row_begin[rank] || r >= P.rank_row_end[rank]) {
+        for (long long b = S.row_start[r]; b < S.row_start[r + 1]; ++b) for (int q = 0; q < 36; ++q) S.vH[(size_t)b * 36 + q] = nan;
+        for (int q = 0; q < 6; ++q) S.vdadd[(size_t)r * 6 + q] = nan;
+      }
+  }
+  nd::Tables& t = S.t;
+  t = nd::Tables{};
+  t.n = n; t.first = first; t.row_start = S.row_start.data(); t.nodes = S.nodes.data(); t.H = S.vH.data(); t.dadd = S.vdadd.data();
+  t.Hw = S.vH.data(); t.daddw = S.vdadd.data();
+  t.L = poisoned(S.vL, (size_t)nblocks * 36);
+  t.z = poisoned(S.vz, (size_t)n * 6);
+  std::memcpy(t.z, rhs, (size_t)n * 6 * sizeof(double));
+  t.zs = poisoned(S.vzs, (size_t)n * 6);
+  t.dinv = poisoned(S.vd, (size_t)n * 36);
+  t.x = poisoned(S.vx, (size_t)n * 6);
+  t.U = poisoned(S.vU, (size_t)P.sizeU); t.u = t.U; t.Z = poisoned(S.vZ, (size_t)P.sizeZ);
+  t.E = poisoned(S.vE, (size_t)P.sizeE); t.T = poisoned(S.vT, (size_t)P.sizeT); t.W = poisoned(S.vW, (size_t)P.sizeW);
+  t.w = poisoned(S.vw, (size_t)P.sizew);
+  S.zeros.assign(32, 0); S.last_by_w.assign(32 * 32, 0); S.tri.assign(33, 0);
+  for (int i = 0; i < 33; ++i) S.tri[i] = (long long)i * (i + 1) / 2;
+  for (int w = 0; w < 32; ++w) for (int i = 0; i < 32; ++i) S.last_by_w[w * 32 + i] = w - 1;
+  nd::DenseViewArrays dv{S.zeros.data(), S.tri.data(), S.last_by_w.data()};
+  S.status.assign(P.nodes.size(), 0);
+  nd::build_level_jobs(P, t, P.first_rel.data(), P.rs_adj.data(), P.last_rel.data(), nblocks, dv, S.status.data(), S.jobs, rank);
+  S.lv.clear();
+  for (auto& J : S.jobs)
+    S.lv.push_back(nd::LevelDev{J.ids.data(), (int)J.ids.size(), J.factor.data(), (int)J.factor.size(), J.spike.data(), (int)J.spike.size(),
+                                J.syrk.data(), (int)J.syrk.size(), J.back.data(), (int)J.back.size(), J.asm_stride, J.corr_stride,
+                                J.max_ks, J.max_rows, J.max_col});
+  S.sep_row0.assign((size_t)P.n_ranks, -1); S.sep_rows.assign((size_t)P.n_ranks, 0);
+  for (int r = 0; r + 1 < P.n_ranks; ++r) { S.sep_row0[r] = P.sep_start[(r + 1) * P.q]; S.sep_rows[r] = P.sep_width[(r + 1) * P.q]; }
+  S.reg = nd::RegionDev{P.n_ranks, rank, P.slot_rows, P.max_col, P.region0, P.slot, P.slotU, P.slotu, P.slotH, S.sep_row0.data(), S.sep_rows.data()};
+}
+
 }  // namespace
 
-// Solves (H + diag(dadd)) x = rhs with p_want chunks (fewer when the structure does not allow as many).
+// Solves (H + diag(dadd)) x = rhs with p_want chunks (fewer when the structure does not allow as many) as n_ranks ranks would:
+// every rank sees only the rows it owns (the others are NaN), runs its own subtree, the exchange region is "all-gathered" by
+// copying the slots, every rank runs the top tree and its downward sweep; x is assembled from the rows each rank owns.
 // first[] must be monotone (Envelope::build); H is the envelope storage for it.  Returns the number of chunks used, 0 when
 // no plan exists.  info: [0] tree depth (levels), [1] nodes, [2] longest interior, [3] widest separator
-extern "C" int nd_emu_solve(int n, const int* first, const double* H, const double* dadd, const double* rhs, double* x,
-                            int p_want, int* info) {
+extern "C" int nd_emu_solve_ranks(int n, const int* first, const double* H, const double* dadd, const double* rhs, double* x,
+                                  int p_want, int n_ranks, int* info) {
   std::vector<long long> row_start((size_t)n + 1, 0);
   for (int r = 0; r < n; ++r) row_start[r + 1] = row_start[r] + (r - first[r] + 1);
   const long long nblocks = row_start[n];
@@ -212,37 +271,27 @@ extern "C" int nd_emu_solve(int n, const int* first, const double* H, const doub
     }
   }
   nd::Plan P;
-  const int p = nd::choose_chunks(n, first, last.data(), row_start.data(), max_col, p_want, P);
+  const int p = nd::choose_chunks(n, first, last.data(), row_start.data(), max_col, p_want, P, n_ranks);
   if (p == 0) return 0;
-  std::vector<nd::NodeDev> nodes;
-  for (const nd::Node& v : P.nodes) nodes.push_back(nd::to_dev(v));
-  std::vector<double> vL, vz, vzs, vd, vU, vu, vZ, vE, vT, vW, vw;
-  nd::Tables t{};
-  t.n = n; t.first = first; t.row_start = row_start.data(); t.nodes = nodes.data(); t.H = H; t.dadd = dadd;
-  t.L = poisoned(vL, (size_t)nblocks * 36);
-  t.z = poisoned(vz, (size_t)n * 6);
-  std::memcpy(t.z, rhs, (size_t)n * 6 * sizeof(double));
-  t.zs = poisoned(vzs, (size_t)n * 6);
-  t.dinv = poisoned(vd, (size_t)n * 36);
-  t.x = x;
-  t.U = poisoned(vU, (size_t)P.sizeU); t.u = poisoned(vu, (size_t)P.sizeu); t.Z = poisoned(vZ, (size_t)P.sizeZ);
-  t.E = poisoned(vE, (size_t)P.sizeE); t.T = poisoned(vT, (size_t)P.sizeT); t.W = poisoned(vW, (size_t)P.sizeW);
-  t.w = poisoned(vw, (size_t)P.sizew);
-  std::vector<int> zeros(32, 0), last_by_w(32 * 32, 0);
-  std::vector<long long> tri(33, 0);
-  for (int i = 0; i < 33; ++i) tri[i] = (long long)i * (i + 1) / 2;
-  for (int w = 0; w < 32; ++w) for (int i = 0; i < 32; ++i) last_by_w[w * 32 + i] = w - 1;
-  nd::DenseViewArrays dv{zeros.data(), tri.data(), last_by_w.data()};
-  std::vector<int> status(P.nodes.size(), 0);
-  std::vector<nd::LevelJobs> jobs;
-  nd::build_level_jobs(P, t, P.first_rel.data(), P.rs_adj.data(), P.last_rel.data(), nblocks, dv, status.data(), jobs);
-  std::vector<nd::LevelDev> lv;
-  for (auto& J : jobs)
-    lv.push_back(nd::LevelDev{J.ids.data(), (int)J.ids.size(), J.factor.data(), (int)J.factor.size(), J.spike.data(), (int)J.spike.size(),
-                              J.syrk.data(), (int)J.syrk.size(), J.back.data(), (int)J.back.size(), J.asm_stride, J.corr_stride,
-                              J.max_ks, J.max_rows, J.max_col});
+  std::vector<RankState> R((size_t)n_ranks);
   NdHostExec ex;
-  nd::run(ex, P, t, lv.data(), (int)lv.size(), nblocks, nd::leaf_e_stride(P), nd::leaf_final_stride(P));
+  const long long leaf_e = nd::leaf_e_stride(P), leaf_fin = nd::leaf_final_stride(P);
+  for (int r = 0; r < n_ranks; ++r) {
+    R[r].row_start = row_start;
+    setup_rank(R[r], P, n, first, H, dadd, rhs, nblocks, r);
+    nd::run_up_local(ex, P, R[r].t, R[r].lv.data(), (int)R[r].lv.size(), nblocks, leaf_e, leaf_fin, &R[r].reg);
+  }
+  if (n_ranks > 1)
+    for (int dst = 0; dst < n_ranks; ++dst)                 // the all-gather: slot r of rank r -> slot r of everybody
+      for (int src = 0; src < n_ranks; ++src)
+        if (src != dst) std::memcpy(R[dst].t.U + P.region0 + (long long)src * P.slot, R[src].t.U + P.region0 + (long long)src * P.slot, (size_t)P.slot * sizeof(double));
+  int bad = 0;
+  for (int r = 0; r < n_ranks; ++r) {
+    nd::run_top_down(ex, P, R[r].t, R[r].lv.data(), (int)R[r].lv.size(), n_ranks > 1 ? &R[r].reg : nullptr);
+    ex.pass((long long)6 * n, nd::ZeroForeignF{R[r].t.x, P.rank_row_begin[r], P.rank_row_end[r]});
+    for (int st : R[r].status) bad |= st;
+  }
+  for (int i = 0; i < 6 * n; ++i) { double s = 0.0; for (int r = 0; r < n_ranks; ++r) s += R[r].t.x[i]; x[i] = s; }   // the all-reduce
   if (info) {
     info[0] = (int)P.levels.size(); info[1] = (int)P.nodes.size();
     int mi = 0, mw = 0;
@@ -250,7 +299,10 @@ extern "C" int nd_emu_solve(int n, const int* first, const double* H, const doub
     for (int j = 1; j < P.p; ++j) mw = std::max(mw, P.sep_width[j]);
     info[2] = mi; info[3] = mw;
   }
-  int bad = 0;
-  for (int s : status) bad |= s;
   return bad ? -p : p;
+}
+
+extern "C" int nd_emu_solve(int n, const int* first, const double* H, const double* dadd, const double* rhs, double* x,
+                            int p_want, int* info) {
+  return nd_emu_solve_ranks(n, first, H, dadd, rhs, x, p_want, 1, info);
 }

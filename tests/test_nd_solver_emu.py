@@ -24,6 +24,7 @@ def emu(tmp_path_factory):
     assert r.returncode == 0, r.stderr
     lib = ctypes.CDLL(str(so))
     lib.nd_emu_solve.restype = ctypes.c_int
+    lib.nd_emu_solve_ranks.restype = ctypes.c_int
     return lib
 
 
@@ -60,12 +61,12 @@ def random_system(n, first, row_start, rng, indefinite, fill=0.8):
     return M, L
 
 
-def solve(emu, n, first, H, dadd, rhs, p):
+def solve(emu, n, first, H, dadd, rhs, p, ranks=1):
     x = np.full(6 * n, np.nan)
     info = np.zeros(4, np.int32)
     c = lambda a, t: a.ctypes.data_as(ctypes.POINTER(t))
-    used = emu.nd_emu_solve(n, c(first, ctypes.c_int), c(H, ctypes.c_double), c(dadd, ctypes.c_double), c(rhs, ctypes.c_double),
-                            c(x, ctypes.c_double), p, c(info, ctypes.c_int))
+    used = emu.nd_emu_solve_ranks(n, c(first, ctypes.c_int), c(H, ctypes.c_double), c(dadd, ctypes.c_double), c(rhs, ctypes.c_double),
+                                  c(x, ctypes.c_double), p, ranks, c(info, ctypes.c_int))
     return used, x, info
 
 
@@ -146,3 +147,20 @@ def test_refuses_what_it_cannot_cut(emu):
     if used:
         xr = np.linalg.solve(M + np.diag(dadd), rhs)
         assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max()
+
+
+@pytest.mark.parametrize("n,b,p,ranks", [(400, 12, 4, 2), (400, 12, 2, 2), (900, 30, 8, 2), (900, 30, 8, 4), (901, 20, 8, 8), (1500, 30, 16, 8),
+                                          (1203, 9, 24, 4), (640, 30, 12, 4)])
+def test_rank_sharded_solve_matches_dense(emu, n, b, p, ranks):
+    """Multi-GPU data flow without GPUs: every rank holds ONLY the rows it owns (the rest is NaN), eliminates its
+    own chunks and inner separators, the fixed-size slots (subtree-root update + rank-separator rows) are all-gathered, the top
+    tree is eliminated redundantly, x is assembled from the owned rows."""
+    rng = np.random.default_rng(7000 + n + ranks)
+    first, rs = envelope([max(0, r - b) for r in range(n)])
+    M, H = random_system(n, first, rs, rng, True)
+    dadd = rng.uniform(0.05, 0.2, 6 * n)
+    rhs = rng.normal(0, 1, 6 * n)
+    used, x, info = solve(emu, n, first, H, dadd, rhs, p, ranks)
+    assert used == p, (used, info)
+    xr = np.linalg.solve(M + np.diag(dadd), rhs)
+    assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max(), np.abs(x - xr).max()
