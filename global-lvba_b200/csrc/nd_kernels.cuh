@@ -22,26 +22,34 @@ __global__ void __launch_bounds__(256) nd_pass_kernel(long long n, F f) {
 // Spike: Z = L^-1 E for KS right-hand sides (SpikeJob, nd_passes.h).  blockIdx.x = group of kSpikeCols right-hand sides,
 // blockIdx.y = job.
 //
-// A warp owns 4 right-hand sides for the whole job: lane = col + 4 jq; the eight lanes jq = 0..7 of a column split the
-// <= 30 blocks L_kj of row k among them (j = first + jq + 8 it, it = 0..3), each accumulating all six components of
-// sum_j L_kj z_j over ITS blocks (36 DFMA per block: the 6x6 block is fetched once for six outputs), three xor-shuffles
-// add the eight partial sums.  The last 32 block rows of Z of the warp's columns live in shared memory private to the warp
-// (column height <= 30), so the only block-wide hand-shake per row is the one that publishes the next row of L: its blocks
-// are contiguous in the envelope and are staged by cp.async two rows ahead, into slots of 38 doubles so that the eight
-// blocks a warp reads at once fall into distinct banks.  Row labels (first / row_start) and the entering rows of E are
-// fetched four / one rows ahead: no global-memory latency sits on the row-to-row chain.
-// Measured (ncu, profiles/r02_*): the row-to-row chain of a warp is bound by instruction count and latency (fp64 pipe 18 %,
-// ~1 warp per scheduler), so the block loop is fully unrolled with predicated (zero-weight) tails and pure DFMA chains.
+// Row k of the recurrence is  z_k = e_k - sum_j L_kj z_j  over the <= 30 blocks of row k of L.  A warp owns kSpikeC
+// right-hand sides for the whole job and its LANE owns one block: lane s multiplies L_{k, first+s} — fetched ONCE, 18
+// LDS.128 — with the kSpikeC columns of z_{first+s} (36 DFMA per column), then a reduce-scatter over the 32 lanes (xor 16,
+// 8, 4 halve the 6 x kSpikeC partial sums, xor 2, 1 finish them: 27 shuffles for 24 values) leaves every output with one
+// lane of eight.  Measured with the previous layout (profiles/r02_spike_ablation.txt): letting every lane fetch whole
+// blocks for ONE right-hand side moved 43 kB per warp and row through the shared-memory return path (128 B/clk per SM) and
+// cost 1 750 cycles per row against 324 of FP64 pipe time; here it is 15 kB.
+// The last 32 block rows of Z of the warp's columns live in shared memory private to the warp (column height <= 30), so the
+// only block-wide hand-shake per row is the one that publishes the next row of L: its blocks are contiguous in the envelope
+// and are staged by cp.async two rows ahead, into slots of 38 doubles (consecutive lanes 48 bytes apart modulo 128:
+// conflict-free LDS.128).  Row labels (first / row_start) and the entering rows of E are fetched four / one rows ahead: no
+// global-memory latency sits on the row-to-row chain.
+constexpr int kSpikeC = 4;                       // right-hand sides per warp
 constexpr int kSpikeWarps = 4;
-constexpr int kSpikeCols = 4 * kSpikeWarps;      // right-hand sides per CTA
+constexpr int kSpikeCols = kSpikeC * kSpikeWarps;   // right-hand sides per CTA
 constexpr int kSpikeThreads = 32 * kSpikeWarps;
-constexpr int kSpikeZStride = 28;                // doubles per block row of a warp's Z window: [6][4] + 4 padding (bank spread)
+constexpr int kSpikeZStride = 26;                // doubles per block row of a warp's Z window: [6][4] + 2 (lanes 80 bytes apart modulo 128)
 constexpr int kSpikeBS = 38;                     // doubles per staged block of L
 constexpr int kSpikeBufs = 3;                    // rows of L in flight (cp.async, two rows ahead)
 constexpr size_t kSpikeSmem = sizeof(double) * (kSpikeBufs * 32 * kSpikeBS + kSpikeWarps * 33 * kSpikeZStride);
+static_assert(kSpikeC == 4, "the reduce-scatter below is written for 24 values per lane");
+
+// LVBA_SPIKE_MODE (development, results are wrong unless 0): 1 = no block products, 2 = no staging of L, 4 = no E loads / Z stores
+__device__ int g_spike_mode = 0;
 
 __global__ void __launch_bounds__(kSpikeThreads)
 nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
+  const int dbg_mode = g_spike_mode;
   extern __shared__ __align__(16) double smem_spike[];
   double* sRow = smem_spike;                                   // [kSpikeBufs][32][kSpikeBS] blocks of rows k, k+1, k+2
   const nd::SpikeJob J = jobs[blockIdx.y];
@@ -49,14 +57,18 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
   const int c0 = blockIdx.x * kSpikeCols;
   if (c0 >= J.KS) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int col4 = lane & 3, jq = lane >> 2;
-  const int c = c0 + warp * 4 + col4;                          // this lane's right-hand side
-  const bool act = c < J.KS;
+  const int cw = c0 + warp * kSpikeC;                          // first right-hand side of this warp
   double* sZw = smem_spike + kSpikeBufs * 32 * kSpikeBS + warp * 33 * kSpikeZStride;   // [32 rows + 1 zero row][6][4]
   const int n = e.n, n_stop = J.n_stop, KS = J.KS;
-  if (lane < kSpikeZStride) sZw[32 * kSpikeZStride + lane] = 0.0;        // row 32: zeros (operand of the predicated-off blocks)
+  if (lane < kSpikeZStride) sZw[32 * kSpikeZStride + lane] = 0.0;        // row 32: zeros (operand of the lanes without a block)
   for (int o = tid; o < kSpikeBufs * 32 * kSpikeBS; o += kSpikeThreads) sRow[o] = 0.0;   // L slots never hold non-finite garbage
   const int sb0 = tid / 18, sh = tid - sb0 * 18;
+  // after the reduce-scatter lane l (l & 3 == 0) holds the outputs o = 3 (l >> 2) + {0, 1, 2} of the 24 (o = x * 4 + column)
+  const int og = (lane >> 2) * 3;
+  const bool owner = (lane & 3) == 0;
+  int ox[3], oc[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) { ox[q] = (og + q) >> 2; oc[q] = (og + q) & 3; }
   __syncthreads();
   auto stage_row = [&](int k, int f, long long rs) {           // blocks (k, f .. min(k, n_stop)-1) -> sRow[k % 3]
     if (k >= n) return;
@@ -64,7 +76,7 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
     const int nb = jend > f ? jend - f : 0;
     const double* src = J.L + rs * 36;
     double* dst = sRow + (k % kSpikeBufs) * (32 * kSpikeBS);
-    if (tid < 126)                                             // thread -> (block, 16-byte piece): 7 blocks per sweep
+    if (tid < 126 && !(dbg_mode & 2))                          // thread -> (block, 16-byte piece): 7 blocks per sweep
       for (int b = sb0; b < nb; b += 7) cp_async16_zfill(dst + b * kSpikeBS + 2 * sh, src + b * 36 + 2 * sh, true);
   };
   // labels: row k (f0), rows k+1 .. k+3 (f1..f3, rs2, rs3): fetched four rows ahead of their use in the chain
@@ -72,9 +84,9 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
   int f1 = n > 1 ? e.first[1] : 0; long long rs1 = n > 1 ? e.row_start[1] : 0;
   int f2 = n > 2 ? e.first[2] : 0; long long rs2 = n > 2 ? e.row_start[2] : 0;
   int f3 = n > 3 ? e.first[3] : 0; long long rs3 = n > 3 ? e.row_start[3] : 0;
-  double en[6];                                                // E of the next row (lanes jq == 0)
+  double en[3];                                                // E of the next row: this lane's three outputs
 #pragma unroll
-  for (int x = 0; x < 6; ++x) en[x] = (jq == 0 && act && 0 < J.nE) ? J.E[((long long)x) * KS + c] : 0.0;
+  for (int q = 0; q < 3; ++q) en[q] = (owner && cw + oc[q] < KS && 0 < J.nE && !(dbg_mode & 4)) ? J.E[((long long)ox[q]) * KS + cw + oc[q]] : 0.0;
   stage_row(0, f0, e.row_start[0]);
   asm volatile("cp.async.commit_group;" ::: "memory");
   stage_row(1, f1, rs1);
@@ -86,49 +98,72 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
     asm volatile("cp.async.commit_group;" ::: "memory");
     const int f4 = (k + 4 < n) ? e.first[k + 4] : 0;
     const long long rs4 = (k + 4 < n) ? e.row_start[k + 4] : 0;
-    double ecur[6];
+    double ecur[3];
 #pragma unroll
-    for (int x = 0; x < 6; ++x) ecur[x] = en[x];
-    if (jq == 0 && act && k + 1 < J.nE) {
+    for (int q = 0; q < 3; ++q) ecur[q] = en[q];
 #pragma unroll
-      for (int x = 0; x < 6; ++x) en[x] = J.E[((long long)(k + 1) * 6 + x) * KS + c];
-    } else {
-#pragma unroll
-      for (int x = 0; x < 6; ++x) en[x] = 0.0;
-    }
+    for (int q = 0; q < 3; ++q)
+      en[q] = (owner && cw + oc[q] < KS && k + 1 < J.nE && !(dbg_mode & 4)) ? J.E[((long long)(k + 1) * 6 + ox[q]) * KS + cw + oc[q]] : 0.0;
     const int jend = k < n_stop ? k : n_stop;
-    const double2* rowb = reinterpret_cast<const double2*>(sRow + (k % kSpikeBufs) * (32 * kSpikeBS) + jq * kSpikeBS);
-    double acc[6] = {0, 0, 0, 0, 0, 0};
+    // ---- this lane's block L_{k, f0 + lane} times the four columns of z_{f0 + lane}
+    double v[24];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int j = f0 + jq + 8 * it;
-      // a block beyond the row's end multiplies the zero row of the window (its L slot holds stale but finite data or
-      // zeros from an earlier row; 0 x finite = 0 — slots are zero-filled once below so that they are never NaN)
-      const int zr = (j < jend) ? (j & 31) : 32;
-      const double2* b2 = rowb + it * (8 * kSpikeBS / 2);
-      const double* zj = sZw + zr * kSpikeZStride + col4;
-      const double z0 = zj[0], z1 = zj[4], z2 = zj[8], z3 = zj[12], z4 = zj[16], z5 = zj[20];
+    for (int o = 0; o < 24; ++o) v[o] = 0.0;
+    if (!(dbg_mode & 1)) {
+      const int j = f0 + lane;
+      const int zr = (j < jend) ? (j & 31) : 32;               // no block: the zero row (the L slot holds finite stale data)
+      const double2* b2 = reinterpret_cast<const double2*>(sRow + (k % kSpikeBufs) * (32 * kSpikeBS) + lane * kSpikeBS);
+      const double2* z2 = reinterpret_cast<const double2*>(sZw + zr * kSpikeZStride);
+      double z[24];                                            // z[y * 4 + c]
+#pragma unroll
+      for (int h = 0; h < 12; ++h) { const double2 t = z2[h]; z[2 * h] = t.x; z[2 * h + 1] = t.y; }
 #pragma unroll
       for (int x = 0; x < 6; ++x) {
         const double2 p0 = b2[3 * x], p1 = b2[3 * x + 1], p2 = b2[3 * x + 2];
-        double a = acc[x];
-        a = fma(p0.x, z0, a); a = fma(p0.y, z1, a); a = fma(p1.x, z2, a); a = fma(p1.y, z3, a); a = fma(p2.x, z4, a); a = fma(p2.y, z5, a);
-        acc[x] = a;
+        const double l[6] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double a = l[0] * z[c];
+#pragma unroll
+          for (int y = 1; y < 6; ++y) a = fma(l[y], z[y * 4 + c], a);
+          v[x * 4 + c] = a;
+        }
       }
     }
+    // ---- reduce-scatter over the 32 lanes: 24 -> 12 -> 6 -> 3 values per lane, then two plain butterflies
+    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+    double w12[12], w6[6], w3[3];
 #pragma unroll
-    for (int x = 0; x < 6; ++x) {
-      acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 4);
-      acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 8);
-      acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], 16);
+    for (int o = 0; o < 12; ++o) {
+      const double send = b16 ? v[o] : v[o + 12];
+      const double keep = b16 ? v[o + 12] : v[o];
+      w12[o] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
-    __syncwarp();                                              // every lane has read the window entries it needs of row k-32
-    if (jq == 0) {
 #pragma unroll
-      for (int x = 0; x < 6; ++x) {
-        const double v = ecur[x] - acc[x];
-        sZw[(k & 31) * kSpikeZStride + x * 4 + col4] = v;      // row k-32 is no longer needed (column height <= 30)
-        if (act) J.Z[((long long)k * 6 + x) * KS + c] = v;
+    for (int o = 0; o < 6; ++o) {
+      const double send = b8 ? w12[o] : w12[o + 6];
+      const double keep = b8 ? w12[o + 6] : w12[o];
+      w6[o] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      const double send = b4 ? w6[o] : w6[o + 3];
+      const double keep = b4 ? w6[o + 3] : w6[o];
+      w3[o] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      w3[o] += __shfl_xor_sync(0xffffffffu, w3[o], 2);
+      w3[o] += __shfl_xor_sync(0xffffffffu, w3[o], 1);
+    }
+    // lane l now holds the outputs 12 (l >> 4 & 1) + 6 (l >> 3 & 1) + 3 (l >> 2 & 1) + {0,1,2} = 3 (l >> 2) + {0,1,2}
+    __syncwarp();                                              // every lane has read the window entries it needs of row k-32
+    if (owner) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const double r = ecur[q] - w3[q];
+        sZw[(k & 31) * kSpikeZStride + ox[q] * 4 + oc[q]] = r;       // row k-32 is no longer needed (column height <= 30)
+        if (cw + oc[q] < KS && !(dbg_mode & 4)) J.Z[((long long)k * 6 + ox[q]) * KS + cw + oc[q]] = r;
       }
     }
     __syncwarp();

@@ -124,6 +124,11 @@ struct NdDevice {
       LVBA_TRY(xchg.alloc((size_t)std::max<long long>(mx, 1)));
     }
     LVBA_CUDA(cudaFuncSetAttribute(nd_spike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpikeSmem));
+    {
+      const char* m = getenv("LVBA_SPIKE_MODE");             // development only (nd_kernels.cuh)
+      const int mode = m ? atoi(m) : 0;
+      LVBA_CUDA(cudaMemcpyToSymbol(g_spike_mode, &mode, sizeof(int)));
+    }
     LVBA_CUDA(cudaFuncSetAttribute(nd_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
     LVBA_CUDA(cudaStreamSynchronize(s));                     // local vectors
     leaf_e = nd::leaf_e_stride(plan); leaf_fin = nd::leaf_final_stride(plan);
