@@ -39,6 +39,7 @@ EXPORTS = [
     "lvba_voxel_map_lookup", "lvba_voxel_map_lidar_create", "lvba_voxel_map_lidar_lm", "lvba_voxel_map_destroy",
     "lvba_depth_grid_create", "lvba_depth_render", "lvba_depth_backproject", "lvba_depth_grid_destroy",
     "lvba_tracks_triangulate", "lvba_tracks_mean_reproj",
+    "lvba_fuse_default_opts", "lvba_tracks_fuse_create", "lvba_tracks_fuse_summary", "lvba_tracks_fuse_export", "lvba_tracks_fuse_destroy",
     "lvba_anchor_clouds_create", "lvba_anchor_clouds_export", "lvba_anchor_clouds_destroy",
     "lvba_env_solve", "lvba_lidar_owned_rows", "lvba_visual_owned_rows", "lvba_comm_bytes_sent",
     "lvba_comm_unique_id", "lvba_comm_init", "lvba_comm_destroy", "lvba_comm_info", "lvba_shard_owner",
@@ -603,6 +604,45 @@ def tracks_mean_reproj(obs_ptr, obs_cam, obs_uv, cams, intr, Xw, min_count, devi
 
 
 # ------------------------------------------------------------------ B6: anchor clouds
+class FuseOpts(C.Structure):
+    _fields_ = [("obser_thr", C.c_int32), ("min_view_angle_deg", C.c_double), ("reproj_mean_thr_px", C.c_double),
+                ("depth_gate_m", C.c_double), ("device", C.c_int32)]
+
+
+class FuseSummary(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("n_keypoints", "n_components", "n_candidates", "n_tracks", "n_depth_selected", "n_tri_selected",
+                                         "n_rounds", "n_attempts", "n_obs", "n_inliers", "kernel_launches")] + [("ms_total", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def tracks_fuse(kp_ptr, kp_uv, matches, cams, intr, kp_Xw, kp_valid, obser_thr=3, min_view_angle_deg=8.0, reproj_thr=3.0, depth_gate=0.12, device=-1):
+    """lvba_tracks_fuse_create + export (boundary B7: BuildTracksAndFuse3D).  matches: (m, 4) int (img_a, kp_a, img_b, kp_b) in the
+    reference's visiting order.  Returns dict(obs_ptr, img, kp, inlier, Xw, source, mean, summary)."""
+    lib = load_library()
+    kp_ptr = np.ascontiguousarray(kp_ptr, np.int64); uv = np.ascontiguousarray(kp_uv, np.float32)
+    m = np.ascontiguousarray(matches, np.int32).reshape(-1, 4)
+    cols = [np.ascontiguousarray(m[:, q]) for q in range(4)]
+    cams = _f64(cams); intr = _f64(intr); X = _f64(kp_Xw); va = np.ascontiguousarray(kp_valid, np.uint8)
+    o = FuseOpts(); lib.lvba_fuse_default_opts(C.byref(o))
+    o.obser_thr = obser_thr; o.min_view_angle_deg = min_view_angle_deg; o.reproj_mean_thr_px = reproj_thr; o.depth_gate_m = depth_gate; o.device = device
+    h = C.c_void_p(); s = FuseSummary()
+    _chk(lib.lvba_tracks_fuse_create(C.c_int32(len(kp_ptr) - 1), _p(kp_ptr, C.c_int64), _p(uv, C.c_float), C.c_int64(len(m)),
+                                     _p(cols[0], C.c_int32), _p(cols[1], C.c_int32), _p(cols[2], C.c_int32), _p(cols[3], C.c_int32),
+                                     _p(cams, C.c_double), _p(intr, C.c_double), _p(X, C.c_double), _p(va, C.c_uint8), C.byref(o),
+                                     C.byref(h), C.byref(s)))
+    try:
+        n, no = s.n_tracks, s.n_obs
+        obs_ptr = np.zeros(n + 1, np.int64); img = np.zeros(no, np.int32); kp = np.zeros(no, np.int32); inl = np.zeros(no, np.uint8)
+        Xw = np.zeros((n, 3)); src = np.zeros(n, np.uint8); mean = np.zeros(n)
+        _chk(lib.lvba_tracks_fuse_export(h, _p(obs_ptr, C.c_int64), _p(img, C.c_int32), _p(kp, C.c_int32), _p(inl, C.c_uint8),
+                                         _p(Xw, C.c_double), _p(src, C.c_uint8), _p(mean, C.c_double)))
+    finally:
+        lib.lvba_tracks_fuse_destroy(h)
+    return dict(obs_ptr=obs_ptr, img=img, kp=kp, inlier=inl, Xw=Xw, source=src, mean=mean, summary=s.as_dict())
+
+
 def anchor_clouds(scans, rel_poses, win_ptr, leaf=0.1, device=-1):
     """Tail of runWindowBA's window loop (lvba_system.cpp:284-301): returns [one (n_w, 3) float32 cloud per window]."""
     lib = load_library()

@@ -8,6 +8,7 @@
 #include "depth_api.cuh"
 #include "track_api.cuh"
 #include "anchor_api.cuh"
+#include "fuse_api.cuh"
 
 extern "C" {
 

@@ -32,8 +32,10 @@ __global__ void __launch_bounds__(256) nd_pass_kernel(long long n, F f) {
 // The last 32 block rows of Z of the warp's columns live in shared memory private to the warp (column height <= 30), so the
 // only block-wide hand-shake per row is the one that publishes the next row of L: its blocks are contiguous in the envelope
 // and are staged by cp.async two rows ahead, into slots of 38 doubles (consecutive lanes 48 bytes apart modulo 128:
-// conflict-free LDS.128).  Row labels (first / row_start) and the entering rows of E are fetched four / one rows ahead: no
-// global-memory latency sits on the row-to-row chain.
+// conflict-free LDS.128).  No global-memory latency sits on the row-to-row chain: the entering row of E rides in the same
+// cp.async group as the row of L, and the row labels (first / row_start) sit in a 64-entry shared-memory ring refilled 32 rows
+// at a time (measured: a label or E value loaded into a register in row k and consumed in row k+1 exposed an L2 round trip per
+// row — the loop skeleton alone cost 1 200 cycles per row, profiles/r02_spike_ablation.txt).
 constexpr int kSpikeC = 4;                       // right-hand sides per warp
 constexpr int kSpikeWarps = 4;
 constexpr int kSpikeCols = kSpikeC * kSpikeWarps;   // right-hand sides per CTA
@@ -41,7 +43,7 @@ constexpr int kSpikeThreads = 32 * kSpikeWarps;
 constexpr int kSpikeZStride = 26;                // doubles per block row of a warp's Z window: [6][4] + 2 (lanes 80 bytes apart modulo 128)
 constexpr int kSpikeBS = 38;                     // doubles per staged block of L
 constexpr int kSpikeBufs = 3;                    // rows of L in flight (cp.async, two rows ahead)
-constexpr size_t kSpikeSmem = sizeof(double) * (kSpikeBufs * 32 * kSpikeBS + kSpikeWarps * 33 * kSpikeZStride);
+constexpr size_t kSpikeSmem = sizeof(double) * (kSpikeBufs * 32 * kSpikeBS + kSpikeWarps * 33 * kSpikeZStride + kSpikeBufs * kSpikeWarps * 24 + 64) + sizeof(int) * 64;
 static_assert(kSpikeC == 4, "the reduce-scatter below is written for 24 values per lane");
 
 // LVBA_SPIKE_MODE (development, results are wrong unless 0): 1 = no block products, 2 = no staging of L, 4 = no E loads / Z stores
@@ -59,51 +61,50 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cw = c0 + warp * kSpikeC;                          // first right-hand side of this warp
   double* sZw = smem_spike + kSpikeBufs * 32 * kSpikeBS + warp * 33 * kSpikeZStride;   // [32 rows + 1 zero row][6][4]
+  double* sE = smem_spike + kSpikeBufs * 32 * kSpikeBS + kSpikeWarps * 33 * kSpikeZStride;   // [kSpikeBufs][warps][6][4] entering rows of E
+  long long* sLabRS = reinterpret_cast<long long*>(sE + kSpikeBufs * kSpikeWarps * 24);  // [64] row_start of row r at r & 63
+  int* sLabF = reinterpret_cast<int*>(sLabRS + 64);                                       // [64] first column of row r at r & 63
   const int n = e.n, n_stop = J.n_stop, KS = J.KS;
   if (lane < kSpikeZStride) sZw[32 * kSpikeZStride + lane] = 0.0;        // row 32: zeros (operand of the lanes without a block)
   for (int o = tid; o < kSpikeBufs * 32 * kSpikeBS; o += kSpikeThreads) sRow[o] = 0.0;   // L slots never hold non-finite garbage
+  for (int r = tid; r < 64; r += kSpikeThreads) { sLabF[r] = (r < n) ? e.first[r] : 0; sLabRS[r] = (r < n) ? e.row_start[r] : 0; }
   const int sb0 = tid / 18, sh = tid - sb0 * 18;
   // after the reduce-scatter lane l (l & 3 == 0) holds the outputs o = 3 (l >> 2) + {0, 1, 2} of the 24 (o = x * 4 + column)
   const int og = (lane >> 2) * 3;
   const bool owner = (lane & 3) == 0;
-  int ox[3], oc[3];
-#pragma unroll
-  for (int q = 0; q < 3; ++q) { ox[q] = (og + q) >> 2; oc[q] = (og + q) & 3; }
   __syncthreads();
-  auto stage_row = [&](int k, int f, long long rs) {           // blocks (k, f .. min(k, n_stop)-1) -> sRow[k % 3]
+  // row k: blocks (k, f .. min(k, n_stop)-1) and the entering row of E of every warp -> buffers k % 3 (one cp.async group)
+  auto stage_row = [&](int k) {
     if (k >= n) return;
+    const int f = sLabF[k & 63];
+    const long long rs = sLabRS[k & 63];
     const int jend = k < n_stop ? k : n_stop;
     const int nb = jend > f ? jend - f : 0;
     const double* src = J.L + rs * 36;
     double* dst = sRow + (k % kSpikeBufs) * (32 * kSpikeBS);
     if (tid < 126 && !(dbg_mode & 2))                          // thread -> (block, 16-byte piece): 7 blocks per sweep
       for (int b = sb0; b < nb; b += 7) cp_async16_zfill(dst + b * kSpikeBS + 2 * sh, src + b * 36 + 2 * sh, true);
+    if (lane < 12) {                                           // E[k][x][cw .. cw+3]: two 16-byte pieces per component
+      const int x = lane >> 1, h = lane & 1;
+      const bool ok = k < J.nE && cw + 2 * h < KS && !(dbg_mode & 4);      // (KS is even: a piece is inside or outside as a whole)
+      cp_async16_zfill(sE + ((k % kSpikeBufs) * kSpikeWarps + warp) * 24 + x * 4 + 2 * h,
+                       ok ? J.E + ((long long)k * 6 + x) * KS + cw + 2 * h : J.L, ok);
+    }
   };
-  // labels: row k (f0), rows k+1 .. k+3 (f1..f3, rs2, rs3): fetched four rows ahead of their use in the chain
-  int f0 = e.first[0];
-  int f1 = n > 1 ? e.first[1] : 0; long long rs1 = n > 1 ? e.row_start[1] : 0;
-  int f2 = n > 2 ? e.first[2] : 0; long long rs2 = n > 2 ? e.row_start[2] : 0;
-  int f3 = n > 3 ? e.first[3] : 0; long long rs3 = n > 3 ? e.row_start[3] : 0;
-  double en[3];                                                // E of the next row: this lane's three outputs
-#pragma unroll
-  for (int q = 0; q < 3; ++q) en[q] = (owner && cw + oc[q] < KS && 0 < J.nE && !(dbg_mode & 4)) ? J.E[((long long)ox[q]) * KS + cw + oc[q]] : 0.0;
-  stage_row(0, f0, e.row_start[0]);
+  stage_row(0);
   asm volatile("cp.async.commit_group;" ::: "memory");
-  stage_row(1, f1, rs1);
+  stage_row(1);
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int k = 0; k < n; ++k) {
     asm volatile("cp.async.wait_group 1;" ::: "memory");       // everything but the newest group (row k+1): row k has landed
     __syncthreads();                                           // row k of L staged by everybody; everybody is done with row k-1
-    stage_row(k + 2, f2, rs2);                                 // into the buffer row k-1 used
+    if ((k & 31) == 0 && k > 0 && warp == 0) {                 // labels of rows k+32 .. k+63 (their ring slots held rows k-32 .. k-1)
+      const int r = k + 32 + lane;
+      if (r < n) { sLabF[r & 63] = e.first[r]; sLabRS[r & 63] = e.row_start[r]; }
+    }
+    stage_row(k + 2);                                          // into the buffers row k-1 used
     asm volatile("cp.async.commit_group;" ::: "memory");
-    const int f4 = (k + 4 < n) ? e.first[k + 4] : 0;
-    const long long rs4 = (k + 4 < n) ? e.row_start[k + 4] : 0;
-    double ecur[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) ecur[q] = en[q];
-#pragma unroll
-    for (int q = 0; q < 3; ++q)
-      en[q] = (owner && cw + oc[q] < KS && k + 1 < J.nE && !(dbg_mode & 4)) ? J.E[((long long)(k + 1) * 6 + ox[q]) * KS + cw + oc[q]] : 0.0;
+    const int f0 = sLabF[k & 63];
     const int jend = k < n_stop ? k : n_stop;
     // ---- this lane's block L_{k, f0 + lane} times the four columns of z_{f0 + lane}
     double v[24];
@@ -159,15 +160,16 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
     // lane l now holds the outputs 12 (l >> 4 & 1) + 6 (l >> 3 & 1) + 3 (l >> 2 & 1) + {0,1,2} = 3 (l >> 2) + {0,1,2}
     __syncwarp();                                              // every lane has read the window entries it needs of row k-32
     if (owner) {
+      const double* ek = sE + ((k % kSpikeBufs) * kSpikeWarps + warp) * 24;
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        const double r = ecur[q] - w3[q];
-        sZw[(k & 31) * kSpikeZStride + ox[q] * 4 + oc[q]] = r;       // row k-32 is no longer needed (column height <= 30)
-        if (cw + oc[q] < KS && !(dbg_mode & 4)) J.Z[((long long)k * 6 + ox[q]) * KS + cw + oc[q]] = r;
+        const int o = og + q, ox = o >> 2, oc = o & 3;
+        const double r = ek[o] - w3[q];
+        sZw[(k & 31) * kSpikeZStride + o] = r;                 // row k-32 is no longer needed (column height <= 30)
+        if (cw + oc < KS && !(dbg_mode & 4)) J.Z[((long long)k * 6 + ox) * KS + cw + oc] = r;
       }
     }
     __syncwarp();
-    f0 = f1; f1 = f2; f2 = f3; rs2 = rs3; f3 = f4; rs3 = rs4;
   }
 }
 

@@ -45,6 +45,11 @@ struct CudaExec {
     return LVBA_OK;
   }
   template <class T>
+  int put(T* dev, const T* host, size_t n) {       // host -> device; the host range must stay alive until the next sync()
+    if (n) LVBA_CUDA(cudaMemcpyAsync(dev, host, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+    return LVBA_OK;
+  }
+  template <class T>
   int fetch(T* host, const T* dev, size_t n) {
     if (n) LVBA_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, stream));
     LVBA_CUDA(cudaStreamSynchronize(stream));

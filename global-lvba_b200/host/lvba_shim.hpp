@@ -18,6 +18,8 @@
 //                                                    merged + down-sampled anchor clouds (boundary B6)
 //   lvba_b200::DepthRenderer                         replaces buildGridMapFromOptimized + generateDepthWithVoxel
 //                                                    (src/lvba_system.cpp:1266-1338, 835-919)
+//   lvba_b200::build_tracks_and_fuse_3d              replaces BuildTracksAndFuse3D (src/lvba_system.cpp:921-1263): matches +
+//                                                    keypoints + depth candidates -> tracks_ (boundary B7)
 //
 // Same names, argument meaning and error behaviour as the reference: void-like use (the reference ignores
 // solver failure), state written back only on success, size mismatches throw std::runtime_error like
@@ -28,6 +30,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "lvba_b200.h"
@@ -448,6 +451,73 @@ inline int solve_visual(std::vector<std::array<double, 4>>& qs, std::vector<std:
   return lvba_visual_lm(M, T, qs.empty() ? nullptr : qs[0].data(), ts.empty() ? nullptr : ts[0].data(),
                         Xs.empty() ? nullptr : Xs[0].data(), plane_nd.data(), obs_ptr.data(), obs_cam.data(), obs_uv.data(), intr,
                         sigma_px, sigma_plane, /*fixed_cam=*/0, opts, summary);
+}
+
+// ---- B7: BuildTracksAndFuse3D (src/lvba_system.cpp:921-1263).  all_keypoints[i][k].x/.y, all_matches[pairIndex(i,j,N)] =
+//      vector<pair<int,int>> in the reference's upper-triangular pair layout (utils.hpp pairIndex), Rcw / tcw per image,
+//      kp_Xw / kp_valid = the depth candidate of every keypoint in (image, keypoint) order (DepthRenderer::backproject ==
+//      the loop at :1020-1038).  Fills tracks with the reference's Track fields: observations (image, keypoint) of the whole
+//      component, inlier_indices, Xw_fused.  Track order, observation order and inlier sets are those of the reference up to
+//      the iteration order of its unordered_maps (include/lvba_b200.h).
+struct FusedTrack {
+  std::vector<std::pair<int, int>> observations;
+  std::vector<int> inlier_indices;
+  std::array<double, 3> Xw_fused;
+  int source;                    // 1 depth candidate, 2 triangulation
+  double mean_reproj;
+};
+template <class KeypointImages, class MatchTable, class RotVec, class VecVec>
+inline int build_tracks_and_fuse_3d(const KeypointImages& all_keypoints, const MatchTable& all_matches, const RotVec& Rcw_all, const VecVec& tcw_all,
+                                    double fx, double fy, double cx, double cy, double d0, double d1, double d2, double d3,
+                                    const std::vector<double>& kp_Xw, const std::vector<uint8_t>& kp_valid, std::vector<FusedTrack>& tracks,
+                                    const lvba_fuse_opts* opts = nullptr, lvba_fuse_summary* summary = nullptr) {
+  const int N = (int)all_keypoints.size();
+  if ((int)Rcw_all.size() != N || (int)tcw_all.size() != N) throw std::runtime_error("lvba_b200::build_tracks_and_fuse_3d: pose / image count mismatch");
+  std::vector<int64_t> kp_ptr((size_t)N + 1, 0);
+  for (int i = 0; i < N; ++i) kp_ptr[i + 1] = kp_ptr[i] + (int64_t)all_keypoints[i].size();
+  const int64_t n_kp = kp_ptr[N];
+  if ((int64_t)kp_valid.size() != n_kp || (int64_t)kp_Xw.size() != 3 * n_kp) throw std::runtime_error("lvba_b200::build_tracks_and_fuse_3d: depth candidate size mismatch");
+  std::vector<float> uv((size_t)n_kp * 2);
+  for (int i = 0; i < N; ++i)
+    for (size_t k = 0; k < all_keypoints[i].size(); ++k) { uv[2 * (kp_ptr[i] + k)] = all_keypoints[i][k].x; uv[2 * (kp_ptr[i] + k) + 1] = all_keypoints[i][k].y; }
+  std::vector<int32_t> ma, ka, mb, kb;
+  for (int i = 0; i < N - 1; ++i)                                   // the visiting order of :937-953
+    for (int j = i + 1; j < N; ++j) {
+      const size_t idx = (size_t)i * (size_t)N - (size_t)i * ((size_t)i + 1) / 2 + (size_t)(j - i - 1);      // pairIndex(i, j, N)
+      if (idx >= all_matches.size()) continue;
+      for (const auto& m : all_matches[idx]) { ma.push_back(i); ka.push_back(m.first); mb.push_back(j); kb.push_back(m.second); }
+    }
+  std::vector<double> cams((size_t)N * 12);
+  for (int i = 0; i < N; ++i) {
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) cams[12 * i + 3 * r + c] = Rcw_all[i](r, c);
+    for (int r = 0; r < 3; ++r) cams[12 * i + 9 + r] = tcw_all[i](r);
+  }
+  const double intr[8] = {fx, fy, cx, cy, d0, d1, d2, d3};
+  lvba_track_set* h = nullptr;
+  lvba_fuse_summary s;
+  const int rc = lvba_tracks_fuse_create(N, kp_ptr.data(), uv.data(), (int64_t)ma.size(), ma.data(), ka.data(), mb.data(), kb.data(), cams.data(),
+                                         intr, kp_Xw.data(), kp_valid.data(), opts, &h, &s);
+  if (rc != LVBA_OK) return rc;
+  std::vector<int64_t> obs_ptr((size_t)s.n_tracks + 1);
+  std::vector<int32_t> img((size_t)s.n_obs), kp((size_t)s.n_obs);
+  std::vector<uint8_t> inl((size_t)s.n_obs), src((size_t)s.n_tracks);
+  std::vector<double> Xw((size_t)s.n_tracks * 3), mean((size_t)s.n_tracks);
+  const int rc2 = lvba_tracks_fuse_export(h, obs_ptr.data(), img.data(), kp.data(), inl.data(), Xw.data(), src.data(), mean.data());
+  lvba_tracks_fuse_destroy(h);
+  if (rc2 != LVBA_OK) return rc2;
+  tracks.clear();
+  tracks.resize((size_t)s.n_tracks);
+  for (int64_t t = 0; t < s.n_tracks; ++t) {
+    FusedTrack& tr = tracks[(size_t)t];
+    for (int64_t o = obs_ptr[t]; o < obs_ptr[t + 1]; ++o) {
+      tr.observations.emplace_back(img[(size_t)o], kp[(size_t)o]);
+      if (inl[(size_t)o]) tr.inlier_indices.push_back((int)(o - obs_ptr[t]));
+    }
+    tr.Xw_fused = {Xw[3 * t], Xw[3 * t + 1], Xw[3 * t + 2]};
+    tr.source = src[(size_t)t]; tr.mean_reproj = mean[(size_t)t];
+  }
+  if (summary) *summary = s;
+  return LVBA_OK;
 }
 
 }  // namespace lvba_b200

@@ -377,6 +377,48 @@ int lvba_tracks_mean_reproj(int64_t n_tracks, const int64_t* obs_ptr, const int3
                             double* mean_reproj, int32_t* count, uint8_t* ok);
 
 /* ======================================================================================
+ * Boundary B7: track fusion — LvbaSystem::BuildTracksAndFuse3D
+ * (reference src/lvba_system.cpp:921-1263) as one call.  In: the keypoints of all images
+ * (CSR), the pairwise matches as four parallel arrays in the order the reference visits them
+ * (image pairs (i < j) by ascending i then j, the matches of a pair in stored order), camera
+ * poses [n_images][12] = Rcw row-major then tcw, intrinsics fx fy cx cy k1 k2 p1 p2, and the
+ * depth-fused 3-D candidate of every keypoint with its validity flag (what
+ * lvba_depth_backproject returns: the loop at :1020-1038).  Out: the tracks in the order the
+ * reference appends them; Track::observations = the whole connected component in BFS order,
+ * Track::inlier_indices as one flag per observation, Xw_fused, which candidate was chosen
+ * (1 depth, 2 triangulation) and its mean reprojection error.  The (image, keypoint, inlier)
+ * lists are the observation CSR of lvba_visual_lm once the inliers are kept (:1610-1617).
+ * Where the reference iterates std::unordered_map<int,int> (unspecified order: the greedy
+ * view-angle filter depends on it) the images of a component are visited in ascending id.
+ * ====================================================================================== */
+typedef struct lvba_fuse_opts {
+  int32_t obser_thr;              /* minimum members / images / survivors (lvba_system.h:139: 3) */
+  double min_view_angle_deg;      /* track_fusion/min_view_angle (8) */
+  double reproj_mean_thr_px;      /* track_fusion/reproj_mean_thr (3) */
+  double depth_gate_m;            /* distance to the anchor's depth point (0.12, :1050) */
+  int32_t device;                 /* -1: current */
+} lvba_fuse_opts;
+typedef struct lvba_fuse_summary {
+  int64_t n_keypoints, n_components, n_candidates, n_tracks, n_depth_selected, n_tri_selected;
+  int64_t n_rounds, n_attempts;   /* retries: a failed component is tried again from its next keypoint as BFS seed (:1199) */
+  int64_t n_obs, n_inliers;       /* totals over the tracks: sizes of the export arrays */
+  int64_t kernel_launches;
+  double ms_total;
+} lvba_fuse_summary;
+typedef struct lvba_track_set lvba_track_set;
+void lvba_fuse_default_opts(lvba_fuse_opts* o);
+int lvba_tracks_fuse_create(int32_t n_images, const int64_t* kp_ptr /* [n_images+1] */, const float* kp_uv /* [n_kp][2] */,
+                            int64_t n_matches, const int32_t* match_img_a, const int32_t* match_kp_a, const int32_t* match_img_b,
+                            const int32_t* match_kp_b, const double* cams, const double intr[8], const double* kp_Xw /* [n_kp][3] */,
+                            const uint8_t* kp_valid /* [n_kp] */, const lvba_fuse_opts* opts /* NULL: defaults */,
+                            lvba_track_set** out, lvba_fuse_summary* summary /* may be NULL */);
+int lvba_tracks_fuse_summary(const lvba_track_set* s, lvba_fuse_summary* summary);
+/* arrays sized from the summary: obs_ptr [n_tracks+1], obs_* [n_obs], Xw [n_tracks][3], source / mean_reproj [n_tracks]; any but obs_ptr may be NULL */
+int lvba_tracks_fuse_export(lvba_track_set* s, int64_t* obs_ptr, int32_t* obs_img, int32_t* obs_kp, uint8_t* obs_inlier, double* Xw,
+                            uint8_t* source, double* mean_reproj);
+int lvba_tracks_fuse_destroy(lvba_track_set* s);
+
+/* ======================================================================================
  * The block LDL^T of the pose / camera system on its own (diagnostics, solver tests and the
  * solver line of bench.py).  Solves (A + diag(dadd)) x = rhs for a symmetric matrix of 6x6
  * blocks stored as a block envelope: row r keeps the blocks of columns first[r]..r

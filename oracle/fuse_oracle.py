@@ -1,0 +1,136 @@
+"""CPU restatement of the reference's track fusion — TEST INFRASTRUCTURE (only tests/ may import it):
+    LvbaSystem::BuildTracksAndFuse3D   src/lvba_system.cpp:921-1263
+with ComputeMeanReproj (:8-50) and TriangulateTrackDLT (:52-111) from oracle/track_oracle.py.
+
+Literal where the reference is defined: adjacency in push_back order (:937-953), BFS with a FIFO queue from every unvisited
+keypoint in (image, keypoint) order (:964-988), size / image-count gates (:989, :1001), first observation per image in member
+order (:996-1000), depth candidate (:1016-1103), triangulation candidate (:1106-1159), choice (:1161-1199), release of a failed
+component so that the scan tries it again from its next keypoint (:1199, :1203).
+The reference iterates std::unordered_map<int,int> (image -> member) in three places; that order is unspecified.  Here — and in
+global-lvba_b200/csrc/fuse_pipeline.h — the images are visited in ASCENDING id.  Parity unpinned: the reference cannot be built
+here and ships no fixtures for this stage."""
+from __future__ import annotations
+
+from collections import deque
+
+import numpy as np
+
+from oracle import track_oracle as trk
+
+
+def fuse(kp_ptr, kp_uv, matches, cams, intr, kp_Xw, kp_valid, obser_thr=3, min_view_angle_deg=8.0, reproj_thr=3.0, depth_gate=0.12):
+    """matches: (m, 4) int array (img_a, kp_a, img_b, kp_b) in the reference's visiting order.
+    Returns a list of tracks {seed, obs (k,2), inlier (k,) bool, Xw, mean, source} in the reference's track order."""
+    N = len(kp_ptr) - 1
+    n_kp = int(kp_ptr[-1])
+    img_of = np.repeat(np.arange(N), np.diff(kp_ptr))
+    adj = [[] for _ in range(n_kp)]
+    for ia, ka, ib, kb in np.asarray(matches, np.int64).reshape(-1, 4):
+        if not (0 <= ia < N and 0 <= ib < N):
+            continue
+        if not (0 <= ka < kp_ptr[ia + 1] - kp_ptr[ia] and 0 <= kb < kp_ptr[ib + 1] - kp_ptr[ib]):
+            continue
+        a, b = int(kp_ptr[ia] + ka), int(kp_ptr[ib] + kb)
+        adj[a].append(b); adj[b].append(a)
+    cos_min = np.cos(min_view_angle_deg * np.pi / 180.0)
+    state = np.full(n_kp, -1, np.int64)          # obs_to_track
+    tracks = []
+    cams = np.asarray(cams, np.float64).reshape(-1, 12)
+
+    def centre(cam):
+        R = cams[cam, :9].reshape(3, 3); t = cams[cam, 9:]
+        return -R.T @ t
+
+    def view_filter(cand, point_of):
+        """cand: member positions in ascending image order; greedy filter (:1069-1095 / :1124-1150)"""
+        kept, dirs = [], []
+        for t in cand:
+            cam = int(img_of[comp[t]])
+            d = point_of(t) - centre(cam)
+            nrm = np.linalg.norm(d)
+            if nrm < 1e-6:
+                continue
+            d = d / nrm
+            min_dot = min([float(d @ q) for q in dirs], default=1.0)
+            if not dirs or min_dot <= cos_min:
+                kept.append(t); dirs.append(d)
+        return kept
+
+    def sel_arrays(sel):
+        g = [comp[t] for t in sel]
+        return cams[[int(img_of[x]) for x in g]], np.asarray(kp_uv, np.float32).reshape(-1, 2)[g]
+
+    for seed in range(n_kp):
+        if state[seed] != -1:
+            continue
+        comp = []
+        q = deque([seed]); state[seed] = -2
+        while q:
+            cur = q.popleft(); comp.append(cur)
+            for nb in adj[cur]:
+                if state[nb] == -1:
+                    state[nb] = -2; q.append(nb)
+        def release():
+            for g in comp:
+                state[g] = -1
+        if len(comp) < obser_thr:
+            release(); continue
+        first = {}
+        for t, g in enumerate(comp):
+            first.setdefault(int(img_of[g]), t)
+        if len(first) < obser_thr:
+            release(); continue
+        imgs = sorted(first)
+        # ---- depth candidate
+        depth_ok, Xd, mean_d, kept_d = False, np.zeros(3), np.inf, []
+        valid = [t for t, g in enumerate(comp) if kp_valid[g]]
+        if len(valid) >= obser_thr:
+            Xa = np.asarray(kp_Xw[comp[valid[0]]], np.float64)
+            best = {}
+            for t in valid:
+                if np.linalg.norm(np.asarray(kp_Xw[comp[t]], np.float64) - Xa) < depth_gate:
+                    best.setdefault(int(img_of[comp[t]]), t)
+            if len(best) >= obser_thr:
+                order = [best[i] for i in sorted(best)]
+                Xd = np.zeros(3)
+                for t in order:
+                    Xd = Xd + np.asarray(kp_Xw[comp[t]], np.float64)
+                Xd = Xd / float(len(order))
+                kept_d = view_filter(order, lambda t: np.asarray(kp_Xw[comp[t]], np.float64))
+                if len(kept_d) >= obser_thr:
+                    cs, uv = sel_arrays(kept_d)
+                    ok, m, _ = trk.mean_reproj(Xd, cs, uv, intr, obser_thr)
+                    mean_d = m if ok else np.inf
+                    depth_ok = ok and m <= reproj_thr
+        # ---- triangulation candidate
+        tri_ok, Xt, mean_t, kept_t = False, np.zeros(3), np.inf, []
+        if len(first) >= 4:
+            order = [first[i] for i in imgs]
+            cs, uv = sel_arrays(order)
+            ok, Xs, _, _ = trk.triangulate_dlt(cs, uv, intr)
+            if ok:
+                kept_t = view_filter(order, lambda t: Xs)
+                if len(kept_t) >= 4:
+                    cs, uv = sel_arrays(kept_t)
+                    ok2, Xt, m2, _ = trk.triangulate_dlt(cs, uv, intr)
+                    if ok2:
+                        mean_t = m2
+                        tri_ok = m2 <= reproj_thr
+        if depth_ok and tri_ok:
+            src = 2 if mean_t < mean_d else 1
+        elif tri_ok:
+            src = 2
+        elif depth_ok:
+            src = 1
+        else:
+            release(); continue
+        X, mean, kept = (Xt, mean_t, kept_t) if src == 2 else (Xd, mean_d, kept_d)
+        if not np.all(np.isfinite(X)) or np.all(np.abs(X) <= 1e-12):
+            release(); continue
+        tid = len(tracks)
+        inl = np.zeros(len(comp), bool); inl[kept] = True
+        obs = np.array([[int(img_of[g]), int(g - kp_ptr[img_of[g]])] for g in comp], np.int32)
+        tracks.append(dict(seed=seed, obs=obs, inlier=inl, Xw=np.array(X, np.float64), mean=float(mean), source=src))
+        for g in comp:
+            state[g] = tid
+    return tracks

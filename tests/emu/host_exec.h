@@ -36,6 +36,8 @@ struct HostExec {
   template <class T>
   int fill_zero(T* p, size_t n) { std::memset(p, 0, n * sizeof(T)); return 0; }
   template <class T>
+  int put(T* dev, const T* host, size_t n) { std::memcpy(dev, host, n * sizeof(T)); return 0; }
+  template <class T>
   int fetch(T* host, const T* dev, size_t n) { std::memcpy(host, dev, n * sizeof(T)); return 0; }
   int min_max(const int32_t* p, int64_t n, int32_t* mn, int32_t* mx) {
     *mn = *std::min_element(p, p + n); *mx = *std::max_element(p, p + n); return 0;

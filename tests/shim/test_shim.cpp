@@ -129,7 +129,50 @@ static int depth_case() {
   return (filled > 10000 && wrong == 0 && second == 0) ? 0 : 1;
 }
 
+// B7: a ring of cameras looking at a few points -> build_tracks_and_fuse_3d with mock sift::Keypoint / match tables
+struct Keypoint { float x, y; };
+static int fuse_case() {
+  const int N = 6, NP = 12;
+  const double fx = 646.78472, fy = 646.65775, cx = 313.456795, cy = 261.399612;
+  std::vector<M3> Rcw(N); std::vector<V3> tcw(N);
+  for (int i = 0; i < N; ++i) { Rcw[i] = M3{{1, 0, 0, 0, 1, 0, 0, 0, 1}}; tcw[i] = V3{{-0.6 * i, 0.0, 0.0}}; }     // camera centres at x = 0.6 i
+  std::vector<std::vector<Keypoint>> kps(N);
+  std::vector<std::vector<std::pair<int, int>>> matches((size_t)N * (N - 1) / 2);
+  std::vector<double> kpX; std::vector<uint8_t> kpV;
+  unsigned s = 99;
+  auto rnd = [&] { s = s * 1664525u + 1013904223u; return (double)(s >> 8) / (1u << 24) - 0.5; };
+  std::vector<std::array<double, 3>> pts(NP);
+  for (auto& p : pts) p = {1.5 + 2.0 * rnd(), 1.0 * rnd(), 6.0 + 2.0 * rnd()};
+  std::vector<std::vector<int>> kp_of(NP, std::vector<int>(N, -1));
+  for (int i = 0; i < N; ++i)
+    for (int p = 0; p < NP; ++p) {
+      const double X = pts[p][0] - 0.6 * i, Y = pts[p][1], Z = pts[p][2];
+      kp_of[p][i] = (int)kps[i].size();
+      kps[i].push_back(Keypoint{(float)(fx * X / Z + cx), (float)(fy * Y / Z + cy)});
+    }
+  for (int i = 0; i < N; ++i)                                                    // depth candidates in (image, keypoint) order
+    for (int p = 0; p < NP; ++p) { for (int d = 0; d < 3; ++d) kpX.push_back(pts[p][d] + 0.005 * rnd()); kpV.push_back(p % 4 == 3 ? 0 : 1); }
+  for (int i = 0; i < N - 1; ++i)
+    for (int j = i + 1; j < N; ++j)
+      for (int p = 0; p < NP; ++p) matches[(size_t)i * N - (size_t)i * (i + 1) / 2 + (j - i - 1)].push_back({kp_of[p][i], kp_of[p][j]});
+  std::vector<lvba_b200::FusedTrack> tracks;
+  lvba_fuse_summary fs{};
+  const int rc = lvba_b200::build_tracks_and_fuse_3d(kps, matches, Rcw, tcw, fx, fy, cx, cy, 0.0, 0.0, 0.0, 0.0, kpX, kpV, tracks, nullptr, &fs);
+  if (rc == LVBA_ERR_NO_DEVICE) return 2;
+  if (rc != LVBA_OK) { std::printf("fuse error %d: %s\n", rc, lvba_last_error()); return 1; }
+  double worst = 0;
+  for (const auto& t : tracks) {
+    if ((int)t.observations.size() != N || (int)t.inlier_indices.size() < 3) { std::printf("fuse: bad track shape\n"); return 1; }
+    const int p = t.observations[0].second;                                       // keypoint index == point index in image 0
+    for (int d = 0; d < 3; ++d) worst = std::fmax(worst, std::fabs(t.Xw_fused[d] - pts[p][d]));
+  }
+  std::printf("fuse ok: %zu tracks (%lld depth, %lld triangulated), worst |X - truth| = %.2e\n", tracks.size(), (long long)fs.n_depth_selected,
+              (long long)fs.n_tri_selected, worst);
+  return ((int)tracks.size() == NP && worst < 0.05) ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && std::string(argv[1]) == "fuse") return fuse_case();             // B7, run by tests/test_zz_fuse_gpu.py
   if (argc > 1 && std::string(argv[1]) == "windows") return window_stage_case(false);   // B3 + B1 batched, run by tests/test_zz_voxel_gpu.py
   if (argc > 1 && std::string(argv[1]) == "windowba") return window_stage_case(true);   // ... and the anchors (B6), tests/test_zz_offline_gpu.py
   if (argc > 1 && std::string(argv[1]) == "depth") return depth_case();           // B4, run by tests/test_zz_depth_gpu.py

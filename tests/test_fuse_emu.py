@@ -1,0 +1,85 @@
+"""Track fusion (global-lvba_b200/csrc/fuse_pipeline.h — LvbaSystem::BuildTracksAndFuse3D, reference src/lvba_system.cpp:921-1263)
+checked without a GPU: the host component builder, the retry rounds and the per-component device functor run through the
+sequential host policy (tests/emu/fuse_emu.cpp) against the literal restatement oracle/fuse_oracle.py — same tracks in the same
+order, same observations in BFS order, same inlier sets, same candidate choice, 3-D points to 1e-9."""
+import ctypes
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "tests"))
+
+import fuse_scene  # noqa: E402
+from oracle import fuse_oracle as fo  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    so = tmp_path_factory.mktemp("emu") / "libfuse_emu.so"
+    san = ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-g"] if os.environ.get("LVBA_EMU_SANITIZE") else []
+    cmd = ["g++", "-std=c++17", "-O2", *san, "-ffp-contract=off", "-Wall", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "fuse_emu.cpp"), "-o", str(so)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = ctypes.CDLL(str(so))
+    lib.fuse_emu_run.restype = ctypes.c_longlong
+    return lib
+
+
+def run_emu(emu, s, obser_thr=3, angle=8.0, thr=3.0, gate=0.12):
+    c = lambda a, t: a.ctypes.data_as(ctypes.POINTER(t))
+    m = np.ascontiguousarray(s["matches"], np.int32)
+    ma_i, ma_k, mb_i, mb_k = (np.ascontiguousarray(m[:, q]) for q in range(4))
+    counts = np.zeros(8, np.int64)
+    kp_ptr = np.ascontiguousarray(s["kp_ptr"], np.int64); uv = np.ascontiguousarray(s["kp_uv"], np.float32)
+    cams = np.ascontiguousarray(s["cams"], np.float64); X = np.ascontiguousarray(s["kp_Xw"], np.float64); va = np.ascontiguousarray(s["kp_valid"], np.uint8)
+    intr = np.ascontiguousarray(s["intr"], np.float64)
+    n = emu.fuse_emu_run(len(kp_ptr) - 1, c(kp_ptr, ctypes.c_longlong), c(uv, ctypes.c_float), ctypes.c_longlong(len(m)), c(ma_i, ctypes.c_int), c(ma_k, ctypes.c_int),
+                         c(mb_i, ctypes.c_int), c(mb_k, ctypes.c_int), c(cams, ctypes.c_double), c(intr, ctypes.c_double), c(X, ctypes.c_double),
+                         c(va, ctypes.c_ubyte), obser_thr, ctypes.c_double(angle), ctypes.c_double(thr), ctypes.c_double(gate), c(counts, ctypes.c_longlong))
+    assert n >= 0
+    n_obs = int(counts[0])
+    obs_ptr = np.zeros(n + 1, np.int64); img = np.zeros(n_obs, np.int32); kp = np.zeros(n_obs, np.int32); inl = np.zeros(n_obs, np.uint8)
+    Xw = np.zeros((n, 3)); src = np.zeros(n, np.uint8); mean = np.zeros(n); seed = np.zeros(n, np.int64)
+    emu.fuse_emu_export(c(obs_ptr, ctypes.c_longlong), c(img, ctypes.c_int), c(kp, ctypes.c_int), c(inl, ctypes.c_ubyte), c(Xw, ctypes.c_double),
+                        c(src, ctypes.c_ubyte), c(mean, ctypes.c_double), c(seed, ctypes.c_longlong))
+    return dict(obs_ptr=obs_ptr, img=img, kp=kp, inlier=inl, Xw=Xw, source=src, mean=mean, seed=seed, counts=counts)
+
+
+def compare(got, ref):
+    assert len(got["seed"]) == len(ref), (len(got["seed"]), len(ref))
+    for i, t in enumerate(ref):
+        a, b = got["obs_ptr"][i], got["obs_ptr"][i + 1]
+        assert got["seed"][i] == t["seed"]
+        assert np.array_equal(got["img"][a:b], t["obs"][:, 0]) and np.array_equal(got["kp"][a:b], t["obs"][:, 1])
+        assert got["source"][i] == t["source"], (i, got["source"][i], t["source"], got["mean"][i], t["mean"])
+        assert np.array_equal(got["inlier"][a:b].astype(bool), t["inlier"])
+        assert np.abs(got["Xw"][i] - t["Xw"]).max() <= 1e-9 * max(1.0, np.abs(t["Xw"]).max())
+        assert abs(got["mean"][i] - t["mean"]) <= 1e-9 * max(1.0, t["mean"])
+
+
+@pytest.mark.parametrize("seed,kw", [(0, {}), (1, dict(wrong=0.15)), (2, dict(no_depth=0.6)), (3, dict(bad_depth=0.3, px_noise=1.2)),
+                                     (4, dict(n_images=30, n_points=300)), (5, dict(no_depth=1.0)), (6, dict(n_images=5, n_points=40))])
+def test_fusion_matches_the_oracle(emu, seed, kw):
+    s = fuse_scene.make(seed=seed, **kw)
+    ref = fo.fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"])
+    got = run_emu(emu, s)
+    compare(got, ref)
+    assert len(ref) > 0 or kw.get("n_images") == 5
+    if seed in (0, 4):
+        assert (got["source"] == 1).any() and (got["source"] == 2).any()        # both candidates get chosen somewhere
+    assert got["counts"][4] >= got["counts"][2]                                  # failed components were tried again from other seeds
+
+
+def test_thresholds_and_retries(emu):
+    s = fuse_scene.make(seed=11, wrong=0.2, bad_depth=0.3)
+    for thr, angle, px in ((2, 1.0, 6.0), (4, 15.0, 1.5), (3, 8.0, 0.8)):
+        ref = fo.fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"], obser_thr=thr,
+                      min_view_angle_deg=angle, reproj_thr=px)
+        got = run_emu(emu, s, obser_thr=thr, angle=angle, thr=px)
+        compare(got, ref)
+    assert got["counts"][3] > 1                                                  # more than one round: retries from later seeds happened

@@ -22,7 +22,7 @@ def test_shim_compiles_and_refuses_without_gpu(pkg, tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     if pkg.device_count() == 0:
         assert r.returncode == 2, r.stdout + r.stderr
-        for case in ("surfmap", "windows", "windowba", "depth"):                                                # B3 / B4 mirrors refuse the same way
+        for case in ("surfmap", "windows", "windowba", "depth", "fuse"):                                                # B3 / B4 mirrors refuse the same way
             r = subprocess.run([str(exe), case], capture_output=True, text=True)
             assert r.returncode == 2, r.stdout + r.stderr
     else:
