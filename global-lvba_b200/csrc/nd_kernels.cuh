@@ -32,10 +32,10 @@ __global__ void __launch_bounds__(256) nd_pass_kernel(long long n, F f) {
 // The last 32 block rows of Z of the warp's columns live in shared memory private to the warp (column height <= 30), so the
 // only block-wide hand-shake per row is the one that publishes the next row of L: its blocks are contiguous in the envelope
 // and are staged by cp.async two rows ahead, into slots of 38 doubles (consecutive lanes 48 bytes apart modulo 128:
-// conflict-free LDS.128).  No global-memory latency sits on the row-to-row chain: the entering row of E rides in the same
-// cp.async group as the row of L, and the row labels (first / row_start) sit in a 64-entry shared-memory ring refilled 32 rows
-// at a time (measured: a label or E value loaded into a register in row k and consumed in row k+1 exposed an L2 round trip per
-// row — the loop skeleton alone cost 1 200 cycles per row, profiles/r02_spike_ablation.txt).
+// conflict-free LDS.128).  Row labels (first / row_start) and the entering rows of E are fetched four / one rows ahead: no
+// global-memory latency sits on the row-to-row chain.  (Tried and measured slower, profiles/r02_spike_ablation.txt: labels in a
+// shared-memory ring + E rows by cp.async — the loop is bound by the number of instructions a warp issues per row, ~4.4 cycles
+// each with one warp per scheduler, not by a load latency.)
 constexpr int kSpikeC = 4;                       // right-hand sides per warp
 constexpr int kSpikeWarps = 4;
 constexpr int kSpikeCols = kSpikeC * kSpikeWarps;   // right-hand sides per CTA
@@ -43,7 +43,7 @@ constexpr int kSpikeThreads = 32 * kSpikeWarps;
 constexpr int kSpikeZStride = 26;                // doubles per block row of a warp's Z window: [6][4] + 2 (lanes 80 bytes apart modulo 128)
 constexpr int kSpikeBS = 38;                     // doubles per staged block of L
 constexpr int kSpikeBufs = 3;                    // rows of L in flight (cp.async, two rows ahead)
-constexpr size_t kSpikeSmem = sizeof(double) * (kSpikeBufs * 32 * kSpikeBS + kSpikeWarps * 33 * kSpikeZStride + kSpikeBufs * kSpikeWarps * 24 + 64) + sizeof(int) * 64;
+constexpr size_t kSpikeSmem = sizeof(double) * (kSpikeBufs * 32 * kSpikeBS + kSpikeWarps * 33 * kSpikeZStride);
 static_assert(kSpikeC == 4, "the reduce-scatter below is written for 24 values per lane");
 
 // LVBA_SPIKE_MODE (development, results are wrong unless 0): 1 = no block products, 2 = no staging of L, 4 = no E loads / Z stores
@@ -61,50 +61,51 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cw = c0 + warp * kSpikeC;                          // first right-hand side of this warp
   double* sZw = smem_spike + kSpikeBufs * 32 * kSpikeBS + warp * 33 * kSpikeZStride;   // [32 rows + 1 zero row][6][4]
-  double* sE = smem_spike + kSpikeBufs * 32 * kSpikeBS + kSpikeWarps * 33 * kSpikeZStride;   // [kSpikeBufs][warps][6][4] entering rows of E
-  long long* sLabRS = reinterpret_cast<long long*>(sE + kSpikeBufs * kSpikeWarps * 24);  // [64] row_start of row r at r & 63
-  int* sLabF = reinterpret_cast<int*>(sLabRS + 64);                                       // [64] first column of row r at r & 63
   const int n = e.n, n_stop = J.n_stop, KS = J.KS;
   if (lane < kSpikeZStride) sZw[32 * kSpikeZStride + lane] = 0.0;        // row 32: zeros (operand of the lanes without a block)
   for (int o = tid; o < kSpikeBufs * 32 * kSpikeBS; o += kSpikeThreads) sRow[o] = 0.0;   // L slots never hold non-finite garbage
-  for (int r = tid; r < 64; r += kSpikeThreads) { sLabF[r] = (r < n) ? e.first[r] : 0; sLabRS[r] = (r < n) ? e.row_start[r] : 0; }
   const int sb0 = tid / 18, sh = tid - sb0 * 18;
   // after the reduce-scatter lane l (l & 3 == 0) holds the outputs o = 3 (l >> 2) + {0, 1, 2} of the 24 (o = x * 4 + column)
   const int og = (lane >> 2) * 3;
   const bool owner = (lane & 3) == 0;
+  int ox[3], oc[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) { ox[q] = (og + q) >> 2; oc[q] = (og + q) & 3; }
   __syncthreads();
-  // row k: blocks (k, f .. min(k, n_stop)-1) and the entering row of E of every warp -> buffers k % 3 (one cp.async group)
-  auto stage_row = [&](int k) {
+  auto stage_row = [&](int k, int f, long long rs) {           // blocks (k, f .. min(k, n_stop)-1) -> sRow[k % 3]
     if (k >= n) return;
-    const int f = sLabF[k & 63];
-    const long long rs = sLabRS[k & 63];
     const int jend = k < n_stop ? k : n_stop;
     const int nb = jend > f ? jend - f : 0;
     const double* src = J.L + rs * 36;
     double* dst = sRow + (k % kSpikeBufs) * (32 * kSpikeBS);
     if (tid < 126 && !(dbg_mode & 2))                          // thread -> (block, 16-byte piece): 7 blocks per sweep
       for (int b = sb0; b < nb; b += 7) cp_async16_zfill(dst + b * kSpikeBS + 2 * sh, src + b * 36 + 2 * sh, true);
-    if (lane < 12) {                                           // E[k][x][cw .. cw+3]: two 16-byte pieces per component
-      const int x = lane >> 1, h = lane & 1;
-      const bool ok = k < J.nE && cw + 2 * h < KS && !(dbg_mode & 4);      // (KS is even: a piece is inside or outside as a whole)
-      cp_async16_zfill(sE + ((k % kSpikeBufs) * kSpikeWarps + warp) * 24 + x * 4 + 2 * h,
-                       ok ? J.E + ((long long)k * 6 + x) * KS + cw + 2 * h : J.L, ok);
-    }
   };
-  stage_row(0);
+  // labels: row k (f0), rows k+1 .. k+3 (f1..f3, rs2, rs3): fetched four rows ahead of their use in the chain
+  int f0 = e.first[0];
+  int f1 = n > 1 ? e.first[1] : 0; long long rs1 = n > 1 ? e.row_start[1] : 0;
+  int f2 = n > 2 ? e.first[2] : 0; long long rs2 = n > 2 ? e.row_start[2] : 0;
+  int f3 = n > 3 ? e.first[3] : 0; long long rs3 = n > 3 ? e.row_start[3] : 0;
+  double en[3];                                                // E of the next row: this lane's three outputs
+#pragma unroll
+  for (int q = 0; q < 3; ++q) en[q] = (owner && cw + oc[q] < KS && 0 < J.nE && !(dbg_mode & 4)) ? J.E[((long long)ox[q]) * KS + cw + oc[q]] : 0.0;
+  stage_row(0, f0, e.row_start[0]);
   asm volatile("cp.async.commit_group;" ::: "memory");
-  stage_row(1);
+  stage_row(1, f1, rs1);
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int k = 0; k < n; ++k) {
     asm volatile("cp.async.wait_group 1;" ::: "memory");       // everything but the newest group (row k+1): row k has landed
     __syncthreads();                                           // row k of L staged by everybody; everybody is done with row k-1
-    if ((k & 31) == 0 && k > 0 && warp == 0) {                 // labels of rows k+32 .. k+63 (their ring slots held rows k-32 .. k-1)
-      const int r = k + 32 + lane;
-      if (r < n) { sLabF[r & 63] = e.first[r]; sLabRS[r & 63] = e.row_start[r]; }
-    }
-    stage_row(k + 2);                                          // into the buffers row k-1 used
+    stage_row(k + 2, f2, rs2);                                 // into the buffer row k-1 used
     asm volatile("cp.async.commit_group;" ::: "memory");
-    const int f0 = sLabF[k & 63];
+    const int f4 = (k + 4 < n) ? e.first[k + 4] : 0;
+    const long long rs4 = (k + 4 < n) ? e.row_start[k + 4] : 0;
+    double ecur[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) ecur[q] = en[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      en[q] = (owner && cw + oc[q] < KS && k + 1 < J.nE && !(dbg_mode & 4)) ? J.E[((long long)(k + 1) * 6 + ox[q]) * KS + cw + oc[q]] : 0.0;
     const int jend = k < n_stop ? k : n_stop;
     // ---- this lane's block L_{k, f0 + lane} times the four columns of z_{f0 + lane}
     double v[24];
@@ -160,16 +161,15 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
     // lane l now holds the outputs 12 (l >> 4 & 1) + 6 (l >> 3 & 1) + 3 (l >> 2 & 1) + {0,1,2} = 3 (l >> 2) + {0,1,2}
     __syncwarp();                                              // every lane has read the window entries it needs of row k-32
     if (owner) {
-      const double* ek = sE + ((k % kSpikeBufs) * kSpikeWarps + warp) * 24;
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        const int o = og + q, ox = o >> 2, oc = o & 3;
-        const double r = ek[o] - w3[q];
-        sZw[(k & 31) * kSpikeZStride + o] = r;                 // row k-32 is no longer needed (column height <= 30)
-        if (cw + oc < KS && !(dbg_mode & 4)) J.Z[((long long)k * 6 + ox) * KS + cw + oc] = r;
+        const double r = ecur[q] - w3[q];
+        sZw[(k & 31) * kSpikeZStride + ox[q] * 4 + oc[q]] = r;       // row k-32 is no longer needed (column height <= 30)
+        if (cw + oc[q] < KS && !(dbg_mode & 4)) J.Z[((long long)k * 6 + ox[q]) * KS + cw + oc[q]] = r;
       }
     }
     __syncwarp();
+    f0 = f1; f1 = f2; f2 = f3; rs2 = rs3; f3 = f4; rs3 = rs4;
   }
 }
 
@@ -325,85 +325,132 @@ nd_correct_apply_kernel(nd::Tables t, const int* __restrict__ ids, int stride) {
 //
 // The register-window kernel of factor_la.cuh slides a 31-row window along a band and pays ~4 900 cycles per pivot column
 // whatever the column holds; a separator is dense and SHRINKS (the trailing matrix of pivot k has (29-k)(30-k)/2 blocks),
-// and its 30 pivots sit on the critical path of every tree level.  Here every block of the lower triangle lives in the
-// registers of one PAIR thread for the whole factorisation (thread <-> (i, j)), and ONE extra warp owns the pivot column:
-//   phase B  (column warp, lane <-> row i = k+1+lane)  every lane inverts D_k (the same instruction stream for all lanes:
-//            one warp's worth of FP64 issue slots; two reciprocals on the dependent chain, factor_la.cuh), then scales its
-//            own block: L_ik = T_ik D_k^-1 -> shared memory and global memory, z_i -= L_ik z_k;
-//   phase C  (pair threads) every live block (i, j), i >= j > k:  G -= L_ik T_jk^T  (216 DFMA, operands by LDS.128; the
-//            thread map groups 8 x 4 patches of blocks into a warp so that a warp touches <= 8 + 4 distinct operand
-//            blocks); the blocks of column k+1 are final after it and go to shared memory (T_{i,k+1}, D_{k+1}).
-// Two block barriers per pivot.  One CTA per separator; grid = separators of the tree level.
+// and its 30 pivots sit on the critical path of every tree level.  Every block of the lower triangle lives in the registers
+// of one PAIR thread for the whole factorisation (thread <-> (i, j)); a COLUMN GROUP of six warps owns the pivot column and
+// runs ONE PIVOT AHEAD of the pair threads (look-ahead), thread <-> (block row i, row r of the 6 x 6 block):
+//   iteration s, column group:  column s arrives as the pair threads left it (updated through pivot s-2); apply pivot s-1 to
+//                               it (36 DFMA per thread); the diagonal block goes to warp 0, which inverts it (two
+//                               reciprocals on the dependent chain, factor_la.cuh); every thread scales its row:
+//                               L_is = T_is D_s^-1 -> shared + global memory, z_i -= L_is z_s;
+//   iteration s, pair threads:  G -= L_{i,s-1} T_{j,s-1}^T for their blocks of columns j >= s+1 (216 DFMA; the thread map
+//                               groups 8 x 4 patches of blocks into a warp: <= 8 + 4 distinct operand blocks per warp);
+//                               column s+1 is then handed to the column group through shared memory.
+// One block barrier per pivot; the column group's chain (update 36 + inverse ~300 + scale ~90 instructions per warp) and the
+// pair threads' update overlap.  Measured before the look-ahead (profiles/r02_*): 5 900 cycles per pivot = 3 100 (one warp
+// inverting and scaling 216 DFMA per lane) + 1 900 (trailing update, FP64 bound) + barriers.
+// One CTA per separator; grid = separators of the tree level.
 constexpr int kDenseMax = 30;
 constexpr int kDensePairThreads = 480;       // 465 blocks of the 30 x 30 lower triangle
-constexpr int kDenseThreads = kDensePairThreads + 32;
+constexpr int kDenseInvWarp = 480;           // threads 480..511: the warp that inverts the pivot block (pair-side register budget)
+constexpr int kDenseColBase = 512;           // threads 512..703: 6 warps, warp = row of the 6 x 6 block, lane = block row
+constexpr int kDenseColThreads = 192;
+constexpr int kDenseThreads = 768;           // 4 + 2 warpgroups (704..767 idle): the register re-allocation works on warpgroups
+constexpr int kDensePairRegs = 96, kDenseColRegs = 64;       // 512 * 96 + 256 * 64 == 65536 ; launched at 80
 constexpr int kDenseS = 38;                  // doubles per operand block in shared memory (bank spread, 16 B aligned)
+constexpr size_t kDenseSmem = sizeof(double) * (6 * kDenseMax * kDenseS + 36 + 36 + kDenseMax * 6 + 8);
 
 __global__ void __launch_bounds__(kDenseThreads, 1)
 nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short* __restrict__ tmap) {
-  __shared__ __align__(16) double sL[kDenseMax * kDenseS];
-  __shared__ __align__(16) double sT[2][kDenseMax * kDenseS];       // T_{i,k}: parity k & 1
-  __shared__ __align__(16) double sD[2][36];
-  __shared__ double sZ[kDenseMax * 6];
+  extern __shared__ __align__(16) double smem_dense[];
+  double* sL = smem_dense;                                 // [2][30][S] L_{i,s}   parity s & 1
+  double* sT = sL + 2 * kDenseMax * kDenseS;               // [2][30][S] T_{i,s}   parity s & 1
+  double* sC = sT + 2 * kDenseMax * kDenseS;               // [2][30][S] column c as the pair threads left it, parity c & 1
+  double* sD = sC + 2 * kDenseMax * kDenseS;               // [36] pivot block (rows written by the six threads of block row s)
+  double* sK = sD + 36;                                    // [36] its inverse
+  double* sZ = sK + 36;                                    // [30][6]
   const FactorJob J = jobs[blockIdx.x];
   const int n = J.e.n;
   const int tid = threadIdx.x;
   for (int o = tid; o < n * 6; o += kDenseThreads) sZ[o] = J.z[o];
-  if (tid >= kDensePairThreads) {
-    // ================================================= column warp
-    const int lane = tid - kDensePairThreads;
+  // register re-allocation: one setmaxnreg site per warpgroup-uniform branch (warpgroups 0-3: pair threads + inverting warp)
+  if (tid >= kDenseColBase) reg_dealloc<kDenseColRegs>(); else reg_alloc<kDensePairRegs>();
+  if (tid >= kDenseColBase) {
+    // ================================================= column group (+ two idle warps that only keep the block barriers company)
+    const int ct = tid - kDenseColBase;
+    const bool idle = ct >= kDenseColThreads;
+    const int r = idle ? 0 : (ct >> 5), i = idle ? 31 : (ct & 31); // row r of block row i
+    const bool mine = !idle && i < n;
+    double lrow[6] = {0, 0, 0, 0, 0, 0};                           // row r of L_{i,s-1}
+    __syncthreads();                                               // (P) columns 0 and 1 published by the pair threads
+    for (int s = 0; s < n; ++s) {
+      const int par = s & 1;
+      // ---- (1) column s as of pivot s-1: row r of block (i, s), i >= s
+      double t[6] = {0, 0, 0, 0, 0, 0};
+      if (mine && i >= s) {
+        const double2* c2 = reinterpret_cast<const double2*>(sC + (par * kDenseMax + i) * kDenseS + r * 6);
+        const double2 q0 = c2[0], q1 = c2[1], q2 = c2[2];
+        t[0] = q0.x; t[1] = q0.y; t[2] = q1.x; t[3] = q1.y; t[4] = q2.x; t[5] = q2.y;
+        if (s > 0) {                                               // -= L_{i,s-1}[r][.] T_{s,s-1}^T
+          const double* ts = sT + ((par ^ 1) * kDenseMax + s) * kDenseS;
+#pragma unroll
+          for (int y = 0; y < 6; ++y) {
+            const double2 u0 = reinterpret_cast<const double2*>(ts + y * 6)[0], u1 = reinterpret_cast<const double2*>(ts + y * 6)[1],
+                          u2 = reinterpret_cast<const double2*>(ts + y * 6)[2];
+            double a = t[y];
+            a = fma(-lrow[0], u0.x, a); a = fma(-lrow[1], u0.y, a); a = fma(-lrow[2], u1.x, a);
+            a = fma(-lrow[3], u1.y, a); a = fma(-lrow[4], u2.x, a); a = fma(-lrow[5], u2.y, a);
+            t[y] = a;
+          }
+        }
+        if (i == s) {
+          double2* d2 = reinterpret_cast<double2*>(sD + r * 6);
+          d2[0] = make_double2(t[0], t[1]); d2[1] = make_double2(t[2], t[3]); d2[2] = make_double2(t[4], t[5]);
+        }
+      }
+      if (!idle) {
+        named_bar_sync(2, kDenseColThreads + 32);                  // pivot block complete -> the inverting warp
+        named_bar_sync(3, kDenseColThreads + 32);                  // D_s^-1 visible
+      }
+      // ---- (2) scale: row r of L_is = T_is D_s^-1, publish T and L, forward substitution
+      if (mine && i > s) {
+        double lr[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          double a = t[0] * sK[c];
+#pragma unroll
+          for (int q = 1; q < 6; ++q) a = fma(t[q], sK[q * 6 + c], a);
+          lr[c] = a;
+        }
+        double2* t2 = reinterpret_cast<double2*>(sT + (par * kDenseMax + i) * kDenseS + r * 6);
+        double2* l2 = reinterpret_cast<double2*>(sL + (par * kDenseMax + i) * kDenseS + r * 6);
+        double2* g2 = reinterpret_cast<double2*>(J.L + ((long long)i * (i + 1) / 2 + s) * 36 + r * 6);
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+          t2[h] = make_double2(t[2 * h], t[2 * h + 1]);
+          const double2 lv = make_double2(lr[2 * h], lr[2 * h + 1]);
+          l2[h] = lv; g2[h] = lv;
+        }
+        double zs = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { zs = fma(lr[q], sZ[s * 6 + q], zs); lrow[q] = lr[q]; }
+        sZ[i * 6 + r] -= zs;
+      }
+      __syncthreads();                                             // (s) L_s, T_s published; column s+2 handed over by the pair threads
+    }
+  } else if (tid >= kDenseInvWarp) {
+    // ================================================= the inverting warp
+    const int lane = tid - kDenseInvWarp;
     int bad = 0;
-    __syncthreads();                                               // (0) column 0 and D_0 published
-    for (int k = 0; k < n; ++k) {
-      const int par = k & 1;
-      const int i = k + 1 + lane;
+    __syncthreads();                                               // (P)
+    for (int s = 0; s < n; ++s) {
+      named_bar_sync(2, kDenseColThreads + 32);
       double xl[21], K[21];
 #pragma unroll
       for (int a = 0; a < 6; ++a)
 #pragma unroll
-        for (int b = 0; b <= a; ++b) xl[LVBA_T(a, b)] = sD[par][a * 6 + b];
+        for (int b = 0; b <= a; ++b) xl[LVBA_T(a, b)] = sD[a * 6 + b];
       sym6_block_inverse(xl, K);
-      auto kk = [&](int r, int c) -> double { return r >= c ? K[LVBA_T(r, c)] : K[LVBA_T(c, r)]; };
+      auto kk = [&](int rr, int c) -> double { return rr >= c ? K[LVBA_T(rr, c)] : K[LVBA_T(c, rr)]; };
       if (!isfinite((K[LVBA_T(0, 0)] + K[LVBA_T(5, 5)]) + (K[LVBA_T(3, 0)] + K[LVBA_T(2, 1)]))) bad = 1;
-      if (lane == 31 || (lane == 0 && n - k - 1 <= 0)) {           // an idle lane (or lane 0 of the last pivot) stores D_k^-1
-        double* dk = J.dinv + (long long)k * 36;
+      if (lane == 0) {                                             // D_s^-1 (full symmetric) for the column group and for the caller
+        double* dk = J.dinv + (long long)s * 36;
 #pragma unroll
-        for (int r = 0; r < 6; ++r)
+        for (int rr = 0; rr < 6; ++rr)
 #pragma unroll
-          for (int c = 0; c < 6; ++c) dk[r * 6 + c] = kk(r, c);
+          for (int c = 0; c < 6; ++c) { const double v = kk(rr, c); sK[rr * 6 + c] = v; dk[rr * 6 + c] = v; }
       }
-      if (i < n) {
-        const double2* t2 = reinterpret_cast<const double2*>(&sT[par][i * kDenseS]);
-        double2* l2 = reinterpret_cast<double2*>(sL + i * kDenseS);
-        double2* g2 = reinterpret_cast<double2*>(J.L + ((long long)i * (i + 1) / 2 + k) * 36);
-        double zk[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) zk[q] = sZ[k * 6 + q];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {                              // row r of L_ik = T_ik D_k^-1, straight to its destinations
-          const double2 g0 = t2[3 * r], g1 = t2[3 * r + 1], g2v = t2[3 * r + 2];
-          const double gr[6] = {g0.x, g0.y, g1.x, g1.y, g2v.x, g2v.y};
-          double lr[6];
-#pragma unroll
-          for (int c = 0; c < 6; ++c) {
-            double s = 0.0;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) s += gr[q] * kk(q, c);
-            lr[c] = s;
-          }
-#pragma unroll
-          for (int h = 0; h < 3; ++h) {
-            const double2 lv = make_double2(lr[2 * h], lr[2 * h + 1]);
-            l2[3 * r + h] = lv; g2[3 * r + h] = lv;
-          }
-          double zs = 0.0;
-#pragma unroll
-          for (int q = 0; q < 6; ++q) zs += lr[q] * zk[q];
-          sZ[i * 6 + r] -= zs;
-        }
-      }
-      __syncthreads();                                             // (1) L_{.,k} published
-      __syncthreads();                                             // (2) column k+1 and D_{k+1} published by the pair threads
+      named_bar_sync(3, kDenseColThreads + 32);
+      __syncthreads();                                             // (s)
     }
     if (bad && lane == 0) J.status[0] = 1;
   } else {
@@ -420,33 +467,35 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
 #pragma unroll
       for (int q = 0; q < 36; ++q) G[q] = 0.0;
     }
-    // a block of column c is final after pivot c-1: it goes to shared memory (T_{i,c} or D_c) for the column warp
+    // hand column c (this thread's block (i, c)) to the column group
     auto publish = [&](int c) {
-      double2* d2 = (i == c) ? reinterpret_cast<double2*>(sD[c & 1]) : reinterpret_cast<double2*>(&sT[c & 1][i * kDenseS]);
+      double2* d2 = reinterpret_cast<double2*>(sC + ((c & 1) * kDenseMax + i) * kDenseS);
 #pragma unroll
       for (int q = 0; q < 18; ++q) d2[q] = make_double2(G[2 * q], G[2 * q + 1]);
     };
-    if (live && j == 0) publish(0);
-    __syncthreads();                                               // (0)
-    for (int k = 0; k < n; ++k) {
-      __syncthreads();                                             // (1) L_{.,k} published
-      if (live && j > k) {
-        const double2* l2 = reinterpret_cast<const double2*>(sL + i * kDenseS);
-        const double2* t2 = reinterpret_cast<const double2*>(&sT[k & 1][j * kDenseS]);
+    if (live && j <= 1) publish(j);                                // columns 0 and 1 as they are
+    __syncthreads();                                               // (P)
+    for (int s = 0; s < n; ++s) {
+      // the trailing update of pivot s-1 for the columns the pair threads still own (j >= s+1)
+      if (s >= 1 && live && j >= s + 1) {
+        const int par = (s - 1) & 1;
+        const double2* l2 = reinterpret_cast<const double2*>(sL + (par * kDenseMax + i) * kDenseS);
+        const double2* t2 = reinterpret_cast<const double2*>(sT + (par * kDenseMax + j) * kDenseS);
 #pragma unroll
         for (int y = 0; y < 6; ++y) {
           const double2 t0 = t2[3 * y], t1 = t2[3 * y + 1], t2v = t2[3 * y + 2];
 #pragma unroll
           for (int x = 0; x < 6; ++x) {
             const double2 a0 = l2[3 * x], a1 = l2[3 * x + 1], a2 = l2[3 * x + 2];
-            double s = G[x * 6 + y];
-            s -= a0.x * t0.x; s -= a0.y * t0.y; s -= a1.x * t1.x; s -= a1.y * t1.y; s -= a2.x * t2v.x; s -= a2.y * t2v.y;
-            G[x * 6 + y] = s;
+            double a = G[x * 6 + y];
+            a = fma(-a0.x, t0.x, a); a = fma(-a0.y, t0.y, a); a = fma(-a1.x, t1.x, a);
+            a = fma(-a1.y, t1.y, a); a = fma(-a2.x, t2v.x, a); a = fma(-a2.y, t2v.y, a);
+            G[x * 6 + y] = a;
           }
         }
-        if (j == k + 1) publish(k + 1);
+        if (j == s + 1) publish(s + 1);                            // column s+1 (updated through pivot s-1) -> column group, iteration s+1
       }
-      __syncthreads();                                             // (2)
+      __syncthreads();                                             // (s)
     }
   }
   __syncthreads();

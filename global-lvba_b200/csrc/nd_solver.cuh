@@ -130,6 +130,7 @@ struct NdDevice {
       LVBA_CUDA(cudaMemcpyToSymbol(g_spike_mode, &mode, sizeof(int)));
     }
     LVBA_CUDA(cudaFuncSetAttribute(nd_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
+    LVBA_CUDA(cudaFuncSetAttribute(nd_dense_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmem));
     LVBA_CUDA(cudaStreamSynchronize(s));                     // local vectors
     leaf_e = nd::leaf_e_stride(plan); leaf_fin = nd::leaf_final_stride(plan);
     chunks = p; ready = true;
@@ -201,7 +202,7 @@ struct NdCudaExec {
   void factor_dense(const FactorJob* jobs, int n, int max_col) {
     if (n <= 0) return;
     if (!dense_map) { factor(jobs, n, max_col); return; }
-    nd_dense_factor_kernel<<<n, kDenseThreads, 0, s>>>(jobs, dense_map);
+    nd_dense_factor_kernel<<<n, kDenseThreads, kDenseSmem, s>>>(jobs, dense_map);
     ++launches;
   }
   void spike(const nd::SpikeJob* jobs, int n, int max_ks, int) {
