@@ -265,11 +265,20 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
 
   // ---- shard: voxel -> owner of its lowest pose index
   Comm& cm = comm();
+  bool sorted_voxels = false;
   std::vector<int64_t> mine;
   mine.reserve((size_t)V);
   for (int64_t a = 0; a < V; ++a)
     if (!cm.active() || (P->solver.dist() ? P->solver.dist_owner(pose_idx[vox_ptr[a]]) : shard_owner(pose_idx[vox_ptr[a]], W, cm.n_ranks)) == cm.rank)
       mine.push_back(a);
+  {
+    // voxels in the order of their lowest pose: a batch CTA then touches ~30 consecutive pose rows of H (its diagonal blocks and
+    // gradient rows can be reduced per pose before they leave the SM, and its REDs stay inside a few hundred kB of L2)
+    const char* sv = getenv("LVBA_SORT_VOXELS");
+    sorted_voxels = n_groups == 0 && sv && sv[0] == '1';
+    if (sorted_voxels)
+      std::stable_sort(mine.begin(), mine.end(), [&](int64_t x, int64_t y) { return pose_idx[vox_ptr[x]] < pose_idx[vox_ptr[y]]; });
+  }
   if (n_groups > 0)      // windows in order: batches and their partial sums become contiguous per window
     std::stable_sort(mine.begin(), mine.end(), [&](int64_t x, int64_t y) { return pose_grp[pose_idx[vox_ptr[x]]] < pose_grp[pose_idx[vox_ptr[y]]]; });
   // voxels seen from more than kSlots poses do not fit a batch CTA: they leave `mine` and take the passes of lidar_big.h
@@ -342,7 +351,7 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   std::vector<int> l_pidx((size_t)nnz);
   {
     DevBuf<double> aos;
-    const bool contiguous = Vl == V && n_groups == 0;            // single rank, caller's order: the records go up as they are
+    const bool contiguous = Vl == V && n_groups == 0 && !sorted_voxels;     // single rank, caller's order: the records go up as they are
     if (contiguous) {
       const double* aos_src = d_clusters;
       if (!aos_src) LVBA_TRY(aos.alloc((size_t)std::max<long long>(nnz, 1) * 10));

@@ -125,9 +125,8 @@ struct NdDevice {
     }
     LVBA_CUDA(cudaFuncSetAttribute(nd_spike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpikeSmem));
     {
-      const char* m = getenv("LVBA_SPIKE_MODE");             // development only (nd_kernels.cuh)
-      const int mode = m ? atoi(m) : 0;
-      LVBA_CUDA(cudaMemcpyToSymbol(g_spike_mode, &mode, sizeof(int)));
+      const char* m = getenv("LVBA_SPIKE_MODE");             // development only (nd_kernels.cuh); the symbol is 0 unless asked
+      if (m) { const int mode = atoi(m); LVBA_CUDA(cudaMemcpyToSymbol(g_spike_mode, &mode, sizeof(int))); }
     }
     LVBA_CUDA(cudaFuncSetAttribute(nd_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
     LVBA_CUDA(cudaFuncSetAttribute(nd_dense_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmem));

@@ -91,6 +91,9 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   }
   LVBA_TRY(select_device(device));
   const double t_begin = wall_ms();
+  const bool tlog = getenv("LVBA_SETUP_TIMING") != nullptr;
+  double tprev = t_begin;
+  auto lap = [&](const char* what) { if (tlog) { cudaStreamSynchronize(nullptr); const double tn = wall_ms(); fprintf(stderr, "[visual setup] %-26s %8.2f ms\n", what, tn - tprev); tprev = tn; } };
   std::unique_ptr<lvba_visual_problem> P(new lvba_visual_problem());
   P->M = M; P->T = T; P->fixed_cam = fixed_cam;
   for (int i = 0; i < 8; ++i) P->intr[i] = intr[i];
@@ -117,6 +120,7 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   P->n_rows = (int)P->cam_of_row.size();
   const int64_t Tv_all = (int64_t)valid.size();
 
+  lap("valid landmarks / rows");
   // ---- envelope of the reduced camera system over ALL valid landmarks
   std::vector<int> first_raw(std::max(P->n_rows, 1));
   for (int r = 0; r < P->n_rows; ++r) first_raw[r] = r;
@@ -143,6 +147,7 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
     LVBA_TRY(P->solver.prepare(P->env, s));
   }
 
+  lap("envelope + solver prepare");
   // ---- shard: landmark -> owner of its lowest camera index
   Comm& cm = comm();
   std::vector<int64_t> mine;
@@ -172,6 +177,7 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
       }
     }
   });
+  lap("gather observations");
   // ---- batches
   std::vector<int> batch_trk{0};
   {
@@ -219,6 +225,7 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
     });
   }
   P->n_pairs = (long long)pairs.size();
+  lap("batches + pair table");
 
   // ---- upload
   LVBA_TRY(P->trk_ptr.upload(trk_ptr, s, &P->h2d));
@@ -254,6 +261,7 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   LVBA_CUDA(cudaFuncSetAttribute(visual_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)visual_build_smem_bytes()));
   LVBA_CUDA(cudaFuncSetAttribute(visual_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)visual_backsub_smem_bytes()));
   LVBA_CUDA(cudaStreamSynchronize(s));
+  lap("uploads + allocations");
   lvba_visual_default_opts(&P->opts);
   P->ms_setup = wall_ms() - t_begin;
   *out = P.release();

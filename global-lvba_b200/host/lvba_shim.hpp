@@ -418,6 +418,33 @@ class DepthRenderer {
     return lvba_depth_render(grid_, M, cams.data(), image_ts.data(), half_w, intr, image_width, image_height, depth.data(), summary);
   }
 
+  // The depth candidates of BuildTracksAndFuse3D (:1020-1038) for every keypoint: all_keypoints[i][k].x / .y, result in
+  // (image, keypoint) order: kp_Xw [n_kp * 3] (zeros where invalid), kp_valid [n_kp].  The depth images stay on the device.
+  template <class Mat3Vec, class Vec3Vec, class KeypointImages>
+  int backproject(const Mat3Vec& Rcw_all, const Vec3Vec& tcw_all, const std::vector<double>& image_ts, const KeypointImages& all_keypoints,
+                  double fx, double fy, double cx, double cy, double k1, double k2, double p1, double p2, int image_width, int image_height,
+                  std::vector<double>& kp_Xw, std::vector<uint8_t>& kp_valid, double half_w = 0.5, lvba_depth_summary* summary = nullptr) {
+    if (!grid_) throw std::runtime_error("lvba_b200::DepthRenderer: grid not built");
+    const int M = (int)image_ts.size();
+    if ((int)Rcw_all.size() != M || (int)tcw_all.size() != M || (int)all_keypoints.size() != M)
+      throw std::runtime_error("lvba_b200::DepthRenderer: pose / image / keypoint count mismatch");
+    std::vector<double> cams((size_t)M * 12);
+    std::vector<int64_t> kp_ptr((size_t)M + 1, 0);
+    for (int k = 0; k < M; ++k) {
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) cams[12 * k + 3 * r + c] = Rcw_all[k](r, c);
+      for (int r = 0; r < 3; ++r) cams[12 * k + 9 + r] = tcw_all[k](r);
+      kp_ptr[k + 1] = kp_ptr[k] + (int64_t)all_keypoints[k].size();
+    }
+    std::vector<float> uv((size_t)kp_ptr[M] * 2);
+    for (int k = 0; k < M; ++k)
+      for (size_t j = 0; j < all_keypoints[k].size(); ++j) { uv[2 * (kp_ptr[k] + j)] = all_keypoints[k][j].x; uv[2 * (kp_ptr[k] + j) + 1] = all_keypoints[k][j].y; }
+    const double intr[8] = {fx, fy, cx, cy, k1, k2, p1, p2};
+    kp_Xw.assign((size_t)kp_ptr[M] * 3, 0.0);
+    kp_valid.assign((size_t)kp_ptr[M], 0);
+    return lvba_depth_backproject(grid_, M, cams.data(), image_ts.data(), half_w, intr, image_width, image_height, kp_ptr.data(), uv.data(),
+                                  kp_Xw.data(), kp_valid.data(), summary);
+  }
+
  private:
   lvba_depth_grid* grid_ = nullptr;
 };
