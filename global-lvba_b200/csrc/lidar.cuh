@@ -15,9 +15,10 @@
 //              pose pair is the rank-3 product  c1 f1_i f1_j^T + c2 f2_i f2_j^T - 2/N^2 b_i b_j^T
 //              (algebraically identical to bavoxel.hpp:159-163, re-associated);
 //   * phase 4: every warp takes 8 pose pairs at a time: 8*36 = 288 block elements = 9 per lane, each a
-//              3-FMA product of shared-memory factors followed by one RED.ADD.F64 into the block-envelope
-//              Hessian.  A warp's 32 REDs of one instruction hit 32 consecutive doubles (coalesced
-//              sectors).  Diagonal blocks and g_i are staged in shared memory and flushed the same way.
+//              3-FMA product of factors followed by one RED.ADD.F64 into the block-envelope Hessian.  Four lanes share a
+//              pair and write one aligned 32-byte sector per instruction; a lane reads the 27 factor values of its 9
+//              elements from shared memory once.  Diagonal blocks and g_i are staged in shared memory and flushed with
+//              32 consecutive doubles per warp instruction.
 // FP64 throughout: lambda0 ~ 1e-4 m^2 is a difference of O(1e4) m^2 terms (P/N - vbar vbar^T).
 #pragma once
 #include "common.cuh"
@@ -27,7 +28,8 @@ namespace lvba {
 
 constexpr int kSlots = 128;            // slots (threads) per batch CTA
 constexpr int kMaxVoxPerBatch = 64;    // K >= 2 per voxel  =>  <= kSlots/2 voxels per batch
-constexpr int kStageStride = 37;       // doubles per slot in the staging buffer (36 + 1 pad: odd => no LDS.64 bank conflicts)
+constexpr int kStageStride = 37;       // visual build: doubles per slot in the staging buffer (36 + 1 pad: odd => no LDS.64 bank conflicts)
+constexpr int kLStage = 19;            // LiDAR build: 10 cluster values, then HALF a diagonal block (18 + 1 pad)
 constexpr int kFStride = 19;           // 18 factor doubles + 1 pad
 constexpr int kVoxParams = 16;
 
@@ -87,7 +89,7 @@ LVBA_DEV void voxel_cov(const double* stage, int s_lo, int s_hi, double cov[6], 
 #pragma unroll
   for (int q = 0; q < 10; ++q) acc[q] = 0.0;
   for (int s = s_lo; s < s_hi; ++s) {
-    const double* p = stage + s * kStageStride;
+    const double* p = stage + s * kLStage;
 #pragma unroll
     for (int q = 0; q < 10; ++q) acc[q] += p[q];
   }
@@ -147,8 +149,8 @@ __global__ void __launch_bounds__(kSlots)
 lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, double* __restrict__ H,
                    double* __restrict__ g, double* __restrict__ batch_res) {
   extern __shared__ double sm[];
-  double* stage = sm;                                   // [kSlots][kStageStride]
-  double* sF = stage + kSlots * kStageStride;           // [kSlots][kFStride]
+  double* stage = sm;                                   // [kSlots][kLStage]
+  double* sF = stage + kSlots * kLStage;           // [kSlots][kFStride]
   double* sG = sF + kSlots * kFStride;                  // [kSlots][6]
   double* sV = sG + kSlots * 6;                         // [kMaxVoxPerBatch][kVoxParams]
   double* red = sV + kMaxVoxPerBatch * kVoxParams;      // [32]
@@ -157,9 +159,6 @@ lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, 
   int* sPose = reinterpret_cast<int*>(sRowRS + kSlots); // [kSlots]
   int* sRowFirst = sPose + kSlots;                      // [kSlots] envelope first[] of the slot's pose row
   unsigned char* sVoxOf = reinterpret_cast<unsigned char*>(sRowFirst + kSlots);   // [kSlots]
-  // per-warp pair scratch
-  long long* sPairBase = reinterpret_cast<long long*>(sVoxOf + kSlots);       // [4 warps][8]
-  unsigned* sPairCode = reinterpret_cast<unsigned*>(sPairBase + (kSlots / 32) * 8);   // [4 warps][8]
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int v0 = lv.batch_vox[b], v1 = lv.batch_vox[b + 1], nv = v1 - v0;
@@ -174,7 +173,7 @@ lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, 
     double out[10];
     transform_cluster(s, out);
 #pragma unroll
-    for (int q = 0; q < 10; ++q) stage[tid * kStageStride + q] = out[q];
+    for (int q = 0; q < 10; ++q) stage[tid * kLStage + q] = out[q];
     sPose[tid] = pose;
     const long long rs = env.row_start[pose];
     const int fr = env.first[pose];
@@ -205,6 +204,7 @@ lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, 
   __syncthreads();
 
   // ---- phase 3: per slot A_i, g_i, H_ii, factors (bavoxel.hpp:112-149)
+  double Hb[36];
   if (tid < ns) {
     const double* vp = sV + sVoxOf[tid] * kVoxParams;
     const double uk[3] = {vp[0], vp[1], vp[2]}, u1[3] = {vp[3], vp[4], vp[5]}, u2[3] = {vp[6], vp[7], vp[8]};
@@ -247,7 +247,6 @@ lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, 
       f2[j] = Auk[j] * u2[0] + Auk[6 + j] * u2[1] + Auk[12 + j] * u2[2];
     }
     // diagonal block
-    double Hb[36];
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -276,10 +275,7 @@ lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, 
           Hb[6 * (3 + i) + 3 + j] += k33 * uk[i] * uk[j];
         }
     }
-    // stage: diagonal block, gradient, factors
-    double* st = stage + tid * kStageStride;
-#pragma unroll
-    for (int q = 0; q < 36; ++q) st[q] = Hb[q];
+    // stage: gradient, factors (the diagonal block follows in two halves, below)
     double* sg = sG + tid * 6;
     double* sf = sF + tid * kFStride;
     // off-diagonal blocks are  c1 f1 f1^T + c2 f2 f2^T - 2/N^2 b b^T  with c1, c2 < 0 (lambda0 is the smallest
@@ -291,69 +287,83 @@ lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, 
     const double s3n = s3 * s.n;
     sf[15] = s3n * uk[0]; sf[16] = s3n * uk[1]; sf[17] = s3n * uk[2];
   }
-  __syncthreads();
 
-  // ---- phase 4a: flush diagonal blocks and gradients (coalesced REDs)
-  for (int e = tid; e < ns * 36; e += kSlots) {
-    const int sl = e / 36, el = e - sl * 36;
-    atomicAdd(H + sDiag[sl] + el, stage[sl * kStageStride + el]);
+  // ---- phase 4a: flush diagonal blocks (two halves through the staging buffer: 18 doubles per slot keep the CTA at
+  //      55 kB of shared memory = 4 CTAs per SM) and gradients, 32 consecutive doubles per warp instruction
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    __syncthreads();                                      // half 0: phase 2 is done with the clusters; half 1: flush 0 is done
+    if (tid < ns) {
+      double* st = stage + tid * kLStage;
+#pragma unroll
+      for (int q = 0; q < 18; ++q) st[q] = Hb[18 * half + q];
+    }
+    __syncthreads();
+    for (int e = tid; e < ns * 18; e += kSlots) {
+      const int sl = e / 18, el = e - sl * 18;
+      atomicAdd(H + sDiag[sl] + 18 * half + el, stage[sl * kLStage + el]);
+    }
   }
   for (int e = tid; e < ns * 6; e += kSlots) {
     const int sl = e / 6, el = e - sl * 6;
     atomicAdd(g + 6 * (long long)sPose[sl] + el, sG[e]);
   }
 
-  // ---- phase 4b: off-diagonal blocks, 8 pairs (288 elements) per warp iteration
+  // ---- phase 4b: off-diagonal blocks, 8 pairs (288 elements) per warp iteration.
+  // Lane (pq, k) = (lane >> 2, lane & 3) owns the elements 4 m + k, m = 0..8, of pair pq: every RED instruction of the warp
+  // writes one aligned 32-byte sector per pair (8 full sectors, as a linear mapping would), but a lane stays inside one pair,
+  // so its factors are read from shared memory once — 27 loads for 9 elements instead of 6 per element.  With el = 4 m + k,
+  // row = el / 6 and column = el % 6 depend on the lane only through k:
+  //   m % 3 == 0: row 2j,                 column k
+  //   m % 3 == 1: row 2j + (k >= 2),      column k < 2 ? 4 + k : k - 2
+  //   m % 3 == 2: row 2j + 1,             column 2 + k                      (j = m / 3)
+  // so the three columns sit in registers indexed by m % 3 (compile time) and the row of the middle case is a select.
   const long long p0 = lv.batch_pair[b], np = lv.batch_pair[b + 1] - p0;
-  long long* myBase = sPairBase + warp * 8;
-  unsigned* myCode = sPairCode + warp * 8;
-  // lane-constant decode of element e = lane + 32 m -> (pair slot pr, row a, col bq, el): pr | a<<4 | bq<<8 | el<<12
-  unsigned dec[9];
-#pragma unroll
-  for (int m = 0; m < 9; ++m) {
-    const int e = lane + 32 * m;
-    const int pr = e / 36, el = e - pr * 36, aa = el / 6, bq = el - aa * 6;
-    dec[m] = (unsigned)pr | ((unsigned)aa << 4) | ((unsigned)bq << 8) | ((unsigned)el << 12);
-  }
+  const int pq = lane >> 2, k = lane & 3;
+  const bool hi = k >= 2;
+  const int col0 = k, col1 = hi ? k - 2 : 4 + k, col2 = 2 + k;
   unsigned code_next = 0;
   {
     const long long c0 = (long long)warp * 8;
-    if (c0 + lane < np && lane < 8) code_next = lv.pairs[p0 + c0 + lane];
+    if (c0 + pq < np) code_next = lv.pairs[p0 + c0 + pq];
   }
   for (long long c = (long long)warp * 8; c < np; c += (kSlots / 32) * 8) {
-    const int cnt = (int)((np - c < 8) ? (np - c) : 8);
+    const bool live = c + pq < np;
     const unsigned code = code_next;
     {                                                     // prefetch the next chunk's pair codes
       const long long cn = c + (kSlots / 32) * 8;
-      code_next = (lane < 8 && cn + lane < np) ? lv.pairs[p0 + cn + lane] : 0u;
+      code_next = (cn + pq < np) ? lv.pairs[p0 + cn + pq] : 0u;
     }
-    __syncwarp();
-    if (lane < cnt) {
+    if (live) {
       const int li = code & 0xff, lj = (code >> 8) & 0xff;
       // lower-triangle block: row = larger pose (slot lj, ascending order inside a voxel), col = slot li
-      myBase[lane] = (sRowRS[lj] + (sPose[li] - sRowFirst[lj])) * 36;
-      myCode[lane] = (unsigned)(li * kFStride) | ((unsigned)(lj * kFStride) << 16);
-    }
-    __syncwarp();
+      double* dst = H + (sRowRS[lj] + (sPose[li] - sRowFirst[lj])) * 36 + k;
+      const double* fi = sF + li * kFStride;               // column factors
+      const double* fj = sF + lj * kFStride;               // row factors
+      double ci[3][3], rj[6][3];
 #pragma unroll
-    for (int m = 0; m < 9; ++m) {
-      const unsigned d = dec[m];
-      const int pr = d & 15;
-      if (pr < cnt) {
-        const unsigned off = myCode[pr];
-        const double* fi = sF + (off & 0xffff) + ((d >> 8) & 15);      // column index bq of the (j,i) block
-        const double* fj = sF + (off >> 16) + ((d >> 4) & 15);         // row index a
-        const double val = -(fi[0] * fj[0] + fi[6] * fj[6] + fi[12] * fj[12]);
-        atomicAdd(H + myBase[pr] + (d >> 12), val);
+      for (int t = 0; t < 3; ++t) { ci[0][t] = fi[6 * t + col0]; ci[1][t] = fi[6 * t + col1]; ci[2][t] = fi[6 * t + col2]; }
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) rj[a][t] = fj[6 * t + a];
+#pragma unroll
+      for (int m = 0; m < 9; ++m) {
+        const int j2 = 2 * (m / 3), ph = m % 3;
+        double r0, r1, r2;
+        if (ph == 0) { r0 = rj[j2][0]; r1 = rj[j2][1]; r2 = rj[j2][2]; }
+        else if (ph == 2) { r0 = rj[j2 + 1][0]; r1 = rj[j2 + 1][1]; r2 = rj[j2 + 1][2]; }
+        else { r0 = hi ? rj[j2 + 1][0] : rj[j2][0]; r1 = hi ? rj[j2 + 1][1] : rj[j2][1]; r2 = hi ? rj[j2 + 1][2] : rj[j2][2]; }
+        const double val = -(ci[ph][0] * r0 + ci[ph][1] * r1 + ci[ph][2] * r2);
+        atomicAdd(dst + 4 * m, val);
       }
     }
   }
 }
 
 constexpr size_t lidar_build_smem_bytes() {
-  return sizeof(double) * (kSlots * kStageStride + kSlots * kFStride + kSlots * 6 + kMaxVoxPerBatch * kVoxParams + 32)
-       + sizeof(long long) * 2 * kSlots + sizeof(int) * 2 * kSlots + kSlots /*u8*/
-       + sizeof(long long) * (kSlots / 32) * 8 + sizeof(unsigned) * (kSlots / 32) * 8 + 64;
+  return sizeof(double) * (kSlots * kLStage + kSlots * kFStride + kSlots * 6 + kMaxVoxPerBatch * kVoxParams + 32)
+       + sizeof(long long) * 2 * kSlots + sizeof(int) * 2 * kSlots + kSlots /*u8*/ + 64;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -345,7 +345,8 @@ constexpr int kDenseInvWarp = 480;           // threads 480..511: the warp that 
 constexpr int kDenseColBase = 512;           // threads 512..703: 6 warps, warp = row of the 6 x 6 block, lane = block row
 constexpr int kDenseColThreads = 192;
 constexpr int kDenseThreads = 768;           // 4 + 2 warpgroups (704..767 idle): the register re-allocation works on warpgroups
-constexpr int kDensePairRegs = 96, kDenseColRegs = 64;       // 512 * 96 + 256 * 64 == 65536 ; launched at 80
+constexpr int kDensePairRegs = 96, kDenseColRegs = 48;       // 512 * 96 + 256 * 48 == 768 * 80 = 61440, the pool the CTA is launched with: setmaxnreg.inc waits for ever if the budgets exceed it
+static_assert((kDenseColBase) * kDensePairRegs + (kDenseThreads - kDenseColBase) * kDenseColRegs <= kDenseThreads * 80, "register budgets exceed the launch pool");
 constexpr int kDenseS = 38;                  // doubles per operand block in shared memory (bank spread, 16 B aligned)
 constexpr size_t kDenseSmem = sizeof(double) * (6 * kDenseMax * kDenseS + 36 + 36 + kDenseMax * 6 + 8);
 

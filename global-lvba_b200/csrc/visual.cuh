@@ -333,8 +333,6 @@ visual_build_kernel(VisualView vv, EnvView env, VisualState st, VisualLM lm, dou
   long long* sRowRS = sDiag + kSlots;                            // [kSlots] envelope row_start of the camera row
   int* sRow = reinterpret_cast<int*>(sRowRS + kSlots);           // [kSlots]
   int* sRowFirst = sRow + kSlots;                                // [kSlots]
-  long long* sPairBase = reinterpret_cast<long long*>(sRowFirst + kSlots);     // [warps][8]
-  unsigned* sPairCode = reinterpret_cast<unsigned*>(sPairBase + (kSlots / 32) * 8);
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t0 = vv.batch_trk[b], t1 = vv.batch_trk[b + 1], nt = t1 - t0;
@@ -420,46 +418,45 @@ visual_build_kernel(VisualView vv, EnvView env, VisualState st, VisualLM lm, dou
       atomicAdd(dst + 6 * (long long)r + a, sG[e]);
     }
   }
-  // ---- phase 4b: camera pairs
+  // ---- phase 4b: camera pairs.  Lane (pq, k) = (lane >> 2, lane & 3) owns the elements 4 m + k, m = 0..8, of pair pq (the
+  //      mapping of lidar_build_kernel's phase 4b): one aligned 32-byte sector per pair and instruction, factors read once.
   const long long p0 = vv.batch_pair[b], np = vv.batch_pair[b + 1] - p0;
-  long long* myBase = sPairBase + warp * 8;
-  unsigned* myCode = sPairCode + warp * 8;
-  unsigned dec[9];
-#pragma unroll
-  for (int m = 0; m < 9; ++m) {
-    const int e = lane + 32 * m;
-    const int pr = e / 36, el = e - pr * 36, aa = el / 6, bq = el - aa * 6;
-    dec[m] = (unsigned)pr | ((unsigned)aa << 4) | ((unsigned)bq << 8) | ((unsigned)el << 12);
-  }
+  const int pq = lane >> 2, k = lane & 3;
+  const bool upper = k >= 2;
+  const int col0 = k, col1 = upper ? k - 2 : 4 + k, col2 = 2 + k;
   unsigned code_next = 0;
   {
     const long long c0 = (long long)warp * 8;
-    if (c0 + lane < np && lane < 8) code_next = vv.pairs[p0 + c0 + lane];
+    if (c0 + pq < np) code_next = vv.pairs[p0 + c0 + pq];
   }
   for (long long c = (long long)warp * 8; c < np; c += (kSlots / 32) * 8) {
-    const int cnt = (int)((np - c < 8) ? (np - c) : 8);
+    const bool live = c + pq < np;
     const unsigned code = code_next;
     {
       const long long cn = c + (kSlots / 32) * 8;
-      code_next = (lane < 8 && cn + lane < np) ? vv.pairs[p0 + cn + lane] : 0u;
+      code_next = (cn + pq < np) ? vv.pairs[p0 + cn + pq] : 0u;
     }
-    __syncwarp();
-    if (lane < cnt) {
+    if (live) {
       const int hi = code & 0xff, lo = (code >> 8) & 0xff;
-      myBase[lane] = (sRowRS[hi] + (sRow[lo] - sRowFirst[hi])) * 36;
-      myCode[lane] = (unsigned)(hi * kVFStride) | ((unsigned)(lo * kVFStride + 18) << 16);
-    }
-    __syncwarp();
+      double* dst = S + (sRowRS[hi] + (sRow[lo] - sRowFirst[hi])) * 36 + k;
+      const double* y = sF + hi * kVFStride;               // Y_hi, row a at 3 a
+      const double* ee = sF + lo * kVFStride + 18;         // E_lo, row bq at 3 bq
+      double ce[3][3], ry[6][3];
 #pragma unroll
-    for (int m = 0; m < 9; ++m) {
-      const unsigned d = dec[m];
-      const int pr = d & 15;
-      if (pr < cnt) {
-        const unsigned off = myCode[pr];
-        const double* y = sF + (off & 0xffff) + 3 * ((d >> 4) & 15);      // Y_hi row a
-        const double* ee = sF + (off >> 16) + 3 * ((d >> 8) & 15);        // E_lo row bq
-        const double val = -(y[0] * ee[0] + y[1] * ee[1] + y[2] * ee[2]);
-        atomicAdd(S + myBase[pr] + (d >> 12), val);
+      for (int t = 0; t < 3; ++t) { ce[0][t] = ee[3 * col0 + t]; ce[1][t] = ee[3 * col1 + t]; ce[2][t] = ee[3 * col2 + t]; }
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) ry[a][t] = y[3 * a + t];
+#pragma unroll
+      for (int m = 0; m < 9; ++m) {
+        const int j2 = 2 * (m / 3), ph = m % 3;
+        double r0, r1, r2;
+        if (ph == 0) { r0 = ry[j2][0]; r1 = ry[j2][1]; r2 = ry[j2][2]; }
+        else if (ph == 2) { r0 = ry[j2 + 1][0]; r1 = ry[j2 + 1][1]; r2 = ry[j2 + 1][2]; }
+        else { r0 = upper ? ry[j2 + 1][0] : ry[j2][0]; r1 = upper ? ry[j2 + 1][1] : ry[j2][1]; r2 = upper ? ry[j2 + 1][2] : ry[j2][2]; }
+        const double val = -(r0 * ce[ph][0] + r1 * ce[ph][1] + r2 * ce[ph][2]);
+        atomicAdd(dst + 4 * m, val);
       }
     }
   }
@@ -467,8 +464,7 @@ visual_build_kernel(VisualView vv, EnvView env, VisualState st, VisualLM lm, dou
 
 constexpr size_t visual_build_smem_bytes() {
   return sizeof(double) * (kSlots * kStageStride + kSlots * kVFStride + kSlots * 18 + kMaxTrkPerBatch * kTrkParams + 32)
-       + sizeof(long long) * 2 * kSlots + sizeof(int) * 2 * kSlots
-       + sizeof(long long) * (kSlots / 32) * 8 + sizeof(unsigned) * (kSlots / 32) * 8 + 64;
+       + sizeof(long long) * 2 * kSlots + sizeof(int) * 2 * kSlots + 64;
 }
 
 // ------------------------------------------------------------------------------------------------
