@@ -230,6 +230,16 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   cudaStream_t s = P->stream;
 
   lap("ctx/stream/pinned");
+  // the caller's cluster records (the bulk of the upload: 80 B per slot) start crossing PCIe now, in ONE copy, while the
+  // host derives the structure below; every path further down reads them from `aos_dev`
+  DevBuf<double> aos;
+  const double* aos_dev = d_clusters;
+  if (!aos_dev && vox_ptr[V] > 0) {
+    LVBA_TRY(aos.alloc((size_t)vox_ptr[V] * 10));
+    LVBA_CUDA(cudaMemcpyAsync(aos.p, clusters, (size_t)vox_ptr[V] * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
+    P->h2d += vox_ptr[V] * 80;
+    aos_dev = aos.p;
+  }
   P->h_vox_ptr_all.assign(vox_ptr, vox_ptr + V + 1);
   P->h_pose_idx_all.assign(pose_idx, pose_idx + vox_ptr[V]);
   lap("host copies");
@@ -237,9 +247,18 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   // ---- envelope structure over ALL voxels (identical on every rank)
   std::vector<int> first_raw(W);
   for (int r = 0; r < W; ++r) first_raw[r] = r;
-  for (int64_t a = 0; a < V; ++a) {
-    const int m = pose_idx[vox_ptr[a]];
-    for (int64_t q = vox_ptr[a]; q < vox_ptr[a + 1]; ++q) first_raw[pose_idx[q]] = std::min(first_raw[pose_idx[q]], m);
+  {
+    std::vector<int> first_w((size_t)kMaxSetupThreads * (size_t)W);
+    for (int w = 0; w < kMaxSetupThreads; ++w) std::copy(first_raw.begin(), first_raw.end(), first_w.begin() + (size_t)w * (size_t)W);
+    parallel_chunks(V, 1 << 14, [&](int64_t a0, int64_t a1, int w) {
+      int* fr = first_w.data() + (size_t)w * (size_t)W;
+      for (int64_t a = a0; a < a1; ++a) {
+        const int m = pose_idx[vox_ptr[a]];
+        for (int64_t q = vox_ptr[a]; q < vox_ptr[a + 1]; ++q) fr[pose_idx[q]] = std::min(fr[pose_idx[q]], m);
+      }
+    });
+    for (int w = 0; w < kMaxSetupThreads; ++w)
+      for (int r = 0; r < W; ++r) first_raw[r] = std::min(first_raw[r], first_w[(size_t)w * (size_t)W + r]);
   }
   LVBA_TRY(P->env.build(first_raw, s, &P->h2d));
   LVBA_TRY(P->solver.prepare(P->env, s));
@@ -348,43 +367,25 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   const long long nnz_pad = ((nnz + 31) / 32) * 32 + 32;
   LVBA_TRY(P->cl.alloc((size_t)5 * nnz_pad));
   LVBA_TRY(P->cl.zero(s));
-  std::vector<int> l_pidx((size_t)nnz);
+  const bool contiguous = Vl == V && n_groups == 0 && !sorted_voxels;       // single rank, caller's order: the records and pose indices are used as they are
+  std::vector<int> l_pidx(contiguous ? (size_t)0 : (size_t)nnz);
   {
-    DevBuf<double> aos;
-    const bool contiguous = Vl == V && n_groups == 0 && !sorted_voxels;     // single rank, caller's order: the records go up as they are
     if (contiguous) {
-      const double* aos_src = d_clusters;
-      if (!aos_src) LVBA_TRY(aos.alloc((size_t)std::max<long long>(nnz, 1) * 10));
       if (nnz > 0) {
-        if (!aos_src) {
-          LVBA_CUDA(cudaMemcpyAsync(aos.p, clusters, (size_t)nnz * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
-          P->h2d += nnz * 80;
-          aos_src = aos.p;
-        }
-        std::copy(pose_idx, pose_idx + nnz, l_pidx.begin());
-        lidar_aos_to_soa_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(nnz, nnz_pad, aos_src, P->cl.p);
+        lidar_aos_to_soa_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(nnz, nnz_pad, aos_dev, P->cl.p);
         ++P->launches;
       }
-      LVBA_CUDA(cudaStreamSynchronize(s));   // aos is freed on scope exit
     } else {
-      // a shard (or a window-sorted batch) owns scattered voxels: ONE copy of the caller's array + a device-side gather
+      // a shard (or a window-sorted batch) owns scattered voxels: the ONE copy of the caller's array + a device-side gather
       // (per-run copies cost ~2.5 us each: 100k runs = 250 ms on a 2-rank split of config C)
-      const long long nnz_all = vox_ptr[V];
-      const double* aos_src = d_clusters;
-      if (!aos_src) LVBA_TRY(aos.alloc((size_t)std::max<long long>(nnz_all, 1) * 10));
       std::vector<int> src((size_t)nnz);
       long long w = 0;
       for (int64_t i = 0; i < Vl; ++i)
         for (int64_t q = vox_ptr[mine[i]]; q < vox_ptr[mine[i] + 1]; ++q, ++w) { src[w] = (int)q; l_pidx[w] = pose_idx[q]; }
       DevBuf<int> d_src;
       if (nnz > 0) {
-        if (!aos_src) {
-          LVBA_CUDA(cudaMemcpyAsync(aos.p, clusters, (size_t)nnz_all * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
-          P->h2d += nnz_all * 80;
-          aos_src = aos.p;
-        }
         LVBA_TRY(d_src.upload(src, s, &P->h2d));
-        lidar_aos_to_soa_gather_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(nnz, nnz_pad, aos_src, d_src.p, P->cl.p);
+        lidar_aos_to_soa_gather_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(nnz, nnz_pad, aos_dev, d_src.p, P->cl.p);
         ++P->launches;
       }
       if (!bigv.empty()) {                   // the big voxels' records stay AoS (lidar_big.h reads them slot by slot)
@@ -398,11 +399,6 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
           bpp.push_back(bpp.back() + K * (K - 1) / 2);
         }
         P->n_big = (long long)bigv.size(); P->n_big_slots = (long long)bsrc.size(); P->n_big_pairs = bpp.back();
-        if (!aos_src) {                      // no slot of this rank was small: the records are not on the device yet
-          LVBA_CUDA(cudaMemcpyAsync(aos.p, clusters, (size_t)nnz_all * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
-          P->h2d += nnz_all * 80;
-          aos_src = aos.p;
-        }
         DevBuf<int> d_bsrc;
         LVBA_TRY(d_bsrc.upload(bsrc, s, &P->h2d));
         LVBA_TRY(P->big_vox_ptr.upload(bvp, s, &P->h2d));
@@ -411,15 +407,17 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
         LVBA_TRY(P->big_cl.alloc((size_t)P->n_big_slots * 10));
         LVBA_TRY(P->big_params.alloc((size_t)P->n_big * big::kParams));
         LVBA_TRY(P->big_feat.alloc((size_t)P->n_big_slots * big::kFeat));
-        lidar_gather_aos_kernel<<<(unsigned)((P->n_big_slots + 255) / 256), 256, 0, s>>>(P->n_big_slots, d_bsrc.p, aos_src, P->big_cl.p);
+        lidar_gather_aos_kernel<<<(unsigned)((P->n_big_slots + 255) / 256), 256, 0, s>>>(P->n_big_slots, d_bsrc.p, aos_dev, P->big_cl.p);
         ++P->launches;
         LVBA_CUDA(cudaStreamSynchronize(s)); // the host vectors and d_bsrc go out of scope
       }
-      LVBA_CUDA(cudaStreamSynchronize(s));   // aos, src, d_src are freed on scope exit
+      LVBA_CUDA(cudaStreamSynchronize(s));   // src and d_src are freed on scope exit
     }
   }
   if (tlog) { cudaStreamSynchronize(s); } lap("cluster upload+SoA");
-  LVBA_TRY(P->pidx.upload(l_pidx, s, &P->h2d));
+  static_assert(sizeof(int) == sizeof(int32_t), "pose_idx is uploaded as it is");
+  if (contiguous) LVBA_TRY(P->pidx.upload(reinterpret_cast<const int*>(pose_idx), (size_t)nnz, s, &P->h2d));
+  else LVBA_TRY(P->pidx.upload(l_pidx, s, &P->h2d));
   LVBA_TRY(P->vox_ptr.upload(l_vox_ptr, s, &P->h2d));
   LVBA_TRY(P->batch_vox.upload(batch_vox, s, &P->h2d));
   LVBA_TRY(P->batch_pair.upload(batch_pair, s, &P->h2d));
@@ -441,6 +439,7 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   LVBA_TRY(P->scal.zero(s));
   LVBA_CUDA(cudaFuncSetAttribute(lidar_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lidar_build_smem_bytes()));
   LVBA_CUDA(cudaStreamSynchronize(s));
+  aos.release();                                               // the caller's records were consumed by the kernels above
   lap("index upload+allocs");
   lvba_lidar_default_opts(&P->opts);
   P->ms_setup = wall_ms() - t0;

@@ -181,13 +181,13 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
 // 4 x 4 register tile.  Partial sums of the row groups meet in U by RED.ADD.F64.  FP64-FMA bound.
 constexpr int kSyrkTile = 64;            // scalar columns per tile side
 constexpr int kSyrkChunk = 4;            // block rows per shared-memory chunk (24 scalar rows)
-constexpr int kSyrkSplit = 32;           // block rows per CTA
+constexpr int kSyrkSplit = 8;            // block rows per CTA (default; LVBA_SYRK_SPLIT overrides): two chunks, both in flight from the start
 constexpr int kSyrkLd = kSyrkTile + 4;   // leading dimension of the shared tiles
 constexpr int kSyrkTileDoubles = kSyrkChunk * 6 * kSyrkLd;
 constexpr size_t kSyrkSmem = sizeof(double) * (5 * kSyrkTileDoubles + 2 * kSyrkChunk * 36 + 2 * kSyrkChunk * 6 + kSyrkChunk * 6);
 
 __global__ void __launch_bounds__(256)
-nd_syrk_kernel(const nd::SyrkSeg* __restrict__ segs) {
+nd_syrk_kernel(const nd::SyrkSeg* __restrict__ segs, int split) {
   constexpr int TS = kSyrkTile, RC = kSyrkChunk * 6, LD = kSyrkLd;
   extern __shared__ __align__(16) double smem_syrk[];
   double* sA = smem_syrk;                             // [2][RC][LD] Z[r][tile row side]
@@ -200,9 +200,9 @@ nd_syrk_kernel(const nd::SyrkSeg* __restrict__ segs) {
   int ti = 0, tj = 0;                                 // tile (ti, tj), tj <= ti, from the linear index
   { int t = blockIdx.x; while ((ti + 1) * (ti + 2) / 2 <= t) ++ti; tj = t - ti * (ti + 1) / 2; }
   if (ti * TS >= G.KS) return;
-  const int k0 = blockIdx.y * kSyrkSplit;
+  const int k0 = blockIdx.y * split;
   if (k0 >= G.rows) return;
-  const int k1 = min(G.rows, k0 + kSyrkSplit);
+  const int k1 = min(G.rows, k0 + split);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int KS = G.KS;
   // chunk kc -> buffer par: 16-byte pieces (KS is even, the tiles start at even columns); rows / columns beyond the data are zero-filled
@@ -353,8 +353,8 @@ constexpr size_t kDenseSmem = sizeof(double) * (6 * kDenseMax * kDenseS + 36 + 3
 __global__ void __launch_bounds__(kDenseThreads, 1)
 nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short* __restrict__ tmap) {
   extern __shared__ __align__(16) double smem_dense[];
-  double* sL = smem_dense;                                 // [2][30][S] L_{i,s}   parity s & 1
-  double* sT = sL + 2 * kDenseMax * kDenseS;               // [2][30][S] T_{i,s}   parity s & 1
+  double* sL = smem_dense;                                 // [2][30][S] L_{i,s}^T ([q * 6 + x] = L[x][q])   parity s & 1
+  double* sT = sL + 2 * kDenseMax * kDenseS;               // [2][30][S] T_{i,s}^T   parity s & 1
   double* sC = sT + 2 * kDenseMax * kDenseS;               // [2][30][S] column c as the pair threads left it, parity c & 1
   double* sD = sC + 2 * kDenseMax * kDenseS;               // [36] pivot block (rows written by the six threads of block row s)
   double* sK = sD + 36;                                    // [36] its inverse
@@ -381,16 +381,14 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
         const double2* c2 = reinterpret_cast<const double2*>(sC + (par * kDenseMax + i) * kDenseS + r * 6);
         const double2 q0 = c2[0], q1 = c2[1], q2 = c2[2];
         t[0] = q0.x; t[1] = q0.y; t[2] = q1.x; t[3] = q1.y; t[4] = q2.x; t[5] = q2.y;
-        if (s > 0) {                                               // -= L_{i,s-1}[r][.] T_{s,s-1}^T
-          const double* ts = sT + ((par ^ 1) * kDenseMax + s) * kDenseS;
+        if (s > 0) {                                               // -= L_{i,s-1}[r][.] T_{s,s-1}^T   (sT holds T^T: [q][y])
+          const double2* ts = reinterpret_cast<const double2*>(sT + ((par ^ 1) * kDenseMax + s) * kDenseS);
 #pragma unroll
-          for (int y = 0; y < 6; ++y) {
-            const double2 u0 = reinterpret_cast<const double2*>(ts + y * 6)[0], u1 = reinterpret_cast<const double2*>(ts + y * 6)[1],
-                          u2 = reinterpret_cast<const double2*>(ts + y * 6)[2];
-            double a = t[y];
-            a = fma(-lrow[0], u0.x, a); a = fma(-lrow[1], u0.y, a); a = fma(-lrow[2], u1.x, a);
-            a = fma(-lrow[3], u1.y, a); a = fma(-lrow[4], u2.x, a); a = fma(-lrow[5], u2.y, a);
-            t[y] = a;
+          for (int q = 0; q < 6; ++q) {
+            const double2 u0 = ts[3 * q], u1 = ts[3 * q + 1], u2 = ts[3 * q + 2];
+            const double l = -lrow[q];
+            t[0] = fma(l, u0.x, t[0]); t[1] = fma(l, u0.y, t[1]); t[2] = fma(l, u1.x, t[2]);
+            t[3] = fma(l, u1.y, t[3]); t[4] = fma(l, u2.x, t[4]); t[5] = fma(l, u2.y, t[5]);
           }
         }
         if (i == s) {
@@ -412,15 +410,13 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
           for (int q = 1; q < 6; ++q) a = fma(t[q], sK[q * 6 + c], a);
           lr[c] = a;
         }
-        double2* t2 = reinterpret_cast<double2*>(sT + (par * kDenseMax + i) * kDenseS + r * 6);
-        double2* l2 = reinterpret_cast<double2*>(sL + (par * kDenseMax + i) * kDenseS + r * 6);
+        double* tt = sT + (par * kDenseMax + i) * kDenseS + r;       // transposed operand blocks: [q * 6 + row]
+        double* lt = sL + (par * kDenseMax + i) * kDenseS + r;
         double2* g2 = reinterpret_cast<double2*>(J.L + ((long long)i * (i + 1) / 2 + s) * 36 + r * 6);
 #pragma unroll
-        for (int h = 0; h < 3; ++h) {
-          t2[h] = make_double2(t[2 * h], t[2 * h + 1]);
-          const double2 lv = make_double2(lr[2 * h], lr[2 * h + 1]);
-          l2[h] = lv; g2[h] = lv;
-        }
+        for (int q = 0; q < 6; ++q) { tt[q * 6] = t[q]; lt[q * 6] = lr[q]; }
+#pragma unroll
+        for (int h = 0; h < 3; ++h) g2[h] = make_double2(lr[2 * h], lr[2 * h + 1]);
         double zs = 0.0;
 #pragma unroll
         for (int q = 0; q < 6; ++q) { zs = fma(lr[q], sZ[s * 6 + q], zs); lrow[q] = lr[q]; }
@@ -480,18 +476,23 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
       // the trailing update of pivot s-1 for the columns the pair threads still own (j >= s+1)
       if (s >= 1 && live && j >= s + 1) {
         const int par = (s - 1) & 1;
-        const double2* l2 = reinterpret_cast<const double2*>(sL + (par * kDenseMax + i) * kDenseS);
-        const double2* t2 = reinterpret_cast<const double2*>(sT + (par * kDenseMax + j) * kDenseS);
+        // rank-1 steps over the contraction index q: column q of T_j (six values) and two entries of column q of L_i at a time are
+        // live beside the 36 accumulators — 16 operand registers, which is what fits the 96-register budget without spilling G
+        const double2* l2 = reinterpret_cast<const double2*>(sL + (par * kDenseMax + i) * kDenseS);     // L_i^T: [q][x]
+        const double2* t2 = reinterpret_cast<const double2*>(sT + (par * kDenseMax + j) * kDenseS);     // T_j^T: [q][y]
 #pragma unroll
-        for (int y = 0; y < 6; ++y) {
-          const double2 t0 = t2[3 * y], t1 = t2[3 * y + 1], t2v = t2[3 * y + 2];
+        for (int q = 0; q < 6; ++q) {
+          const double2 t0 = t2[3 * q], t1 = t2[3 * q + 1], t2v = t2[3 * q + 2];
 #pragma unroll
-          for (int x = 0; x < 6; ++x) {
-            const double2 a0 = l2[3 * x], a1 = l2[3 * x + 1], a2 = l2[3 * x + 2];
-            double a = G[x * 6 + y];
-            a = fma(-a0.x, t0.x, a); a = fma(-a0.y, t0.y, a); a = fma(-a1.x, t1.x, a);
-            a = fma(-a1.y, t1.y, a); a = fma(-a2.x, t2v.x, a); a = fma(-a2.y, t2v.y, a);
-            G[x * 6 + y] = a;
+          for (int xp = 0; xp < 3; ++xp) {
+            const double2 lv = l2[3 * q + xp];
+            const double l0 = -lv.x, l1 = -lv.y;
+            double* g0 = G + (2 * xp) * 6;
+            double* g1 = G + (2 * xp + 1) * 6;
+            g0[0] = fma(l0, t0.x, g0[0]); g0[1] = fma(l0, t0.y, g0[1]); g0[2] = fma(l0, t1.x, g0[2]);
+            g0[3] = fma(l0, t1.y, g0[3]); g0[4] = fma(l0, t2v.x, g0[4]); g0[5] = fma(l0, t2v.y, g0[5]);
+            g1[0] = fma(l1, t0.x, g1[0]); g1[1] = fma(l1, t0.y, g1[1]); g1[2] = fma(l1, t1.x, g1[2]);
+            g1[3] = fma(l1, t1.y, g1[3]); g1[4] = fma(l1, t2v.x, g1[4]); g1[5] = fma(l1, t2v.y, g1[5]);
           }
         }
         if (j == s + 1) publish(s + 1);                            // column s+1 (updated through pivot s-1) -> column group, iteration s+1

@@ -58,6 +58,91 @@ struct lvba_visual_problem {
 
 namespace lvba {
 
+// ---- set-up kernels: the per-observation arrays and the pair table are derived on the device from the caller's arrays
+// (uploaded as they are: one DMA each from the caller's — ideally pinned — memory) instead of being gathered on the host
+// and pushed through pageable staging copies (config C: 16 MB of observations + 18 MB of pair words).
+// One thread per local landmark k (source landmark trk_id[k]): its observations, camera rows and plane.
+__global__ void visual_gather_kernel(long long Tv, const int* __restrict__ trk_id, const int* __restrict__ trk_ptr,
+                                     const long long* __restrict__ obs_ptr, const int* __restrict__ raw_cam,
+                                     const float2* __restrict__ raw_uv, const double* __restrict__ raw_plane,
+                                     const int* __restrict__ row_of_cam, int* __restrict__ l_cam, int* __restrict__ l_row,
+                                     float2* __restrict__ l_uv, double* __restrict__ l_plane) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Tv) return;
+  const long long i = trk_id[k];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) l_plane[4 * k + j] = raw_plane[4 * i + j];
+  long long w = trk_ptr[k];
+  for (long long q = obs_ptr[i]; q < obs_ptr[i + 1]; ++q, ++w) {
+    const int c = raw_cam[q];
+    l_cam[w] = c; l_row[w] = row_of_cam[c]; l_uv[w] = raw_uv[q];
+  }
+}
+
+// The camera-pair words of one batch in the order visual_build_kernel walks them (landmarks ascending, x < y inside a
+// landmark; hi = the larger reduced row; a camera observed twice contributes both orderings).  Thread = landmark of the batch;
+// count == true writes the number of words of the batch to batch_pair[b + 1], otherwise the words go to pairs + batch_pair[b].
+template <bool kCount>
+__global__ void __launch_bounds__(kSlots)
+visual_pairs_kernel(const int* __restrict__ trk_ptr, const int* __restrict__ batch_trk, const int* __restrict__ obs_row,
+                    long long* __restrict__ batch_pair, unsigned* __restrict__ pairs) {
+  __shared__ long long off[kMaxTrkPerBatch + 1];
+  const int b = blockIdx.x, lt = threadIdx.x;
+  const int k0 = batch_trk[b], nt = batch_trk[b + 1] - k0, sbase = trk_ptr[k0];
+  int lo = 0, hi = 0;
+  long long cnt = 0;
+  if (lt < nt) {
+    lo = trk_ptr[k0 + lt] - sbase; hi = trk_ptr[k0 + lt + 1] - sbase;
+    for (int x = lo; x < hi; ++x) {
+      const int rx = obs_row[sbase + x];
+      if (rx < 0) continue;
+      for (int y = x + 1; y < hi; ++y) {
+        const int ry = obs_row[sbase + y];
+        if (ry < 0) continue;
+        cnt += (rx == ry) ? 2 : 1;
+      }
+    }
+    off[lt + 1] = cnt;
+  }
+  if (lt == 0) off[0] = 0;
+  __syncthreads();
+  if (lt == 0) for (int i = 0; i < nt; ++i) off[i + 1] += off[i];
+  __syncthreads();
+  if (kCount) {
+    if (lt == 0) batch_pair[b + 1] = off[nt];
+    return;
+  }
+  if (lt >= nt) return;
+  unsigned* dst = pairs + batch_pair[b] + off[lt];
+  const unsigned tl = (unsigned)lt << 16;
+  for (int x = lo; x < hi; ++x) {
+    const int rx = obs_row[sbase + x];
+    if (rx < 0) continue;
+    for (int y = x + 1; y < hi; ++y) {
+      const int ry = obs_row[sbase + y];
+      if (ry < 0) continue;
+      if (rx > ry) *dst++ = (unsigned)x | ((unsigned)y << 8) | tl;
+      else if (ry > rx) *dst++ = (unsigned)y | ((unsigned)x << 8) | tl;
+      else { *dst++ = (unsigned)x | ((unsigned)y << 8) | tl; *dst++ = (unsigned)y | ((unsigned)x << 8) | tl; }
+    }
+  }
+}
+
+// in-place inclusive scan of batch_pair[1..n] by one block (n_batches is a few ten thousand)
+__global__ void visual_pair_scan_kernel(int n, long long* __restrict__ batch_pair) {
+  __shared__ long long part[1024];
+  const int tid = threadIdx.x, per = (n + 1023) / 1024;
+  const int i0 = 1 + tid * per, i1 = min(n + 1, i0 + per);
+  long long s = 0;
+  for (int i = i0; i < i1; ++i) s += batch_pair[i];
+  part[tid] = s;
+  __syncthreads();
+  if (tid == 0) { long long run = 0; for (int w = 0; w < 1024; ++w) { const long long v = part[w]; part[w] = run; run += v; } batch_pair[0] = 0; }
+  __syncthreads();
+  long long run = part[tid];
+  for (int i = i0; i < i1; ++i) { run += batch_pair[i]; batch_pair[i] = run; }
+}
+
 inline bool plane_valid(const double* p) {   // has_valid_plane, src/lvba_system.cpp:1598
   for (int i = 0; i < 4; ++i) if (!std::isfinite(p[i])) return false;
   return std::fabs(p[0]) > 1e-6 || std::fabs(p[1]) > 1e-6 || std::fabs(p[2]) > 1e-6;
@@ -107,12 +192,27 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   // ---- valid landmarks, active cameras (src/lvba_system.cpp:1582-1583, 1598-1603)
   std::vector<int64_t> valid;
   std::vector<char> cam_used(M, 0);
-  for (int64_t i = 0; i < T; ++i) {
-    if (!plane_valid(plane_nd + 4 * i)) continue;
-    if (obs_ptr[i + 1] - obs_ptr[i] > kSlots)
-      return fail(LVBA_ERR_UNSUPPORTED, "landmark %lld has %lld observations; this build handles <= %d", (long long)i, (long long)(obs_ptr[i + 1] - obs_ptr[i]), kSlots);
-    valid.push_back(i);
-    for (int64_t q_ = obs_ptr[i]; q_ < obs_ptr[i + 1]; ++q_) cam_used[obs_cam[q_]] = 1;
+  {
+    std::vector<char> is_valid((size_t)T, 0), used_w((size_t)kMaxSetupThreads * (size_t)M, 0);
+    int64_t too_long[kMaxSetupThreads];
+    for (int w = 0; w < kMaxSetupThreads; ++w) too_long[w] = -1;
+    parallel_chunks(T, 1 << 13, [&](int64_t i0, int64_t i1, int w) {
+      char* used = used_w.data() + (size_t)w * (size_t)M;
+      for (int64_t i = i0; i < i1; ++i) {
+        if (!plane_valid(plane_nd + 4 * i)) continue;
+        if (obs_ptr[i + 1] - obs_ptr[i] > kSlots) { if (too_long[w] < 0) too_long[w] = i; continue; }
+        is_valid[(size_t)i] = 1;
+        for (int64_t q_ = obs_ptr[i]; q_ < obs_ptr[i + 1]; ++q_) used[obs_cam[q_]] = 1;
+      }
+    });
+    for (int w = 0; w < kMaxSetupThreads; ++w)
+      if (too_long[w] >= 0) {
+        const int64_t i = too_long[w];
+        return fail(LVBA_ERR_UNSUPPORTED, "landmark %lld has %lld observations; this build handles <= %d", (long long)i, (long long)(obs_ptr[i + 1] - obs_ptr[i]), kSlots);
+      }
+    for (int w = 0; w < kMaxSetupThreads; ++w)
+      for (int c = 0; c < M; ++c) cam_used[c] |= used_w[(size_t)w * (size_t)M + c];
+    for (int64_t i = 0; i < T; ++i) if (is_valid[(size_t)i]) valid.push_back(i);
   }
   if (fixed_cam >= 0 && fixed_cam < M) cam_used[fixed_cam] = 0;
   std::vector<int> row_of_cam(M, -1);
@@ -125,21 +225,31 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   std::vector<int> first_raw(std::max(P->n_rows, 1));
   for (int r = 0; r < P->n_rows; ++r) first_raw[r] = r;
   std::vector<int> min_row(Tv_all, 0), min_sys_row(Tv_all, 0);
-  for (int64_t k = 0; k < Tv_all; ++k) {
-    const int64_t i = valid[k];
-    int m = INT32_MAX, mcam = INT32_MAX;
-    for (int64_t q_ = obs_ptr[i]; q_ < obs_ptr[i + 1]; ++q_) {
-      const int r = row_of_cam[obs_cam[q_]];
-      if (r >= 0) m = std::min(m, r);
-      mcam = std::min(mcam, (int)obs_cam[q_]);
-    }
-    min_row[k] = (mcam == INT32_MAX) ? 0 : mcam;      // shard key: lowest camera index
-    min_sys_row[k] = (m == INT32_MAX) ? 0 : m;        // row-owned reduced system: lowest row of the landmark's clique
-    if (m == INT32_MAX) continue;
-    for (int64_t q_ = obs_ptr[i]; q_ < obs_ptr[i + 1]; ++q_) {
-      const int r = row_of_cam[obs_cam[q_]];
-      if (r >= 0) first_raw[r] = std::min(first_raw[r], m);
-    }
+  {
+    const size_t nr = first_raw.size();
+    std::vector<int> first_w((size_t)kMaxSetupThreads * nr);
+    for (int w = 0; w < kMaxSetupThreads; ++w) std::copy(first_raw.begin(), first_raw.end(), first_w.begin() + (size_t)w * nr);
+    parallel_chunks(Tv_all, 1 << 13, [&](int64_t k0, int64_t k1, int w) {
+      int* fr = first_w.data() + (size_t)w * nr;
+      for (int64_t k = k0; k < k1; ++k) {
+        const int64_t i = valid[k];
+        int m = INT32_MAX, mcam = INT32_MAX;
+        for (int64_t q_ = obs_ptr[i]; q_ < obs_ptr[i + 1]; ++q_) {
+          const int r = row_of_cam[obs_cam[q_]];
+          if (r >= 0) m = std::min(m, r);
+          mcam = std::min(mcam, (int)obs_cam[q_]);
+        }
+        min_row[k] = (mcam == INT32_MAX) ? 0 : mcam;      // shard key: lowest camera index
+        min_sys_row[k] = (m == INT32_MAX) ? 0 : m;        // row-owned reduced system: lowest row of the landmark's clique
+        if (m == INT32_MAX) continue;
+        for (int64_t q_ = obs_ptr[i]; q_ < obs_ptr[i + 1]; ++q_) {
+          const int r = row_of_cam[obs_cam[q_]];
+          if (r >= 0) fr[r] = std::min(fr[r], m);
+        }
+      }
+    });
+    for (int w = 0; w < kMaxSetupThreads; ++w)
+      for (size_t r = 0; r < nr; ++r) first_raw[r] = std::min(first_raw[r], first_w[(size_t)w * nr + r]);
   }
   if (P->n_rows > 0) {
     first_raw.resize(P->n_rows);
@@ -163,21 +273,7 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   }
   const long long nnz = trk_ptr[Tv];
   P->nnz = nnz;
-  std::vector<int> l_cam((size_t)nnz), l_row((size_t)nnz);
-  std::vector<float2> l_uv((size_t)nnz);
-  std::vector<double> l_plane((size_t)Tv * 4);
-  parallel_chunks(Tv, 1 << 13, [&](int64_t k0, int64_t k1, int) {
-    for (int64_t k = k0; k < k1; ++k) {
-      const int64_t i = mine[k];
-      for (int j = 0; j < 4; ++j) l_plane[4 * k + j] = plane_nd[4 * i + j];
-      long long w = trk_ptr[k];
-      for (int64_t q_ = obs_ptr[i]; q_ < obs_ptr[i + 1]; ++q_, ++w) {
-        l_cam[w] = obs_cam[q_]; l_row[w] = row_of_cam[obs_cam[q_]];
-        l_uv[w] = make_float2(obs_uv[2 * q_], obs_uv[2 * q_ + 1]);
-      }
-    }
-  });
-  lap("gather observations");
+  lap("landmark list");
   // ---- batches
   std::vector<int> batch_trk{0};
   {
@@ -190,55 +286,47 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
     if (Tv > 0) batch_trk.push_back((int)Tv);
   }
   P->n_batches = (int)batch_trk.size() - 1;
-  // ---- camera pair table (both cameras active; hi = larger reduced row)
-  std::vector<long long> batch_pair(P->n_batches + 1, 0);
-  std::vector<unsigned> pairs;
-  {
-    // visit the pairs of batch b in the order the build kernel walks them; emit(code) is called once per table entry
-    auto walk = [&](int b, auto&& emit) {
-      const int sbase = trk_ptr[batch_trk[b]];
-      for (int k = batch_trk[b]; k < batch_trk[b + 1]; ++k) {
-        const unsigned lt = (unsigned)(k - batch_trk[b]);
-        const int lo = trk_ptr[k] - sbase, hi = trk_ptr[k + 1] - sbase;
-        for (int x = lo; x < hi; ++x) {
-          if (l_row[sbase + x] < 0) continue;
-          for (int y2 = x + 1; y2 < hi; ++y2) {
-            if (l_row[sbase + y2] < 0) continue;
-            const int rx = l_row[sbase + x], ry = l_row[sbase + y2];
-            if (rx > ry) emit((unsigned)x | ((unsigned)y2 << 8) | (lt << 16));
-            else if (ry > rx) emit((unsigned)y2 | ((unsigned)x << 8) | (lt << 16));
-            else {   // same camera observed twice: both orderings land in the diagonal block
-              emit((unsigned)x | ((unsigned)y2 << 8) | (lt << 16));
-              emit((unsigned)y2 | ((unsigned)x << 8) | (lt << 16));
-            }
-          }
-        }
-      }
-    };
-    parallel_chunks(P->n_batches, 256, [&](int64_t b0, int64_t b1, int) {        // pass 1: entries per batch
-      for (int64_t b = b0; b < b1; ++b) { long long c = 0; walk((int)b, [&](unsigned) { ++c; }); batch_pair[b + 1] = c; }
-    });
-    for (int b = 0; b < P->n_batches; ++b) batch_pair[b + 1] += batch_pair[b];
-    pairs.resize((size_t)batch_pair[P->n_batches]);
-    parallel_chunks(P->n_batches, 256, [&](int64_t b0, int64_t b1, int) {        // pass 2: fill
-      for (int64_t b = b0; b < b1; ++b) { unsigned* dst = pairs.data() + batch_pair[b]; walk((int)b, [&](unsigned code) { *dst++ = code; }); }
-    });
-  }
-  P->n_pairs = (long long)pairs.size();
-  lap("batches + pair table");
+  lap("batches");
 
-  // ---- upload
+  // ---- upload the caller's arrays as they are; gather the per-observation arrays and build the pair table on the device
   LVBA_TRY(P->trk_ptr.upload(trk_ptr, s, &P->h2d));
+  LVBA_TRY(P->batch_pair.alloc((size_t)P->n_batches + 1));
+  LVBA_TRY(P->batch_pair.zero(s));
   if (Tv > 0) {
+    const int64_t nnz_all = obs_ptr[T];
+    DevBuf<long long> d_obs_ptr;
+    DevBuf<int> d_raw_cam, d_row_of_cam;
+    DevBuf<float2> d_raw_uv;
+    DevBuf<double> d_raw_plane;
+    static_assert(sizeof(long long) == sizeof(int64_t), "obs_ptr is uploaded as it is");
+    LVBA_TRY(d_obs_ptr.upload(reinterpret_cast<const long long*>(obs_ptr), (size_t)T + 1, s, &P->h2d));
+    LVBA_TRY(d_raw_cam.upload(obs_cam, (size_t)nnz_all, s, &P->h2d));
+    LVBA_TRY(d_raw_uv.upload(reinterpret_cast<const float2*>(obs_uv), (size_t)nnz_all, s, &P->h2d));
+    LVBA_TRY(d_raw_plane.upload(plane_nd, (size_t)T * 4, s, &P->h2d));
+    LVBA_TRY(d_row_of_cam.upload(row_of_cam, s, &P->h2d));
     LVBA_TRY(P->trk_id.upload(trk_id, s, &P->h2d));
-    LVBA_TRY(P->obs_cam.upload(l_cam, s, &P->h2d));
-    LVBA_TRY(P->obs_row.upload(l_row, s, &P->h2d));
-    LVBA_TRY(P->obs_uv.upload(l_uv, s, &P->h2d));
-    LVBA_TRY(P->plane.upload(l_plane, s, &P->h2d));
+    LVBA_TRY(P->obs_cam.alloc((size_t)nnz)); LVBA_TRY(P->obs_row.alloc((size_t)nnz)); LVBA_TRY(P->obs_uv.alloc((size_t)nnz));
+    LVBA_TRY(P->plane.alloc((size_t)Tv * 4));
+    LVBA_TRY(P->batch_trk.upload(batch_trk, s, &P->h2d));
+    visual_gather_kernel<<<(unsigned)((Tv + 127) / 128), 128, 0, s>>>(Tv, P->trk_id.p, P->trk_ptr.p, d_obs_ptr.p, d_raw_cam.p, d_raw_uv.p,
+                                                                     d_raw_plane.p, d_row_of_cam.p, P->obs_cam.p, P->obs_row.p, P->obs_uv.p, P->plane.p);
+    visual_pairs_kernel<true><<<P->n_batches, kSlots, 0, s>>>(P->trk_ptr.p, P->batch_trk.p, P->obs_row.p, P->batch_pair.p, nullptr);
+    visual_pair_scan_kernel<<<1, 1024, 0, s>>>(P->n_batches, P->batch_pair.p);
+    long long np = 0;
+    LVBA_CUDA(cudaMemcpyAsync(&np, P->batch_pair.p + P->n_batches, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    LVBA_CUDA(cudaStreamSynchronize(s));          // the temporaries above may now go back to the pool
+    P->n_pairs = np;
+    if (np > 0) {
+      LVBA_TRY(P->pairs.alloc((size_t)np));
+      visual_pairs_kernel<false><<<P->n_batches, kSlots, 0, s>>>(P->trk_ptr.p, P->batch_trk.p, P->obs_row.p, P->batch_pair.p, P->pairs.p);
+    }
+    LVBA_CUDA(cudaGetLastError());
+    P->launches += 4;
+  } else {
+    LVBA_TRY(P->batch_trk.upload(batch_trk, s, &P->h2d));
+    P->n_pairs = 0;
   }
-  LVBA_TRY(P->batch_trk.upload(batch_trk, s, &P->h2d));
-  LVBA_TRY(P->batch_pair.upload(batch_pair, s, &P->h2d));
-  if (!pairs.empty()) LVBA_TRY(P->pairs.upload(pairs, s, &P->h2d));
+  lap("device gather + pair table");
   if (P->n_rows > 0) LVBA_TRY(P->d_cam_of_row.upload(P->cam_of_row, s, &P->h2d));
   LVBA_TRY(P->q.upload(q, (size_t)M * 4, s, &P->h2d));
   LVBA_TRY(P->t.upload(t, (size_t)M * 3, s, &P->h2d));

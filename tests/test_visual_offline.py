@@ -66,7 +66,7 @@ def test_check_mode_reads_images_database_and_config(tool, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     info = json.loads(r.stdout.strip().splitlines()[-1])
     assert info["images"] == 6 and abs(info["first_image"] - sc["image_ts"][0]) < 1e-9          # every 2nd of the 12 files
-    assert info["width"] == 640 and info["height"] == 512 and abs(info["fx"] - 0.5 * visual_scene.INTR_FULL[0]) < 1e-9
+    assert info["width"] == 80 and info["height"] == 64 and abs(info["fx"] - 0.5 * visual_scene.INTR_FULL[0]) < 1e-9
     assert info["keypoints"] == sum(len(k) for k in sc["keypoints"])
     want = sum(float(k[:, 0].astype(np.float64).sum() + 2.0 * k[:, 1].astype(np.float64).sum()) for k in sc["keypoints"])
     assert abs(info["kp_sum"] - want) <= 1e-6 * abs(want)

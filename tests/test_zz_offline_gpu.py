@@ -168,14 +168,14 @@ def test_visual_stage_from_a_colmap_database(tmp_path):
            str(pkg.LIB_PATH), f"-Wl,-rpath,{pkg.LIB_PATH.parent}", "-L/usr/local/cuda/lib64", "-lcudart", "-ldl"]
     assert subprocess.run(cmd, capture_output=True, text=True).returncode == 0
     data = tmp_path / "data"
-    sc = visual_scene.make(data, seed=3, W=8, n_per_scan=6000, n_landmarks=260)
+    sc = visual_scene.make(data, seed=3, W=8, n_landmarks=700)
     r = subprocess.run([str(exe), "--data", str(data), "--config", str(data / "config.yaml"), "--visual"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     lines = [json.loads(x) for x in r.stdout.strip().splitlines()]
     vis = [x for x in lines if x.get("stage") == "visual"][0]
     assert vis["images"] == 8 and vis["keypoints"] == sum(len(k) for k in sc["keypoints"])
     assert vis["depth_valid"] > 0.5 * vis["keypoints"]                      # most keypoints sit on LiDAR-covered surfaces
-    assert vis["tracks"] >= 150 and vis["points_kept"] >= 100 and vis["surf_voxels"] > 0
+    assert vis["tracks"] >= 120 and vis["points_kept"] >= 80 and vis["surf_voxels"] > 0
     assert vis["cost_last"] < 0.5 * vis["cost_first"] and vis["iterations"] >= 2
 
     def read_images(path):
@@ -202,4 +202,4 @@ def test_visual_stage_from_a_colmap_database(tmp_path):
     assert rot_err(after)[1:].mean() < 0.6 * rot_err(before)[1:].mean()
     pts = np.loadtxt(data / "Colmap" / "sparse" / "points3D.txt")
     assert pts.shape == (vis["points_kept"], 8) and np.all(pts[:, 0] == np.arange(len(pts))) and np.all(pts[:, 4:7] == 128)
-    assert np.abs(pts[:, 1] - 2.6).max() < 0.1                              # the landmarks lie on the wall x = 2.6
+    assert np.abs(pts[:, 2] + 2.4).max() < 0.1                              # the landmarks lie on the wall y = -2.4

@@ -1,14 +1,17 @@
 """A small LiDAR + camera dataset on disk in the reference's layout, for the tests of `lvba_offline --visual`: the room corner of
-oracle.synth.make_scan_scene seen by a camera riding on the LiDAR body (looking along body +x), landmarks = world points of the
+oracle.synth.make_scan_scene seen by a camera riding on the LiDAR body (looking sideways at the wall y = -2.4 while moving along it), landmarks = world points of the
 scans themselves (so they lie on the planes the voxel map finds), keypoints = distorted projections + pixel noise, inlier matches
 between every pair of images that share a landmark, written into a COLMAP database."""
 import numpy as np
 
 from oracle import dataset_writer as dw, synth
 
-INTR_FULL = np.array([1293.56944, 1293.3155, 626.91359, 522.799224, -0.07616, 0.123001, -0.00113, 0.000251])
+# A small image on purpose: the depth candidate of a keypoint needs LiDAR depth in all four neighbouring pixels (fetchDepthBilinear,
+# include/utils.hpp:246-275), so the scans must cover the image densely — 80 x 64 pixels after scaling keeps the point count modest.
+WIDTH_FULL, HEIGHT_FULL = 160, 128
+INTR_FULL = np.array([96.0, 96.3, 79.7, 64.2, -0.05, 0.01, 5e-4, -3e-4])
 SCALE = 0.5
-RCL = np.array([[0.0, -1.0, 0.0], [0.0, 0.0, -1.0], [1.0, 0.0, 0.0]])       # camera z = body x, camera x = -body y, camera y = -body z
+RCL = np.array([[-1.0, 0.0, 0.0], [0.0, 0.0, -1.0], [0.0, -1.0, 0.0]])      # camera z = -body y (sideways, towards the wall y = -2.4), x = -body x, y = -body z
 PCL = np.array([0.02, 0.10, -0.03])
 
 
@@ -27,14 +30,14 @@ def project(Rcw, tcw, X, intr, width, height):
     return u, v
 
 
-def make(root, seed=3, W=8, n_per_scan=6000, n_landmarks=260, cam_noise=(0.004, 0.01), px_noise=0.3, extra_between=1, shuffle_db_ids=True):
+def make(root, seed=3, W=8, n_per_scan=30000, n_landmarks=260, cam_noise=(0.01, 0.03), px_noise=0.1, extra_between=1, shuffle_db_ids=True):
     """Writes the dataset under `root` and returns a dict with the ground truth."""
     rng = np.random.default_rng(seed)
     scans, poses = synth.make_scan_scene(seed, W=W, n_per_scan=n_per_scan)
     ts = dw.write_lidar_dataset(root, scans, poses)                                   # frame timestamps 1000.0 + 0.1 i
     image_ts = [t + 0.013 for t in ts]                                               # one image just after every scan
     intr = INTR_FULL.copy(); intr[:4] *= SCALE
-    width, height = int(round(1280 * SCALE)), int(round(1024 * SCALE))
+    width, height = int(round(WIDTH_FULL * SCALE)), int(round(HEIGHT_FULL * SCALE))
     # quaternion round trip of the pose file (15 digits): what the loader reads
     body = poses.copy()
     for i in range(W):
@@ -49,7 +52,7 @@ def make(root, seed=3, W=8, n_per_scan=6000, n_landmarks=260, cam_noise=(0.004, 
         image_poses[i, :9] = (body[i, :9].reshape(3, 3) @ synth.so3_exp(rng.normal(0, cam_noise[0], (1, 3)))[0]).ravel()
         image_poses[i, 9:] += rng.normal(0, cam_noise[1], 3)
     world = np.concatenate([np.asarray(s, np.float64) @ body[i, :9].reshape(3, 3).T + body[i, 9:] for i, s in enumerate(scans)])
-    on_wall = np.abs(world[:, 0] - 2.6) < 0.03                                        # the wall the cameras look at
+    on_wall = np.abs(world[:, 1] + 2.4) < 0.03                                        # the wall the cameras look at (they move along it)
     cand = world[on_wall]
     pts = cand[rng.choice(len(cand), n_landmarks, replace=False)]
     kps = [[] for _ in range(W)]
@@ -77,9 +80,7 @@ def make(root, seed=3, W=8, n_per_scan=6000, n_landmarks=260, cam_noise=(0.004, 
     if shuffle_db_ids:
         db_ids = [int(x) for x in rng.permutation(np.arange(3, W + 3))]
     dw.write_image_set(root, image_ts, image_poses, extra_between=extra_between)
-    if extra_between:                                                                 # the database holds exactly the sampled images
-        pass
     dw.write_colmap_db(root / "Colmap" / "colmap.db", image_ts, keypoints, {k: np.array(v) for k, v in pair.items()}, db_ids=db_ids)
-    dw.write_config_yaml(root / "config.yaml", INTR_FULL, 1280, 1024, SCALE, RCL, PCL, image_step=extra_between + 1, lidar=False, stage2_voxel=0.5)
+    dw.write_config_yaml(root / "config.yaml", INTR_FULL, WIDTH_FULL, HEIGHT_FULL, SCALE, RCL, PCL, image_step=extra_between + 1, lidar=False, stage2_voxel=0.5)
     return dict(scans=scans, poses=body, ts=ts, image_ts=image_ts, image_poses=image_poses, cams_true=cams_true, intr=intr, width=width, height=height,
                 keypoints=keypoints, pair=pair, pts=pts, db_ids=db_ids)
