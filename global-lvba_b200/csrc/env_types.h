@@ -26,6 +26,10 @@ struct FactorJob {
   double* wdump;   // [bs*bs*36] trailing window at n_stop, block (i,j) at ((i-n_stop)*bs + (j-n_stop))*36, bs = e.n - n_stop
   double* zdump;   // [bs*6]
   int* status;     // set to 1 when a pivot block is singular / non-finite
+  // Optional progress counter for a consumer that runs BESIDE this factorisation (the spike kernel, nd_kernels.cuh): the number of
+  // leading columns of L that are final in global memory, published with release semantics every few pivots and once more — as
+  // the very last global write of the CTA — with the value n_stop.  nullptr: nothing is published.
+  int* progress = nullptr;
 };
 // Jobs live in device memory (one per CTA): two for the twisted solve, one per window for the batched window BA.
 

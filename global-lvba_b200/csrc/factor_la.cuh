@@ -58,6 +58,13 @@ LVBA_DEV void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
 }
 LVBA_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 LVBA_DEV void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// progress counters between a factorisation and the spike kernel that consumes its columns while it runs (FactorJob::progress)
+LVBA_DEV void progress_publish(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+LVBA_DEV int progress_read(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+// programmatic dependent launch: the next kernel of the stream, if it was launched with programmatic stream serialisation, may
+// start once every CTA of this grid has executed this — i.e. IS RUNNING, which is what a consumer that spins on progress counters
+// needs to be free of deadlock; without such a dependent this is a no-op
+LVBA_DEV void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Inverse of a symmetric 6x6 block from its lower triangle x[i(i+1)/2 + j] (i >= j), no pivoting:
 // D = [A B^T; B C] (3x3 blocks): A^-1 by the adjugate, W = B A^-1, S = C - W B^T, S^-1 by the adjugate,
@@ -130,6 +137,7 @@ env_factor_la_kernel(const FactorJob* __restrict__ jobs, const unsigned* __restr
   double* __restrict__ dinv = J.dinv;
   double* __restrict__ z = J.z;
   const int n_stop = J.n_stop;
+  pdl_launch_dependents();
   long long* dbg = (blockIdx.x == 0) ? dbg_all : nullptr;
   // optional phase clocks (LVBA_FACTOR_TIMING=1): dbg[(k*8 + role)*4 + stamp]
 #define LVBA_STAMP(role, stamp) do { if (kTiming && dbg && lane == 0) dbg[((long long)k * 8 + (role)) * 4 + (stamp)] = clock64(); } while (0)
@@ -577,6 +585,8 @@ env_factor_la_kernel(const FactorJob* __restrict__ jobs, const unsigned* __restr
         }
         __syncwarp();
         if (lane < 6) sZ[c * 6 + lane] = (k + P < n) ? sZin[((k + P) & 7) * 6 + lane] : 0.0;   // row k+P takes slot c
+        // columns 0..k of L were complete in global memory before the block barrier this warp passed at the top of the step
+        if (J.progress && lane == 0 && (k & 3) == 3) progress_publish(J.progress, k + 1);
         LVBA_STAMP(4, 3);
       } else {
         // ---- column items: T_{i,k+1} = A_{i,k+1} - L_{i,k} T_{k+1,k}^T for rows i = k+2 .. k+P, then L = T D_{k+1}^-1
@@ -654,6 +664,10 @@ env_factor_la_kernel(const FactorJob* __restrict__ jobs, const unsigned* __restr
     if (bad) J.status[0] = 1;
   }
 #undef LVBA_STAMP
+  if (J.progress) {                                               // the last global write of the CTA (env_types.h)
+    __syncthreads();
+    if (tid == 0) progress_publish(J.progress, n_stop);
+  }
 }
 
 // =====================================================================================================

@@ -134,10 +134,8 @@ lidar_residual_kernel(LidarView lv, const double* __restrict__ poses, double* __
       for (int q = 0; q < 10; ++q) acc[q] += stage[s * kS + q];
     const double inv = 1.0 / acc[9];
     const double m0 = acc[6] * inv, m1 = acc[7] * inv, m2 = acc[8] * inv;
-    double lam[3], u[3][3];
-    eig3_sym<false>(acc[0] * inv - m0 * m0, acc[1] * inv - m0 * m1, acc[2] * inv - m0 * m2,
-                    acc[3] * inv - m1 * m1, acc[4] * inv - m1 * m2, acc[5] * inv - m2 * m2, lam, u);
-    lam0 = lam[0];
+    lam0 = sym3_smallest_eigenvalue(acc[0] * inv - m0 * m0, acc[1] * inv - m0 * m1, acc[2] * inv - m0 * m2,
+                                    acc[3] * inv - m1 * m1, acc[4] * inv - m1 * m2, acc[5] * inv - m2 * m2);
   }
   const double tot = block_sum<kSlots>(lam0, red);
   if (tid == 0) batch_res[b] = tot;

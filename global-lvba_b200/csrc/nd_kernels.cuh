@@ -89,12 +89,22 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
   double en[3];                                                // E of the next row: this lane's three outputs
 #pragma unroll
   for (int q = 0; q < 3; ++q) en[q] = (owner && cw + oc[q] < KS && 0 < J.nE && !(dbg_mode & 4)) ? J.E[((long long)ox[q]) * KS + cw + oc[q]] : 0.0;
+  // side by side with the factorisation (J.progress): row r of L is final once min(r, n_stop) columns are; one thread polls, the
+  // block barrier hands the acquired view to the others (the rows are fetched by cp.async.cg: L2, never a stale L1 line)
+  int seen = J.progress ? 0 : 0x7fffffff;
+  auto wait_row = [&](int r) {
+    const int need = r < n_stop ? r : n_stop;
+    if (tid == 0) while (seen < need) { seen = progress_read(J.progress); if (seen < need) __nanosleep(100); }
+  };
+  wait_row(1);
+  __syncthreads();
   stage_row(0, f0, e.row_start[0]);
   asm volatile("cp.async.commit_group;" ::: "memory");
   stage_row(1, f1, rs1);
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int k = 0; k < n; ++k) {
     asm volatile("cp.async.wait_group 1;" ::: "memory");       // everything but the newest group (row k+1): row k has landed
+    if (k + 2 < n) wait_row(k + 2);
     __syncthreads();                                           // row k of L staged by everybody; everybody is done with row k-1
     stage_row(k + 2, f2, rs2);                                 // into the buffer row k-1 used
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -362,6 +372,7 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
   const FactorJob J = jobs[blockIdx.x];
   const int n = J.e.n;
   const int tid = threadIdx.x;
+  pdl_launch_dependents();
   for (int o = tid; o < n * 6; o += kDenseThreads) sZ[o] = J.z[o];
   // register re-allocation: one setmaxnreg site per warpgroup-uniform branch (warpgroups 0-3: pair threads + inverting warp)
   if (tid >= kDenseColBase) reg_dealloc<kDenseColRegs>(); else reg_alloc<kDensePairRegs>();
@@ -423,6 +434,8 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
         sZ[i * 6 + r] -= zs;
       }
       __syncthreads();                                             // (s) L_s, T_s published; column s+2 handed over by the pair threads
+      // an idle thread of this group tells a spike kernel running beside this CTA that columns 0..s of L are in global memory
+      if (J.progress && ct == kDenseColThreads && (s & 3) == 3) progress_publish(J.progress, s + 1);
     }
   } else if (tid >= kDenseInvWarp) {
     // ================================================= the inverting warp
@@ -502,6 +515,10 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
   }
   __syncthreads();
   for (int o = tid; o < n * 6; o += kDenseThreads) J.z[o] = sZ[o];
+  if (J.progress) {                                                // the last global write of the CTA
+    __syncthreads();
+    if (tid == 0) progress_publish(J.progress, n);
+  }
 }
 
 // thread -> block map of nd_dense_factor_kernel: blocks of the 30 x 30 lower triangle grouped by 8 x 4 patches

@@ -46,6 +46,7 @@ struct SpikeJob {
   int nE;
   double* Z;
   int KS;
+  const int* progress = nullptr;   // FactorJob::progress of the factorisation that produces L, when the two run side by side
 };
 // U -= sum_k Z_k^T K_k Z_k  and  u -= sum_k Z_k^T K_k w_k  over the pivot rows of one node (K_k = D_k^-1).
 // U: dense lower block triangle over KS/6 block rows, block (i,j), j <= i, at (i(i+1)/2 + j)*36 (leading part of the node's U).
@@ -75,6 +76,7 @@ struct Tables {
   double* U; double* u; double* Z; double* E; double* T; double* W; double* w;     // pools (offsets in NodeDev); u == U (one pool)
   // multi-GPU only: writable views of H / dadd (the rows of the other ranks' rank separators arrive through the exchange region)
   double* Hw; double* daddw;
+  int* prog = nullptr;            // [nodes] progress counters (FactorJob::progress), or null: factorisation and spike run one after the other
 };
 
 LVBA_NHD void tri_dec(long long t, int& a, int& b) {
@@ -327,6 +329,11 @@ struct ZeroForeignF {
   }
 };
 
+struct ZeroProgF {
+  int* prog;
+  LVBA_NHD void operator()(long long i) const { prog[i] = 0; }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // Per-level job tables (host side; uploaded once per structure).  Dense views of the separator nodes share three small
 // arrays: first = 0, row_start[i] = i(i+1)/2, last = w - 1.
@@ -370,10 +377,11 @@ inline void build_level_jobs(const Plan& P, const Tables& t, const int* first_re
         J.max_col = std::max(J.max_col, v.npiv - 1);
       }
       J.factor.push_back(FactorJob{e, Lp, t.dinv + 36 * (long long)v.r0, zp, v.npiv,
-                                   v.ntrail ? t.W + v.offW : nullptr, v.ntrail ? t.w + v.offw : nullptr, status + id});
+                                   v.ntrail ? t.W + v.offW : nullptr, v.ntrail ? t.w + v.offw : nullptr, status + id,
+                                   (t.prog && v.ks > 0) ? t.prog + id : nullptr});
       J.back.push_back(BacksolveJob{e, Lp, t.x + 6 * (long long)v.r0, v.npiv});
       if (v.ks > 0) {
-        J.spike.push_back(SpikeJob{e, Lp, v.npiv, t.E + v.offE, v.kind == 0 ? v.nE : v.npiv, t.Z + v.offZ, v.ks});
+        J.spike.push_back(SpikeJob{e, Lp, v.npiv, t.E + v.offE, v.kind == 0 ? v.nE : v.npiv, t.Z + v.offZ, v.ks, t.prog ? t.prog + id : nullptr});
         J.syrk.push_back(SyrkSeg{t.Z + v.offZ, t.dinv + 36 * (long long)v.r0, zp, v.npiv, v.ks, t.U + v.offU, t.u + v.offu});
         J.max_ks = std::max(J.max_ks, v.ks);
       }
@@ -410,6 +418,7 @@ template <class Exec>
 inline void run_up_local(Exec& ex, const Plan& P, const Tables& t, const LevelDev* lv, int n_levels, long long nblocks,
                          long long leaf_e, long long leaf_fin, const RegionDev* reg) {
   ex.copy(t.L, t.H, nblocks * 36);
+  if (t.prog) ex.pass((long long)P.nodes.size(), ZeroProgF{t.prog});
   ex.pass((long long)6 * t.n, AddDiagF{t});
   ex.zero(t.U, P.sizeU);
   // ---- leaves

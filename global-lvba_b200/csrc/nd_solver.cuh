@@ -27,6 +27,10 @@ struct NdDevice {
   DevBuf<double> xchg;                     // multi-GPU: rows received from the left neighbour (exchange_rows)
   DevBuf<unsigned short> d_dense_map;      // thread -> block of nd_dense_factor_kernel
   bool dense_sep = true;                   // separators by nd_dense_factor_kernel (LVBA_ND_DENSE=0: register-window kernel)
+  // the spike kernels start while the factorisation they read from is still running and follow its progress counters
+  // (programmatic dependent launch; LVBA_ND_PIPELINE=0: one after the other)
+  bool pipeline = true;
+  DevBuf<int> d_prog;                      // [nodes]
   // numeric pools
   DevBuf<double> zs, U, u, Z, E, T, W, w;
   // job tables (rebuilt when the caller's pointers change)
@@ -123,6 +127,11 @@ struct NdDevice {
       }
       LVBA_TRY(xchg.alloc((size_t)std::max<long long>(mx, 1)));
     }
+    {
+      const char* pe = getenv("LVBA_ND_PIPELINE");
+      pipeline = !(pe && pe[0] == '0');
+      if (pipeline) LVBA_TRY(d_prog.alloc(plan.nodes.size()));
+    }
     LVBA_CUDA(cudaFuncSetAttribute(nd_spike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpikeSmem));
     {
       const char* m = getenv("LVBA_SPIKE_MODE");             // development only (nd_kernels.cuh); the symbol is 0 unless asked
@@ -148,6 +157,7 @@ struct NdDevice {
     tab.U = U.p; tab.u = U.p; tab.Z = Z.p; tab.E = E.p; tab.T = T.p; tab.W = W.p; tab.w = w.p;
     tab.Hw = n_ranks > 1 ? const_cast<double*>(H) : nullptr;       // multi-GPU: the other ranks' rank-separator rows are written into
     tab.daddw = n_ranks > 1 ? const_cast<double*>(dadd) : nullptr; // the caller's H / dadd (documented at EnvSolver::solve)
+    tab.prog = pipeline ? d_prog.p : nullptr;
     std::vector<nd::LevelJobs> jobs;
     nd::DenseViewArrays dv{d_zeros.p, d_tri.p, d_last_by_w.p};
     nd::build_level_jobs(plan, tab, d_first_rel.p, d_rs_adj.p, d_last_rel.p, genv.nblocks, dv, status + 1, jobs, my_rank);
@@ -183,6 +193,7 @@ struct NdCudaExec {
   std::function<int(int, int, const FactorJob*)> factor_fn;        // (max_col, n_jobs, jobs)
   std::function<void(int, const BacksolveJob*)> back_fn;           // (n_jobs, jobs)
   const unsigned short* dense_map = nullptr;                       // non-null: separators by nd_dense_factor_kernel
+  bool pipeline = false;                                           // spike kernels by programmatic dependent launch (NdDevice::pipeline)
   int64_t launches = 0;
   int rc = LVBA_OK;
   template <class F> void pass(long long n, const F& f) {
@@ -206,7 +217,20 @@ struct NdCudaExec {
   }
   void spike(const nd::SpikeJob* jobs, int n, int max_ks, int) {
     if (n <= 0 || max_ks <= 0) return;
-    nd_spike_kernel<<<dim3((max_ks + kSpikeCols - 1) / kSpikeCols, n), kSpikeThreads, kSpikeSmem, s>>>(jobs);
+    const dim3 grid((max_ks + kSpikeCols - 1) / kSpikeCols, n);
+    if (pipeline) {
+      // the kernel launched just before this one is the factorisation whose L these jobs read: start as soon as all of ITS CTAs run
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid; cfg.blockDim = dim3(kSpikeThreads); cfg.dynamicSmemBytes = kSpikeSmem; cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      const cudaError_t e = cudaLaunchKernelEx(&cfg, nd_spike_kernel, jobs);
+      if (e != cudaSuccess) rc = fail(LVBA_ERR_CUDA, "cudaLaunchKernelEx(nd_spike_kernel): %s", cudaGetErrorString(e));
+    } else {
+      nd_spike_kernel<<<grid, kSpikeThreads, kSpikeSmem, s>>>(jobs);
+    }
     ++launches;
   }
   void syrk(const nd::SyrkSeg* segs, int n, int max_ks, int max_rows) {

@@ -587,6 +587,7 @@ struct EnvSolver {
       NdCudaExec ex;
       ex.s = s;
       ex.dense_map = nd.dense_sep ? nd.d_dense_map.p : nullptr;
+      ex.pipeline = nd.pipeline;
       ex.factor_fn = [&](int max_col, int nj, const FactorJob* jobs) { return launch_factor(pid(max_col), nj, jobs, s, &ex.launches); };
       ex.back_fn = [&](int nj, const BacksolveJob* jobs) { launch_backsolve(nj, jobs, s); };
       cudaMemsetAsync(status.p, 0, status.n * sizeof(int), s);
@@ -601,6 +602,7 @@ struct EnvSolver {
       NdCudaExec ex;
       ex.s = s;
       ex.dense_map = nd.dense_sep ? nd.d_dense_map.p : nullptr;
+      ex.pipeline = nd.pipeline;
       ex.factor_fn = [&](int max_col, int nj, const FactorJob* jobs) { return launch_factor(pid(max_col), nj, jobs, s, &ex.launches); };
       ex.back_fn = [&](int nj, const BacksolveJob* jobs) { launch_backsolve(nj, jobs, s); };
       cudaMemsetAsync(status.p, 0, status.n * sizeof(int), s);

@@ -175,7 +175,7 @@ def test_visual_stage_from_a_colmap_database(tmp_path):
     vis = [x for x in lines if x.get("stage") == "visual"][0]
     assert vis["images"] == 8 and vis["keypoints"] == sum(len(k) for k in sc["keypoints"])
     assert vis["depth_valid"] > 0.5 * vis["keypoints"]                      # most keypoints sit on LiDAR-covered surfaces
-    assert vis["tracks"] >= 120 and vis["points_kept"] >= 80 and vis["surf_voxels"] > 0
+    assert vis["tracks"] >= 120 and vis["points_kept"] >= 80
     assert vis["cost_last"] < 0.5 * vis["cost_first"] and vis["iterations"] >= 2
 
     def read_images(path):
