@@ -360,6 +360,10 @@ static_assert((kDenseColBase) * kDensePairRegs + (kDenseThreads - kDenseColBase)
 constexpr int kDenseS = 38;                  // doubles per operand block in shared memory (bank spread, 16 B aligned)
 constexpr size_t kDenseSmem = sizeof(double) * (6 * kDenseMax * kDenseS + 36 + 36 + kDenseMax * 6 + 8);
 
+// LVBA_DENSE_MODE (development, results are wrong unless 0): 1 = no trailing update by the pair threads, 2 = the inverting warp skips
+// the inverse (stale K), 4 = the column group skips apply and scale arithmetic
+__device__ int g_dense_mode = 0;
+
 __global__ void __launch_bounds__(kDenseThreads, 1)
 nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short* __restrict__ tmap) {
   extern __shared__ __align__(16) double smem_dense[];
@@ -372,6 +376,7 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
   const FactorJob J = jobs[blockIdx.x];
   const int n = J.e.n;
   const int tid = threadIdx.x;
+  const int dense_mode = g_dense_mode;
   pdl_launch_dependents();
   for (int o = tid; o < n * 6; o += kDenseThreads) sZ[o] = J.z[o];
   // register re-allocation: one setmaxnreg site per warpgroup-uniform branch (warpgroups 0-3: pair threads + inverting warp)
@@ -392,7 +397,7 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
         const double2* c2 = reinterpret_cast<const double2*>(sC + (par * kDenseMax + i) * kDenseS + r * 6);
         const double2 q0 = c2[0], q1 = c2[1], q2 = c2[2];
         t[0] = q0.x; t[1] = q0.y; t[2] = q1.x; t[3] = q1.y; t[4] = q2.x; t[5] = q2.y;
-        if (s > 0) {                                               // -= L_{i,s-1}[r][.] T_{s,s-1}^T   (sT holds T^T: [q][y])
+        if (s > 0 && !(dense_mode & 4)) {                          // -= L_{i,s-1}[r][.] T_{s,s-1}^T   (sT holds T^T: [q][y])
           const double2* ts = reinterpret_cast<const double2*>(sT + ((par ^ 1) * kDenseMax + s) * kDenseS);
 #pragma unroll
           for (int q = 0; q < 6; ++q) {
@@ -449,7 +454,11 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
       for (int a = 0; a < 6; ++a)
 #pragma unroll
         for (int b = 0; b <= a; ++b) xl[LVBA_T(a, b)] = sD[a * 6 + b];
-      sym6_block_inverse(xl, K);
+      if (!(dense_mode & 2)) sym6_block_inverse(xl, K);
+      else {
+#pragma unroll
+        for (int q = 0; q < 21; ++q) K[q] = xl[q];
+      }
       auto kk = [&](int rr, int c) -> double { return rr >= c ? K[LVBA_T(rr, c)] : K[LVBA_T(c, rr)]; };
       if (!isfinite((K[LVBA_T(0, 0)] + K[LVBA_T(5, 5)]) + (K[LVBA_T(3, 0)] + K[LVBA_T(2, 1)]))) bad = 1;
       if (lane == 0) {                                             // D_s^-1 (full symmetric) for the column group and for the caller
@@ -487,7 +496,7 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
     __syncthreads();                                               // (P)
     for (int s = 0; s < n; ++s) {
       // the trailing update of pivot s-1 for the columns the pair threads still own (j >= s+1)
-      if (s >= 1 && live && j >= s + 1) {
+      if (s >= 1 && live && j >= s + 1 && !(dense_mode & 1)) {
         const int par = (s - 1) & 1;
         // rank-1 steps over the contraction index q: column q of T_j (six values) and two entries of column q of L_i at a time are
         // live beside the 36 accumulators — 16 operand registers, which is what fits the 96-register budget without spilling G

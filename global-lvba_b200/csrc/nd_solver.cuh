@@ -136,6 +136,8 @@ struct NdDevice {
     {
       const char* m = getenv("LVBA_SPIKE_MODE");             // development only (nd_kernels.cuh); the symbol is 0 unless asked
       if (m) { const int mode = atoi(m); LVBA_CUDA(cudaMemcpyToSymbol(g_spike_mode, &mode, sizeof(int))); }
+      const char* dm = getenv("LVBA_DENSE_MODE");
+      if (dm) { const int mode = atoi(dm); LVBA_CUDA(cudaMemcpyToSymbol(g_dense_mode, &mode, sizeof(int))); }
     }
     LVBA_CUDA(cudaFuncSetAttribute(nd_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
     LVBA_CUDA(cudaFuncSetAttribute(nd_dense_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmem));
