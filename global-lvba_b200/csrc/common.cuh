@@ -150,6 +150,69 @@ LVBA_DEV double sym3_smallest_eigenvalue(double a00, double a01, double a02, dou
   return l[0];
 }
 
+// Full eigen-decomposition of a plane voxel's covariance without the Jacobi sweeps (one warp of a batch CTA solves ~18 of them
+// while the other three wait: a third of the CTA's life in lidar_build_kernel): lambda_0 by the Newton iteration above, its
+// eigenvector as the largest cross product of two rows of A - lambda_0 I (rank 2), the other two pairs from the 2 x 2 problem in
+// the plane orthogonal to it (one Jacobi rotation).  Residuals |A u - lambda u| and orthogonality ~1e-15 |A| whenever
+// |p'(lambda_0)| = (lambda_1 - lambda_0)(lambda_2 - lambda_0) >= 1e-2 tr^2; otherwise eig3_sym decides.  Eigenvalues ascending,
+// u[k] = eigenvector k; signs undefined, as with every other solver (every use is even in u).
+LVBA_DEV void eig3_sym_plane(double a00, double a01, double a02, double a11, double a12, double a22, double lam[3], double u[3][3]) {
+  const double m00 = a11 * a22 - a12 * a12, m01 = a01 * a22 - a12 * a02, m02 = a01 * a12 - a11 * a02;
+  const double c2 = a00 + a11 + a22;
+  const double c1 = m00 + (a00 * a22 - a02 * a02) + (a00 * a11 - a01 * a01);
+  const double c0 = a00 * m00 - a01 * m01 + a02 * m02;
+  double l0 = 0.0, fp = -c1;
+  bool settled = false;
+#pragma unroll 1
+  for (int it = 0; it < 10; ++it) {
+    const double f = fma(fma(c2 - l0, l0, -c1), l0, c0);
+    fp = fma(fma(-3.0, l0, 2.0 * c2), l0, -c1);
+    const double d = f / fp;
+    l0 -= d;
+    if (fabs(d) <= 1e-16 * fabs(c2)) { settled = true; break; }
+  }
+  if (!(settled && fabs(fp) >= 1e-2 * c2 * c2)) { eig3_sym<true>(a00, a01, a02, a11, a12, a22, lam, u); return; }
+  // null vector of M = A - l0 I
+  const double r0[3] = {a00 - l0, a01, a02}, r1[3] = {a01, a11 - l0, a12}, r2[3] = {a02, a12, a22 - l0};
+  double x01[3], x02[3], x12[3];
+  cross3(r0, r1, x01); cross3(r0, r2, x02); cross3(r1, r2, x12);
+  const double n01 = dot3(x01, x01), n02 = dot3(x02, x02), n12 = dot3(x12, x12);
+  double e0[3], nn = n01;
+  e0[0] = x01[0]; e0[1] = x01[1]; e0[2] = x01[2];
+  if (n02 > nn) { nn = n02; e0[0] = x02[0]; e0[1] = x02[1]; e0[2] = x02[2]; }
+  if (n12 > nn) { nn = n12; e0[0] = x12[0]; e0[1] = x12[1]; e0[2] = x12[2]; }
+  const double in0 = rsqrt(nn);
+  // rsqrt is not correctly rounded: one normalisation step more keeps |u0| = 1 to the last bits
+  e0[0] *= in0; e0[1] *= in0; e0[2] *= in0;
+  { const double fix = 1.0 / sqrt(dot3(e0, e0)); e0[0] *= fix; e0[1] *= fix; e0[2] *= fix; }
+  // orthonormal basis of the plane: v1 = u0 x e_axis (axis of the smallest |u0| component), v2 = u0 x v1
+  const double ax = fabs(e0[0]), ay = fabs(e0[1]), az = fabs(e0[2]);
+  double v1[3];
+  if (ax <= ay && ax <= az) { v1[0] = 0.0; v1[1] = e0[2]; v1[2] = -e0[1]; }
+  else if (ay <= az) { v1[0] = -e0[2]; v1[1] = 0.0; v1[2] = e0[0]; }
+  else { v1[0] = e0[1]; v1[1] = -e0[0]; v1[2] = 0.0; }
+  { const double fix = 1.0 / sqrt(dot3(v1, v1)); v1[0] *= fix; v1[1] *= fix; v1[2] *= fix; }
+  double v2[3];
+  cross3(e0, v1, v2);
+  const double Av1[3] = {a00 * v1[0] + a01 * v1[1] + a02 * v1[2], a01 * v1[0] + a11 * v1[1] + a12 * v1[2], a02 * v1[0] + a12 * v1[1] + a22 * v1[2]};
+  const double Av2[3] = {a00 * v2[0] + a01 * v2[1] + a02 * v2[2], a01 * v2[0] + a11 * v2[1] + a12 * v2[2], a02 * v2[0] + a12 * v2[1] + a22 * v2[2]};
+  const double b11 = dot3(v1, Av1), b12 = dot3(v1, Av2), b22 = dot3(v2, Av2);
+  double l1 = b11, l2 = b22, c = 1.0, sn = 0.0;
+  if (b12 != 0.0) {
+    const double theta = (b22 - b11) / (2.0 * b12);
+    const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+    c = 1.0 / sqrt(t * t + 1.0); sn = t * c;
+    l1 = b11 - t * b12; l2 = b22 + t * b12;
+  }
+  double w1[3], w2[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { w1[k] = c * v1[k] - sn * v2[k]; w2[k] = sn * v1[k] + c * v2[k]; }
+  const bool swap = l1 > l2;
+  lam[0] = l0; lam[1] = swap ? l2 : l1; lam[2] = swap ? l1 : l2;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { u[0][k] = e0[k]; u[1][k] = swap ? w2[k] : w1[k]; u[2][k] = swap ? w1[k] : w2[k]; }
+}
+
 // ---------------------------------------------------------------- Rodrigues, reference tools.hpp:62-77
 LVBA_DEV void so3_exp(const double* w, double* R) {
   const double th = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);

@@ -157,7 +157,7 @@ lidar_residual_kernel(LidarView lv, const double* __restrict__ poses, double* __
 
 // ------------------------------------------------------------------------------------------------
 // Hessian + gradient + residual build
-__global__ void __launch_bounds__(kSlots)
+__global__ void __launch_bounds__(kSlots, 4)
 lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, double* __restrict__ H,
                    double* __restrict__ g, double* __restrict__ batch_res) {
   extern __shared__ double sm[];
@@ -201,7 +201,7 @@ lidar_build_kernel(LidarView lv, EnvView env, const double* __restrict__ poses, 
     double cov[6], vbar[3], Nsum;
     voxel_cov(stage, lo, hi, cov, vbar, Nsum);
     double lam[3], u[3][3];
-    eig3_sym<true>(cov[0], cov[1], cov[2], cov[3], cov[4], cov[5], lam, u);
+    eig3_sym_plane(cov[0], cov[1], cov[2], cov[3], cov[4], cov[5], lam, u);
     lam0 = lam[0];
     double* p = sV + tid * kVoxParams;
 #pragma unroll

@@ -271,12 +271,18 @@ int lvba_voxel_map_lookup(lvba_voxel_map* m, int64_t n, const double* X, double*
   LVBA_CUDA(cudaSetDevice(m->device));
   auto& v = m->map;
   lvba::DevBuf<double> dX, dout;
-  lvba::StreamDrain drain(nullptr);
+  lvba::StreamDrain drain(v.ex.stream);
+  const bool tlog = getenv("LVBA_SETUP_TIMING") != nullptr;
+  double tprev = lvba::wall_ms();
+  auto lap = [&](const char* what) { if (tlog) { cudaStreamSynchronize(v.ex.stream); const double t = lvba::wall_ms(); fprintf(stderr, "[voxel lookup] %-18s %8.2f ms\n", what, t - tprev); tprev = t; } };
   LVBA_TRY(dX.upload(X, (size_t)n * 3, v.ex.stream));
   LVBA_TRY(dout.alloc((size_t)n * 4));
+  lap("alloc + upload");
   LVBA_TRY(v.lookup(n, dX.p, dout.p));
+  lap("lookup pass");
   LVBA_CUDA(cudaMemcpyAsync(plane_nd, dout.p, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, v.ex.stream));
   LVBA_CUDA(cudaStreamSynchronize(v.ex.stream));
+  lap("download");
   m->sum.kernel_launches = v.ex.launches;
   return LVBA_OK;
 }
