@@ -120,6 +120,7 @@ struct lvba_lidar_problem {
   // host copies kept for counters / structure queries
   std::vector<long long> h_vox_ptr_all;
   std::vector<int> h_pose_idx_all;
+  bool have_structure = false;
   cudaStream_t stream = nullptr;
   lvba::DevBuf<double2> cl;
   lvba::DevBuf<int> pidx, vox_ptr, batch_vox;
@@ -208,7 +209,9 @@ inline int lidar_validate(int32_t W, int64_t V, const int64_t* vox_ptr, const in
 inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const int32_t* pose_idx,
                              const double* clusters, const double* poses, int32_t device,
                              lvba_lidar_problem** out, int32_t n_groups = 0, const int32_t* grp_ptr = nullptr,
-                             const double* d_clusters = nullptr) {
+                             const double* d_clusters = nullptr, bool keep_structure = true) {
+  // keep_structure: copy the caller's CSR for lvba_lidar_counts (a handle may outlive the caller's arrays); the one-shot calls,
+  // whose handle dies before they return, skip the 7 MB of copies
   // d_clusters: the same AoS records already resident on the selected device (a voxel map's export buffer); when set,
   // `clusters` may be null and no cluster bytes cross PCIe.
   if (!out) return fail(LVBA_ERR_INVALID_ARG, "out is null");
@@ -232,16 +235,27 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   lap("ctx/stream/pinned");
   // the caller's cluster records (the bulk of the upload: 80 B per slot) start crossing PCIe now, in ONE copy, while the
   // host derives the structure below; every path further down reads them from `aos_dev`
+  // (on a stream of its own: the set-up below synchronises `s` several times for its small uploads)
   DevBuf<double> aos;
   const double* aos_dev = d_clusters;
+  struct CopyLane {
+    cudaStream_t st = nullptr; cudaEvent_t done = nullptr;
+    ~CopyLane() { if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); } if (done) cudaEventDestroy(done); }
+  } lane;
   if (!aos_dev && vox_ptr[V] > 0) {
     LVBA_TRY(aos.alloc((size_t)vox_ptr[V] * 10));
-    LVBA_CUDA(cudaMemcpyAsync(aos.p, clusters, (size_t)vox_ptr[V] * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
+    LVBA_CUDA(cudaStreamCreateWithFlags(&lane.st, cudaStreamNonBlocking));
+    LVBA_CUDA(cudaEventCreateWithFlags(&lane.done, cudaEventDisableTiming));
+    LVBA_CUDA(cudaMemcpyAsync(aos.p, clusters, (size_t)vox_ptr[V] * 10 * sizeof(double), cudaMemcpyHostToDevice, lane.st));
+    LVBA_CUDA(cudaEventRecord(lane.done, lane.st));
     P->h2d += vox_ptr[V] * 80;
     aos_dev = aos.p;
   }
-  P->h_vox_ptr_all.assign(vox_ptr, vox_ptr + V + 1);
-  P->h_pose_idx_all.assign(pose_idx, pose_idx + vox_ptr[V]);
+  if (keep_structure) {
+    P->h_vox_ptr_all.assign(vox_ptr, vox_ptr + V + 1);
+    P->h_pose_idx_all.assign(pose_idx, pose_idx + vox_ptr[V]);
+  }
+  P->have_structure = keep_structure;
   lap("host copies");
 
   // ---- envelope structure over ALL voxels (identical on every rank)
@@ -286,10 +300,15 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   Comm& cm = comm();
   bool sorted_voxels = false;
   std::vector<int64_t> mine;
-  mine.reserve((size_t)V);
-  for (int64_t a = 0; a < V; ++a)
-    if (!cm.active() || (P->solver.dist() ? P->solver.dist_owner(pose_idx[vox_ptr[a]]) : shard_owner(pose_idx[vox_ptr[a]], W, cm.n_ranks)) == cm.rank)
-      mine.push_back(a);
+  if (!cm.active()) {                                          // one rank: every voxel, in the caller's order
+    mine.resize((size_t)V);
+    parallel_chunks(V, 1 << 15, [&](int64_t a0, int64_t a1, int) { for (int64_t a = a0; a < a1; ++a) mine[(size_t)a] = a; });
+  } else {
+    mine.reserve((size_t)V);
+    for (int64_t a = 0; a < V; ++a)
+      if ((P->solver.dist() ? P->solver.dist_owner(pose_idx[vox_ptr[a]]) : shard_owner(pose_idx[vox_ptr[a]], W, cm.n_ranks)) == cm.rank)
+        mine.push_back(a);
+  }
   {
     // voxels in the order of their lowest pose: a batch CTA then touches ~30 consecutive pose rows of H (its diagonal blocks and
     // gradient rows can be reduced per pose before they leave the SM, and its REDs stay inside a few hundred kB of L2)
@@ -304,7 +323,13 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   std::vector<int64_t> bigv;
   {
     std::vector<int64_t> small;
-    for (int64_t a : mine) if (vox_ptr[a + 1] - vox_ptr[a] > kSlots) bigv.push_back(a);
+    bool any_big[kMaxSetupThreads] = {};
+    parallel_chunks((int64_t)mine.size(), 1 << 15, [&](int64_t i0, int64_t i1, int w) {
+      for (int64_t i = i0; i < i1; ++i) if (vox_ptr[mine[(size_t)i] + 1] - vox_ptr[mine[(size_t)i]] > kSlots) { any_big[w] = true; break; }
+    });
+    bool has_big = false;
+    for (bool b : any_big) has_big = has_big || b;
+    if (has_big) for (int64_t a : mine) if (vox_ptr[a + 1] - vox_ptr[a] > kSlots) bigv.push_back(a);
     if (!bigv.empty()) {
       for (int64_t a : mine) if (vox_ptr[a + 1] - vox_ptr[a] <= kSlots) small.push_back(a);
       mine.swap(small);
@@ -351,14 +376,18 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   }
   // ---- pair table
   std::vector<long long> batch_pair(P->n_batches + 1, 0);
-  long long np = 0;
-  for (int b = 0; b < P->n_batches; ++b) {
-    for (int i = batch_vox[b]; i < batch_vox[b + 1]; ++i) {
-      const long long K = l_vox_ptr[i + 1] - l_vox_ptr[i];
-      np += K * (K - 1) / 2;
+  parallel_chunks(P->n_batches, 1 << 10, [&](int64_t b0, int64_t b1, int) {
+    for (int64_t b = b0; b < b1; ++b) {
+      long long c = 0;
+      for (int i = batch_vox[(size_t)b]; i < batch_vox[(size_t)b + 1]; ++i) {
+        const long long K = l_vox_ptr[i + 1] - l_vox_ptr[i];
+        c += K * (K - 1) / 2;
+      }
+      batch_pair[(size_t)b + 1] = c;
     }
-    batch_pair[b + 1] = np;
-  }
+  });
+  for (int b = 0; b < P->n_batches; ++b) batch_pair[b + 1] += batch_pair[b];
+  const long long np = batch_pair[P->n_batches];
   P->n_pairs = np;
 
   lap("batches+pair table");
@@ -369,6 +398,7 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   LVBA_TRY(P->cl.zero(s));
   const bool contiguous = Vl == V && n_groups == 0 && !sorted_voxels;       // single rank, caller's order: the records and pose indices are used as they are
   std::vector<int> l_pidx(contiguous ? (size_t)0 : (size_t)nnz);
+  if (lane.done) LVBA_CUDA(cudaStreamWaitEvent(s, lane.done, 0));            // the kernels below read the records
   {
     if (contiguous) {
       if (nnz > 0) {
@@ -843,6 +873,7 @@ int lvba_lidar_iterate(lvba_lidar_problem* p, int32_t n_iter, lvba_summary* summ
 
 int lvba_lidar_counts(lvba_lidar_problem* p, int64_t* nnz, int64_t* n_blocks_env, int64_t* n_blocks_nonzero, int64_t* n_pairs) {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
+  if (!p->have_structure) return lvba::fail(LVBA_ERR_UNSUPPORTED, "this problem was created without its host-side structure copy");
   if (nnz) *nnz = (int64_t)p->h_pose_idx_all.size();
   if (n_blocks_env) *n_blocks_env = p->env.nblocks;
   int64_t np = 0;
@@ -867,7 +898,10 @@ int lvba_lidar_lm(int32_t W, int64_t V, const int64_t* vox_ptr, const int32_t* p
   lvba_lidar_opts o;
   if (opts) o = *opts; else lvba_lidar_default_opts(&o);
   lvba_lidar_problem* p = nullptr;
-  int rc = lvba_lidar_create(W, V, vox_ptr, pose_idx, clusters, poses, o.device, &p);
+  int rc;
+  try { rc = lvba::lidar_create_impl(W, V, vox_ptr, pose_idx, clusters, poses, o.device, &p, 0, nullptr, nullptr, /*keep_structure=*/false); }
+  catch (const std::bad_alloc&) { return lvba::fail(LVBA_ERR_NOMEM, "host allocation failed"); }
+  catch (...) { return lvba::fail(LVBA_ERR_INVALID_ARG, "unexpected exception in lvba_lidar_lm"); }
   if (rc != LVBA_OK) return rc;
   lvba_summary s;
   memset(&s, 0, sizeof s);

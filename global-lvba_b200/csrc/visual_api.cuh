@@ -261,9 +261,11 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   // ---- shard: landmark -> owner of its lowest camera index
   Comm& cm = comm();
   std::vector<int64_t> mine;
-  for (int64_t k = 0; k < Tv_all; ++k)
-    if (!cm.active() || (P->solver.dist() ? P->solver.dist_owner(min_sys_row[k]) : shard_owner(min_row[k], M, cm.n_ranks)) == cm.rank)
-      mine.push_back(valid[k]);
+  if (!cm.active()) mine.swap(valid);                          // one rank: every valid landmark
+  else
+    for (int64_t k = 0; k < Tv_all; ++k)
+      if ((P->solver.dist() ? P->solver.dist_owner(min_sys_row[k]) : shard_owner(min_row[k], M, cm.n_ranks)) == cm.rank)
+        mine.push_back(valid[k]);
   const int64_t Tv = (int64_t)mine.size();
   P->Tv = Tv;
   std::vector<int> trk_ptr(Tv + 1, 0), trk_id(Tv);
@@ -331,10 +333,15 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   LVBA_TRY(P->q.upload(q, (size_t)M * 4, s, &P->h2d));
   LVBA_TRY(P->t.upload(t, (size_t)M * 3, s, &P->h2d));
   LVBA_TRY(P->X.upload(X, (size_t)T * 3, s, &P->h2d));
-  LVBA_TRY(P->q0.upload(q, (size_t)M * 4, s)); LVBA_TRY(P->t0.upload(t, (size_t)M * 3, s)); LVBA_TRY(P->X0.upload(X, (size_t)T * 3, s));
-  LVBA_TRY(P->qc.upload(q, (size_t)M * 4, s));
-  LVBA_TRY(P->tc.upload(t, (size_t)M * 3, s));
-  LVBA_TRY(P->Xc.upload(X, (size_t)T * 3, s));
+  {   // restore point and candidate start as device-side copies of what just went up (no second and third trip over PCIe)
+    auto dup = [&](DevBuf<double>& dst, const DevBuf<double>& src, size_t count) -> int {
+      LVBA_TRY(dst.alloc(count));
+      if (count) LVBA_CUDA(cudaMemcpyAsync(dst.p, src.p, count * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      return LVBA_OK;
+    };
+    LVBA_TRY(dup(P->q0, P->q, (size_t)M * 4)); LVBA_TRY(dup(P->t0, P->t, (size_t)M * 3)); LVBA_TRY(dup(P->X0, P->X, (size_t)T * 3));
+    LVBA_TRY(dup(P->qc, P->q, (size_t)M * 4)); LVBA_TRY(dup(P->tc, P->t, (size_t)M * 3)); LVBA_TRY(dup(P->Xc, P->X, (size_t)T * 3));
+  }
   const size_t n6 = (size_t)std::max(P->n_rows, 1) * 6;
   LVBA_TRY(P->S.alloc((size_t)std::max<long long>(P->env.nblocks, 1) * 36));
   LVBA_TRY(P->rhs.alloc(n6)); LVBA_TRY(P->y.alloc(n6)); LVBA_TRY(P->dadd.alloc(n6));
