@@ -358,7 +358,7 @@ constexpr int kDenseThreads = 768;           // 4 + 2 warpgroups (704..767 idle)
 constexpr int kDensePairRegs = 96, kDenseColRegs = 48;       // 512 * 96 + 256 * 48 == 768 * 80 = 61440, the pool the CTA is launched with: setmaxnreg.inc waits for ever if the budgets exceed it
 static_assert((kDenseColBase) * kDensePairRegs + (kDenseThreads - kDenseColBase) * kDenseColRegs <= kDenseThreads * 80, "register budgets exceed the launch pool");
 constexpr int kDenseS = 38;                  // doubles per operand block in shared memory (bank spread, 16 B aligned)
-constexpr size_t kDenseSmem = sizeof(double) * (6 * kDenseMax * kDenseS + 36 + 36 + kDenseMax * 6 + 8);
+constexpr size_t kDenseSmem = sizeof(double) * (6 * kDenseMax * kDenseS + 36 + 72 + kDenseMax * 6 + 8);
 
 // LVBA_DENSE_MODE (development, results are wrong unless 0): 1 = no trailing update by the pair threads, 2 = the inverting warp skips
 // the inverse (stale K), 4 = the column group skips apply and scale arithmetic
@@ -371,8 +371,8 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
   double* sT = sL + 2 * kDenseMax * kDenseS;               // [2][30][S] T_{i,s}^T   parity s & 1
   double* sC = sT + 2 * kDenseMax * kDenseS;               // [2][30][S] column c as the pair threads left it, parity c & 1
   double* sD = sC + 2 * kDenseMax * kDenseS;               // [36] pivot block (rows written by the six threads of block row s)
-  double* sK = sD + 36;                                    // [36] its inverse
-  double* sZ = sK + 36;                                    // [30][6]
+  double* sK = sD + 36;                                    // [2][36] its inverse, parity s & 1 (an idle warp copies it to global memory one step later)
+  double* sZ = sK + 72;                                    // [30][6]
   const FactorJob J = jobs[blockIdx.x];
   const int n = J.e.n;
   const int tid = threadIdx.x;
@@ -418,13 +418,13 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
       }
       // ---- (2) scale: row r of L_is = T_is D_s^-1, publish T and L, forward substitution
       if (mine && i > s) {
-        double lr[6];
+        double lr[6] = {0, 0, 0, 0, 0, 0};
+        const double2* k2 = reinterpret_cast<const double2*>(sK + par * 36);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          double a = t[0] * sK[c];
-#pragma unroll
-          for (int q = 1; q < 6; ++q) a = fma(t[q], sK[q * 6 + c], a);
-          lr[c] = a;
+        for (int q = 0; q < 6; ++q) {
+          const double2 k0 = k2[3 * q], k1 = k2[3 * q + 1], kk2 = k2[3 * q + 2];
+          lr[0] = fma(t[q], k0.x, lr[0]); lr[1] = fma(t[q], k0.y, lr[1]); lr[2] = fma(t[q], k1.x, lr[2]);
+          lr[3] = fma(t[q], k1.y, lr[3]); lr[4] = fma(t[q], kk2.x, lr[4]); lr[5] = fma(t[q], kk2.y, lr[5]);
         }
         double* tt = sT + (par * kDenseMax + i) * kDenseS + r;       // transposed operand blocks: [q * 6 + row]
         double* lt = sL + (par * kDenseMax + i) * kDenseS + r;
@@ -439,8 +439,13 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
         sZ[i * 6 + r] -= zs;
       }
       __syncthreads();                                             // (s) L_s, T_s published; column s+2 handed over by the pair threads
-      // an idle thread of this group tells a spike kernel running beside this CTA that columns 0..s of L are in global memory
-      if (J.progress && ct == kDenseColThreads && (s & 3) == 3) progress_publish(J.progress, s + 1);
+      // the two idle warps of this group: D_s^-1 to global memory (the inverting warp left it in sK[par]; it writes that buffer again
+      // two pivots from now), and word to a spike kernel running beside this CTA that columns 0..s of L are in global memory
+      if (idle) {
+        if (ct - kDenseColThreads < 18)
+          reinterpret_cast<double2*>(J.dinv + (long long)s * 36)[ct - kDenseColThreads] = reinterpret_cast<const double2*>(sK + par * 36)[ct - kDenseColThreads];
+        if (J.progress && ct == kDenseColThreads + 32 && (s & 3) == 3) progress_publish(J.progress, s + 1);
+      }
     }
   } else if (tid >= kDenseInvWarp) {
     // ================================================= the inverting warp
@@ -461,12 +466,12 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
       }
       auto kk = [&](int rr, int c) -> double { return rr >= c ? K[LVBA_T(rr, c)] : K[LVBA_T(c, rr)]; };
       if (!isfinite((K[LVBA_T(0, 0)] + K[LVBA_T(5, 5)]) + (K[LVBA_T(3, 0)] + K[LVBA_T(2, 1)]))) bad = 1;
-      if (lane == 0) {                                             // D_s^-1 (full symmetric) for the column group and for the caller
-        double* dk = J.dinv + (long long)s * 36;
+      if (lane == 0) {                                             // D_s^-1 (full symmetric) for the column group; 18 STS.128
+        double2* k2 = reinterpret_cast<double2*>(sK + (s & 1) * 36);
 #pragma unroll
         for (int rr = 0; rr < 6; ++rr)
 #pragma unroll
-          for (int c = 0; c < 6; ++c) { const double v = kk(rr, c); sK[rr * 6 + c] = v; dk[rr * 6 + c] = v; }
+          for (int h = 0; h < 3; ++h) k2[rr * 3 + h] = make_double2(kk(rr, 2 * h), kk(rr, 2 * h + 1));
       }
       named_bar_sync(3, kDenseColThreads + 32);
       __syncthreads();                                             // (s)
