@@ -82,7 +82,7 @@ def main():
               "points conserved (<= input)": bool(cl[:, 9].sum() <= N)}
     rng = np.random.default_rng(1)
     X = np.column_stack([rng.uniform(0, 0.5 * args.scans, args.queries), rng.uniform(-9, 9, args.queries), rng.uniform(-2, 4, args.queries)])
-    m.lookup(X[:1000])
+    m.lookup(X)                                  # warm-up at the same size: the first call of a size pays cudaMalloc (the pool is cold)
     t0 = time.perf_counter(); nd = m.lookup(X); t_lookup = (time.perf_counter() - t0) * 1e3
     m.close()
     # CPU restatement on a bounded sample (first scans only)
@@ -98,13 +98,16 @@ def main():
            "ms_device": best_dev, "ms_call": best_call, "points_per_s_device": N / (best_dev * 1e-3), "points_per_s_call": N / (best_call * 1e-3),
            "algorithmic_GBps_device": (12.0 * N + 80.0 * summ["nnz"]) / (best_dev * 1e-3) / 1e9,
            "h2d_bytes": int(summ["h2d_bytes"]), "kernel_launches": int(summ["kernel_launches"]),
-           "lookup": {"queries": int(args.queries), "ms_call": t_lookup, "hit_fraction": float(np.mean(np.any(nd != 0, axis=1)))},
+           "lookup": {"queries": int(args.queries), "ms_call": t_lookup, "note": "second call of this size (the first pays cudaMalloc)", "hit_fraction": float(np.mean(np.any(nd != 0, axis=1)))},
            "checks": checks, "cpu": cpu, "depth": None}
     print(json.dumps(out), flush=True)          # B3 alone first: it survives whatever the B4 part below does
     # ---- boundary B4 on the same scans: grid of world points + depth images of cameras riding on every 25th pose
     depth = None
     try:
         frame_ts = 0.1 * np.arange(args.scans)
+        t0 = time.perf_counter(); dg = pkg.DepthGrid(xyz, poses, frame_ts, 0.5, scan_ptr=scan_ptr); t_grid_cold = (time.perf_counter() - t0) * 1e3
+        cold_device = dg.summary["ms_device"]
+        dg.close()                                # its ~2 GB of buffers go back to the library's pool; the second build is the steady state
         t0 = time.perf_counter(); dg = pkg.DepthGrid(xyz, poses, frame_ts, 0.5, scan_ptr=scan_ptr); t_grid = (time.perf_counter() - t0) * 1e3
         ids = np.arange(0, args.scans, max(1, args.scans // 16))[:16]
         Rci = np.array([[0.0, -1.0, 0.0], [0.0, 0.0, -1.0], [1.0, 0.0, 0.0]])
@@ -118,7 +121,7 @@ def main():
         uv = np.column_stack([rng.uniform(0, 1279, 160000), rng.uniform(0, 1023, 160000)]).astype(np.float32)
         kp_ptr = np.arange(len(ids) + 1, dtype=np.int64) * 10000
         _, valid, binfo = dg.backproject(cams, frame_ts[ids], intr, 1280, 1024, kp_ptr, uv)
-        depth = {"grid": {"ms_call": t_grid, "ms_device": dg.summary["ms_device"], "n_voxels": dg.summary["n_voxels"], "n_pairs": dg.summary["n_pairs"]},
+        depth = {"grid": {"ms_call": t_grid, "ms_device": dg.summary["ms_device"], "ms_call_first": t_grid_cold, "ms_device_first": cold_device, "n_voxels": dg.summary["n_voxels"], "n_pairs": dg.summary["n_pairs"]},
                  "render": {"images": int(len(ids)), "size": "1280x1024", "ms_device": info["ms_device"], "ms_call": info["ms_total"],
                             "points_projected": int(info["work_chunks"]) * 64, "projections_per_s_device": info["work_chunks"] * 64 / max(info["ms_device"], 1e-9) * 1e3,
                             "filled_fraction": float(np.mean(img > 0)), "kernel_launches": int(info["kernel_launches"])},
