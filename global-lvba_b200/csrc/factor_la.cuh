@@ -47,7 +47,7 @@ struct LaCfg {
   // P = 31: one block per thread: 640 threads launch at 96 registers, 512*104 + 128*64 == 640*96
   //         two blocks per thread: 384 threads launch at 168, 256*200 + 128*96 <= 384*168
   static constexpr int kPairRegs = kTile2 ? 200 : 104, kLaRegs = kTile2 ? 96 : 64;
-  static constexpr int kDoubles = 6 * P * S + 2 * P * 36 + 2 * 36 + 36 + 2 * 36 + P * 6 + 48 + 40;
+  static constexpr int kDoubles = 6 * P * S + 2 * P * 36 + 2 * 36 + 36 + 2 * 36 + P * 6 + 48 + 40 + 48;    // ... + scratch of the warp-cooperative 6x6 inverse
   static constexpr size_t kSmem = sizeof(double) * (size_t)kDoubles + sizeof(long long) * 64 + sizeof(int) * 64 + 32;
 };
 
@@ -120,6 +120,66 @@ LVBA_DEV void sym6_block_inverse(const double (&x)[21], double (&K)[21]) {
     for (int j = 0; j < 3; ++j) K[LVBA_T(3 + i, j)] = K21[i][j];
 }
 
+// The same inverse computed by a WARP: lanes 0..8 <-> entry (i, j) of the 3 x 3 blocks, stages handed over through 45 doubles of
+// shared memory private to the warp.  One thread working through sym6_block_inverse issues ~280 dependent-ish instructions
+// (measured in the separator kernel: 1 700 cycles alone on its scheduler, 2 560 beside the pair warps — two thirds of a pivot
+// step); here a lane issues ~120, six hand-overs included.  D: 36 doubles row-major, LOWER triangle read.  K: 36 doubles, full,
+// exactly symmetric (the mirror entries are copies).  All 32 lanes must call; `scr` holds >= 48 doubles.
+LVBA_DEV void sym6_block_inverse_warp(const double* __restrict__ D, double* __restrict__ K, double* __restrict__ scr, int lane) {
+  const unsigned full = 0xffffffffu;
+  const bool on = lane < 9;
+  const int l = on ? lane : 0;
+  const int i = l / 3, j = l - 3 * i;
+  const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+  double* Ai = scr; double* W = scr + 9; double* S = scr + 18; double* Si = scr + 27; double* K21 = scr + 36;
+  auto d6 = [](int p, int q) { return p >= q ? p * 6 + q : q * 6 + p; };     // lower-triangle offsets of a 6 x 6 / 3 x 3 row-major block
+  auto d3 = [](int p, int q) { return p >= q ? p * 3 + q : q * 3 + p; };
+  {                                                                         // A^-1 = cofactors / det (A symmetric)
+    const double c = D[d6(i1, j1)] * D[d6(i2, j2)] - D[d6(i1, j2)] * D[d6(i2, j1)];
+    const double c0 = __shfl_sync(full, c, 0), c1 = __shfl_sync(full, c, 1), c2 = __shfl_sync(full, c, 2);
+    const double det = D[0] * c0 + D[6] * c1 + D[12] * c2;
+    const double r = __drcp_rn(det);
+    if (on) Ai[l] = c * r;
+  }
+  __syncwarp();
+  {                                                                         // W = B A^-1, B[i][m] = D(3+i, m)
+    const double* b = D + (3 + i) * 6;
+    const double w = b[0] * Ai[j] + b[1] * Ai[3 + j] + b[2] * Ai[6 + j];
+    if (on) W[l] = w;
+  }
+  __syncwarp();
+  {                                                                         // S = C - W B^T
+    const double* b = D + (3 + j) * 6;
+    const double v = D[d6(3 + i, 3 + j)] - (W[3 * i] * b[0] + W[3 * i + 1] * b[1] + W[3 * i + 2] * b[2]);
+    if (on) S[l] = v;
+  }
+  __syncwarp();
+  {                                                                         // S^-1 (lower triangle of S read)
+    const double c = S[d3(i1, j1)] * S[d3(i2, j2)] - S[d3(i1, j2)] * S[d3(i2, j1)];
+    const double c0 = __shfl_sync(full, c, 0), c1 = __shfl_sync(full, c, 1), c2 = __shfl_sync(full, c, 2);
+    const double det = S[0] * c0 + S[3] * c1 + S[6] * c2;
+    const double r = __drcp_rn(det);
+    if (on) Si[l] = c * r;
+  }
+  __syncwarp();
+  {                                                                         // K21 = -S^-1 W
+    const double v = -(Si[d3(i, 0)] * W[j] + Si[d3(i, 1)] * W[3 + j] + Si[d3(i, 2)] * W[6 + j]);
+    if (on) K21[l] = v;
+  }
+  __syncwarp();
+  if (on) {                                                                 // K11 = A^-1 - W^T K21 ; assemble K (lanes i >= j write the symmetric pairs)
+    const double k21 = K21[l];
+    K[(3 + i) * 6 + j] = k21; K[j * 6 + 3 + i] = k21;
+    if (i >= j) {
+      const double k11 = Ai[d3(i, j)] - (W[i] * K21[j] + W[3 + i] * K21[3 + j] + W[6 + i] * K21[6 + j]);
+      const double k22 = Si[d3(i, j)];
+      K[i * 6 + j] = k11; K[j * 6 + i] = k11;
+      K[(3 + i) * 6 + 3 + j] = k22; K[(3 + j) * 6 + 3 + i] = k22;
+    }
+  }
+  __syncwarp();
+}
+
 #ifdef LVBA_LAB
 __device__ int g_la_mode = 0;      // solver_lab only: 1 = pair threads skip their update, 2 = look-ahead group skips its math
 #endif
@@ -153,7 +213,8 @@ env_factor_la_kernel(const FactorJob* __restrict__ jobs, const unsigned* __restr
   double* sZ = sK + 72;                          // [P][6]
   double* sZin = sZ + P * 6;                     // [8][6]   rhs entries of the rows about to enter (ring by row & 7)
   double* sZero = sZin + 48;                     // [S]      zero operand (a block that must not change this step)
-  long long* sLabRS = reinterpret_cast<long long*>(sZero + 40);   // [64] row_start of row r at r & 63 (ring, filled by cp.async)
+  double* sInv = sZero + 40;                     // [48]     scratch of sym6_block_inverse_warp
+  long long* sLabRS = reinterpret_cast<long long*>(sInv + 48);    // [64] row_start of row r at r & 63 (ring, filled by cp.async)
   int* sLabF = reinterpret_cast<int*>(sLabRS + 64);              // [64] first column of row r at r & 63
   const int tid = threadIdx.x, lane = tid & 31;
   const int n = e.n;
@@ -459,23 +520,9 @@ env_factor_la_kernel(const FactorJob* __restrict__ jobs, const unsigned* __restr
     };
     // warp 0: K = D^-1.  src: 36 row-major, lower triangle read.  dst: 36 row-major, full symmetric.
     auto invert_pivot = [&](const double* src, double* dst, int kc) {
-      double x[21], K[21];
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j) x[LVBA_T(i, j)] = src[i * 6 + j];
-      sym6_block_inverse(x, K);
+      sym6_block_inverse_warp(src, dst, sInv, lane);
       // every entry of K carries one of the two reciprocals: four entries are enough to catch a singular pivot
-      if (!isfinite((K[LVBA_T(0, 0)] + K[LVBA_T(5, 5)]) + (K[LVBA_T(3, 0)] + K[LVBA_T(2, 1)]))) bad = 1;
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          double2* d2 = reinterpret_cast<double2*>(dst + i * 6);
-          auto kk = [&](int r, int c) -> double { return r >= c ? K[LVBA_T(r, c)] : K[LVBA_T(c, r)]; };
-          d2[0] = make_double2(kk(i, 0), kk(i, 1)); d2[1] = make_double2(kk(i, 2), kk(i, 3)); d2[2] = make_double2(kk(i, 4), kk(i, 5));
-        }
-      }
-      __syncwarp();
+      if (!isfinite((dst[0] + dst[35]) + (dst[18] + dst[13]))) bad = 1;
       if (lane < 18 && kc < n_stop) reinterpret_cast<double2*>(dinv + (long long)kc * 36)[lane] = reinterpret_cast<const double2*>(dst)[lane];
     };
     // column item: row slot `slot`, block row x.  t = T_{i,col}[x][.] (already updated); writes L_{i,col}[x][.] = t K

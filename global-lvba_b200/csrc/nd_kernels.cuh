@@ -358,7 +358,7 @@ constexpr int kDenseThreads = 768;           // 4 + 2 warpgroups (704..767 idle)
 constexpr int kDensePairRegs = 96, kDenseColRegs = 48;       // 512 * 96 + 256 * 48 == 768 * 80 = 61440, the pool the CTA is launched with: setmaxnreg.inc waits for ever if the budgets exceed it
 static_assert((kDenseColBase) * kDensePairRegs + (kDenseThreads - kDenseColBase) * kDenseColRegs <= kDenseThreads * 80, "register budgets exceed the launch pool");
 constexpr int kDenseS = 38;                  // doubles per operand block in shared memory (bank spread, 16 B aligned)
-constexpr size_t kDenseSmem = sizeof(double) * (6 * kDenseMax * kDenseS + 36 + 72 + kDenseMax * 6 + 8);
+constexpr size_t kDenseSmem = sizeof(double) * (6 * kDenseMax * kDenseS + 36 + 72 + kDenseMax * 6 + 8 + 48);
 
 // LVBA_DENSE_MODE (development, results are wrong unless 0): 1 = no trailing update by the pair threads, 2 = the inverting warp skips
 // the inverse (stale K), 4 = the column group skips apply and scale arithmetic; 8 (results stay right) = the pair threads start
@@ -374,6 +374,7 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
   double* sD = sC + 2 * kDenseMax * kDenseS;               // [36] pivot block (rows written by the six threads of block row s)
   double* sK = sD + 36;                                    // [2][36] its inverse, parity s & 1 (an idle warp copies it to global memory one step later)
   double* sZ = sK + 72;                                    // [30][6]
+  double* sInv = sZ + kDenseMax * 6 + 8;                   // [48] scratch of sym6_block_inverse_warp
   const FactorJob J = jobs[blockIdx.x];
   const int n = J.e.n;
   const int tid = threadIdx.x;
@@ -468,25 +469,11 @@ nd_dense_factor_kernel(const FactorJob* __restrict__ jobs, const unsigned short*
     for (int s = 0; s < n; ++s) {
       named_bar_sync(2, kDenseColThreads + 32);
       LVBA_DSTAMP(2, lane == 0);
-      double xl[21], K[21];
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-#pragma unroll
-        for (int b = 0; b <= a; ++b) xl[LVBA_T(a, b)] = sD[a * 6 + b];
-      if (!(dense_mode & 2)) sym6_block_inverse(xl, K);
-      else {
-#pragma unroll
-        for (int q = 0; q < 21; ++q) K[q] = xl[q];
-      }
-      auto kk = [&](int rr, int c) -> double { return rr >= c ? K[LVBA_T(rr, c)] : K[LVBA_T(c, rr)]; };
-      if (!isfinite((K[LVBA_T(0, 0)] + K[LVBA_T(5, 5)]) + (K[LVBA_T(3, 0)] + K[LVBA_T(2, 1)]))) bad = 1;
-      if (lane == 0) {                                             // D_s^-1 (full symmetric) for the column group; 18 STS.128
-        double2* k2 = reinterpret_cast<double2*>(sK + (s & 1) * 36);
-#pragma unroll
-        for (int rr = 0; rr < 6; ++rr)
-#pragma unroll
-          for (int h = 0; h < 3; ++h) k2[rr * 3 + h] = make_double2(kk(rr, 2 * h), kk(rr, 2 * h + 1));
-      }
+      double* Kp = sK + (s & 1) * 36;                              // D_s^-1 (full symmetric) for the column group, and for the idle warp that copies it out
+      if (!(dense_mode & 2)) sym6_block_inverse_warp(sD, Kp, sInv, lane);
+      else if (lane < 18) reinterpret_cast<double2*>(Kp)[lane] = reinterpret_cast<const double2*>(sD)[lane];
+      __syncwarp();
+      if (!isfinite((Kp[0] + Kp[35]) + (Kp[18] + Kp[13]))) bad = 1;
       LVBA_DSTAMP(5, lane == 0);
       named_bar_sync(3, kDenseColThreads + 32);
       if (dense_mode & 8) __syncthreads();                         // (X)
