@@ -188,15 +188,19 @@ nd_spike_kernel(const nd::SpikeJob* __restrict__ jobs) {
 // product (KS x R)(R x KS), R = 6 rows, of Z^T with Y = K Z.  grid = (tiles of 64 x 64 scalars of the lower triangle,
 // groups of kSyrkSplit block rows, segments); a CTA walks its rows in chunks of 4 block rows: Z for the tile's row and
 // column side is brought to shared memory by cp.async one chunk ahead, Y = K Z is formed there, each thread accumulates a
-// 4 x 4 register tile.  Partial sums of the row groups meet in U by RED.ADD.F64.  FP64-FMA bound.
+// 8 x 8 register tile (64 threads per 64 x 64 tile: 16 operand doubles from shared memory per 64 FMAs — a 4 x 4 tile loads 8 per 16
+// and is bound by the 128 B/clk shared-memory return path, at half the FP64 rate).  A thread's rows / columns are four PAIRS 16 apart
+// (2 t + 16 m + {0,1}), so that the LDS.128 of a warp cover 128 contiguous bytes.  Partial sums of the row groups meet in U by
+// RED.ADD.F64.
 constexpr int kSyrkTile = 64;            // scalar columns per tile side
+constexpr int kSyrkThreads = 64;         // 8 x 8 threads, 8 x 8 outputs each
 constexpr int kSyrkChunk = 4;            // block rows per shared-memory chunk (24 scalar rows)
 constexpr int kSyrkSplit = 8;            // block rows per CTA (default; LVBA_SYRK_SPLIT overrides): two chunks, both in flight from the start
 constexpr int kSyrkLd = kSyrkTile + 4;   // leading dimension of the shared tiles
 constexpr int kSyrkTileDoubles = kSyrkChunk * 6 * kSyrkLd;
 constexpr size_t kSyrkSmem = sizeof(double) * (5 * kSyrkTileDoubles + 2 * kSyrkChunk * 36 + 2 * kSyrkChunk * 6 + kSyrkChunk * 6);
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSyrkThreads)
 nd_syrk_kernel(const nd::SyrkSeg* __restrict__ segs, int split) {
   constexpr int TS = kSyrkTile, RC = kSyrkChunk * 6, LD = kSyrkLd;
   extern __shared__ __align__(16) double smem_syrk[];
@@ -213,36 +217,36 @@ nd_syrk_kernel(const nd::SyrkSeg* __restrict__ segs, int split) {
   const int k0 = blockIdx.y * split;
   if (k0 >= G.rows) return;
   const int k1 = min(G.rows, k0 + split);
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
   const int KS = G.KS;
   // chunk kc -> buffer par: 16-byte pieces (KS is even, the tiles start at even columns); rows / columns beyond the data are zero-filled
   auto prefetch = [&](int kc, int par) {
     const int nr = min(kSyrkChunk, k1 - kc) * 6;
     double* dA = sA + par * kSyrkTileDoubles;
     double* dB = sB + par * kSyrkTileDoubles;
-    for (int o = tid; o < RC * (TS / 2); o += 256) {
+    for (int o = tid; o < RC * (TS / 2); o += kSyrkThreads) {
       const int r = o / (TS / 2), a2 = (o - r * (TS / 2)) * 2;
       const double* zr = G.Z + ((long long)kc * 6 + (r < nr ? r : 0)) * KS;
       const bool va = r < nr && ti * TS + a2 < KS, vb = r < nr && tj * TS + a2 < KS;
       cp_async16_zfill(dA + r * LD + a2, va ? zr + ti * TS + a2 : G.Z, va);
       cp_async16_zfill(dB + r * LD + a2, vb ? zr + tj * TS + a2 : G.Z, vb);
     }
-    for (int o = tid; o < kSyrkChunk * 18; o += 256) {
+    for (int o = tid; o < kSyrkChunk * 18; o += kSyrkThreads) {
       const int bk = o / 18;
       const bool v = kc + bk < k1;
       cp_async16_zfill(sK + par * kSyrkChunk * 36 + 2 * o, v ? G.K + (long long)kc * 36 + 2 * o : G.K, v);
     }
-    for (int o = tid; o < kSyrkChunk * 3; o += 256) {
+    for (int o = tid; o < kSyrkChunk * 3; o += kSyrkThreads) {
       const int bk = o / 3;
       const bool v = kc + bk < k1;
       cp_async16_zfill(sW + par * RC + 2 * o, v ? G.w + (long long)kc * 6 + 2 * o : G.w, v);
     }
   };
-  double acc[4][4];
+  double acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
   double racc = 0.0;
   prefetch(k0, 0);
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -255,7 +259,7 @@ nd_syrk_kernel(const nd::SyrkSeg* __restrict__ segs, int split) {
     const double* cA = sA + par * kSyrkTileDoubles;
     const double* cB = sB + par * kSyrkTileDoubles;
     const double* cK = sK + par * kSyrkChunk * 36;
-    for (int o = tid; o < RC * TS; o += 256) {                           // Y = K Z on the column side
+    for (int o = tid; o < RC * TS; o += kSyrkThreads) {                  // Y = K Z on the column side
       const int r = o / TS, b = o - r * TS, bk = r / 6, x = r - bk * 6;
       const double* Kx = cK + bk * 36 + x * 6;
       double s = 0.0;
@@ -271,15 +275,19 @@ nd_syrk_kernel(const nd::SyrkSeg* __restrict__ segs, int split) {
       sKw[tid] = s;
     }
     __syncthreads();
-#pragma unroll 4
+#pragma unroll 2
     for (int r = 0; r < RC; ++r) {
-      const double2 a01 = *reinterpret_cast<const double2*>(cA + r * LD + 4 * ty), a23 = *reinterpret_cast<const double2*>(cA + r * LD + 4 * ty + 2);
-      const double2 b01 = *reinterpret_cast<const double2*>(sY + r * LD + 4 * tx), b23 = *reinterpret_cast<const double2*>(sY + r * LD + 4 * tx + 2);
-      const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+      double av[8], bv[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int m = 0; m < 4; ++m) {
+        const double2 a = *reinterpret_cast<const double2*>(cA + r * LD + 2 * ty + 16 * m);
+        const double2 b = *reinterpret_cast<const double2*>(sY + r * LD + 2 * tx + 16 * m);
+        av[2 * m] = a.x; av[2 * m + 1] = a.y; bv[2 * m] = b.x; bv[2 * m + 1] = b.y;
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
     }
     if (tj == 0 && tid < TS) {
       double s = 0.0;
@@ -289,10 +297,10 @@ nd_syrk_kernel(const nd::SyrkSeg* __restrict__ segs, int split) {
     __syncthreads();                                                     // sY, sKw and this chunk's buffers are free again
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int ga = ti * TS + 4 * ty + i, gb = tj * TS + 4 * tx + j;       // scalar row / column inside the boundary
+    for (int j = 0; j < 8; ++j) {
+      const int ga = ti * TS + 2 * ty + 16 * (i >> 1) + (i & 1), gb = tj * TS + 2 * tx + 16 * (j >> 1) + (j & 1);   // scalar row / column inside the boundary
       const int bi = ga / 6, bj = gb / 6;
       if (bj <= bi && ga < KS && gb < KS) atomicAdd(&G.U[((long long)bi * (bi + 1) / 2 + bj) * 36 + (ga - 6 * bi) * 6 + (gb - 6 * bj)], -acc[i][j]);
     }

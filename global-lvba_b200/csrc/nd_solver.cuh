@@ -239,7 +239,7 @@ struct NdCudaExec {
     if (n <= 0 || max_ks <= 0) return;
     const int nt1 = (max_ks + kSyrkTile - 1) / kSyrkTile, nt = nt1 * (nt1 + 1) / 2;
     static const int split = [] { const char* e = getenv("LVBA_SYRK_SPLIT"); const int v = e ? atoi(e) : 0; return v > 0 ? ((v + kSyrkChunk - 1) / kSyrkChunk) * kSyrkChunk : kSyrkSplit; }();
-    nd_syrk_kernel<<<dim3(nt, (max_rows + split - 1) / split, n), 256, kSyrkSmem, s>>>(segs, split);
+    nd_syrk_kernel<<<dim3(nt, (max_rows + split - 1) / split, n), kSyrkThreads, kSyrkSmem, s>>>(segs, split);
     ++launches;
   }
   void correct_apply(const nd::Tables& t, const int* ids, int n_ids, int stride) {
