@@ -121,10 +121,12 @@ LVBA_DEV void sym6_block_inverse(const double (&x)[21], double (&K)[21]) {
 }
 
 // The same inverse computed by a WARP: lanes 0..8 <-> entry (i, j) of the 3 x 3 blocks, stages handed over through 45 doubles of
-// shared memory private to the warp.  One thread working through sym6_block_inverse issues ~280 dependent-ish instructions
-// (measured in the separator kernel: 1 700 cycles alone on its scheduler, 2 560 beside the pair warps — two thirds of a pivot
-// step); here a lane issues ~120, six hand-overs included.  D: 36 doubles row-major, LOWER triangle read.  K: 36 doubles, full,
-// exactly symmetric (the mirror entries are copies).  All 32 lanes must call; `scr` holds >= 48 doubles.
+// shared memory private to the warp; a lane issues ~120 instructions where one thread working through sym6_block_inverse issues
+// ~280, and 84 registers of the calling warp become free.  Measured with in-kernel clocks in the separator kernel
+// (make EXTRA=-DLVBA_DENSE_CLOCKS, LVBA_DENSE_MODE=16/17): NOT faster — 1 970 cycles against 1 710 alone on its scheduler, 2 800
+// against 2 570 beside the pair warps: the segment is bound by the latency of the two reciprocals and of the hand-overs, not by the
+// instruction count.  Kept for the registers it frees.  D: 36 doubles row-major, LOWER triangle read.  K: 36 doubles, full, exactly
+// symmetric (the mirror entries are copies).  All 32 lanes must call; `scr` holds >= 48 doubles.
 LVBA_DEV void sym6_block_inverse_warp(const double* __restrict__ D, double* __restrict__ K, double* __restrict__ scr, int lane) {
   const unsigned full = 0xffffffffu;
   const bool on = lane < 9;
