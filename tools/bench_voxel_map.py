@@ -92,7 +92,8 @@ def main():
         k = min(args.cpu_sample_scans, args.scans)
         scans = [xyz[scan_ptr[j]:scan_ptr[j + 1]] for j in range(k)]
         t0 = time.perf_counter(); vox.voxelize(scans, poses[:k], args.voxel_size); tc = time.perf_counter() - t0
-        cpu = {"points_per_s": k * args.points / tc, "kind": "port (numpy, 1 thread)", "sample": f"{k} scans x {args.points} points"}
+        cpu = {"points_per_s": k * args.points / tc, "kind": "port (numpy, 1 thread)", "sample": f"{k} scans x {args.points} points",
+               "note": "a single-thread numpy restatement: reported for orientation, not a baseline to quote a speed-up against"}
     out = {"workload": f"{args.scans} scans x {args.points} points (street scene), root voxel {args.voxel_size} m, layer_limit 2",
            "n_points": int(N), "n_voxels": int(summ["n_voxels"]), "nnz": int(summ["nnz"]), "n_nodes": summ["n_nodes"],
            "ms_device": best_dev, "ms_call": best_call, "points_per_s_device": N / (best_dev * 1e-3), "points_per_s_call": N / (best_call * 1e-3),
