@@ -15,6 +15,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real CUDA device (run on the B200 box)")
 
 
+def pytest_collection_finish(session):
+    """tests/test_emu_shuffled.py re-runs the host-policy suites in three child processes; when it is part of the run, start
+    them now so that they work beside the rest of the (mostly single-threaded) CPU suite instead of after it."""
+    for item in session.items:
+        if item.nodeid.startswith("tests/test_emu_shuffled.py") or "/test_emu_shuffled.py" in item.nodeid:
+            if not session.config.option.collectonly:
+                item.module._launch_all()
+            break
+
+
 @pytest.fixture(scope="session")
 def pkg():
     """The ctypes binding of liblvba_b200.so (built on demand; never a CPU fallback)."""

@@ -77,8 +77,14 @@ CASES = [
 ]
 
 
+# shuffled / sanitizer re-runs (tests/test_emu_shuffled.py) leave out the largest systems (ASan slows the solves ~10x)
+RERUN_MAX_N = (600 if os.environ.get("LVBA_EMU_SANITIZE") else 1000) if os.environ.get("LVBA_EMU_RERUN") else None
+
+
 @pytest.mark.parametrize("n,b,p,indef", CASES)
 def test_banded_systems_match_dense_solve(emu, n, b, p, indef):
+    if RERUN_MAX_N and n >= RERUN_MAX_N:
+        pytest.skip("size case; covered by the plain run")
     rng = np.random.default_rng(1000 * n + p)
     first, rs = envelope([max(0, r - b) for r in range(n)])
     M, H = random_system(n, first, rs, rng, indef)
@@ -155,6 +161,8 @@ def test_rank_sharded_solve_matches_dense(emu, n, b, p, ranks):
     """Multi-GPU data flow without GPUs: every rank holds ONLY the rows it owns (the rest is NaN), eliminates its
     own chunks and inner separators, the fixed-size slots (subtree-root update + rank-separator rows) are all-gathered, the top
     tree is eliminated redundantly, x is assembled from the owned rows."""
+    if RERUN_MAX_N and n >= RERUN_MAX_N:
+        pytest.skip("size case; covered by the plain run")
     rng = np.random.default_rng(7000 + n + ranks)
     first, rs = envelope([max(0, r - b) for r in range(n)])
     M, H = random_system(n, first, rs, rng, True)
