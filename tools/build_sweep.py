@@ -10,21 +10,33 @@ import numpy as np
 import __graft_entry__ as graft
 from oracle import synth
 
-ap = argparse.ArgumentParser(); ap.add_argument("--out", default=""); args = ap.parse_args()
-pkg = graft.load_package(); pkg.load_library()
-try:
-    peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]); src = "measured"
-except Exception:
-    peak, src = 6650.0, "fallback"
+ap = argparse.ArgumentParser(); ap.add_argument("--out", default=""); ap.add_argument("--ks", default="2,3,4,6,8,12,16"); args = ap.parse_args()
+KS = tuple(int(k) for k in args.ks.split(","))
 W, NNZ = 2000, 1_400_000
-rows = []
-for K in (2, 3, 4, 6, 8, 12, 16):
+
+
+def generate(K):
+    """One sweep point: the config-C generator (oracle/synth.py) at a fixed number of poses per voxel."""
     V = NNZ // K
     rng = np.random.Generator(np.random.Philox(key=20260923 + K))
     R_gt, p_gt = synth.make_trajectory(W, rng)
     R0 = R_gt @ synth.so3_exp(rng.normal(0, 0.005, (W, 3))); p0 = p_gt + rng.normal(0, 0.03, (W, 3))
     vp, pi, cl = synth.make_lidar(W, V, R_gt, p_gt, rng, k_lo=K, k_hi=K)
-    poses = np.concatenate([R0.reshape(W, 9), p0], 1)
+    return K, V, vp, pi, cl, np.concatenate([R0.reshape(W, 9), p0], 1)
+
+
+# the generator simulates every point of every cluster (20-40 s per sweep point on one core): all points at once, in child
+# processes forked BEFORE the CUDA library is loaded
+import multiprocessing as mp
+with mp.get_context("fork").Pool(len(KS)) as pool:
+    problems = pool.map(generate, KS)
+pkg = graft.load_package(); pkg.load_library()
+try:
+    peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]); src = "measured"
+except Exception:
+    peak, src = 6650.0, "fallback"
+rows = []
+for K, V, vp, pi, cl, poses in problems:
     L = pkg.LidarProblem(vp, pi, cl, poses)
     o = pkg.lidar_default_opts(); o.rel_tol = -1.0; o.max_iter = 1 << 30
     tb, tr = [], []
