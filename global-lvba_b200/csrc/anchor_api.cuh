@@ -14,7 +14,7 @@ struct lvba_anchor_clouds {
 extern "C" {
 
 int lvba_anchor_clouds_create(int32_t n_windows, const int32_t* win_ptr, const int64_t* scan_ptr, const float* xyz, int32_t xyz_stride_floats,
-                              const double* rel_poses, double leaf, int32_t device, lvba_anchor_clouds** out, int64_t* n_points_out) {
+                              const double* rel_poses, double leaf, int32_t device, lvba_anchor_clouds** out, int64_t* n_points_out) LVBA_ABI_BEGIN {
   if (!out) return lvba::fail(LVBA_ERR_INVALID_ARG, "null output handle");
   *out = nullptr;
   if (n_windows <= 0 || !win_ptr || !scan_ptr) return lvba::fail(LVBA_ERR_INVALID_ARG, "n_windows=%d must be positive, win_ptr / scan_ptr non-null", n_windows);
@@ -74,9 +74,9 @@ int lvba_anchor_clouds_create(int32_t n_windows, const int32_t* win_ptr, const i
   if (n_points_out) *n_points_out = h->ac.n_out;
   *out = h.release();
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_anchor_clouds_create")
 
-int lvba_anchor_clouds_export(lvba_anchor_clouds* a, int64_t* cloud_ptr, float* xyz, double* ms_device) {
+int lvba_anchor_clouds_export(lvba_anchor_clouds* a, int64_t* cloud_ptr, float* xyz, double* ms_device) LVBA_ABI_BEGIN {
   if (!a) return lvba::fail(LVBA_ERR_INVALID_ARG, "null handle");
   LVBA_CUDA(cudaSetDevice(a->device));
   cudaStream_t s = a->ac.ex.stream;
@@ -85,13 +85,13 @@ int lvba_anchor_clouds_export(lvba_anchor_clouds* a, int64_t* cloud_ptr, float* 
   LVBA_CUDA(cudaStreamSynchronize(s));
   if (ms_device) *ms_device = a->ms_device;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_anchor_clouds_export")
 
-int lvba_anchor_clouds_destroy(lvba_anchor_clouds* a) {
+int lvba_anchor_clouds_destroy(lvba_anchor_clouds* a) LVBA_ABI_BEGIN {
   if (!a) return LVBA_OK;
   cudaSetDevice(a->device);
   delete a;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_anchor_clouds_destroy")
 
 }  // extern "C"

@@ -15,7 +15,7 @@ extern "C" {
 
 int lvba_depth_grid_create(int32_t n_frames, const int64_t* scan_ptr, const float* xyz, int32_t xyz_stride_floats,
                            const double* poses, const double* frame_ts, double voxel_size, int32_t device,
-                           lvba_depth_grid** out, lvba_depth_summary* summary) {
+                           lvba_depth_grid** out, lvba_depth_summary* summary) LVBA_ABI_BEGIN {
   using clk = std::chrono::steady_clock;
   const auto t0 = clk::now();
   if (!out) return lvba::fail(LVBA_ERR_INVALID_ARG, "null output handle");
@@ -82,10 +82,10 @@ int lvba_depth_grid_create(int32_t n_frames, const int64_t* scan_ptr, const floa
   if (summary) *summary = s;
   *out = h.release();
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_depth_grid_create")
 
 int lvba_depth_render(lvba_depth_grid* g, int32_t n_images, const double* cams, const double* image_ts, double half_window,
-                      const double intr[8], int32_t width, int32_t height, float* depth, lvba_depth_summary* summary) {
+                      const double intr[8], int32_t width, int32_t height, float* depth, lvba_depth_summary* summary) LVBA_ABI_BEGIN {
   using clk = std::chrono::steady_clock;
   const auto t0 = clk::now();
   if (!g || n_images < 0 || (n_images > 0 && (!cams || !image_ts || !depth)) || !intr) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument or negative image count");
@@ -133,13 +133,13 @@ int lvba_depth_render(lvba_depth_grid* g, int32_t n_images, const double* cams, 
     summary->work_pairs = pairs; summary->work_chunks = chunks;
   }
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_depth_render")
 
 // The depth-candidate loop of BuildTracksAndFuse3D (src/lvba_system.cpp:1020-1038) for every keypoint of every image: the
 // images are rendered batch by batch and sampled where they are; they never leave the device.
 int lvba_depth_backproject(lvba_depth_grid* g, int32_t n_images, const double* cams, const double* image_ts, double half_window,
                            const double intr[8], int32_t width, int32_t height, const int64_t* kp_ptr, const float* kp_uv,
-                           double* Xw, uint8_t* valid, lvba_depth_summary* summary) {
+                           double* Xw, uint8_t* valid, lvba_depth_summary* summary) LVBA_ABI_BEGIN {
   using clk = std::chrono::steady_clock;
   const auto t0 = clk::now();
   if (!g || n_images < 0 || !intr || !kp_ptr || (n_images > 0 && (!cams || !image_ts))) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument or negative image count");
@@ -205,13 +205,13 @@ int lvba_depth_backproject(lvba_depth_grid* g, int32_t n_images, const double* c
     summary->work_pairs = pairs; summary->work_chunks = chunks;
   }
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_depth_backproject")
 
-int lvba_depth_grid_destroy(lvba_depth_grid* g) {
+int lvba_depth_grid_destroy(lvba_depth_grid* g) LVBA_ABI_BEGIN {
   if (!g) return LVBA_OK;
   cudaSetDevice(g->device);
   delete g;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_depth_grid_destroy")
 
 }  // extern "C"

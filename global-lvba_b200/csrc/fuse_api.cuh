@@ -27,7 +27,7 @@ void lvba_fuse_default_opts(lvba_fuse_opts* o) {
 int lvba_tracks_fuse_create(int32_t n_images, const int64_t* kp_ptr, const float* kp_uv, int64_t n_matches, const int32_t* match_img_a,
                             const int32_t* match_kp_a, const int32_t* match_img_b, const int32_t* match_kp_b, const double* cams,
                             const double intr[8], const double* kp_Xw, const uint8_t* kp_valid, const lvba_fuse_opts* opts,
-                            lvba_track_set** out, lvba_fuse_summary* summary) {
+                            lvba_track_set** out, lvba_fuse_summary* summary) LVBA_ABI_BEGIN {
   using namespace lvba;
   if (!out) return fail(LVBA_ERR_INVALID_ARG, "out is null");
   *out = nullptr;
@@ -69,16 +69,16 @@ int lvba_tracks_fuse_create(int32_t n_images, const int64_t* kp_ptr, const float
   if (summary) *summary = s;
   *out = h.release();
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_tracks_fuse_create")
 
-int lvba_tracks_fuse_summary(const lvba_track_set* s, lvba_fuse_summary* summary) {
+int lvba_tracks_fuse_summary(const lvba_track_set* s, lvba_fuse_summary* summary) LVBA_ABI_BEGIN {
   if (!s || !summary) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   *summary = s->sum;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_tracks_fuse_summary")
 
 int lvba_tracks_fuse_export(lvba_track_set* s, int64_t* obs_ptr, int32_t* obs_img, int32_t* obs_kp, uint8_t* obs_inlier, double* Xw,
-                            uint8_t* source, double* mean_reproj) {
+                            uint8_t* source, double* mean_reproj) LVBA_ABI_BEGIN {
   if (!s || !obs_ptr) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   int64_t o = 0;
   obs_ptr[0] = 0;
@@ -95,11 +95,11 @@ int lvba_tracks_fuse_export(lvba_track_set* s, int64_t* obs_ptr, int32_t* obs_im
     if (mean_reproj) mean_reproj[i] = t.mean;
   }
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_tracks_fuse_export")
 
-int lvba_tracks_fuse_destroy(lvba_track_set* s) {
+int lvba_tracks_fuse_destroy(lvba_track_set* s) LVBA_ABI_BEGIN {
   delete s;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_tracks_fuse_destroy")
 
 }  // extern "C"

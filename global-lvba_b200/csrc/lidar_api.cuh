@@ -771,40 +771,40 @@ int lvba_lidar_create(int32_t W, int64_t V, const int64_t* vox_ptr, const int32_
   catch (...) { return lvba::fail(LVBA_ERR_INVALID_ARG, "unexpected exception in lvba_lidar_create"); }
 }
 
-int lvba_lidar_destroy(lvba_lidar_problem* p) {
+int lvba_lidar_destroy(lvba_lidar_problem* p) LVBA_ABI_BEGIN {
   if (!p) return LVBA_OK;
   cudaSetDevice(p->device);
   delete p;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_lidar_destroy")
 
-int lvba_lidar_set_poses(lvba_lidar_problem* p, const double* poses) {
+int lvba_lidar_set_poses(lvba_lidar_problem* p, const double* poses) LVBA_ABI_BEGIN {
   if (!p || !poses) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   LVBA_TRY(p->poses.upload(poses, (size_t)p->W * 12, p->stream, &p->h2d));
   LVBA_CUDA(cudaStreamSynchronize(p->stream));
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_lidar_set_poses")
 
-int lvba_lidar_get_poses(lvba_lidar_problem* p, double* poses) {
+int lvba_lidar_get_poses(lvba_lidar_problem* p, double* poses) LVBA_ABI_BEGIN {
   if (!p || !poses) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   LVBA_CUDA(cudaMemcpyAsync(poses, p->poses.p, (size_t)p->W * 12 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
   LVBA_CUDA(cudaStreamSynchronize(p->stream));
   p->d2h += (int64_t)p->W * 96;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_lidar_get_poses")
 
-int lvba_lidar_build(lvba_lidar_problem* p, double* residual_sum) {
+int lvba_lidar_build(lvba_lidar_problem* p, double* residual_sum) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   LVBA_TRY(lvba::lidar_build_dev(p, p->poses.p, 0));
   LVBA_TRY(lvba::lidar_fetch_scal(p));
   if (residual_sum) *residual_sum = p->h_scal[0];
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_lidar_build")
 
-int lvba_lidar_residual(lvba_lidar_problem* p, const double* poses, double* residual_sum) {
+int lvba_lidar_residual(lvba_lidar_problem* p, const double* poses, double* residual_sum) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   const double* dp = p->poses.p;
@@ -816,9 +816,9 @@ int lvba_lidar_residual(lvba_lidar_problem* p, const double* poses, double* resi
   LVBA_TRY(lvba::lidar_fetch_scal(p));
   if (residual_sum) *residual_sum = p->h_scal[3];
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_lidar_residual")
 
-int lvba_lidar_solve(lvba_lidar_problem* p, double u, double* dx) {
+int lvba_lidar_solve(lvba_lidar_problem* p, double u, double* dx) LVBA_ABI_BEGIN {
   if (!p || !dx) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   LVBA_TRY(lvba::lidar_solve_dev(p, u));
@@ -826,9 +826,9 @@ int lvba_lidar_solve(lvba_lidar_problem* p, double u, double* dx) {
   LVBA_TRY(lvba::lidar_fetch_scal(p));
   p->d2h += (int64_t)p->W * 48;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_lidar_solve")
 
-int lvba_lidar_structure(lvba_lidar_problem* p, int64_t* nblocks, int32_t* brow, int32_t* bcol) {
+int lvba_lidar_structure(lvba_lidar_problem* p, int64_t* nblocks, int32_t* brow, int32_t* bcol) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   if (nblocks) *nblocks = p->env.nblocks;
   if (brow && bcol) {
@@ -839,39 +839,39 @@ int lvba_lidar_structure(lvba_lidar_problem* p, int64_t* nblocks, int32_t* brow,
       }
   }
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_lidar_structure")
 
-int lvba_lidar_get_system(lvba_lidar_problem* p, double* g, double* blocks) {
+int lvba_lidar_get_system(lvba_lidar_problem* p, double* g, double* blocks) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   if (g) LVBA_CUDA(cudaMemcpyAsync(g, p->g.p, (size_t)p->W * 6 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
   if (blocks) LVBA_CUDA(cudaMemcpyAsync(blocks, p->H.p, (size_t)p->env.nblocks * 36 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
   LVBA_CUDA(cudaStreamSynchronize(p->stream));
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_lidar_get_system")
 
-int lvba_lidar_reset_lm(lvba_lidar_problem* p, const lvba_lidar_opts* opts) {
+int lvba_lidar_reset_lm(lvba_lidar_problem* p, const lvba_lidar_opts* opts) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   if (opts) p->opts = *opts; else lvba_lidar_default_opts(&p->opts);
   p->u = p->opts.u0; p->v = p->opts.v0; p->is_calc_hess = true; p->have_first = false; p->converged = false;
   p->iters = p->accepted = p->builds = 0; p->termination = LVBA_TERM_MAX_ITER; p->residual1 = 0.0;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_lidar_reset_lm")
 
-int lvba_lidar_reset_state(lvba_lidar_problem* p) {
+int lvba_lidar_reset_state(lvba_lidar_problem* p) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   LVBA_CUDA(cudaMemcpyAsync(p->poses.p, p->poses0.p, (size_t)p->W * 12 * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_lidar_reset_state")
 
-int lvba_lidar_iterate(lvba_lidar_problem* p, int32_t n_iter, lvba_summary* summary) {
+int lvba_lidar_iterate(lvba_lidar_problem* p, int32_t n_iter, lvba_summary* summary) LVBA_ABI_BEGIN {
   if (!p || n_iter < 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "bad argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   return lvba::lidar_iterate_impl(p, n_iter, summary);
-}
+} LVBA_ABI_END("lvba_lidar_iterate")
 
-int lvba_lidar_counts(lvba_lidar_problem* p, int64_t* nnz, int64_t* n_blocks_env, int64_t* n_blocks_nonzero, int64_t* n_pairs) {
+int lvba_lidar_counts(lvba_lidar_problem* p, int64_t* nnz, int64_t* n_blocks_env, int64_t* n_blocks_nonzero, int64_t* n_pairs) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   if (!p->have_structure) return lvba::fail(LVBA_ERR_UNSUPPORTED, "this problem was created without its host-side structure copy");
   if (nnz) *nnz = (int64_t)p->h_pose_idx_all.size();
@@ -890,7 +890,7 @@ int lvba_lidar_counts(lvba_lidar_problem* p, int64_t* nnz, int64_t* n_blocks_env
   if (n_pairs) *n_pairs = np;
   if (want_nz) *n_blocks_nonzero = (int64_t)seen.size();
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_lidar_counts")
 
 int lvba_lidar_lm(int32_t W, int64_t V, const int64_t* vox_ptr, const int32_t* pose_idx, const double* clusters,
                   double* poses, const lvba_lidar_opts* opts, lvba_summary* summary) {

@@ -32,7 +32,7 @@ const char* lvba_status_string(int status) {
 
 // ---------------------------------------------------------------- the block LDL^T on its own (diagnostics / tests)
 int lvba_env_solve(int32_t n, const int32_t* first, const double* blocks, const double* dadd, const double* rhs,
-                   double* x, int32_t path, int32_t chunks, int32_t reps, int32_t device, double* ms, int32_t* info) {
+                   double* x, int32_t path, int32_t chunks, int32_t reps, int32_t device, double* ms, int32_t* info) LVBA_ABI_BEGIN {
   using namespace lvba;
   if (n <= 0 || !first || !blocks || !dadd || !rhs || !x) return fail(LVBA_ERR_INVALID_ARG, "null argument or n <= 0");
   if (path < LVBA_SOLVE_AUTO || path > LVBA_SOLVE_ANY_WIDTH) return fail(LVBA_ERR_INVALID_ARG, "unknown path %d", path);
@@ -91,10 +91,10 @@ int lvba_env_solve(int32_t n, const int32_t* first, const double* blocks, const 
     cudaStreamSynchronize(s);       // nothing of `sol` / the buffers may be in flight when they go back to the pool
   }
   return rc;
-}
+} LVBA_ABI_END("lvba_env_solve")
 
 // ---------------------------------------------------------------- multi-GPU
-int lvba_comm_unique_id(void* id_out) {
+int lvba_comm_unique_id(void* id_out) LVBA_ABI_BEGIN {
   if (!id_out) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   lvba::Comm& c = lvba::comm();
   LVBA_TRY(c.load());
@@ -104,9 +104,9 @@ int lvba_comm_unique_id(void* id_out) {
   if (r != ncclSuccess) return lvba::fail(LVBA_ERR_COMM, "ncclGetUniqueId: %s", c.GetErrorString(r));
   memcpy(id_out, &id, sizeof id);
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_comm_unique_id")
 
-int lvba_comm_init(int32_t n_ranks, int32_t rank, const void* id, int32_t device) {
+int lvba_comm_init(int32_t n_ranks, int32_t rank, const void* id, int32_t device) LVBA_ABI_BEGIN {
   if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return lvba::fail(LVBA_ERR_INVALID_ARG, "bad rank %d / %d", rank, n_ranks);
   lvba::Comm& c = lvba::comm();
   if (c.comm) return lvba::fail(LVBA_ERR_INVALID_ARG, "communicator already initialised");
@@ -120,21 +120,21 @@ int lvba_comm_init(int32_t n_ranks, int32_t rank, const void* id, int32_t device
   ncclResult_t r = c.CommInitRank(&c.comm, n_ranks, uid, rank);
   if (r != ncclSuccess) { c.comm = nullptr; c.n_ranks = 1; c.rank = 0; return lvba::fail(LVBA_ERR_COMM, "ncclCommInitRank: %s", c.GetErrorString(r)); }
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_comm_init")
 
-int lvba_comm_destroy(void) {
+int lvba_comm_destroy(void) LVBA_ABI_BEGIN {
   lvba::Comm& c = lvba::comm();
   if (c.comm) { c.CommDestroy(c.comm); c.comm = nullptr; }
   c.n_ranks = 1; c.rank = 0;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_comm_destroy")
 
-int lvba_comm_info(int32_t* n_ranks, int32_t* rank) {
+int lvba_comm_info(int32_t* n_ranks, int32_t* rank) LVBA_ABI_BEGIN {
   lvba::Comm& c = lvba::comm();
   if (n_ranks) *n_ranks = c.n_ranks;
   if (rank) *rank = c.rank;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_comm_info")
 
 int64_t lvba_comm_bytes_sent(void) {
   lvba::Comm& c = lvba::comm();
@@ -142,22 +142,22 @@ int64_t lvba_comm_bytes_sent(void) {
   c.bytes_sent = 0;
   return b;
 }
-int lvba_lidar_owned_rows(lvba_lidar_problem* p, int32_t* row_begin, int32_t* row_end, int32_t* sharded) {
+int lvba_lidar_owned_rows(lvba_lidar_problem* p, int32_t* row_begin, int32_t* row_end, int32_t* sharded) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null problem");
   const bool d = p->solver.dist();
   if (row_begin) *row_begin = d ? p->solver.dist_begin() : 0;
   if (row_end) *row_end = d ? p->solver.dist_end() : p->W;
   if (sharded) *sharded = d ? 1 : 0;
   return LVBA_OK;
-}
-int lvba_visual_owned_rows(lvba_visual_problem* p, int32_t* row_begin, int32_t* row_end, int32_t* sharded) {
+} LVBA_ABI_END("lvba_lidar_owned_rows")
+int lvba_visual_owned_rows(lvba_visual_problem* p, int32_t* row_begin, int32_t* row_end, int32_t* sharded) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null problem");
   const bool d = p->n_rows > 0 && p->solver.dist();
   if (row_begin) *row_begin = d ? p->solver.dist_begin() : 0;
   if (row_end) *row_end = d ? p->solver.dist_end() : p->n_rows;
   if (sharded) *sharded = d ? 1 : 0;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_visual_owned_rows")
 
 int32_t lvba_shard_owner(int32_t min_pose, int32_t n_rows, int32_t n_ranks) { return lvba::shard_owner(min_pose, n_rows, n_ranks); }
 

@@ -48,6 +48,13 @@ inline int fail(int code, const char* fmt, ...) {
       return ::lvba::fail(LVBA_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,  \
                           cudaGetErrorString(err__));                                          \
   } while (0)
+// Every extern "C" entry point is a function-try-block: no C++ exception (std::bad_alloc / std::length_error from the host
+// containers of the set-up passes) crosses the C ABI — the caller gets a status code and lvba_last_error().
+#define LVBA_ABI_BEGIN try
+#define LVBA_ABI_END(name)                                                                                          \
+  catch (const std::bad_alloc&) { return ::lvba::fail(LVBA_ERR_NOMEM, name ": host allocation failed"); }            \
+  catch (const std::exception& e) { return ::lvba::fail(LVBA_ERR_NOMEM, name ": exception: %s", e.what()); }         \
+  catch (...) { return ::lvba::fail(LVBA_ERR_INVALID_ARG, name ": unexpected exception"); }
 #define LVBA_TRY(call)             \
   do {                             \
     int rc__ = (call);             \

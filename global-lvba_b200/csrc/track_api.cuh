@@ -73,9 +73,9 @@ int lvba_tracks_triangulate(int64_t n_tracks, const int64_t* obs_ptr, const int3
 
 int lvba_tracks_mean_reproj(int64_t n_tracks, const int64_t* obs_ptr, const int32_t* obs_cam, const float* obs_uv, int32_t n_cams,
                             const double* cams, const double intr[8], int32_t device, const double* Xw, int32_t min_count,
-                            double* mean_reproj, int32_t* count, uint8_t* ok) {
+                            double* mean_reproj, int32_t* count, uint8_t* ok) LVBA_ABI_BEGIN {
   if (min_count < 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "min_count < 0");
   return lvba::tracks_run<false>(n_tracks, obs_ptr, obs_cam, obs_uv, n_cams, cams, intr, device, Xw, min_count, nullptr, mean_reproj, count, ok);
-}
+} LVBA_ABI_END("lvba_tracks_mean_reproj")
 
 }  // extern "C"

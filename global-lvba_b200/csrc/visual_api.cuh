@@ -539,14 +539,14 @@ int lvba_visual_create(int32_t M, int64_t T, const double* q, const double* t, c
   catch (...) { return lvba::fail(LVBA_ERR_INVALID_ARG, "unexpected exception in lvba_visual_create"); }
 }
 
-int lvba_visual_destroy(lvba_visual_problem* p) {
+int lvba_visual_destroy(lvba_visual_problem* p) LVBA_ABI_BEGIN {
   if (!p) return LVBA_OK;
   cudaSetDevice(p->device);
   delete p;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_visual_destroy")
 
-int lvba_visual_set_state(lvba_visual_problem* p, const double* q, const double* t, const double* X) {
+int lvba_visual_set_state(lvba_visual_problem* p, const double* q, const double* t, const double* X) LVBA_ABI_BEGIN {
   if (!p || !q || !t || (p->T > 0 && !X)) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   LVBA_TRY(p->q.upload(q, (size_t)p->M * 4, p->stream, &p->h2d)); LVBA_TRY(p->qc.upload(q, (size_t)p->M * 4, p->stream));
@@ -554,9 +554,9 @@ int lvba_visual_set_state(lvba_visual_problem* p, const double* q, const double*
   LVBA_TRY(p->X.upload(X, (size_t)p->T * 3, p->stream, &p->h2d)); LVBA_TRY(p->Xc.upload(X, (size_t)p->T * 3, p->stream));
   LVBA_CUDA(cudaStreamSynchronize(p->stream));
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_visual_set_state")
 
-int lvba_visual_get_state(lvba_visual_problem* p, double* q, double* t, double* X) {
+int lvba_visual_get_state(lvba_visual_problem* p, double* q, double* t, double* X) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   if (q) LVBA_CUDA(cudaMemcpyAsync(q, p->q.p, (size_t)p->M * 4 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
@@ -580,9 +580,9 @@ int lvba_visual_get_state(lvba_visual_problem* p, double* q, double* t, double* 
   LVBA_CUDA(cudaStreamSynchronize(p->stream));
   p->d2h += (int64_t)p->M * 56 + p->T * 24;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_visual_get_state")
 
-int lvba_visual_cost(lvba_visual_problem* p, double* cost) {
+int lvba_visual_cost(lvba_visual_problem* p, double* cost) LVBA_ABI_BEGIN {
   if (!p || !cost) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   cudaStream_t s = p->stream;
@@ -594,10 +594,10 @@ int lvba_visual_cost(lvba_visual_problem* p, double* cost) {
   LVBA_CUDA(cudaStreamSynchronize(s));
   *cost = p->h_scal[0];
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_visual_cost")
 
 int lvba_visual_step(lvba_visual_problem* p, double radius, int32_t jacobi_scaling, int32_t recompute_scale,
-                     double* cam_step, double* pt_step, double* model_cost_change, double* cost) {
+                     double* cam_step, double* pt_step, double* model_cost_change, double* cost) LVBA_ABI_BEGIN {
   if (!p || !(radius > 0)) return lvba::fail(LVBA_ERR_INVALID_ARG, "bad argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   if (recompute_scale || !p->have_scale) LVBA_TRY(lvba::visual_compute_scale(p, jacobi_scaling));
@@ -610,9 +610,9 @@ int lvba_visual_step(lvba_visual_problem* p, double radius, int32_t jacobi_scali
   if (model_cost_change) *model_cost_change = p->h_scal[2];
   if (cost) *cost = p->h_scal[0];
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_visual_step")
 
-int lvba_visual_structure(lvba_visual_problem* p, int32_t* n_active, int32_t* cam_of_row, int64_t* nblocks, int32_t* brow, int32_t* bcol) {
+int lvba_visual_structure(lvba_visual_problem* p, int32_t* n_active, int32_t* cam_of_row, int64_t* nblocks, int32_t* brow, int32_t* bcol) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   if (n_active) *n_active = p->n_rows;
   if (cam_of_row) for (int r = 0; r < p->n_rows; ++r) cam_of_row[r] = p->cam_of_row[r];
@@ -624,26 +624,26 @@ int lvba_visual_structure(lvba_visual_problem* p, int32_t* n_active, int32_t* ca
         brow[b] = r; bcol[b] = c;
       }
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_visual_structure")
 
-int lvba_visual_get_system(lvba_visual_problem* p, double* rhs, double* blocks) {
+int lvba_visual_get_system(lvba_visual_problem* p, double* rhs, double* blocks) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   if (rhs && p->n_rows > 0) LVBA_CUDA(cudaMemcpyAsync(rhs, p->rhs.p, (size_t)p->n_rows * 6 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
   if (blocks && p->env.nblocks > 0) LVBA_CUDA(cudaMemcpyAsync(blocks, p->S.p, (size_t)p->env.nblocks * 36 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
   LVBA_CUDA(cudaStreamSynchronize(p->stream));
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_visual_get_system")
 
-int lvba_visual_reset_lm(lvba_visual_problem* p, const lvba_visual_opts* opts) {
+int lvba_visual_reset_lm(lvba_visual_problem* p, const lvba_visual_opts* opts) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   if (opts) p->opts = *opts; else lvba_visual_default_opts(&p->opts);
   p->radius = p->opts.initial_radius; p->nu = 2.0; p->have_scale = false; p->have_first = false; p->converged = false;
   p->iters = p->accepted = p->builds = p->invalid = 0; p->termination = LVBA_TERM_MAX_ITER;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_visual_reset_lm")
 
-int lvba_visual_reset_state(lvba_visual_problem* p) {
+int lvba_visual_reset_state(lvba_visual_problem* p) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   cudaStream_t s = p->stream;
@@ -652,26 +652,26 @@ int lvba_visual_reset_state(lvba_visual_problem* p) {
   LVBA_CUDA(cudaMemcpyAsync(p->t.p, p->t0.p, nt, cudaMemcpyDeviceToDevice, s)); LVBA_CUDA(cudaMemcpyAsync(p->tc.p, p->t0.p, nt, cudaMemcpyDeviceToDevice, s));
   if (nx) { LVBA_CUDA(cudaMemcpyAsync(p->X.p, p->X0.p, nx, cudaMemcpyDeviceToDevice, s)); LVBA_CUDA(cudaMemcpyAsync(p->Xc.p, p->X0.p, nx, cudaMemcpyDeviceToDevice, s)); }
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_visual_reset_state")
 
-int lvba_visual_iterate(lvba_visual_problem* p, int32_t n_iter, lvba_summary* summary) {
+int lvba_visual_iterate(lvba_visual_problem* p, int32_t n_iter, lvba_summary* summary) LVBA_ABI_BEGIN {
   if (!p || n_iter < 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "bad argument");
   LVBA_CUDA(cudaSetDevice(p->device));
   return lvba::visual_iterate_impl(p, n_iter, summary);
-}
+} LVBA_ABI_END("lvba_visual_iterate")
 
-int lvba_visual_counts(lvba_visual_problem* p, int64_t* nnz_valid, int64_t* n_valid_tracks, int64_t* n_blocks_env, int64_t* n_pairs) {
+int lvba_visual_counts(lvba_visual_problem* p, int64_t* nnz_valid, int64_t* n_valid_tracks, int64_t* n_blocks_env, int64_t* n_pairs) LVBA_ABI_BEGIN {
   if (!p) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   if (nnz_valid) *nnz_valid = p->nnz;
   if (n_valid_tracks) *n_valid_tracks = p->Tv;
   if (n_blocks_env) *n_blocks_env = p->env.nblocks;
   if (n_pairs) *n_pairs = p->n_pairs;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_visual_counts")
 
 int lvba_visual_lm(int32_t M, int64_t T, double* q, double* t, double* X, const double* plane_nd, const int64_t* obs_ptr,
                    const int32_t* obs_cam, const float* obs_uv, const double intr[8], double sigma_px, double sigma_plane,
-                   int32_t fixed_cam, const lvba_visual_opts* opts, lvba_summary* summary) {
+                   int32_t fixed_cam, const lvba_visual_opts* opts, lvba_summary* summary) LVBA_ABI_BEGIN {
   const double t0 = lvba::wall_ms();
   lvba_visual_opts o;
   if (opts) o = *opts; else lvba_visual_default_opts(&o);
@@ -690,6 +690,6 @@ int lvba_visual_lm(int32_t M, int64_t T, double* q, double* t, double* X, const 
   }
   lvba_visual_destroy(p);
   return rc;
-}
+} LVBA_ABI_END("lvba_visual_lm")
 
 }  // extern "C"

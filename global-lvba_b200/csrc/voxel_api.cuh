@@ -221,15 +221,15 @@ int lvba_voxel_map_create(int32_t W, const int64_t* scan_ptr, const float* xyz, 
 // One independent map per window of consecutive scans, built together (runWindowBA, src/lvba_system.cpp:232-258).
 int lvba_voxel_map_create_windows(int32_t n_windows, const int32_t* win_ptr, const int64_t* scan_ptr, const float* xyz,
                                   int32_t xyz_stride_floats, const double* poses, const lvba_voxel_opts* opts, lvba_voxel_map** out,
-                                  lvba_voxel_summary* summary) {
+                                  lvba_voxel_summary* summary) LVBA_ABI_BEGIN {
   if (n_windows <= 0 || !win_ptr) return lvba::fail(LVBA_ERR_INVALID_ARG, "n_windows=%d must be positive and win_ptr non-null", n_windows);
   if (win_ptr[0] != 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "win_ptr[0] must be 0");
   for (int w = 0; w < n_windows; ++w)
     if (win_ptr[w + 1] < win_ptr[w]) return lvba::fail(LVBA_ERR_INVALID_ARG, "win_ptr must be non-decreasing");
   return lvba::voxel_map_create_impl(win_ptr[n_windows], scan_ptr, xyz, xyz_stride_floats, poses, opts, out, summary, n_windows, win_ptr);
-}
+} LVBA_ABI_END("lvba_voxel_map_create_windows")
 
-int lvba_voxel_map_windows(lvba_voxel_map* m, int32_t* n_windows, int32_t* vox_window) {
+int lvba_voxel_map_windows(lvba_voxel_map* m, int32_t* n_windows, int32_t* vox_window) LVBA_ABI_BEGIN {
   if (!m) return lvba::fail(LVBA_ERR_INVALID_ARG, "null map");
   if (n_windows) *n_windows = m->map.n_windows;
   if (vox_window && m->map.V > 0) {
@@ -238,16 +238,16 @@ int lvba_voxel_map_windows(lvba_voxel_map* m, int32_t* n_windows, int32_t* vox_w
     LVBA_CUDA(cudaStreamSynchronize(m->map.ex.stream));
   }
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_voxel_map_windows")
 
-int lvba_voxel_map_summary(const lvba_voxel_map* m, lvba_voxel_summary* summary) {
+int lvba_voxel_map_summary(const lvba_voxel_map* m, lvba_voxel_summary* summary) LVBA_ABI_BEGIN {
   if (!m || !summary) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   *summary = m->sum;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_voxel_map_summary")
 
 int lvba_voxel_map_export(lvba_voxel_map* m, int64_t* vox_ptr, int32_t* pose_idx, double* clusters, int64_t* root_key,
-                          int8_t* path, double* centre, double* normal, double* eigenvalues) {
+                          int8_t* path, double* centre, double* normal, double* eigenvalues) LVBA_ABI_BEGIN {
   if (!m) return lvba::fail(LVBA_ERR_INVALID_ARG, "null map");
   LVBA_CUDA(cudaSetDevice(m->device));
   auto& v = m->map;
@@ -263,9 +263,9 @@ int lvba_voxel_map_export(lvba_voxel_map* m, int64_t* vox_ptr, int32_t* pose_idx
   if (eigenvalues && V) LVBA_CUDA(cudaMemcpyAsync(eigenvalues, v.vox_eig.p, V * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
   LVBA_CUDA(cudaStreamSynchronize(s));
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_voxel_map_export")
 
-int lvba_voxel_map_lookup(lvba_voxel_map* m, int64_t n, const double* X, double* plane_nd) {
+int lvba_voxel_map_lookup(lvba_voxel_map* m, int64_t n, const double* X, double* plane_nd) LVBA_ABI_BEGIN {
   if (!m || n < 0 || (n > 0 && (!X || !plane_nd))) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument or negative count");
   if (n == 0) return LVBA_OK;
   LVBA_CUDA(cudaSetDevice(m->device));
@@ -285,7 +285,7 @@ int lvba_voxel_map_lookup(lvba_voxel_map* m, int64_t n, const double* X, double*
   lap("download");
   m->sum.kernel_launches = v.ex.launches;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_voxel_map_lookup")
 
 // tras_opt straight into path A: the map's plane voxels become a device-resident LiDAR problem.  Only the CSR index
 // arrays (12 B per cluster) visit the host, for the symbolic analysis; the 80-byte cluster records stay in HBM.
@@ -310,7 +310,7 @@ int lvba_voxel_map_lidar_create(lvba_voxel_map* m, const double* poses, lvba_lid
 // cut_voxel + recut (the map) -> tras_opt + BALM2::damping_iter (this call).  min_voxels_per_pose: the caller-side skip of
 // src/lvba_system.cpp:262-266 (`plvec_voxels.size() < 3 * x_win.size()`): LVBA_OK, LVBA_TERM_SKIPPED, poses untouched.
 int lvba_voxel_map_lidar_lm(lvba_voxel_map* m, double* poses, int32_t min_voxels_per_pose, const lvba_lidar_opts* opts,
-                            lvba_summary* summary) {
+                            lvba_summary* summary) LVBA_ABI_BEGIN {
   if (!m || !poses) return lvba::fail(LVBA_ERR_INVALID_ARG, "null argument");
   if (min_voxels_per_pose < 0) return lvba::fail(LVBA_ERR_INVALID_ARG, "min_voxels_per_pose must be >= 0");
   const double t0 = lvba::wall_ms();
@@ -337,7 +337,7 @@ int lvba_voxel_map_lidar_lm(lvba_voxel_map* m, double* poses, int32_t min_voxels
   }
   lvba_lidar_destroy(p);
   return rc;
-}
+} LVBA_ABI_END("lvba_voxel_map_lidar_lm")
 
 // The whole window stage of runWindowBA (src/lvba_system.cpp:232-266) from a windowed map: tras_opt + damping_iter of every
 // window in one batched solve (lvba_lidar_lm_batch), the clusters never leaving the device.
@@ -379,11 +379,11 @@ int lvba_voxel_map_lidar_lm_batch(lvba_voxel_map* m, double* poses, int32_t min_
   return rc;
 }
 
-int lvba_voxel_map_destroy(lvba_voxel_map* m) {
+int lvba_voxel_map_destroy(lvba_voxel_map* m) LVBA_ABI_BEGIN {
   if (!m) return LVBA_OK;
   cudaSetDevice(m->device);
   delete m;
   return LVBA_OK;
-}
+} LVBA_ABI_END("lvba_voxel_map_destroy")
 
 }  // extern "C"
