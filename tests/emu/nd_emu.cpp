@@ -306,3 +306,76 @@ extern "C" int nd_emu_solve(int n, const int* first, const double* H, const doub
                             int p_want, int* info) {
   return nd_emu_solve_ranks(n, first, H, dadd, rhs, x, p_want, 1, info);
 }
+
+// ------------------------------------------------------------------------------------------------
+// One rank at a time, for the world-size-2 gloo test (tests/test_rank_flow_gloo.py): the collectives between the two halves
+// are REAL torch.distributed calls between processes, not the in-process copies of nd_emu_solve_ranks.
+//   nd_emu_plan_rows  -> the block rows each rank owns (what the library reports through lvba_lidar_owned_rows)
+//   nd_emu_rank_up    -> this rank eliminates its own subtree from ITS rows of H (foreign rows are poisoned) and packs its slot;
+//                        returns the exchange region (n_ranks slots; the caller all-gathers slot `rank` into everybody's region)
+//   nd_emu_rank_down  -> top of the tree, downward sweep, foreign rows of x zeroed (the caller all-reduces x)
+namespace {
+struct RankRun {
+  nd::Plan P;
+  RankState S;
+  std::vector<int> first, last;
+  int n = 0, rank = 0, n_ranks = 1;
+};
+RankRun* g_run = nullptr;
+
+int plan_for(int n, const int* first, int p_want, int n_ranks, std::vector<long long>& row_start, std::vector<int>& last, nd::Plan& P) {
+  row_start.assign((size_t)n + 1, 0);
+  for (int r = 0; r < n; ++r) row_start[r + 1] = row_start[r] + (r - first[r] + 1);
+  last.assign((size_t)n, 0);
+  int max_col = 0, i = 0;
+  for (int k = 0; k < n; ++k) {
+    if (i < k) i = k;
+    while (i + 1 < n && first[i + 1] <= k) ++i;
+    last[k] = i;
+    max_col = std::max(max_col, i - k);
+  }
+  return nd::choose_chunks(n, first, last.data(), row_start.data(), max_col, p_want, P, n_ranks);
+}
+}  // namespace
+
+extern "C" int nd_emu_plan_rows(int n, const int* first, int p_want, int n_ranks, int* row_begin, int* row_end) {
+  nd::Plan P;
+  std::vector<long long> rs;
+  std::vector<int> last;
+  const int p = plan_for(n, first, p_want, n_ranks, rs, last, P);
+  if (p == 0) return 0;
+  for (int r = 0; r < n_ranks; ++r) { row_begin[r] = P.rank_row_begin[r]; row_end[r] = P.rank_row_end[r]; }
+  return p;
+}
+
+extern "C" int nd_emu_rank_up(int n, const int* first, const double* H, const double* dadd, const double* rhs, int p_want, int n_ranks,
+                              int rank, double** region, long long* slot_doubles) {
+  delete g_run;
+  g_run = new RankRun();
+  RankRun& G = *g_run;
+  G.n = n; G.rank = rank; G.n_ranks = n_ranks;
+  G.first.assign(first, first + n);
+  const int p = plan_for(n, G.first.data(), p_want, n_ranks, G.S.row_start, G.last, G.P);
+  if (p == 0) return 0;
+  const long long nblocks = G.S.row_start[n];
+  setup_rank(G.S, G.P, n, G.first.data(), H, dadd, rhs, nblocks, rank);
+  NdHostExec ex;
+  nd::run_up_local(ex, G.P, G.S.t, G.S.lv.data(), (int)G.S.lv.size(), nblocks, nd::leaf_e_stride(G.P), nd::leaf_final_stride(G.P), &G.S.reg);
+  *region = G.S.t.U + G.P.region0;
+  *slot_doubles = G.P.slot;
+  return p;
+}
+
+extern "C" int nd_emu_rank_down(double* x) {
+  if (!g_run) return -1;
+  RankRun& G = *g_run;
+  NdHostExec ex;
+  nd::run_top_down(ex, G.P, G.S.t, G.S.lv.data(), (int)G.S.lv.size(), G.n_ranks > 1 ? &G.S.reg : nullptr);
+  ex.pass((long long)6 * G.n, nd::ZeroForeignF{G.S.t.x, G.P.rank_row_begin[G.rank], G.P.rank_row_end[G.rank]});
+  int bad = 0;
+  for (int st : G.S.status) bad |= st;
+  std::memcpy(x, G.S.t.x, (size_t)6 * G.n * sizeof(double));
+  delete g_run;
+  g_run = nullptr;
+  return bad;
+}
