@@ -2,7 +2,8 @@
 tools/mgpu_check.py under torchrun — must reproduce the oracle: the block rows of H each rank owns (1e-7), the damped step
 (1e-6), the LM traces of both paths (final costs 1e-6, same iteration counts) on a 500-pose problem (BASELINE configs[1]).
 The data flow itself (owned rows only, one all-gather, replicated top tree) is checked without GPUs in
-tests/test_nd_solver_emu.py::test_rank_sharded_solve_matches_dense."""
+tests/test_nd_solver_emu.py::test_rank_sharded_solve_matches_dense and, between two processes over gloo, in
+tests/test_rank_flow_gloo.py."""
 import os
 import subprocess
 import sys
