@@ -223,3 +223,53 @@ def test_null_handles_and_pointers_are_refused_not_dereferenced(pkg):
         assert call() == -1, k                                       # LVBA_ERR_INVALID_ARG
     for destroy in (lib.lvba_voxel_map_destroy, lib.lvba_depth_grid_destroy, lib.lvba_anchor_clouds_destroy):
         assert destroy(null) == 0                                    # destroying nothing is fine
+
+
+def test_track_fusion_argument_checks_need_no_gpu(pkg):
+    """lvba_tracks_fuse_create (boundary B7): every malformed input is refused before a device is looked for."""
+    cams = np.tile(np.concatenate([np.eye(3).ravel(), np.zeros(3)]), (2, 1)); intr = np.array([100.0, 100, 50, 50, 0, 0, 0, 0])
+    kp_ptr = np.array([0, 2, 4], np.int64); uv = np.zeros((4, 2), np.float32); m = np.array([[0, 0, 1, 0], [0, 1, 1, 1]], np.int32)
+    X = np.zeros((4, 3)); valid = np.ones(4, np.uint8)
+    bad_cams = cams.copy(); bad_cams[1, 10] = np.inf
+    bad_intr = intr.copy(); bad_intr[0] = np.nan
+    bad_X = X.copy(); bad_X[2, 1] = np.nan
+    cases = [dict(kp_ptr=np.array([1, 2, 4], np.int64)), dict(kp_ptr=np.array([0, 3, 2], np.int64)), dict(cams=bad_cams), dict(intr=bad_intr),
+             dict(kp_Xw=bad_X), dict(obser_thr=0), dict(reproj_thr=-1.0), dict(depth_gate=float("nan")), dict(min_view_angle_deg=float("inf"))]
+    for kw in cases:
+        a = dict(kp_ptr=kp_ptr, kp_uv=uv, matches=m, cams=cams, intr=intr, kp_Xw=X, kp_valid=valid)
+        opt = {k: kw.pop(k) for k in list(kw) if k in ("obser_thr", "reproj_thr", "depth_gate", "min_view_angle_deg")}
+        a.update(kw)
+        with pytest.raises(pkg.LvbaError) as e:
+            pkg.tracks_fuse(a["kp_ptr"], a["kp_uv"], a["matches"], a["cams"], a["intr"], a["kp_Xw"], a["kp_valid"], **opt)
+        assert e.value.status == -1, (kw, opt)
+    # a NaN depth candidate that is flagged invalid is not an error; without a device the call then stops at the device check
+    ok_X = bad_X.copy(); v2 = valid.copy(); v2[2] = 0
+    if pkg.device_count() == 0:
+        with pytest.raises(pkg.LvbaError) as e:
+            pkg.tracks_fuse(kp_ptr, uv, m, cams, intr, ok_X, v2)
+        assert e.value.status == -2
+
+
+def test_solver_entry_argument_checks_need_no_gpu(pkg):
+    """lvba_env_solve: the envelope description is validated on the host (first[r] in [0, r], non-decreasing, known path)."""
+    n = 4
+    blocks = np.zeros((10, 36)); dadd = np.ones(6 * n); rhs = np.ones(6 * n)
+    for first, path in (([0, 0, 3, 2], pkg.SOLVE_AUTO), ([0, 2, 1, 1], pkg.SOLVE_AUTO), ([0, -1, 0, 0], pkg.SOLVE_AUTO), ([0, 0, 0, 0], 99), ([0, 0, 0, 0], -3)):
+        with pytest.raises(pkg.LvbaError) as e:
+            pkg.env_solve(first, blocks, dadd, rhs, path=path)
+        assert e.value.status == -1, (first, path)
+    if pkg.device_count() == 0:
+        with pytest.raises(pkg.LvbaError) as e:
+            pkg.env_solve([0, 0, 0, 0], blocks, dadd, rhs)
+        assert e.value.status == -2
+
+
+def test_communicator_argument_checks_need_no_gpu(pkg):
+    lib = pkg.load_library()
+    import ctypes as C
+    assert lib.lvba_comm_init(C.c_int32(0), C.c_int32(0), None, C.c_int32(0)) == -1          # n_ranks < 1
+    assert lib.lvba_comm_init(C.c_int32(2), C.c_int32(2), None, C.c_int32(0)) == -1          # rank >= n_ranks
+    assert lib.lvba_comm_unique_id(None) == -1
+    n, r = C.c_int32(-5), C.c_int32(-5)
+    assert lib.lvba_comm_info(C.byref(n), C.byref(r)) == 0 and (n.value, r.value) == (1, 0)   # no communicator: one rank, rank 0
+    assert lib.lvba_comm_destroy() == 0                                                       # idempotent
