@@ -229,19 +229,14 @@ struct VoxelCountF {         // pass 4c, over [0, V] (terminator 0)
     count[v] = (int64_t)(L.node_seg[m + 1] - L.node_seg[m]);
   }
 };
-struct VoxelFillF {          // pass 4d
-  const uint32_t* ref; const uint64_t* ext_key; LayerView lay[kMaxLayers]; KeyPacking pk; const int64_t* vox_ptr;
-  int32_t* pose_idx; double* clusters; int64_t* root_key; int8_t* path; double* centre; double* direct; double* eig; int32_t* window;
+struct VoxelFillF {          // pass 4d: per plane voxel — key, path, centre, normal, eigenvalues
+  const uint32_t* ref; const uint64_t* ext_key; LayerView lay[kMaxLayers]; KeyPacking pk;
+  int64_t* root_key; int8_t* path; double* centre; double* direct; double* eig; int32_t* window;
   LVBA_HD void operator()(int64_t v) const {
     window[v] = (int32_t)pk.window_of(ext_key[v] >> 6);
     const int layer = (int)(ref[v] >> 30);
     const LayerView& L = lay[layer];
     const uint32_t m = ref[v] & 0x3fffffffu;
-    int64_t q = vox_ptr[v];
-    for (uint32_t s = L.node_seg[m]; s < L.node_seg[m + 1]; ++s, ++q) {
-      pose_idx[q] = L.seg_pose[s];
-      for (int k = 0; k < 10; ++k) clusters[10 * q + k] = L.seg_cluster[10 * (int64_t)s + k];
-    }
     int64_t k3[3];
     pk.unpack(ext_key[v] >> 6, k3);
     for (int k = 0; k < 3; ++k) {
@@ -253,6 +248,25 @@ struct VoxelFillF {          // pass 4d
     path[3 * v] = (int8_t)layer;
     path[3 * v + 1] = layer >= 1 ? (int8_t)((ext_key[v] >> 3) & 7) : (int8_t)-1;
     path[3 * v + 2] = layer >= 2 ? (int8_t)(ext_key[v] & 7) : (int8_t)-1;
+  }
+};
+// pass 4e: one item per (voxel, pose) SLOT of the output CSR — pose index and the 10-double cluster record of the slot.
+// (One item per voxel copying its whole segment — a street voxel is seen from ~50-80 poses — ran as 27 CTAs waiting on one
+// dependent load after the other: 445 us of the 1.27 ms map build at 5 M points, ncu long_scoreboard 98 %,
+// profiles/r02_setup_ncu_summary.md.)  The voxel of slot q is the last v with vox_ptr[v] <= q.
+struct SlotFillF {
+  const uint32_t* ref; LayerView lay[kMaxLayers]; const int64_t* vox_ptr; int64_t V; int32_t* pose_idx; double* clusters;
+  LVBA_HD void operator()(int64_t q) const {
+    int64_t lo = 0, hi = V;                                 // vox_ptr[lo] <= q < vox_ptr[hi]
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (vox_ptr[mid] <= q) lo = mid; else hi = mid;
+    }
+    const LayerView& L = lay[ref[lo] >> 30];
+    const uint32_t m = ref[lo] & 0x3fffffffu;
+    const int64_t s = (int64_t)L.node_seg[m] + (q - vox_ptr[lo]);
+    pose_idx[q] = L.seg_pose[s];
+    for (int k = 0; k < 10; ++k) clusters[10 * q + k] = L.seg_cluster[10 * s + k];
   }
 };
 
@@ -477,9 +491,11 @@ struct VoxelMap {
     LVBA_VOX_TRY(vox_root.alloc((size_t)V * 3)); LVBA_VOX_TRY(vox_path.alloc((size_t)V * 3));
     LVBA_VOX_TRY(vox_centre.alloc((size_t)V * 3)); LVBA_VOX_TRY(vox_direct.alloc((size_t)V * 3)); LVBA_VOX_TRY(vox_eig.alloc((size_t)V * 3));
     LVBA_VOX_TRY(vox_window.alloc((size_t)V));
-    VoxelFillF ff{ref.p, ext.p, {}, pk, vox_ptr.p, vox_pose.p, vox_cluster.p, vox_root.p, vox_path.p, vox_centre.p, vox_direct.p, vox_eig.p, vox_window.p};
-    for (int L = 0; L < kMaxLayers; ++L) ff.lay[L] = cf.lay[L];
+    VoxelFillF ff{ref.p, ext.p, {}, pk, vox_root.p, vox_path.p, vox_centre.p, vox_direct.p, vox_eig.p, vox_window.p};
+    SlotFillF sf{ref.p, {}, vox_ptr.p, V, vox_pose.p, vox_cluster.p};
+    for (int L = 0; L < kMaxLayers; ++L) { ff.lay[L] = cf.lay[L]; sf.lay[L] = cf.lay[L]; }
     LVBA_VOX_TRY(ex.for_each(V, ff));
+    LVBA_VOX_TRY(ex.for_each(nnz, sf));
     return ex.sync();
   }
 
