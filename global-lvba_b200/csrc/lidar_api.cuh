@@ -302,7 +302,7 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   std::vector<int64_t> mine;
   if (!cm.active()) {                                          // one rank: every voxel, in the caller's order
     mine.resize((size_t)V);
-    parallel_chunks(V, 1 << 15, [&](int64_t a0, int64_t a1, int) { for (int64_t a = a0; a < a1; ++a) mine[(size_t)a] = a; });
+    for (int64_t a = 0; a < V; ++a) mine[(size_t)a] = a;        // ~0.1 ms at 200 k voxels: cheaper than waking the helpers
   } else {
     mine.reserve((size_t)V);
     for (int64_t a = 0; a < V; ++a)
@@ -323,12 +323,8 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   std::vector<int64_t> bigv;
   {
     std::vector<int64_t> small;
-    bool any_big[kMaxSetupThreads] = {};
-    parallel_chunks((int64_t)mine.size(), 1 << 15, [&](int64_t i0, int64_t i1, int w) {
-      for (int64_t i = i0; i < i1; ++i) if (vox_ptr[mine[(size_t)i] + 1] - vox_ptr[mine[(size_t)i]] > kSlots) { any_big[w] = true; break; }
-    });
     bool has_big = false;
-    for (bool b : any_big) has_big = has_big || b;
+    for (size_t i = 0; i < mine.size() && !has_big; ++i) has_big = vox_ptr[mine[i] + 1] - vox_ptr[mine[i]] > kSlots;
     if (has_big) for (int64_t a : mine) if (vox_ptr[a + 1] - vox_ptr[a] > kSlots) bigv.push_back(a);
     if (!bigv.empty()) {
       for (int64_t a : mine) if (vox_ptr[a + 1] - vox_ptr[a] <= kSlots) small.push_back(a);

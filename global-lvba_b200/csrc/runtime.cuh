@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/lvba_b200.h"
+#include "setup_pool.h"
 #include "envelope.cuh"
 #include "envelope_wide.h"
 #include "factor_la.cuh"
@@ -75,19 +76,6 @@ inline int select_device(int device) {
 }
 
 // ---------------------------------------------------------------- host parallel loop (symbolic set-up)
-// fn(begin, end, worker) over [0, n) split into contiguous chunks on up to 8 threads.  The set-up of a one-shot call
-// (validation, gathers, pair tables) is a few milliseconds of single-threaded loops next to ~40 ms of device work.
-template <class Fn>
-inline void parallel_chunks(int64_t n, int64_t min_chunk, Fn fn) {
-  unsigned hw = std::thread::hardware_concurrency();
-  int nt = (int)std::min<int64_t>(std::min<unsigned>(hw ? hw : 1u, 8u), std::max<int64_t>(1, n / std::max<int64_t>(min_chunk, 1)));
-  if (nt <= 1) { fn((int64_t)0, n, 0); return; }
-  std::vector<std::thread> th;
-  th.reserve((size_t)nt - 1);
-  for (int w = 1; w < nt; ++w) th.emplace_back([=] { fn(n * w / nt, n * (w + 1) / nt, w); });
-  fn((int64_t)0, n / nt, 0);
-  for (auto& t : th) t.join();
-}
 constexpr int kMaxSetupThreads = 8;
 
 // ---------------------------------------------------------------- device memory pool
