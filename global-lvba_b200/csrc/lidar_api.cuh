@@ -146,6 +146,7 @@ struct lvba_lidar_problem {
   lvba::DevBuf<int> d_grp_ptr, d_pose_grp, d_grp_batch, d_accept;
   lvba::DevBuf<double> d_u_grp, d_grp_scal;
   double* h_grp_scal = nullptr;        // pinned [4G]: r1 sum, q1, bad flag, r2 sum per window
+  size_t h_grp_scal_bytes = 0;
   // ---- voxels seen from more than kSlots poses: outside the batches, through the passes of lidar_big.h
   long long n_big = 0, n_big_slots = 0, n_big_pairs = 0;
   lvba::DevBuf<int64_t> big_vox_ptr, big_pair_ptr;
@@ -163,9 +164,9 @@ struct lvba_lidar_problem {
     return v_;
   }
   ~lvba_lidar_problem() {
-    if (h_scal) cudaFreeHost(h_scal);
-    if (h_grp_scal) cudaFreeHost(h_grp_scal);
     if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }     // buffers (members, destroyed after this body) must be idle when parked
+    lvba::pinned_pool().give(h_scal, 8 * sizeof(double));                          // after the drain: no read-back may still be writing them
+    lvba::pinned_pool().give(h_grp_scal, h_grp_scal_bytes);
   }
 };
 
@@ -229,7 +230,7 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
   LVBA_CUDA(cudaGetDevice(&P->device));
   LVBA_CUDA(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
   P->timers.stream = P->stream;
-  LVBA_CUDA(cudaMallocHost((void**)&P->h_scal, 8 * sizeof(double)));
+  LVBA_TRY(pinned_pool().take(8 * sizeof(double), (void**)&P->h_scal));
   cudaStream_t s = P->stream;
 
   lap("ctx/stream/pinned");
@@ -367,7 +368,8 @@ inline int lidar_create_impl(int32_t W, int64_t V, const int64_t* vox_ptr, const
     LVBA_TRY(P->d_u_grp.alloc((size_t)n_groups));
     LVBA_TRY(P->d_grp_scal.alloc((size_t)4 * n_groups));
     LVBA_TRY(P->d_grp_scal.zero(s));
-    LVBA_CUDA(cudaMallocHost((void**)&P->h_grp_scal, (size_t)4 * n_groups * sizeof(double)));
+    P->h_grp_scal_bytes = (size_t)4 * n_groups * sizeof(double);
+    LVBA_TRY(pinned_pool().take(P->h_grp_scal_bytes, (void**)&P->h_grp_scal));
     LVBA_CUDA(cudaStreamSynchronize(s));                       // local vectors
   }
   // ---- pair table

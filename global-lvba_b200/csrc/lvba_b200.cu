@@ -15,7 +15,7 @@ extern "C" {
 int lvba_version(void) { return LVBA_B200_VERSION; }
 int lvba_device_count(void) { return lvba::device_count(); }
 const char* lvba_last_error(void) { return lvba::last_error_ref().c_str(); }
-int lvba_release_cached_memory(void) { lvba::device_pool().clear(); return LVBA_OK; }
+int lvba_release_cached_memory(void) { lvba::device_pool().clear(); lvba::pinned_pool().clear(); return LVBA_OK; }
 const char* lvba_status_string(int status) {
   switch (status) {
     case LVBA_OK: return "ok";

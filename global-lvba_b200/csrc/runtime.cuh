@@ -116,6 +116,44 @@ inline DevicePool& device_pool() {
   return *p;
 }
 
+// Pinned host scratch (the few doubles every LM pass reads back): cudaMallocHost / cudaFreeHost page-lock and unlock memory
+// through the driver on every one-shot call; the blocks are parked like the device buffers above.
+struct PinnedPool {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_list;
+  size_t cached_bytes = 0;
+  static constexpr size_t kMaxCached = 64ull << 20;
+  static size_t bucket(size_t bytes) { return (std::max<size_t>(bytes, 1) + 4095) & ~size_t(4095); }
+  int take(size_t bytes, void** out) {
+    const size_t b = bucket(bytes);
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = free_list.find(b);
+      if (it != free_list.end()) { *out = it->second; free_list.erase(it); cached_bytes -= b; return LVBA_OK; }
+    }
+    LVBA_CUDA(cudaMallocHost(out, b));
+    return LVBA_OK;
+  }
+  void give(void* p, size_t bytes) {
+    if (!p) return;
+    const size_t b = bucket(bytes);
+    std::lock_guard<std::mutex> g(mu);
+    if (cached_bytes + b > kMaxCached) { cudaFreeHost(p); return; }
+    free_list.insert({b, p});
+    cached_bytes += b;
+  }
+  void clear() {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& kv : free_list) cudaFreeHost(kv.second);
+    free_list.clear();
+    cached_bytes = 0;
+  }
+};
+inline PinnedPool& pinned_pool() {
+  static PinnedPool* p = new PinnedPool();     // intentionally leaked: no CUDA calls in static destructors
+  return *p;
+}
+
 // ---------------------------------------------------------------- device buffer
 template <typename T>
 struct DevBuf {

@@ -51,8 +51,8 @@ struct lvba_visual_problem {
   lvba::VisualState state() const { return lvba::VisualState{q.p, t.p, X.p}; }
   lvba::VisualState cand() const { return lvba::VisualState{qc.p, tc.p, Xc.p}; }
   ~lvba_visual_problem() {
-    if (h_scal) cudaFreeHost(h_scal);
     if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }     // buffers (members) must be idle when parked
+    lvba::pinned_pool().give(h_scal, 16 * sizeof(double));                         // after the drain
   }
 };
 
@@ -186,7 +186,7 @@ inline int visual_create_impl(int32_t M, int64_t T, const double* q, const doubl
   LVBA_CUDA(cudaGetDevice(&P->device));
   LVBA_CUDA(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
   P->timers.stream = P->stream;
-  LVBA_CUDA(cudaMallocHost((void**)&P->h_scal, 16 * sizeof(double)));
+  LVBA_TRY(pinned_pool().take(16 * sizeof(double), (void**)&P->h_scal));
   cudaStream_t s = P->stream;
 
   // ---- valid landmarks, active cameras (src/lvba_system.cpp:1582-1583, 1598-1603)
