@@ -1,0 +1,14 @@
+// Stand-in for the old (non-templated) Sophus::SE3 include/utils.hpp:480-492 names (NOT Sophus; test infrastructure).
+#pragma once
+#include "../mini_eigen.h"
+namespace Sophus {
+class SE3 {
+  Eigen::Matrix3d R_;
+  Eigen::Vector3d t_;
+ public:
+  SE3() : R_(Eigen::Matrix3d::Identity()) {}
+  SE3(const Eigen::Matrix3d& R, const Eigen::Vector3d& t) : R_(R), t_(t) {}
+  Eigen::Matrix3d rotation_matrix() const { return R_; }
+  const Eigen::Vector3d& translation() const { return t_; }
+};
+}  // namespace Sophus

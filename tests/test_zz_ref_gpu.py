@@ -1,0 +1,106 @@
+"""The CUDA path against what THE REFERENCE'S OWN SOURCE computed (tests/golden/ref_balm.npz; how it was made and what the
+stand-in libraries under it do and do not pin: tests/golden/make_golden_ref.py, tests/test_ref_pin.py, oracle/ref_shim/mini_eigen.h).
+Nothing is regenerated on the GPU box and /root/reference is not read: the committed vectors are the reference here.
+
+Through the C ABI: B1 Hessian build / residual pass / full damping_iter, B3 voxel map + plane lookup + the window solve on the map
+without the clusters leaving HBM, B6 anchor clouds, B2 cost (the two Ceres functors summed over the problem).
+Tolerances as in tests/test_lidar_gpu.py (lambda_0 is a difference of O(1e4) terms): residual sums 1e-8 relative,
+g / H 1e-7 of their largest entry, LM end poses 1e-6, final cost 1e-6 (north star); integer data, keys, point counts and the
+float32 anchor points exact.  Runs in a child process under a timeout like the other test_zz_* files."""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+CODE = """
+import sys
+import numpy as np
+sys.path.insert(0, %r)
+import __graft_entry__ as graft
+pkg = graft.load_package(); pkg.load_library()
+assert pkg.device_count() >= 1
+G = np.load(%r)
+split = lambda flat, ptr: [flat[ptr[i]:ptr[i + 1]] for i in range(len(ptr) - 1)]
+lex = lambda a: a[np.lexsort(a.T[::-1])]
+launches = 0
+
+# ---- B1: acc_evaluate2 / evaluate_only_residual / damping_iter
+for tag in ("L1", "L2", "L3"):
+    vp, pi, cl, ps = G[tag + "_vox_ptr"], G[tag + "_pose_idx"], G[tag + "_clusters"], G[tag + "_poses"]
+    W = len(ps)
+    keep = np.diff(vp) >= 2                                   # push_voxel (bavoxel.hpp:45-54) is the caller's side of B1
+    assert int(keep.sum()) == int(G[tag + "_kept"])
+    if not keep.all():
+        sel = np.concatenate([np.arange(vp[a], vp[a + 1]) for a in np.nonzero(keep)[0]])
+        vp = np.concatenate([[0], np.cumsum(np.diff(vp)[keep])]).astype(np.int64); pi = pi[sel]; cl = cl[sel]
+    P = pkg.LidarProblem(vp, pi, cl, ps)
+    r = P.build()
+    g, br, bc, bl = P.get_system()
+    H = pkg.env_blocks_to_dense(br, bc, bl, W)
+    r_ref, g_ref, H_ref = float(G[tag + "_residual_sum"]), G[tag + "_g"], G[tag + "_H"]
+    assert abs(r - r_ref) <= 1e-8 * abs(r_ref), (tag, r, r_ref)
+    assert np.abs(g - g_ref).max() <= 1e-7 * np.abs(g_ref).max(), tag
+    assert np.abs(H - H_ref).max() <= 1e-7 * np.abs(H_ref).max(), tag
+    if tag != "L3":
+        r_gt = P.residual(G[tag + "_poses_gt"])
+        assert abs(r_gt - float(G[tag + "_residual_gt"])) <= 1e-8 * abs(float(G[tag + "_residual_gt"])), tag
+    P.close()
+    if tag != "L3":
+        poses, s = pkg.lidar_lm(vp, pi, cl, ps)
+        assert np.abs(poses - G[tag + "_lm_poses"]).max() <= 1e-6, (tag, np.abs(poses - G[tag + "_lm_poses"]).max())
+        V = len(vp) - 1
+        assert abs(s["cost_last"] * V - float(G[tag + "_lm_residual_sum"])) <= 1e-6 * float(G[tag + "_lm_residual_sum"]), tag
+        assert abs(s["cost_first"] - float(G[tag + "_residual_avg_threads"])) <= 1e-8 * float(G[tag + "_residual_avg_threads"]), tag
+        launches += s["kernel_launches"]
+
+# ---- B3: cut_voxel -> recut -> tras_opt, findCorrespondPoint, damping_iter on the map
+scans = split(G["M_xyz"], G["M_scan_ptr"])
+m = pkg.VoxelMap(scans, G["M_poses"], float(G["M_voxel_size"]), G["M_eigen_ratio"])
+got = m.export()
+assert np.array_equal(got["vox_ptr"], G["M_vox_ptr"]) and np.array_equal(got["pose_idx"], G["M_pose_idx"])
+assert np.array_equal(got["key"], G["M_key"]) and np.array_equal(got["path"][:, 0], G["M_layer"])
+assert np.array_equal(got["path"][:, 1:].astype(np.int32), G["M_path"])
+assert np.array_equal(got["clusters"][:, 9], G["M_clusters"][:, 9])
+assert np.abs(got["clusters"] - G["M_clusters"]).max() <= 1e-12 * np.abs(G["M_clusters"]).max()
+assert np.abs(got["centre"] - G["M_centre"]).max() <= 1e-9 and np.abs(got["eigenvalues"] - G["M_eigenvalues"]).max() <= 1e-9
+assert np.all(np.abs(np.einsum("ij,ij->i", got["normal"], G["M_direct"])) >= 1 - 1e-6)         # eigenvector sign is the library's
+st, d, c = G["M_lookup_state"], G["M_lookup_direct"], G["M_lookup_centre"]
+nd_ref = np.zeros((len(st), 4))
+for i in np.nonzero(st == 2)[0]:                              # the (n, d) step of recompute_local_planes (lvba_system.cpp:1552-1563)
+    if np.all(np.isfinite(d[i])) and np.linalg.norm(d[i]) >= 1e-6 and np.all(np.isfinite(c[i])):
+        n = d[i] / np.linalg.norm(d[i]); nd_ref[i, :3] = n; nd_ref[i, 3] = -n @ c[i]
+nd = m.lookup(G["M_lookup_X"])
+assert np.array_equal(np.all(nd == 0, axis=1), np.all(nd_ref == 0, axis=1))
+sgn = np.sign(np.einsum("ij,ij->i", nd[:, :3], nd_ref[:, :3])); sgn[sgn == 0] = 1
+assert np.abs(nd * sgn[:, None] - nd_ref).max() <= 1e-6
+poses, s = m.lidar_lm(G["M_poses"])
+assert np.abs(poses - G["M_lm_poses"]).max() <= 1e-6, np.abs(poses - G["M_lm_poses"]).max()
+launches += s["kernel_launches"]
+m.close()
+
+# ---- B6: pl_transform + down_sampling_voxel2 (the reference's order is its unordered_map's: compared as sets)
+cloud = pkg.anchor_clouds(scans, G["A_rel"], np.array([0, len(scans)], np.int32), float(G["A_leaf"]))[0]
+assert np.array_equal(lex(cloud), G["A_cloud_sorted"])
+
+# ---- B2: the cost Ceres evaluates = 1/2 (sum of ReprojErrorWhitenedDistorted^2 + sum of PointPlaneErrorWhitened^2)
+n = G["V_plane_nd"][:, :3]
+tv = np.isfinite(G["V_plane_nd"]).all(1) & (np.abs(n) > 1e-6).any(1)      # has_valid_plane, lvba_system.cpp:1598
+trk = np.repeat(np.arange(len(G["V_obs_ptr"]) - 1), np.diff(G["V_obs_ptr"]))
+cost_ref = 0.5 * (float((G["V_reproj_r"][tv[trk]] ** 2).sum()) + float((G["V_plane_r"][tv] ** 2).sum()))
+P = pkg.VisualProblem(G["V_q"], G["V_t"], G["V_X"], G["V_plane_nd"], G["V_obs_ptr"], G["V_obs_cam"], G["V_obs_uv"], G["V_intr"],
+                      float(G["V_sigma_px"]), float(G["V_sigma_plane"]))
+cost = P.cost()
+P.close()
+assert abs(cost - cost_ref) <= 1e-10 * cost_ref, (cost, cost_ref)
+assert launches > 0
+print('CHILD-OK')
+""" % (str(ROOT), str(ROOT / "tests" / "golden" / "ref_balm.npz"))
+
+
+@pytest.mark.gpu
+def test_device_reproduces_what_the_reference_source_computed():
+    r = subprocess.run([sys.executable, "-c", CODE], capture_output=True, text=True, timeout=300, cwd=str(ROOT))
+    assert r.returncode == 0 and "CHILD-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
