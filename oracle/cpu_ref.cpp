@@ -4,8 +4,11 @@
 // one: own Jacobi eigen-solver, own block LDL^T) and the CPU baseline that bench.py times beside the GPU
 // (`cpu_baseline`, and `--impl reference`).  Nothing under global-lvba_b200/ links or calls it.
 //
-// PARITY UNPINNED: the reference has no tests / golden vectors for this path and cannot be compiled here
-// (needs Eigen, Ceres, PCL, ROS — SURVEY.md §8c), so this is a port, not the reference binary.  It keeps
+// PARITY: path A of this port is held against the reference's own source (tests/test_ref_pin.py: H, g, residual, damping_iter end
+// poses vs tests/golden/ref_balm.npz; tools/ref_scale_check.py at configs B and C -> profiles/r02_ref_pin_scale_B.txt, _C.txt), the two Ceres
+// cost functors likewise through the numpy oracle; the Ceres trust-region loop of path B stays a restatement of the published 2.1.0
+// algorithm (no Ceres here).  The reference as a whole (ROS node, Eigen, Ceres, PCL) cannot be built here, so the
+// timed CPU arm is this port, not the reference binary.  It keeps
 // the reference's arithmetic and threading model and replaces only what cannot exist at the named sizes:
 //   * dense per-voxel vector<PointCluster>(win_size) and dense 6W x 6W Hessians  ->  CSR slots and a
 //     block-envelope (skyline) Hessian (the literal layout needs 41 GB + 22 GB at config C);

@@ -4,12 +4,14 @@ TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, bench.py's cpu_baseline
 leg and __graft_entry__.smoke() may import this.  The shipped solver is the
 CUDA library (global-lvba_b200/csrc) and never calls into this file.
 
-PARITY UNPINNED: the reference ships no tests, fixtures or golden vectors for
-this path and cannot be compiled here (needs Eigen, PCL,
-ROS).  This restatement is pinned instead by finite-difference identities
-(tests/test_oracle_lidar.py): the analytic gradient/Hessian below must equal
-the derivatives of the residual-only function along the reference's own
-retraction R <- R*Exp(dphi), p <- p + dp.
+PARITY: PINNED AGAINST THE REFERENCE'S OWN SOURCE for this path — tests/test_ref_pin.py holds every function below
+against tests/golden/ref_balm.npz, written by include/BALM/tools.hpp + include/BALM/bavoxel.hpp compiled where they lie
+(oracle/ref_driver.cpp -> oracle/_ref/libbalm_ref.so) on stand-ins for Eigen / PCL (oracle/ref_shim/: own Jacobi
+eigen-solver and envelope LDL^T under the reference's lines — NOT Eigen; see ref_shim/mini_eigen.h for what that leaves
+open).  Observed: H / g / sum(lambda_0) 1e-11 relative, damping_iter end poses 2e-11.  The reference ships no tests,
+fixtures or golden vectors of its own.  Also pinned by finite-difference identities
+(tests/test_oracle_lidar.py): the analytic gradient/Hessian below must equal the derivatives of the residual-only
+function along the reference's own retraction R <- R*Exp(dphi), p <- p + dp.
 
 Each function restates, line for line, the cited reference code:
 

@@ -2,9 +2,12 @@
 
 TEST INFRASTRUCTURE, NOT PRODUCT CODE (see oracle/lidar_oracle.py header).
 
-PARITY UNPINNED: the reference has no tests or fixtures for this path and its
-solver is ceres-solver 2.1.0 (README.md:21, CMakeLists.txt:33), which is not
-vendored under /root/reference and not installed here.  What is restated:
+PARITY: the two cost functors ARE pinned against the reference's own source (include/utils.hpp:51-147 compiled where it
+lies, evaluated with T = double and with T = Jet as ceres::AutoDiffCostFunction does: oracle/ref_driver.cpp,
+tests/golden/ref_balm.npz, tests/test_ref_pin.py — residuals 1e-10, Jacobians 1e-12, the z_c <= 1e-8 branch and a
+non-unit quaternion included).  THE SOLVER IS UNPINNED: it is ceres-solver 2.1.0 (README.md:21, CMakeLists.txt:33), a
+third-party dependency that is neither vendored under /root/reference nor installed here; its trust-region algorithm
+is restated below from the published algorithm and no Ceres binary exists here to hold it against.  What is restated:
 
   reproj_residual / jac   ReprojErrorWhitenedDistorted   include/utils.hpp:61-111
   plane_residual / jac    PointPlaneErrorWhitened        include/utils.hpp:133-139

@@ -1,6 +1,6 @@
 """North-star check at the config the metric is quoted on (BASELINE.json configs[2]: 2000 poses / 200k plane voxels / 100k tracks):
-the GPU path against the CPU restatement of the reference (oracle/cpu_ref.cpp — parity unpinned: the reference itself needs
-Eigen / Ceres and cannot be built here).
+the GPU path against the CPU restatement of the reference (oracle/cpu_ref.cpp, itself held against the reference's own
+BALM sources at configs B and C: tools/ref_scale_check.py, profiles/r02_ref_pin_scale_B.txt, _C.txt; the Ceres loop of path B is a restatement).
   * per-pose update of the first LM iteration (BALM2::damping_iter, reference include/BALM/bavoxel.hpp:692-710):
       backward error  |(H + u diag H) dx + g|_inf <= 1e-12 |g|_inf  with the GPU's own H, g  (what the block LDL^T owes), and
       |dx_gpu - dx_cpu|_inf <= 1e-8 |dx_cpu|_inf  (BASELINE north star; H itself agrees to ~1e-9 — lambda_0 is a difference of
