@@ -18,9 +18,45 @@ import numpy as np
 from oracle import track_oracle as trk
 
 
-def fuse(kp_ptr, kp_uv, matches, cams, intr, kp_Xw, kp_valid, obser_thr=3, min_view_angle_deg=8.0, reproj_thr=3.0, depth_gate=0.12):
+_FAST_BKT = [2, 2, 2, 3, 5, 5, 7, 7, 11, 11, 11, 11, 13, 13]
+_PRIMES = [17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97, 103, 109, 113, 127, 137, 139, 149, 157, 167, 179, 193, 199, 211,
+           227, 241, 257, 277, 293, 313, 337, 359, 383, 409, 439, 467, 503, 541, 577, 619, 661, 709, 761, 823, 887, 953, 1031, 1109, 1193, 1289, 1381,
+           1493, 1613, 1741, 1879, 2029, 2179, 2357, 2549, 2753, 2971, 3209, 3469, 3739, 4027, 4349, 4703, 5087, 5503, 5953, 6427, 6949, 7517, 8123]
+
+
+def libstdcxx_order(reserve, keys):
+    """Iteration order of a GNU libstdc++ std::unordered_map<int,int> after reserve(`reserve`) and the insertion of the distinct non-negative
+    `keys` in this order — the order the reference's `for (auto& kv : map)` loops run in when it is built with g++ (the language leaves it
+    open).  Restated from libstdc++'s published hashtable policy: reserve(n) gives the smallest bucket count >= n from the prime table (a
+    fast table below 14), std::hash<int> is the identity, a node whose bucket is empty goes to the FRONT of the one global list, a node
+    whose bucket is occupied goes to the front of that bucket's run.  No rehash happens afterwards: the reference never inserts more keys than
+    it reserved.  Held against the real container on random inputs in tests/test_ref_system_pin.py."""
+    n = int(reserve)
+    if n == 0:
+        nb = 1
+    elif n < len(_FAST_BKT):
+        nb = _FAST_BKT[n]
+    else:
+        nb = next(p for p in _PRIMES if p >= n)
+    assert len(keys) <= max(nb, 1), "more keys than reserved: a rehash would reorder the list"
+    order = []                                   # the global singly linked list, front first
+    for k in keys:
+        b = int(k) % nb
+        pos = next((i for i, x in enumerate(order) if int(x) % nb == b), None)
+        order.insert(0 if pos is None else pos, int(k))
+    return order
+
+
+def fuse(kp_ptr, kp_uv, matches, cams, intr, kp_Xw, kp_valid, obser_thr=3, min_view_angle_deg=8.0, reproj_thr=3.0, depth_gate=0.12, map_order=None):
     """matches: (m, 4) int array (img_a, kp_a, img_b, kp_b) in the reference's visiting order.
-    Returns a list of tracks {seed, obs (k,2), inlier (k,) bool, Xw, mean, source} in the reference's track order."""
+    Returns a list of tracks {seed, obs (k,2), inlier (k,) bool, Xw, mean, source, kept (inlier positions in the order they were kept)} in the
+    reference's track order.
+    map_order(reserve, keys) -> keys in the order the reference's `for (auto& kv : unordered_map)` loops visit them (`keys` = image ids in insertion
+    order, `reserve` = the argument of the map's reserve()).  None = ascending image id, the order this repo's ABI documents; with the C++ library's
+    own answer (oracle/lvba_system_ref.unordered_map_order) this function reproduces the reference's BuildTracksAndFuse3D track for track
+    (tests/test_ref_system_pin.py)."""
+    if map_order is None:
+        map_order = lambda reserve, keys: sorted(keys)  # noqa: E731
     N = len(kp_ptr) - 1
     n_kp = int(kp_ptr[-1])
     img_of = np.repeat(np.arange(N), np.diff(kp_ptr))
@@ -80,7 +116,7 @@ def fuse(kp_ptr, kp_uv, matches, cams, intr, kp_Xw, kp_valid, obser_thr=3, min_v
             first.setdefault(int(img_of[g]), t)
         if len(first) < obser_thr:
             release(); continue
-        imgs = sorted(first)
+        imgs = map_order(len(comp), list(first))                      # unique_id.reserve(component.size()), inserted in member order (:994-999)
         # ---- depth candidate
         depth_ok, Xd, mean_d, kept_d = False, np.zeros(3), np.inf, []
         valid = [t for t, g in enumerate(comp) if kp_valid[g]]
@@ -91,7 +127,8 @@ def fuse(kp_ptr, kp_uv, matches, cams, intr, kp_Xw, kp_valid, obser_thr=3, min_v
                 if np.linalg.norm(np.asarray(kp_Xw[comp[t]], np.float64) - Xa) < depth_gate:
                     best.setdefault(int(img_of[comp[t]]), t)
             if len(best) >= obser_thr:
-                order = [best[i] for i in sorted(best)]
+                n_inl = sum(1 for t in valid if np.linalg.norm(np.asarray(kp_Xw[comp[t]], np.float64) - Xa) < depth_gate)
+                order = [best[i] for i in map_order(n_inl, list(best))]   # best_id.reserve(inliers.size()), inserted in inlier order (:1051-1056)
                 Xd = np.zeros(3)
                 for t in order:
                     Xd = Xd + np.asarray(kp_Xw[comp[t]], np.float64)
@@ -130,7 +167,7 @@ def fuse(kp_ptr, kp_uv, matches, cams, intr, kp_Xw, kp_valid, obser_thr=3, min_v
         tid = len(tracks)
         inl = np.zeros(len(comp), bool); inl[kept] = True
         obs = np.array([[int(img_of[g]), int(g - kp_ptr[img_of[g]])] for g in comp], np.int32)
-        tracks.append(dict(seed=seed, obs=obs, inlier=inl, Xw=np.array(X, np.float64), mean=float(mean), source=src))
+        tracks.append(dict(seed=seed, obs=obs, inlier=inl, Xw=np.array(X, np.float64), mean=float(mean), source=src, kept=list(kept)))
         for g in comp:
             state[g] = tid
     return tracks

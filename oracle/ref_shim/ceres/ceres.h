@@ -9,6 +9,10 @@
 // is NOT here — it stays a restatement (oracle/visual_oracle.py).
 #pragma once
 #include <cmath>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
 namespace ceres {
 
 template <typename T, int N>
@@ -62,6 +66,62 @@ class CostFunction {
  public:
   virtual ~CostFunction() {}
 };
+class LossFunction { public: virtual ~LossFunction() {} };
+class HuberLoss : public LossFunction { public: double a; explicit HuberLoss(double a_) : a(a_) {} };
+class CauchyLoss : public LossFunction { public: double a; explicit CauchyLoss(double a_) : a(a_) {} };
+class Manifold { public: virtual ~Manifold() {} };
+class EigenQuaternionManifold : public Manifold {};
+class QuaternionManifold : public Manifold {};
+enum LinearSolverType { DENSE_NORMAL_CHOLESKY, DENSE_QR, SPARSE_NORMAL_CHOLESKY, DENSE_SCHUR, SPARSE_SCHUR, ITERATIVE_SCHUR, CGNR };
+enum TerminationType { CONVERGENCE, NO_CONVERGENCE, FAILURE, USER_SUCCESS, USER_FAILURE };
+// ceres::Problem here RECORDS what the reference hands to it (parameter blocks with their manifolds and constancy, residual blocks
+// with cost functor, loss and parameter pointers); ceres::Solve passes the record and the options to a hook the oracle's driver
+// installs.  There is no solver in this file.
+class Problem {
+ public:
+  struct ParamBlock { double* p; int size; Manifold* manifold; bool constant; };
+  struct ResidualBlock { CostFunction* cost; LossFunction* loss; std::vector<double*> params; };
+  std::vector<ParamBlock> params;
+  std::map<double*, size_t> index;
+  std::vector<ResidualBlock> residuals;
+  ~Problem() { for (auto& r : residuals) delete r.cost; for (auto& b : params) delete b.manifold; }
+  void AddParameterBlock(double* p, int size, Manifold* m = nullptr) {
+    auto it = index.find(p);
+    if (it == index.end()) { index[p] = params.size(); params.push_back({p, size, m, false}); }
+    else if (m != nullptr) params[it->second].manifold = m;
+  }
+  void SetParameterBlockConstant(double* p) { params[index.at(p)].constant = true; }
+  void SetManifold(double* p, Manifold* m) { params[index.at(p)].manifold = m; }
+  template <typename... Ps>
+  void AddResidualBlock(CostFunction* cost, LossFunction* loss, Ps... ps) { residuals.push_back({cost, loss, {ps...}}); }
+  int NumResidualBlocks() const { return (int)residuals.size(); }
+  int NumParameterBlocks() const { return (int)params.size(); }
+};
+struct Solver {
+  struct Options {
+    LinearSolverType linear_solver_type = SPARSE_NORMAL_CHOLESKY;
+    int max_num_iterations = 50;
+    bool minimizer_progress_to_stdout = false;
+    int num_threads = 1;
+    double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
+    double max_solver_time_in_seconds = 1e9;
+  };
+  struct Summary {
+    TerminationType termination_type = NO_CONVERGENCE;
+    double initial_cost = 0, final_cost = 0;
+    int num_successful_steps = 0, num_unsuccessful_steps = 0;
+    std::vector<int> iterations;
+    std::string message;
+    std::string BriefReport() const { return "stand-in: see the driver's hook"; }
+    std::string FullReport() const { return BriefReport(); }
+    bool IsSolutionUsable() const { return termination_type != FAILURE; }
+  };
+};
+inline std::function<void(const Solver::Options&, Problem*, Solver::Summary*)>& solve_hook() {
+  static std::function<void(const Solver::Options&, Problem*, Solver::Summary*)> h;
+  return h;
+}
+inline void Solve(const Solver::Options& o, Problem* p, Solver::Summary* s) { if (solve_hook()) solve_hook()(o, p, s); }
 // Sized like ceres::AutoDiffCostFunction<Functor, kNumResiduals, N0, N1, ...>; evaluation lives in the oracle's driver
 // (oracle/ref_driver.cpp), which seeds the Jets the same way Ceres does (one unit partial per parameter coordinate).
 template <typename Functor, int kNumResiduals, int... Ns>

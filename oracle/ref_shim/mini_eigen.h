@@ -85,6 +85,7 @@ template <typename T, int R, int C>
 class Matrix {
  public:
   typedef T Scalar;
+  enum { RowsAtCompileTime = R, ColsAtCompileTime = C };
   mini::Store<T, R, C> s;
 
   Matrix() {
@@ -121,6 +122,14 @@ class Matrix {
   const T& operator()(int i) const { return s.d[i]; }
   T& operator[](int i) { return s.d[i]; }
   const T& operator[](int i) const { return s.d[i]; }
+  T* data() { return &s.d[0]; }
+  const T* data() const { return &s.d[0]; }
+  T& w() { return s.d[3]; }
+  const T& w() const { return s.d[3]; }
+  template <int N> Matrix<T, N, 1> head() const { Matrix<T, N, 1> v; for (int i = 0; i < N; ++i) v(i) = s.d[i]; return v; }
+  template <int N> Matrix<T, N, 1> tail() const { Matrix<T, N, 1> v; for (int i = 0; i < N; ++i) v(i) = s.d[size() - N + i]; return v; }
+  bool isZero(T prec = T(1e-12)) const { for (int i = 0; i < size(); ++i) if (!(std::abs(s.d[i]) <= prec)) return false; return true; }   // |x| <= prec * 1
+  Matrix normalized() const { Matrix m(*this); m.normalize(); return m; }
   T& x() { return s.d[0]; }
   T& y() { return s.d[1]; }
   T& z() { return s.d[2]; }
@@ -313,46 +322,63 @@ typedef Matrix<double, 4, 4> Matrix4d;
 typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
 typedef Matrix<double, Dynamic, 1> VectorXd;
 
-// ---------------------------------------------------------------- symmetric eigen-solver (fixed 3x3 is what the path uses)
+// ---------------------------------------------------------------- symmetric eigen-solver (3x3 on the path, 4x4 in the DLT)
 template <typename M>
 class SelfAdjointEigenSolver {
   typedef typename M::Scalar T;
   M vec_;
-  Matrix<T, 3, 1> val_;
+  Matrix<T, Dynamic, 1> val_dyn_;
+  Matrix<T, 3, 1> val3_;
+  Matrix<T, 4, 1> val4_;
+  int info_ = 0;
 
  public:
   SelfAdjointEigenSolver() {}
   explicit SelfAdjointEigenSolver(const M& m) { compute(m); }
-  // Ascending eigenvalues, eigenvectors in the columns.  Reads the lower triangle only, as Eigen documents.
+  // Ascending eigenvalues, eigenvectors in the columns.  Reads the lower triangle only, as Eigen documents.  Cyclic Jacobi.
   SelfAdjointEigenSolver& compute(const M& m) {
-    T a[3][3], v[3][3];
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { a[i][j] = (i >= j) ? m(i, j) : m(j, i); v[i][j] = (i == j) ? T(1) : T(0); }
+    const int n = m.rows();
+    std::vector<T> a((size_t)n * n), v((size_t)n * n, T(0));
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { a[i * n + j] = (i >= j) ? m(i, j) : m(j, i); }
+    for (int i = 0; i < n; ++i) v[i * n + i] = T(1);
     for (int sweep = 0; sweep < 64; ++sweep) {
-      const T off = std::abs(a[0][1]) + std::abs(a[0][2]) + std::abs(a[1][2]);
+      T off = T(0);
+      for (int p = 0; p < n; ++p) for (int q = p + 1; q < n; ++q) off += std::abs(a[p * n + q]);
       if (off == T(0)) break;
-      for (int p = 0; p < 2; ++p)
-        for (int q = p + 1; q < 3; ++q) {
-          if (a[p][q] == T(0)) continue;
-          const T theta = (a[q][q] - a[p][p]) / (T(2) * a[p][q]);
+      for (int p = 0; p < n - 1; ++p)
+        for (int q = p + 1; q < n; ++q) {
+          if (a[p * n + q] == T(0)) continue;
+          const T theta = (a[q * n + q] - a[p * n + p]) / (T(2) * a[p * n + q]);
           const T t = (theta >= T(0) ? T(1) : T(-1)) / (std::abs(theta) + std::sqrt(theta * theta + T(1)));
           const T c = T(1) / std::sqrt(t * t + T(1)), sn = t * c;
-          for (int k = 0; k < 3; ++k) { const T akp = a[k][p], akq = a[k][q]; a[k][p] = c * akp - sn * akq; a[k][q] = sn * akp + c * akq; }
-          for (int k = 0; k < 3; ++k) { const T apk = a[p][k], aqk = a[q][k]; a[p][k] = c * apk - sn * aqk; a[q][k] = sn * apk + c * aqk; }
-          for (int k = 0; k < 3; ++k) { const T vkp = v[k][p], vkq = v[k][q]; v[k][p] = c * vkp - sn * vkq; v[k][q] = sn * vkp + c * vkq; }
-          a[p][q] = a[q][p] = T(0);
+          for (int k = 0; k < n; ++k) { const T akp = a[k * n + p], akq = a[k * n + q]; a[k * n + p] = c * akp - sn * akq; a[k * n + q] = sn * akp + c * akq; }
+          for (int k = 0; k < n; ++k) { const T apk = a[p * n + k], aqk = a[q * n + k]; a[p * n + k] = c * apk - sn * aqk; a[q * n + k] = sn * apk + c * aqk; }
+          for (int k = 0; k < n; ++k) { const T vkp = v[k * n + p], vkq = v[k * n + q]; v[k * n + p] = c * vkp - sn * vkq; v[k * n + q] = sn * vkp + c * vkq; }
+          a[p * n + q] = a[q * n + p] = T(0);
         }
     }
-    int idx[3] = {0, 1, 2};
-    std::sort(idx, idx + 3, [&](int x, int y) { return a[x][x] < a[y][y]; });
-    for (int j = 0; j < 3; ++j) {
-      val_(j) = a[idx[j]][idx[j]];
-      for (int i = 0; i < 3; ++i) vec_(i, j) = v[i][idx[j]];
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](int x, int y) { return a[x * n + x] < a[y * n + y]; });
+    vec_ = m;
+    val_dyn_.resize(n);
+    for (int j = 0; j < n; ++j) {
+      const T lam = a[idx[j] * n + idx[j]];
+      val_dyn_(j) = lam;
+      if (n == 3) val3_(j) = lam;
+      if (n == 4) val4_(j) = lam;
+      for (int i = 0; i < n; ++i) vec_(i, j) = v[i * n + idx[j]];
     }
+    info_ = 0;
     return *this;
   }
-  const Matrix<T, 3, 1>& eigenvalues() const { return val_; }
+  template <int R = M::RowsAtCompileTime> typename std::enable_if<R == 3, const Matrix<T, 3, 1>&>::type eigenvalues() const { return val3_; }
+  template <int R = M::RowsAtCompileTime> typename std::enable_if<R == 4, const Matrix<T, 4, 1>&>::type eigenvalues() const { return val4_; }
+  template <int R = M::RowsAtCompileTime> typename std::enable_if<(R != 3 && R != 4), const Matrix<T, Dynamic, 1>&>::type eigenvalues() const { return val_dyn_; }
   const M& eigenvectors() const { return vec_; }
+  int info() const { return info_; }
 };
+enum ComputationInfo { Success = 0, NumericalIssue = 1, NoConvergence = 2, InvalidInput = 3 };
 
 // ---------------------------------------------------------------- rotations (outside the hot path)
 template <typename T> class AngleAxis;
@@ -362,6 +388,32 @@ class Quaternion {
   T w_, x_, y_, z_;
   Quaternion() : w_(1), x_(0), y_(0), z_(0) {}
   Quaternion(T w, T x, T y, T z) : w_(w), x_(x), y_(y), z_(z) {}
+  // rotation matrix -> quaternion by the branch on the trace / largest diagonal entry that Eigen documents (w >= 0 on the first branch)
+  explicit Quaternion(const Matrix<T, 3, 3>& m) {
+    T t = m.trace();
+    if (t > T(0)) {
+      t = std::sqrt(t + T(1));
+      w_ = T(0.5) * t; t = T(0.5) / t;
+      x_ = (m(2, 1) - m(1, 2)) * t; y_ = (m(0, 2) - m(2, 0)) * t; z_ = (m(1, 0) - m(0, 1)) * t;
+    } else {
+      int i = 0;
+      if (m(1, 1) > m(0, 0)) i = 1;
+      if (m(2, 2) > m(i, i)) i = 2;
+      const int j = (i + 1) % 3, k = (j + 1) % 3;
+      t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + T(1));
+      T v[3];
+      v[i] = T(0.5) * t; t = T(0.5) / t;
+      w_ = (m(k, j) - m(j, k)) * t; v[j] = (m(j, i) + m(i, j)) * t; v[k] = (m(k, i) + m(i, k)) * t;
+      x_ = v[0]; y_ = v[1]; z_ = v[2];
+    }
+  }
+  T& w() { return w_; } T& x() { return x_; } T& y() { return y_; } T& z() { return z_; }
+  const T& w() const { return w_; } const T& x() const { return x_; } const T& y() const { return y_; } const T& z() const { return z_; }
+  T norm() const { return std::sqrt(w_ * w_ + x_ * x_ + y_ * y_ + z_ * z_); }
+  void normalize() { const T n = norm(); w_ /= n; x_ /= n; y_ /= n; z_ /= n; }
+  Quaternion normalized() const { Quaternion q(*this); q.normalize(); return q; }
+  Quaternion conjugate() const { return Quaternion(w_, -x_, -y_, -z_); }
+  Matrix<T, 3, 1> operator*(const Matrix<T, 3, 1>& p) const { return toRotationMatrix() * p; }
   Quaternion operator*(const Quaternion& o) const {
     return Quaternion(w_ * o.w_ - x_ * o.x_ - y_ * o.y_ - z_ * o.z_, w_ * o.x_ + x_ * o.w_ + y_ * o.z_ - z_ * o.y_,
                       w_ * o.y_ - x_ * o.z_ + y_ * o.w_ + z_ * o.x_, w_ * o.z_ + x_ * o.y_ - y_ * o.x_ + z_ * o.w_);

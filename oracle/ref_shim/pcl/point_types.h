@@ -15,4 +15,9 @@ struct PointXYZRGB {
   PointXYZRGB() : data{0, 0, 0, 1}, b(0), g(0), r(0), a(255) {}
 };
 struct PointXYZRGBA : PointXYZRGB {};
+struct PointXYZ {
+  union { float data[4]; struct { float x, y, z; }; };
+  PointXYZ() : data{0, 0, 0, 1} {}
+  PointXYZ(float a, float b, float c) : data{a, b, c, 1} {}
+};
 }  // namespace pcl

@@ -10,5 +10,9 @@ class SE3 {
   SE3(const Eigen::Matrix3d& R, const Eigen::Vector3d& t) : R_(R), t_(t) {}
   Eigen::Matrix3d rotation_matrix() const { return R_; }
   const Eigen::Vector3d& translation() const { return t_; }
+  Eigen::Vector3d& translation() { return t_; }
+  SE3 operator*(const SE3& o) const { return SE3(R_ * o.R_, R_ * o.t_ + t_); }          // composition, as Sophus defines it
+  Eigen::Vector3d operator*(const Eigen::Vector3d& p) const { return R_ * p + t_; }
+  SE3 inverse() const { const Eigen::Matrix3d Rt = R_.transpose(); return SE3(Rt, -(Rt * t_)); }
 };
 }  // namespace Sophus

@@ -1,0 +1,30 @@
+// Declarations of the SQLite C API calls loadFromColmapDB (src/lvba_system.cpp:510-685) makes (NOT the SQLite header; test
+// infrastructure).  SQLite publishes this ABI; the symbols resolve against the system's libsqlite3.so.0 at link time, so the
+// reference's reader runs against a real database.
+#pragma once
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct sqlite3 sqlite3;
+typedef struct sqlite3_stmt sqlite3_stmt;
+typedef long long sqlite3_int64;
+#define SQLITE_OK 0
+#define SQLITE_ROW 100
+#define SQLITE_DONE 101
+int sqlite3_open(const char*, sqlite3**);
+int sqlite3_close(sqlite3*);
+const char* sqlite3_errmsg(sqlite3*);
+int sqlite3_prepare_v2(sqlite3*, const char*, int, sqlite3_stmt**, const char**);
+int sqlite3_step(sqlite3_stmt*);
+int sqlite3_reset(sqlite3_stmt*);
+int sqlite3_finalize(sqlite3_stmt*);
+int sqlite3_bind_int(sqlite3_stmt*, int, int);
+int sqlite3_bind_int64(sqlite3_stmt*, int, sqlite3_int64);
+int sqlite3_column_int(sqlite3_stmt*, int);
+sqlite3_int64 sqlite3_column_int64(sqlite3_stmt*, int);
+const unsigned char* sqlite3_column_text(sqlite3_stmt*, int);
+const void* sqlite3_column_blob(sqlite3_stmt*, int);
+int sqlite3_column_bytes(sqlite3_stmt*, int);
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,261 @@
+"""The stage oracles, pinned against the REFERENCE'S PIPELINE SOURCE (src/lvba_system.cpp).
+
+tests/golden/ref_system.npz holds seeded inputs and what LvbaSystem's own member functions computed from them — runWindowBA,
+runLidarBA, buildGridMapFromOptimized, updateCameraPosesFromLidar, generateDepthWithVoxel, BuildTracksAndFuse3D and the Ceres problem
+optimizeCameraPoses builds — with the whole of src/lvba_system.cpp compiled where it lies (oracle/ref_system_driver.cpp) on the
+stand-in library headers of oracle/ref_shim/ (own code; what that leaves open: ref_shim/mini_eigen.h).  Without a GPU:
+
+  L  the oracle chain the offline tool is tested against (voxel map + damping_iter per window with the 3-voxels-per-pose skip rule,
+     anchor clouds, relative poses, two global stages, pose of every frame from its anchor) reproduces the reference's runLidarBA
+  D  the numpy restatement of the camera-pose correction and oracle/depth_oracle.py reproduce the reference's camera poses and its
+     depth images BIT FOR BIT; the device's depth passes, run through the host policy, do too
+  F  oracle/fuse_oracle.py reproduces BuildTracksAndFuse3D track for track — same track order, observation order, inlier order,
+     points to 1e-12 — once it is told the order the reference's three `for (auto& kv : unordered_map)` loops run in.  C++ leaves
+     that order open; with g++ it is libstdc++'s, restated in fuse_oracle.libstdcxx_order and held against the real container here.
+     The ABI of this repo documents ASCENDING image id instead; on this scene the two orders give 70 vs 63 tracks — the choice matters,
+     and it is a property of the reference's container, not of the restatement
+  P  the problem the reference hands to Ceres: camera 0 constant (q and t), EigenQuaternionManifold on every camera, no loss function,
+     sigma 0.5 px / 0.01 m, 50 iterations DENSE_SCHUR, default tolerances; the points that enter are exactly the usable tracks with a
+     valid plane, their planes those of the voxel oracle on the oracle's anchor clouds (live test: the scene is rebuilt, not stored)
+
+Where oracle/_ref/liblvba_system_ref.so can be built (this container) the file is regenerated and must come out bit for bit.
+"""
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "tests"))
+
+from oracle import anchor_oracle as ao, depth_oracle as dep, fuse_oracle as fo, lidar_oracle as lo, lvba_system_ref as sr, synth, visual_oracle as vis, voxel_oracle as vox  # noqa: E402
+import test_depth_emu  # noqa: E402
+
+G = np.load(ROOT / "tests" / "golden" / "ref_system.npz")
+needs_ref = pytest.mark.skipif(not sr.available(), reason="oracle/_ref/liblvba_system_ref.so needs /root/reference (not on the GPU box)")
+
+
+def split(flat, ptr):
+    return [flat[ptr[i]:ptr[i + 1]] for i in range(len(ptr) - 1)]
+
+
+def lex(a):
+    return a[np.lexsort(a.T[::-1])]
+
+
+# ------------------------------------------------------------------------------------------------ L
+def lidar_chain(use_rel):
+    """runWindowBA (src/lvba_system.cpp:204-302) + runLidarBA (:304-409) out of the stage oracles."""
+    scans = split(G["L_xyz"], G["L_scan_ptr"]); start = G["L_poses"]
+    W, win = len(scans), int(G["L_window"])
+    win_ptr = list(range(0, W, win)) + [W]
+    anchor_index = np.full(W, -1, np.int32); rel = np.zeros((W, 12)); rel[:, [0, 4, 8]] = 1.0      # IMUST(): identity, zero
+    anchors, clouds = [], []
+    for w in range(len(win_ptr) - 1):
+        a, b = win_ptr[w], win_ptr[w + 1]
+        vp, pi, cl, _ = vox.voxelize(scans[a:b], start[a:b], float(G["L_s1_voxel"]), vox.EIGEN_RATIO_DEFAULT)  # :247-258: stage-1 SIZE, but the plane test reads
+        #                                       the process-wide array, which still holds bavoxel.hpp:17's default here (the configured arrays are set at :358, later)
+        if len(vp) - 1 < 3 * (b - a):                                                                      # :259-263
+            continue
+        x_win = start[a:b]
+        if len(vp) - 1 > 0:
+            x_win, _ = lo.damping_iter(vp, pi, cl, start[a:b])                                             # :264
+        aligned = start[a:b].copy()
+        if use_rel:                                                                                        # :267-279
+            R_align = start[a, :9].reshape(3, 3) @ x_win[0, :9].reshape(3, 3).T
+            p_align = start[a, 9:] - R_align @ x_win[0, 9:]
+            for j in range(b - a):
+                aligned[j, :9] = (R_align @ x_win[j, :9].reshape(3, 3)).ravel(); aligned[j, 9:] = R_align @ x_win[j, 9:] + p_align
+        r = rel_to(start[a], aligned)                                                                      # :283-289: anchor = the ODOMETRY pose of frame 0
+        rel[a:b] = r; anchor_index[a:b] = len(anchors)
+        clouds.append(ao.anchor_clouds(scans[a:b], r, np.array([0, b - a]), float(G["L_anchor_leaf"]))[0])
+        anchors.append(start[a])
+    anchors = np.array(anchors)
+    for vs_, er in ((float(G["L_s1_voxel"]), G["L_s1_ratio"]), (float(G["L_s2_voxel"]), G["L_s2_ratio"])):   # :355-389
+        vp, pi, cl, _ = vox.voxelize(clouds, anchors, vs_, er)
+        anchors, _ = lo.damping_iter(vp, pi, cl, anchors)
+    final = start.copy()
+    for i in range(W):                                                                                     # :393-403
+        k = anchor_index[i]
+        if k < 0:
+            continue
+        A = anchors[k, :9].reshape(3, 3)
+        final[i, :9] = (A @ rel[i, :9].reshape(3, 3)).ravel(); final[i, 9:] = A @ rel[i, 9:] + anchors[k, 9:]
+    return anchor_index, rel, clouds, final
+
+
+def rel_to(anchor, poses):
+    """rel.R = anchor.R^T x.R ; rel.p = anchor.R^T (x.p - anchor.p)  (:286-289)."""
+    Ra = anchor[:9].reshape(3, 3); out = np.zeros_like(poses)
+    for j in range(len(poses)):
+        out[j, :9] = (Ra.T @ poses[j, :9].reshape(3, 3)).ravel(); out[j, 9:] = Ra.T @ (poses[j, 9:] - anchor[9:])
+    return out
+
+
+def test_window_stage_anchor_bookkeeping_equals_reference_source():
+    idx, rel, clouds, _ = lidar_chain(False)
+    assert np.array_equal(idx, G["L_anchor_index"]) and idx.tolist() == [0, 0, 0, -1, -1, -1, 1, 1, 1]      # the middle window is skipped
+    assert np.abs(rel - G["L_rel_poses"]).max() <= 1e-12
+    ref_clouds = split(G["L_anchor_clouds_sorted"], G["L_anchor_cloud_ptr"])
+    assert len(clouds) == len(ref_clouds) == 2
+    for c, r in zip(clouds, ref_clouds):
+        assert np.array_equal(lex(c), r)                                                                   # float32 points, bit for bit
+    assert np.array_equal(G["L_anchor_poses"], G["L_poses"][[0, 6]])                                        # anchors keep the odometry pose (:283)
+
+
+@pytest.mark.parametrize("use_rel", [False, True])
+def test_lidar_half_equals_reference_source(use_rel):
+    _, _, _, final = lidar_chain(use_rel)
+    ref = G["L_final_poses_rel"] if use_rel else G["L_final_poses"]
+    assert np.abs(final - ref).max() <= 1e-9
+    assert np.array_equal(ref[3:6], G["L_poses"][3:6])                    # frames of the skipped window keep their odometry pose (:396)
+    assert np.abs(ref - G["L_poses"]).max() > 1e-3                        # the others moved
+    if use_rel:
+        assert np.abs(G["L_final_poses_rel"] - G["L_final_poses"]).max() > 1e-5       # the switch does something
+
+
+# ------------------------------------------------------------------------------------------------ D
+def camera_chain():
+    """updateCameraPosesFromLidar (:412-446) and the extrinsics of initFromDatasetIO (:497-503) / generateDepthWithVoxel (:861-862)."""
+    opt, before, ts = G["D_poses"], G["D_poses_before"], G["D_frame_ts"]
+    body = np.zeros_like(G["D_image_poses"])
+    for i, t_img in enumerate(G["D_image_ts"]):
+        it = int(np.searchsorted(ts, t_img, side="left"))                 # std::lower_bound
+        idx = len(ts) - 1 if it == len(ts) else it
+        if 0 < it < len(ts) and abs(ts[idx - 1] - t_img) < abs(ts[idx] - t_img):
+            idx -= 1
+        Ro, po = opt[idx, :9].reshape(3, 3), opt[idx, 9:]; Rb, pb = before[idx, :9].reshape(3, 3), before[idx, 9:]
+        Rd = Ro @ Rb.T; pd = Ro @ (-(Rb.T @ pb)) + po                     # T_opt * T_orig^-1
+        Rc, pc = G["D_image_poses"][i, :9].reshape(3, 3), G["D_image_poses"][i, 9:]
+        body[i, :9] = (Rd @ Rc).ravel(); body[i, 9:] = Rd @ pc + pd
+    Rli = G["D_Ril"].T; tli = -Rli @ G["D_til"]
+    Rci = G["D_Rcl"] @ Rli; tci = G["D_Rcl"] @ tli + G["D_tcl"]
+    cams = np.zeros_like(body)
+    for i in range(len(body)):
+        Rcw = Rci @ body[i, :9].reshape(3, 3).T
+        cams[i, :9] = Rcw.ravel(); cams[i, 9:] = -Rcw @ body[i, 9:] + tci
+    return body, cams
+
+
+def test_camera_poses_from_the_lidar_result_equal_reference_source():
+    body, cams = camera_chain()
+    assert np.abs(body - G["D_camera_body_poses"]).max() <= 1e-12
+    assert np.abs(cams - G["D_cams"]).max() <= 1e-12
+    assert np.abs(G["D_cams"] - G["D_cams_odometry"]).max() > 1e-3        # the LiDAR correction moved the cameras
+
+
+def depth_scene():
+    return dict(scans=split(G["D_xyz"], G["D_scan_ptr"]), poses=G["D_poses"], frame_ts=G["D_frame_ts"], cams=G["D_cams"], image_ts=G["D_image_ts"],
+                intr=G["D_intr"], width=int(G["D_size"][0]), height=int(G["D_size"][1]))
+
+
+@pytest.mark.parametrize("literal", [False, True])
+def test_depth_images_equal_reference_source_bit_for_bit(literal):
+    s = depth_scene()
+    fn = dep.render_literal if literal else dep.render
+    img = fn(s["scans"], s["poses"], s["frame_ts"], s["cams"], s["image_ts"], s["intr"], s["width"], s["height"])
+    assert np.array_equal(img, G["D_depth"]) and int((G["D_depth"] > 0).sum()) > 5000
+
+
+def test_device_depth_passes_equal_reference_source_bit_for_bit(tmp_path_factory):
+    import ctypes
+    import subprocess
+    so = tmp_path_factory.mktemp("emu_ref_sys") / "libdepth_emu.so"
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "depth_emu.cpp"), "-o", str(so)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rc, img, info = test_depth_emu.emu_render(ctypes.CDLL(str(so)), depth_scene())
+    assert rc == 0 and info["pairs"] > 0
+    assert np.array_equal(img, G["D_depth"])
+
+
+# ------------------------------------------------------------------------------------------------ F
+def fuse_inputs():
+    kp_ptr, kp_uv = G["F_kp_ptr"], G["F_kp_uv"]
+    Xw, valid = dep.backproject(list(G["F_depth"]), G["F_cams"], G["F_intr"], kp_ptr, kp_uv)
+    return kp_ptr, kp_uv, G["F_matches"], G["F_cams"], G["F_intr"], Xw, valid
+
+
+def test_track_fusion_equals_reference_source_under_its_container_order():
+    tr = fo.fuse(*fuse_inputs(), map_order=fo.libstdcxx_order)
+    assert len(tr) == len(G["F_Xw"]) == 70
+    for k, t in enumerate(tr):
+        ob = G["F_obs"][G["F_obs_ptr"][k]:G["F_obs_ptr"][k + 1]]
+        assert np.array_equal(t["obs"], ob), k                                                  # same component, same member order
+        assert list(t["kept"]) == G["F_inl"][G["F_inl_ptr"][k]:G["F_inl_ptr"][k + 1]].tolist(), k     # same inliers in the same order
+        assert np.abs(t["Xw"] - G["F_Xw"][k]).max() <= 1e-12, k
+
+
+def test_ascending_order_is_a_different_but_documented_choice():
+    """What the ABI documents (ascending image id) against what the reference's container does under g++: same logic, other visiting order."""
+    tr = fo.fuse(*fuse_inputs())
+    ref = {tuple(map(tuple, G["F_obs"][G["F_obs_ptr"][k]:G["F_obs_ptr"][k + 1]].tolist())) for k in range(len(G["F_Xw"]))}
+    mine = {tuple(map(tuple, sorted(t["obs"].tolist()))) for t in tr}
+    assert len(tr) == 63 and mine <= {tuple(sorted(r)) for r in ref}                            # every ascending-order track is a reference track
+
+
+@needs_ref
+def test_libstdcxx_order_restatement_equals_the_real_container():
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        res = int(rng.integers(1, 60))
+        keys = rng.choice(90, size=int(rng.integers(1, min(res, 40) + 1)), replace=False).tolist()
+        assert sr.unordered_map_order(res, keys) == fo.libstdcxx_order(res, keys), (res, keys)
+
+
+# ------------------------------------------------------------------------------------------------ P
+def test_problem_handed_to_ceres():
+    assert G["P_cam_const"].tolist() == [3] + [0] * 7                     # q AND t of camera 0 constant (:1582-1583), nothing else
+    assert np.all(G["P_cam_manifold"] == 1)                               # EigenQuaternionManifold on every camera, also the constant one (:1579)
+    assert not G["P_obs_loss"].any() and not G["P_pl_loss"].any()         # the two HuberLoss objects are created (:1585-1586) and never passed (:1630, :1639)
+    assert np.all(G["P_obs_sigma"] == 0.5) and np.all(G["P_pl_sigma"] == 0.01)
+    assert G["P_options"].tolist() == [50.0, 3.0, 1e-6, 1e-10, 1e-8]       # max_num_iterations, DENSE_SCHUR, function / gradient / parameter tolerance
+    assert np.all(G["P_obs_intr"] == G["F_intr"][None])
+    assert np.array_equal(G["P_pl_pt"], np.arange(len(G["P_X"])))         # one plane residual per point block, in order
+    assert np.all(np.diff(G["P_obs_pt"]) >= 0) and set(G["P_obs_pt"].tolist()) == set(range(len(G["P_X"])))
+    n = np.linalg.norm(G["P_pl_nd"][:, :3], axis=1)
+    assert np.abs(n - 1).max() <= 1e-12
+    # the parameter blocks start from the cameras / fused points of the stages before
+    q = G["P_q"]; R = vis.quat_to_rot(q)
+    assert np.abs(R.reshape(-1, 9) - G["F_cams"][:, :9]).max() <= 1e-12 and np.abs(G["P_t"] - G["F_cams"][:, 9:]).max() == 0
+    assert np.abs(np.linalg.norm(q, axis=1) - 1).max() <= 1e-15           # q_eig.normalize() (:1515); the sign of q is the library's branch, no result depends on it
+    # every point block is a fused track, every observation one of its INLIERS with the keypoint's pixel as the measurement
+    for j, X in enumerate(G["P_X"]):
+        k = int(np.nonzero(np.all(G["F_Xw"] == X, axis=1))[0][0])
+        ob = G["F_obs"][G["F_obs_ptr"][k]:G["F_obs_ptr"][k + 1]]; inl = G["F_inl"][G["F_inl_ptr"][k]:G["F_inl_ptr"][k + 1]]
+        rows = np.nonzero(G["P_obs_pt"] == j)[0]
+        assert G["P_obs_cam"][rows].tolist() == ob[inl, 0].tolist()
+        uv = np.array([G["F_kp_uv"][G["F_kp_ptr"][c] + kp] for c, kp in ob[inl]], np.float64)
+        assert np.array_equal(G["P_obs_uv"][rows], uv)
+
+
+@needs_ref
+def test_points_and_planes_of_the_problem_against_the_oracle_chain_live():
+    """Rebuilds the scene (2.9 MB of scans, not stored): usable tracks (:1432-1438), anchor clouds (:1471-1490), surf map under the eigen-ratio array
+    in force (:1498-1506), recompute_local_planes (:1529-1566) out of the stage oracles vs what the reference recorded."""
+    import visual_scene as vs
+    g = vs.make(Path(tempfile.mkdtemp()), seed=3, W=8)
+    win, leaf = int(G["P_window"]), float(G["P_anchor_leaf"])
+    win_ptr = np.array(list(range(0, 8, win)) + [8])
+    rel = ao.rel_poses(g["poses"], win_ptr)
+    clouds = ao.anchor_clouds(g["scans"], rel, win_ptr, leaf)
+    roots = vox.build_tree_literal(clouds, g["poses"][win_ptr[:-1]], float(G["P_voxel"]), G["P_ratio"])
+    usable = [k for k in range(len(G["F_Xw"])) if G["F_obs_ptr"][k + 1] - G["F_obs_ptr"][k] >= 3 and np.all(np.isfinite(G["F_Xw"][k])) and not np.all(np.abs(G["F_Xw"][k]) <= 1e-12)]
+    nd = vox.plane_lookup_literal(roots, G["F_Xw"][usable], float(G["P_voxel"]))
+    has = vis.valid_tracks(nd)
+    assert np.array_equal(G["F_Xw"][np.array(usable)[has]], G["P_X"])                            # the same tracks enter, in the same order
+    sgn = np.sign(np.einsum("ij,ij->i", nd[has][:, :3], G["P_pl_nd"][:, :3]))
+    assert np.abs(nd[has] * sgn[:, None] - G["P_pl_nd"]).max() <= 1e-9                          # plane (n, d) up to the eigenvector's sign
+
+
+# ------------------------------------------------------------------------------------------------ the file itself
+@needs_ref
+def test_fixture_is_what_the_reference_pipeline_source_computes_bit_for_bit():
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    import make_golden_ref_system
+    fresh = make_golden_ref_system.generate()
+    assert sorted(fresh) == sorted(G.files)
+    for k in G.files:
+        assert np.array_equal(np.asarray(fresh[k]), G[k], equal_nan=True), k

@@ -104,3 +104,37 @@ print('CHILD-OK')
 def test_device_reproduces_what_the_reference_source_computed():
     r = subprocess.run([sys.executable, "-c", CODE], capture_output=True, text=True, timeout=300, cwd=str(ROOT))
     assert r.returncode == 0 and "CHILD-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+
+
+CODE_SYSTEM = """
+import sys
+import numpy as np
+sys.path.insert(0, %r)
+import __graft_entry__ as graft
+pkg = graft.load_package(); pkg.load_library()
+assert pkg.device_count() >= 1
+G = np.load(%r)
+split = lambda flat, ptr: [flat[ptr[i]:ptr[i + 1]] for i in range(len(ptr) - 1)]
+lex = lambda a: a[np.lexsort(a.T[::-1])]
+# ---- B4: buildGridMapFromOptimized + generateDepthWithVoxel of src/lvba_system.cpp, bit for bit (grid voxel 0.5 m, window +-0.5 s: :1279, :1300)
+g = pkg.DepthGrid(split(G["D_xyz"], G["D_scan_ptr"]), G["D_poses"], G["D_frame_ts"], 0.5)
+img, info = g.render(G["D_cams"], G["D_image_ts"], G["D_intr"], int(G["D_size"][0]), int(G["D_size"][1]), 0.5)
+g.close()
+assert np.array_equal(img, G["D_depth"]) and info["kernel_launches"] > 0
+# ---- B6 inside runWindowBA: the anchor clouds of the two windows that were solved (use_window_ba_rel = false: relative poses from the odometry)
+scans = split(G["L_xyz"], G["L_scan_ptr"])
+keep = [0, 1, 2, 6, 7, 8]
+clouds = pkg.anchor_clouds([scans[i] for i in keep], G["L_rel_poses"][keep], np.array([0, 3, 6], np.int32), float(G["L_anchor_leaf"]))
+for c, r in zip(clouds, split(G["L_anchor_clouds_sorted"], G["L_anchor_cloud_ptr"])):
+    assert np.array_equal(lex(c), r)
+print('CHILD-OK')
+""" % (str(ROOT), str(ROOT / "tests" / "golden" / "ref_system.npz"))
+
+
+@pytest.mark.gpu
+def test_device_reproduces_what_the_reference_pipeline_source_computed():
+    """tests/golden/ref_system.npz (src/lvba_system.cpp compiled where it lies; CPU twin: tests/test_ref_system_pin.py): depth images and
+    anchor clouds bit for bit.  The track fusion is compared on the CPU only: the reference's container order differs from the ABI's
+    documented ascending order (tests/test_ref_system_pin.py::test_ascending_order_is_a_different_but_documented_choice)."""
+    r = subprocess.run([sys.executable, "-c", CODE_SYSTEM], capture_output=True, text=True, timeout=300, cwd=str(ROOT))
+    assert r.returncode == 0 and "CHILD-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
