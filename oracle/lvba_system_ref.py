@@ -136,6 +136,15 @@ class System:
         m = np.ascontiguousarray(matches, np.int32).reshape(-1, 4)
         self.lib.sys_set_keypoints_and_matches(self.h, _p(kp_ptr), _p(kp_uv), C.c_int64(len(m)), _p(m))
 
+    def load_colmap_db(self, dataset_path, db_path):
+        """loadFromColmapDB; returns (ok, kp_ptr, kp_uv, matches (n, 4))."""
+        ok = bool(self.lib.sys_load_colmap_db(self.h, str(dataset_path).encode(), str(db_path).encode()))
+        nk = C.c_int64(); nm = C.c_int64()
+        self.lib.sys_frontend_sizes(self.h, C.byref(nk), C.byref(nm))
+        kp_ptr = np.zeros(self.M + 1, np.int64); kp_uv = np.zeros((nk.value, 2), np.float32); m = np.zeros((nm.value, 4), np.int32)
+        self.lib.sys_get_frontend(self.h, _p(kp_ptr), _p(kp_uv), _p(m))
+        return ok, kp_ptr, kp_uv, m
+
     def build_tracks(self):
         no = C.c_int64(); ni = C.c_int64()
         n = int(self.lib.sys_build_tracks(self.h, C.byref(no), C.byref(ni)))

@@ -234,6 +234,31 @@ void sys_set_keypoints_and_matches(void* h, const int64_t* kp_ptr, const float* 
   for (int64_t m = 0; m < n_matches; ++m)
     s.all_matches_[lvba::pairIndex(matches[4 * m], matches[4 * m + 2], M)].push_back({matches[4 * m + 1], matches[4 * m + 3]});
 }
+// loadFromColmapDB (:510-685) against a real database (SQLite = the system's library): fills all_keypoints_ / all_matches_ of the images
+// sys_set_camera listed.  dataset_path: the directory getImagePath (:2146) names the images under; returns what the reference returns.
+int sys_load_colmap_db(void* h, const char* dataset_path, const char* db_path) {
+  auto& s = *static_cast<Sys*>(h)->s;
+  s.dataset_path_ = dataset_path; s.dataset_io_->dataset_path_ = dataset_path; s.dataset_io_->colmap_db_path_ = db_path;
+  return s.loadFromColmapDB() ? 1 : 0;
+}
+void sys_frontend_sizes(void* h, int64_t* n_kp, int64_t* n_matches) {
+  auto& s = *static_cast<Sys*>(h)->s;
+  *n_kp = *n_matches = 0;
+  for (auto& k : s.all_keypoints_) *n_kp += (int64_t)k.size();
+  for (auto& m : s.all_matches_) *n_matches += (int64_t)m.size();
+}
+// keypoints per image (kp_ptr: M + 1) and matches as (img_a, kp_a, img_b, kp_b) in all_matches_ order (pairIndex order, then stored order)
+void sys_get_frontend(void* h, int64_t* kp_ptr, float* kp_uv, int32_t* matches) {
+  auto& s = *static_cast<Sys*>(h)->s;
+  const int M = (int)s.all_keypoints_.size();
+  int64_t q = 0;
+  kp_ptr[0] = 0;
+  for (int k = 0; k < M; ++k) { for (auto& kp : s.all_keypoints_[k]) { kp_uv[2 * q] = kp.x; kp_uv[2 * q + 1] = kp.y; ++q; } kp_ptr[k + 1] = q; }
+  int64_t m = 0;
+  for (int a = 0; a < M - 1; ++a)
+    for (int b = a + 1; b < M; ++b)
+      for (auto& pr : s.all_matches_[lvba::pairIndex(a, b, M)]) { matches[4 * m] = a; matches[4 * m + 1] = pr.first; matches[4 * m + 2] = b; matches[4 * m + 3] = pr.second; ++m; }
+}
 // BuildTracksAndFuse3D (:921-1263).  Returns the number of tracks; sizes through the two counters.
 int64_t sys_build_tracks(void* h, int64_t* n_obs, int64_t* n_inl) {
   auto& s = *static_cast<Sys*>(h)->s;

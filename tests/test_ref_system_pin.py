@@ -259,3 +259,29 @@ def test_fixture_is_what_the_reference_pipeline_source_computes_bit_for_bit():
     assert sorted(fresh) == sorted(G.files)
     for k in G.files:
         assert np.array_equal(np.asarray(fresh[k]), G[k], equal_nan=True), k
+
+
+# ------------------------------------------------------------------------------------------------ N4: the COLMAP database reader
+@needs_ref
+def test_reference_reader_reads_the_database_the_dataset_writer_writes():
+    """loadFromColmapDB (src/lvba_system.cpp:510-685, run from its own source against the system's SQLite) on the database
+    oracle/dataset_writer.py wrote: database ids shuffled (so some pairs are stored with swapped columns, :655-660), one match with an
+    out-of-range keypoint (dropped, :668-672).  It must hand back exactly the scene's keypoints and matches in the order
+    BuildTracksAndFuse3D visits them — the same truth tests/test_visual_offline.py holds the product's own reader
+    (global-lvba_b200/host/lvba_visual_offline.hpp) against."""
+    import visual_scene as vs
+    root = Path(tempfile.mkdtemp())
+    g = vs.make(root, seed=5, W=6, n_per_scan=4000, n_landmarks=120)
+    assert sorted(g["db_ids"]) != g["db_ids"]
+    S = sr.System()
+    S.set_lidar(g["scans"][:1], g["poses"][:1], g["ts"][:1])
+    S.set_camera(g["width"], g["height"], g["intr"], vs.RCL.ravel(), vs.PCL, np.eye(3).ravel(), np.zeros(3), np.array(g["image_ts"]), g["image_poses"])
+    ok, kp_ptr, kp_uv, m = S.load_colmap_db(str(root) + "/", root / "Colmap" / "colmap.db")
+    S.close()
+    assert ok
+    assert np.array_equal(np.diff(kp_ptr), [len(k) for k in g["keypoints"]]) and np.array_equal(kp_uv, np.concatenate(g["keypoints"]))
+    M = len(g["keypoints"])
+    want = [(a, ka, b, kb) for a in range(M) for b in range(a + 1, M) for (ka, kb) in g["pair"].get((a, b), [])
+            if ka < len(g["keypoints"][a]) and kb < len(g["keypoints"][b])]
+    dropped = sum(len(v) for v in g["pair"].values()) - len(want)
+    assert dropped == 1 and np.array_equal(m, np.array(want, np.int32))
