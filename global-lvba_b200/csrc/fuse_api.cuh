@@ -22,6 +22,7 @@ void lvba_fuse_default_opts(lvba_fuse_opts* o) {
   o->reproj_mean_thr_px = 3.0;        // track_fusion/reproj_mean_thr, :130
   o->depth_gate_m = 0.12;             // :1050
   o->device = -1;
+  o->map_order = LVBA_FUSE_ORDER_ASCENDING;
 }
 
 int lvba_tracks_fuse_create(int32_t n_images, const int64_t* kp_ptr, const float* kp_uv, int64_t n_matches, const int32_t* match_img_a,
@@ -42,6 +43,8 @@ int lvba_tracks_fuse_create(int32_t n_images, const int64_t* kp_ptr, const float
   if (opts) o = *opts; else lvba_fuse_default_opts(&o);
   if (o.obser_thr < 1 || !(o.reproj_mean_thr_px >= 0) || !(o.depth_gate_m >= 0) || !std::isfinite(o.min_view_angle_deg))
     return fail(LVBA_ERR_INVALID_ARG, "bad fusion options");
+  if (o.map_order != LVBA_FUSE_ORDER_ASCENDING && o.map_order != LVBA_FUSE_ORDER_LIBSTDCXX)
+    return fail(LVBA_ERR_INVALID_ARG, "map_order %d is neither LVBA_FUSE_ORDER_ASCENDING nor LVBA_FUSE_ORDER_LIBSTDCXX", (int)o.map_order);
   for (int64_t k = 0; k < (int64_t)n_images * 12; ++k)
     if (!std::isfinite(cams[k])) return fail(LVBA_ERR_INVALID_ARG, "non-finite camera entry %lld", (long long)k);
   for (int k = 0; k < 8; ++k)
@@ -54,7 +57,7 @@ int lvba_tracks_fuse_create(int32_t n_images, const int64_t* kp_ptr, const float
   std::unique_ptr<lvba_track_set> h(new lvba_track_set());
   CudaExec ex;
   StreamDrain drain(nullptr);
-  fuse::Params prm{o.obser_thr, std::cos(o.min_view_angle_deg * M_PI / 180.0), o.reproj_mean_thr_px, o.depth_gate_m};
+  fuse::Params prm{o.obser_thr, std::cos(o.min_view_angle_deg * M_PI / 180.0), o.reproj_mean_thr_px, o.depth_gate_m, (int)o.map_order};
   const int rc = fuse::run(ex, n_images, kp_ptr, kp_uv, n_matches, match_img_a, match_kp_a, match_img_b, match_kp_b, cams, intr, kp_Xw,
                            kp_valid, prm, h->res);
   if (rc != LVBA_OK) return rc;

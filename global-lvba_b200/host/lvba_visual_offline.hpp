@@ -51,6 +51,7 @@ struct Config {
   std::vector<float> eigen1{0.3f, 0.1f, 0.06f, 0.03f}, eigen2{0.3f, 0.1f, 0.06f, 0.03f};     // bavoxel.hpp:17
   bool enable_lidar_ba = true, enable_visual_ba = true, colmap_output = true;
   double min_view_angle = 8.0, reproj_mean_thr = 3.0, filter_size_points3D = 0.01;
+  int fuse_map_order = LVBA_FUSE_ORDER_ASCENDING;     // not a reference parameter: which unordered_map order the track fusion mimics (lvba_b200.h)
   bool scaled = false;
   // the tail of readParameters (:59-62): the image is used at `scale`
   void apply_scale() {
@@ -425,7 +426,7 @@ inline int run_visual_ba(const Config& cfg, const std::vector<Cloud*>& pl_fulls,
   // BuildTracksAndFuse3D
   lvba_fuse_opts fo;
   lvba_fuse_default_opts(&fo);
-  fo.min_view_angle_deg = cfg.min_view_angle; fo.reproj_mean_thr_px = cfg.reproj_mean_thr;
+  fo.min_view_angle_deg = cfg.min_view_angle; fo.reproj_mean_thr_px = cfg.reproj_mean_thr; fo.map_order = cfg.fuse_map_order;
   rc = build_tracks_and_fuse_3d(all_keypoints, all_matches, res.Rcw_after, res.tcw_after, cfg.fx, cfg.fy, cfg.cx, cfg.cy, cfg.d0, cfg.d1, cfg.d2, cfg.d3,
                                 kp_Xw, kp_valid, res.tracks, &fo, &res.fuse);
   if (rc != LVBA_OK) { if (err) *err = std::string("track fusion: ") + lvba_last_error(); return rc; }

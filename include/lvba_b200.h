@@ -389,7 +389,11 @@ int lvba_tracks_mean_reproj(int64_t n_tracks, const int64_t* obs_ptr, const int3
  * (1 depth, 2 triangulation) and its mean reprojection error.  The (image, keypoint, inlier)
  * lists are the observation CSR of lvba_visual_lm once the inliers are kept (:1610-1617).
  * Where the reference iterates std::unordered_map<int,int> (unspecified order: the greedy
- * view-angle filter depends on it) the images of a component are visited in ascending id.
+ * view-angle filter depends on it, and with it which tracks survive) the images of a component are
+ * visited in ascending id (map_order = LVBA_FUSE_ORDER_ASCENDING, the default: independent of any C++
+ * library) or in the order GNU libstdc++'s container has after the reference's reserve() / insert
+ * calls (LVBA_FUSE_ORDER_LIBSTDCXX: what a g++ build of the reference does; with it the stage
+ * reproduces the reference's own source track for track, tests/test_ref_system_pin.py).
  * ====================================================================================== */
 typedef struct lvba_fuse_opts {
   int32_t obser_thr;              /* minimum members / images / survivors (lvba_system.h:139: 3) */
@@ -397,7 +401,10 @@ typedef struct lvba_fuse_opts {
   double reproj_mean_thr_px;      /* track_fusion/reproj_mean_thr (3) */
   double depth_gate_m;            /* distance to the anchor's depth point (0.12, :1050) */
   int32_t device;                 /* -1: current */
+  int32_t map_order;              /* LVBA_FUSE_ORDER_*: visiting order of the three unordered_map loops (:1057, :1069, :1124) */
 } lvba_fuse_opts;
+#define LVBA_FUSE_ORDER_ASCENDING 0
+#define LVBA_FUSE_ORDER_LIBSTDCXX 1
 typedef struct lvba_fuse_summary {
   int64_t n_keypoints, n_components, n_candidates, n_tracks, n_depth_selected, n_tri_selected;
   int64_t n_rounds, n_attempts;   /* retries: a failed component is tried again from its next keypoint as BFS seed (:1199) */

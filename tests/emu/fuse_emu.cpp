@@ -17,9 +17,9 @@ static fuse::Result g_res;
 extern "C" long long fuse_emu_run(int n_images, const long long* kp_ptr, const float* kp_uv, long long n_matches, const int* ma_img, const int* ma_kp,
                                   const int* mb_img, const int* mb_kp, const double* cams, const double* intr, const double* kp_Xw,
                                   const unsigned char* kp_valid, int obser_thr, double min_view_angle_deg, double reproj_thr, double depth_gate,
-                                  long long* counts) {
+                                  long long* counts, int map_order) {
   HostExec ex;
-  fuse::Params prm{obser_thr, std::cos(min_view_angle_deg * M_PI / 180.0), reproj_thr, depth_gate};
+  fuse::Params prm{obser_thr, std::cos(min_view_angle_deg * M_PI / 180.0), reproj_thr, depth_gate, map_order};
   static_assert(sizeof(long long) == sizeof(int64_t), "");
   const int rc = fuse::run(ex, n_images, (const int64_t*)kp_ptr, kp_uv, n_matches, ma_img, ma_kp, mb_img, mb_kp, cams, intr, kp_Xw, kp_valid, prm, g_res);
   if (rc != 0) return -1;

@@ -30,7 +30,7 @@ def emu(tmp_path_factory):
     return lib
 
 
-def run_emu(emu, s, obser_thr=3, angle=8.0, thr=3.0, gate=0.12):
+def run_emu(emu, s, obser_thr=3, angle=8.0, thr=3.0, gate=0.12, map_order=0):
     c = lambda a, t: a.ctypes.data_as(ctypes.POINTER(t))
     m = np.ascontiguousarray(s["matches"], np.int32)
     ma_i, ma_k, mb_i, mb_k = (np.ascontiguousarray(m[:, q]) for q in range(4))
@@ -40,7 +40,7 @@ def run_emu(emu, s, obser_thr=3, angle=8.0, thr=3.0, gate=0.12):
     intr = np.ascontiguousarray(s["intr"], np.float64)
     n = emu.fuse_emu_run(len(kp_ptr) - 1, c(kp_ptr, ctypes.c_longlong), c(uv, ctypes.c_float), ctypes.c_longlong(len(m)), c(ma_i, ctypes.c_int), c(ma_k, ctypes.c_int),
                          c(mb_i, ctypes.c_int), c(mb_k, ctypes.c_int), c(cams, ctypes.c_double), c(intr, ctypes.c_double), c(X, ctypes.c_double),
-                         c(va, ctypes.c_ubyte), obser_thr, ctypes.c_double(angle), ctypes.c_double(thr), ctypes.c_double(gate), c(counts, ctypes.c_longlong))
+                         c(va, ctypes.c_ubyte), obser_thr, ctypes.c_double(angle), ctypes.c_double(thr), ctypes.c_double(gate), c(counts, ctypes.c_longlong), ctypes.c_int(map_order))
     assert n >= 0
     n_obs = int(counts[0])
     obs_ptr = np.zeros(n + 1, np.int64); img = np.zeros(n_obs, np.int32); kp = np.zeros(n_obs, np.int32); inl = np.zeros(n_obs, np.uint8)
@@ -48,6 +48,23 @@ def run_emu(emu, s, obser_thr=3, angle=8.0, thr=3.0, gate=0.12):
     emu.fuse_emu_export(c(obs_ptr, ctypes.c_longlong), c(img, ctypes.c_int), c(kp, ctypes.c_int), c(inl, ctypes.c_ubyte), c(Xw, ctypes.c_double),
                         c(src, ctypes.c_ubyte), c(mean, ctypes.c_double), c(seed, ctypes.c_longlong))
     return dict(obs_ptr=obs_ptr, img=img, kp=kp, inlier=inl, Xw=Xw, source=src, mean=mean, seed=seed, counts=counts)
+
+
+@pytest.mark.parametrize("seed,kw", [(0, {}), (1, dict(wrong=0.15)), (3, dict(bad_depth=0.3, px_noise=1.2)), (4, dict(n_images=30, n_points=300)),
+                                     (7, dict(n_images=45, n_points=200, wrong=0.1))])
+def test_fusion_in_the_container_order_of_a_gxx_build_matches_the_oracle(emu, seed, kw):
+    """map_order = LVBA_FUSE_ORDER_LIBSTDCXX: the three unordered_map loops in GNU libstdc++'s order (more images than buckets in the larger
+    scenes: colliding keys share a bucket run).  The oracle under the same order is what reproduces the reference's own source
+    (tests/test_ref_system_pin.py)."""
+    s = fuse_scene.make(seed=seed, **kw)
+    ref = fo.fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"], map_order=fo.libstdcxx_order)
+    asc = fo.fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"])
+    got = run_emu(emu, s, map_order=1)
+    compare(got, ref)
+    assert len(ref) > 0
+    if seed in (1, 4, 7):                                                        # the order is not a formality: other inliers, other points
+        same = len(asc) == len(ref) and all(np.array_equal(a["inlier"], b["inlier"]) and np.array_equal(a["obs"], b["obs"]) for a, b in zip(asc, ref))
+        assert not same
 
 
 def compare(got, ref):

@@ -188,6 +188,31 @@ def test_track_fusion_equals_reference_source_under_its_container_order():
         assert np.abs(t["Xw"] - G["F_Xw"][k]).max() <= 1e-12, k
 
 
+def test_device_fusion_pass_equals_reference_source_under_its_container_order(tmp_path_factory):
+    """csrc/fuse_pipeline.h (host component walk + rounds + the per-component device functor) through the host policy with
+    map_order = LVBA_FUSE_ORDER_LIBSTDCXX against what the reference's own BuildTracksAndFuse3D produced."""
+    import ctypes
+    import subprocess
+    import test_fuse_emu
+    so = tmp_path_factory.mktemp("emu_ref_fuse") / "libfuse_emu.so"
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "fuse_emu.cpp"), "-o", str(so)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = ctypes.CDLL(str(so)); lib.fuse_emu_run.restype = ctypes.c_longlong
+    kp_ptr, kp_uv, matches, cams, intr, Xw, valid = fuse_inputs()
+    got = test_fuse_emu.run_emu(lib, dict(kp_ptr=kp_ptr, kp_uv=kp_uv, matches=matches, cams=cams, intr=intr, kp_Xw=Xw, kp_valid=valid), map_order=1)
+    assert len(got["seed"]) == len(G["F_Xw"]) == 70
+    for k in range(70):
+        a, b = got["obs_ptr"][k], got["obs_ptr"][k + 1]
+        ob = G["F_obs"][G["F_obs_ptr"][k]:G["F_obs_ptr"][k + 1]]
+        assert np.array_equal(np.column_stack([got["img"][a:b], got["kp"][a:b]]), ob), k
+        inl = np.zeros(b - a, bool); inl[G["F_inl"][G["F_inl_ptr"][k]:G["F_inl_ptr"][k + 1]]] = True
+        assert np.array_equal(got["inlier"][a:b].astype(bool), inl), k
+        assert np.abs(got["Xw"][k] - G["F_Xw"][k]).max() <= 1e-9, k
+    asc = test_fuse_emu.run_emu(lib, dict(kp_ptr=kp_ptr, kp_uv=kp_uv, matches=matches, cams=cams, intr=intr, kp_Xw=Xw, kp_valid=valid), map_order=0)
+    assert len(asc["seed"]) == 63                                                  # the documented default order: another answer on this scene
+
+
 def test_ascending_order_is_a_different_but_documented_choice():
     """What the ABI documents (ascending image id) against what the reference's container does under g++: same logic, other visiting order."""
     tr = fo.fuse(*fuse_inputs())

@@ -138,3 +138,38 @@ def test_device_reproduces_what_the_reference_pipeline_source_computed():
     documented ascending order (tests/test_ref_system_pin.py::test_ascending_order_is_a_different_but_documented_choice)."""
     r = subprocess.run([sys.executable, "-c", CODE_SYSTEM], capture_output=True, text=True, timeout=300, cwd=str(ROOT))
     assert r.returncode == 0 and "CHILD-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+
+
+CODE_FUSE = """
+import sys
+import numpy as np
+sys.path.insert(0, %r)
+import __graft_entry__ as graft
+from oracle import depth_oracle as dep
+pkg = graft.load_package(); pkg.load_library()
+assert pkg.device_count() >= 1
+G = np.load(%r)
+kp_ptr, kp_uv = G["F_kp_ptr"], G["F_kp_uv"]
+Xw, valid = dep.backproject(list(G["F_depth"]), G["F_cams"], G["F_intr"], kp_ptr, kp_uv)      # equals the reference's depth candidates bit for bit (CPU test)
+t = pkg.tracks_fuse(kp_ptr, kp_uv, G["F_matches"], G["F_cams"], G["F_intr"], Xw, valid, map_order=pkg.FUSE_ORDER_LIBSTDCXX)
+assert t["summary"]["n_tracks"] == len(G["F_Xw"]) == 70 and t["summary"]["kernel_launches"] > 0
+assert np.array_equal(t["obs_ptr"], G["F_obs_ptr"])
+assert np.array_equal(np.column_stack([t["img"], t["kp"]]), G["F_obs"])                        # same tracks, same order, same member order
+inl = np.zeros(len(t["img"]), bool)
+for k in range(70):
+    inl[G["F_obs_ptr"][k] + G["F_inl"][G["F_inl_ptr"][k]:G["F_inl_ptr"][k + 1]]] = True
+assert np.array_equal(t["inlier"].astype(bool), inl)
+assert np.abs(t["Xw"] - G["F_Xw"]).max() <= 1e-9
+a = pkg.tracks_fuse(kp_ptr, kp_uv, G["F_matches"], G["F_cams"], G["F_intr"], Xw, valid)         # the documented default order: another answer here
+assert a["summary"]["n_tracks"] == 63
+print('CHILD-OK')
+""" % (str(ROOT), str(ROOT / "tests" / "golden" / "ref_system.npz"))
+
+
+@pytest.mark.gpu
+def test_device_track_fusion_reproduces_the_reference_source_under_its_container_order():
+    """B7 with lvba_fuse_opts::map_order = LVBA_FUSE_ORDER_LIBSTDCXX against the reference's own BuildTracksAndFuse3D (tests/golden/ref_system.npz):
+    track order, member order, inlier sets, fused points.  CPU twin through the host policy:
+    tests/test_ref_system_pin.py::test_device_fusion_pass_equals_reference_source_under_its_container_order."""
+    r = subprocess.run([sys.executable, "-c", CODE_FUSE], capture_output=True, text=True, timeout=300, cwd=str(ROOT))
+    assert r.returncode == 0 and "CHILD-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])

@@ -17,6 +17,8 @@
 //                matches of the COLMAP database (--db FILE, default <data>/<data_config/colmap_db_path>), and write the COLMAP text
 //                model <data>/Colmap/sparse/{images,points3D}.txt (--sparse-dir DIR) — global-lvba_b200/host/lvba_visual_offline.hpp
 //   --no-lidar   data_config/enable_lidar_ba = false: the visual stage starts from the odometry poses
+//   --fuse-order ascending|libstdcxx   visiting order of the track fusion's three unordered_map loops (lvba_fuse_opts::map_order): ascending image
+//                id (default, library independent) or the order of a g++ build of the reference
 //   --lidar-opt F   skip the LiDAR stage and take its result from F (TUM lines, one per scan — what a previous run wrote)
 //   --check --visual   also load images, image poses and the database, and print their summary and the updated camera poses' checksum
 #include <cstdio>
@@ -37,6 +39,7 @@ int main(int argc, char** argv) {
   double voxel[2] = {0.5, 0.5};                                              // BALM_stage1/2 root_voxel_size defaults (dataset_io.cpp:55-57)
   float eigen[2][4] = {{0.3f, 0.1f, 0.06f, 0.03f}, {0.3f, 0.1f, 0.06f, 0.03f}};   // bavoxel.hpp:17
   bool stage1 = true, check = false, window_rel = false, visual = false, lidar = true, have_config = false;
+  int fuse_order = LVBA_FUSE_ORDER_ASCENDING;
   int window = 0;
   double anchor_leaf = 0.1;
   std::string db_path, sparse_dir, lidar_opt;
@@ -57,6 +60,7 @@ int main(int argc, char** argv) {
     else if (a == "--check") check = true;
     else if (a == "--visual") visual = true;
     else if (a == "--no-lidar") lidar = false;
+    else if (a == "--fuse-order") { const std::string v = next(); if (v == "libstdcxx") fuse_order = LVBA_FUSE_ORDER_LIBSTDCXX; else if (v == "ascending") fuse_order = LVBA_FUSE_ORDER_ASCENDING; else return 64; }
     else if (a == "--db") db_path = next();
     else if (a == "--lidar-opt") lidar_opt = next();
     else if (a == "--sparse-dir") sparse_dir = next();
@@ -181,6 +185,7 @@ int main(int argc, char** argv) {
   }
   const float default_eigen[4] = {0.3f, 0.1f, 0.06f, 0.03f};                  // bavoxel.hpp:17 when set_eigen_ratio_array never ran
   off::VisualResult vr;
+  cfg.fuse_map_order = fuse_order;
   const int vrc = off::run_visual_ba(cfg, frame_clouds, frames, frames_before, images_ids, image_poses, keypoints, matches,
                                      lidar ? eigen[1] : default_eigen, vr, &err);
   if (vrc != LVBA_OK) { std::fprintf(stderr, "visual stage failed (%d): %s\n", vrc, err.c_str()); return vrc == LVBA_ERR_NO_DEVICE ? 2 : 1; }
