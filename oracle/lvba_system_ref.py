@@ -59,9 +59,18 @@ class System:
     """One lvba::LvbaSystem.  Parameters of the ROS parameter server the constructor reads can be given as `params`."""
 
     def __init__(self, params=None):
+        """params: {name: number | str | list of numbers} — the ROS parameter server the constructors read (src/dataset_io.cpp:28-58,
+        src/lvba_system.cpp:127-133).  With data_config/data_path naming a dataset directory the reference's own loader fills the system."""
         self.lib = load()
+        self.lib.sys_clear_params()
         for k, v in (params or {}).items():
-            self.lib.sys_set_param(k.encode(), C.c_double(float(v)))
+            if isinstance(v, str):
+                self.lib.sys_set_param_str(k.encode(), v.encode())
+            elif isinstance(v, (list, tuple, np.ndarray)):
+                a = np.ascontiguousarray(v, np.float64).ravel()
+                self.lib.sys_set_param_vec(k.encode(), C.c_int(len(a)), _p(a))
+            else:
+                self.lib.sys_set_param(k.encode(), C.c_double(float(v)))
         self.h = C.c_void_p(self.lib.sys_create())
         self.W = 0; self.M = 0; self.width = 0; self.height = 0; self.n_points = 0
 
@@ -71,6 +80,18 @@ class System:
 
     def __del__(self):
         self.close()
+
+    def dataset(self):
+        """What DatasetIO's constructor loaded: dict(frame_ts, frame_poses, scans, intensity, image_ts, image_poses, cam, data_path, db_path)."""
+        nf = C.c_int64(); npt = C.c_int64(); ni = C.c_int64()
+        self.lib.sys_dataset_sizes(self.h, C.byref(nf), C.byref(npt), C.byref(ni))
+        nf, npt, ni = nf.value, npt.value, ni.value
+        fts = np.zeros(nf); fp = np.zeros((nf, 12)); sp = np.zeros(nf + 1, np.int64); xyz = np.zeros((npt, 3), np.float32); inten = np.zeros(npt, np.float32)
+        its = np.zeros(ni); ip = np.zeros((ni, 12)); cam = np.zeros(12); paths = C.create_string_buffer(4096)
+        self.lib.sys_dataset_get(self.h, _p(fts), _p(fp), _p(sp), _p(xyz), _p(inten), _p(its), _p(ip), _p(cam), paths)
+        dp, db = paths.value.decode().split("\n")
+        return dict(frame_ts=fts, frame_poses=fp, scans=[xyz[sp[i]:sp[i + 1]] for i in range(len(sp) - 1)], intensity=inten, image_ts=its, image_poses=ip,
+                    cam=cam, data_path=dp, db_path=db)
 
     # ---- inputs
     def set_lidar(self, scans, poses, ts=None):

@@ -68,6 +68,7 @@ class Mat {
 template <typename T> using Ptr = std::shared_ptr<T>;
 struct CLAHE { void apply(const Mat&, Mat&) { std::abort(); } };
 template <typename T> class Mat_ : public Mat { public: Mat_() {} Mat_(int r, int c) : Mat(r, c, CV_64F) {}
+  static Mat_ eye(int r, int c) { return Mat_(r, c); }
   T& operator()(int y, int x) { return this->template at<T>(y, x); }
   template <typename S> Mat_& operator<<(S) { return *this; } template <typename S> Mat_& operator,(S) { return *this; } };
 enum { INTER_LINEAR = 1, INTER_CUBIC = 2, COLOR_BGR2Lab = 44, COLOR_Lab2BGR = 56, COLOR_BGR2GRAY = 6, COLOR_GRAY2BGR = 8, IMREAD_COLOR = 1, IMREAD_GRAYSCALE = 0, IMREAD_UNCHANGED = -1,

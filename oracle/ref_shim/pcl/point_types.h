@@ -15,6 +15,11 @@ struct PointXYZRGB {
   PointXYZRGB() : data{0, 0, 0, 1}, b(0), g(0), r(0), a(255) {}
 };
 struct PointXYZRGBA : PointXYZRGB {};
+struct PointXYZI {
+  union { float data[4]; struct { float x, y, z; }; };
+  float intensity;
+  PointXYZI() : data{0, 0, 0, 1}, intensity(0) {}
+};
 struct PointXYZ {
   union { float data[4]; struct { float x, y, z; }; };
   PointXYZ() : data{0, 0, 0, 1} {}

@@ -8,6 +8,7 @@ class SE3 {
  public:
   SE3() : R_(Eigen::Matrix3d::Identity()) {}
   SE3(const Eigen::Matrix3d& R, const Eigen::Vector3d& t) : R_(R), t_(t) {}
+  SE3(const Eigen::Quaterniond& q, const Eigen::Vector3d& t) : R_(q.toRotationMatrix()), t_(t) {}
   Eigen::Matrix3d rotation_matrix() const { return R_; }
   const Eigen::Vector3d& translation() const { return t_; }
   Eigen::Vector3d& translation() { return t_; }

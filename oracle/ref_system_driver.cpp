@@ -10,8 +10,9 @@
 // the BALM / utils headers they call.  ROS, PCL, OpenCV, Ceres, Sophus, SiftGPU and Eigen resolve to the stand-ins under
 // oracle/ref_shim/ (own code; NOT those libraries): publishers swallow their messages, image files are not written, and
 // ceres::Problem RECORDS the problem optimizeCameraPoses builds and hands it to the hook below instead of solving it.  SQLite is the
-// system's libsqlite3.so.0 (declarations in ref_shim/sqlite3.h).  src/dataset_io.cpp (file loading) is not compiled: DatasetIO's
-// constructor is defined here as "defaults only" and the driver fills the public fields the pipeline reads.
+// system's libsqlite3.so.0 (declarations in ref_shim/sqlite3.h).  src/dataset_io.cpp (the dataset loader) is included the same way; its PCD
+// files go through the stand-in reader of ref_shim/pcl/io/pcd_io.h (NOT PCL's parser).  LvbaSystem's constructor runs the loader on the
+// parameter table's data path; the driver's setters then overwrite the public fields for the tests that bring their own arrays.
 //
 // What a fixture made with this pins: the reference's own sequencing and arithmetic of the stages named above (skip rule, anchors,
 // relative poses, the two global stages, depth splatting, the match graph / component walk / candidate choice of the track fusion,
@@ -20,17 +21,14 @@
 // (the tests use the restated Ceres loop of oracle/visual_oracle.py) and writes the answer back into the reference's parameter blocks,
 // after which the reference's own code carries on.  No algorithm lives in this file.
 #include REF_SYSTEM_CPP
+#ifndef ROOT_DIR
+#define ROOT_DIR ""          // CMakeLists.txt:13 prefixes data_config/data_path with the package directory; the tests pass absolute paths
+#endif
+#include REF_DATASET_CPP
 
 #include <cstdint>
 #include <sstream>
 
-namespace lvba {
-// src/dataset_io.cpp is not compiled (PCL / OpenCV file readers); only the constructor is referenced by LvbaSystem.
-DatasetIO::DatasetIO(ros::NodeHandle&) {
-  width_ = height_ = 0; fx_ = fy_ = cx_ = cy_ = k1_ = k2_ = p1_ = p2_ = 0; resize_scale_ = 1.0; image_stride_ = 1;
-}
-void DatasetIO::undistortImage(const cv::Mat&, cv::Mat&) { std::abort(); }
-}  // namespace lvba
 
 namespace {
 
@@ -108,6 +106,31 @@ void sys_destroy(void* h) { delete static_cast<Sys*>(h); }
 // optimizeCameraPoses inherits whatever the last stage left there.  Tests that run the camera half alone state it explicitly.
 void sys_set_eigen_ratio_array(const float* r) { set_eigen_ratio_array({r[0], r[1], r[2], r[3]}); }
 void sys_set_param(const char* name, double v) { ros::ParamValue p; p.num = v; ros::param_table()[name] = p; }
+void sys_set_param_str(const char* name, const char* v) { ros::ParamValue p; p.str = v; ros::param_table()[name] = p; }
+void sys_set_param_vec(const char* name, int n, const double* v) { ros::ParamValue p; p.vec.assign(v, v + n); ros::param_table()[name] = p; }
+void sys_clear_params() { ros::param_table().clear(); }
+// what DatasetIO's constructor loaded (src/dataset_io.cpp): sizes, then the arrays
+void sys_dataset_sizes(void* h, int64_t* n_frames, int64_t* n_points, int64_t* n_images) {
+  auto& d = *static_cast<Sys*>(h)->s->dataset_io_;
+  *n_frames = (int64_t)d.x_buf_.size(); *n_images = (int64_t)d.images_ids_.size(); *n_points = 0;
+  for (auto& pl : d.pl_fulls_) *n_points += (int64_t)pl->size();
+}
+void sys_dataset_get(void* h, double* frame_ts, double* frame_poses, int64_t* scan_ptr, float* xyz, float* intensity, double* image_ts, double* image_poses,
+                     double* cam /* width height fx fy cx cy k1 k2 p1 p2 scale stride */, char* paths /* data path \n db path, 4096 */) {
+  auto& d = *static_cast<Sys*>(h)->s->dataset_io_;
+  for (size_t i = 0; i < d.x_buf_.size(); ++i) { frame_ts[i] = d.x_buf_[i].t; pose_out(d.x_buf_[i].R, d.x_buf_[i].p, frame_poses + 12 * i); }
+  int64_t o = 0;
+  scan_ptr[0] = 0;
+  for (size_t i = 0; i < d.pl_fulls_.size(); ++i) {
+    for (auto& p : d.pl_fulls_[i]->points) { xyz[3 * o] = p.x; xyz[3 * o + 1] = p.y; xyz[3 * o + 2] = p.z; intensity[o] = p.intensity; ++o; }
+    scan_ptr[i + 1] = o;
+  }
+  for (size_t k = 0; k < d.images_ids_.size(); ++k) image_ts[k] = d.images_ids_[k];
+  for (size_t k = 0; k < d.image_poses_.size(); ++k) pose_out(d.image_poses_[k].rotation_matrix(), d.image_poses_[k].translation(), image_poses + 12 * k);
+  const double c[12] = {(double)d.width_, (double)d.height_, d.fx_, d.fy_, d.cx_, d.cy_, d.k1_, d.k2_, d.p1_, d.p2_, d.resize_scale_, (double)d.image_stride_};
+  for (int j = 0; j < 12; ++j) cam[j] = c[j];
+  std::snprintf(paths, 4096, "%s\n%s", d.dataset_path_.c_str(), d.colmap_db_path_.c_str());
+}
 
 // ---------------------------------------------------------------------------------------------- inputs (public fields of DatasetIO)
 void sys_set_lidar(void* h, int W, const int64_t* scan_ptr, const float* xyz, const double* poses, const double* ts) {

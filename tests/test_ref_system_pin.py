@@ -310,3 +310,40 @@ def test_reference_reader_reads_the_database_the_dataset_writer_writes():
             if ka < len(g["keypoints"][a]) and kb < len(g["keypoints"][b])]
     dropped = sum(len(v) for v in g["pair"].values()) - len(want)
     assert dropped == 1 and np.array_equal(m, np.array(want, np.int32))
+
+
+# ------------------------------------------------------------------------------------------------ N4: the dataset loader
+@needs_ref
+def test_reference_loader_reads_the_dataset_the_dataset_writer_writes():
+    """DatasetIO's constructor (src/dataset_io.cpp, run from its own source; PCD files through the stand-in reader of oracle/ref_shim/pcl/io/pcd_io.h,
+    which has no LZF: the compressed scans of the writer are rewritten uncompressed) on the directory oracle/dataset_writer.py lays out — the layout
+    tests/test_dataset_loader.py holds the product's loader (global-lvba_b200/host/lvba_dataset.hpp) against.  Pins: frame timestamps come from the
+    file NAMES (:228-233), TUM lines with a comment, an empty and an unparsable line and un-normalised quaternions (:137-180), images = every
+    image_sample_step-th file by timestamp and the same stride over the VALID pose lines (:118-121, :159), intrinsics scaled by cam_model/scale (:59-62),
+    colmap_db_path appended to the data path (:65)."""
+    from oracle import dataset_writer as dw
+    root = Path(tempfile.mkdtemp())
+    scans, poses = synth.make_scan_scene(3, W=7, n_per_scan=900)
+    scans[4] = scans[4][:0]                                              # an empty scan file
+    ts = dw.write_lidar_dataset(root, scans, poses)
+    for i in range(len(scans)):
+        if i % 3 == 2:
+            dw.write_pcd(root / "all_pcd_body" / f"{ts[i]:.6f}.pcd", scans[i], np.arange(len(scans[i])) % 7, "binary")
+    (root / "all_pcd_body" / "notes.txt").write_text("ignored")
+    image_ts = [t + 0.013 for t in ts]
+    image_poses = poses.copy(); image_poses[:, 9:] += np.random.default_rng(1).normal(0, 0.02, (7, 3))
+    dw.write_image_set(root, image_ts, image_poses, extra_between=1)
+    S = sr.System({"data_config/data_path": str(root) + "/", "data_config/colmap_db_path": "Colmap/colmap.db", "data_config/image_sample_step": 2,
+                   "cam_model/cam_width": 160, "cam_model/cam_height": 128, "cam_model/scale": 0.5, "cam_model/cam_fx": 96.0, "cam_model/cam_fy": 96.3,
+                   "cam_model/cam_cx": 79.7, "cam_model/cam_cy": 64.2})
+    d = S.dataset()
+    S.close()
+    assert d["data_path"] == str(root) + "/" and d["db_path"] == str(root) + "/Colmap/colmap.db"
+    assert d["cam"][:6].tolist() == [80.0, 64.0, 48.0, 48.15, 39.85, 32.1] and d["cam"][10:].tolist() == [0.5, 2.0]
+    assert np.array_equal(d["frame_ts"], np.array(ts))                   # from the names: the TUM file's own timestamps (0, 1, 2 ...) are ignored
+    assert [len(s) for s in d["scans"]] == [len(s) for s in scans] and all(np.array_equal(a, b) for a, b in zip(d["scans"], scans))
+    assert np.array_equal(d["intensity"], np.concatenate([np.arange(len(s)) % 7 for s in scans]).astype(np.float32))
+    rt = lambda P: np.array([np.r_[dw.quat_to_R(dw.R_to_quat(p[:9].reshape(3, 3))).ravel(), p[9:]] for p in P])  # noqa: E731
+    assert np.abs(d["frame_poses"] - rt(poses)).max() <= 1e-11            # 15-digit text, quaternion normalised on reading (:165-166)
+    assert np.abs(d["image_ts"] - np.array(image_ts)).max() <= 1e-9 and len(d["image_ts"]) == 7      # 14 files, every second one
+    assert np.abs(d["image_poses"] - rt(image_poses)).max() <= 1e-11      # the skipped lines carry poses 100 m away: none of them was taken
