@@ -74,6 +74,9 @@ def generate():
     S = sr.System()
     S.set_lidar(scans, noisy)
     S.set_stages(True, win, 0.1, True, True, 1.0, o["L_s1_ratio"], 1.0, o["L_s2_ratio"])
+    _, ac_rel, o["L_rel_poses_rel"], _ = S.run_window_ba()          # rel = anchor^-1 * (window-LM pose aligned to the anchor): the window solves, frame by frame
+    o["L_anchor_clouds_rel_sorted"] = np.concatenate([lex(c) for c in ac_rel])
+    sr.set_eigen_ratio_array(DEFAULT_RATIO)
     o["L_final_poses_rel"] = S.run_lidar_ba()
     S.close()
 

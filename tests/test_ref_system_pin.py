@@ -102,6 +102,13 @@ def test_window_stage_anchor_bookkeeping_equals_reference_source():
     assert len(clouds) == len(ref_clouds) == 2
     for c, r in zip(clouds, ref_clouds):
         assert np.array_equal(lex(c), r)                                                                   # float32 points, bit for bit
+    # use_window_ba_rel: the relative poses now carry the window solves themselves (damping_iter per window, aligned to the anchor)
+    _, rel_w, clouds_w, _ = lidar_chain(True)
+    assert np.abs(rel_w - G["L_rel_poses_rel"]).max() <= 1e-10 and np.abs(G["L_rel_poses_rel"] - G["L_rel_poses"]).max() > 1e-3
+    assert np.array_equal(rel_w[3:6], np.tile(np.r_[np.eye(3).ravel(), np.zeros(3)], (3, 1)))               # skipped window: IMUST() stays
+    got = np.concatenate([lex(c) for c in clouds_w])
+    assert got.shape == G["L_anchor_clouds_rel_sorted"].shape
+    assert np.mean(np.all(got == G["L_anchor_clouds_rel_sorted"], axis=1)) > 0.99                           # float32 of poses equal to 1e-11: a last-bit flip here and there
     assert np.array_equal(G["L_anchor_poses"], G["L_poses"][[0, 6]])                                        # anchors keep the odometry pose (:283)
 
 

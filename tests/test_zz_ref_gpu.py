@@ -127,6 +127,26 @@ keep = [0, 1, 2, 6, 7, 8]
 clouds = pkg.anchor_clouds([scans[i] for i in keep], G["L_rel_poses"][keep], np.array([0, 3, 6], np.int32), float(G["L_anchor_leaf"]))
 for c, r in zip(clouds, split(G["L_anchor_clouds_sorted"], G["L_anchor_cloud_ptr"])):
     assert np.array_equal(lex(c), r)
+# ---- N1: the window stage of runWindowBA (:232-279) — one voxel map and one damping_iter per window, batched on the device, the
+# 3-voxels-per-pose skip rule — against the window solves the reference's own code produced (use_window_ba_rel: rel = anchor^-1 * aligned pose)
+W, win = len(scans), int(G["L_window"])
+win_ptr = np.array(list(range(0, W, win)) + [W], np.int32)
+m = pkg.VoxelMap(scans, G["L_poses"], float(G["L_s1_voxel"]), (0.3, 0.1, 0.06, 0.03), win_ptr=win_ptr)     # bavoxel.hpp:17's ratios are in force here
+solved, sums, tot = m.lidar_lm_batch(G["L_poses"], min_voxels_per_pose=3)
+m.close()
+rel = np.zeros((W, 12)); rel[:, [0, 4, 8]] = 1.0
+for w in range(len(win_ptr) - 1):
+    a, b = int(win_ptr[w]), int(win_ptr[w + 1])
+    if np.array_equal(solved[a:b], G["L_poses"][a:b]):
+        continue                                              # a skipped window keeps its poses and gets no anchor (:259-263)
+    Ro, po = G["L_poses"][a, :9].reshape(3, 3), G["L_poses"][a, 9:]
+    R_align = Ro @ solved[a, :9].reshape(3, 3).T; p_align = po - R_align @ solved[a, 9:]              # :267-279
+    for j in range(a, b):
+        Rj = R_align @ solved[j, :9].reshape(3, 3); pj = R_align @ solved[j, 9:] + p_align
+        rel[j, :9] = (Ro.T @ Rj).ravel(); rel[j, 9:] = Ro.T @ (pj - po)                                # :286-289
+assert np.array_equal(rel[3:6], G["L_rel_poses_rel"][3:6])     # the middle window was skipped on the device too
+assert np.abs(rel - G["L_rel_poses_rel"]).max() <= 1e-6, np.abs(rel - G["L_rel_poses_rel"]).max()
+assert tot["kernel_launches"] > 0
 print('CHILD-OK')
 """ % (str(ROOT), str(ROOT / "tests" / "golden" / "ref_system.npz"))
 
