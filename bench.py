@@ -170,7 +170,8 @@ def run_reference(args, p, cfg):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": max(ta, tb), "threads_path_A": ta, "threads_path_B": tb,
                              "host_hardware_threads": hw, "kind": "port", "thread_sweep_ms_per_pass": sweep,
                              "sample": "each step = 1 full LM pass of path A + 1 of path B on the full problem (oracle/cpu_ref.cpp: the reference "
-                                       "restated; Eigen/Ceres are not installable here)"},
+                                       "restated; Eigen/Ceres are not installable here)",
+                             "why_port": "the reference's own source does compile (oracle/_ref, on stand-in library headers) and the port is held against it — H 4.6e-11, g 1.3e-11 at this config, the whole damping_iter at config B (profiles/r02_ref_pin_scale_*.txt) — but BALM2::damping_iter as written keeps vector<PointCluster>(win_size) per voxel and 19 dense 6W x 6W matrices: 42 GB + 22 GB and minutes per pass at 2000 poses, on our eager stand-in for Eigen; the port (CSR slots, block envelope, the reference's thread model) is the faster, fairer opponent"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "calls_timed": n_calls, **info,
                     "step": "one full call of each boundary to the reference's caps (<= 10 / <= 50 passes), time / passes executed"},
             "gpu_launches": 0}
@@ -435,7 +436,8 @@ def main():
             line["cpu_baseline"] = {"value": 1e3 / (tA + tB), "unit": UNIT, "cores": max(ta_, tb_), "threads_path_A": ta_, "threads_path_B": tb_,
                                     "host_hardware_threads": hw, "kind": "port", "thread_sweep_ms_per_pass": sweep,
                                     "sample": "1 full LM pass of path A + 1 of path B on the full problem (oracle/cpu_ref.cpp) at the fastest thread "
-                                              "count of the sweep (the reference's fixed 16 included)", "ms_A": tA, "ms_B": tB}
+                                              "count of the sweep (the reference's fixed 16 included)", "ms_A": tA, "ms_B": tB,
+                                    "why_port": "the reference's own source does compile (oracle/_ref, on stand-in library headers) and the port is held against it — H 4.6e-11, g 1.3e-11 at this config, the whole damping_iter at config B (profiles/r02_ref_pin_scale_*.txt) — but BALM2::damping_iter as written keeps vector<PointCluster>(win_size) per voxel and 19 dense 6W x 6W matrices: 42 GB + 22 GB and minutes per pass at 2000 poses, on our eager stand-in for Eigen; the port (CSR slots, block envelope, the reference's thread model) is the faster, fairer opponent"}
             if not args.no_parity:
                 # north-star check at the benchmarked config: full LM (caps 10 / 50) on the GPU against the CPU restatement
                 from oracle import cpu_ref
