@@ -5,7 +5,7 @@ The outputs come from oracle/_ref/libbalm_ref.so, i.e. /root/reference/include/B
 stand-ins for the libraries this image lacks (oracle/ref_shim/: own 3x3 eigen-solver, sparse LDL^T, dual numbers — see
 ref_shim/mini_eigen.h for what that does and does not pin).  /root/reference does not exist on the GPU box, so the
 vectors are committed; tests/test_ref_pin.py holds the oracles (numpy and C++) against them and, where the library can
-be built, regenerates them and demands the identical bits; tests/test_zz_ref_gpu.py holds the CUDA path against them.
+be built, regenerates them and demands the identical bits; tests/test_zzz_ref_gpu.py holds the CUDA path against them.
 
 Run from the repo root (only where /root/reference exists):   python tests/golden/make_golden_ref.py
 """

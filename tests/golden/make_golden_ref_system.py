@@ -4,7 +4,7 @@ The outputs come from oracle/_ref/liblvba_system_ref.so: /root/reference/src/lvb
 lies and driven through LvbaSystem's own public members (oracle/ref_system_driver.cpp, `make -C oracle ref`), on the stand-in library
 headers of oracle/ref_shim/ (what they are and what they leave open: ref_shim/mini_eigen.h).  /root/reference does not
 exist on the GPU box, so the vectors are committed; tests/test_ref_system_pin.py holds the oracles and the host-policy runs of the device
-passes against them and regenerates the file bit for bit where the library can be built; tests/test_zz_ref_gpu.py holds the device.
+passes against them and regenerates the file bit for bit where the library can be built; tests/test_zzz_ref_gpu.py holds the device.
 
 Sections:  L  runWindowBA + runLidarBA (window stage with a skipped window, anchors, the two global stages, poses of every frame)
            D  buildGridMapFromOptimized -> updateCameraPosesFromLidar -> generateDepthWithVoxel (after a LiDAR correction)

@@ -12,7 +12,7 @@ is the reference's).  Here, without a GPU:
   4. where oracle/_ref/libbalm_ref.so can be built (this container), the file is regenerated and must come out bit for bit,
      and further seeded problems are compared live (reference source vs oracle) at sizes the fixture does not hold.
 
-The CUDA path is held against the same file in tests/test_zz_ref_gpu.py.  Tolerances: integer / key / count data exact;
+The CUDA path is held against the same file in tests/test_zzz_ref_gpu.py.  Tolerances: integer / key / count data exact;
 float64 sums whose order differs 1e-12 relative; quantities behind the eigen-decomposition of P/N - v v^T (lambda_0, g, H:
 a difference of O(1e2..1e4) terms) 1e-9 relative — observed 1e-11; LM end poses 1e-9 (observed 2e-11).
 """
