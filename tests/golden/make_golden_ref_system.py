@@ -10,6 +10,7 @@ Sections:  L  runWindowBA + runLidarBA (window stage with a skipped window, anch
            D  buildGridMapFromOptimized -> updateCameraPosesFromLidar -> generateDepthWithVoxel (after a LiDAR correction)
            F  BuildTracksAndFuse3D on depth images + keypoints + matches (track order, observation order, inlier order, points)
            P  the Ceres problem optimizeCameraPoses builds (recorded, not solved)
+           V  the whole camera half end to end (reference reader + fusion + problem, the restated Ceres loop in the solver hook): results only
 
 Run from the repo root (only where /root/reference exists):   python tests/golden/make_golden_ref_system.py
 """
@@ -136,6 +137,40 @@ def generate():
         o["P_" + k] = v
     o["P_options"] = rec["options"][:5]                       # [5] is std::thread::hardware_concurrency() of the machine
     o["P_window"] = np.int64(4); o["P_anchor_leaf"] = np.float64(0.1); o["P_voxel"] = np.float64(0.5); o["P_ratio"] = np.array([0.08] * 4, np.float32)
+    # ---------------------------------------------------------------- V: the whole camera half, end to end, on the scene of tests/test_zz_offline_gpu.py
+    # runVisualBAWithLidarAssist (:144-154) with LiDAR BA disabled: grid -> camera poses -> depth -> the reference's own COLMAP reader -> track
+    # fusion -> optimizeCameraPoses; where ceres::Solve stands, the restated Ceres loop (oracle/visual_oracle.py) solves the recorded problem and the
+    # reference's own code writes the result back.  Only results are stored: the test rebuilds the (seeded) scene.
+    from oracle import visual_oracle as vis
+    rootv = Path(tempfile.mkdtemp())
+    gv = vs.make(rootv, seed=3, W=8, n_landmarks=700)
+    S2 = sr.System()
+    S2.set_lidar(gv["scans"], gv["poses"], gv["ts"])
+    S2.set_stages(False, window_size=10, anchor_leaf=0.05, s2_voxel=0.5, s2_ratio=(0.3, 0.1, 0.06, 0.03))     # what write_config_yaml puts in config.yaml
+    S2.set_camera(gv["width"], gv["height"], gv["intr"], vs.RCL.ravel(), vs.PCL, np.eye(3).ravel(), np.zeros(3), np.array(gv["image_ts"]), gv["image_poses"])
+    S2.build_grid(); S2.update_camera_poses()
+    _, c0v, c1v = S2.generate_depth()
+    ok, _, _, _ = S2.load_colmap_db(str(rootv) + "/", rootv / "Colmap" / "colmap.db")
+    assert ok
+    Tv = S2.build_tracks()
+    sr.set_eigen_ratio_array(DEFAULT_RATIO)                    # enable_lidar_ba = false: set_eigen_ratio_array never ran (bavoxel.hpp:17 in force)
+    info = {}
+
+    def solver(P):
+        obs_ptr = np.concatenate([[0], np.cumsum(np.bincount(P["obs_pt"], minlength=len(P["X"])))])
+        nd = np.zeros((len(P["X"]), 4)); nd[P["pl_pt"]] = P["pl_nd"]
+        pr = vis.VisualProblem(P["q"], P["t"], P["X"], nd, obs_ptr, P["obs_cam"], P["obs_uv"].astype(np.float32), P["obs_intr"][0],
+                               float(P["obs_sigma"][0, 0]), float(P["pl_sigma"][0]))
+        info["cost_first"] = pr.cost()
+        pr, lm = vis.ceres_lm(pr, max_iter=int(P["options"][0]))
+        info.update(cost_last=lm["cost"], iters=lm["iters"], points=len(P["X"]))
+        return pr.q, pr.t, pr.X
+
+    _, cams_after = S2.optimize_camera_poses(solver)
+    o["V_cams_before"] = c1v; o["V_cams_after"] = cams_after
+    o["V_counts"] = np.array([len(Tv["Xw"]), info["points"], info["iters"]], np.int64)
+    o["V_costs"] = np.array([info["cost_first"], info["cost_last"]])
+    S2.close()
     # the anchor clouds the surf map of optimizeCameraPoses is cut from are not stored (2.9 MB of scans behind them): the live test rebuilds the scene
     S.close()
     return o

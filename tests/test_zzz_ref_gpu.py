@@ -195,3 +195,40 @@ def test_device_track_fusion_reproduces_the_reference_source_under_its_container
     tests/test_ref_system_pin.py::test_device_fusion_pass_equals_reference_source_under_its_container_order."""
     r = subprocess.run([sys.executable, "-c", CODE_FUSE], capture_output=True, text=True, timeout=300, cwd=str(ROOT))
     assert r.returncode == 0 and "CHILD-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+
+
+@pytest.mark.gpu
+def test_offline_camera_half_reproduces_the_reference_pipeline_source(tmp_path):
+    """`lvba_offline --visual --fuse-order libstdcxx` (the whole camera half on the device: depth candidates -> track fusion -> anchors -> surf map ->
+    planes -> visual LM) against the reference's own runVisualBAWithLidarAssist chain on the same seeded dataset (tests/golden/ref_system.npz, section V:
+    src/lvba_system.cpp compiled where it lies, its own COLMAP reader, the restated Ceres loop in the place of ceres::Solve): the same number of fused
+    tracks, the same points entering the problem, the same initial cost, cameras equal to what images.txt's six decimals resolve."""
+    import json
+    import numpy as np
+    import __graft_entry__ as graft
+    sys.path.insert(0, str(ROOT / "tests"))
+    import visual_scene
+    from oracle import dataset_writer as dw
+    G = np.load(ROOT / "tests" / "golden" / "ref_system.npz")
+    pkg = graft.load_package()
+    exe = tmp_path / "lvba_offline"
+    cmd = ["g++", "-std=c++17", "-O2", "-I", str(ROOT / "include"), str(ROOT / "tools" / "lvba_offline.cpp"), "-o", str(exe),
+           str(pkg.LIB_PATH), f"-Wl,-rpath,{pkg.LIB_PATH.parent}", "-L/usr/local/cuda/lib64", "-lcudart", "-ldl"]
+    assert subprocess.run(cmd, capture_output=True, text=True).returncode == 0
+    data = tmp_path / "data"
+    visual_scene.make(data, seed=3, W=8, n_landmarks=700)
+    r = subprocess.run([str(exe), "--data", str(data), "--config", str(data / "config.yaml"), "--visual", "--fuse-order", "libstdcxx"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    vis = [x for x in (json.loads(ln) for ln in r.stdout.strip().splitlines()) if x.get("stage") == "visual"][0]
+    assert vis["tracks"] == int(G["V_counts"][0]) and vis["points_kept"] == int(G["V_counts"][1])
+    assert abs(vis["cost_first"] - G["V_costs"][0]) <= 1e-6 * G["V_costs"][0]
+    assert abs(vis["cost_last"] - G["V_costs"][1]) <= 1e-3 * G["V_costs"][1]
+    rows = [ln.split() for ln in (data / "Colmap" / "sparse" / "images.txt").read_text().splitlines()]
+    after = np.zeros((len(rows) // 2, 12))
+    for k in range(len(rows) // 2):
+        q = np.array([float(v) for v in rows[2 * k][1:5]]); t = np.array([float(v) for v in rows[2 * k][5:8]])
+        after[k, :9] = dw.quat_to_R(q).ravel(); after[k, 9:] = t
+    assert after.shape == G["V_cams_after"].shape
+    assert np.abs(after - G["V_cams_after"]).max() <= 1e-4, np.abs(after - G["V_cams_after"]).max()      # the cameras moved by 8e-2 from their start
+    assert np.abs(G["V_cams_after"] - G["V_cams_before"]).max() > 1e-2
