@@ -43,6 +43,17 @@ def _scans(scans):
     return ptr, xyz
 
 
+def track_helpers(obs_ptr, obs_cam, obs_uv, cams, intr, Xw=None, min_count=3):
+    """The reference's file-scope TriangulateTrackDLT (Xw None) / ComputeMeanReproj (Xw given) on CSR tracks.  Returns (Xw, mean, count, ok)."""
+    op = np.ascontiguousarray(obs_ptr, np.int64); oc = np.ascontiguousarray(obs_cam, np.int32); uv = np.ascontiguousarray(obs_uv, np.float32)
+    cm = np.ascontiguousarray(cams, np.float64).reshape(-1, 12); it = np.ascontiguousarray(intr, np.float64)
+    T = len(op) - 1
+    out = np.zeros((T, 3)); mean = np.zeros(T); cnt = np.zeros(T, np.int32); ok = np.zeros(T, np.uint8)
+    xin = None if Xw is None else np.ascontiguousarray(Xw, np.float64)
+    load().sys_track_helpers(C.c_int64(T), _p(op), _p(oc), _p(uv), C.c_int(len(cm)), _p(cm), _p(it), _p(xin), C.c_int(min_count), _p(out), _p(mean), _p(cnt), _p(ok))
+    return (out if Xw is None else xin), mean, cnt, ok.astype(bool)
+
+
 def unordered_map_order(reserve, keys):
     """Iteration order of std::unordered_map<int,int> after reserve(reserve) and inserting `keys` (distinct) in this order."""
     k = np.ascontiguousarray(keys, np.int32); out = np.zeros(len(k), np.int32)

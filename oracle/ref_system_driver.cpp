@@ -303,6 +303,38 @@ void sys_get_tracks(void* h, int64_t* obs_ptr, int32_t* obs, int64_t* inl_ptr, i
   }
 }
 
+// TriangulateTrackDLT (:52-111) and ComputeMeanReproj (:8-50) — file-scope helpers of src/lvba_system.cpp, reachable because that file is part of this
+// translation unit — on CSR tracks (one observation per camera): obs_ptr [T+1], obs_cam, obs_uv [n][2]; cams [M][12] = (Rcw, tcw).
+// Xw_in == nullptr: triangulate every track (Xw, mean, count, ok out); otherwise the mean reprojection error of the given point per track.
+void sys_track_helpers(int64_t T, const int64_t* obs_ptr, const int32_t* obs_cam, const float* obs_uv, int M, const double* cams, const double* intr,
+                       const double* Xw_in, int min_count, double* Xw, double* mean, int32_t* count, uint8_t* ok) {
+  lvba::CameraIntrinsics cam;
+  cam.fx = intr[0]; cam.fy = intr[1]; cam.cx = intr[2]; cam.cy = intr[3]; cam.k1 = intr[4]; cam.k2 = intr[5]; cam.p1 = intr[6]; cam.p2 = intr[7];
+  std::vector<Eigen::Matrix3d> R(M); std::vector<Eigen::Vector3d> t(M);
+  for (int k = 0; k < M; ++k) { IMUST x = pose_in(cams + 12 * k, 0); R[k] = x.R; t[k] = x.p; }
+  for (int64_t tr = 0; tr < T; ++tr) {
+    const int n = (int)(obs_ptr[tr + 1] - obs_ptr[tr]);
+    std::vector<std::vector<sift::Keypoint>> kps(M, std::vector<sift::Keypoint>(n));
+    std::vector<std::pair<int, int>> component;
+    std::unordered_map<int, int> selected;
+    for (int j = 0; j < n; ++j) {
+      const int c = obs_cam[obs_ptr[tr] + j];
+      kps[c][j].x = obs_uv[2 * (obs_ptr[tr] + j)]; kps[c][j].y = obs_uv[2 * (obs_ptr[tr] + j) + 1];
+      component.push_back({c, j});
+      selected[c] = j;
+    }
+    double m = 0.0; int cnt = 0; bool good;
+    if (Xw_in == nullptr) {
+      Eigen::Vector3d X = Eigen::Vector3d::Zero();
+      good = lvba::TriangulateTrackDLT(selected, component, kps, R, t, cam, X, m, cnt);
+      for (int j = 0; j < 3; ++j) Xw[3 * tr + j] = X(j);
+    } else {
+      good = lvba::ComputeMeanReproj(Eigen::Vector3d(Xw_in[3 * tr], Xw_in[3 * tr + 1], Xw_in[3 * tr + 2]), selected, component, kps, R, t, cam, min_count, m, cnt);
+    }
+    mean[tr] = m; count[tr] = cnt; ok[tr] = good ? 1 : 0;
+  }
+}
+
 // Iteration order of a std::unordered_map<int,int> after reserve(reserve_n) and the insertion of `keys` in the given order — the order the
 // reference's three `for (auto& kv : map)` loops of the track fusion run in (:1057, :1069, :1124).  The language leaves it unspecified; this is the
 // answer of the C++ library the reference is compiled with here.

@@ -354,3 +354,42 @@ def test_reference_loader_reads_the_dataset_the_dataset_writer_writes():
     assert np.abs(d["frame_poses"] - rt(poses)).max() <= 1e-11            # 15-digit text, quaternion normalised on reading (:165-166)
     assert np.abs(d["image_ts"] - np.array(image_ts)).max() <= 1e-9 and len(d["image_ts"]) == 7      # 14 files, every second one
     assert np.abs(d["image_poses"] - rt(image_poses)).max() <= 1e-11      # the skipped lines carry poses 100 m away: none of them was taken
+
+
+# ------------------------------------------------------------------------------------------------ B5: the per-track helpers on their own
+@needs_ref
+def test_dlt_and_mean_reprojection_equal_reference_source_live():
+    """TriangulateTrackDLT (src/lvba_system.cpp:52-111) and ComputeMeanReproj (:8-50), called directly (they are file-scope functions of the
+    included source), vs oracle/track_oracle.py and the device functors through the host policy (tests/emu/track_emu.cpp) on 400 tracks.
+    The reference sums in its container's order and solves the 4x4 eigen-problem with the library's solver (here: the stand-in's Jacobi):
+    agreement to 1e-9, not to the bit."""
+    import ctypes
+    import subprocess
+    import test_track_emu as tt
+    from oracle import track_oracle as tro
+    p, cams, op, oc, uv, intr = tt._problem()
+    T = len(op) - 1
+    Xr, mr, cr, okr = sr.track_helpers(op, oc, uv, cams, intr)
+    so = Path(tempfile.mkdtemp()) / "libtrack_emu.so"
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "track_emu.cpp"), "-o", str(so)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    emu = ctypes.CDLL(str(so))
+    Xe = np.zeros((T, 3)); me = np.zeros(T); ce = np.zeros(T, np.int32); oke = np.zeros(T, np.uint8)
+    emu.emu_tracks_triangulate(ctypes.c_int64(T), tt._ptr(op, ctypes.c_int64), tt._ptr(oc, ctypes.c_int32), tt._ptr(uv, ctypes.c_float), ctypes.c_int32(40),
+                               tt._ptr(cams, ctypes.c_double), tt._ptr(intr, ctypes.c_double), tt._ptr(Xe, ctypes.c_double), tt._ptr(me, ctypes.c_double),
+                               tt._ptr(ce, ctypes.c_int32), oke.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    assert np.array_equal(okr, oke.astype(bool)) and okr.sum() > 100 and not okr.all()
+    assert np.array_equal(cr[okr], ce[okr])
+    assert np.abs(Xr[okr] - Xe[okr]).max() <= 1e-9 * max(1.0, np.abs(Xr[okr]).max()) and np.abs(mr[okr] - me[okr]).max() <= 1e-9
+    for t in np.nonzero(okr)[0][::9]:
+        sel = list(range(op[t], op[t + 1]))
+        o_ok, X, m, c = tro.triangulate_dlt(cams[oc[sel]], uv[sel], intr)
+        assert o_ok and c == cr[t] and np.abs(X - Xr[t]).max() <= 1e-7 * max(1.0, np.abs(X).max()) and abs(m - mr[t]) <= 1e-7   # LAPACK eigh vs Jacobi on short baselines: the smallest eigenvector of A^T A is conditioned like 1e7
+    X = np.ascontiguousarray(p["X_gt"] + 0.01)
+    _, m2, c2, ok2 = sr.track_helpers(op, oc, uv, cams, intr, Xw=X, min_count=5)
+    assert ok2.any() and not ok2.all()
+    for t in range(0, T, 5):
+        sel = list(range(op[t], op[t + 1]))
+        o_ok, m, c = tro.mean_reproj(X[t], cams[oc[sel]], uv[sel], intr, 5)
+        assert o_ok == bool(ok2[t]) and c == c2[t] and (not o_ok or abs(m - m2[t]) <= 1e-9)
