@@ -47,22 +47,22 @@ def lex(a):
 
 
 # ------------------------------------------------------------------------------------------------ L
-def lidar_chain(use_rel):
-    """runWindowBA (src/lvba_system.cpp:204-302) + runLidarBA (:304-409) out of the stage oracles."""
-    scans = split(G["L_xyz"], G["L_scan_ptr"]); start = G["L_poses"]
-    W, win = len(scans), int(G["L_window"])
+def lidar_chain(use_rel, scans=None, start=None, win=None, leaf=None, s1=None, s2=None, stage1=True):
+    """runWindowBA (src/lvba_system.cpp:204-302) + runLidarBA (:304-409) out of the stage oracles.  Defaults: section L of the fixture."""
+    if scans is None:
+        scans = split(G["L_xyz"], G["L_scan_ptr"]); start = G["L_poses"]; win = int(G["L_window"]); leaf = float(G["L_anchor_leaf"])
+        s1 = (float(G["L_s1_voxel"]), G["L_s1_ratio"]); s2 = (float(G["L_s2_voxel"]), G["L_s2_ratio"])
+    W = len(scans)
     win_ptr = list(range(0, W, win)) + [W]
     anchor_index = np.full(W, -1, np.int32); rel = np.zeros((W, 12)); rel[:, [0, 4, 8]] = 1.0      # IMUST(): identity, zero
     anchors, clouds = [], []
     for w in range(len(win_ptr) - 1):
         a, b = win_ptr[w], win_ptr[w + 1]
-        vp, pi, cl, _ = vox.voxelize(scans[a:b], start[a:b], float(G["L_s1_voxel"]), vox.EIGEN_RATIO_DEFAULT)  # :247-258: stage-1 SIZE, but the plane test reads
+        vp, pi, cl, _ = vox.voxelize(scans[a:b], start[a:b], s1[0], vox.EIGEN_RATIO_DEFAULT)                # :247-258: stage-1 SIZE, but the plane test reads
         #                                       the process-wide array, which still holds bavoxel.hpp:17's default here (the configured arrays are set at :358, later)
         if len(vp) - 1 < 3 * (b - a):                                                                      # :259-263
             continue
-        x_win = start[a:b]
-        if len(vp) - 1 > 0:
-            x_win, _ = lo.damping_iter(vp, pi, cl, start[a:b])                                             # :264
+        x_win, _ = lo.damping_iter(vp, pi, cl, start[a:b])                                                 # :264
         aligned = start[a:b].copy()
         if use_rel:                                                                                        # :267-279
             R_align = start[a, :9].reshape(3, 3) @ x_win[0, :9].reshape(3, 3).T
@@ -71,10 +71,10 @@ def lidar_chain(use_rel):
                 aligned[j, :9] = (R_align @ x_win[j, :9].reshape(3, 3)).ravel(); aligned[j, 9:] = R_align @ x_win[j, 9:] + p_align
         r = rel_to(start[a], aligned)                                                                      # :283-289: anchor = the ODOMETRY pose of frame 0
         rel[a:b] = r; anchor_index[a:b] = len(anchors)
-        clouds.append(ao.anchor_clouds(scans[a:b], r, np.array([0, b - a]), float(G["L_anchor_leaf"]))[0])
+        clouds.append(ao.anchor_clouds(scans[a:b], r, np.array([0, b - a]), leaf)[0])
         anchors.append(start[a])
     anchors = np.array(anchors)
-    for vs_, er in ((float(G["L_s1_voxel"]), G["L_s1_ratio"]), (float(G["L_s2_voxel"]), G["L_s2_ratio"])):   # :355-389
+    for vs_, er in ([s1] if stage1 else []) + [s2]:                                                        # :355-389 (stage 1 only if BALM_stage1/enable)
         vp, pi, cl, _ = vox.voxelize(clouds, anchors, vs_, er)
         anchors, _ = lo.damping_iter(vp, pi, cl, anchors)
     final = start.copy()
@@ -122,6 +122,29 @@ def test_lidar_half_equals_reference_source(use_rel):
     assert np.abs(ref - G["L_poses"]).max() > 1e-3                        # the others moved
     if use_rel:
         assert np.abs(G["L_final_poses_rel"] - G["L_final_poses"]).max() > 1e-5       # the switch does something
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,W,win,use_rel,stage1,index", [(31, 10, 4, False, True, [0, 0, 0, 0, 1, 1, 1, 1, 2, 2]), (32, 10, 4, True, True, [0, 0, 0, 0, 1, 1, 1, 1, 2, 2]),
+                                                             (33, 7, 3, True, False, [0, 0, 0, 1, 1, 1, -1])])
+def test_lidar_half_live_ragged_windows_and_stage_switches(seed, W, win, use_rel, stage1, index):
+    """A last window shorter than the others, a last window of ONE frame (no voxel can see two poses: skipped, its frame keeps the odometry pose),
+    BALM_stage1/enable = false, both settings of use_window_ba_rel: the reference's runLidarBA, run live, against the oracle chain."""
+    scans, poses = synth.make_scan_scene(seed, W=W, n_per_scan=2500)
+    rng = np.random.default_rng(seed)
+    noisy = poses.copy()
+    for i in range(W):
+        noisy[i, :9] = (noisy[i, :9].reshape(3, 3) @ synth.so3_exp(rng.normal(0, 0.004, (1, 3)))[0]).ravel(); noisy[i, 9:] += rng.normal(0, 0.01, 3)
+    s1r = np.array([0.3, 0.1, 0.06, 0.03], np.float32); s2r = np.array([0.08] * 4, np.float32)
+    sr.set_eigen_ratio_array(s1r)                                  # a fresh process: bavoxel.hpp:17
+    S = sr.System()
+    S.set_lidar(scans, noisy)
+    S.set_stages(True, win, 0.1, use_rel, stage1, 1.0, s1r, 0.5, s2r)
+    out = S.run_lidar_ba()
+    S.close()
+    idx, _, _, final = lidar_chain(use_rel, scans, noisy, win, 0.1, (1.0, s1r), (0.5, s2r), stage1)
+    assert idx.tolist() == index
+    assert np.abs(out - final).max() <= 1e-9 and np.abs(out - noisy).max() > 1e-3
 
 
 # ------------------------------------------------------------------------------------------------ D
