@@ -2,7 +2,9 @@
   rel poses              src/lvba_system.cpp:286-289   rel.R = anchor.R^T x.R ; rel.p = anchor.R^T (x.p - anchor.p)
   pl_transform           include/BALM/tools.hpp:385-395   p <- (float)(R p + t) per coordinate
   down_sampling_voxel2   include/BALM/tools.hpp:301-359   per voxel the original point closest to the voxel centre, first wins ties
-The reference returns the survivors in unordered_map order; both restatements here return them sorted by voxel key."""
+The reference returns the survivors in unordered_map order; both restatements here return them sorted by voxel key.
+PARITY: pinned against the reference's own source (include/BALM/tools.hpp compiled where it lies): the surviving float32 points equal bit for bit,
+as a set (tests/golden/ref_balm.npz, ref_system.npz; tests/test_ref_pin.py, tests/test_ref_system_pin.py)."""
 from __future__ import annotations
 
 import numpy as np

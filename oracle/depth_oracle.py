@@ -1,5 +1,7 @@
 """CPU restatement of the reference's depth rendering (first half) — TEST INFRASTRUCTURE; nothing in
 the product imports it.
+PARITY: pinned against the reference's own source (src/lvba_system.cpp and include/utils.hpp compiled where they lie): depth images, projection,
+undistortion and the depth-candidate chain BIT FOR BIT (tests/golden/ref_system.npz, ref_balm.npz; tests/test_ref_system_pin.py, test_ref_pin.py).
 
 Follows:
   buildGridMapFromOptimized   src/lvba_system.cpp:1266-1338   world points bucketed into 0.5 m voxels (float key, `-= 1.0f`

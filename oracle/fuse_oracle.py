@@ -6,9 +6,14 @@ Literal where the reference is defined: adjacency in push_back order (:937-953),
 keypoint in (image, keypoint) order (:964-988), size / image-count gates (:989, :1001), first observation per image in member
 order (:996-1000), depth candidate (:1016-1103), triangulation candidate (:1106-1159), choice (:1161-1199), release of a failed
 component so that the scan tries it again from its next keypoint (:1199, :1203).
-The reference iterates std::unordered_map<int,int> (image -> member) in three places; that order is unspecified.  Here — and in
-global-lvba_b200/csrc/fuse_pipeline.h — the images are visited in ASCENDING id.  Parity unpinned: the reference cannot be built
-here and ships no fixtures for this stage."""
+The reference iterates std::unordered_map<int,int> (image -> member) in three places; that order is unspecified and DECIDES the result (the
+greedy view-angle filter keeps what it meets first).  `fuse(..., map_order=...)` takes it as a parameter: None = ASCENDING image id (the default
+order of global-lvba_b200/csrc/fuse_pipeline.h and of the ABI), `libstdcxx_order` = what GNU libstdc++'s container does after the reference's
+reserve() / insert calls (LVBA_FUSE_ORDER_LIBSTDCXX in the ABI).
+PARITY: pinned against the reference's own source — under `libstdcxx_order` this function reproduces LvbaSystem::BuildTracksAndFuse3D, compiled
+from src/lvba_system.cpp where it lies (oracle/ref_system_driver.cpp), track for track: tests/golden/ref_system.npz, tests/test_ref_system_pin.py;
+`libstdcxx_order` itself is held against the real std::unordered_map there.
+"""
 from __future__ import annotations
 
 from collections import deque

@@ -1,6 +1,8 @@
 """CPU restatement of the per-track numerics of the reference's track fusion — TEST INFRASTRUCTURE:
   TriangulateTrackDLT   src/lvba_system.cpp:52-111   ;   ComputeMeanReproj   src/lvba_system.cpp:8-50
-(undistortPixelToNormalized / projectWorldToPixel: include/utils.hpp:183-233, restated in oracle/depth_oracle.py)."""
+(undistortPixelToNormalized / projectWorldToPixel: include/utils.hpp:183-233, restated in oracle/depth_oracle.py).
+PARITY: pinned against the reference's own file-scope functions, called from src/lvba_system.cpp compiled where it lies (tests/test_ref_system_pin.py:
+directly on 400 tracks to 1e-7 — LAPACK eigh here, Jacobi under the reference's lines — and through BuildTracksAndFuse3D to 1e-12)."""
 from __future__ import annotations
 
 import numpy as np

@@ -1,5 +1,8 @@
 """CPU restatement of the reference's set-up stage — TEST INFRASTRUCTURE, groundwork
 for a GPU voxelisation kernel; nothing in the product imports it.
+PARITY: pinned against the reference's own source (include/BALM/bavoxel.hpp compiled where it lies, oracle/ref_driver.cpp): keys, octree paths,
+layers, pose lists and — for the literal restatement — the cluster sums to the bit, plane look-ups, the LM on the map (tests/golden/ref_balm.npz,
+tests/test_ref_pin.py).
 
 Follows, line by line:
   cut_voxel            include/BALM/bavoxel.hpp:799-836   points -> root voxel (float division, negative fix, int64 key)
