@@ -13,7 +13,7 @@ ROOT = Path(__file__).resolve().parents[1]
 
 
 SUITES = ["tests/test_voxel_emu.py", "tests/test_depth_emu.py", "tests/test_anchor_emu.py", "tests/test_wide_solver_emu.py",
-          "tests/test_big_voxel_emu.py", "tests/test_track_emu.py", "tests/test_nd_solver_emu.py"]
+          "tests/test_big_voxel_emu.py", "tests/test_track_emu.py", "tests/test_nd_solver_emu.py", "tests/test_fuse_emu.py"]
 _runs = {}
 
 
