@@ -432,3 +432,87 @@ def test_dlt_and_mean_reprojection_equal_reference_source_live():
         sel = list(range(op[t], op[t + 1]))
         o_ok, m, c = tro.mean_reproj(X[t], cams[oc[sel]], uv[sel], intr, 5)
         assert o_ok == bool(ok2[t]) and c == c2[t] and (not o_ok or abs(m - m2[t]) <= 1e-9)
+
+
+# ------------------------------------------------------------------------------------------------ F, differential: many scenes, live
+def _depth_images_for(s, width=640, height=512):
+    """Depth images that hand every keypoint with a depth candidate (roughly) the camera-frame depth of that candidate: its four bilinear
+    neighbours are set to z_c.  Overlapping neighbourhoods overwrite each other — both sides read the images, so that only varies the scene."""
+    M = len(s["kp_ptr"]) - 1
+    img = np.zeros((M, height, width), np.float32)
+    for i in range(M):
+        R = s["cams"][i, :9].reshape(3, 3); t = s["cams"][i, 9:]
+        for g in range(int(s["kp_ptr"][i]), int(s["kp_ptr"][i + 1])):
+            if not s["kp_valid"][g]:
+                continue
+            z = float((R @ s["kp_Xw"][g] + t)[2])
+            u, v = float(s["kp_uv"][g, 0]), float(s["kp_uv"][g, 1])
+            if z <= 0.1 or not (0 <= u < width - 1 and 0 <= v < height - 1):
+                continue
+            x, y = int(np.floor(u)), int(np.floor(v))
+            img[i, y:y + 2, x:x + 2] = np.float32(z)
+    return img
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,kw", [(0, {}), (1, dict(wrong=0.15)), (2, dict(no_depth=0.6)), (3, dict(bad_depth=0.3, px_noise=1.2)),
+                                     (4, dict(n_images=30, n_points=300)), (7, dict(n_images=45, n_points=200, wrong=0.1)), (8, dict(n_images=20, n_points=150, wrong=0.3))])
+def test_track_fusion_differential_reference_source_vs_oracle_and_device_pass(seed, kw, tmp_path_factory):
+    """BuildTracksAndFuse3D from the reference's own source on the scenes of tests/test_fuse_emu.py (wrong matches that merge components, missing and
+    wrong depth, up to 45 images: more keys than buckets in the reference's maps, failed components retried from other seeds) against
+    oracle/fuse_oracle.py under the container order and against csrc/fuse_pipeline.h through the host policy with LVBA_FUSE_ORDER_LIBSTDCXX."""
+    import ctypes
+    import subprocess
+    import fuse_scene
+    import test_fuse_emu
+    s = fuse_scene.make(seed=seed, **kw)
+    depth = _depth_images_for(s)
+    Xw, valid = dep.backproject(list(depth), s["cams"], s["intr"], s["kp_ptr"], s["kp_uv"])
+    S = sr.System()
+    S.set_fusion_inputs(s["cams"], depth, s["intr"], s["kp_ptr"], s["kp_uv"], s["matches"])
+    T = S.build_tracks()
+    S.close()
+    tr = fo.fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], Xw, valid, map_order=fo.libstdcxx_order)
+    assert len(tr) == len(T["Xw"]) > 0
+    for k, t in enumerate(tr):
+        assert np.array_equal(t["obs"], T["obs"][T["obs_ptr"][k]:T["obs_ptr"][k + 1]]), k
+        assert list(t["kept"]) == T["inl"][T["inl_ptr"][k]:T["inl_ptr"][k + 1]].tolist(), k
+        assert np.abs(t["Xw"] - T["Xw"][k]).max() <= 1e-7 * max(1.0, np.abs(T["Xw"][k]).max()), k      # DLT on short baselines: LAPACK eigh vs Jacobi
+    so = tmp_path_factory.mktemp("emu_ref_fuse_diff") / "libfuse_emu.so"
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "fuse_emu.cpp"), "-o", str(so)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = ctypes.CDLL(str(so)); lib.fuse_emu_run.restype = ctypes.c_longlong
+    got = test_fuse_emu.run_emu(lib, dict(s, kp_Xw=Xw, kp_valid=valid), map_order=1)
+    assert len(got["seed"]) == len(T["Xw"])
+    for k in range(len(T["Xw"])):
+        a, b = got["obs_ptr"][k], got["obs_ptr"][k + 1]
+        assert np.array_equal(np.column_stack([got["img"][a:b], got["kp"][a:b]]), T["obs"][T["obs_ptr"][k]:T["obs_ptr"][k + 1]]), k
+        inl = np.zeros(b - a, bool); inl[T["inl"][T["inl_ptr"][k]:T["inl_ptr"][k + 1]]] = True
+        assert np.array_equal(got["inlier"][a:b].astype(bool), inl), k
+        assert np.abs(got["Xw"][k] - T["Xw"][k]).max() <= 1e-9 * max(1.0, np.abs(T["Xw"][k]).max()), k
+
+
+# ------------------------------------------------------------------------------------------------ D, differential: more scenes, live
+@needs_ref
+@pytest.mark.parametrize("seed,F,M,size", [(11, 5, 3, (64, 48)), (12, 9, 6, (120, 90)), (13, 4, 5, (200, 160))])
+def test_depth_rendering_differential_reference_source_vs_oracle(seed, F, M, size):
+    """buildGridMapFromOptimized + generateDepthWithVoxel from the reference's own source on further scenes (image timestamps outside the scan range
+    included: some images see no frame) — images equal to the oracle's bit for bit."""
+    sc = synth.make_depth_scene(seed, F=F, n_per_scan=1800, M=M, width=size[0], height=size[1])
+    img_ts = np.round(sc["image_ts"], 6)
+    img_ts[0] = sc["frame_ts"][0] - 3.0                                   # nothing within +-0.5 s: an empty image
+    body = np.zeros((M, 12))
+    for k in range(M):                                                    # body poses whose cameras are sc["cams"]: Rcw = Rci Rwi^T with Rci = I, tci = 0
+        Rcw = sc["cams"][k, :9].reshape(3, 3); tcw = sc["cams"][k, 9:]
+        body[k, :9] = Rcw.T.ravel(); body[k, 9:] = -Rcw.T @ tcw
+    S = sr.System()
+    S.set_lidar(sc["scans"], sc["poses"], sc["frame_ts"])
+    S.set_stages(False)
+    S.set_camera(size[0], size[1], sc["intr"], np.eye(3).ravel(), np.zeros(3), np.eye(3).ravel(), np.zeros(3), img_ts, body)
+    S.build_grid(); S.update_camera_poses()
+    d, _, c1 = S.generate_depth()
+    S.close()
+    assert np.abs(c1 - sc["cams"]).max() <= 1e-12
+    img = dep.render(sc["scans"], sc["poses"], sc["frame_ts"], c1, img_ts, sc["intr"], size[0], size[1])
+    assert np.array_equal(img, d) and not d[0].any() and (d[1:] > 0).sum() > 500
