@@ -6,9 +6,8 @@ Through the C ABI: B1 Hessian build / residual pass / full damping_iter, B3 voxe
 without the clusters leaving HBM, B6 anchor clouds, B2 cost (the two Ceres functors summed over the problem).
 Tolerances as in tests/test_lidar_gpu.py (lambda_0 is a difference of O(1e4) terms): residual sums 1e-8 relative,
 g / H 1e-7 of their largest entry, LM end poses 1e-6, final cost 1e-6 (north star); integer data, keys, point counts and the
-float32 anchor points exact.  Runs in a child process under a timeout like the other test_zz_* files, and sorts after all of them: the
-first test below has passed on a B200 (profiles/r02_ref_pin_gpu.txt); the others were written after the round's GPU budget was spent (their
-checks are dry-run on the CPU through the host policy / an oracle stand-in) and must not keep any other file from running under `-x`."""
+float32 anchor points exact.  Runs in a child process under a timeout like the other test_zz_* files and sorts after all of them.  All tests
+below have passed on a B200 (profiles/r02_ref_pin_gpu.txt, profiles/r02_ref_pin_gpu_system.txt)."""
 import subprocess
 import sys
 from pathlib import Path
