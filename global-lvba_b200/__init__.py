@@ -624,17 +624,19 @@ class FuseSummary(C.Structure):
 
 
 def tracks_fuse(kp_ptr, kp_uv, matches, cams, intr, kp_Xw, kp_valid, obser_thr=3, min_view_angle_deg=8.0, reproj_thr=3.0, depth_gate=0.12, device=-1,
-                map_order=FUSE_ORDER_ASCENDING):
+                map_order=None):
     """lvba_tracks_fuse_create + export (boundary B7: BuildTracksAndFuse3D).  matches: (m, 4) int (img_a, kp_a, img_b, kp_b) in the
-    reference's visiting order.  map_order: FUSE_ORDER_ASCENDING (documented default) or FUSE_ORDER_LIBSTDCXX (the container order of a g++ build
-    of the reference).  Returns dict(obs_ptr, img, kp, inlier, Xw, source, mean, summary)."""
+    reference's visiting order.  map_order: None = the library's default (FUSE_ORDER_LIBSTDCXX: the container order of a g++ build of the reference),
+    or FUSE_ORDER_ASCENDING (library independent).  Returns dict(obs_ptr, img, kp, inlier, Xw, source, mean, summary)."""
     lib = load_library()
     kp_ptr = np.ascontiguousarray(kp_ptr, np.int64); uv = np.ascontiguousarray(kp_uv, np.float32)
     m = np.ascontiguousarray(matches, np.int32).reshape(-1, 4)
     cols = [np.ascontiguousarray(m[:, q]) for q in range(4)]
     cams = _f64(cams); intr = _f64(intr); X = _f64(kp_Xw); va = np.ascontiguousarray(kp_valid, np.uint8)
     o = FuseOpts(); lib.lvba_fuse_default_opts(C.byref(o))
-    o.obser_thr = obser_thr; o.min_view_angle_deg = min_view_angle_deg; o.reproj_mean_thr_px = reproj_thr; o.depth_gate_m = depth_gate; o.device = device; o.map_order = map_order
+    o.obser_thr = obser_thr; o.min_view_angle_deg = min_view_angle_deg; o.reproj_mean_thr_px = reproj_thr; o.depth_gate_m = depth_gate; o.device = device
+    if map_order is not None:
+        o.map_order = map_order
     h = C.c_void_p(); s = FuseSummary()
     _chk(lib.lvba_tracks_fuse_create(C.c_int32(len(kp_ptr) - 1), _p(kp_ptr, C.c_int64), _p(uv, C.c_float), C.c_int64(len(m)),
                                      _p(cols[0], C.c_int32), _p(cols[1], C.c_int32), _p(cols[2], C.c_int32), _p(cols[3], C.c_int32),

@@ -22,7 +22,7 @@ void lvba_fuse_default_opts(lvba_fuse_opts* o) {
   o->reproj_mean_thr_px = 3.0;        // track_fusion/reproj_mean_thr, :130
   o->depth_gate_m = 0.12;             // :1050
   o->device = -1;
-  o->map_order = LVBA_FUSE_ORDER_ASCENDING;
+  o->map_order = LVBA_FUSE_ORDER_LIBSTDCXX;   // what a g++ build of the reference does; verified against the reference's own source (tests/test_zzz_ref_gpu.py)
 }
 
 int lvba_tracks_fuse_create(int32_t n_images, const int64_t* kp_ptr, const float* kp_uv, int64_t n_matches, const int32_t* match_img_a,

@@ -19,10 +19,10 @@
 // The reference iterates three std::unordered_map<int,int> (image id -> member) whose order is unspecified; the sums over
 // them (mean of the depth points, A^T A of the DLT, mean reprojection error) depend on it in the last bits and the GREEDY
 // view-angle filter depends on it outright.  Two orders are implemented (Params::map_order, lvba_fuse_opts::map_order):
-//   0  ASCENDING image id — the order this ABI documents; independent of any C++ library;
+//   0  ASCENDING image id — independent of any C++ library;
 //   1  the order GNU libstdc++'s std::unordered_map<int,int> iterates in after the reference's reserve() calls and insertions
 //      (stl_map_order below: published bucket-count table, identity hash, insert-at-front-of-list / front-of-bucket) — what a g++
-//      build of the reference does.  With it the stage reproduces the reference's own BuildTracksAndFuse3D track for track
+//      build of the reference does, and the default of the ABI.  With it the stage reproduces the reference's own BuildTracksAndFuse3D track for track
 //      (tests/test_ref_system_pin.py: the reference's source compiled where it lies vs this pipeline through the host policy).
 // Everything else (BFS order, first-per-image rule, thresholds) is the reference's in both.
 //

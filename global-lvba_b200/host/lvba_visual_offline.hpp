@@ -51,7 +51,7 @@ struct Config {
   std::vector<float> eigen1{0.3f, 0.1f, 0.06f, 0.03f}, eigen2{0.3f, 0.1f, 0.06f, 0.03f};     // bavoxel.hpp:17
   bool enable_lidar_ba = true, enable_visual_ba = true, colmap_output = true;
   double min_view_angle = 8.0, reproj_mean_thr = 3.0, filter_size_points3D = 0.01;
-  int fuse_map_order = LVBA_FUSE_ORDER_ASCENDING;     // not a reference parameter: which unordered_map order the track fusion mimics (lvba_b200.h)
+  int fuse_map_order = LVBA_FUSE_ORDER_LIBSTDCXX;     // not a reference parameter: which unordered_map order the track fusion mimics (lvba_b200.h)
   bool scaled = false;
   // the tail of readParameters (:59-62): the image is used at `scale`
   void apply_scale() {

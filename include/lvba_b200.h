@@ -390,10 +390,11 @@ int lvba_tracks_mean_reproj(int64_t n_tracks, const int64_t* obs_ptr, const int3
  * lists are the observation CSR of lvba_visual_lm once the inliers are kept (:1610-1617).
  * Where the reference iterates std::unordered_map<int,int> (unspecified order: the greedy
  * view-angle filter depends on it, and with it which tracks survive) the images of a component are
- * visited in ascending id (map_order = LVBA_FUSE_ORDER_ASCENDING, the default: independent of any C++
- * library) or in the order GNU libstdc++'s container has after the reference's reserve() / insert
- * calls (LVBA_FUSE_ORDER_LIBSTDCXX: what a g++ build of the reference does; with it the stage
- * reproduces the reference's own source track for track, tests/test_ref_system_pin.py).
+ * visited in the order GNU libstdc++'s container has after the reference's reserve() / insert calls
+ * (map_order = LVBA_FUSE_ORDER_LIBSTDCXX, the default: what a g++ build of the reference does; with
+ * it the stage reproduces the reference's own source track for track, tests/test_ref_system_pin.py,
+ * tests/test_zzz_ref_gpu.py) or in ascending id (LVBA_FUSE_ORDER_ASCENDING: independent of any C++
+ * library).
  * ====================================================================================== */
 typedef struct lvba_fuse_opts {
   int32_t obser_thr;              /* minimum members / images / survivors (lvba_system.h:139: 3) */

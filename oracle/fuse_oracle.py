@@ -7,9 +7,9 @@ keypoint in (image, keypoint) order (:964-988), size / image-count gates (:989, 
 order (:996-1000), depth candidate (:1016-1103), triangulation candidate (:1106-1159), choice (:1161-1199), release of a failed
 component so that the scan tries it again from its next keypoint (:1199, :1203).
 The reference iterates std::unordered_map<int,int> (image -> member) in three places; that order is unspecified and DECIDES the result (the
-greedy view-angle filter keeps what it meets first).  `fuse(..., map_order=...)` takes it as a parameter: None = ASCENDING image id (the default
-order of global-lvba_b200/csrc/fuse_pipeline.h and of the ABI), `libstdcxx_order` = what GNU libstdc++'s container does after the reference's
-reserve() / insert calls (LVBA_FUSE_ORDER_LIBSTDCXX in the ABI).
+greedy view-angle filter keeps what it meets first).  `fuse(..., map_order=...)` takes it as a parameter: `libstdcxx_order` (default) = what GNU
+libstdc++'s container does after the reference's reserve() / insert calls — LVBA_FUSE_ORDER_LIBSTDCXX, the default of the ABI; `ascending_order` =
+ascending image id, the ABI's library-independent alternative (LVBA_FUSE_ORDER_ASCENDING).
 PARITY: pinned against the reference's own source — under `libstdcxx_order` this function reproduces LvbaSystem::BuildTracksAndFuse3D, compiled
 from src/lvba_system.cpp where it lies (oracle/ref_system_driver.cpp), track for track: tests/golden/ref_system.npz, tests/test_ref_system_pin.py;
 `libstdcxx_order` itself is held against the real std::unordered_map there.
@@ -52,16 +52,21 @@ def libstdcxx_order(reserve, keys):
     return order
 
 
+def ascending_order(reserve, keys):
+    """The library-independent alternative the ABI offers (LVBA_FUSE_ORDER_ASCENDING): images in ascending id."""
+    return sorted(keys)
+
+
 def fuse(kp_ptr, kp_uv, matches, cams, intr, kp_Xw, kp_valid, obser_thr=3, min_view_angle_deg=8.0, reproj_thr=3.0, depth_gate=0.12, map_order=None):
     """matches: (m, 4) int array (img_a, kp_a, img_b, kp_b) in the reference's visiting order.
     Returns a list of tracks {seed, obs (k,2), inlier (k,) bool, Xw, mean, source, kept (inlier positions in the order they were kept)} in the
     reference's track order.
     map_order(reserve, keys) -> keys in the order the reference's `for (auto& kv : unordered_map)` loops visit them (`keys` = image ids in insertion
-    order, `reserve` = the argument of the map's reserve()).  None = ascending image id, the order this repo's ABI documents; with the C++ library's
-    own answer (oracle/lvba_system_ref.unordered_map_order) this function reproduces the reference's BuildTracksAndFuse3D track for track
-    (tests/test_ref_system_pin.py)."""
+    order, `reserve` = the argument of the map's reserve()).  None = `libstdcxx_order`, the order of a g++ build of the reference and the default of
+    the ABI (LVBA_FUSE_ORDER_LIBSTDCXX): with it this function reproduces the reference's BuildTracksAndFuse3D track for track
+    (tests/test_ref_system_pin.py).  `ascending_order` is the ABI's library-independent alternative."""
     if map_order is None:
-        map_order = lambda reserve, keys: sorted(keys)  # noqa: E731
+        map_order = libstdcxx_order
     N = len(kp_ptr) - 1
     n_kp = int(kp_ptr[-1])
     img_of = np.repeat(np.arange(N), np.diff(kp_ptr))

@@ -37,7 +37,8 @@ out.update(a_xyz=np.concatenate(scans).astype(np.float32), a_scan_ptr=np.concate
 print("B6:", [len(c) for c in clouds], "points of", [sum(len(scans[j]) for j in range(win_ptr[w], win_ptr[w + 1])) for w in range(len(sizes))])
 # ---- B7
 f = fuse_scene.make(seed=23, n_images=12, n_points=90, wrong=0.1, bad_depth=0.15)
-tracks = fo.fuse(f["kp_ptr"], f["kp_uv"], f["matches"], f["cams"], f["intr"], f["kp_Xw"], f["kp_valid"])
+tracks = fo.fuse(f["kp_ptr"], f["kp_uv"], f["matches"], f["cams"], f["intr"], f["kp_Xw"], f["kp_valid"], map_order=fo.ascending_order)   # LVBA_FUSE_ORDER_ASCENDING (the container order of the
+# reference is pinned by tests/golden/ref_system.npz, written by the reference's own source)
 obs = np.concatenate([t["obs"] for t in tracks]).astype(np.int32)
 out.update(f_kp_ptr=f["kp_ptr"], f_kp_uv=f["kp_uv"], f_matches=f["matches"], f_cams=f["cams"], f_intr=f["intr"], f_kp_Xw=f["kp_Xw"], f_kp_valid=f["kp_valid"],
            f_obs_ptr=np.concatenate([[0], np.cumsum([len(t["obs"]) for t in tracks])]).astype(np.int64), f_obs_img=obs[:, 0], f_obs_kp=obs[:, 1],

@@ -157,7 +157,10 @@ static int fuse_case() {
       for (int p = 0; p < NP; ++p) matches[(size_t)i * N - (size_t)i * (i + 1) / 2 + (j - i - 1)].push_back({kp_of[p][i], kp_of[p][j]});
   std::vector<lvba_b200::FusedTrack> tracks;
   lvba_fuse_summary fs{};
-  const int rc = lvba_b200::build_tracks_and_fuse_3d(kps, matches, Rcw, tcw, fx, fy, cx, cy, 0.0, 0.0, 0.0, 0.0, kpX, kpV, tracks, nullptr, &fs);
+  lvba_fuse_opts fo;
+  lvba_fuse_default_opts(&fo);
+  fo.map_order = LVBA_FUSE_ORDER_ASCENDING;     // this case predates the container-order mode (the default since); that mode has its own device tests
+  const int rc = lvba_b200::build_tracks_and_fuse_3d(kps, matches, Rcw, tcw, fx, fy, cx, cy, 0.0, 0.0, 0.0, 0.0, kpX, kpV, tracks, &fo, &fs);
   if (rc == LVBA_ERR_NO_DEVICE) return 2;
   if (rc != LVBA_OK) { std::printf("fuse error %d: %s\n", rc, lvba_last_error()); return 1; }
   double worst = 0;

@@ -58,7 +58,7 @@ def test_fusion_in_the_container_order_of_a_gxx_build_matches_the_oracle(emu, se
     (tests/test_ref_system_pin.py)."""
     s = fuse_scene.make(seed=seed, **kw)
     ref = fo.fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"], map_order=fo.libstdcxx_order)
-    asc = fo.fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"])
+    asc = fo.fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"], map_order=fo.ascending_order)
     got = run_emu(emu, s, map_order=1)
     compare(got, ref)
     assert len(ref) > 0
@@ -83,8 +83,8 @@ def compare(got, ref):
                                      (4, dict(n_images=30, n_points=300)), (5, dict(no_depth=1.0)), (6, dict(n_images=5, n_points=40))])
 def test_fusion_matches_the_oracle(emu, seed, kw):
     s = fuse_scene.make(seed=seed, **kw)
-    ref = fo.fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"])
-    got = run_emu(emu, s)
+    ref = fo.fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"], map_order=fo.ascending_order)
+    got = run_emu(emu, s)                                                        # map_order = 0: LVBA_FUSE_ORDER_ASCENDING
     compare(got, ref)
     assert len(ref) > 0 or kw.get("n_images") == 5
     if seed in (0, 4):
@@ -96,7 +96,7 @@ def test_thresholds_and_retries(emu):
     s = fuse_scene.make(seed=11, wrong=0.2, bad_depth=0.3)
     for thr, angle, px in ((2, 1.0, 6.0), (4, 15.0, 1.5), (3, 8.0, 0.8)):
         ref = fo.fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"], obser_thr=thr,
-                      min_view_angle_deg=angle, reproj_thr=px)
+                      min_view_angle_deg=angle, reproj_thr=px, map_order=fo.ascending_order)
         got = run_emu(emu, s, obser_thr=thr, angle=angle, thr=px)
         compare(got, ref)
     assert got["counts"][3] > 1                                                  # more than one round: retries from later seeds happened

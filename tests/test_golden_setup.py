@@ -64,7 +64,7 @@ def test_oracles_reproduce_the_fixture():
     clouds = ao.anchor_clouds(split(GOLD["a_xyz"], GOLD["a_scan_ptr"]), GOLD["a_rel"], GOLD["a_win_ptr"], float(GOLD["a_leaf"]))
     assert all(np.array_equal(c, g) for c, g in zip(clouds, split(GOLD["a_cloud_xyz"], GOLD["a_cloud_ptr"])))
     f = fuse_scene_in()
-    tracks = fo.fuse(f["kp_ptr"], f["kp_uv"], f["matches"], f["cams"], f["intr"], f["kp_Xw"], f["kp_valid"])
+    tracks = fo.fuse(f["kp_ptr"], f["kp_uv"], f["matches"], f["cams"], f["intr"], f["kp_Xw"], f["kp_valid"], map_order=fo.ascending_order)   # the file was written under LVBA_FUSE_ORDER_ASCENDING
     gold = golden_tracks()
     assert len(tracks) == len(gold) == 24
     for t, g in zip(tracks, gold):

@@ -245,8 +245,9 @@ def test_device_fusion_pass_equals_reference_source_under_its_container_order(tm
 
 
 def test_ascending_order_is_a_different_but_documented_choice():
-    """What the ABI documents (ascending image id) against what the reference's container does under g++: same logic, other visiting order."""
-    tr = fo.fuse(*fuse_inputs())
+    """The ABI's library-independent alternative (LVBA_FUSE_ORDER_ASCENDING) against what the reference's container does under g++ (the default): same
+    logic, other visiting order."""
+    tr = fo.fuse(*fuse_inputs(), map_order=fo.ascending_order)
     ref = {tuple(map(tuple, G["F_obs"][G["F_obs_ptr"][k]:G["F_obs_ptr"][k + 1]].tolist())) for k in range(len(G["F_Xw"]))}
     mine = {tuple(map(tuple, sorted(t["obs"].tolist()))) for t in tr}
     assert len(tr) == 63 and mine <= {tuple(sorted(r)) for r in ref}                            # every ascending-order track is a reference track

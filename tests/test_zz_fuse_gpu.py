@@ -41,8 +41,8 @@ def compare(got, ref):
                                      (5, dict(no_depth=1.0))])
 def test_fusion_matches_the_oracle(pkg, seed, kw):
     s = fuse_scene.make(seed=seed, **kw)
-    ref = fo.fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"])
-    got = pkg.tracks_fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"])
+    ref = fo.fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"], map_order=fo.ascending_order)
+    got = pkg.tracks_fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"], map_order=pkg.FUSE_ORDER_ASCENDING)
     compare(got, ref)
     sm = got["summary"]
     assert sm["n_tracks"] == len(ref) and sm["n_attempts"] >= sm["n_candidates"] and sm["kernel_launches"] == sm["n_rounds"]
@@ -51,7 +51,7 @@ def test_fusion_matches_the_oracle(pkg, seed, kw):
 def test_fused_tracks_feed_the_visual_lm(pkg):
     """the reference's chain: BuildTracksAndFuse3D -> optimizeCameraPoses (inlier observations only, :1610-1617)"""
     s = fuse_scene.make(seed=7, n_images=24, n_points=400, wrong=0.02)
-    got = pkg.tracks_fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"])
+    got = pkg.tracks_fuse(s["kp_ptr"], s["kp_uv"], s["matches"], s["cams"], s["intr"], s["kp_Xw"], s["kp_valid"], map_order=pkg.FUSE_ORDER_ASCENDING)
     n = len(got["source"])
     assert n > 50
     keep = got["inlier"].astype(bool)

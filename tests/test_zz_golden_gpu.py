@@ -28,7 +28,8 @@ assert np.array_equal(img, G["d_images"]) and info["kernel_launches"] > 0
 clouds = pkg.anchor_clouds(split(G["a_xyz"], G["a_scan_ptr"]), G["a_rel"], G["a_win_ptr"], float(G["a_leaf"]))
 assert all(np.array_equal(c, r) for c, r in zip(clouds, split(G["a_cloud_xyz"], G["a_cloud_ptr"])))
 # ---- B7
-t = pkg.tracks_fuse(G["f_kp_ptr"], G["f_kp_uv"], G["f_matches"], G["f_cams"], G["f_intr"], G["f_kp_Xw"], G["f_kp_valid"])
+t = pkg.tracks_fuse(G["f_kp_ptr"], G["f_kp_uv"], G["f_matches"], G["f_cams"], G["f_intr"], G["f_kp_Xw"], G["f_kp_valid"],
+                    map_order=pkg.FUSE_ORDER_ASCENDING)       # the file holds the ascending-order answer (the container order: tests/test_zzz_ref_gpu.py)
 assert np.array_equal(t["obs_ptr"], G["f_obs_ptr"]) and np.array_equal(t["img"], G["f_obs_img"]) and np.array_equal(t["kp"], G["f_obs_kp"])
 assert np.array_equal(t["inlier"].astype(np.uint8), G["f_inlier"]) and np.array_equal(np.asarray(t["source"], np.uint8), G["f_source"])
 assert np.abs(t["Xw"] - G["f_Xw"]).max() <= 1e-9 * max(1.0, np.abs(G["f_Xw"]).max())

@@ -181,7 +181,7 @@ for k in range(70):
     inl[G["F_obs_ptr"][k] + G["F_inl"][G["F_inl_ptr"][k]:G["F_inl_ptr"][k + 1]]] = True
 assert np.array_equal(t["inlier"].astype(bool), inl)
 assert np.abs(t["Xw"] - G["F_Xw"]).max() <= 1e-9
-a = pkg.tracks_fuse(kp_ptr, kp_uv, G["F_matches"], G["F_cams"], G["F_intr"], Xw, valid)         # the documented default order: another answer here
+a = pkg.tracks_fuse(kp_ptr, kp_uv, G["F_matches"], G["F_cams"], G["F_intr"], Xw, valid, map_order=pkg.FUSE_ORDER_ASCENDING)   # the library-independent order: another answer here
 assert a["summary"]["n_tracks"] == 63
 print('CHILD-OK')
 """ % (str(ROOT), str(ROOT / "tests" / "golden" / "ref_system.npz"))

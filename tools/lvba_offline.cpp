@@ -17,8 +17,8 @@
 //                matches of the COLMAP database (--db FILE, default <data>/<data_config/colmap_db_path>), and write the COLMAP text
 //                model <data>/Colmap/sparse/{images,points3D}.txt (--sparse-dir DIR) — global-lvba_b200/host/lvba_visual_offline.hpp
 //   --no-lidar   data_config/enable_lidar_ba = false: the visual stage starts from the odometry poses
-//   --fuse-order ascending|libstdcxx   visiting order of the track fusion's three unordered_map loops (lvba_fuse_opts::map_order): ascending image
-//                id (default, library independent) or the order of a g++ build of the reference
+//   --fuse-order libstdcxx|ascending   visiting order of the track fusion's three unordered_map loops (lvba_fuse_opts::map_order): the order of a g++
+//                build of the reference (default) or ascending image id (library independent)
 //   --lidar-opt F   skip the LiDAR stage and take its result from F (TUM lines, one per scan — what a previous run wrote)
 //   --check --visual   also load images, image poses and the database, and print their summary and the updated camera poses' checksum
 #include <cstdio>
@@ -39,7 +39,7 @@ int main(int argc, char** argv) {
   double voxel[2] = {0.5, 0.5};                                              // BALM_stage1/2 root_voxel_size defaults (dataset_io.cpp:55-57)
   float eigen[2][4] = {{0.3f, 0.1f, 0.06f, 0.03f}, {0.3f, 0.1f, 0.06f, 0.03f}};   // bavoxel.hpp:17
   bool stage1 = true, check = false, window_rel = false, visual = false, lidar = true, have_config = false;
-  int fuse_order = LVBA_FUSE_ORDER_ASCENDING;
+  int fuse_order = LVBA_FUSE_ORDER_LIBSTDCXX;         // the library's default: what a g++ build of the reference does
   int window = 0;
   double anchor_leaf = 0.1;
   std::string db_path, sparse_dir, lidar_opt;
