@@ -1,8 +1,8 @@
 // fuse_api.cuh — boundary B7: LvbaSystem::BuildTracksAndFuse3D (reference src/lvba_system.cpp:921-1263)
 // as ONE call: pairwise matches + keypoints + per-keypoint depth candidates (boundary B4, lvba_depth_backproject) + camera
 // poses in, fused 3-D landmarks with their observation / inlier lists out — the CSR lvba_visual_lm takes.  The match graph and
-// the retry rounds run on the host (fuse_pipeline.h documents which reference lines they mirror and the one deliberate
-// difference: images are visited in ascending id where the reference iterates an unordered_map); the per-component work
+// the retry rounds run on the host (fuse_pipeline.h documents which reference lines they mirror and the one freedom the
+// reference leaves open: the order of its three unordered_map loops — lvba_fuse_opts::map_order); the per-component work
 // (gating, view-angle filter, DLT, reprojection tests, choice) is one device item per component.  No host path.
 #pragma once
 #include "fuse_pipeline.h"
