@@ -14,7 +14,8 @@ bench quotes, once, and its output is committed (profiles/r02_ref_pin_scale_B.tx
                                            144 M-entry triplet loop per pass) is not run at this size.
 
 bench.py's `parity_C` gate then ties the CUDA path to that same CPU arm at config C on the GPU box.
-TEST INFRASTRUCTURE: reads oracle/, never the product.    python tools/ref_scale_check.py [B] [C]
+  R: the whole damping_iter on 24 random small problems, reference source vs numpy oracle vs port (profiles/r02_ref_pin_scale_R.txt)
+TEST INFRASTRUCTURE: reads oracle/, never the product.    python tools/ref_scale_check.py [B] [C] [R]
 """
 import multiprocessing as mp
 import sys
@@ -97,6 +98,24 @@ def config_c(log, procs=4, parts=16):
     log(f"  H   max|diff| / max|H| = {err / sc:.2e} over {len(br_)} blocks; largest reference entry outside the port's block list {out:.1e}")
 
 
+def random_sweep(log, n=24, seed=123):
+    """Whole damping_iter on random problems (4..70 poses, 3..30 voxels per pose): reference source vs numpy oracle vs C++ port."""
+    from oracle import lidar_oracle as lo
+    rng = np.random.default_rng(seed)
+    worst = 0.0
+    for _ in range(n):
+        W = int(rng.integers(4, 70)); V = int(rng.integers(3 * W, 30 * W)); sd = int(rng.integers(1, 10 ** 6))
+        p = synth.make_problem(W, V, 0, seed=sd, visual=False)
+        a = (p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"])
+        ref = balm_ref.lidar_damping_iter(*a)
+        ora, info = lo.damping_iter(*a)
+        port, _ = cpu_ref.lidar_lm(*a, threads=4)
+        d1, d2 = float(np.abs(ref - ora).max()), float(np.abs(ref - port).max())
+        worst = max(worst, d1, d2)
+        log(f"  W {W:3d} V {V:5d} seed {sd:6d}: {info['iters']:2d} passes, {info['accepted']} accepted; end poses |ref - numpy| {d1:.1e}  |ref - port| {d2:.1e}  (moved {np.abs(ref - p['poses']).max():.3f})")
+    log(f"random sweep: worst end-pose difference {worst:.1e} over {n} problems (north star: final cost 1e-6)")
+
+
 if __name__ == "__main__":
     assert balm_ref.available(), "needs oracle/_ref/libbalm_ref.so (make -C oracle ref, where /root/reference exists)"
     which = [a.upper() for a in sys.argv[1:]] or ["B", "C"]
@@ -110,6 +129,8 @@ if __name__ == "__main__":
         config_b(log)
     if "C" in which:
         config_c(log)
+    if "R" in which:
+        random_sweep(log)
     out = ROOT / "profiles" / ("r02_ref_pin_scale_" + "".join(which) + ".txt")
     out.write_text("\n".join(lines) + "\n")
     print("wrote", out)
