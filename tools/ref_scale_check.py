@@ -96,6 +96,22 @@ def config_c(log, procs=4, parts=16):
     log(f"  residual: reference sum {res:.15e}  port {r:.15e} (or x kept)  rel {min(abs(r - res), abs(r * kept - res)) / abs(res):.2e}")
     log(f"  g   max|diff| / max|g| = {np.abs(g - g_p).max() / np.abs(g).max():.2e}")
     log(f"  H   max|diff| / max|H| = {err / sc:.2e} over {len(br_)} blocks; largest reference entry outside the port's block list {out:.1e}")
+    # the first damped step (u = 0.01, D = diag H: bavoxel.hpp:692-710) solved from the REFERENCE SOURCE's H and g (sparse LU) vs the port's own step
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    rows, cols, vals = [], [], []
+    for k in range(len(br_)):
+        i, j = int(br_[k]), int(bc[k])
+        for (a, b_) in ((i, j), (j, i)) if i != j else ((i, j),):
+            blk = H[6 * a:6 * a + 6, 6 * b_:6 * b_ + 6]
+            r_, c_ = np.meshgrid(np.arange(6 * a, 6 * a + 6), np.arange(6 * b_, 6 * b_ + 6), indexing="ij")
+            rows.append(r_.ravel()); cols.append(c_.ravel()); vals.append(blk.ravel())
+    A = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=H.shape)
+    A = A + 0.01 * sp.diags(A.diagonal())
+    dx_ref = spla.splu(A).solve(-g.ravel())
+    dx_port, _ = cpu_ref.lidar_step(p["vox_ptr"], p["pose_idx"], p["clusters"], p["poses"], u=0.01, threads=8)
+    log(f"  first damped step: |dx(reference-source H, g) - dx(port)| / max|dx| = {np.abs(dx_ref - dx_port.ravel()).max() / np.abs(dx_ref).max():.2e}"
+        f"   (north star: 1e-8 per pose update; backward error of the reference-side solve {np.abs(A @ dx_ref + g.ravel()).max() / np.abs(g).max():.1e})")
 
 
 def random_sweep(log, n=24, seed=123):
