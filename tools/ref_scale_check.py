@@ -14,6 +14,7 @@ bench quotes, once, and its output is committed (profiles/r02_ref_pin_scale_B.tx
                                            144 M-entry triplet loop per pass) is not run at this size.
 
 bench.py's `parity_C` gate then ties the CUDA path to that same CPU arm at config C on the GPU box.
+  V: path B at config C — cost and Jacobians from the reference's own cost functors vs the port / the numpy oracle (profiles/r02_ref_pin_scale_V.txt)
   R: the whole damping_iter on 24 random small problems, reference source vs numpy oracle vs port (profiles/r02_ref_pin_scale_R.txt)
 TEST INFRASTRUCTURE: reads oracle/, never the product.    python tools/ref_scale_check.py [B] [C] [R]
 """
@@ -114,6 +115,29 @@ def config_c(log, procs=4, parts=16):
         f"   (north star: 1e-8 per pose update; backward error of the reference-side solve {np.abs(A @ dx_ref + g.ravel()).max() / np.abs(g).max():.1e})")
 
 
+def config_c_visual(log):
+    """Path B at config C: the cost Ceres would evaluate, from the reference's own cost functors (include/utils.hpp compiled where it lies), against the
+    cost the CPU arm starts its LM from; and the functor Jacobians (Jets) against the numpy oracle's analytic ones on every observation."""
+    from oracle import visual_oracle as vis
+    p = synth.make_config("C")                                   # the bench's problem (LiDAR part generated too: the visual part follows it in the seed's stream)
+    trk = np.repeat(np.arange(len(p["obs_ptr"]) - 1), np.diff(p["obs_ptr"]))
+    t = time.time()
+    r, J = balm_ref.reproj(p["q"][p["obs_cam"]], p["t"][p["obs_cam"]], p["X"][trk], p["obs_uv"], p["intr"], p["sigma_px"], p["sigma_px"])
+    rp, Jp = balm_ref.point_plane(p["X"], p["plane_nd"], p["sigma_plane"])
+    t_ref = time.time() - t
+    tv = vis.valid_tracks(p["plane_nd"])
+    cost_ref = 0.5 * (float((r[tv[trk]] ** 2).sum()) + float((rp[tv] ** 2).sum()))
+    _, _, _, info = cpu_ref.visual_lm(p["q"], p["t"], p["X"], p["plane_nd"], p["obs_ptr"], p["obs_cam"], p["obs_uv"], p["intr"], p["sigma_px"], p["sigma_plane"],
+                                      max_iter=1, threads=8)
+    log(f"config C path B: {len(trk)} observations / {len(p['X'])} tracks through the reference's functors (T = double and T = Jet) in {t_ref:.1f} s")
+    log(f"  cost 1/2 sum r^2: reference functors {cost_ref:.15e}  port {info['cost_first']:.15e}  rel {abs(cost_ref - info['cost_first']) / cost_ref:.2e}")
+    ro, Jq, Jt, JX = vis.reproj_eval(p["q"][p["obs_cam"]], p["t"][p["obs_cam"]], p["X"][trk], np.asarray(p["obs_uv"], np.float32).astype(np.float64), p["intr"], p["sigma_px"])
+    qn = p["q"][p["obs_cam"]]; qn = qn / np.linalg.norm(qn, axis=1, keepdims=True)
+    Jq_ref = J[:, :, :4] @ vis.plus_jacobian(qn)
+    sc = max(np.abs(J).max(), 1.0)
+    log(f"  residuals vs numpy {np.abs(ro - r).max() / np.abs(r).max():.2e}; Jacobians (Jet vs analytic) d/dq {np.abs(Jq - Jq_ref).max() / sc:.2e}  d/dt {np.abs(Jt - J[:, :, 4:7]).max() / sc:.2e}  d/dX {np.abs(JX - J[:, :, 7:]).max() / sc:.2e}")
+
+
 def random_sweep(log, n=24, seed=123):
     """Whole damping_iter on random problems (4..70 poses, 3..30 voxels per pose): reference source vs numpy oracle vs C++ port."""
     from oracle import lidar_oracle as lo
@@ -145,6 +169,8 @@ if __name__ == "__main__":
         config_b(log)
     if "C" in which:
         config_c(log)
+    if "V" in which:
+        config_c_visual(log)
     if "R" in which:
         random_sweep(log)
     out = ROOT / "profiles" / ("r02_ref_pin_scale_" + "".join(which) + ".txt")
