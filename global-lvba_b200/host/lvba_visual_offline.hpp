@@ -14,6 +14,7 @@
 // the reference takes the same path whenever the database matches the image list (:693-700).
 // SQLite is bound at run time (dlopen of libsqlite3.so.0; its C API is declared below because this image has no sqlite3.h).
 #pragma once
+#include <limits>
 #include <dlfcn.h>
 
 #include <array>
@@ -542,10 +543,11 @@ inline int run_visual_ba(const Config& cfg, const std::vector<Cloud*>& pl_fulls,
 
 // ------------------------------------------------------------------------------------------------ COLMAP text model
 // images.txt as written at :2018-2024: `k qw qx qy qz tx ty tz 1 k.jpg` then the empty observation line `0.0 0.0 -1`
-inline bool write_images_txt(const std::string& file, const std::vector<M3>& Rcw, const std::vector<V3>& tcw) {
+inline bool write_images_txt(const std::string& file, const std::vector<M3>& Rcw, const std::vector<V3>& tcw, const std::vector<uint8_t>* listed = nullptr) {
   FILE* f = std::fopen(file.c_str(), "w");
   if (!f) return false;
   for (size_t k = 0; k < Rcw.size(); ++k) {
+    if (listed && k < listed->size() && !(*listed)[k]) continue;          // the reference skips an image without LiDAR in its window before this line (:1994-1997)
     double q[4];
     eigen_quaternion(Rcw[k], q);
     std::fprintf(f, "%zu %.6f %.6f %.6f %.6f %.6f %.6f %.6f 1 %zu.jpg\n0.0 0.0 -1\n", k, q[0], q[1], q[2], q[3], tcw[k](0), tcw[k](1), tcw[k](2), k);
@@ -562,6 +564,89 @@ inline bool write_points3D_txt(const std::string& file, const std::vector<FusedT
     if (t < used.size() && !used[t]) continue;
     std::fprintf(f, "%zu %.6f %.6f %.6f 128 128 128 0\n", i++, tracks[t].Xw_fused[0], tracks[t].Xw_fused[1], tracks[t].Xw_fused[2]);
   }
+  return std::fclose(f) == 0;
+}
+
+// ------------------------------------------------------------------------------------------------ the reference's points3D.txt
+// VisualizeOptComparison (src/lvba_system.cpp:1932-2143) does not write the fused landmarks: per image it takes the scans within +-0.5 s (:1971-1974),
+// moves them to the world with the optimised LiDAR poses and stores them as FLOAT (:1980-1986), keeps per pixel (rounded projection, :2043-2045) the point
+// nearest to the camera (`zc + 1e-6f < zbuf`, :2050), appends the survivors in pixel order (:2064-2067), and after all images thins the union with
+// down_sampling_voxel2 at colmap_output/filter_size_points3D (:2119).  The colour comes from the decoded image — image decoding is outside this library, so
+// the rows below carry (128, 128, 128); positions and the choice of points are the reference's.  An image whose window holds no LiDAR point is skipped —
+// in images.txt too (:1994-1997 precede the pose line): `written` reports which images the reference would list.
+// The reference returns the thinned set in unordered_map order; here the rows follow ascending voxel key.
+struct LidarPoint3D { float x, y, z; };
+inline void colmap_points_from_lidar(const Config& cfg, const std::vector<Cloud*>& pl_fulls, const std::vector<Pose>& x_buf_opt, const std::vector<double>& images_ids,
+                                     const std::vector<M3>& Rcw, const std::vector<V3>& tcw, std::vector<LidarPoint3D>& out, std::vector<uint8_t>* written = nullptr) {
+  const int W = cfg.width, H = cfg.height;
+  std::vector<LidarPoint3D> merged;
+  if (written) written->assign(images_ids.size(), 0);
+  std::vector<float> zbuf;
+  std::vector<LidarPoint3D> pix;
+  for (size_t k = 0; k < images_ids.size() && k < Rcw.size(); ++k) {
+    std::vector<LidarPoint3D> cloud;
+    for (size_t idx = 0; idx < x_buf_opt.size() && idx < pl_fulls.size(); ++idx) {
+      if (std::fabs(x_buf_opt[idx].t - images_ids[k]) > 0.5) continue;
+      const M3 R = to_m3(x_buf_opt[idx].R);
+      const V3 p = to_v3(x_buf_opt[idx].p);
+      for (const auto& pb : pl_fulls[idx]->points) {
+        const V3 xb{{(double)pb.x, (double)pb.y, (double)pb.z}};
+        const V3 xw = mul(R, xb);
+        cloud.push_back(LidarPoint3D{(float)(xw(0) + p(0)), (float)(xw(1) + p(1)), (float)(xw(2) + p(2))});
+      }
+    }
+    if (cloud.empty()) continue;
+    if (written) (*written)[k] = 1;
+    zbuf.assign((size_t)W * H, std::numeric_limits<float>::infinity());
+    pix.assign((size_t)W * H, LidarPoint3D{0, 0, 0});
+    const float eps = 1e-6f;
+    for (const auto& q : cloud) {
+      const V3 xw{{(double)q.x, (double)q.y, (double)q.z}};
+      const V3 rc = mul(Rcw[k], xw);
+      const double X = rc(0) + tcw[k](0), Y = rc(1) + tcw[k](1), Z = rc(2) + tcw[k](2);          // projectWorldToPixel, include/utils.hpp:183-205
+      if (!(std::isfinite(X) && std::isfinite(Y) && std::isfinite(Z)) || Z <= 1e-12) continue;
+      const double x = X / Z, y = Y / Z;
+      const double r2 = x * x + y * y, r4 = r2 * r2;
+      const double radial = 1.0 + cfg.d0 * r2 + cfg.d1 * r4;
+      const double x_tan = 2.0 * cfg.d2 * x * y + cfg.d3 * (r2 + 2.0 * x * x);
+      const double y_tan = cfg.d2 * (r2 + 2.0 * y * y) + 2.0 * cfg.d3 * x * y;
+      const double xd = x * radial + x_tan, yd = y * radial + y_tan;
+      if (!(std::isfinite(xd) && std::isfinite(yd))) continue;
+      const double u = cfg.fx * xd + cfg.cx, v = cfg.fy * yd + cfg.cy;
+      if (!(std::isfinite(u) && std::isfinite(v))) continue;
+      const int uu = (int)std::round(u), vv = (int)std::round(v);
+      if (uu < 0 || uu >= W || vv < 0 || vv >= H) continue;
+      const size_t i = (size_t)vv * W + uu;
+      if (Z + eps < zbuf[i]) { zbuf[i] = (float)Z; pix[i] = q; }
+    }
+    for (size_t i = 0; i < zbuf.size(); ++i) if (std::isfinite(zbuf[i])) merged.push_back(pix[i]);
+  }
+  // down_sampling_voxel2 (include/BALM/tools.hpp:301-359): per voxel the original point nearest to the voxel centre, the first one on ties
+  out.clear();
+  const double leaf = cfg.filter_size_points3D;
+  if (leaf < 0.001) { out = merged; return; }
+  struct Best { double d2; size_t i; };
+  std::map<std::array<int64_t, 3>, Best> best;
+  for (size_t i = 0; i < merged.size(); ++i) {
+    const float c[3] = {merged[i].x, merged[i].y, merged[i].z};
+    std::array<int64_t, 3> key; double d2 = 0.0, d[3];
+    for (int j = 0; j < 3; ++j) {
+      float loc = (float)(c[j] / leaf);
+      if (loc < 0.f) loc -= 1.f;
+      key[j] = (int64_t)loc;
+      d[j] = (double)c[j] - ((double)key[j] + 0.5) * leaf;
+    }
+    d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    auto it = best.find(key);
+    if (it == best.end()) best.emplace(key, Best{d2, i});
+    else if (d2 < it->second.d2) it->second = Best{d2, i};
+  }
+  for (const auto& kv : best) out.push_back(merged[kv.second.i]);
+}
+inline bool write_points3D_lidar_txt(const std::string& file, const std::vector<LidarPoint3D>& pts) {
+  FILE* f = std::fopen(file.c_str(), "w");
+  if (!f) return false;
+  for (size_t i = 0; i < pts.size(); ++i) std::fprintf(f, "%zu %.6f %.6f %.6f 128 128 128 0\n", i, pts[i].x, pts[i].y, pts[i].z);
   return std::fclose(f) == 0;
 }
 

@@ -104,6 +104,14 @@ class System:
         return dict(frame_ts=fts, frame_poses=fp, scans=[xyz[sp[i]:sp[i + 1]] for i in range(len(sp) - 1)], intensity=inten, image_ts=its, image_poses=ip,
                     cam=cam, data_path=dp, db_path=db)
 
+    def init_from_dataset(self):
+        """initFromDatasetIO (:448-507) on what the reference's own loader read (the constructor ran it on data_config/data_path)."""
+        d = self.dataset()
+        self.W = len(d["frame_ts"]); self.M = len(d["image_ts"]); self.width = int(d["cam"][0]); self.height = int(d["cam"][1])
+        self.n_points = sum(len(x) for x in d["scans"])
+        self.lib.sys_init_from_dataset(self.h)
+        return d
+
     # ---- inputs
     def set_lidar(self, scans, poses, ts=None):
         ptr, xyz = _scans(scans)
@@ -176,6 +184,10 @@ class System:
         kp_ptr = np.zeros(self.M + 1, np.int64); kp_uv = np.zeros((nk.value, 2), np.float32); m = np.zeros((nm.value, 4), np.int32)
         self.lib.sys_get_frontend(self.h, _p(kp_ptr), _p(kp_uv), _p(m))
         return ok, kp_ptr, kp_uv, m
+
+    def colmap_export(self, dataset_path, grey=128):
+        """VisualizeOptComparison: writes <dataset_path>/Colmap/sparse/images.txt and points3D.txt (every image = one grey value)."""
+        self.lib.sys_colmap_export(self.h, str(dataset_path).encode(), C.c_int(self.width), C.c_int(self.height), C.c_int(grey))
 
     def build_tracks(self):
         no = C.c_int64(); ni = C.c_int64()

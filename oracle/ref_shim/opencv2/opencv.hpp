@@ -9,6 +9,7 @@
 #include <set>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <iomanip>
 #include <iostream>
 #include <memory>
@@ -45,7 +46,10 @@ class Mat {
   static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
   static Mat zeros(Size sz, int type) { return Mat(sz.height, sz.width, type); }
   static int elem(int type) { return type == CV_32FC1 ? 4 : type == CV_16UC1 ? 2 : type == CV_64F ? 8 : type == CV_8UC3 ? 3 : type == CV_8UC1 ? 1 : 8; }
-  void fill(double v) { if (type_ == CV_32FC1) for (size_t i = 0; i < (size_t)rows * cols; ++i) reinterpret_cast<float*>(buf_->data())[i] = (float)v; }
+  void fill(double v) {
+    if (type_ == CV_32FC1) for (size_t i = 0; i < (size_t)rows * cols; ++i) reinterpret_cast<float*>(buf_->data())[i] = (float)v;
+    else if (type_ == CV_8UC3 || type_ == CV_8UC1) std::memset(buf_->data(), (int)v, buf_->size());
+  }
   Mat& setTo(const Scalar& s) { fill(s.v[0]); return *this; }
   unsigned char* data = nullptr;          // only handed to SiftGPU (out of scope)
   Size size() const { return Size(cols, rows); }
@@ -75,7 +79,14 @@ enum { INTER_LINEAR = 1, INTER_CUBIC = 2, COLOR_BGR2Lab = 44, COLOR_Lab2BGR = 56
        LINE_AA = 16, LINE_8 = 8, FILLED = -1, FONT_HERSHEY_SIMPLEX = 0, BORDER_CONSTANT = 0 };
 struct RNG { explicit RNG(unsigned long long = 0) {} int uniform(int a, int) { return a; } double uniform(double a, double) { return a; } };
 // image files, drawing, remapping: visualisation / export only — nothing on the path reads what they produce
-inline Mat imread(const std::string&, int = IMREAD_COLOR) { return Mat(); }
+// imread: no decoder here.  The tests of the COLMAP export (VisualizeOptComparison, src/lvba_system.cpp:1932-2143) ask for "an image of this size in
+// one colour" through stub_image(): every file then reads as rows x cols pixels of (grey, grey, grey); by default files read as empty (as before).
+struct StubImage { int rows = 0, cols = 0, grey = 128; };
+inline StubImage& stub_image() { static StubImage s; return s; }
+inline Mat imread(const std::string&, int = IMREAD_COLOR) {
+  const StubImage& s = stub_image();
+  return s.rows > 0 ? Mat(s.rows, s.cols, CV_8UC3, Scalar(s.grey)) : Mat();
+}
 inline bool imwrite(const std::string&, const Mat&) { return true; }
 inline void circle(Mat&, Point, int, const Scalar&, int = 1, int = LINE_8, int = 0) {}
 inline void line(Mat&, Point, Point, const Scalar&, int = 1, int = LINE_8, int = 0) {}
@@ -84,7 +95,7 @@ inline void rectangle(Mat&, Rect, const Scalar&, int = 1, int = LINE_8, int = 0)
 inline void putText(Mat&, const std::string&, Point, int, double, const Scalar&, int = 1, int = LINE_8, bool = false) {}
 inline void hconcat(const Mat&, const Mat&, Mat&) {}
 inline void vconcat(const Mat&, const Mat&, Mat&) {}
-inline void remap(const Mat&, Mat&, const Mat&, const Mat&, int, int = BORDER_CONSTANT, const Scalar& = Scalar()) { std::abort(); }
+inline void remap(const Mat& src, Mat& dst, const Mat&, const Mat&, int, int = BORDER_CONSTANT, const Scalar& = Scalar()) { dst = src.clone(); }   // undistortion of an image that is only written to disk
 inline void initUndistortRectifyMap(const Mat&, const Mat&, const Mat&, const Mat&, Size, int, Mat&, Mat&) {}
 [[noreturn]] inline void out_of_scope() { std::abort(); }
 inline void resize(const Mat&, Mat&, Size, double = 0, double = 0, int = INTER_LINEAR) { out_of_scope(); }

@@ -282,6 +282,19 @@ void sys_get_frontend(void* h, int64_t* kp_ptr, float* kp_uv, int32_t* matches) 
     for (int b = a + 1; b < M; ++b)
       for (auto& pr : s.all_matches_[lvba::pairIndex(a, b, M)]) { matches[4 * m] = a; matches[4 * m + 1] = pr.first; matches[4 * m + 2] = b; matches[4 * m + 3] = pr.second; ++m; }
 }
+// The COLMAP text model as the reference writes it — VisualizeOptComparison (:1932-2143, reached through pubRGBCloud -> showTracksComparePCL at the end of
+// runVisualBAWithLidarAssist): images.txt (one pose line + "0.0 0.0 -1" per image that loads and has LiDAR within +-0.5 s) and points3D.txt (the LiDAR points
+// nearest per pixel in every image, merged, down_sampling_voxel2 at colmap_output/filter_size_points3D, coloured from the image).  There is no image decoder
+// here: every image file reads as width x height pixels of one grey value (ref_shim/opencv2/opencv.hpp), so the colours written are that grey.
+// Uses Rcw_all_ / Rcw_all_optimized_ as generateDepthWithVoxel left them; frees dataset_io_->pl_fulls_ at the end, as the reference does.
+void sys_colmap_export(void* h, const char* dataset_path, int width, int height, int grey) {
+  auto& s = *static_cast<Sys*>(h)->s;
+  s.dataset_path_ = dataset_path;
+  cv::stub_image().rows = height; cv::stub_image().cols = width; cv::stub_image().grey = grey;
+  s.VisualizeOptComparison(s.images_ids_, true);
+  s.fout_poses_after.close(); s.fout_points_after.close();
+  cv::stub_image().rows = 0;
+}
 // BuildTracksAndFuse3D (:921-1263).  Returns the number of tracks; sizes through the two counters.
 int64_t sys_build_tracks(void* h, int64_t* n_obs, int64_t* n_inl) {
   auto& s = *static_cast<Sys*>(h)->s;

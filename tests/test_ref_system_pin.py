@@ -517,3 +517,45 @@ def test_depth_rendering_differential_reference_source_vs_oracle(seed, F, M, siz
     assert np.abs(c1 - sc["cams"]).max() <= 1e-12
     img = dep.render(sc["scans"], sc["poses"], sc["frame_ts"], c1, img_ts, sc["intr"], size[0], size[1])
     assert np.array_equal(img, d) and not d[0].any() and (d[1:] > 0).sum() > 500
+
+
+# ------------------------------------------------------------------------------------------------ N4: the COLMAP text model
+@needs_ref
+def test_colmap_export_equals_the_reference_writer(pkg, tmp_path):
+    """VisualizeOptComparison (src/lvba_system.cpp:1932-2143), run from its own source on a dataset its own loader read (every image file = one grey value:
+    there is no decoder on either side), against `lvba_offline --check --visual --points3d lidar` (host code of global-lvba_b200/host/lvba_visual_offline.hpp,
+    no GPU): images.txt line for line, points3D.txt row for row as a set (the reference lists the thinned points in unordered_map order)."""
+    import subprocess
+    import visual_scene as vs
+    from oracle import dataset_writer as dw
+    data = tmp_path / "data"
+    g = vs.make(data, seed=4, W=6, n_per_scan=6000, n_landmarks=60)
+    for i, t in enumerate(g["ts"]):                                        # the stand-in PCD reader under the reference has no LZF
+        if i % 3 == 2:
+            dw.write_pcd(data / "all_pcd_body" / f"{t:.6f}.pcd", g["scans"][i], np.arange(len(g["scans"][i])) % 7, "binary")
+    exe = tmp_path / "lvba_offline"
+    cmd = ["g++", "-std=c++17", "-O2", "-I", str(ROOT / "include"), str(ROOT / "tools" / "lvba_offline.cpp"), "-o", str(exe),
+           str(pkg.LIB_PATH), f"-Wl,-rpath,{pkg.LIB_PATH.parent}", "-L/usr/local/cuda/lib64", "-lcudart", "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    mine = tmp_path / "mine"
+    r = subprocess.run([str(exe), "--data", str(data), "--config", str(data / "config.yaml"), "--check", "--visual", "--points3d", "lidar", "--sparse-dir", str(mine)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    F = vs.INTR_FULL
+    S = sr.System({"data_config/data_path": str(data) + "/", "data_config/colmap_db_path": "Colmap/colmap.db", "data_config/image_sample_step": 2,
+                   "cam_model/cam_width": vs.WIDTH_FULL, "cam_model/cam_height": vs.HEIGHT_FULL, "cam_model/scale": vs.SCALE, "cam_model/cam_fx": F[0],
+                   "cam_model/cam_fy": F[1], "cam_model/cam_cx": F[2], "cam_model/cam_cy": F[3], "cam_model/cam_d0": F[4], "cam_model/cam_d1": F[5],
+                   "cam_model/cam_d2": F[6], "cam_model/cam_d3": F[7], "extrin_calib/Rcl": vs.RCL.ravel(), "extrin_calib/Pcl": vs.PCL,
+                   "extrin_calib/extrinsic_R": np.eye(3).ravel(), "extrin_calib/extrinsic_T": np.zeros(3)})
+    d = S.init_from_dataset()
+    assert len(d["frame_ts"]) == 6 and len(d["image_ts"]) == 6
+    S.build_grid(); S.update_camera_poses(); S.generate_depth()
+    S.colmap_export(str(data) + "/")
+    S.close()
+    ref_dir = data / "Colmap" / "sparse"
+    assert (mine / "images.txt").read_text() == (ref_dir / "images.txt").read_text()
+    rows = lambda f: sorted(" ".join(ln.split()[1:]) for ln in f.read_text().splitlines())  # noqa: E731
+    a, b = rows(mine / "points3D.txt"), rows(ref_dir / "points3D.txt")
+    assert len(a) == len(b) > 2000 and a == b
+    assert all(ln.endswith("128 128 128 0") for ln in a[:50])

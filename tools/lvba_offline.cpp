@@ -17,6 +17,11 @@
 //                matches of the COLMAP database (--db FILE, default <data>/<data_config/colmap_db_path>), and write the COLMAP text
 //                model <data>/Colmap/sparse/{images,points3D}.txt (--sparse-dir DIR) — global-lvba_b200/host/lvba_visual_offline.hpp
 //   --no-lidar   data_config/enable_lidar_ba = false: the visual stage starts from the odometry poses
+//   --points3d landmarks|lidar   what points3D.txt holds: the fused landmarks the visual problem kept, in grey (default), or the reference's own
+//                selection (VisualizeOptComparison, src/lvba_system.cpp:1932-2143): the LiDAR points nearest per pixel in every image, merged and thinned at
+//                colmap_output/filter_size_points3D — positions as the reference writes them, colour grey (no image decoder here); images without LiDAR in
+//                their +-0.5 s window are left out of images.txt as the reference leaves them out.  With --check --visual this export alone runs (host
+//                code, no GPU) from the odometry cameras
 //   --fuse-order libstdcxx|ascending   visiting order of the track fusion's three unordered_map loops (lvba_fuse_opts::map_order): the order of a g++
 //                build of the reference (default) or ascending image id (library independent)
 //   --lidar-opt F   skip the LiDAR stage and take its result from F (TUM lines, one per scan — what a previous run wrote)
@@ -39,6 +44,7 @@ int main(int argc, char** argv) {
   double voxel[2] = {0.5, 0.5};                                              // BALM_stage1/2 root_voxel_size defaults (dataset_io.cpp:55-57)
   float eigen[2][4] = {{0.3f, 0.1f, 0.06f, 0.03f}, {0.3f, 0.1f, 0.06f, 0.03f}};   // bavoxel.hpp:17
   bool stage1 = true, check = false, window_rel = false, visual = false, lidar = true, have_config = false;
+  bool points3d_lidar = false;
   int fuse_order = LVBA_FUSE_ORDER_LIBSTDCXX;         // the library's default: what a g++ build of the reference does
   int window = 0;
   double anchor_leaf = 0.1;
@@ -61,6 +67,7 @@ int main(int argc, char** argv) {
     else if (a == "--visual") visual = true;
     else if (a == "--no-lidar") lidar = false;
     else if (a == "--fuse-order") { const std::string v = next(); if (v == "libstdcxx") fuse_order = LVBA_FUSE_ORDER_LIBSTDCXX; else if (v == "ascending") fuse_order = LVBA_FUSE_ORDER_ASCENDING; else return 64; }
+    else if (a == "--points3d") { const std::string v = next(); if (v == "lidar") points3d_lidar = true; else if (v == "landmarks") points3d_lidar = false; else return 64; }
     else if (a == "--db") db_path = next();
     else if (a == "--lidar-opt") lidar_opt = next();
     else if (a == "--sparse-dir") sparse_dir = next();
@@ -179,6 +186,21 @@ int main(int argc, char** argv) {
     }
     for (const auto& im : keypoints) { n_kp += (long long)im.size(); for (const auto& k : im) kp_sum += (double)k.x + 2.0 * (double)k.y; }
     for (size_t k = 0; k < matches.size(); ++k) { n_match += (long long)matches[k].size(); for (const auto& m : matches[k]) match_sum += (long long)(k + 1) * (m.first + 3LL * m.second); }
+    if (points3d_lidar) {
+      std::vector<off::M3> Rcw_all; std::vector<off::V3> tcw_all;
+      for (const auto& p : cam) { off::M3 Rcw; off::V3 tcw; off::world_to_camera(p, Rci, tci, Rcw, tcw); Rcw_all.push_back(Rcw); tcw_all.push_back(tcw); }
+      std::vector<off::LidarPoint3D> lp; std::vector<uint8_t> listed;
+      off::colmap_points_from_lidar(cfg, frame_clouds, frames, images_ids, Rcw_all, tcw_all, lp, &listed);
+      if (sparse_dir.empty()) sparse_dir = data + "Colmap/sparse/";
+      if (sparse_dir.back() != '/') sparse_dir += '/';
+      std::error_code ec2;
+      std::filesystem::create_directories(sparse_dir, ec2);
+      if (!off::write_images_txt(sparse_dir + "images.txt", Rcw_all, tcw_all, &listed) || !off::write_points3D_lidar_txt(sparse_dir + "points3D.txt", lp)) {
+        std::fprintf(stderr, "cannot write the COLMAP text model under %s\n", sparse_dir.c_str());
+        return 1;
+      }
+      std::printf("{\"written\": \"%s\", \"points3D\": %zu, \"kind\": \"lidar\"}\n", sparse_dir.c_str(), lp.size());
+    }
     std::printf("{\"images\": %zu, \"first_image\": %.6f, \"width\": %d, \"height\": %d, \"fx\": %.9f, \"keypoints\": %lld, \"kp_sum\": %.6f, \"matches\": %lld, \"match_sum\": %lld, \"cam_sum\": %.9f}\n",
                 images_ids.size(), images_ids[0], cfg.width, cfg.height, cfg.fx, n_kp, kp_sum, n_match, match_sum, cam_sum);
     return 0;
@@ -199,9 +221,11 @@ int main(int argc, char** argv) {
   if (sparse_dir.back() != '/') sparse_dir += '/';
   std::error_code ec;
   std::filesystem::create_directories(sparse_dir, ec);
-  if (!off::write_images_txt(sparse_dir + "images.txt", vr.Rcw_after, vr.tcw_after) ||
+  std::vector<off::LidarPoint3D> lp; std::vector<uint8_t> listed;
+  if (points3d_lidar) off::colmap_points_from_lidar(cfg, frame_clouds, frames, images_ids, vr.Rcw_after, vr.tcw_after, lp, &listed);
+  if (!off::write_images_txt(sparse_dir + "images.txt", vr.Rcw_after, vr.tcw_after, points3d_lidar ? &listed : nullptr) ||
       !off::write_images_txt(sparse_dir + "images_before.txt", vr.Rcw_before, vr.tcw_before) ||
-      !off::write_points3D_txt(sparse_dir + "points3D.txt", vr.tracks, vr.track_used)) {
+      !(points3d_lidar ? off::write_points3D_lidar_txt(sparse_dir + "points3D.txt", lp) : off::write_points3D_txt(sparse_dir + "points3D.txt", vr.tracks, vr.track_used))) {
     std::fprintf(stderr, "cannot write the COLMAP text model under %s\n", sparse_dir.c_str());
     return 1;
   }
