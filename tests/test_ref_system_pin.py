@@ -533,6 +533,11 @@ def test_colmap_export_equals_the_reference_writer(pkg, tmp_path):
     for i, t in enumerate(g["ts"]):                                        # the stand-in PCD reader under the reference has no LZF
         if i % 3 == 2:
             dw.write_pcd(data / "all_pcd_body" / f"{t:.6f}.pcd", g["scans"][i], np.arange(len(g["scans"][i])) % 7, "binary")
+    # one more image 5 s after the last scan: no LiDAR within +-0.5 s -> the reference lists it neither in images.txt nor in the points (:1994-1997)
+    image_ts = list(g["image_ts"]) + [g["image_ts"][-1] + 5.0]
+    image_poses = np.vstack([g["image_poses"], g["image_poses"][-1:]])
+    dw.write_image_set(data, image_ts, image_poses, extra_between=1)
+    dw.write_colmap_db(data / "Colmap" / "colmap.db", image_ts, g["keypoints"] + [np.zeros((0, 2), np.float32)], {k: np.array(v) for k, v in g["pair"].items() if k != (0, 1)})
     exe = tmp_path / "lvba_offline"
     cmd = ["g++", "-std=c++17", "-O2", "-I", str(ROOT / "include"), str(ROOT / "tools" / "lvba_offline.cpp"), "-o", str(exe),
            str(pkg.LIB_PATH), f"-Wl,-rpath,{pkg.LIB_PATH.parent}", "-L/usr/local/cuda/lib64", "-lcudart", "-ldl"]
@@ -549,12 +554,13 @@ def test_colmap_export_equals_the_reference_writer(pkg, tmp_path):
                    "cam_model/cam_d2": F[6], "cam_model/cam_d3": F[7], "extrin_calib/Rcl": vs.RCL.ravel(), "extrin_calib/Pcl": vs.PCL,
                    "extrin_calib/extrinsic_R": np.eye(3).ravel(), "extrin_calib/extrinsic_T": np.zeros(3)})
     d = S.init_from_dataset()
-    assert len(d["frame_ts"]) == 6 and len(d["image_ts"]) == 6
+    assert len(d["frame_ts"]) == 6 and len(d["image_ts"]) == 7
     S.build_grid(); S.update_camera_poses(); S.generate_depth()
     S.colmap_export(str(data) + "/")
     S.close()
     ref_dir = data / "Colmap" / "sparse"
     assert (mine / "images.txt").read_text() == (ref_dir / "images.txt").read_text()
+    assert len((ref_dir / "images.txt").read_text().splitlines()) == 12          # six of the seven images: the late one is left out on both sides
     rows = lambda f: sorted(" ".join(ln.split()[1:]) for ln in f.read_text().splitlines())  # noqa: E731
     a, b = rows(mine / "points3D.txt"), rows(ref_dir / "points3D.txt")
     assert len(a) == len(b) > 2000 and a == b
