@@ -86,7 +86,9 @@ def test_window_batch_argument_checks_need_no_gpu(pkg):
     if pkg.device_count() == 0:
         with pytest.raises(pkg.LvbaError) as e:
             pkg.lidar_lm_batch(wp, np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros((0, 10)), p_)
-        assert e.value.status == -2                                          # no CPU fallback
+        assert e.value.status == -2
+    o = pkg.FuseOpts(); pkg.load_library().lvba_fuse_default_opts(__import__("ctypes").byref(o))
+    assert o.map_order == pkg.FUSE_ORDER_LIBSTDCXX == 1 and pkg.FUSE_ORDER_ASCENDING == 0      # the default is the order of a g++ build of the reference                                          # no CPU fallback
 
 
 def test_voxel_map_argument_checks_need_no_gpu(pkg):
@@ -234,10 +236,11 @@ def test_track_fusion_argument_checks_need_no_gpu(pkg):
     bad_intr = intr.copy(); bad_intr[0] = np.nan
     bad_X = X.copy(); bad_X[2, 1] = np.nan
     cases = [dict(kp_ptr=np.array([1, 2, 4], np.int64)), dict(kp_ptr=np.array([0, 3, 2], np.int64)), dict(cams=bad_cams), dict(intr=bad_intr),
-             dict(kp_Xw=bad_X), dict(obser_thr=0), dict(reproj_thr=-1.0), dict(depth_gate=float("nan")), dict(min_view_angle_deg=float("inf"))]
+             dict(kp_Xw=bad_X), dict(obser_thr=0), dict(reproj_thr=-1.0), dict(depth_gate=float("nan")), dict(min_view_angle_deg=float("inf")),
+             dict(map_order=7), dict(map_order=-1)]
     for kw in cases:
         a = dict(kp_ptr=kp_ptr, kp_uv=uv, matches=m, cams=cams, intr=intr, kp_Xw=X, kp_valid=valid)
-        opt = {k: kw.pop(k) for k in list(kw) if k in ("obser_thr", "reproj_thr", "depth_gate", "min_view_angle_deg")}
+        opt = {k: kw.pop(k) for k in list(kw) if k in ("obser_thr", "reproj_thr", "depth_gate", "min_view_angle_deg", "map_order")}
         a.update(kw)
         with pytest.raises(pkg.LvbaError) as e:
             pkg.tracks_fuse(a["kp_ptr"], a["kp_uv"], a["matches"], a["cams"], a["intr"], a["kp_Xw"], a["kp_valid"], **opt)
