@@ -565,3 +565,25 @@ def test_colmap_export_equals_the_reference_writer(pkg, tmp_path):
     a, b = rows(mine / "points3D.txt"), rows(ref_dir / "points3D.txt")
     assert len(a) == len(b) > 2000 and a == b
     assert all(ln.endswith("128 128 128 0") for ln in a[:50])
+
+
+@needs_ref
+def test_lidar_half_live_without_the_window_stage():
+    """window_ba/enable = false (:217-225): the global stages run on the frames themselves — the path `lvba_offline` takes without --window."""
+    scans, poses = synth.make_scan_scene(41, W=6, n_per_scan=2500)
+    rng = np.random.default_rng(41)
+    noisy = poses.copy()
+    for i in range(6):
+        noisy[i, :9] = (noisy[i, :9].reshape(3, 3) @ synth.so3_exp(rng.normal(0, 0.004, (1, 3)))[0]).ravel(); noisy[i, 9:] += rng.normal(0, 0.01, 3)
+    s1r = np.array([0.3, 0.1, 0.06, 0.03], np.float32); s2r = np.array([0.08] * 4, np.float32)
+    sr.set_eigen_ratio_array(s1r)
+    S = sr.System()
+    S.set_lidar(scans, noisy)
+    S.set_stages(False, 10, 0.1, False, True, 1.0, s1r, 0.5, s2r)
+    out = S.run_lidar_ba()
+    S.close()
+    x = noisy
+    for vs_, er in ((1.0, s1r), (0.5, s2r)):
+        vp, pi, cl, _ = vox.voxelize(scans, x, vs_, er)
+        x, _ = lo.damping_iter(vp, pi, cl, x)
+    assert np.abs(out - x).max() <= 1e-9 and np.abs(out - noisy).max() > 1e-3
