@@ -50,7 +50,7 @@ struct Params {
 };
 
 // ------------------------------------------------------------------------------------------------ container order (map_order = 1)
-// std::__detail::_Prime_rehash_policy::_M_next_bkt of GNU libstdc++ (GCC 13; the table has not changed since 4.x): bucket count after
+// std::__detail::_Prime_rehash_policy::_M_next_bkt of GNU libstdc++ (read out of GCC 13.3's library by calling it for every n): bucket count after
 // reserve(n) with max_load_factor 1.  Table entries as the library publishes them (up to 2.0e9: far beyond any component).
 inline const uint32_t* stl_prime_table(int* n) {
   static const uint32_t primes[] = {
