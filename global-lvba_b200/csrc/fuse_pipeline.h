@@ -73,7 +73,7 @@ inline const uint32_t* stl_prime_table(int* n) {
 // `primes` / `n_primes`: the table above, in the memory space of the caller (host: stl_prime_table; device: a copy uploaded by run())
 LVBA_HD uint32_t stl_bucket_count(uint32_t n, const uint32_t* primes, int n_primes) {
   const unsigned char fast[14] = {2, 2, 2, 3, 5, 5, 7, 7, 11, 11, 11, 11, 13, 13};
-  if (n == 0) return 1;
+  if (n == 0) return 2;               // reserve(0) = rehash(0): the container asks for room for one more element, _M_next_bkt(1) = 2
   if (n < 14) return fast[n];
   int lo = 0, hi = n_primes;
   while (lo < hi) { const int mid = (lo + hi) / 2; if (primes[mid] < n) lo = mid + 1; else hi = mid; }      // first entry >= n

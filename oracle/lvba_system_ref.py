@@ -54,6 +54,11 @@ def track_helpers(obs_ptr, obs_cam, obs_uv, cams, intr, Xw=None, min_count=3):
     return (out if Xw is None else xin), mean, cnt, ok.astype(bool)
 
 
+def bucket_count_after_reserve(n):
+    lib = load(); lib.sys_bucket_count_after_reserve.restype = C.c_uint64
+    return int(lib.sys_bucket_count_after_reserve(C.c_uint64(int(n))))
+
+
 def unordered_map_order(reserve, keys):
     """Iteration order of std::unordered_map<int,int> after reserve(reserve) and inserting `keys` (distinct) in this order."""
     k = np.ascontiguousarray(keys, np.int32); out = np.zeros(len(k), np.int32)

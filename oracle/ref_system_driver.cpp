@@ -359,6 +359,13 @@ void sys_unordered_map_order(int64_t reserve_n, int64_t n, const int32_t* keys, 
   for (const auto& kv : m) out[k++] = kv.first;
 }
 
+// bucket_count() of a std::unordered_map<int,int> after reserve(n): the library's own answer
+uint64_t sys_bucket_count_after_reserve(uint64_t n) {
+  std::unordered_map<int, int> m;
+  m.reserve((size_t)n);
+  return (uint64_t)m.bucket_count();
+}
+
 // optimizeCameraPoses (:1409-1660) with the problem it builds recorded and handed to `cb` in place of ceres::Solve; after `cb` returns the
 // reference's own code reads the parameter blocks back (:1651-1667).  Returns the number of residual blocks recorded.
 int64_t sys_optimize_camera_poses(void* h, void (*cb)(void*), void* user) {

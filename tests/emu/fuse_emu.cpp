@@ -41,3 +41,10 @@ extern "C" void fuse_emu_export(long long* obs_ptr, int* obs_img, int* obs_kp, u
     source[i] = t.source; mean[i] = t.mean; seed[i] = t.seed;
   }
 }
+
+// stl_bucket_count of fuse_pipeline.h on its own (tests/test_ref_system_pin.py holds it against the real container's bucket_count())
+extern "C" unsigned emu_stl_bucket_count(unsigned n) {
+  int np = 0;
+  const uint32_t* pr = fuse::stl_prime_table(&np);
+  return fuse::stl_bucket_count(n, pr, np);
+}

@@ -587,3 +587,22 @@ def test_lidar_half_live_without_the_window_stage():
         vp, pi, cl, _ = vox.voxelize(scans, x, vs_, er)
         x, _ = lo.damping_iter(vp, pi, cl, x)
     assert np.abs(out - x).max() <= 1e-9 and np.abs(out - noisy).max() > 1e-3
+
+
+@needs_ref
+def test_bucket_count_table_equals_the_real_container(tmp_path_factory):
+    """stl_bucket_count (csrc/fuse_pipeline.h) and the table of oracle/fuse_oracle.py against std::unordered_map::reserve(n) / bucket_count() of the
+    library the reference is compiled with: every n up to 300, then every table entry below 3e6 and its two neighbours."""
+    import ctypes
+    import subprocess
+    so = tmp_path_factory.mktemp("emu_bkt") / "libfuse_emu.so"
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", str(ROOT / "tests" / "emu" / "fuse_emu.cpp"), "-o", str(so)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = ctypes.CDLL(str(so)); lib.emu_stl_bucket_count.restype = ctypes.c_uint
+    ns = list(range(0, 300)) + [p + d for p in fo._PRIMES if p < 3_000_000 for d in (-1, 0, 1)]
+    for n in ns:
+        real = sr.bucket_count_after_reserve(n)
+        assert lib.emu_stl_bucket_count(ctypes.c_uint(n)) == real, n
+        if n >= 14:
+            assert next(p for p in fo._PRIMES if p >= n) == real, n
