@@ -362,8 +362,8 @@ def test_reference_reader_reads_the_database_the_dataset_writer_writes():
 # ------------------------------------------------------------------------------------------------ N4: the dataset loader
 @needs_ref
 def test_reference_loader_reads_the_dataset_the_dataset_writer_writes():
-    """DatasetIO's constructor (src/dataset_io.cpp, run from its own source; PCD files through the stand-in reader of oracle/ref_shim/pcl/io/pcd_io.h,
-    which has no LZF: the compressed scans of the writer are rewritten uncompressed) on the directory oracle/dataset_writer.py lays out — the layout
+    """DatasetIO's constructor (src/dataset_io.cpp, run from its own source; PCD files through the stand-in reader of oracle/ref_shim/pcl/io/pcd_io.h)
+    on the directory oracle/dataset_writer.py lays out — the layout
     tests/test_dataset_loader.py holds the product's loader (global-lvba_b200/host/lvba_dataset.hpp) against.  Pins: frame timestamps come from the
     file NAMES (:228-233), TUM lines with a comment, an empty and an unparsable line and un-normalised quaternions (:137-180), images = every
     image_sample_step-th file by timestamp and the same stride over the VALID pose lines (:118-121, :159), intrinsics scaled by cam_model/scale (:59-62),
@@ -372,10 +372,7 @@ def test_reference_loader_reads_the_dataset_the_dataset_writer_writes():
     root = Path(tempfile.mkdtemp())
     scans, poses = synth.make_scan_scene(3, W=7, n_per_scan=900)
     scans[4] = scans[4][:0]                                              # an empty scan file
-    ts = dw.write_lidar_dataset(root, scans, poses)
-    for i in range(len(scans)):
-        if i % 3 == 2:
-            dw.write_pcd(root / "all_pcd_body" / f"{ts[i]:.6f}.pcd", scans[i], np.arange(len(scans[i])) % 7, "binary")
+    ts = dw.write_lidar_dataset(root, scans, poses)                       # binary, ascii and LZF-compressed PCD files in turn
     (root / "all_pcd_body" / "notes.txt").write_text("ignored")
     image_ts = [t + 0.013 for t in ts]
     image_poses = poses.copy(); image_poses[:, 9:] += np.random.default_rng(1).normal(0, 0.02, (7, 3))
@@ -530,9 +527,6 @@ def test_colmap_export_equals_the_reference_writer(pkg, tmp_path):
     from oracle import dataset_writer as dw
     data = tmp_path / "data"
     g = vs.make(data, seed=4, W=6, n_per_scan=6000, n_landmarks=60)
-    for i, t in enumerate(g["ts"]):                                        # the stand-in PCD reader under the reference has no LZF
-        if i % 3 == 2:
-            dw.write_pcd(data / "all_pcd_body" / f"{t:.6f}.pcd", g["scans"][i], np.arange(len(g["scans"][i])) % 7, "binary")
     # one more image 5 s after the last scan: no LiDAR within +-0.5 s -> the reference lists it neither in images.txt nor in the points (:1994-1997)
     image_ts = list(g["image_ts"]) + [g["image_ts"][-1] + 5.0]
     image_poses = np.vstack([g["image_poses"], g["image_poses"][-1:]])
