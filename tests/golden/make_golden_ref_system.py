@@ -138,16 +138,21 @@ def generate():
     o["P_options"] = rec["options"][:5]                       # [5] is std::thread::hardware_concurrency() of the machine
     o["P_window"] = np.int64(4); o["P_anchor_leaf"] = np.float64(0.1); o["P_voxel"] = np.float64(0.5); o["P_ratio"] = np.array([0.08] * 4, np.float32)
     # ---------------------------------------------------------------- V: the whole camera half, end to end, on the scene of tests/test_zz_offline_gpu.py
-    # runVisualBAWithLidarAssist (:144-154) with LiDAR BA disabled: grid -> camera poses -> depth -> the reference's own COLMAP reader -> track
+    # runVisualBAWithLidarAssist (:144-154) with LiDAR BA disabled: the reference's own dataset loader -> grid -> camera poses -> depth -> its own COLMAP reader -> track
     # fusion -> optimizeCameraPoses; where ceres::Solve stands, the restated Ceres loop (oracle/visual_oracle.py) solves the recorded problem and the
     # reference's own code writes the result back.  Only results are stored: the test rebuilds the (seeded) scene.
     from oracle import visual_oracle as vis
     rootv = Path(tempfile.mkdtemp())
     gv = vs.make(rootv, seed=3, W=8, n_landmarks=700)
-    S2 = sr.System()
-    S2.set_lidar(gv["scans"], gv["poses"], gv["ts"])
-    S2.set_stages(False, window_size=10, anchor_leaf=0.05, s2_voxel=0.5, s2_ratio=(0.3, 0.1, 0.06, 0.03))     # what write_config_yaml puts in config.yaml
-    S2.set_camera(gv["width"], gv["height"], gv["intr"], vs.RCL.ravel(), vs.PCL, np.eye(3).ravel(), np.zeros(3), np.array(gv["image_ts"]), gv["image_poses"])
+    F = vs.INTR_FULL                                          # the reference's own loader reads the directory (src/dataset_io.cpp): what config.yaml says, as ROS parameters
+    S2 = sr.System({"data_config/data_path": str(rootv) + "/", "data_config/colmap_db_path": "Colmap/colmap.db", "data_config/image_sample_step": 2,
+                    "cam_model/cam_width": vs.WIDTH_FULL, "cam_model/cam_height": vs.HEIGHT_FULL, "cam_model/scale": vs.SCALE, "cam_model/cam_fx": F[0],
+                    "cam_model/cam_fy": F[1], "cam_model/cam_cx": F[2], "cam_model/cam_cy": F[3], "cam_model/cam_d0": F[4], "cam_model/cam_d1": F[5],
+                    "cam_model/cam_d2": F[6], "cam_model/cam_d3": F[7], "extrin_calib/Rcl": vs.RCL.ravel(), "extrin_calib/Pcl": vs.PCL,
+                    "extrin_calib/extrinsic_R": np.eye(3).ravel(), "extrin_calib/extrinsic_T": np.zeros(3),
+                    "window_ba/enable": 0, "window_ba/size": 10, "window_ba/anchor_leaf_size": 0.05, "BALM_stage2/root_voxel_size": 0.5})
+    dsv = S2.init_from_dataset()
+    assert len(dsv["frame_ts"]) == 8 and len(dsv["image_ts"]) == 8
     S2.build_grid(); S2.update_camera_poses()
     _, c0v, c1v = S2.generate_depth()
     ok, _, _, _ = S2.load_colmap_db(str(rootv) + "/", rootv / "Colmap" / "colmap.db")
